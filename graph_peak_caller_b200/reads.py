@@ -1,0 +1,198 @@
+"""Reads as a structure of arrays, plus the small obg-style value types
+(``Position``, ``Interval``) that the reference API hands around.
+
+The reference consumes an iterable of ``offsetbasedgraph.Interval`` objects
+and looks at three things per read: ``region_paths`` (signed node ids, all
+negative for a reverse-strand read), ``start_position`` and ``end_position``
+(reference sample/sparsegraphpileup.py:47-92, control/linearmap.py:62-74).
+``ReadBatch`` stores exactly that for all reads at once:
+
+    start_node[R] int32 (signed id)   start_off[R] int32
+    end_node[R]   int32 (signed id)   end_off[R]   int32
+    path_ptr[R+1] int64               path[sum P]  int32 (signed ids)
+
+Iterating a ``ReadBatch`` yields ``Interval`` views, so code written against
+the reference's iterable-of-intervals contract keeps working, but the product
+path never does that: it uploads the arrays as they are.
+"""
+import json
+
+import numpy as np
+
+
+class Position:
+    __slots__ = ("region_path_id", "offset")
+
+    def __init__(self, region_path_id, offset):
+        self.region_path_id = int(region_path_id)
+        self.offset = int(offset)
+
+    def __eq__(self, other):
+        return (self.region_path_id == other.region_path_id
+                and self.offset == other.offset)
+
+    def __hash__(self):
+        return hash((self.region_path_id, self.offset))
+
+    def __repr__(self):
+        return "%d:%d" % (self.region_path_id, self.offset)
+
+
+class Interval:
+    """obg ``Interval``/``DirectedInterval`` (value type only)."""
+
+    def __init__(self, start_position, end_position, region_paths=None,
+                 graph=None, direction=None):
+        if region_paths is None:
+            region_paths = [start_position.region_path_id]
+            if end_position.region_path_id != region_paths[0]:
+                region_paths.append(end_position.region_path_id)
+        region_paths = [int(r) for r in region_paths]
+        if not isinstance(start_position, Position):
+            start_position = Position(region_paths[0], start_position)
+        if not isinstance(end_position, Position):
+            end_position = Position(region_paths[-1], end_position)
+        self.start_position = start_position
+        self.end_position = end_position
+        self.region_paths = region_paths
+        self.graph = graph
+        self.direction = 1 if direction is None else direction
+
+    def length(self):
+        g = self.graph
+        total = sum(g.node_size(rp) for rp in self.region_paths)
+        return int(total - self.start_position.offset
+                   - (g.node_size(self.region_paths[-1]) - self.end_position.offset))
+
+    def get_reverse(self):
+        g = self.graph
+        sp, ep = self.start_position, self.end_position
+        return self.__class__(
+            Position(-ep.region_path_id, g.node_size(ep.region_path_id) - ep.offset),
+            Position(-sp.region_path_id, g.node_size(sp.region_path_id) - sp.offset),
+            [-rp for rp in reversed(self.region_paths)], graph=g)
+
+    def get_subinterval(self, start_offset, end_offset):
+        g = self.graph
+        walked = -self.start_position.offset
+        start = end = None
+        rps = []
+        for rp in self.region_paths:
+            size = g.node_size(rp)
+            if start is None and walked + size > start_offset:
+                start = Position(rp, start_offset - walked)
+            if start is not None:
+                rps.append(rp)
+            if walked + size >= end_offset:
+                end = Position(rp, end_offset - walked)
+                break
+            walked += size
+        if start is None or end is None:
+            raise ValueError("sub-interval outside interval")
+        return Interval(start, end, rps, graph=g)
+
+    def hash(self, ignore_end_pos=False):
+        if ignore_end_pos:
+            return hash(self.start_position)
+        return hash((self.start_position, self.end_position,
+                     tuple(self.region_paths)))
+
+    def __eq__(self, other):
+        return (self.start_position == other.start_position
+                and self.end_position == other.end_position
+                and list(self.region_paths) == list(other.region_paths))
+
+    def __hash__(self):
+        return self.hash()
+
+    def __repr__(self):
+        return "Interval(%r, %r, %r)" % (self.start_position, self.end_position,
+                                         self.region_paths)
+
+    def to_file_line(self):
+        return json.dumps({"start": self.start_position.offset,
+                           "end": self.end_position.offset,
+                           "region_paths": self.region_paths,
+                           "direction": int(self.direction)})
+
+    @classmethod
+    def from_file_line(cls, line, graph=None):
+        o = json.loads(line)
+        return cls(o["start"], o["end"], o["region_paths"],
+                   direction=o.get("direction"), graph=graph)
+
+
+DirectedInterval = Interval
+
+
+class ReadBatch:
+    """All reads of one chromosome as flat arrays (host side, numpy)."""
+
+    def __init__(self, start_node, start_off, end_node, end_off, path_ptr, path):
+        self.start_node = np.ascontiguousarray(start_node, dtype=np.int32)
+        self.start_off = np.ascontiguousarray(start_off, dtype=np.int32)
+        self.end_node = np.ascontiguousarray(end_node, dtype=np.int32)
+        self.end_off = np.ascontiguousarray(end_off, dtype=np.int32)
+        self.path_ptr = np.ascontiguousarray(path_ptr, dtype=np.int64)
+        self.path = np.ascontiguousarray(path, dtype=np.int32)
+        n = self.start_node.size
+        if not (self.start_off.size == n == self.end_node.size == self.end_off.size
+                and self.path_ptr.size == n + 1
+                and (n == 0 or self.path_ptr[-1] == self.path.size)):
+            raise ValueError("inconsistent read arrays")
+        self._device = None
+
+    def __len__(self):
+        return int(self.start_node.size)
+
+    @classmethod
+    def from_intervals(cls, intervals):
+        """Flatten any iterable of obg-style intervals (host loop: ingest,
+        not the measured path)."""
+        sn, so, en, eo, ptr, path = [], [], [], [], [0], []
+        for iv in intervals:
+            sn.append(iv.start_position.region_path_id)
+            so.append(iv.start_position.offset)
+            en.append(iv.end_position.region_path_id)
+            eo.append(iv.end_position.offset)
+            path.extend(int(r) for r in iv.region_paths)
+            ptr.append(len(path))
+        return cls(sn, so, en, eo, ptr, path)
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self.interval(i)
+
+    def interval(self, i, graph=None):
+        lo, hi = self.path_ptr[i], self.path_ptr[i + 1]
+        return Interval(Position(self.start_node[i], self.start_off[i]),
+                        Position(self.end_node[i], self.end_off[i]),
+                        self.path[lo:hi].tolist(), graph=graph)
+
+    def select(self, keep):
+        """Sub-batch of the reads whose index is in / mask is set in ``keep``."""
+        keep = np.asarray(keep)
+        idx = np.flatnonzero(keep) if keep.dtype == bool else keep.astype(np.int64)
+        lens = np.diff(self.path_ptr)[idx]
+        ptr = np.r_[0, np.cumsum(lens)].astype(np.int64)
+        gather = (np.repeat(self.path_ptr[:-1][idx] - ptr[:-1], lens)
+                  + np.arange(ptr[-1]))
+        return ReadBatch(self.start_node[idx], self.start_off[idx],
+                         self.end_node[idx], self.end_off[idx], ptr,
+                         self.path[gather])
+
+    def nbytes(self):
+        return sum(a.nbytes for a in (self.start_node, self.start_off,
+                                      self.end_node, self.end_off,
+                                      self.path_ptr, self.path))
+
+    def to_file(self, file_name):
+        np.savez(file_name, start_node=self.start_node, start_off=self.start_off,
+                 end_node=self.end_node, end_off=self.end_off,
+                 path_ptr=self.path_ptr, path=self.path)
+
+    @classmethod
+    def from_file(cls, file_name):
+        o = np.load(file_name)
+        return cls(o["start_node"], o["start_off"], o["end_node"], o["end_off"],
+                   o["path_ptr"], o["path"])
