@@ -1,0 +1,170 @@
+// Shared device/host helpers for the sm_100a callpeaks kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gpc_b200.h"
+
+namespace gpc {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define GPC_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) {                                              \
+            gpc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,       \
+                           cudaGetErrorString(e__));                           \
+            return GPC_ERR_CUDA;                                               \
+        }                                                                      \
+    } while (0)
+
+#define GPC_TRY(call)                                                          \
+    do {                                                                       \
+        int s__ = (call);                                                      \
+        if (s__ != GPC_OK) return s__;                                         \
+    } while (0)
+
+#define GPC_LAUNCH_CHECK() GPC_CUDA(cudaGetLastError())
+
+// Stream-ordered scratch that frees itself (cudaMallocAsync pool).
+struct Scratch {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    Scratch() {}
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    ~Scratch() { release(); }
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        release();
+        s = stream;
+        if (bytes == 0) bytes = 16;
+        return cudaMallocAsync(&p, bytes, stream);
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+int sm_count();
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- warp / block primitives ------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_sum(T v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(FULL, v, d);
+        if (lane_id() >= (unsigned)d) v += o;
+    }
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+// Block-wide exclusive sum.  `smem` needs 33 T's.  Returns the exclusive
+// prefix of `v` for this thread; `total` receives the block sum.  Contains
+// __syncthreads, so every thread of the block must call it.
+template <typename T>
+__device__ __forceinline__ T block_excl_sum(T v, T* smem, T& total) {
+    T incl = warp_incl_sum(v);
+    unsigned w = warp_id(), l = lane_id();
+    unsigned nw = (blockDim.x + 31) >> 5;
+    if (l == 31) smem[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        T x = (l < nw) ? smem[l] : T(0);
+        T xi = warp_incl_sum(x);
+        smem[l] = xi - x;
+        if (l == 31) smem[32] = xi;
+    }
+    __syncthreads();
+    T base = smem[w];
+    total = smem[32];
+    __syncthreads();
+    return base + incl - v;
+}
+
+// ---- chained scan (decoupled look-back) over tiles --------------------------
+// One 64-bit word per tile: status in the top 2 bits, 62-bit payload below.
+// Tiles must be claimed in launch order (atomic ticket) so a tile only ever
+// waits on tiles that are already running.
+constexpr unsigned long long LB_EMPTY = 0ull;
+constexpr unsigned long long LB_AGG = 1ull << 62;
+constexpr unsigned long long LB_PREFIX = 2ull << 62;
+constexpr unsigned long long LB_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long long v) {
+    *reinterpret_cast<volatile unsigned long long*>(p) = v;
+}
+
+// Called by ONE thread of the tile.  Publishes `agg` (< 2^62), walks back and
+// returns the exclusive prefix (sum of the aggregates of all earlier tiles),
+// then publishes the inclusive prefix.
+__device__ __forceinline__ unsigned long long lookback_excl(unsigned long long* status,
+                                                            unsigned tile,
+                                                            unsigned long long agg) {
+    if (tile == 0) {
+        lb_store(&status[0], LB_PREFIX | agg);
+        return 0;
+    }
+    lb_store(&status[tile], LB_AGG | agg);
+    unsigned long long excl = 0;
+    int t = (int)tile - 1;
+    while (true) {
+        unsigned long long s = lb_load(&status[t]);
+        unsigned long long st = s & ~LB_MASK;
+        if (st == LB_EMPTY) continue;
+        excl += s & LB_MASK;
+        if (st == LB_PREFIX) break;
+        --t;
+    }
+    lb_store(&status[tile], LB_PREFIX | (excl + agg));
+    return excl;
+}
+
+__device__ __forceinline__ uint4 node_record(const gpc_graph_t& g, uint32_t v) {
+    return __ldg(reinterpret_cast<const uint4*>(g.node_rec) + v);
+}
+
+// Order-preserving maps between IEEE doubles and unsigned 64-bit keys.
+__host__ __device__ __forceinline__ unsigned long long f64_to_key(double d) {
+    unsigned long long u;
+#ifdef __CUDA_ARCH__
+    u = (unsigned long long)__double_as_longlong(d);
+#else
+    memcpy(&u, &d, 8);
+#endif
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double key_to_f64(unsigned long long k) {
+    unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)u);
+#else
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
+#endif
+}
+
+}  // namespace gpc

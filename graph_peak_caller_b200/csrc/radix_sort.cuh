@@ -1,0 +1,231 @@
+// LSD radix sort, 8-bit digits, "onesweep" structure:
+//   1. one histogram kernel counts every digit of every pass in a single read
+//      of the keys;
+//   2. per pass, one scatter kernel: each 4096-key tile ranks its keys with
+//      warp match_any (stable), publishes its 256 digit counts through a
+//      chained scan (decoupled look-back) and writes its keys out grouped by
+//      digit, staged through shared memory so that stores are coalesced runs.
+// Traffic per pass: keys read once, written once (+1 KB of tile status).
+// Passes whose digit is the same for every key are skipped (64-bit keys).
+#pragma once
+#include "common.cuh"
+
+namespace gpc {
+
+constexpr int RS_BITS = 8;
+constexpr int RS_RADIX = 1 << RS_BITS;
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+template <typename KeyT> struct RsTraits;
+template <> struct RsTraits<uint32_t> { static constexpr int ITEMS = 16; static constexpr int MAX_PASSES = 4; };
+template <> struct RsTraits<unsigned long long> { static constexpr int ITEMS = 8; static constexpr int MAX_PASSES = 8; };
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const KeyT* __restrict__ keys, size_t n, int begin_bit, int n_passes,
+               unsigned* __restrict__ hist /* [n_passes][256] */) {
+    __shared__ unsigned sh[RsTraits<KeyT>::MAX_PASSES * RS_RADIX];
+    for (int i = threadIdx.x; i < n_passes * RS_RADIX; i += RS_THREADS) sh[i] = 0;
+    __syncthreads();
+    size_t stride = (size_t)gridDim.x * RS_THREADS;
+    for (size_t i = (size_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += stride) {
+        KeyT k = keys[i];
+        for (int p = 0; p < n_passes; ++p) {
+            unsigned d = (unsigned)(k >> (begin_bit + p * RS_BITS)) & (RS_RADIX - 1);
+            atomicAdd(&sh[p * RS_RADIX + d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_passes * RS_RADIX; i += RS_THREADS) {
+        unsigned v = sh[i];
+        if (v) atomicAdd(&hist[i], v);
+    }
+}
+
+// One block per pass: exclusive scan of its 256 counts (in place) and a flag
+// telling whether one digit holds every key (pass can be skipped).
+static __global__ void __launch_bounds__(RS_RADIX)
+rs_scan_hist_kernel(unsigned* __restrict__ hist, unsigned n, unsigned* __restrict__ trivial) {
+    __shared__ unsigned sm[33];
+    unsigned* h = hist + blockIdx.x * RS_RADIX;
+    unsigned v = h[threadIdx.x];
+    if (v == n && n > 0) trivial[blockIdx.x] = 1;
+    unsigned total;
+    unsigned ex = block_excl_sum<unsigned>(v, sm, total);
+    h[threadIdx.x] = ex;
+}
+
+constexpr unsigned RS_ST_AGG = 1u << 30;
+constexpr unsigned RS_ST_PREFIX = 2u << 30;
+constexpr unsigned RS_ST_MASK = (1u << 30) - 1;
+
+template <typename KeyT, bool HAS_VALUE>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
+                   const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
+                   unsigned n, int shift, const unsigned* __restrict__ digit_base,
+                   unsigned* __restrict__ status /* [tiles][256], zeroed */,
+                   unsigned* __restrict__ ticket /* zeroed */) {
+    constexpr int ITEMS = RsTraits<KeyT>::ITEMS;
+    constexpr int TILE = RS_THREADS * ITEMS;
+    __shared__ unsigned warp_hist[RS_WARPS][RS_RADIX];
+    __shared__ unsigned digit_start[RS_RADIX];   // exclusive offsets inside the tile
+    __shared__ unsigned out_base[RS_RADIX];      // global index of tile-sorted slot 0 of digit d
+    __shared__ KeyT s_keys[TILE];
+    __shared__ uint32_t s_vals[HAS_VALUE ? TILE : 1];
+    __shared__ unsigned s_scan[33];
+    __shared__ unsigned s_tile;
+
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS)
+        (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const unsigned tile_base = tile * TILE;
+    const unsigned count = min((unsigned)TILE, n - tile_base);
+    const unsigned w = warp_id(), l = lane_id();
+    const unsigned warp_base = w * (ITEMS * 32);
+
+    KeyT key[ITEMS];
+    unsigned short rank[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        unsigned idx = warp_base + j * 32 + l;
+        key[j] = (idx < count) ? keys_in[tile_base + idx] : ~KeyT(0);
+    }
+    // stable ranking: items in (j, lane) order == memory order inside the warp chunk
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        unsigned d = (unsigned)(key[j] >> shift) & (RS_RADIX - 1);
+        unsigned peers = __match_any_sync(FULL, d);
+        unsigned leader = __ffs(peers) - 1;
+        unsigned before = __popc(peers & ((1u << l) - 1));
+        unsigned old = 0;
+        if (l == leader) {
+            old = warp_hist[w][d];
+            warp_hist[w][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(FULL, old, leader);
+        rank[j] = (unsigned short)(old + before);
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive scan over the warps, tile count
+    const unsigned d = threadIdx.x;   // RS_THREADS == RS_RADIX
+    unsigned tot = 0;
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ++ww) {
+        unsigned t = warp_hist[ww][d];
+        warp_hist[ww][d] = tot;
+        tot += t;
+    }
+    unsigned tile_total;
+    unsigned dstart = block_excl_sum<unsigned>(tot, s_scan, tile_total);
+    digit_start[d] = dstart;
+    // chained scan for digit d over the tiles
+    unsigned excl = 0;
+    {
+        volatile unsigned* st = status;
+        if (tile == 0) {
+            st[d] = RS_ST_PREFIX | tot;
+        } else {
+            st[tile * RS_RADIX + d] = RS_ST_AGG | tot;
+            int t = (int)tile - 1;
+            while (true) {
+                unsigned s = st[t * RS_RADIX + d];
+                unsigned flag = s & ~RS_ST_MASK;
+                if (flag == 0) continue;
+                excl += s & RS_ST_MASK;
+                if (flag == RS_ST_PREFIX) break;
+                --t;
+            }
+            st[tile * RS_RADIX + d] = RS_ST_PREFIX | (excl + tot);
+        }
+    }
+    out_base[d] = digit_base[d] + excl - dstart;
+    __syncthreads();
+    // tile-local sorted position of every key
+    unsigned pos[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        unsigned dd = (unsigned)(key[j] >> shift) & (RS_RADIX - 1);
+        pos[j] = digit_start[dd] + warp_hist[w][dd] + rank[j];
+        s_keys[pos[j]] = key[j];
+    }
+    if (HAS_VALUE) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            unsigned idx = warp_base + j * 32 + l;
+            if (idx < count) s_vals[pos[j]] = vals_in[tile_base + idx];
+        }
+    }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < count; i += RS_THREADS) {
+        KeyT k = s_keys[i];
+        unsigned dd = (unsigned)(k >> shift) & (RS_RADIX - 1);
+        unsigned dst = out_base[dd] + i;
+        keys_out[dst] = k;
+        if (HAS_VALUE) vals_out[dst] = s_vals[i];
+    }
+}
+
+// Host driver.  Sorts bits [begin_bit, end_bit) of `keys` (n < 2^30).
+// `keys`/`vals` and `keys_tmp`/`vals_tmp` ping-pong; *result_in_tmp says where
+// the sorted data ended up.  `skip_trivial` costs one 32-byte D2H read.
+template <typename KeyT, bool HAS_VALUE>
+int radix_sort(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, size_t n,
+               int begin_bit, int end_bit, bool skip_trivial, bool* result_in_tmp,
+               cudaStream_t stream) {
+    *result_in_tmp = false;
+    if (n <= 1) return GPC_OK;
+    if (n >= (1ull << 30)) {
+        set_error("radix_sort: %zu keys exceed the 2^30 limit", n);
+        return GPC_ERR_ARG;
+    }
+    constexpr int TILE = RS_THREADS * RsTraits<KeyT>::ITEMS;
+    const int n_passes = (end_bit - begin_bit + RS_BITS - 1) / RS_BITS;
+    if (n_passes <= 0) return GPC_OK;
+    if (n_passes > RsTraits<KeyT>::MAX_PASSES) {
+        set_error("radix_sort: too many passes");
+        return GPC_ERR_ARG;
+    }
+    const unsigned tiles = div_up(n, TILE);
+    // scratch: hist[n_passes*256] | trivial[8] | ticket[8] | status[tiles*256] per pass
+    size_t head = (size_t)n_passes * RS_RADIX + 16;
+    size_t per_pass = (size_t)tiles * RS_RADIX;
+    Scratch sc;
+    GPC_CUDA(sc.alloc((head + per_pass * n_passes) * sizeof(unsigned), stream));
+    unsigned* hist = sc.as<unsigned>();
+    unsigned* trivial = hist + (size_t)n_passes * RS_RADIX;
+    unsigned* ticket = trivial + 8;
+    unsigned* status = hist + head;
+    GPC_CUDA(cudaMemsetAsync(sc.p, 0, (head + per_pass * n_passes) * sizeof(unsigned), stream));
+    unsigned hist_blocks = min(div_up(n, RS_THREADS * 8), (unsigned)(sm_count() * 8));
+    rs_hist_kernel<KeyT><<<hist_blocks, RS_THREADS, 0, stream>>>(keys, n, begin_bit, n_passes, hist);
+    GPC_LAUNCH_CHECK();
+    rs_scan_hist_kernel<<<n_passes, RS_RADIX, 0, stream>>>(hist, (unsigned)n, trivial);
+    GPC_LAUNCH_CHECK();
+    unsigned h_trivial[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (skip_trivial) {
+        GPC_CUDA(cudaMemcpyAsync(h_trivial, trivial, sizeof(h_trivial), cudaMemcpyDeviceToHost, stream));
+        GPC_CUDA(cudaStreamSynchronize(stream));
+    }
+    bool in_tmp = false;
+    for (int p = 0; p < n_passes; ++p) {
+        if (h_trivial[p]) continue;
+        const KeyT* kin = in_tmp ? keys_tmp : keys;
+        KeyT* kout = in_tmp ? keys : keys_tmp;
+        const uint32_t* vin = in_tmp ? vals_tmp : vals;
+        uint32_t* vout = in_tmp ? vals : vals_tmp;
+        rs_onesweep_kernel<KeyT, HAS_VALUE><<<tiles, RS_THREADS, 0, stream>>>(
+            kin, kout, vin, vout, (unsigned)n, begin_bit + p * RS_BITS,
+            hist + (size_t)p * RS_RADIX, status + per_pass * p, ticket + p);
+        GPC_LAUNCH_CHECK();
+        in_tmp = !in_tmp;
+    }
+    *result_in_tmp = in_tmp;
+    return GPC_OK;
+}
+
+}  // namespace gpc

@@ -1,0 +1,551 @@
+// Sample (ChIP) pileup on sm_100a.
+//
+// Replaces, for the whole read set at once, the reference's
+//   ReadsAdderWDirect.add_reads        sample/sparsegraphpileup.py:37-119
+//   SparseExtender.run_linear          sample/sparsegraphpileup.py:151-184
+//   ReverseSparseExtender              sample/sparsegraphpileup.py:190-211
+//   SparseDiffs.from_pileup + get_sparse_values   sparsediffs.py:137-141,180-190
+//   UniqueIntervals                    intervals.py:17-33
+//
+// The reference sweeps the nodes in topological order with a
+// {read id -> remaining} dict per node.  Here every read is walked on its own:
+// its body pieces, then a small frontier {node -> max remaining} popped in id
+// (= topological) order; contiguous pieces are merged before they are emitted
+// as packed +1/-1 events.  One event stream feeds both the fragment pileup and
+// the direct (reads only) pileup; one radix sort and one chained scan turn it
+// into the two canonical run-length tracks.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gpc {
+
+// event key = position << 3 | tag << 1 | (delta is -1)
+constexpr unsigned TAG_BOTH = 0, TAG_DIRECT = 1, TAG_FRAG = 2;
+constexpr int EVENT_POS_SHIFT = 3;
+
+constexpr int WALK_THREADS = 256;
+constexpr int WALK_STAGE = 3072;     // staged events per block (12 KB)
+constexpr int FRONTIER_CAP = 32;
+
+struct Emitter {
+    uint32_t* s_buf;
+    unsigned* s_count;
+    uint32_t* g_events;
+    unsigned long long* g_count;
+    unsigned long long g_cap;
+    uint32_t G;
+    bool fwd;
+
+    // +1 (open) or -1 (close) at oriented position p
+    __device__ __forceinline__ void emit(uint32_t p, bool close, unsigned tag) {
+        uint32_t pos = fwd ? p : (G - p);
+        bool minus = fwd ? close : !close;
+        uint32_t key = (pos << EVENT_POS_SHIFT) | (tag << 1) | (minus ? 1u : 0u);
+        cg::coalesced_group g = cg::coalesced_threads();
+        unsigned base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(s_count, g.size());
+        base = g.shfl(base, 0);
+        unsigned slot = base + g.thread_rank();
+        if (slot < WALK_STAGE) {
+            s_buf[slot] = key;
+        } else {   // staging full: append straight to the global stream
+            unsigned long long at = atomicAdd(g_count, 1ull);
+            if (at < g_cap) g_events[at] = key;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(WALK_THREADS)
+walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restrict__ read_index,
+                  unsigned n_reads, int extension, uint32_t* __restrict__ events,
+                  unsigned long long event_cap, unsigned long long* __restrict__ event_count,
+                  uint8_t* __restrict__ touched, int* __restrict__ err) {
+    __shared__ uint32_t s_buf[WALK_STAGE];
+    __shared__ unsigned s_count;
+    __shared__ unsigned long long s_gbase;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+
+    const unsigned i = blockIdx.x * WALK_THREADS + threadIdx.x;
+    if (i < n_reads) {
+        const unsigned r = read_index ? read_index[i] : i;
+        const int sn = reads.start_node[r], en = reads.end_node[r];
+        const int so = reads.start_off[r], eo = reads.end_off[r];
+        const long long p0 = reads.path_ptr[r], p1 = reads.path_ptr[r + 1];
+        const bool fwd = sn > 0;
+        const uint32_t n = graph.n_nodes, G = graph.size_bp;
+        const int mn = graph.min_node;
+        bool ok = (p1 > p0) && ((en > 0) == fwd) && so >= 0 && eo >= 0;
+        if (ok) {
+            for (long long q = p0; q < p1; ++q) {
+                int id = reads.path[q];
+                long long v = (long long)(id < 0 ? -id : id) - mn;
+                if ((id > 0) != fwd || v < 0 || v >= (long long)n) ok = false;
+            }
+        }
+        if (!ok) {
+            atomicExch(err, GPC_ERR_INVALID_INTERVAL);
+        } else {
+            Emitter em{s_buf, &s_count, events, event_count, event_cap, G, fwd};
+            // ---- read body --------------------------------------------------
+            uint32_t ce = 0;          // oriented end of the currently open interval
+            uint32_t last_len = 0, last_start = 0;
+            uint32_t last_v = 0;
+            const int k = (int)(p1 - p0);
+            for (int j = 0; j < k; ++j) {
+                int id = reads.path[p0 + j];
+                uint32_t v = (uint32_t)((id < 0 ? -id : id) - mn);
+                uint4 rec = node_record(graph, v);
+                uint32_t len = rec.w;
+                uint32_t ns = fwd ? rec.x : (G - rec.x - len);
+                uint32_t ps = (j == 0) ? ns + (uint32_t)so : ns;
+                touched[v] = 1;
+                if (j == 0) {
+                    em.emit(ps, false, TAG_BOTH);
+                } else if (ps != ce) {
+                    em.emit(ce, true, TAG_BOTH);
+                    em.emit(ps, false, TAG_BOTH);
+                }
+                ce = ns + len;
+                last_len = len; last_start = ns; last_v = v;
+            }
+            // ---- read end: direct pileup closes here, fragment goes on ------
+            em.emit(last_start + (uint32_t)eo, true, TAG_DIRECT);
+            uint32_t total = (uint32_t)eo + (uint32_t)extension;
+            ce = last_start + min(total, last_len);
+            // ---- extension frontier ----------------------------------------
+            uint32_t fkey[FRONTIER_CAP];
+            uint32_t frem[FRONTIER_CAP];
+            int fc = 0;
+            bool overflow = false;
+            uint32_t cur_v = last_v;
+            uint32_t carry = total > last_len ? total - last_len : 0;
+            while (true) {
+                if (carry) {
+                    uint4 a = node_record(graph, cur_v);
+                    uint4 b = node_record(graph, cur_v + 1);
+                    uint32_t lo = fwd ? a.y : a.z, hi = fwd ? b.y : b.z;
+                    const uint32_t* adj = fwd ? graph.succ : graph.pred;
+                    for (uint32_t e = lo; e < hi; ++e) {
+                        uint32_t wv = adj[e];
+                        uint32_t key = fwd ? wv : ~wv;
+                        int f = 0;
+                        for (; f < fc; ++f) if (fkey[f] == key) break;
+                        if (f < fc) {
+                            frem[f] = max(frem[f], carry);
+                        } else if (fc < FRONTIER_CAP) {
+                            fkey[fc] = key; frem[fc] = carry; ++fc;
+                        } else {
+                            overflow = true;
+                        }
+                    }
+                }
+                if (fc == 0) break;
+                int best = 0;
+                for (int f = 1; f < fc; ++f) if (fkey[f] < fkey[best]) best = f;
+                uint32_t key = fkey[best], rem = frem[best];
+                --fc;
+                fkey[best] = fkey[fc]; frem[best] = frem[fc];
+                cur_v = fwd ? key : ~key;
+                uint4 rec = node_record(graph, cur_v);
+                uint32_t len = rec.w;
+                uint32_t ns = fwd ? rec.x : (G - rec.x - len);
+                touched[cur_v] = 1;
+                if (ns != ce) {
+                    em.emit(ce, true, TAG_FRAG);
+                    em.emit(ns, false, TAG_FRAG);
+                }
+                ce = ns + min(rem, len);
+                carry = rem > len ? rem - len : 0;
+            }
+            em.emit(ce, true, TAG_FRAG);
+            if (overflow) atomicExch(err, GPC_ERR_FRONTIER_OVERFLOW);
+        }
+    }
+    __syncthreads();
+    const unsigned staged = min(s_count, (unsigned)WALK_STAGE);
+    if (threadIdx.x == 0) s_gbase = atomicAdd(event_count, (unsigned long long)staged);
+    __syncthreads();
+    const unsigned long long gb = s_gbase;
+    for (unsigned t = threadIdx.x; t < staged; t += WALK_THREADS)
+        if (gb + t < event_cap) events[gb + t] = s_buf[t];
+}
+
+// ---- events -> two canonical run-length tracks ------------------------------
+//
+// Input: event keys sorted ascending.  For each track (0 fragment, 1 direct):
+// delta of an event = +-1 if its tag belongs to the track, else 0.  An entry
+// (position, running sum) is written after the last event of every position
+// whose net delta is non-zero, plus always one entry at position 0 -- the
+// canonical SparseValues of the reference (sparsediffs.py:13-20).
+
+constexpr int RUN_THREADS = 256;
+constexpr int RUN_ITEMS = 8;
+constexpr int RUN_TILE = RUN_THREADS * RUN_ITEMS;
+
+struct RunAgg {              // tile aggregate for the first chained scan
+    int tot[2];              // sum of deltas
+    int seg[2];              // sum of deltas after the last position change in the tile
+    int has_head;            // tile contains a position change
+    int pad[3];
+};
+
+struct Seg { int head; int a, b; };
+__device__ __forceinline__ Seg seg_combine(const Seg& x, const Seg& y) {
+    if (y.head) return y;
+    return Seg{x.head, x.a + y.a, x.b + y.b};
+}
+
+__device__ __forceinline__ void event_delta(uint32_t key, int& dfrag, int& ddir) {
+    int s = (key & 1u) ? -1 : 1;
+    unsigned tag = (key >> 1) & 3u;
+    dfrag = (tag != TAG_DIRECT) ? s : 0;
+    ddir = (tag != TAG_FRAG) ? s : 0;
+}
+
+__global__ void __launch_bounds__(RUN_THREADS)
+events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
+                      uint32_t* __restrict__ frag_idx, int32_t* __restrict__ frag_val,
+                      uint32_t* __restrict__ dir_idx, int32_t* __restrict__ dir_val,
+                      RunAgg* __restrict__ aggs, RunAgg* __restrict__ prefixes,
+                      unsigned* __restrict__ st1 /* zeroed */,
+                      unsigned long long* __restrict__ st2 /* zeroed */,
+                      unsigned long long* __restrict__ st3 /* zeroed */,
+                      unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts) {
+    __shared__ unsigned s_slot;
+    __shared__ int s_scan[33];
+    __shared__ Seg s_seg[RUN_THREADS / 32];
+    __shared__ RunAgg s_carry;
+    __shared__ unsigned long long s_obase[2];
+    const unsigned tile = claim_tile(ticket, &s_slot);
+    const unsigned base = tile * RUN_TILE + threadIdx.x * RUN_ITEMS;
+
+    uint32_t key[RUN_ITEMS + 1];
+    bool valid[RUN_ITEMS];
+#pragma unroll
+    for (int j = 0; j <= RUN_ITEMS; ++j)
+        key[j] = (base + j < n) ? keys[base + j] : 0xffffffffu;
+    uint32_t prev_key = (base > 0 && base - 1 < n) ? keys[base - 1] : 0xffffffffu;
+
+    // thread-local pass: totals and the segmented (per position) partial sums
+    int tf = 0, td = 0;
+    Seg seg{0, 0, 0};
+    uint32_t ppos = prev_key >> EVENT_POS_SHIFT;
+#pragma unroll
+    for (int j = 0; j < RUN_ITEMS; ++j) {
+        valid[j] = base + j < n;
+        if (valid[j]) {
+            int df, dd;
+            event_delta(key[j], df, dd);
+            uint32_t pos = key[j] >> EVENT_POS_SHIFT;
+            bool head = (base + j == 0) || pos != ppos;
+            seg = seg_combine(seg, Seg{head ? 1 : 0, df, dd});
+            tf += df; td += dd;
+            ppos = pos;
+        }
+    }
+    // block scan of totals
+    int tile_f, tile_d;
+    int ex_f = block_excl_sum<int>(tf, s_scan, tile_f);
+    int ex_d = block_excl_sum<int>(td, s_scan, tile_d);
+    // block exclusive scan of the segmented operator
+    Seg incl = seg;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Seg o;
+        o.head = __shfl_up_sync(FULL, incl.head, d);
+        o.a = __shfl_up_sync(FULL, incl.a, d);
+        o.b = __shfl_up_sync(FULL, incl.b, d);
+        if (lane_id() >= (unsigned)d) incl = seg_combine(o, incl);
+    }
+    if (lane_id() == 31) s_seg[warp_id()] = incl;
+    __syncthreads();
+    Seg carry{0, 0, 0};      // everything before this thread inside the tile
+    for (unsigned w = 0; w < warp_id(); ++w) carry = seg_combine(carry, s_seg[w]);
+    {
+        Seg up;
+        up.head = __shfl_up_sync(FULL, incl.head, 1);
+        up.a = __shfl_up_sync(FULL, incl.a, 1);
+        up.b = __shfl_up_sync(FULL, incl.b, 1);
+        if (lane_id() > 0) carry = seg_combine(carry, up);
+    }
+    // tile aggregate -> first chained scan (totals + open-group partial sums)
+    if (threadIdx.x == RUN_THREADS - 1) {
+        Seg all = seg_combine(carry, seg);
+        RunAgg mine;
+        mine.tot[0] = tile_f; mine.tot[1] = tile_d;
+        mine.seg[0] = all.a; mine.seg[1] = all.b; mine.has_head = all.head;
+        RunAgg in;           // exclusive prefix over earlier tiles
+        in.tot[0] = in.tot[1] = in.seg[0] = in.seg[1] = in.has_head = 0;
+        volatile unsigned* vs = st1;
+        if (tile > 0) {
+            aggs[tile] = mine;
+            __threadfence();
+            vs[tile] = 1;
+            // walk back; `in` is built right-to-left
+            bool seg_closed = false;
+            int t = (int)tile - 1;
+            while (true) {
+                unsigned s = vs[t];
+                if (s == 0) continue;
+                __threadfence();
+                RunAgg a = (s == 2) ? prefixes[t] : aggs[t];
+                in.tot[0] += a.tot[0]; in.tot[1] += a.tot[1];
+                if (!seg_closed) {
+                    in.seg[0] += a.seg[0]; in.seg[1] += a.seg[1];
+                    if (a.has_head) seg_closed = true;
+                }
+                if (s == 2) break;
+                --t;
+            }
+        }
+        RunAgg pre;          // inclusive prefix = state after this tile
+        pre.tot[0] = in.tot[0] + mine.tot[0]; pre.tot[1] = in.tot[1] + mine.tot[1];
+        if (mine.has_head) { pre.seg[0] = mine.seg[0]; pre.seg[1] = mine.seg[1]; }
+        else { pre.seg[0] = in.seg[0] + mine.seg[0]; pre.seg[1] = in.seg[1] + mine.seg[1]; }
+        pre.has_head = 1;    // as a prefix the segment sums are complete
+        prefixes[tile] = pre;
+        __threadfence();
+        vs[tile] = 2;
+        s_carry = in;
+    }
+    __syncthreads();
+    const RunAgg tin = s_carry;
+    // second thread-local pass: decide emissions
+    int run_f = tin.tot[0] + ex_f, run_d = tin.tot[1] + ex_d;
+    Seg sg = carry.head ? carry : Seg{0, carry.a + tin.seg[0], carry.b + tin.seg[1]};
+    uint32_t e_idx[2][RUN_ITEMS];
+    int e_val[2][RUN_ITEMS];
+    int cnt[2] = {0, 0};
+    ppos = prev_key >> EVENT_POS_SHIFT;
+#pragma unroll
+    for (int j = 0; j < RUN_ITEMS; ++j) {
+        if (valid[j]) {
+            int df, dd;
+            event_delta(key[j], df, dd);
+            uint32_t pos = key[j] >> EVENT_POS_SHIFT;
+            bool head = (base + j == 0) || pos != ppos;
+            if (head) { sg.a = 0; sg.b = 0; }
+            sg.a += df; sg.b += dd;
+            run_f += df; run_d += dd;
+            bool last = (base + j + 1 >= n) || (key[j + 1] >> EVENT_POS_SHIFT) != pos;
+            if (last) {
+                if (sg.a != 0 || pos == 0) { e_idx[0][cnt[0]] = pos; e_val[0][cnt[0]] = run_f; ++cnt[0]; }
+                if (sg.b != 0 || pos == 0) { e_idx[1][cnt[1]] = pos; e_val[1][cnt[1]] = run_d; ++cnt[1]; }
+            }
+            ppos = pos;
+        }
+    }
+    // an entry at position 0 always exists: synthesise it when no event sits there
+    const bool synth = (tile == 0 && threadIdx.x == 0 && (key[0] >> EVENT_POS_SHIFT) != 0);
+    int c0 = cnt[0] + (synth ? 1 : 0), c1 = cnt[1] + (synth ? 1 : 0);
+    int tot0, tot1;
+    int o0 = block_excl_sum<int>(c0, s_scan, tot0);
+    int o1 = block_excl_sum<int>(c1, s_scan, tot1);
+    if (threadIdx.x == 0) {
+        s_obase[0] = lookback_excl(st2, tile, (unsigned long long)tot0);
+        s_obase[1] = lookback_excl(st3, tile, (unsigned long long)tot1);
+        if (tile == gridDim.x - 1) {
+            out_counts[0] = s_obase[0] + tot0;
+            out_counts[1] = s_obase[1] + tot1;
+        }
+    }
+    __syncthreads();
+    unsigned long long w0 = s_obase[0] + o0, w1 = s_obase[1] + o1;
+    if (synth) {
+        frag_idx[w0] = 0; frag_val[w0] = 0; ++w0;
+        dir_idx[w1] = 0; dir_val[w1] = 0; ++w1;
+    }
+#pragma unroll
+    for (int j = 0; j < RUN_ITEMS; ++j) {
+        if (j < cnt[0]) { frag_idx[w0 + j] = e_idx[0][j]; frag_val[w0 + j] = e_val[0][j]; }
+        if (j < cnt[1]) { dir_idx[w1 + j] = e_idx[1][j]; dir_val[w1 + j] = e_val[1][j]; }
+    }
+}
+
+// ---- duplicate filter (hash set keyed by start position) --------------------
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+constexpr unsigned long long DEDUP_EMPTY = ~0ull;
+
+// Pass 1: claim a slot for the key (start node, start offset) and keep the
+// smallest read index that carries it ("first read wins", intervals.py:26-33).
+__global__ void dedup_insert_kernel(const int32_t* __restrict__ start_node,
+                                    const int32_t* __restrict__ start_off, unsigned n,
+                                    unsigned long long* __restrict__ table_keys,
+                                    unsigned* __restrict__ table_first, unsigned mask,
+                                    unsigned* __restrict__ slot_of) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long key = ((unsigned long long)(uint32_t)start_node[i] << 32) |
+                             (uint32_t)start_off[i];
+    unsigned h = (unsigned)mix64(key) & mask;
+    while (true) {
+        unsigned long long cur = table_keys[h];
+        if (cur == DEDUP_EMPTY) {
+            unsigned long long old = atomicCAS(&table_keys[h], DEDUP_EMPTY, key);
+            cur = (old == DEDUP_EMPTY) ? key : old;
+        }
+        if (cur == key) {
+            atomicMin(&table_first[h], i);
+            slot_of[i] = h;
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+__global__ void dedup_flag_kernel(const unsigned* __restrict__ table_first,
+                                  const unsigned* __restrict__ slot_of, unsigned n,
+                                  uint8_t* __restrict__ keep) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keep[i] = table_first[slot_of[i]] == i;
+}
+
+__global__ void compact_index_kernel(const uint8_t* __restrict__ keep,
+                                     const uint32_t* __restrict__ offs, unsigned n,
+                                     uint32_t* __restrict__ out) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && keep[i]) out[offs[i]] = i;
+}
+
+}  // namespace gpc
+
+using namespace gpc;
+
+extern "C" int gpc_unique_reads(const int32_t* start_node, const int32_t* start_off,
+                                uint64_t n_reads, uint32_t* out_index, uint64_t* out_count,
+                                void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    *out_count = 0;
+    if (n_reads == 0) return GPC_OK;
+    if (n_reads >= (1ull << 31)) { set_error("too many reads"); return GPC_ERR_ARG; }
+    unsigned n = (unsigned)n_reads;
+    unsigned cap = 1024;
+    while (cap < 2ull * n) cap <<= 1;
+    Scratch keys, first, slot, keep, offs, total;
+    GPC_CUDA(keys.alloc((size_t)cap * 8, stream));
+    GPC_CUDA(first.alloc((size_t)cap * 4, stream));
+    GPC_CUDA(slot.alloc((size_t)n * 4, stream));
+    GPC_CUDA(keep.alloc(n, stream));
+    GPC_CUDA(offs.alloc((size_t)n * 4, stream));
+    GPC_CUDA(total.alloc(8, stream));
+    GPC_CUDA(cudaMemsetAsync(keys.p, 0xff, (size_t)cap * 8, stream));
+    GPC_CUDA(cudaMemsetAsync(first.p, 0xff, (size_t)cap * 4, stream));
+    unsigned blocks = div_up(n, 256);
+    dedup_insert_kernel<<<blocks, 256, 0, stream>>>(start_node, start_off, n,
+                                                   keys.as<unsigned long long>(),
+                                                   first.as<unsigned>(), cap - 1,
+                                                   slot.as<unsigned>());
+    GPC_LAUNCH_CHECK();
+    dedup_flag_kernel<<<blocks, 256, 0, stream>>>(first.as<unsigned>(), slot.as<unsigned>(), n,
+                                                 keep.as<uint8_t>());
+    GPC_LAUNCH_CHECK();
+    GPC_TRY(exclusive_scan<uint8_t>(keep.as<uint8_t>(), offs.as<uint32_t>(), n,
+                                    total.as<unsigned long long>(), stream));
+    compact_index_kernel<<<blocks, 256, 0, stream>>>(keep.as<uint8_t>(), offs.as<uint32_t>(), n,
+                                                    out_index);
+    GPC_LAUNCH_CHECK();
+    unsigned long long h = 0;
+    GPC_CUDA(cudaMemcpyAsync(&h, total.p, 8, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    *out_count = h;
+    return GPC_OK;
+}
+
+extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* reads,
+                                 const uint32_t* read_index, uint64_t n_reads, int32_t extension,
+                                 uint32_t* events, uint64_t event_capacity,
+                                 uint64_t* n_events, uint8_t* touched, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    *n_events = 0;
+    if (extension <= 0) {
+        set_error("Invalid extension size %d used. Must be positive. Is fragment length < read length?", extension);
+        return GPC_ERR_ARG;
+    }
+    if (graph->size_bp >= (1u << 29)) {
+        set_error("graph of %u bp exceeds the 2^29 limit of the packed event key", graph->size_bp);
+        return GPC_ERR_ARG;
+    }
+    GPC_CUDA(cudaMemsetAsync(touched, 0, graph->n_nodes, stream));
+    if (n_reads == 0) return GPC_OK;
+    Scratch ctr;
+    GPC_CUDA(ctr.alloc(16, stream));
+    GPC_CUDA(cudaMemsetAsync(ctr.p, 0, 16, stream));
+    unsigned long long* count = ctr.as<unsigned long long>();
+    int* err = reinterpret_cast<int*>(count + 1);
+    walk_reads_kernel<<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+        *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
+        touched, err);
+    GPC_LAUNCH_CHECK();
+    unsigned long long h[2] = {0, 0};
+    GPC_CUDA(cudaMemcpyAsync(h, ctr.p, 16, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    *n_events = h[0];
+    int e = (int)(h[1] & 0xffffffffu);
+    if (e == GPC_ERR_INVALID_INTERVAL) {
+        set_error("Interval has node(s) not part of graph/pileup");
+        return e;
+    }
+    if (e == GPC_ERR_FRONTIER_OVERFLOW) {
+        set_error("extension frontier exceeded %d simultaneous nodes", FRONTIER_CAP);
+        return e;
+    }
+    if (h[0] > event_capacity) return GPC_ERR_CAPACITY;   // caller retries with *n_events
+    return GPC_OK;
+}
+
+extern "C" int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64_t n_events,
+                                  uint32_t size_bp, uint32_t* frag_idx, int32_t* frag_val,
+                                  uint64_t* n_frag, uint32_t* direct_idx, int32_t* direct_val,
+                                  uint64_t* n_direct, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_events == 0) {   // empty track: one entry (0, 0)
+        GPC_CUDA(cudaMemsetAsync(frag_idx, 0, 4, stream));
+        GPC_CUDA(cudaMemsetAsync(frag_val, 0, 4, stream));
+        GPC_CUDA(cudaMemsetAsync(direct_idx, 0, 4, stream));
+        GPC_CUDA(cudaMemsetAsync(direct_val, 0, 4, stream));
+        *n_frag = *n_direct = 1;
+        return GPC_OK;
+    }
+    int bits = EVENT_POS_SHIFT;
+    while (bits < 32 && (((unsigned long long)size_bp << EVENT_POS_SHIFT) >> bits)) ++bits;
+    bool in_tmp = false;
+    GPC_TRY((radix_sort<uint32_t, false>(events, events_tmp, nullptr, nullptr, n_events, 0, bits,
+                                         false, &in_tmp, stream)));
+    const uint32_t* sorted = in_tmp ? events_tmp : events;
+    unsigned tiles = div_up(n_events, RUN_TILE);
+    size_t bytes = (size_t)tiles * (2 * sizeof(RunAgg) + 4 + 8 + 8) + 64;
+    Scratch sc;
+    GPC_CUDA(sc.alloc(bytes, stream));
+    GPC_CUDA(cudaMemsetAsync(sc.p, 0, bytes, stream));
+    char* p = sc.as<char>();
+    unsigned long long* counts = reinterpret_cast<unsigned long long*>(p);            // 2
+    unsigned* ticket = reinterpret_cast<unsigned*>(p + 16);
+    RunAgg* aggs = reinterpret_cast<RunAgg*>(p + 64);
+    RunAgg* prefixes = aggs + tiles;
+    unsigned long long* st2 = reinterpret_cast<unsigned long long*>(prefixes + tiles);
+    unsigned long long* st3 = st2 + tiles;
+    unsigned* st1 = reinterpret_cast<unsigned*>(st3 + tiles);
+    events_to_runs_kernel<<<tiles, RUN_THREADS, 0, stream>>>(
+        sorted, (unsigned)n_events, frag_idx, frag_val, direct_idx, direct_val, aggs, prefixes, st1,
+        st2, st3, ticket, counts);
+    GPC_LAUNCH_CHECK();
+    unsigned long long h[2];
+    GPC_CUDA(cudaMemcpyAsync(h, counts, 16, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    *n_frag = h[0];
+    *n_direct = h[1];
+    return GPC_OK;
+}

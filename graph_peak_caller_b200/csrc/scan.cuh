@@ -1,0 +1,75 @@
+// Device-wide exclusive prefix sum (single pass, chained scan) and the stream
+// compaction helpers built on it.
+#pragma once
+#include "common.cuh"
+
+namespace gpc {
+
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 8;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
+
+// Claims the next tile index for this block (launch-order ticket).
+__device__ __forceinline__ unsigned claim_tile(unsigned* ticket, unsigned* s_slot) {
+    if (threadIdx.x == 0) *s_slot = atomicAdd(ticket, 1u);
+    __syncthreads();
+    unsigned t = *s_slot;
+    __syncthreads();
+    return t;
+}
+
+// out[i] = sum_{j<i} in[j]  (uint32 in, uint64 running sum stored as uint32:
+// callers guarantee the total fits).  total[0] receives the grand total.
+template <typename InT>
+__global__ void __launch_bounds__(SC_THREADS)
+excl_scan_kernel(const InT* __restrict__ in, uint32_t* __restrict__ out, unsigned n,
+                 unsigned long long* __restrict__ status, unsigned* __restrict__ ticket,
+                 unsigned long long* __restrict__ total) {
+    __shared__ unsigned s_scan[33];
+    __shared__ unsigned s_slot;
+    __shared__ unsigned long long s_prefix;
+    const unsigned tile = claim_tile(ticket, &s_slot);
+    const unsigned base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
+    unsigned v[SC_ITEMS];
+    unsigned sum = 0;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        v[j] = (base + j < n) ? (unsigned)in[base + j] : 0u;
+        sum += v[j];
+    }
+    unsigned tile_total;
+    unsigned ex = block_excl_sum<unsigned>(sum, s_scan, tile_total);
+    if (threadIdx.x == 0) {
+        unsigned long long p = lookback_excl(status, tile, tile_total);
+        s_prefix = p;
+        if (tile == gridDim.x - 1 && total) *total = p + tile_total;
+    }
+    __syncthreads();
+    unsigned run = (unsigned)s_prefix + ex;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        if (base + j < n) out[base + j] = run;
+        run += v[j];
+    }
+}
+
+// Host driver: scratch for status/ticket is taken from the stream pool.
+template <typename InT>
+int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* total_dev,
+                   cudaStream_t stream) {
+    if (n == 0) {
+        if (total_dev) GPC_CUDA(cudaMemsetAsync(total_dev, 0, 8, stream));
+        return GPC_OK;
+    }
+    unsigned tiles = div_up(n, SC_TILE);
+    Scratch sc;
+    GPC_CUDA(sc.alloc((size_t)tiles * 8 + 16, stream));
+    GPC_CUDA(cudaMemsetAsync(sc.p, 0, (size_t)tiles * 8 + 16, stream));
+    unsigned long long* status = sc.as<unsigned long long>() + 2;
+    unsigned* ticket = sc.as<unsigned>();
+    excl_scan_kernel<InT><<<tiles, SC_THREADS, 0, stream>>>(in, out, (unsigned)n, status, ticket, total_dev);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+
+}  // namespace gpc

@@ -1,0 +1,116 @@
+"""HBM residency: the graph and the reads as torch CUDA tensors plus the plain
+pointer structs of include/gpc_b200.h.  PyTorch is only the allocator and the
+stream here; every computation is a kernel of libgpc_b200.so."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .custom_exceptions import DeviceLibraryMissing
+
+
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise DeviceLibraryMissing(
+            "no CUDA device visible: the callpeaks path runs on the GPU only")
+    return torch
+
+
+def device():
+    torch = torch_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr():
+    torch = torch_cuda()
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def to_device(a, dtype=None):
+    torch = torch_cuda()
+    a = np.ascontiguousarray(a if dtype is None else np.asarray(a).astype(dtype))
+    return torch.from_numpy(a).to(device(), non_blocking=False)
+
+
+def empty(n, dtype):
+    torch = torch_cuda()
+    return torch.empty(int(n), dtype=dtype, device=device())
+
+
+class DeviceGraph:
+    """Graph CSR in HBM (include/gpc_b200.h: gpc_graph_t)."""
+
+    def __init__(self, graph, linear_map=None):
+        torch = torch_cuda()
+        n = graph.n_nodes
+        rec = np.zeros((n + 1, 4), dtype=np.uint32)
+        rec[:, 0] = graph.node_off
+        rec[:, 1] = graph.succ_ptr
+        rec[:, 2] = graph.pred_ptr
+        rec[:n, 3] = graph.node_len
+        self.graph = graph
+        self.node_rec = to_device(rec.view(np.int32))
+        self.succ = to_device(graph.succ.astype(np.int32))
+        self.pred = to_device(graph.pred.astype(np.int32))
+        self.lin_start = self.lin_end = None
+        if linear_map is not None:
+            self.set_linear_map(*linear_map)
+        self._struct()
+
+    def set_linear_map(self, starts, ends):
+        self.lin_start = to_device(np.asarray(starts, dtype=np.float64))
+        self.lin_end = to_device(np.asarray(ends, dtype=np.float64))
+        self.linear_length = float(np.asarray(ends)[-1])
+        self._struct()
+
+    def _struct(self):
+        g = self.graph
+        self.c = _lib.GpcGraph(g.n_nodes, g.n_edges, g.size_bp, g.min_node,
+                               ptr(self.node_rec), ptr(self.succ), ptr(self.pred),
+                               ptr(self.lin_start), ptr(self.lin_end))
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in
+                   (self.node_rec, self.succ, self.pred, self.lin_start, self.lin_end)
+                   if t is not None)
+
+
+class DeviceReads:
+    """Reads SoA in HBM (include/gpc_b200.h: gpc_reads_t)."""
+
+    def __init__(self, batch, pinned=False):
+        self.batch = batch
+        self.n = len(batch)
+        self.start_node = to_device(batch.start_node)
+        self.start_off = to_device(batch.start_off)
+        self.end_node = to_device(batch.end_node)
+        self.end_off = to_device(batch.end_off)
+        self.path_ptr = to_device(batch.path_ptr)
+        self.path = to_device(batch.path)
+        self.c = _lib.GpcReads(self.n, ptr(self.start_node), ptr(self.start_off),
+                               ptr(self.end_node), ptr(self.end_off),
+                               ptr(self.path_ptr), ptr(self.path))
+
+
+def device_graph(graph, linear_map=None):
+    """Cached upload of a host Graph."""
+    dg = getattr(graph, "_device", None)
+    if dg is None:
+        dg = DeviceGraph(graph, linear_map)
+        graph._device = dg
+    elif linear_map is not None and dg.lin_start is None:
+        dg.set_linear_map(*linear_map)
+    return dg
+
+
+def device_reads(batch):
+    dr = getattr(batch, "_device", None)
+    if dr is None:
+        dr = DeviceReads(batch)
+        batch._device = dr
+    return dr

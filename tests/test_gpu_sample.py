@@ -1,0 +1,118 @@
+"""GPU parity: duplicate filter and sample / direct pileups through the C ABI
+against the oracle (bit-exact integer tracks)."""
+import numpy as np
+import pytest
+
+from golden_util import GoldenCase, case_names
+from graph_peak_caller_b200.synthetic import make_graph, make_reads
+from oracle import pipeline, sample as osample
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_sample(graph, reads, extension, unique):
+    from graph_peak_caller_b200 import kernels
+    from graph_peak_caller_b200.device import DeviceGraph, DeviceReads
+    dg, dr = DeviceGraph(graph), DeviceReads(reads)
+    index, n = None, len(reads)
+    if unique:
+        index, n = kernels.unique_reads(dr)
+    events, touched = kernels.sample_events(dg, dr, index, n, extension)
+    (fi, fv), (di, dv) = kernels.events_to_runs(events, graph.size_bp)
+    cpu = lambda t: t.cpu().numpy()
+    return dict(index=None if index is None else cpu(index), n=n,
+                sample=(cpu(fi).view(np.uint32).astype(np.int64), cpu(fv).astype(np.float64)),
+                direct=(cpu(di).view(np.uint32).astype(np.int64), cpu(dv).astype(np.float64)),
+                touched=np.flatnonzero(cpu(touched)) + graph.min_node,
+                n_events=events.numel())
+
+
+def check(graph, reads, extension, unique):
+    got = gpu_sample(graph, reads, extension, unique)
+    r = reads
+    if unique:
+        keep = osample.unique_read_mask(reads)
+        assert np.array_equal(got["index"], np.flatnonzero(keep))
+        r = pipeline.unique_reads(reads)
+    ref = osample.fragment_pileup(graph, r, extension)
+    for key in ("sample", "direct"):
+        assert np.array_equal(got[key][0], ref[key][0]), key
+        assert np.array_equal(got[key][1], ref[key][1]), key
+    assert np.array_equal(got["touched"], ref["touched"])
+    return got
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_golden_cases(name):
+    case = GoldenCase(name)
+    m = case.meta
+    got = check(case.graph, case.sample, m["fragment_length"] - m["read_length"], m["unique"])
+    # and straight against what the reference produced (unscaled tracks only)
+    if m["n_sample"] <= m["n_control"]:
+        gi, gv = case.track("sample")
+        assert np.array_equal(got["sample"][0], gi) and np.array_equal(got["sample"][1], gv)
+    di, dv = case.track("direct")
+    assert np.array_equal(got["direct"][0], di) and np.array_equal(got["direct"][1], dv)
+    assert np.array_equal(got["touched"], case.touched)
+
+
+@pytest.mark.parametrize("trial", range(12))
+def test_random_graphs(trial):
+    rng = np.random.default_rng(77 + trial)
+    g = make_graph(int(rng.integers(500, 60000)),
+                   site_rate=float(rng.choice([0.01, 0.03, 0.1, 0.25])), seed=trial,
+                   min_node=int(rng.choice([1, 1000])),
+                   mnp_frac=float(rng.choice([0, 0.3])),
+                   indel_mean=float(rng.choice([2, 5, 30])))
+    R = int(rng.integers(5, 40))
+    ext = int(rng.integers(1, 300))
+    reads = make_reads(g, int(rng.integers(1, 6000)), R, R + ext, seed=trial + 500,
+                       peak_frac=0.5, peak_spacing=3000, dup_frac=0.1)
+    check(g, reads, ext, unique=bool(trial % 2))
+
+
+def test_invalid_interval_raises():
+    from graph_peak_caller_b200.custom_exceptions import InvalidPileupInterval
+    from graph_peak_caller_b200.reads import ReadBatch
+    g = make_graph(1000, 0.02, seed=1)
+    bad = ReadBatch([g.n_nodes + 5], [0], [g.n_nodes + 5], [3], [0, 1], [g.n_nodes + 5])
+    with pytest.raises(InvalidPileupInterval):
+        gpu_sample(g, bad, 10, False)
+
+
+def test_extension_must_be_positive():
+    g = make_graph(1000, 0.02, seed=1)
+    reads = make_reads(g, 10, 10, 20, seed=3)
+    with pytest.raises(Exception):
+        gpu_sample(g, reads, 0, False)
+
+
+def test_medium_size_properties():
+    """1 Mbp / 100k reads: too slow for the Python oracle, so check the
+    size-independent invariants: canonical form, total coverage == sum over
+    reads of covered bases is at least reads*min(len), final value 0."""
+    g = make_graph(1_000_000, 0.02, seed=11)
+    reads = make_reads(g, 100_000, 36, 200, seed=12)
+    got = gpu_sample(g, reads, 164, True)
+    for key in ("sample", "direct"):
+        idx, val = got[key]
+        assert idx[0] == 0 and np.all(np.diff(idx) > 0)
+        assert np.all(val[1:] != val[:-1])
+        assert val.min() >= 0 and val[-1] == 0
+        assert idx[-1] <= g.size_bp
+    # direct pileup mass == total read length of unique reads
+    idx, val = got["direct"]
+    mass = int(np.sum(np.diff(np.r_[idx, g.size_bp]) * val))
+    r = pipeline.unique_reads(reads)
+    nl = g.node_len[np.abs(r.path) - g.min_node]
+    per_read = np.add.reduceat(nl, r.path_ptr[:-1])
+    first = np.abs(r.path[r.path_ptr[:-1]]) - g.min_node
+    last = np.abs(r.path[r.path_ptr[1:] - 1]) - g.min_node
+    fwd = r.start_node > 0
+    # forward: start offset in first node, end offset in last; reverse: mirrored
+    length = per_read - r.start_off - (g.node_len[np.where(fwd, last, first)] - r.end_off) \
+        if False else None
+    s_node = np.abs(r.start_node) - g.min_node
+    e_node = np.abs(r.end_node) - g.min_node
+    length = per_read - r.start_off - (g.node_len[e_node] - r.end_off)
+    assert mass == int(length.sum())
