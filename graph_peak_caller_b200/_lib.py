@@ -40,6 +40,18 @@ _SIGNATURES = {
                           u64, P(u64), c_void_p, c_void_p],
     "gpc_events_to_runs": [c_void_p, c_void_p, u64, u32, c_void_p, c_void_p, P(u64),
                            c_void_p, c_void_p, P(u64), c_void_p],
+    "gpc_control_linear_track": [P(GpcGraph), c_void_p, c_void_p, c_void_p, u64,
+                                 P(i32), i32, i32, f64, c_void_p, c_void_p, P(u64),
+                                 c_void_p, c_void_p],
+    "gpc_control_backproject": [P(GpcGraph), c_void_p, c_void_p, c_void_p, u64, f64, f64,
+                                c_void_p, c_void_p, u64, P(u64), c_void_p],
+    "gpc_pvalues": [c_void_p, c_void_p, u64, f64, c_void_p, c_void_p, u64, c_void_p,
+                    c_void_p, P(u64), c_void_p],
+    "gpc_ptable_local": [c_void_p, c_void_p, u64, u32, c_void_p, c_void_p, u64, P(u64),
+                         c_void_p],
+    "gpc_qtable_build": [c_void_p, c_void_p, u64, u64, c_void_p, c_void_p, P(u64), c_void_p],
+    "gpc_qvalues_apply": [c_void_p, u64, c_void_p, c_void_p, u64, c_void_p, c_void_p],
+    "gpc_threshold": [c_void_p, c_void_p, u64, f64, c_void_p, c_void_p, P(u64), c_void_p],
     "gpc_sort_u32": [c_void_p, c_void_p, u64, i32, i32, P(i32), c_void_p],
     "gpc_sort_u64_pairs": [c_void_p, c_void_p, c_void_p, c_void_p, u64, i32, i32,
                            P(i32), c_void_p],

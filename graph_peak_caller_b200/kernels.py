@@ -91,3 +91,103 @@ def events_to_runs(events, size_bp):
                                       ctypes.byref(nf), ptr(di), ptr(dv),
                                       ctypes.byref(nd), stream_ptr()))
     return (fi[:nf.value], fv[:nf.value]), (di[:nd.value], dv[:nd.value])
+
+
+def control_linear_track(dgraph, dreads, read_index, n_reads, extensions,
+                         fragment_length, min_value, want_x=False):
+    """C2/C3.  Returns (bp float64[U], val float64[U], x or None)."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    cap = max(2 * len(extensions) * int(n_reads), 1)
+    bp, val = empty(cap, torch.float64), empty(cap, torch.float64)
+    x = empty(max(int(n_reads), 1), torch.float64) if want_x else None
+    ext = (ctypes.c_int32 * len(extensions))(*[int(e) for e in extensions])
+    n_out = _u64()
+    _lib.check(lib.gpc_control_linear_track(
+        ctypes.byref(dgraph.c), ptr(dreads.start_node), ptr(dreads.start_off),
+        ptr(read_index), n_reads, ext, len(extensions), int(fragment_length),
+        float(min_value), ptr(bp), ptr(val), ctypes.byref(n_out), ptr(x), stream_ptr()))
+    return bp[:n_out.value], val[:n_out.value], x
+
+
+def control_backproject(dgraph, touched, bp, val, min_value, value_scale=1.0):
+    """C4/C5.  Returns (pos int32[Uc], lambda float64[Uc])."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    cap = dgraph.graph.n_nodes + 2 * bp.numel() + 16
+    while True:
+        pos, lam = empty(cap, torch.int32), empty(cap, torch.float64)
+        n_out = _u64()
+        status = lib.gpc_control_backproject(
+            ctypes.byref(dgraph.c), ptr(touched), ptr(bp), ptr(val), bp.numel(),
+            float(min_value), float(value_scale), ptr(pos), ptr(lam), cap,
+            ctypes.byref(n_out), stream_ptr())
+        if status == _lib.GPC_ERR_CAPACITY:
+            cap = int(n_out.value) + 16
+            continue
+        _lib.check(status)
+        return pos[:n_out.value], lam[:n_out.value]
+
+
+def pvalues(spos, sval, sample_scale, cpos, cval):
+    """P1.  Returns (pos int32[Up], p float64[Up])."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    cap = spos.numel() + cpos.numel()
+    pos, p = empty(max(cap, 1), torch.int32), empty(max(cap, 1), torch.float64)
+    n_out = _u64()
+    _lib.check(lib.gpc_pvalues(ptr(spos), ptr(sval), spos.numel(), float(sample_scale),
+                               ptr(cpos), ptr(cval), cpos.numel(), ptr(pos), ptr(p),
+                               ctypes.byref(n_out), stream_ptr()))
+    return pos[:n_out.value], p[:n_out.value]
+
+
+def ptable_local(pos, p, track_size):
+    """Q1 (local half).  Returns (p float64[D], bp int64[D]) unordered."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    cap = 1 << 16
+    while True:
+        tp, tc = empty(cap, torch.float64), empty(cap, torch.int64)
+        n_out = _u64()
+        status = lib.gpc_ptable_local(ptr(pos), ptr(p), pos.numel(), int(track_size),
+                                      ptr(tp), ptr(tc), cap, ctypes.byref(n_out),
+                                      stream_ptr())
+        if status == _lib.GPC_ERR_CAPACITY:
+            cap = int(n_out.value) + 16
+            continue
+        _lib.check(status)
+        return tp[:n_out.value], tc[:n_out.value]
+
+
+def qtable_build(table_p, table_count, total_bp):
+    """Q1 (global half).  Returns (p descending float64[D], q float64[D])."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    n = table_p.numel()
+    op, oq = empty(max(n, 1), torch.float64), empty(max(n, 1), torch.float64)
+    n_out = _u64()
+    _lib.check(lib.gpc_qtable_build(ptr(table_p), ptr(table_count), n, int(total_bp),
+                                    ptr(op), ptr(oq), ctypes.byref(n_out), stream_ptr()))
+    return op[:n_out.value], oq[:n_out.value]
+
+
+def qvalues_apply(p, table_p, table_q):
+    torch = torch_cuda()
+    lib = _lib.load()
+    q = torch.empty_like(p)
+    _lib.check(lib.gpc_qvalues_apply(ptr(p), p.numel(), ptr(table_p), ptr(table_q),
+                                     table_p.numel(), ptr(q), stream_ptr()))
+    return q
+
+
+def threshold(pos, q, cutoff):
+    """H1.  Returns (pos int32[Ut], value uint8[Ut])."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    n = pos.numel()
+    op, ov = empty(max(n, 1), torch.int32), empty(max(n, 1), torch.uint8)
+    n_out = _u64()
+    _lib.check(lib.gpc_threshold(ptr(pos), ptr(q), n, float(cutoff), ptr(op), ptr(ov),
+                                 ctypes.byref(n_out), stream_ptr()))
+    return op[:n_out.value], ov[:n_out.value]

@@ -105,6 +105,79 @@ int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64_t n_events
                        uint32_t* direct_idx, int32_t* direct_val, uint64_t* n_direct,
                        void* stream);
 
+/* ---- C2/C3  LinearMap.map_interval_collection (control/linearmap.py:51-74) and
+ *            SparseControl.create up to the LinearPileup
+ *            (control/controlgenerator.py:21-41, control/linearpileup.py:130-143)
+ * Projects the start position of every control read onto the linear axis
+ * (reference float64 operation order), builds the +-1 events of each
+ * extension window (half width extensions[w] / 2, weight fragment_length /
+ * (2 * half)), and writes the linear background
+ *     max(min_value, max_w count_w * weight_w)
+ * as breakpoints (out_pos, float64 linear coordinate) and values (out_val).
+ * Capacity of out_pos / out_val: 2 * n_extensions * n_reads.  x_out (may be
+ * NULL): the projected starts, n_reads doubles.  graph->lin_start/lin_end
+ * must be set. */
+int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t* start_node,
+                             const int32_t* start_off, const uint32_t* read_index,
+                             uint64_t n_reads, const int32_t* extensions /* host */,
+                             int32_t n_extensions, int32_t fragment_length, double min_value,
+                             double* out_pos, double* out_val, uint64_t* n_out, double* x_out,
+                             void* stream);
+
+/* ---- C4/C5  LinearPileup.to_sparse_pileup -> LinearMap.to_sparse_pileup
+ *            (control/linearpileup.py:56-103, control/linearmap.py:76-99) ----
+ * Maps the linear background back onto graph positions: an untouched node
+ * gets one entry (node start, min_value); a touched node gets the value in
+ * force at its linear start plus every breakpoint inside its linear span,
+ * positions through numpy's float floor-division.  Values are multiplied by
+ * value_scale (scale_tracks, control/__init__.py:32-42: ratio when < 1).
+ * touched may be NULL (all nodes touched).  out_pos is non-decreasing and may
+ * repeat a position (the last entry wins).  GPC_ERR_CAPACITY reports the
+ * needed capacity in *n_out. */
+int gpc_control_backproject(const gpc_graph_t* graph, const uint8_t* touched, const double* bp,
+                            const double* val, uint64_t n_bp, double min_value,
+                            double value_scale, uint32_t* out_pos, double* out_val,
+                            uint64_t out_capacity, uint64_t* n_out, void* stream);
+
+/* ---- P1  PValuesFinder.get_p_values_pileup (sparsepvalues.py:16-31) ---------
+ * Merges sample runs and control entries; per distinct position
+ * p = -log10 PoissonSF(count * sample_scale, lambda) with the reference's
+ * clamp rules (count 0 -> 0, underflow -> 1000); canonical output.
+ * sample_scale: 1/ratio when ratio > 1, else 1 (scale_tracks).
+ * Capacity of out_pos / out_p: n_sample + n_control. */
+int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val, uint64_t n_sample,
+                double sample_scale, const uint32_t* control_pos, const double* control_val,
+                uint64_t n_control, uint32_t* out_pos, double* out_p, uint64_t* n_out,
+                void* stream);
+
+/* ---- Q1  PToQValuesMapper.__get_sub_counts + _from_subcounts, first half
+ *          (sparsepvalues.py:50-74) ------------------------------------------
+ * Distinct non-zero p of one chromosome with the base pairs they cover
+ * (unordered).  This table is what ranks exchange in a multi-GPU run.
+ * GPC_ERR_CAPACITY reports the needed capacity in *n_distinct. */
+int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n_runs, uint32_t track_size,
+                     double* table_p, uint64_t* table_count, uint64_t table_capacity,
+                     uint64_t* n_distinct, void* stream);
+
+/* ---- Q1  PToQValuesMapper._from_subcounts second half + get_p_to_q_values
+ *          (sparsepvalues.py:53-59, 95-103) -----------------------------------
+ * Input: any concatenation of local tables (p may repeat); total_bp = sum of
+ * the track sizes of all chromosomes.  Output: distinct p descending and
+ * their q (capacity n_entries each). */
+int gpc_qtable_build(const double* table_p, const uint64_t* table_count, uint64_t n_entries,
+                     uint64_t total_bp, double* out_p, double* out_q, uint64_t* n_out,
+                     void* stream);
+
+/* ---- Q2  QValuesFinder.get_q_values (sparsepvalues.py:116-125) --------------
+ * Exact-key lookup of every run's p in the table (p == 0 -> q = 0). */
+int gpc_qvalues_apply(const double* p, uint64_t n_runs, const double* table_p,
+                      const double* table_q, uint64_t n_table, double* out_q, void* stream);
+
+/* ---- H1  SparseValues.threshold_copy (sparsediffs.py:58-62) -----------------
+ * Canonical boolean track of q >= cutoff.  Capacity n_runs. */
+int gpc_threshold(const uint32_t* pos, const double* q, uint64_t n_runs, double cutoff,
+                  uint32_t* out_pos, uint8_t* out_val, uint64_t* n_out, void* stream);
+
 /* ---- building blocks (np.argsort / np.cumsum of the reference's
  *      sparsediffs.py, exported for the host side and the parity tests) ------
  * LSD radix sorts over bits [begin_bit, end_bit); keys/vals ping-pong with
