@@ -52,6 +52,12 @@ _SIGNATURES = {
     "gpc_qtable_build": [c_void_p, c_void_p, u64, u64, c_void_p, c_void_p, P(u64), c_void_p],
     "gpc_qvalues_apply": [c_void_p, u64, c_void_p, c_void_p, u64, c_void_p, c_void_p],
     "gpc_threshold": [c_void_p, c_void_p, u64, f64, c_void_p, c_void_p, P(u64), c_void_p],
+    "gpc_clean_holes": [P(GpcGraph), c_void_p, c_void_p, u64, i32, c_void_p, c_void_p,
+                        c_void_p, u64, P(u64), c_void_p],
+    "gpc_max_paths": [P(GpcGraph), c_void_p, c_void_p, u64, c_void_p, c_void_p, u64,
+                      c_void_p, c_void_p, u64, i32, c_void_p, c_void_p, c_void_p,
+                      c_void_p, c_void_p, c_void_p, u64, c_void_p, u64, c_void_p, P(u64),
+                      P(u64), c_void_p],
     "gpc_sort_u32": [c_void_p, c_void_p, u64, i32, i32, P(i32), c_void_p],
     "gpc_sort_u64_pairs": [c_void_p, c_void_p, c_void_p, c_void_p, u64, i32, i32,
                            P(i32), c_void_p],

@@ -1,0 +1,1109 @@
+// Threshold consumers on sm_100a: hole cleaning, max paths, peak scoring.
+//
+// Replaces the reference's
+//   HolesCleaner                       postprocess/holecleaner.py:9-109
+//   SegmentAnalyzer / SegmentSplitter  postprocess/segmentanalyzer.py:5-134
+//   StubsFilter, LineGraph, DividedLinegraph.filter_small,
+//   PosDividedLineGraph.max_paths      postprocess/graphs.py:14-355
+//   SubGraphAnalyzer                   postprocess/subgraphanalyzer.py:4-39
+//   SparseMaxPaths                     postprocess/maxpaths.py:11-191
+//   CallPeaksFromQvalues.__get_max_paths tail, DensePileup.get_interval_values
+//                                      callpeaks.py:186-212, mindense.py:25-59
+//
+// Holes and peaks are cut into per-node pieces (one thread per piece); pieces
+// are the vertices of a line graph whose edges follow the graph's edges.  The
+// reference runs scipy all-pairs shortest paths per connected component; here
+// components come from a lock-free union-find, the "> 36 vertices" and "no
+// entry vertex" rules are per-component reductions, and the distance test
+// (shortest entry->sink path through a piece  >  read length) is a bounded
+// number of relaxation rounds over the few vertices of small components.
+// Max paths replay scipy's Bellman-Ford sweep order per component (one thread
+// per component) so that ties break exactly as in the reference.
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace gpc {
+
+constexpr int PIECE_TAIL = 0, PIECE_WHOLE = 1, PIECE_HEAD = 2, PIECE_INTERNAL = 3;
+constexpr int INF_I = 1 << 30;
+
+__device__ __forceinline__ uint32_t node_off_at(const gpc_graph_t& g, uint32_t v) {
+    return __ldg(g.node_rec + 4ull * v);
+}
+// largest v with node_off[v] <= pos   (np.digitize(pos, node_off) - 1)
+__device__ __forceinline__ uint32_t node_containing(const gpc_graph_t& g, uint32_t pos) {
+    uint32_t lo = 0, hi = g.n_nodes + 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (node_off_at(g, mid) <= pos) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1;
+}
+// largest v with node_off[v] < pos    (np.digitize(pos, node_off, True) - 1)
+__device__ __forceinline__ uint32_t node_ending(const gpc_graph_t& g, uint32_t pos) {
+    uint32_t lo = 0, hi = g.n_nodes + 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (node_off_at(g, mid) < pos) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1;
+}
+__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* a, uint32_t n, uint32_t x) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- segments (holes or peaks) -> per-node pieces ----------------------------
+
+// seg s = [pos[first + 2s], pos[first + 2s + 1])  (end of the last one may be
+// `tail_end` when the track ends inside a run)
+struct Segments {
+    const uint32_t* pos;
+    uint32_t first;
+    uint32_t n_seg;
+    uint32_t n_pos;
+    uint32_t tail_end;
+};
+__device__ __forceinline__ void segment_bounds(const Segments& sg, uint32_t s, uint32_t& a,
+                                               uint32_t& b) {
+    uint32_t i = sg.first + 2 * s;
+    a = sg.pos[i];
+    b = (i + 1 < sg.n_pos) ? sg.pos[i + 1] : sg.tail_end;
+}
+
+__global__ void segment_nodes_kernel(gpc_graph_t g, Segments sg, uint32_t* __restrict__ v0,
+                                     uint32_t* __restrict__ v1, uint32_t* __restrict__ n_pieces,
+                                     uint32_t* __restrict__ is_multi,
+                                     uint32_t* __restrict__ n_between) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= sg.n_seg) return;
+    uint32_t a, b;
+    segment_bounds(sg, s, a, b);
+    uint32_t x = node_containing(g, a), y = node_ending(g, b);
+    v0[s] = x;
+    v1[s] = y;
+    n_pieces[s] = y - x + 1;
+    if (is_multi) {
+        is_multi[s] = y != x;
+        n_between[s] = y > x + 1 ? y - x - 1 : 0;
+    }
+}
+
+// Hole pieces: any order is fine (one thread per piece, contiguous per hole).
+__global__ void hole_pieces_kernel(gpc_graph_t g, Segments sg, const uint32_t* __restrict__ v0,
+                                   const uint32_t* __restrict__ offs, uint32_t n_pieces,
+                                   uint32_t* __restrict__ p_node, uint32_t* __restrict__ p_start,
+                                   uint32_t* __restrict__ p_end, uint8_t* __restrict__ p_type) {
+    uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= n_pieces) return;
+    uint32_t s = upper_bound_u32(offs, sg.n_seg, pid) - 1;
+    uint32_t a, b;
+    segment_bounds(sg, s, a, b);
+    uint32_t v = v0[s] + (pid - offs[s]);
+    uint32_t ns = node_off_at(g, v), ne = node_off_at(g, v + 1);
+    uint32_t ps = max(a, ns), pe = min(b, ne);
+    bool at_start = ps == ns, at_end = pe == ne;
+    p_node[pid] = v;
+    p_start[pid] = ps;
+    p_end[pid] = pe;
+    p_type[pid] = at_start ? (at_end ? PIECE_WHOLE : PIECE_HEAD)
+                           : (at_end ? PIECE_TAIL : PIECE_INTERNAL);
+}
+
+// Peak pieces in SegmentSplitter order (segmentanalyzer.py:106-134): first the
+// first piece of every segment, then the last piece of every multi-node
+// segment, then the nodes in between, all in segment order.
+__global__ void peak_pieces_kernel(gpc_graph_t g, Segments sg, const uint32_t* __restrict__ v0,
+                                   const uint32_t* __restrict__ v1,
+                                   const uint32_t* __restrict__ multi_rank,
+                                   const uint32_t* __restrict__ between_offs, uint32_t n_multi,
+                                   uint32_t* __restrict__ p_node, uint32_t* __restrict__ p_start,
+                                   uint32_t* __restrict__ p_end, uint8_t* __restrict__ p_type) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= sg.n_seg) return;
+    uint32_t a, b;
+    segment_bounds(sg, s, a, b);
+    auto put = [&](uint32_t pid, uint32_t v) {
+        uint32_t ns = node_off_at(g, v), ne = node_off_at(g, v + 1);
+        uint32_t ps = max(a, ns), pe = min(b, ne);
+        bool at_start = ps == ns, at_end = pe == ne;
+        p_node[pid] = v;
+        p_start[pid] = ps;
+        p_end[pid] = pe;
+        p_type[pid] = at_start ? (at_end ? PIECE_WHOLE : PIECE_HEAD)
+                               : (at_end ? PIECE_TAIL : PIECE_INTERNAL);
+    };
+    put(s, v0[s]);
+    if (v1[s] != v0[s]) {
+        put(sg.n_seg + multi_rank[s], v1[s]);
+        uint32_t base = sg.n_seg + n_multi + between_offs[s];
+        for (uint32_t v = v0[s] + 1; v < v1[s]; ++v) put(base + (v - v0[s] - 1), v);
+    }
+}
+
+// ---- line graph over the pieces ----------------------------------------------
+
+struct PieceGraph {
+    uint32_t n_pieces;
+    const uint32_t* p_node;
+    const uint8_t* p_type;
+    const uint8_t* p_vertex;     // 1: piece is a vertex of the line graph
+    int32_t* in_vertex;          // node -> piece id of its whole/head vertex, or -1
+    int32_t* out_vertex;         // node -> piece id of its tail/whole vertex, or -1
+    uint8_t* node_into;          // node carries a whole/head piece (vertex or not)
+    uint8_t* node_outof;         // node carries a tail/whole piece (vertex or not)
+};
+
+// Holes only: drop whole pieces on untouched nodes (they are always kept,
+// holecleaner.py:61-70) and pieces on graph sources / sinks (StubsFilter,
+// graphs.py:60-75); register the rest in the node maps.
+__global__ void hole_vertices_kernel(gpc_graph_t g, const uint8_t* __restrict__ touched,
+                                     uint32_t n_pieces, const uint32_t* __restrict__ p_node,
+                                     const uint8_t* __restrict__ p_type,
+                                     uint8_t* __restrict__ p_vertex, uint8_t* __restrict__ p_keep,
+                                     int32_t* __restrict__ in_vertex,
+                                     int32_t* __restrict__ out_vertex,
+                                     uint8_t* __restrict__ node_into,
+                                     uint8_t* __restrict__ node_outof) {
+    uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= n_pieces) return;
+    int t = p_type[pid];
+    uint32_t v = p_node[pid];
+    p_vertex[pid] = 0;
+    p_keep[pid] = 0;
+    if (t == PIECE_INTERNAL) return;
+    if (t == PIECE_WHOLE && touched && !touched[v]) { p_keep[pid] = 1; return; }
+    uint4 a = node_record(g, v), b = node_record(g, v + 1);
+    bool has_succ = b.y > a.y, has_pred = b.z > a.z;
+    if (t != PIECE_HEAD) node_outof[v] = 1;
+    if (t != PIECE_TAIL) node_into[v] = 1;
+    bool vertex = (t == PIECE_TAIL) ? has_succ : (t == PIECE_HEAD) ? has_pred : (has_succ && has_pred);
+    if (!vertex) { p_keep[pid] = 1; return; }
+    p_vertex[pid] = 1;
+    if (t != PIECE_HEAD) out_vertex[v] = (int32_t)pid;
+    if (t != PIECE_TAIL) in_vertex[v] = (int32_t)pid;
+}
+
+// Peaks: every non-internal piece is a vertex (PosStubFilter, graphs.py:83-106).
+// Vertex ids follow the reference: tails, wholes, heads, each in piece order.
+__global__ void peak_vertices_kernel(uint32_t n_pieces, const uint32_t* __restrict__ p_node,
+                                     const uint8_t* __restrict__ p_type,
+                                     const uint32_t* __restrict__ rank_tail,
+                                     const uint32_t* __restrict__ rank_whole,
+                                     const uint32_t* __restrict__ rank_head, uint32_t n_tail,
+                                     uint32_t n_whole, int32_t* __restrict__ vertex_of_piece,
+                                     uint32_t* __restrict__ piece_of_vertex,
+                                     int32_t* __restrict__ in_vertex,
+                                     int32_t* __restrict__ out_vertex) {
+    uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= n_pieces) return;
+    int t = p_type[pid];
+    if (t == PIECE_INTERNAL) { vertex_of_piece[pid] = -1; return; }
+    uint32_t vid = t == PIECE_TAIL ? rank_tail[pid]
+                 : t == PIECE_WHOLE ? n_tail + rank_whole[pid]
+                                    : n_tail + n_whole + rank_head[pid];
+    vertex_of_piece[pid] = (int32_t)vid;
+    piece_of_vertex[vid] = pid;
+    uint32_t v = p_node[pid];
+    if (t != PIECE_HEAD) out_vertex[v] = (int32_t)vid;
+    if (t != PIECE_TAIL) in_vertex[v] = (int32_t)vid;
+}
+
+__global__ void class_flags_kernel(uint32_t n, const uint8_t* __restrict__ p_type,
+                                   uint32_t* __restrict__ f_tail, uint32_t* __restrict__ f_whole,
+                                   uint32_t* __restrict__ f_head, uint32_t* __restrict__ f_internal) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int t = p_type[i];
+    f_tail[i] = t == PIECE_TAIL;
+    f_whole[i] = t == PIECE_WHOLE;
+    f_head[i] = t == PIECE_HEAD;
+    f_internal[i] = t == PIECE_INTERNAL;
+}
+
+// union-find -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
+    while (true) {
+        uint32_t p = parent[x];
+        if (p == x) return x;
+        uint32_t gp = parent[p];
+        if (gp != p) parent[x] = gp;   // path halving (benign race)
+        x = p;
+    }
+}
+__device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { uint32_t t = a; a = b; b = t; }     // hook larger root under smaller
+        uint32_t old = atomicCAS(&parent[a], a, b);
+        if (old == a) return;
+    }
+}
+
+__global__ void iota_kernel(uint32_t* a, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+
+// Vertex ids: holes use piece ids, peaks use reference vertex ids; `node_of`
+// gives the graph node of a vertex, `is_source` says whether it has out edges
+// to other pieces (tails and wholes).
+struct VertexView {
+    uint32_t n;
+    const uint32_t* node_of;     // per vertex
+    const uint8_t* type_of;      // per vertex
+    const uint8_t* alive;        // per vertex (may be NULL: all alive)
+    const int32_t* in_vertex;    // per node
+    const int32_t* out_vertex;   // per node
+};
+
+__global__ void uf_edges_kernel(gpc_graph_t g, VertexView vw, uint32_t* __restrict__ parent) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= vw.n) return;
+    if (vw.alive && !vw.alive[u]) return;
+    if (vw.type_of[u] == PIECE_HEAD) return;
+    uint32_t a = vw.node_of[u];
+    uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
+    for (uint32_t e = r0.y; e < r1.y; ++e) {
+        int32_t w = vw.in_vertex[g.succ[e]];
+        if (w >= 0) uf_union(parent, u, (uint32_t)w);
+    }
+}
+
+// entry / exit flags of hole vertices (graphs.py:47-58) and component stats
+__global__ void hole_flags_kernel(gpc_graph_t g, const uint8_t* __restrict__ touched,
+                                  uint32_t last_node, VertexView vw,
+                                  const uint8_t* __restrict__ node_into,
+                                  const uint8_t* __restrict__ node_outof,
+                                  uint32_t* __restrict__ parent, uint8_t* __restrict__ is_entry,
+                                  uint8_t* __restrict__ is_exit, uint32_t* __restrict__ comp_size,
+                                  uint32_t* __restrict__ comp_entry) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= vw.n) return;
+    is_entry[u] = 0;
+    is_exit[u] = 0;
+    if (!vw.alive[u]) return;
+    int t = vw.type_of[u];
+    uint32_t a = vw.node_of[u];
+    uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
+    bool entry = t == PIECE_TAIL;
+    if (!entry) {
+        for (uint32_t e = r0.z; e < r1.z; ++e) {
+            uint32_t p = g.pred[e];
+            if (!node_outof[p] && (!touched || touched[p])) { entry = true; break; }
+        }
+    }
+    bool ex = t == PIECE_HEAD;
+    if (!ex) {
+        for (uint32_t e = r0.y; e < r1.y; ++e) {
+            uint32_t s = g.succ[e];
+            if (!node_into[s] && s < last_node && (!touched || touched[s])) { ex = true; break; }
+        }
+    }
+    is_entry[u] = entry;
+    is_exit[u] = ex;
+    uint32_t root = uf_find(parent, u);
+    parent[u] = root;     // flatten (root's own entry stays root)
+    atomicAdd(&comp_size[root], 1u);
+    if (entry) comp_entry[root] = 1;
+}
+
+__global__ void hole_active_kernel(VertexView vw, const uint32_t* __restrict__ parent,
+                                   const uint32_t* __restrict__ comp_size,
+                                   const uint32_t* __restrict__ comp_entry,
+                                   const uint8_t* __restrict__ is_entry,
+                                   uint8_t* __restrict__ p_keep, uint8_t* __restrict__ active,
+                                   int32_t* __restrict__ to, int32_t* __restrict__ fr) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= vw.n) return;
+    active[u] = 0;
+    if (!vw.alive[u]) return;
+    uint32_t root = parent[u];
+    // root of u after flattening may itself have been re-parented later: chase
+    while (parent[root] != root) root = parent[root];
+    if (comp_size[root] > 36 || !comp_entry[root]) { p_keep[u] = 1; return; }   // graphs.py:254-261
+    active[u] = 1;
+    to[u] = is_entry[u] ? 0 : INF_I;
+    fr[u] = INF_I;
+}
+
+__global__ void hole_relax_kernel(gpc_graph_t g, VertexView vw, const uint32_t* __restrict__ list,
+                                  uint32_t n_list, const uint32_t* __restrict__ p_start,
+                                  const uint32_t* __restrict__ p_end,
+                                  const uint8_t* __restrict__ is_exit, int32_t* __restrict__ to,
+                                  int32_t* __restrict__ fr) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_list) return;
+    uint32_t u = list[i];
+    int t = vw.type_of[u];
+    uint32_t a = vw.node_of[u];
+    uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
+    int size = (int)(p_end[u] - p_start[u]);
+    if (t != PIECE_TAIL) {                      // pull `to` over incoming edges
+        int best = to[u];
+        for (uint32_t e = r0.z; e < r1.z; ++e) {
+            int32_t w = vw.out_vertex[g.pred[e]];
+            if (w >= 0) {
+                int d = to[w];
+                if (d < INF_I) best = min(best, d + (int)(p_end[w] - p_start[w]));
+            }
+        }
+        to[u] = best;
+    }
+    int best = fr[u];
+    if (is_exit[u]) best = min(best, size);
+    if (t != PIECE_HEAD) {
+        for (uint32_t e = r0.y; e < r1.y; ++e) {
+            int32_t w = vw.in_vertex[g.succ[e]];
+            if (w >= 0) {
+                int d = fr[w];
+                if (d < INF_I) best = min(best, d + size);
+            }
+        }
+    }
+    fr[u] = best;
+}
+
+__global__ void hole_decide_kernel(const uint32_t* __restrict__ list, uint32_t n_list,
+                                   const int32_t* __restrict__ to, const int32_t* __restrict__ fr,
+                                   int max_size, uint8_t* __restrict__ p_keep) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_list) return;
+    uint32_t u = list[i];
+    long long d = (long long)to[u] + (long long)fr[u];
+    p_keep[u] = (to[u] >= INF_I || fr[u] >= INF_I || d > max_size) ? 1 : 0;
+}
+
+__global__ void hole_internal_keep_kernel(uint32_t n, const uint8_t* __restrict__ p_type,
+                                          const uint32_t* __restrict__ p_start,
+                                          const uint32_t* __restrict__ p_end, int max_size,
+                                          uint8_t* __restrict__ p_keep) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && p_type[i] == PIECE_INTERNAL)
+        p_keep[i] = (int)(p_end[i] - p_start[i]) > max_size;
+}
+
+// kept pieces -> boundary events  (position << 1 | is_start); slot 0 is the
+// synthetic "track is True from 0" event, the optional last slot the trailing
+// False run of the input (holecleaner.py:36-48)
+__global__ void hole_events_kernel(uint32_t n, const uint8_t* __restrict__ p_keep,
+                                   const uint32_t* __restrict__ offs,
+                                   const uint32_t* __restrict__ p_start,
+                                   const uint32_t* __restrict__ p_end, uint32_t n_kept,
+                                   int trailing, uint32_t trailing_pos,
+                                   uint32_t* __restrict__ events) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        events[0] = 0u;                                       // (0, value 1)
+        if (trailing) events[1 + 2 * n_kept] = (trailing_pos << 1) | 1u;
+    }
+    if (i < n && p_keep[i]) {
+        uint32_t o = 1 + 2 * offs[i];
+        events[o] = (p_start[i] << 1) | 1u;
+        events[o + 1] = (p_end[i] << 1);
+    }
+}
+
+__global__ void bool_runs_flag_kernel(const uint32_t* __restrict__ ev, uint32_t n,
+                                      uint8_t* __restrict__ flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = ev[i];
+    bool last = (i + 1 >= n) || (ev[i + 1] >> 1) != (k >> 1);
+    bool keep = false;
+    if (last) {
+        // first element of my position group
+        uint32_t gidx = i;
+        while (gidx > 0 && (ev[gidx - 1] >> 1) == (k >> 1)) --gidx;
+        if (gidx == 0) keep = true;
+        else keep = (ev[gidx - 1] & 1u) != (k & 1u);   // value = !is_start
+    }
+    flag[i] = keep;
+}
+
+__global__ void bool_runs_emit_kernel(const uint32_t* __restrict__ ev, uint32_t n,
+                                      const uint8_t* __restrict__ flag,
+                                      const uint32_t* __restrict__ offs,
+                                      uint32_t* __restrict__ out_pos, uint8_t* __restrict__ out_val) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) {
+        out_pos[offs[i]] = ev[i] >> 1;
+        out_val[offs[i]] = (ev[i] & 1u) ? 0 : 1;
+    }
+}
+
+__global__ void compact_u32_kernel(const uint8_t* __restrict__ flag, const uint32_t* __restrict__ offs,
+                                   uint32_t n, uint32_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[offs[i]] = i;
+}
+
+// ---- max paths -----------------------------------------------------------------
+
+// score of a piece = sum of the score track over [start, end)  (maxpaths.py:175-191)
+__global__ void piece_scores_kernel(uint32_t n, const uint32_t* __restrict__ p_start,
+                                    const uint32_t* __restrict__ p_end,
+                                    const uint32_t* __restrict__ s_pos,
+                                    const double* __restrict__ s_val, uint32_t n_runs,
+                                    uint32_t track_size, double* __restrict__ score) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a = p_start[i], b = p_end[i];
+    uint32_t j = upper_bound_u32(s_pos, n_runs, a);
+    double sum = 0.0;
+    if (j > 0) --j; else { score[i] = 0.0; return; }
+    uint32_t cur = a;
+    while (cur < b && j < n_runs) {
+        uint32_t nxt = (j + 1 < n_runs) ? s_pos[j + 1] : track_size;
+        uint32_t stop = min(b, nxt);
+        if (stop > cur) sum += (double)(stop - cur) * s_val[j];
+        cur = stop;
+        ++j;
+    }
+    score[i] = sum;
+}
+
+__global__ void peak_flags_kernel(gpc_graph_t g, VertexView vw, uint8_t* __restrict__ is_entry,
+                                  uint8_t* __restrict__ is_exit) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= vw.n) return;
+    int t = vw.type_of[u];
+    uint32_t a = vw.node_of[u];
+    uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
+    bool entry = true;
+    if (t != PIECE_TAIL)
+        for (uint32_t e = r0.z; e < r1.z; ++e)
+            if (vw.out_vertex[g.pred[e]] >= 0) { entry = false; break; }
+    bool ex = true;
+    if (t != PIECE_HEAD)
+        for (uint32_t e = r0.y; e < r1.y; ++e)
+            if (vw.in_vertex[g.succ[e]] >= 0) { ex = false; break; }
+    is_entry[u] = entry;
+    is_exit[u] = ex;     // heads: always connected to the sink
+}
+
+__global__ void comp_keys_kernel(uint32_t n, uint32_t* __restrict__ parent,
+                                 unsigned long long* __restrict__ keys) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    uint32_t root = uf_find(parent, u);
+    keys[u] = ((unsigned long long)root << 32) | u;
+}
+
+__global__ void comp_heads_kernel(const unsigned long long* __restrict__ keys, uint32_t n,
+                                  uint8_t* __restrict__ head) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) head[i] = (i == 0) || (keys[i] >> 32) != (keys[i - 1] >> 32);
+}
+
+__global__ void comp_ptr_kernel(const uint8_t* __restrict__ head, const uint32_t* __restrict__ offs,
+                                uint32_t n, uint32_t n_comp, uint32_t* __restrict__ comp_ptr,
+                                const unsigned long long* __restrict__ keys,
+                                uint32_t* __restrict__ local_of_vertex,
+                                uint32_t* __restrict__ comp_of_vertex) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) comp_ptr[n_comp] = n;
+    if (i >= n) return;
+    if (head[i]) comp_ptr[offs[i]] = i;
+    uint32_t c = offs[i] + (head[i] ? 0 : -1);     // exclusive scan: heads before i
+    uint32_t u = (uint32_t)(keys[i] & 0xffffffffu);
+    comp_of_vertex[u] = c;
+    local_of_vertex[u] = i;                         // position in member order
+}
+
+struct PathOut {
+    uint32_t* path;        // [n_vertices] path of comp c at comp_ptr[c] (forward order, vertex ids)
+    uint32_t* path_len;    // [n_comp]
+    uint8_t* info;         // [n_comp] bit0 is_diff (two bindings), bit1 ambiguous
+};
+
+// One thread per component: literal replay of PosDividedLineGraph.max_paths.
+__global__ void max_paths_kernel(gpc_graph_t g, VertexView vw, uint32_t n_comp,
+                                 const uint32_t* __restrict__ comp_ptr,
+                                 const unsigned long long* __restrict__ member_keys,
+                                 const uint32_t* __restrict__ local_of_vertex,
+                                 const int32_t* __restrict__ weight, const uint8_t* __restrict__ is_entry,
+                                 const uint8_t* __restrict__ is_exit, long long* __restrict__ dist,
+                                 long long* __restrict__ dsink, int32_t* __restrict__ pred,
+                                 PathOut out) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_comp) return;
+    const uint32_t lo = comp_ptr[c], hi = comp_ptr[c + 1];
+    const int nv = (int)(hi - lo);           // vertices without the sink
+    const long long INF = (1ll << 60);
+    auto vertex_at = [&](int j) { return (uint32_t)(member_keys[lo + j] & 0xffffffffu); };
+    if (nv == 1) {                           // graphs.py:342-345
+        out.path[lo] = vertex_at(0);
+        out.path_len[c] = 1;
+        out.info[c] = 0;
+        return;
+    }
+    // Edge iteration of local vertex j in ascending target order (CSR order of
+    // the reference's sliced matrix): piece targets sorted by vertex id, sink last.
+    auto for_edges = [&](int j, auto&& fn) {
+        uint32_t u = vertex_at(j);
+        int t = vw.type_of[u];
+        if (t != PIECE_HEAD) {
+            uint32_t a = vw.node_of[u];
+            uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
+            long long last = -1;
+            while (true) {                   // selection by increasing vertex id
+                long long best = -1;
+                for (uint32_t e = r0.y; e < r1.y; ++e) {
+                    int32_t w = vw.in_vertex[g.succ[e]];
+                    if (w >= 0 && (long long)w > last && (best < 0 || (long long)w < best)) best = w;
+                }
+                if (best < 0) break;
+                fn((int)(local_of_vertex[best] - lo));
+                last = best;
+            }
+        }
+        if (is_exit[u]) fn(nv);              // sink = local index nv
+    };
+    // distance of every vertex to the sink (value only, order independent)
+    for (int j = 0; j < nv; ++j) dsink[lo + j] = INF;
+    bool changed = true;
+    while (changed) {
+        changed = false;
+        for (int j = nv - 1; j >= 0; --j) {
+            long long w = -(long long)weight[vertex_at(j)];
+            long long best = dsink[lo + j];
+            for_edges(j, [&](int tgt) {
+                long long d = tgt == nv ? 0 : dsink[lo + tgt];
+                if (d < INF && w + d < best) best = w + d;
+            });
+            if (best < dsink[lo + j]) { dsink[lo + j] = best; changed = true; }
+        }
+    }
+    // start = first entry vertex with minimal distance to the sink (np.argmin)
+    int first = -1;
+    for (int j = 0; j < nv; ++j)
+        if (is_entry[vertex_at(j)] && (first < 0 || dsink[lo + j] < dsink[lo + first])) first = j;
+    if (first < 0) first = 0;
+    // Bellman-Ford from `first`, scipy sweep order, first strict improvement wins
+    long long dist_sink = INF;
+    int pred_sink = -9999;
+    for (int j = 0; j < nv; ++j) { dist[lo + j] = INF; pred[lo + j] = -9999; }
+    dist[lo + first] = 0;
+    for (int sweep = 0; sweep < nv; ++sweep) {
+        bool any = false;
+        for (int j = 0; j < nv; ++j) {
+            long long d1 = dist[lo + j];
+            if (d1 >= INF) continue;
+            long long w = -(long long)weight[vertex_at(j)];
+            for_edges(j, [&](int tgt) {
+                if (tgt == nv) {
+                    if (d1 + w < dist_sink) { dist_sink = d1 + w; pred_sink = j; any = true; }
+                } else if (d1 + w < dist[lo + tgt]) {
+                    dist[lo + tgt] = d1 + w;
+                    pred[lo + tgt] = j;
+                    any = true;
+                }
+            });
+        }
+        if (!any) break;
+    }
+    // _backtrace (graphs.py:273-283): stops at local vertex 0 as well
+    int len = 0;
+    int cur = pred_sink;
+    while (cur > 0) {
+        out.path[lo + len++] = (uint32_t)cur;     // local ids for now, backwards
+        cur = pred[lo + cur];
+    }
+    if (len == 0 || (int)out.path[lo + len - 1] != first) out.path[lo + len++] = (uint32_t)first;
+    // SubGraphAnalyzer (subgraphanalyzer.py:11-39) on the forward path
+    long long score = 0;                          // dists[sink, sink] == 0 takes part in the min
+    long long wsum = 0;
+    for (int j = 0; j < nv; ++j) {
+        if (dsink[lo + j] < score) score = dsink[lo + j];
+        wsum += (long long)weight[vertex_at(j)];
+    }
+    int info = 0;
+    if (len > 1) {
+        if (-wsum != score) info |= 1;
+        bool amb = false;
+        for (int q = len - 1; q >= 1 && !amb; --q) {      // path[:-1] in forward order
+            int node = (int)out.path[lo + q];
+            long long reach = dist[lo + node];
+            long long w = -(long long)weight[vertex_at(node)];
+            for_edges(node, [&](int tgt) {
+                if (amb) return;
+                if (tgt != nv) {
+                    for (int z = 0; z < len; ++z)
+                        if ((int)out.path[lo + z] == tgt) return;
+                }
+                long long tail = tgt == nv ? 0 : dsink[lo + tgt];
+                if (tail < INF && reach + w + tail == score) amb = true;
+            });
+        }
+        if (amb) info |= 2;
+    }
+    // reverse into forward order and translate to vertex ids
+    for (int a = 0, b = len - 1; a < b; ++a, --b) {
+        uint32_t t = out.path[lo + a];
+        out.path[lo + a] = out.path[lo + b];
+        out.path[lo + b] = t;
+    }
+    for (int a = 0; a < len; ++a) out.path[lo + a] = vertex_at((int)out.path[lo + a]);
+    out.path_len[c] = (uint32_t)len;
+    out.info[c] = (uint8_t)info;
+}
+
+// peaks: component paths first (component order), then internal pieces
+// (piece order).  One thread per peak fills the fixed-size fields; node lists
+// go to path_nodes at path_ptr.
+__global__ void peak_lengths_kernel(uint32_t n_comp, uint32_t n_internal,
+                                    const uint32_t* __restrict__ path_len,
+                                    uint32_t* __restrict__ n_nodes) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_comp) n_nodes[i] = path_len[i];
+    else if (i < n_comp + n_internal) n_nodes[i] = 1;
+}
+
+__global__ void peaks_kernel(gpc_graph_t g, uint32_t n_comp, uint32_t n_internal,
+                             const uint32_t* __restrict__ comp_ptr, const uint32_t* __restrict__ path,
+                             const uint32_t* __restrict__ path_len, const uint8_t* __restrict__ info,
+                             const uint32_t* __restrict__ piece_of_vertex,
+                             const uint32_t* __restrict__ internal_piece,
+                             const uint32_t* __restrict__ p_node, const uint32_t* __restrict__ p_start,
+                             const uint32_t* __restrict__ p_end, const uint32_t* __restrict__ q_pos,
+                             const double* __restrict__ q_val, uint32_t n_q, int internal_id_shift,
+                             const uint32_t* __restrict__ node_ptr, int32_t* __restrict__ out_nodes,
+                             int32_t* __restrict__ out_start, int32_t* __restrict__ out_end,
+                             int32_t* __restrict__ out_length, double* __restrict__ out_score,
+                             uint8_t* __restrict__ out_info) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_comp + n_internal) return;
+    uint32_t o = node_ptr[i];
+    uint32_t len = i < n_comp ? path_len[i] : 1;
+    double best = -INFINITY;
+    long long bp = 0;
+    uint32_t first_start = 0, last_end = 0;
+    for (uint32_t k = 0; k < len; ++k) {
+        uint32_t pid = i < n_comp ? piece_of_vertex[path[comp_ptr[i] + k]]
+                                  : internal_piece[i - n_comp];
+        uint32_t v = p_node[pid];
+        uint32_t ns = node_off_at(g, v), ne = node_off_at(g, v + 1);
+        // the reference takes the whole node for inner path nodes and the piece
+        // borders only at the two ends (maxpaths.py:157-163, mindense.py:41-52)
+        uint32_t a = (k == 0) ? p_start[pid] : ns;
+        uint32_t b = (k == len - 1) ? p_end[pid] : ne;
+        if (k == 0) first_start = a - ns;
+        if (k == len - 1) last_end = b - ns;
+        int id = (int)v + g.min_node;
+        if (i >= n_comp) id = (int)v + 1 + internal_id_shift;     // maxpaths.py:34
+        out_nodes[o + k] = id;
+        bp += (long long)b - (long long)a;
+        if (b > a) {
+            uint32_t j = upper_bound_u32(q_pos, n_q, a);
+            j = j > 0 ? j - 1 : 0;
+            while (j < n_q && q_pos[j] < b) { best = fmax(best, q_val[j]); ++j; }
+        }
+    }
+    out_start[i] = (int32_t)first_start;
+    out_end[i] = (int32_t)last_end;
+    out_length[i] = (int32_t)bp;
+    out_score[i] = bp == 0 ? 0.0 : best;
+    out_info[i] = i < n_comp ? info[i] : 0;
+}
+
+__global__ void score_keys_kernel(const double* __restrict__ score, uint32_t n,
+                                  unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = ~f64_to_key(score[i]); idx[i] = i; }
+}
+
+__global__ void gather_internal_kernel(uint32_t n, const uint8_t* __restrict__ p_type,
+                                       const uint32_t* __restrict__ rank,
+                                       uint32_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && p_type[i] == PIECE_INTERNAL) out[rank[i]] = i;
+}
+__global__ void vertex_fields_kernel(uint32_t n_vertices, const uint32_t* __restrict__ piece_of_vertex,
+                                     const uint32_t* __restrict__ p_node,
+                                     const uint8_t* __restrict__ p_type,
+                                     const double* __restrict__ score, uint32_t* __restrict__ v_node,
+                                     uint8_t* __restrict__ v_type, int32_t* __restrict__ weight) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_vertices) return;
+    uint32_t pid = piece_of_vertex[u];
+    v_node[u] = p_node[pid];
+    v_type[u] = p_type[pid];
+    weight[u] = (int32_t)score[pid];     // astype("int") then int32 (graphs.py:150-151, 183)
+}
+
+static int scan_flags(const uint8_t* flag, uint32_t* offs, size_t n, unsigned long long* total_host,
+                      cudaStream_t stream) {
+    Scratch t;
+    GPC_CUDA(t.alloc(8, stream));
+    GPC_TRY(exclusive_scan<uint8_t>(flag, offs, n, t.as<unsigned long long>(), stream));
+    GPC_CUDA(cudaMemcpyAsync(total_host, t.p, 8, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    return GPC_OK;
+}
+static int scan_counts(const uint32_t* cnt, uint32_t* offs, size_t n, unsigned long long* total_host,
+                       cudaStream_t stream) {
+    Scratch t;
+    GPC_CUDA(t.alloc(8, stream));
+    GPC_TRY(exclusive_scan<uint32_t>(cnt, offs, n, t.as<unsigned long long>(), stream));
+    GPC_CUDA(cudaMemcpyAsync(total_host, t.p, 8, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    return GPC_OK;
+}
+
+}  // namespace gpc
+
+using namespace gpc;
+
+#define GRID(n) div_up((n), 256), 256, 0, stream
+
+extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
+                               uint64_t n_runs, int32_t max_size, const uint8_t* touched,
+                               uint32_t* out_pos, uint8_t* out_val, uint64_t out_capacity,
+                               uint64_t* n_out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    *n_out = 0;
+    if (n_runs == 0) { set_error("empty track"); return GPC_ERR_ARG; }
+    const uint32_t n = graph->n_nodes;
+    uint8_t v_first = 0, v_last = 0;
+    uint32_t p_last = 0;
+    GPC_CUDA(cudaMemcpyAsync(&v_first, val, 1, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaMemcpyAsync(&v_last, val + n_runs - 1, 1, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaMemcpyAsync(&p_last, pos + n_runs - 1, 4, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    const uint32_t lo = v_first ? 1 : 0;
+    uint32_t hi = (uint32_t)n_runs;
+    const int trailing = v_last == 0;
+    if (trailing) hi -= 1;
+    const uint32_t n_holes = hi > lo ? (hi - lo) / 2 : 0;
+    // last_node (holecleaner.py:27-33) as an exclusive 0-based bound on node indexes
+    uint32_t last_node = n + 1;
+    Segments sg{pos, lo, n_holes, hi, 0};
+    Scratch v0, v1, cnt, offs;
+    unsigned long long n_pieces = 0;
+    if (n_holes) {
+        GPC_CUDA(v0.alloc((size_t)n_holes * 4, stream));
+        GPC_CUDA(v1.alloc((size_t)n_holes * 4, stream));
+        GPC_CUDA(cnt.alloc((size_t)n_holes * 4, stream));
+        GPC_CUDA(offs.alloc((size_t)n_holes * 4, stream));
+        segment_nodes_kernel<<<GRID(n_holes)>>>(*graph, sg, v0.as<uint32_t>(), v1.as<uint32_t>(),
+                                                cnt.as<uint32_t>(), nullptr, nullptr);
+        GPC_LAUNCH_CHECK();
+        GPC_TRY(scan_counts(cnt.as<uint32_t>(), offs.as<uint32_t>(), n_holes, &n_pieces, stream));
+    }
+    if (trailing) {
+        // np.searchsorted(node_off, p_last): number of node offsets < p_last.  Successors with a
+        // larger 1-based index are ignored (graphs.py:55)  ->  0-based bound  s < last_node.
+        uint32_t a = 0, b = n + 1;
+        while (a < b) {
+            uint32_t mid = (a + b) >> 1, off = 0;
+            GPC_CUDA(cudaMemcpyAsync(&off, graph->node_rec + 4ull * mid, 4, cudaMemcpyDeviceToHost, stream));
+            GPC_CUDA(cudaStreamSynchronize(stream));
+            if (off < p_last) a = mid + 1; else b = mid;
+        }
+        last_node = a;
+    }
+    const uint32_t P = (uint32_t)n_pieces;
+    Scratch p_node, p_start, p_end, p_type, p_vertex, p_keep, in_v, out_v, n_into, n_outof;
+    GPC_CUDA(p_node.alloc((size_t)P * 4, stream));
+    GPC_CUDA(p_start.alloc((size_t)P * 4, stream));
+    GPC_CUDA(p_end.alloc((size_t)P * 4, stream));
+    GPC_CUDA(p_type.alloc(P, stream));
+    GPC_CUDA(p_vertex.alloc(P, stream));
+    GPC_CUDA(p_keep.alloc(P, stream));
+    unsigned long long n_kept = 0;
+    Scratch keep_offs;
+    GPC_CUDA(keep_offs.alloc((size_t)P * 4, stream));
+    if (P) {
+        GPC_CUDA(in_v.alloc((size_t)n * 4, stream));
+        GPC_CUDA(out_v.alloc((size_t)n * 4, stream));
+        GPC_CUDA(n_into.alloc(n, stream));
+        GPC_CUDA(n_outof.alloc(n, stream));
+        GPC_CUDA(cudaMemsetAsync(in_v.p, 0xff, (size_t)n * 4, stream));
+        GPC_CUDA(cudaMemsetAsync(out_v.p, 0xff, (size_t)n * 4, stream));
+        GPC_CUDA(cudaMemsetAsync(n_into.p, 0, n, stream));
+        GPC_CUDA(cudaMemsetAsync(n_outof.p, 0, n, stream));
+        hole_pieces_kernel<<<GRID(P)>>>(*graph, sg, v0.as<uint32_t>(), offs.as<uint32_t>(), P,
+                                        p_node.as<uint32_t>(), p_start.as<uint32_t>(),
+                                        p_end.as<uint32_t>(), p_type.as<uint8_t>());
+        GPC_LAUNCH_CHECK();
+        hole_vertices_kernel<<<GRID(P)>>>(*graph, touched, P, p_node.as<uint32_t>(),
+                                          p_type.as<uint8_t>(), p_vertex.as<uint8_t>(),
+                                          p_keep.as<uint8_t>(), in_v.as<int32_t>(),
+                                          out_v.as<int32_t>(), n_into.as<uint8_t>(),
+                                          n_outof.as<uint8_t>());
+        GPC_LAUNCH_CHECK();
+        hole_internal_keep_kernel<<<GRID(P)>>>(P, p_type.as<uint8_t>(), p_start.as<uint32_t>(),
+                                               p_end.as<uint32_t>(), max_size, p_keep.as<uint8_t>());
+        GPC_LAUNCH_CHECK();
+        VertexView vw{P, p_node.as<uint32_t>(), p_type.as<uint8_t>(), p_vertex.as<uint8_t>(),
+                      in_v.as<int32_t>(), out_v.as<int32_t>()};
+        Scratch parent, is_entry, is_exit, csize, centry, active, to, fr, aoffs, alist;
+        GPC_CUDA(parent.alloc((size_t)P * 4, stream));
+        GPC_CUDA(is_entry.alloc(P, stream));
+        GPC_CUDA(is_exit.alloc(P, stream));
+        GPC_CUDA(csize.alloc((size_t)P * 4, stream));
+        GPC_CUDA(centry.alloc((size_t)P * 4, stream));
+        GPC_CUDA(active.alloc(P, stream));
+        GPC_CUDA(to.alloc((size_t)P * 4, stream));
+        GPC_CUDA(fr.alloc((size_t)P * 4, stream));
+        GPC_CUDA(aoffs.alloc((size_t)P * 4, stream));
+        GPC_CUDA(cudaMemsetAsync(csize.p, 0, (size_t)P * 4, stream));
+        GPC_CUDA(cudaMemsetAsync(centry.p, 0, (size_t)P * 4, stream));
+        iota_kernel<<<GRID(P)>>>(parent.as<uint32_t>(), P);
+        GPC_LAUNCH_CHECK();
+        uf_edges_kernel<<<GRID(P)>>>(*graph, vw, parent.as<uint32_t>());
+        GPC_LAUNCH_CHECK();
+        hole_flags_kernel<<<GRID(P)>>>(*graph, touched, last_node, vw, n_into.as<uint8_t>(),
+                                       n_outof.as<uint8_t>(), parent.as<uint32_t>(),
+                                       is_entry.as<uint8_t>(), is_exit.as<uint8_t>(),
+                                       csize.as<uint32_t>(), centry.as<uint32_t>());
+        GPC_LAUNCH_CHECK();
+        hole_active_kernel<<<GRID(P)>>>(vw, parent.as<uint32_t>(), csize.as<uint32_t>(),
+                                        centry.as<uint32_t>(), is_entry.as<uint8_t>(),
+                                        p_keep.as<uint8_t>(), active.as<uint8_t>(),
+                                        to.as<int32_t>(), fr.as<int32_t>());
+        GPC_LAUNCH_CHECK();
+        unsigned long long n_active = 0;
+        GPC_TRY(scan_flags(active.as<uint8_t>(), aoffs.as<uint32_t>(), P, &n_active, stream));
+        if (n_active) {
+            GPC_CUDA(alist.alloc((size_t)n_active * 4, stream));
+            compact_u32_kernel<<<GRID(P)>>>(active.as<uint8_t>(), aoffs.as<uint32_t>(), P,
+                                            alist.as<uint32_t>());
+            GPC_LAUNCH_CHECK();
+            for (int round = 0; round < 37; ++round) {
+                hole_relax_kernel<<<GRID(n_active)>>>(*graph, vw, alist.as<uint32_t>(),
+                                                      (uint32_t)n_active, p_start.as<uint32_t>(),
+                                                      p_end.as<uint32_t>(), is_exit.as<uint8_t>(),
+                                                      to.as<int32_t>(), fr.as<int32_t>());
+                GPC_LAUNCH_CHECK();
+            }
+            hole_decide_kernel<<<GRID(n_active)>>>(alist.as<uint32_t>(), (uint32_t)n_active,
+                                                   to.as<int32_t>(), fr.as<int32_t>(), max_size,
+                                                   p_keep.as<uint8_t>());
+            GPC_LAUNCH_CHECK();
+        }
+        GPC_TRY(scan_flags(p_keep.as<uint8_t>(), keep_offs.as<uint32_t>(), P, &n_kept, stream));
+    }
+    // kept pieces -> sorted boundary events -> canonical boolean track
+    const size_t n_ev = 1 + 2 * (size_t)n_kept + (trailing ? 1 : 0);
+    if (n_ev > out_capacity) { *n_out = n_ev; return GPC_ERR_CAPACITY; }
+    Scratch ev0, ev1, flag, eoffs;
+    GPC_CUDA(ev0.alloc(n_ev * 4, stream));
+    GPC_CUDA(ev1.alloc(n_ev * 4, stream));
+    GPC_CUDA(flag.alloc(n_ev, stream));
+    GPC_CUDA(eoffs.alloc(n_ev * 4, stream));
+    hole_events_kernel<<<GRID(P ? P : 1)>>>(P, p_keep.as<uint8_t>(), keep_offs.as<uint32_t>(),
+                                            p_start.as<uint32_t>(), p_end.as<uint32_t>(),
+                                            (uint32_t)n_kept, trailing, p_last, ev0.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
+    int bits = 1;
+    while (bits < 32 && (((unsigned long long)graph->size_bp << 1) >> bits)) ++bits;
+    bool in_tmp = false;
+    GPC_TRY((radix_sort<uint32_t, false>(ev0.as<uint32_t>(), ev1.as<uint32_t>(), nullptr, nullptr,
+                                         n_ev, 0, bits, false, &in_tmp, stream)));
+    const uint32_t* ev = in_tmp ? ev1.as<uint32_t>() : ev0.as<uint32_t>();
+    bool_runs_flag_kernel<<<GRID(n_ev)>>>(ev, (uint32_t)n_ev, flag.as<uint8_t>());
+    GPC_LAUNCH_CHECK();
+    unsigned long long total = 0;
+    GPC_TRY(scan_flags(flag.as<uint8_t>(), eoffs.as<uint32_t>(), n_ev, &total, stream));
+    bool_runs_emit_kernel<<<GRID(n_ev)>>>(ev, (uint32_t)n_ev, flag.as<uint8_t>(),
+                                          eoffs.as<uint32_t>(), out_pos, out_val);
+    GPC_LAUNCH_CHECK();
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    *n_out = total;
+    return GPC_OK;
+}
+
+extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
+                             uint64_t n_runs, const uint32_t* score_pos, const double* score_val,
+                             uint64_t n_score, const uint32_t* q_pos, const double* q_val,
+                             uint64_t n_q, int32_t internal_id_shift, int32_t* peak_start,
+                             int32_t* peak_end, int32_t* peak_length, double* peak_score,
+                             uint8_t* peak_info, uint32_t* peak_node_ptr, uint64_t peak_capacity,
+                             int32_t* peak_nodes, uint64_t node_capacity, uint32_t* order,
+                             uint64_t* n_peaks, uint64_t* n_nodes_total, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    *n_peaks = 0;
+    *n_nodes_total = 0;
+    if (n_runs == 0) { set_error("empty track"); return GPC_ERR_ARG; }
+    const uint32_t n = graph->n_nodes;
+    uint8_t v_first = 0, v_last = 0;
+    GPC_CUDA(cudaMemcpyAsync(&v_first, val, 1, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaMemcpyAsync(&v_last, val + n_runs - 1, 1, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    // get_segments (maxpaths.py:43-50)
+    const uint32_t first = v_first ? 0 : 1;
+    const uint32_t n_idx = (uint32_t)n_runs - first + (v_last ? 1 : 0);
+    const uint32_t S = n_idx / 2;
+    if (S == 0) return GPC_OK;
+    Segments sg{pos, first, S, (uint32_t)n_runs, graph->size_bp};
+    Scratch v0, v1, cnt, multi, between, multi_rank, between_offs;
+    GPC_CUDA(v0.alloc((size_t)S * 4, stream));
+    GPC_CUDA(v1.alloc((size_t)S * 4, stream));
+    GPC_CUDA(cnt.alloc((size_t)S * 4, stream));
+    GPC_CUDA(multi.alloc((size_t)S * 4, stream));
+    GPC_CUDA(between.alloc((size_t)S * 4, stream));
+    GPC_CUDA(multi_rank.alloc((size_t)S * 4, stream));
+    GPC_CUDA(between_offs.alloc((size_t)S * 4, stream));
+    segment_nodes_kernel<<<GRID(S)>>>(*graph, sg, v0.as<uint32_t>(), v1.as<uint32_t>(),
+                                      cnt.as<uint32_t>(), multi.as<uint32_t>(),
+                                      between.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
+    unsigned long long n_multi = 0, n_between = 0;
+    GPC_TRY(scan_counts(multi.as<uint32_t>(), multi_rank.as<uint32_t>(), S, &n_multi, stream));
+    GPC_TRY(scan_counts(between.as<uint32_t>(), between_offs.as<uint32_t>(), S, &n_between, stream));
+    const uint32_t P = S + (uint32_t)n_multi + (uint32_t)n_between;
+    Scratch p_node, p_start, p_end, p_type, f_t, f_w, f_h, f_i, r_t, r_w, r_h, r_i;
+    GPC_CUDA(p_node.alloc((size_t)P * 4, stream));
+    GPC_CUDA(p_start.alloc((size_t)P * 4, stream));
+    GPC_CUDA(p_end.alloc((size_t)P * 4, stream));
+    GPC_CUDA(p_type.alloc(P, stream));
+    peak_pieces_kernel<<<GRID(S)>>>(*graph, sg, v0.as<uint32_t>(), v1.as<uint32_t>(),
+                                    multi_rank.as<uint32_t>(), between_offs.as<uint32_t>(),
+                                    (uint32_t)n_multi, p_node.as<uint32_t>(), p_start.as<uint32_t>(),
+                                    p_end.as<uint32_t>(), p_type.as<uint8_t>());
+    GPC_LAUNCH_CHECK();
+    for (Scratch* s : {&f_t, &f_w, &f_h, &f_i, &r_t, &r_w, &r_h, &r_i})
+        GPC_CUDA(s->alloc((size_t)P * 4, stream));
+    class_flags_kernel<<<GRID(P)>>>(P, p_type.as<uint8_t>(), f_t.as<uint32_t>(), f_w.as<uint32_t>(),
+                                    f_h.as<uint32_t>(), f_i.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
+    unsigned long long n_t = 0, n_w = 0, n_h = 0, n_i = 0;
+    GPC_TRY(scan_counts(f_t.as<uint32_t>(), r_t.as<uint32_t>(), P, &n_t, stream));
+    GPC_TRY(scan_counts(f_w.as<uint32_t>(), r_w.as<uint32_t>(), P, &n_w, stream));
+    GPC_TRY(scan_counts(f_h.as<uint32_t>(), r_h.as<uint32_t>(), P, &n_h, stream));
+    GPC_TRY(scan_counts(f_i.as<uint32_t>(), r_i.as<uint32_t>(), P, &n_i, stream));
+    const uint32_t V = (uint32_t)(n_t + n_w + n_h);
+    // internal pieces in piece order
+    Scratch internal_piece;
+    GPC_CUDA(internal_piece.alloc((size_t)(n_i ? n_i : 1) * 4, stream));
+    // vertex tables
+    Scratch vertex_of_piece, piece_of_vertex, in_v, out_v, v_node, v_type;
+    GPC_CUDA(vertex_of_piece.alloc((size_t)P * 4, stream));
+    GPC_CUDA(piece_of_vertex.alloc((size_t)(V ? V : 1) * 4, stream));
+    GPC_CUDA(in_v.alloc((size_t)n * 4, stream));
+    GPC_CUDA(out_v.alloc((size_t)n * 4, stream));
+    GPC_CUDA(cudaMemsetAsync(in_v.p, 0xff, (size_t)n * 4, stream));
+    GPC_CUDA(cudaMemsetAsync(out_v.p, 0xff, (size_t)n * 4, stream));
+    peak_vertices_kernel<<<GRID(P)>>>(P, p_node.as<uint32_t>(), p_type.as<uint8_t>(),
+                                      r_t.as<uint32_t>(), r_w.as<uint32_t>(), r_h.as<uint32_t>(),
+                                      (uint32_t)n_t, (uint32_t)n_w, vertex_of_piece.as<int32_t>(),
+                                      piece_of_vertex.as<uint32_t>(), in_v.as<int32_t>(),
+                                      out_v.as<int32_t>());
+    GPC_LAUNCH_CHECK();
+    gather_internal_kernel<<<GRID(P)>>>(P, p_type.as<uint8_t>(), r_i.as<uint32_t>(),
+                                        internal_piece.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
+    // piece scores -> int32 weights per vertex (graphs.py:150-151, 183)
+    Scratch score, weight;
+    GPC_CUDA(score.alloc((size_t)P * 8, stream));
+    piece_scores_kernel<<<GRID(P)>>>(P, p_start.as<uint32_t>(), p_end.as<uint32_t>(), score_pos,
+                                     score_val, (uint32_t)n_score, graph->size_bp, score.as<double>());
+    GPC_LAUNCH_CHECK();
+    Scratch parent, is_entry, is_exit, keys0, keys1, head, hoffs, comp_ptr, local_of, comp_of;
+    Scratch dist, dsink, pred, path, path_len, info;
+    unsigned long long n_comp = 0;
+    if (V) {
+        GPC_CUDA(v_node.alloc((size_t)V * 4, stream));
+        GPC_CUDA(v_type.alloc(V, stream));
+        GPC_CUDA(weight.alloc((size_t)V * 4, stream));
+        vertex_fields_kernel<<<GRID(V)>>>(V, piece_of_vertex.as<uint32_t>(), p_node.as<uint32_t>(),
+                                          p_type.as<uint8_t>(), score.as<double>(),
+                                          v_node.as<uint32_t>(), v_type.as<uint8_t>(),
+                                          weight.as<int32_t>());
+        GPC_LAUNCH_CHECK();
+        VertexView vw{V, v_node.as<uint32_t>(), v_type.as<uint8_t>(), nullptr, in_v.as<int32_t>(),
+                      out_v.as<int32_t>()};
+        GPC_CUDA(parent.alloc((size_t)V * 4, stream));
+        GPC_CUDA(is_entry.alloc(V, stream));
+        GPC_CUDA(is_exit.alloc(V, stream));
+        GPC_CUDA(keys0.alloc((size_t)V * 8, stream));
+        GPC_CUDA(keys1.alloc((size_t)V * 8, stream));
+        GPC_CUDA(head.alloc(V, stream));
+        GPC_CUDA(hoffs.alloc((size_t)V * 4, stream));
+        GPC_CUDA(local_of.alloc((size_t)V * 4, stream));
+        GPC_CUDA(comp_of.alloc((size_t)V * 4, stream));
+        iota_kernel<<<GRID(V)>>>(parent.as<uint32_t>(), V);
+        GPC_LAUNCH_CHECK();
+        uf_edges_kernel<<<GRID(V)>>>(*graph, vw, parent.as<uint32_t>());
+        GPC_LAUNCH_CHECK();
+        peak_flags_kernel<<<GRID(V)>>>(*graph, vw, is_entry.as<uint8_t>(), is_exit.as<uint8_t>());
+        GPC_LAUNCH_CHECK();
+        comp_keys_kernel<<<GRID(V)>>>(V, parent.as<uint32_t>(), keys0.as<unsigned long long>());
+        GPC_LAUNCH_CHECK();
+        bool in_tmp = false;
+        GPC_TRY((radix_sort<unsigned long long, false>(keys0.as<unsigned long long>(),
+                                                       keys1.as<unsigned long long>(), nullptr,
+                                                       nullptr, V, 0, 64, true, &in_tmp, stream)));
+        const unsigned long long* mk = in_tmp ? keys1.as<unsigned long long>() : keys0.as<unsigned long long>();
+        comp_heads_kernel<<<GRID(V)>>>(mk, V, head.as<uint8_t>());
+        GPC_LAUNCH_CHECK();
+        GPC_TRY(scan_flags(head.as<uint8_t>(), hoffs.as<uint32_t>(), V, &n_comp, stream));
+        GPC_CUDA(comp_ptr.alloc((size_t)(n_comp + 1) * 4, stream));
+        comp_ptr_kernel<<<GRID(V)>>>(head.as<uint8_t>(), hoffs.as<uint32_t>(), V, (uint32_t)n_comp,
+                                     comp_ptr.as<uint32_t>(), mk, local_of.as<uint32_t>(),
+                                     comp_of.as<uint32_t>());
+        GPC_LAUNCH_CHECK();
+        GPC_CUDA(dist.alloc((size_t)V * 8, stream));
+        GPC_CUDA(dsink.alloc((size_t)V * 8, stream));
+        GPC_CUDA(pred.alloc((size_t)V * 4, stream));
+        GPC_CUDA(path.alloc((size_t)V * 4, stream));
+        GPC_CUDA(path_len.alloc((size_t)n_comp * 4, stream));
+        GPC_CUDA(info.alloc((size_t)n_comp, stream));
+        PathOut po{path.as<uint32_t>(), path_len.as<uint32_t>(), info.as<uint8_t>()};
+        max_paths_kernel<<<div_up(n_comp, 64), 64, 0, stream>>>(
+            *graph, vw, (uint32_t)n_comp, comp_ptr.as<uint32_t>(), mk, local_of.as<uint32_t>(),
+            weight.as<int32_t>(), is_entry.as<uint8_t>(), is_exit.as<uint8_t>(),
+            dist.as<long long>(), dsink.as<long long>(), pred.as<int32_t>(), po);
+        GPC_LAUNCH_CHECK();
+    }
+    const uint32_t n_pk = (uint32_t)n_comp + (uint32_t)n_i;
+    *n_peaks = n_pk;
+    if (n_pk == 0) return GPC_OK;
+    if (n_pk > peak_capacity) return GPC_ERR_CAPACITY;
+    Scratch nn;
+    GPC_CUDA(nn.alloc((size_t)n_pk * 4, stream));
+    peak_lengths_kernel<<<GRID(n_pk)>>>((uint32_t)n_comp, (uint32_t)n_i, path_len.as<uint32_t>(),
+                                        nn.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
+    unsigned long long total_nodes = 0;
+    GPC_TRY(scan_counts(nn.as<uint32_t>(), peak_node_ptr, n_pk, &total_nodes, stream));
+    *n_nodes_total = total_nodes;
+    if (total_nodes > node_capacity) return GPC_ERR_CAPACITY;
+    uint32_t tn = (uint32_t)total_nodes;
+    GPC_CUDA(cudaMemcpyAsync(peak_node_ptr + n_pk, &tn, 4, cudaMemcpyHostToDevice, stream));
+    peaks_kernel<<<GRID(n_pk)>>>(*graph, (uint32_t)n_comp, (uint32_t)n_i, comp_ptr.as<uint32_t>(),
+                                 path.as<uint32_t>(), path_len.as<uint32_t>(), info.as<uint8_t>(),
+                                 piece_of_vertex.as<uint32_t>(), internal_piece.as<uint32_t>(),
+                                 p_node.as<uint32_t>(), p_start.as<uint32_t>(), p_end.as<uint32_t>(),
+                                 q_pos, q_val, (uint32_t)n_q, internal_id_shift, peak_node_ptr,
+                                 peak_nodes, peak_start, peak_end, peak_length, peak_score,
+                                 peak_info);
+    GPC_LAUNCH_CHECK();
+    // stable order by score, descending (callpeaks.py:204-205)
+    Scratch sk0, sk1, si0, si1;
+    GPC_CUDA(sk0.alloc((size_t)n_pk * 8, stream));
+    GPC_CUDA(sk1.alloc((size_t)n_pk * 8, stream));
+    GPC_CUDA(si0.alloc((size_t)n_pk * 4, stream));
+    GPC_CUDA(si1.alloc((size_t)n_pk * 4, stream));
+    score_keys_kernel<<<GRID(n_pk)>>>(peak_score, n_pk, sk0.as<unsigned long long>(), si0.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
+    bool in_tmp = false;
+    GPC_TRY((radix_sort<unsigned long long, true>(sk0.as<unsigned long long>(),
+                                                  sk1.as<unsigned long long>(), si0.as<uint32_t>(),
+                                                  si1.as<uint32_t>(), n_pk, 0, 64, true, &in_tmp,
+                                                  stream)));
+    GPC_CUDA(cudaMemcpyAsync(order, in_tmp ? si1.p : si0.p, (size_t)n_pk * 4,
+                             cudaMemcpyDeviceToDevice, stream));
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    return GPC_OK;
+}
+

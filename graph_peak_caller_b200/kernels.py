@@ -191,3 +191,51 @@ def threshold(pos, q, cutoff):
     _lib.check(lib.gpc_threshold(ptr(pos), ptr(q), n, float(cutoff), ptr(op), ptr(ov),
                                  ctypes.byref(n_out), stream_ptr()))
     return op[:n_out.value], ov[:n_out.value]
+
+
+def clean_holes(dgraph, pos, val, max_size, touched):
+    """H2-H4.  Returns (pos int32[Uh], value uint8[Uh])."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    cap = 2 * pos.numel() + 1024
+    while True:
+        op, ov = empty(cap, torch.int32), empty(cap, torch.uint8)
+        n_out = _u64()
+        status = lib.gpc_clean_holes(ctypes.byref(dgraph.c), ptr(pos), ptr(val), pos.numel(),
+                                     int(max_size), ptr(touched), ptr(op), ptr(ov), cap,
+                                     ctypes.byref(n_out), stream_ptr())
+        if status == _lib.GPC_ERR_CAPACITY:
+            cap = int(n_out.value) + 16
+            continue
+        _lib.check(status)
+        return op[:n_out.value], ov[:n_out.value]
+
+
+def max_paths(dgraph, pos, val, score_pos, score_val, q_pos, q_val, internal_id_shift):
+    """M1-M3.  Returns a dict of CUDA tensors (see include/gpc_b200.h)."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    pcap, ncap = max(1024, pos.numel()), max(4096, 4 * pos.numel())
+    while True:
+        t = dict(start=empty(pcap, torch.int32), end=empty(pcap, torch.int32),
+                 length=empty(pcap, torch.int32), score=empty(pcap, torch.float64),
+                 info=empty(pcap, torch.uint8), node_ptr=empty(pcap + 1, torch.int32),
+                 nodes=empty(ncap, torch.int32), order=empty(pcap, torch.int32))
+        n_peaks, n_nodes = _u64(), _u64()
+        status = lib.gpc_max_paths(
+            ctypes.byref(dgraph.c), ptr(pos), ptr(val), pos.numel(), ptr(score_pos),
+            ptr(score_val), score_pos.numel(), ptr(q_pos), ptr(q_val), q_pos.numel(),
+            int(internal_id_shift), ptr(t["start"]), ptr(t["end"]), ptr(t["length"]),
+            ptr(t["score"]), ptr(t["info"]), ptr(t["node_ptr"]), pcap, ptr(t["nodes"]), ncap,
+            ptr(t["order"]), ctypes.byref(n_peaks), ctypes.byref(n_nodes), stream_ptr())
+        if status == _lib.GPC_ERR_CAPACITY:
+            pcap = max(pcap, int(n_peaks.value) + 16)
+            ncap = max(ncap, int(n_nodes.value) + 16)
+            continue
+        _lib.check(status)
+        n, m = int(n_peaks.value), int(n_nodes.value)
+        out = {k: v[:n] for k, v in t.items() if k not in ("node_ptr", "nodes")}
+        out["node_ptr"] = t["node_ptr"][:n + 1]
+        out["nodes"] = t["nodes"][:m]
+        out["n"] = n
+        return out

@@ -178,6 +178,50 @@ int gpc_qvalues_apply(const double* p, uint64_t n_runs, const double* table_p,
 int gpc_threshold(const uint32_t* pos, const double* q, uint64_t n_runs, double cutoff,
                   uint32_t* out_pos, uint8_t* out_val, uint64_t* n_out, void* stream);
 
+/* ---- H2-H4  HolesCleaner(graph, track, max_size, touched).run()
+ *            (postprocess/holecleaner.py:9-109, segmentanalyzer.py:5-94,
+ *             graphs.py:14-267) -------------------------------------------
+ * Input: canonical boolean track (pos strictly increasing from 0, val
+ * alternating).  Fills every hole (False run between peaks) whose shortest
+ * way through the graph is <= max_size (the read length); holes on untouched
+ * nodes, on graph sources/sinks, in line-graph components of more than 36
+ * pieces or without an entry piece are never filled.  touched: n_nodes bytes
+ * or NULL (every node touched).  Output: canonical boolean track; capacity
+ * 2 * (number of hole pieces) + 2 is always enough, GPC_ERR_CAPACITY reports
+ * the needed size in *n_out. */
+int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
+                    uint64_t n_runs, int32_t max_size, const uint8_t* touched, uint32_t* out_pos,
+                    uint8_t* out_val, uint64_t out_capacity, uint64_t* n_out, void* stream);
+
+/* ---- M1-M3  SparseMaxPaths(track, graph, score_pileup).run()
+ *            (postprocess/maxpaths.py:11-191, graphs.py:270-355,
+ *             subgraphanalyzer.py:4-39) and the scoring tail of
+ *            CallPeaksFromQvalues.__get_max_paths (callpeaks.py:186-212,
+ *            mindense.py:25-59) --------------------------------------------
+ * Input: cleaned boolean track; score track (position, float64 value; the
+ * direct pileup, or the q-values when q_values_max_path); q-value track for
+ * the final score (max q over the path).
+ * Output, one entry per peak in the reference's order (line-graph components
+ * first, then single-node peaks):
+ *   peak_start / peak_end   offsets in the first / last node
+ *   peak_length             bases covered (obg Interval.length())
+ *   peak_score              max q over the path (0 for empty peaks)
+ *   peak_info               bit0 is_diff, bit1 is_ambiguous
+ *   peak_node_ptr[n+1], peak_nodes   node ids of each path
+ *   order                   peak indexes stably sorted by score, descending
+ * internal_id_shift: single-node peaks get id (1-based node index +
+ * internal_id_shift); min_node-1 is the sane value, -(min_node-1) is what the
+ * reference computes (maxpaths.py:34).
+ * GPC_ERR_CAPACITY: *n_peaks / *n_nodes_total hold the needed capacities. */
+int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
+                  uint64_t n_runs, const uint32_t* score_pos, const double* score_val,
+                  uint64_t n_score, const uint32_t* q_pos, const double* q_val, uint64_t n_q,
+                  int32_t internal_id_shift, int32_t* peak_start, int32_t* peak_end,
+                  int32_t* peak_length, double* peak_score, uint8_t* peak_info,
+                  uint32_t* peak_node_ptr, uint64_t peak_capacity, int32_t* peak_nodes,
+                  uint64_t node_capacity, uint32_t* order, uint64_t* n_peaks,
+                  uint64_t* n_nodes_total, void* stream);
+
 /* ---- building blocks (np.argsort / np.cumsum of the reference's
  *      sparsediffs.py, exported for the host side and the parity tests) ------
  * LSD radix sorts over bits [begin_bit, end_bit); keys/vals ping-pong with
