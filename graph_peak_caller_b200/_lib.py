@@ -45,7 +45,7 @@ _SIGNATURES = {
                                  c_void_p, c_void_p],
     "gpc_control_backproject": [P(GpcGraph), c_void_p, c_void_p, c_void_p, u64, f64, f64,
                                 c_void_p, c_void_p, u64, P(u64), c_void_p],
-    "gpc_pvalues": [c_void_p, c_void_p, u64, f64, c_void_p, c_void_p, u64, c_void_p,
+    "gpc_pvalues": [c_void_p, c_void_p, u64, f64, c_void_p, c_void_p, u64, f64, c_void_p,
                     c_void_p, P(u64), c_void_p],
     "gpc_ptable_local": [c_void_p, c_void_p, u64, u32, c_void_p, c_void_p, u64, P(u64),
                          c_void_p],
@@ -54,10 +54,12 @@ _SIGNATURES = {
     "gpc_threshold": [c_void_p, c_void_p, u64, f64, c_void_p, c_void_p, P(u64), c_void_p],
     "gpc_clean_holes": [P(GpcGraph), c_void_p, c_void_p, u64, i32, c_void_p, c_void_p,
                         c_void_p, u64, P(u64), c_void_p],
-    "gpc_max_paths": [P(GpcGraph), c_void_p, c_void_p, u64, c_void_p, c_void_p, u64,
+    "gpc_max_paths": [P(GpcGraph), c_void_p, c_void_p, u64, c_void_p, c_void_p, c_void_p, u64,
                       c_void_p, c_void_p, u64, i32, c_void_p, c_void_p, c_void_p,
                       c_void_p, c_void_p, c_void_p, u64, c_void_p, u64, c_void_p, P(u64),
                       P(u64), c_void_p],
+    "gpc_linear_map_from_graph_host": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       u64, c_void_p, c_void_p],
     "gpc_sort_u32": [c_void_p, c_void_p, u64, i32, i32, P(i32), c_void_p],
     "gpc_sort_u64_pairs": [c_void_p, c_void_p, c_void_p, c_void_p, u64, i32, i32,
                            P(i32), c_void_p],

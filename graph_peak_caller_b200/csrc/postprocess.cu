@@ -448,10 +448,11 @@ __global__ void compact_u32_kernel(const uint8_t* __restrict__ flag, const uint3
 // ---- max paths -----------------------------------------------------------------
 
 // score of a piece = sum of the score track over [start, end)  (maxpaths.py:175-191)
+template <typename ValT>
 __global__ void piece_scores_kernel(uint32_t n, const uint32_t* __restrict__ p_start,
                                     const uint32_t* __restrict__ p_end,
                                     const uint32_t* __restrict__ s_pos,
-                                    const double* __restrict__ s_val, uint32_t n_runs,
+                                    const ValT* __restrict__ s_val, uint32_t n_runs,
                                     uint32_t track_size, double* __restrict__ score) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -463,7 +464,7 @@ __global__ void piece_scores_kernel(uint32_t n, const uint32_t* __restrict__ p_s
     while (cur < b && j < n_runs) {
         uint32_t nxt = (j + 1 < n_runs) ? s_pos[j + 1] : track_size;
         uint32_t stop = min(b, nxt);
-        if (stop > cur) sum += (double)(stop - cur) * s_val[j];
+        if (stop > cur) sum += (double)(stop - cur) * (double)s_val[j];
         cur = stop;
         ++j;
     }
@@ -924,7 +925,8 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
 
 extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
                              uint64_t n_runs, const uint32_t* score_pos, const double* score_val,
-                             uint64_t n_score, const uint32_t* q_pos, const double* q_val,
+                             const int32_t* score_val_i32, uint64_t n_score,
+                             const uint32_t* q_pos, const double* q_val,
                              uint64_t n_q, int32_t internal_id_shift, int32_t* peak_start,
                              int32_t* peak_end, int32_t* peak_length, double* peak_score,
                              uint8_t* peak_info, uint32_t* peak_node_ptr, uint64_t peak_capacity,
@@ -1005,8 +1007,14 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     // piece scores -> int32 weights per vertex (graphs.py:150-151, 183)
     Scratch score, weight;
     GPC_CUDA(score.alloc((size_t)P * 8, stream));
-    piece_scores_kernel<<<GRID(P)>>>(P, p_start.as<uint32_t>(), p_end.as<uint32_t>(), score_pos,
-                                     score_val, (uint32_t)n_score, graph->size_bp, score.as<double>());
+    if (score_val_i32)
+        piece_scores_kernel<int32_t><<<GRID(P)>>>(P, p_start.as<uint32_t>(), p_end.as<uint32_t>(),
+                                                  score_pos, score_val_i32, (uint32_t)n_score,
+                                                  graph->size_bp, score.as<double>());
+    else
+        piece_scores_kernel<double><<<GRID(P)>>>(P, p_start.as<uint32_t>(), p_end.as<uint32_t>(),
+                                                 score_pos, score_val, (uint32_t)n_score,
+                                                 graph->size_bp, score.as<double>());
     GPC_LAUNCH_CHECK();
     Scratch parent, is_entry, is_exit, keys0, keys1, head, hoffs, comp_ptr, local_of, comp_of;
     Scratch dist, dsink, pred, path, path_len, info;

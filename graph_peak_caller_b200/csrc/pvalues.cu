@@ -28,7 +28,8 @@ constexpr int PV_TILE = PV_THREADS * PV_ITEMS;
 __global__ void __launch_bounds__(PV_THREADS)
 pvalues_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sval, unsigned ns,
                double sample_scale, const uint32_t* __restrict__ cpos,
-               const double* __restrict__ cval, unsigned nc, uint32_t* __restrict__ out_pos,
+               const double* __restrict__ cval, unsigned nc, double control_scale,
+               uint32_t* __restrict__ out_pos,
                double* __restrict__ out_p, unsigned long long* __restrict__ status,
                unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_count) {
     __shared__ unsigned s_slot;
@@ -62,16 +63,16 @@ pvalues_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
         double prev_p = 0.0;
         if (have_prev) {
             double k = ib > 0 ? (double)sval[ib - 1] : 0.0;
-            double lam = jb > 0 ? cval[jb - 1] : 0.0;
+            double lam = jb > 0 ? __dmul_rn(cval[jb - 1], control_scale) : 0.0;
             prev_p = neglog10_poisson_sf(k == 0.0 ? 0.0 : k * sample_scale, lam);
         }
         double k_cur = i > 0 ? (double)sval[i - 1] : 0.0;
-        double lam_cur = j > 0 ? cval[j - 1] : 0.0;
+        double lam_cur = j > 0 ? __dmul_rn(cval[j - 1], control_scale) : 0.0;
         for (unsigned d = d0; d < d1; ++d) {
             bool take_s = i < ns && (j >= nc || spos[i] <= cpos[j]);
             uint32_t pos;
             if (take_s) { pos = spos[i]; k_cur = (double)sval[i]; ++i; }
-            else { pos = cpos[j]; lam_cur = cval[j]; ++j; }
+            else { pos = cpos[j]; lam_cur = __dmul_rn(cval[j], control_scale); ++j; }
             bool more = i < ns || j < nc;
             uint32_t next_pos = 0;
             if (more) {
@@ -209,7 +210,6 @@ qtable_kernel(const unsigned long long* __restrict__ sorted_keys,
         unsigned long long tot_c;
         unsigned long long ex_c = block_excl_sum<unsigned long long>(c, s_cnt, tot_c);
         bool last = valid && (i + 1 >= n || sorted_keys[i + 1] != key);
-        bool first = valid && (i == 0 || sorted_keys[i - 1] != key);
         // bp with strictly larger p = running count before the first entry of this p
         // (computed at the group's first element, consumed at its last)
         double p = valid ? key_to_f64(~key) : 0.0;
@@ -226,7 +226,6 @@ qtable_kernel(const unsigned long long* __restrict__ sorted_keys,
             q = p + log10(1.0 + (double)before) - log_n;
             if (g == 0) q = fmax(0.0, q);
         }
-        (void)first;
         // inclusive running minimum over the block
         double m = q;
 #pragma unroll
@@ -298,8 +297,8 @@ using namespace gpc;
 
 extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val, uint64_t n_sample,
                            double sample_scale, const uint32_t* control_pos,
-                           const double* control_val, uint64_t n_control, uint32_t* out_pos,
-                           double* out_p, uint64_t* n_out, void* stream_) {
+                           const double* control_val, uint64_t n_control, double control_scale,
+                           uint32_t* out_pos, double* out_p, uint64_t* n_out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     *n_out = 0;
     uint64_t total = n_sample + n_control;
@@ -315,7 +314,8 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
     unsigned long long* status = count + 4;
     pvalues_kernel<<<tiles, PV_THREADS, 0, stream>>>(sample_pos, sample_val, (unsigned)n_sample,
                                                     sample_scale, control_pos, control_val,
-                                                    (unsigned)n_control, out_pos, out_p, status,
+                                                    (unsigned)n_control, control_scale, out_pos,
+                                                    out_p, status,
                                                     ticket, count);
     GPC_LAUNCH_CHECK();
     unsigned long long h = 0;

@@ -129,7 +129,7 @@ def control_backproject(dgraph, touched, bp, val, min_value, value_scale=1.0):
         return pos[:n_out.value], lam[:n_out.value]
 
 
-def pvalues(spos, sval, sample_scale, cpos, cval):
+def pvalues(spos, sval, sample_scale, cpos, cval, control_scale=1.0):
     """P1.  Returns (pos int32[Up], p float64[Up])."""
     torch = torch_cuda()
     lib = _lib.load()
@@ -137,7 +137,8 @@ def pvalues(spos, sval, sample_scale, cpos, cval):
     pos, p = empty(max(cap, 1), torch.int32), empty(max(cap, 1), torch.float64)
     n_out = _u64()
     _lib.check(lib.gpc_pvalues(ptr(spos), ptr(sval), spos.numel(), float(sample_scale),
-                               ptr(cpos), ptr(cval), cpos.numel(), ptr(pos), ptr(p),
+                               ptr(cpos), ptr(cval), cpos.numel(), float(control_scale),
+                               ptr(pos), ptr(p),
                                ctypes.byref(n_out), stream_ptr()))
     return pos[:n_out.value], p[:n_out.value]
 
@@ -224,7 +225,9 @@ def max_paths(dgraph, pos, val, score_pos, score_val, q_pos, q_val, internal_id_
         n_peaks, n_nodes = _u64(), _u64()
         status = lib.gpc_max_paths(
             ctypes.byref(dgraph.c), ptr(pos), ptr(val), pos.numel(), ptr(score_pos),
-            ptr(score_val), score_pos.numel(), ptr(q_pos), ptr(q_val), q_pos.numel(),
+            ptr(score_val) if score_val.dtype == torch.float64 else None,
+            ptr(score_val) if score_val.dtype == torch.int32 else None,
+            score_pos.numel(), ptr(q_pos), ptr(q_val), q_pos.numel(),
             int(internal_id_shift), ptr(t["start"]), ptr(t["end"]), ptr(t["length"]),
             ptr(t["score"]), ptr(t["info"]), ptr(t["node_ptr"]), pcap, ptr(t["nodes"]), ncap,
             ptr(t["order"]), ctypes.byref(n_peaks), ctypes.byref(n_nodes), stream_ptr())

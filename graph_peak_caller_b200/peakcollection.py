@@ -1,0 +1,97 @@
+"""``Peak`` / ``PeakCollection`` output types of the reference
+(graph_peak_caller/peakcollection.py:10-66, 97-98): an interval with a score,
+written one JSON object per line."""
+import json
+
+from .reads import Interval
+
+
+class Peak(Interval):
+    def __init__(self, start_position, end_position, region_paths=None, graph=None,
+                 direction=None, score=0, unique_id=None, chromosome=None):
+        super().__init__(start_position, end_position, region_paths, graph, direction)
+        self.score = score
+        self.unique_id = unique_id
+        self.info = (0, 0)
+        self.chromosome = chromosome
+        self._length = None
+
+    def __str__(self):
+        return super().__repr__() + " [%s]" % self.score
+
+    __repr__ = __str__
+
+    def length(self):
+        if self._length is not None:
+            return self._length
+        return super().length()
+
+    @classmethod
+    def from_interval_and_score(cls, interval, score):
+        return cls(interval.start_position, interval.end_position, interval.region_paths,
+                   interval.graph, interval.direction, score)
+
+    def set_score(self, score):
+        assert isinstance(score, float), "Score %s is invalid, type %s" % (score, type(score))
+        self.score = score
+
+    def to_file_line(self):
+        return json.dumps({"start": int(self.start_position.offset),
+                           "end": int(self.end_position.offset),
+                           "region_paths": [int(r) for r in self.region_paths],
+                           "direction": int(self.direction),
+                           "average_q_value": float(self.score),
+                           "unique_id": str(self.unique_id),
+                           "is_ambigous": int(self.info[1]),
+                           "is_diff": int(self.info[0]),
+                           "chromosome": self.chromosome})
+
+    @classmethod
+    def from_file_line(cls, line, graph=None):
+        o = json.loads(line)
+        obj = cls(o["start"], o["end"], o["region_paths"], direction=o["direction"],
+                  graph=graph, score=o["average_q_value"], unique_id=o.get("unique_id"))
+        if "chromosome" in o:
+            obj.chromosome = o["chromosome"]
+        obj.info = (o["is_diff"], o["is_ambigous"])
+        return obj
+
+    def get_subinterval(self, start_offset, end_offset):
+        sub = Interval.get_subinterval(self, start_offset, end_offset)
+        peak = Peak(sub.start_position, sub.end_position, sub.region_paths, graph=self.graph,
+                    score=self.score, unique_id=self.unique_id)
+        peak.info = self.info
+        return peak
+
+
+class IntervalCollection:
+    """obg ``IntervalCollection``: a list of intervals with JSON-lines I/O."""
+    interval_class = Interval
+
+    def __init__(self, intervals):
+        self.intervals = intervals
+
+    def __iter__(self):
+        return iter(self.intervals)
+
+    def __len__(self):
+        return len(self.intervals)
+
+    def to_file(self, file_name, text_file=True):
+        with open(file_name, "w") as f:
+            for interval in self.intervals:
+                f.write(interval.to_file_line() + "\n")
+
+    to_text_file = to_file
+
+    @classmethod
+    def from_file(cls, file_name, text_file=True, graph=None):
+        with open(file_name) as f:
+            return cls([cls.interval_class.from_file_line(line, graph=graph)
+                        for line in f if line.strip()])
+
+    create_list_from_file = from_file
+
+
+class PeakCollection(IntervalCollection):
+    interval_class = Peak

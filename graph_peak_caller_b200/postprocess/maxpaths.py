@@ -1,0 +1,57 @@
+"""``SparseMaxPaths`` with the reference's contract
+(graph_peak_caller/postprocess/maxpaths.py:11-65) over gpc_max_paths.
+
+``run()`` returns ``(peaks, subgraphs)`` like the reference; the sub-graph
+matrices the reference hands to its Reporter are an analysis by-product and
+are not produced here (the second element is a list of ``None``)."""
+from .. import kernels, pipeline
+from ..device import device_graph
+from ..graph import Graph
+from ..peakcollection import Peak
+
+# maxpaths.py:34 subtracts (min_node - 1) from the 1-based node index of a
+# single-node peak instead of adding it.  For min_node == 1 both agree; for
+# other graphs the reference's ids point outside the graph (and its own
+# scoring step then fails), so the default here is the real node id.
+REPLICATE_INTERNAL_ID_QUIRK = False
+
+
+class SparseMaxPaths:
+    def __init__(self, sparse_values, graph, score_pileup, variant_maps=None):
+        if variant_maps is not None:
+            raise NotImplementedError("variant maps are outside this path")
+        self._graph = Graph.from_obg(graph)
+        self._sparse_values = sparse_values
+        self._score_pileup = score_pileup
+        self._q_values = None
+
+    def set_q_values(self, q_values):
+        """Track used for the final score (max q over the path)."""
+        self._q_values = q_values
+
+    def run_raw(self):
+        torch = kernels.torch_cuda()
+        pos, val = self._sparse_values.device_arrays()
+        if val.dtype != torch.uint8:
+            val = (val != 0).to(torch.uint8)
+        spos, sval = self._score_pileup.device_arrays()
+        if sval.dtype not in (torch.float64, torch.int32):
+            sval = sval.to(torch.float64)
+        q = self._q_values if self._q_values is not None else self._score_pileup
+        qpos, qval = q.device_arrays(torch.float64)
+        shift = self._graph.min_node - 1
+        return kernels.max_paths(device_graph(self._graph), pos, val, spos, sval, qpos, qval,
+                                 -shift if REPLICATE_INTERNAL_ID_QUIRK else shift)
+
+    def run(self):
+        raw = self.run_raw()
+        ps = pipeline.PeakSet(raw, 0)
+        self.order = ps.order          # stable order by score, descending (device sort)
+        peaks = []
+        for i in range(ps.n_all):
+            start, end, nodes, info, score = ps.peak(i)
+            peak = Peak(start, end, nodes, graph=self._graph, score=score)
+            peak.info = info
+            peak._length = int(ps.length[i])
+            peaks.append(peak)
+        return peaks, [None] * len(peaks)

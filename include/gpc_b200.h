@@ -143,12 +143,14 @@ int gpc_control_backproject(const gpc_graph_t* graph, const uint8_t* touched, co
  * Merges sample runs and control entries; per distinct position
  * p = -log10 PoissonSF(count * sample_scale, lambda) with the reference's
  * clamp rules (count 0 -> 0, underflow -> 1000); canonical output.
- * sample_scale: 1/ratio when ratio > 1, else 1 (scale_tracks).
+ * sample_scale: 1/ratio when ratio > 1, else 1 (scale_tracks); control_scale
+ * multiplies every lambda (ratio when < 1 and not already applied by
+ * gpc_control_backproject, else 1).
  * Capacity of out_pos / out_p: n_sample + n_control. */
 int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val, uint64_t n_sample,
                 double sample_scale, const uint32_t* control_pos, const double* control_val,
-                uint64_t n_control, uint32_t* out_pos, double* out_p, uint64_t* n_out,
-                void* stream);
+                uint64_t n_control, double control_scale, uint32_t* out_pos, double* out_p,
+                uint64_t* n_out, void* stream);
 
 /* ---- Q1  PToQValuesMapper.__get_sub_counts + _from_subcounts, first half
  *          (sparsepvalues.py:50-74) ------------------------------------------
@@ -198,8 +200,9 @@ int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t
  *             subgraphanalyzer.py:4-39) and the scoring tail of
  *            CallPeaksFromQvalues.__get_max_paths (callpeaks.py:186-212,
  *            mindense.py:25-59) --------------------------------------------
- * Input: cleaned boolean track; score track (position, float64 value; the
- * direct pileup, or the q-values when q_values_max_path); q-value track for
+ * Input: cleaned boolean track; score track (position + values, either
+ * float64 in score_val or int32 in score_val_i32, the other NULL: the direct
+ * pileup, or the q-values when q_values_max_path); q-value track for
  * the final score (max q over the path).
  * Output, one entry per peak in the reference's order (line-graph components
  * first, then single-node peaks):
@@ -215,12 +218,24 @@ int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t
  * GPC_ERR_CAPACITY: *n_peaks / *n_nodes_total hold the needed capacities. */
 int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
                   uint64_t n_runs, const uint32_t* score_pos, const double* score_val,
-                  uint64_t n_score, const uint32_t* q_pos, const double* q_val, uint64_t n_q,
+                  const int32_t* score_val_i32, uint64_t n_score, const uint32_t* q_pos,
+                  const double* q_val, uint64_t n_q,
                   int32_t internal_id_shift, int32_t* peak_start, int32_t* peak_end,
                   int32_t* peak_length, double* peak_score, uint8_t* peak_info,
                   uint32_t* peak_node_ptr, uint64_t peak_capacity, int32_t* peak_nodes,
                   uint64_t node_capacity, uint32_t* order, uint64_t* n_peaks,
                   uint64_t* n_nodes_total, void* stream);
+
+/* ---- C1  LinearMap.from_graph / find_starts / find_ends
+ *          (control/linearmap.py:102-154) ------------------------------------
+ * HOST function on HOST arrays (one-off preprocessing that the reference
+ * caches in *_linear_map.npz): starts[v] = longest distance from the source
+ * to the start of node v; ends[v] = linear length - longest distance from
+ * the end of v to the sink. */
+int gpc_linear_map_from_graph_host(const int64_t* node_len, const int64_t* succ_ptr,
+                                   const int32_t* succ, const int64_t* pred_ptr,
+                                   const int32_t* pred, uint64_t n_nodes, double* starts,
+                                   double* ends);
 
 /* ---- building blocks (np.argsort / np.cumsum of the reference's
  *      sparsediffs.py, exported for the host side and the parity tests) ------
