@@ -71,7 +71,8 @@ _lib = None
 
 def exported_symbols():
     """Every entry point include/gpc_b200.h declares."""
-    return ["gpc_last_error_string", "gpc_version_string"] + sorted(_SIGNATURES)
+    return ["gpc_last_error_string", "gpc_version_string", "gpc_launch_count",
+            "gpc_profile_enable", "gpc_profile_report"] + sorted(_SIGNATURES)
 
 
 def load():
@@ -85,6 +86,11 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.gpc_last_error_string.restype = ctypes.c_char_p
     lib.gpc_version_string.restype = ctypes.c_char_p
+    lib.gpc_launch_count.restype = ctypes.c_uint64
+    lib.gpc_profile_enable.argtypes = [ctypes.c_int]
+    lib.gpc_profile_enable.restype = None
+    lib.gpc_profile_report.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
+    lib.gpc_profile_report.restype = ctypes.c_uint64
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -109,3 +115,25 @@ def check(status):
     if status == GPC_ERR_ARG:
         raise Exception(text)
     raise GpcError(status, text)
+
+
+def launch_count():
+    return int(load().gpc_launch_count())
+
+
+def profile_enable(on=True):
+    load().gpc_profile_enable(1 if on else 0)
+
+
+def profile_report():
+    """{kernel name: (calls, total milliseconds, algorithmic bytes)} since the
+    last report."""
+    lib = load()
+    need = int(lib.gpc_profile_report(None, 0))
+    buf = ctypes.create_string_buffer(need + 1)
+    lib.gpc_profile_report(buf, need + 1)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, calls, ms, nbytes = line.split()
+        out[name] = (int(calls), float(ms), float(nbytes))
+    return out

@@ -28,7 +28,21 @@ void set_error(const char* fmt, ...);
         if (s__ != GPC_OK) return s__;                                         \
     } while (0)
 
-#define GPC_LAUNCH_CHECK() GPC_CUDA(cudaGetLastError())
+// Every kernel launch is followed by GPC_LAUNCH_CHECK(); a launch preceded by
+// GPC_PROF("name") is timed with a CUDA event pair on its own stream while
+// profiling is enabled (gpc_profile_enable), and counted always.
+void prof_begin(const char* name, cudaStream_t stream, double algorithmic_bytes = 0.0);
+void prof_end();
+void prof_add_bytes(const char* name, double algorithmic_bytes);
+#define GPC_PROF(name) gpc::prof_begin(name, stream)
+// same, with the ALGORITHMIC bytes of this launch (compulsory input + output,
+// DESIGN.md "roofline accounting") for the achieved-bandwidth figure
+#define GPC_PROF_BYTES(name, bytes) gpc::prof_begin(name, stream, (double)(bytes))
+#define GPC_LAUNCH_CHECK()                                                     \
+    do {                                                                       \
+        gpc::prof_end();                                                       \
+        GPC_CUDA(cudaGetLastError());                                          \
+    } while (0)
 
 // Stream-ordered scratch that frees itself (cudaMallocAsync pool).
 struct Scratch {

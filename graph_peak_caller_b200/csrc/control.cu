@@ -402,6 +402,7 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
     GPC_CUDA(small.alloc(64, stream));
     GPC_CUDA(cudaMemsetAsync(small.p, 0, 64, stream));
     int* err = small.as<int>();
+    GPC_PROF_BYTES("project_events", 12.0 * n_reads + 12.0 * n_ev);
     project_events_kernel<<<div_up(n_reads, 256), 256, 0, stream>>>(
         *graph, start_node, start_off, read_index, (unsigned)n_reads, wp,
         k0.as<unsigned long long>(), t0.as<uint32_t>(), x_out, err);
@@ -425,6 +426,7 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
     LinAgg* prefixes = aggs + tiles;
     unsigned long long* st2 = reinterpret_cast<unsigned long long*>(prefixes + tiles);
     unsigned* st1 = reinterpret_cast<unsigned*>(st2 + tiles);
+    GPC_PROF_BYTES("linear_track", 12.0 * n_ev);
     linear_track_kernel<<<tiles, LIN_THREADS, 0, stream>>>(keys, tags, (unsigned)n_ev, wp, out_pos,
                                                           out_val, aggs, prefixes, st1, st2,
                                                           ticket, count);
@@ -439,6 +441,7 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
         return herr;
     }
     *n_out = h;
+    prof_add_bytes("linear_track", 16.0 * (double)h);
     return GPC_OK;
 }
 
@@ -459,6 +462,7 @@ extern "C" int gpc_control_backproject(const gpc_graph_t* graph, const uint8_t* 
     GPC_CUDA(count.alloc((size_t)n * 4, stream));
     GPC_CUDA(offs.alloc((size_t)n * 4, stream));
     GPC_CUDA(total.alloc(8, stream));
+    GPC_PROF("backproject_count");
     backproject_count_kernel<<<div_up(n, 256), 256, 0, stream>>>(
         *graph, touched, bp, (unsigned)n_bp, first.as<uint32_t>(), count.as<uint32_t>());
     GPC_LAUNCH_CHECK();
@@ -469,6 +473,7 @@ extern "C" int gpc_control_backproject(const gpc_graph_t* graph, const uint8_t* 
     GPC_CUDA(cudaStreamSynchronize(stream));
     *n_out = h;
     if (h > out_capacity) return GPC_ERR_CAPACITY;
+    GPC_PROF("backproject_emit");
     backproject_emit_kernel<<<div_up(n, 256), 256, 0, stream>>>(
         *graph, touched, bp, val, first.as<uint32_t>(), count.as<uint32_t>(),
         offs.as<uint32_t>(), min_value, value_scale, out_pos, out_val);

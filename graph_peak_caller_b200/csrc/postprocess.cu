@@ -794,6 +794,7 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
         GPC_CUDA(v1.alloc((size_t)n_holes * 4, stream));
         GPC_CUDA(cnt.alloc((size_t)n_holes * 4, stream));
         GPC_CUDA(offs.alloc((size_t)n_holes * 4, stream));
+        GPC_PROF("segment_nodes");
         segment_nodes_kernel<<<GRID(n_holes)>>>(*graph, sg, v0.as<uint32_t>(), v1.as<uint32_t>(),
                                                 cnt.as<uint32_t>(), nullptr, nullptr);
         GPC_LAUNCH_CHECK();
@@ -831,16 +832,19 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
         GPC_CUDA(cudaMemsetAsync(out_v.p, 0xff, (size_t)n * 4, stream));
         GPC_CUDA(cudaMemsetAsync(n_into.p, 0, n, stream));
         GPC_CUDA(cudaMemsetAsync(n_outof.p, 0, n, stream));
+        GPC_PROF("hole_pieces");
         hole_pieces_kernel<<<GRID(P)>>>(*graph, sg, v0.as<uint32_t>(), offs.as<uint32_t>(), P,
                                         p_node.as<uint32_t>(), p_start.as<uint32_t>(),
                                         p_end.as<uint32_t>(), p_type.as<uint8_t>());
         GPC_LAUNCH_CHECK();
+        GPC_PROF("hole_vertices");
         hole_vertices_kernel<<<GRID(P)>>>(*graph, touched, P, p_node.as<uint32_t>(),
                                           p_type.as<uint8_t>(), p_vertex.as<uint8_t>(),
                                           p_keep.as<uint8_t>(), in_v.as<int32_t>(),
                                           out_v.as<int32_t>(), n_into.as<uint8_t>(),
                                           n_outof.as<uint8_t>());
         GPC_LAUNCH_CHECK();
+        GPC_PROF("hole_internal_keep");
         hole_internal_keep_kernel<<<GRID(P)>>>(P, p_type.as<uint8_t>(), p_start.as<uint32_t>(),
                                                p_end.as<uint32_t>(), max_size, p_keep.as<uint8_t>());
         GPC_LAUNCH_CHECK();
@@ -858,15 +862,19 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
         GPC_CUDA(aoffs.alloc((size_t)P * 4, stream));
         GPC_CUDA(cudaMemsetAsync(csize.p, 0, (size_t)P * 4, stream));
         GPC_CUDA(cudaMemsetAsync(centry.p, 0, (size_t)P * 4, stream));
+        GPC_PROF("iota");
         iota_kernel<<<GRID(P)>>>(parent.as<uint32_t>(), P);
         GPC_LAUNCH_CHECK();
+        GPC_PROF("uf_edges");
         uf_edges_kernel<<<GRID(P)>>>(*graph, vw, parent.as<uint32_t>());
         GPC_LAUNCH_CHECK();
+        GPC_PROF("hole_flags");
         hole_flags_kernel<<<GRID(P)>>>(*graph, touched, last_node, vw, n_into.as<uint8_t>(),
                                        n_outof.as<uint8_t>(), parent.as<uint32_t>(),
                                        is_entry.as<uint8_t>(), is_exit.as<uint8_t>(),
                                        csize.as<uint32_t>(), centry.as<uint32_t>());
         GPC_LAUNCH_CHECK();
+        GPC_PROF("hole_active");
         hole_active_kernel<<<GRID(P)>>>(vw, parent.as<uint32_t>(), csize.as<uint32_t>(),
                                         centry.as<uint32_t>(), is_entry.as<uint8_t>(),
                                         p_keep.as<uint8_t>(), active.as<uint8_t>(),
@@ -876,16 +884,19 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
         GPC_TRY(scan_flags(active.as<uint8_t>(), aoffs.as<uint32_t>(), P, &n_active, stream));
         if (n_active) {
             GPC_CUDA(alist.alloc((size_t)n_active * 4, stream));
+            GPC_PROF("compact_u32");
             compact_u32_kernel<<<GRID(P)>>>(active.as<uint8_t>(), aoffs.as<uint32_t>(), P,
                                             alist.as<uint32_t>());
             GPC_LAUNCH_CHECK();
             for (int round = 0; round < 37; ++round) {
+                GPC_PROF("hole_relax");
                 hole_relax_kernel<<<GRID(n_active)>>>(*graph, vw, alist.as<uint32_t>(),
                                                       (uint32_t)n_active, p_start.as<uint32_t>(),
                                                       p_end.as<uint32_t>(), is_exit.as<uint8_t>(),
                                                       to.as<int32_t>(), fr.as<int32_t>());
                 GPC_LAUNCH_CHECK();
             }
+            GPC_PROF("hole_decide");
             hole_decide_kernel<<<GRID(n_active)>>>(alist.as<uint32_t>(), (uint32_t)n_active,
                                                    to.as<int32_t>(), fr.as<int32_t>(), max_size,
                                                    p_keep.as<uint8_t>());
@@ -895,12 +906,12 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
     }
     // kept pieces -> sorted boundary events -> canonical boolean track
     const size_t n_ev = 1 + 2 * (size_t)n_kept + (trailing ? 1 : 0);
-    if (n_ev > out_capacity) { *n_out = n_ev; return GPC_ERR_CAPACITY; }
     Scratch ev0, ev1, flag, eoffs;
     GPC_CUDA(ev0.alloc(n_ev * 4, stream));
     GPC_CUDA(ev1.alloc(n_ev * 4, stream));
     GPC_CUDA(flag.alloc(n_ev, stream));
     GPC_CUDA(eoffs.alloc(n_ev * 4, stream));
+    GPC_PROF("hole_events");
     hole_events_kernel<<<GRID(P ? P : 1)>>>(P, p_keep.as<uint8_t>(), keep_offs.as<uint32_t>(),
                                             p_start.as<uint32_t>(), p_end.as<uint32_t>(),
                                             (uint32_t)n_kept, trailing, p_last, ev0.as<uint32_t>());
@@ -911,10 +922,14 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
     GPC_TRY((radix_sort<uint32_t, false>(ev0.as<uint32_t>(), ev1.as<uint32_t>(), nullptr, nullptr,
                                          n_ev, 0, bits, false, &in_tmp, stream)));
     const uint32_t* ev = in_tmp ? ev1.as<uint32_t>() : ev0.as<uint32_t>();
+    GPC_PROF("bool_runs_flag");
     bool_runs_flag_kernel<<<GRID(n_ev)>>>(ev, (uint32_t)n_ev, flag.as<uint8_t>());
     GPC_LAUNCH_CHECK();
     unsigned long long total = 0;
     GPC_TRY(scan_flags(flag.as<uint8_t>(), eoffs.as<uint32_t>(), n_ev, &total, stream));
+    // cleaning only fills holes, so the result never has more runs than the input (+2)
+    if (total > out_capacity) { *n_out = total; return GPC_ERR_CAPACITY; }
+    GPC_PROF("bool_runs_emit");
     bool_runs_emit_kernel<<<GRID(n_ev)>>>(ev, (uint32_t)n_ev, flag.as<uint8_t>(),
                                           eoffs.as<uint32_t>(), out_pos, out_val);
     GPC_LAUNCH_CHECK();
@@ -955,6 +970,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     GPC_CUDA(between.alloc((size_t)S * 4, stream));
     GPC_CUDA(multi_rank.alloc((size_t)S * 4, stream));
     GPC_CUDA(between_offs.alloc((size_t)S * 4, stream));
+    GPC_PROF("segment_nodes");
     segment_nodes_kernel<<<GRID(S)>>>(*graph, sg, v0.as<uint32_t>(), v1.as<uint32_t>(),
                                       cnt.as<uint32_t>(), multi.as<uint32_t>(),
                                       between.as<uint32_t>());
@@ -968,6 +984,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     GPC_CUDA(p_start.alloc((size_t)P * 4, stream));
     GPC_CUDA(p_end.alloc((size_t)P * 4, stream));
     GPC_CUDA(p_type.alloc(P, stream));
+    GPC_PROF("peak_pieces");
     peak_pieces_kernel<<<GRID(S)>>>(*graph, sg, v0.as<uint32_t>(), v1.as<uint32_t>(),
                                     multi_rank.as<uint32_t>(), between_offs.as<uint32_t>(),
                                     (uint32_t)n_multi, p_node.as<uint32_t>(), p_start.as<uint32_t>(),
@@ -975,6 +992,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     GPC_LAUNCH_CHECK();
     for (Scratch* s : {&f_t, &f_w, &f_h, &f_i, &r_t, &r_w, &r_h, &r_i})
         GPC_CUDA(s->alloc((size_t)P * 4, stream));
+    GPC_PROF("class_flags");
     class_flags_kernel<<<GRID(P)>>>(P, p_type.as<uint8_t>(), f_t.as<uint32_t>(), f_w.as<uint32_t>(),
                                     f_h.as<uint32_t>(), f_i.as<uint32_t>());
     GPC_LAUNCH_CHECK();
@@ -995,18 +1013,21 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     GPC_CUDA(out_v.alloc((size_t)n * 4, stream));
     GPC_CUDA(cudaMemsetAsync(in_v.p, 0xff, (size_t)n * 4, stream));
     GPC_CUDA(cudaMemsetAsync(out_v.p, 0xff, (size_t)n * 4, stream));
+    GPC_PROF("peak_vertices");
     peak_vertices_kernel<<<GRID(P)>>>(P, p_node.as<uint32_t>(), p_type.as<uint8_t>(),
                                       r_t.as<uint32_t>(), r_w.as<uint32_t>(), r_h.as<uint32_t>(),
                                       (uint32_t)n_t, (uint32_t)n_w, vertex_of_piece.as<int32_t>(),
                                       piece_of_vertex.as<uint32_t>(), in_v.as<int32_t>(),
                                       out_v.as<int32_t>());
     GPC_LAUNCH_CHECK();
+    GPC_PROF("gather_internal");
     gather_internal_kernel<<<GRID(P)>>>(P, p_type.as<uint8_t>(), r_i.as<uint32_t>(),
                                         internal_piece.as<uint32_t>());
     GPC_LAUNCH_CHECK();
     // piece scores -> int32 weights per vertex (graphs.py:150-151, 183)
     Scratch score, weight;
     GPC_CUDA(score.alloc((size_t)P * 8, stream));
+    GPC_PROF("piece_scores");
     if (score_val_i32)
         piece_scores_kernel<int32_t><<<GRID(P)>>>(P, p_start.as<uint32_t>(), p_end.as<uint32_t>(),
                                                   score_pos, score_val_i32, (uint32_t)n_score,
@@ -1023,6 +1044,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
         GPC_CUDA(v_node.alloc((size_t)V * 4, stream));
         GPC_CUDA(v_type.alloc(V, stream));
         GPC_CUDA(weight.alloc((size_t)V * 4, stream));
+        GPC_PROF("vertex_fields");
         vertex_fields_kernel<<<GRID(V)>>>(V, piece_of_vertex.as<uint32_t>(), p_node.as<uint32_t>(),
                                           p_type.as<uint8_t>(), score.as<double>(),
                                           v_node.as<uint32_t>(), v_type.as<uint8_t>(),
@@ -1039,12 +1061,16 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
         GPC_CUDA(hoffs.alloc((size_t)V * 4, stream));
         GPC_CUDA(local_of.alloc((size_t)V * 4, stream));
         GPC_CUDA(comp_of.alloc((size_t)V * 4, stream));
+        GPC_PROF("iota");
         iota_kernel<<<GRID(V)>>>(parent.as<uint32_t>(), V);
         GPC_LAUNCH_CHECK();
+        GPC_PROF("uf_edges");
         uf_edges_kernel<<<GRID(V)>>>(*graph, vw, parent.as<uint32_t>());
         GPC_LAUNCH_CHECK();
+        GPC_PROF("peak_flags");
         peak_flags_kernel<<<GRID(V)>>>(*graph, vw, is_entry.as<uint8_t>(), is_exit.as<uint8_t>());
         GPC_LAUNCH_CHECK();
+        GPC_PROF("comp_keys");
         comp_keys_kernel<<<GRID(V)>>>(V, parent.as<uint32_t>(), keys0.as<unsigned long long>());
         GPC_LAUNCH_CHECK();
         bool in_tmp = false;
@@ -1052,10 +1078,12 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
                                                        keys1.as<unsigned long long>(), nullptr,
                                                        nullptr, V, 0, 64, true, &in_tmp, stream)));
         const unsigned long long* mk = in_tmp ? keys1.as<unsigned long long>() : keys0.as<unsigned long long>();
+        GPC_PROF("comp_heads");
         comp_heads_kernel<<<GRID(V)>>>(mk, V, head.as<uint8_t>());
         GPC_LAUNCH_CHECK();
         GPC_TRY(scan_flags(head.as<uint8_t>(), hoffs.as<uint32_t>(), V, &n_comp, stream));
         GPC_CUDA(comp_ptr.alloc((size_t)(n_comp + 1) * 4, stream));
+        GPC_PROF("comp_ptr");
         comp_ptr_kernel<<<GRID(V)>>>(head.as<uint8_t>(), hoffs.as<uint32_t>(), V, (uint32_t)n_comp,
                                      comp_ptr.as<uint32_t>(), mk, local_of.as<uint32_t>(),
                                      comp_of.as<uint32_t>());
@@ -1067,6 +1095,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
         GPC_CUDA(path_len.alloc((size_t)n_comp * 4, stream));
         GPC_CUDA(info.alloc((size_t)n_comp, stream));
         PathOut po{path.as<uint32_t>(), path_len.as<uint32_t>(), info.as<uint8_t>()};
+        GPC_PROF("max_paths");
         max_paths_kernel<<<div_up(n_comp, 64), 64, 0, stream>>>(
             *graph, vw, (uint32_t)n_comp, comp_ptr.as<uint32_t>(), mk, local_of.as<uint32_t>(),
             weight.as<int32_t>(), is_entry.as<uint8_t>(), is_exit.as<uint8_t>(),
@@ -1079,6 +1108,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     if (n_pk > peak_capacity) return GPC_ERR_CAPACITY;
     Scratch nn;
     GPC_CUDA(nn.alloc((size_t)n_pk * 4, stream));
+    GPC_PROF("peak_lengths");
     peak_lengths_kernel<<<GRID(n_pk)>>>((uint32_t)n_comp, (uint32_t)n_i, path_len.as<uint32_t>(),
                                         nn.as<uint32_t>());
     GPC_LAUNCH_CHECK();
@@ -1088,6 +1118,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     if (total_nodes > node_capacity) return GPC_ERR_CAPACITY;
     uint32_t tn = (uint32_t)total_nodes;
     GPC_CUDA(cudaMemcpyAsync(peak_node_ptr + n_pk, &tn, 4, cudaMemcpyHostToDevice, stream));
+    GPC_PROF("peaks");
     peaks_kernel<<<GRID(n_pk)>>>(*graph, (uint32_t)n_comp, (uint32_t)n_i, comp_ptr.as<uint32_t>(),
                                  path.as<uint32_t>(), path_len.as<uint32_t>(), info.as<uint8_t>(),
                                  piece_of_vertex.as<uint32_t>(), internal_piece.as<uint32_t>(),
@@ -1102,6 +1133,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     GPC_CUDA(sk1.alloc((size_t)n_pk * 8, stream));
     GPC_CUDA(si0.alloc((size_t)n_pk * 4, stream));
     GPC_CUDA(si1.alloc((size_t)n_pk * 4, stream));
+    GPC_PROF("score_keys");
     score_keys_kernel<<<GRID(n_pk)>>>(peak_score, n_pk, sk0.as<unsigned long long>(), si0.as<uint32_t>());
     GPC_LAUNCH_CHECK();
     bool in_tmp = false;

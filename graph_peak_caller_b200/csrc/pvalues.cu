@@ -312,6 +312,7 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
     unsigned long long* count = sc.as<unsigned long long>();
     unsigned* ticket = reinterpret_cast<unsigned*>(count + 1);
     unsigned long long* status = count + 4;
+    GPC_PROF_BYTES("pvalues", 8.0 * n_sample + 12.0 * n_control);
     pvalues_kernel<<<tiles, PV_THREADS, 0, stream>>>(sample_pos, sample_val, (unsigned)n_sample,
                                                     sample_scale, control_pos, control_val,
                                                     (unsigned)n_control, control_scale, out_pos,
@@ -322,6 +323,7 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
     GPC_CUDA(cudaMemcpyAsync(&h, count, 8, cudaMemcpyDeviceToHost, stream));
     GPC_CUDA(cudaStreamSynchronize(stream));
     *n_out = h;
+    prof_add_bytes("pvalues", 12.0 * (double)h);
     return GPC_OK;
 }
 
@@ -342,6 +344,7 @@ extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n
         GPC_CUDA(cudaMemsetAsync(keys.p, 0, cap * 8, stream));
         GPC_CUDA(cudaMemsetAsync(counts.p, 0, cap * 8, stream));
         GPC_CUDA(cudaMemsetAsync(fail.p, 0, 8, stream));
+        GPC_PROF("ptable_insert");
         ptable_insert_kernel<<<div_up(n, 256), 256, 0, stream>>>(
             pos, p, n, track_size, keys.as<unsigned long long>(), counts.as<unsigned long long>(),
             (unsigned)(cap - 1), fail.as<int>());
@@ -349,6 +352,7 @@ extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n
         GPC_CUDA(flag.alloc(cap, stream));
         GPC_CUDA(offs.alloc(cap * 4, stream));
         GPC_CUDA(total.alloc(8, stream));
+        GPC_PROF("ptable_flag");
         ptable_flag_kernel<<<div_up(cap, 256), 256, 0, stream>>>(keys.as<unsigned long long>(),
                                                                 (unsigned)cap, flag.as<uint8_t>());
         GPC_LAUNCH_CHECK();
@@ -366,6 +370,7 @@ extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n
         }
         *n_distinct = h;
         if (h > table_capacity) return GPC_ERR_CAPACITY;
+        GPC_PROF("ptable_compact");
         ptable_compact_kernel<<<div_up(cap, 256), 256, 0, stream>>>(
             keys.as<unsigned long long>(), counts.as<unsigned long long>(), offs.as<uint32_t>(),
             (unsigned)cap, table_p, reinterpret_cast<unsigned long long*>(table_count));
@@ -388,6 +393,7 @@ extern "C" int gpc_qtable_build(const double* table_p, const uint64_t* table_cou
     GPC_CUDA(i0.alloc((size_t)n * 4, stream));
     GPC_CUDA(i1.alloc((size_t)n * 4, stream));
     GPC_CUDA(cnt.alloc(8, stream));
+    GPC_PROF("qtable_keys");
     qtable_keys_kernel<<<div_up(n, 256), 256, 0, stream>>>(table_p, n, k0.as<unsigned long long>(),
                                                           i0.as<uint32_t>());
     GPC_LAUNCH_CHECK();
@@ -396,6 +402,7 @@ extern "C" int gpc_qtable_build(const double* table_p, const uint64_t* table_cou
                                                   k1.as<unsigned long long>(), i0.as<uint32_t>(),
                                                   i1.as<uint32_t>(), n, 0, 64, true, &in_tmp,
                                                   stream)));
+    GPC_PROF("qtable");
     qtable_kernel<<<1, QT_THREADS, 0, stream>>>(
         in_tmp ? k1.as<unsigned long long>() : k0.as<unsigned long long>(),
         in_tmp ? i1.as<uint32_t>() : i0.as<uint32_t>(),
@@ -417,6 +424,7 @@ extern "C" int gpc_qvalues_apply(const double* p, uint64_t n_runs, const double*
     Scratch miss;
     GPC_CUDA(miss.alloc(8, stream));
     GPC_CUDA(cudaMemsetAsync(miss.p, 0, 8, stream));
+    GPC_PROF("qvalues_apply");
     qvalues_apply_kernel<<<div_up(n_runs, 256), 256, 0, stream>>>(
         p, (unsigned)n_runs, table_p, table_q, (unsigned)n_table, out_q, miss.as<int>());
     GPC_LAUNCH_CHECK();
@@ -437,10 +445,12 @@ extern "C" int gpc_threshold(const uint32_t* pos, const double* q, uint64_t n_ru
     GPC_CUDA(flag.alloc(n, stream));
     GPC_CUDA(offs.alloc((size_t)n * 4, stream));
     GPC_CUDA(total.alloc(8, stream));
+    GPC_PROF("threshold_flag");
     threshold_flag_kernel<<<div_up(n, 256), 256, 0, stream>>>(q, n, cutoff, flag.as<uint8_t>());
     GPC_LAUNCH_CHECK();
     GPC_TRY(exclusive_scan<uint8_t>(flag.as<uint8_t>(), offs.as<uint32_t>(), n,
                                     total.as<unsigned long long>(), stream));
+    GPC_PROF("threshold_emit");
     threshold_emit_kernel<<<div_up(n, 256), 256, 0, stream>>>(pos, q, n, cutoff, flag.as<uint8_t>(),
                                                              offs.as<uint32_t>(), out_pos, out_val);
     GPC_LAUNCH_CHECK();

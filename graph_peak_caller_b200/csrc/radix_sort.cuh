@@ -202,8 +202,10 @@ int radix_sort(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, s
     unsigned* status = hist + head;
     GPC_CUDA(cudaMemsetAsync(sc.p, 0, (head + per_pass * n_passes) * sizeof(unsigned), stream));
     unsigned hist_blocks = min(div_up(n, RS_THREADS * 8), (unsigned)(sm_count() * 8));
+    GPC_PROF_BYTES("rs_hist", (double)n * sizeof(KeyT));
     rs_hist_kernel<KeyT><<<hist_blocks, RS_THREADS, 0, stream>>>(keys, n, begin_bit, n_passes, hist);
     GPC_LAUNCH_CHECK();
+    GPC_PROF("rs_scan_hist");
     rs_scan_hist_kernel<<<n_passes, RS_RADIX, 0, stream>>>(hist, (unsigned)n, trivial);
     GPC_LAUNCH_CHECK();
     unsigned h_trivial[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -218,6 +220,7 @@ int radix_sort(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, s
         KeyT* kout = in_tmp ? keys : keys_tmp;
         const uint32_t* vin = in_tmp ? vals_tmp : vals;
         uint32_t* vout = in_tmp ? vals : vals_tmp;
+        GPC_PROF_BYTES("rs_onesweep", 2.0 * n * (sizeof(KeyT) + (HAS_VALUE ? 4 : 0)));
         rs_onesweep_kernel<KeyT, HAS_VALUE><<<tiles, RS_THREADS, 0, stream>>>(
             kin, kout, vin, vout, (unsigned)n, begin_bit + p * RS_BITS,
             hist + (size_t)p * RS_RADIX, status + per_pass * p, ticket + p);

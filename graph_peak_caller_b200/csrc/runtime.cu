@@ -1,6 +1,10 @@
 // Error text, version string, device properties.
 #include <stdarg.h>
 
+#include <map>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 
 namespace gpc {
@@ -12,6 +16,40 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
+}
+
+// ---- launch counter and per-kernel event timing -------------------------------
+struct ProfRec { const char* name; cudaEvent_t a, b; double bytes; };
+static std::map<std::string, double> g_extra_bytes;
+static std::vector<ProfRec> g_recs;
+static bool g_prof_on = false;
+static unsigned long long g_launches = 0;
+static const char* g_pending = nullptr;
+static cudaStream_t g_pending_stream = nullptr;
+static cudaEvent_t g_pending_a = nullptr;
+static double g_pending_bytes = 0.0;
+
+void prof_add_bytes(const char* name, double bytes) {
+    if (g_prof_on) g_extra_bytes[name] += bytes;
+}
+
+void prof_begin(const char* name, cudaStream_t stream, double bytes) {
+    if (!g_prof_on) return;
+    g_pending = name;
+    g_pending_bytes = bytes;
+    g_pending_stream = stream;
+    cudaEventCreate(&g_pending_a);
+    cudaEventRecord(g_pending_a, stream);
+}
+
+void prof_end() {
+    ++g_launches;
+    if (!g_pending) return;
+    ProfRec r{g_pending, g_pending_a, nullptr, g_pending_bytes};
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.b, g_pending_stream);
+    g_recs.push_back(r);
+    g_pending = nullptr;
 }
 
 int sm_count() {
@@ -55,4 +93,46 @@ extern "C" int gpc_linear_map_from_graph_host(const int64_t* node_len, const int
     double length = ends[0] + (double)node_len[0];               // linearmap.py:153
     for (uint64_t v = 0; v < n_nodes; ++v) ends[v] = length - ends[v];
     return GPC_OK;
+}
+
+extern "C" void gpc_profile_enable(int on) { gpc::g_prof_on = on != 0; }
+extern "C" uint64_t gpc_launch_count(void) { return gpc::g_launches; }
+
+// Writes "name calls total_ms algorithmic_bytes\n" lines for every kernel timed since the last
+// report (synchronises the device) and clears the records.  Returns the
+// number of bytes needed (excluding the terminating 0).
+extern "C" uint64_t gpc_profile_report(char* buf, uint64_t capacity) {
+    cudaDeviceSynchronize();
+    struct Acc { unsigned long long calls = 0; double ms = 0, bytes = 0; };
+    std::map<std::string, Acc> acc;
+    for (auto& r : gpc::g_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto& e = acc[r.name];
+        e.calls += 1;
+        e.ms += ms;
+        e.bytes += r.bytes;
+    }
+    for (auto& kv : gpc::g_extra_bytes) acc[kv.first].bytes += kv.second;
+    if (buf && capacity) {       // a size query (buf == NULL) keeps the records
+        for (auto& r : gpc::g_recs) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        gpc::g_recs.clear();
+        gpc::g_extra_bytes.clear();
+    }
+    std::string out;
+    char line[256];
+    for (auto& kv : acc) {
+        snprintf(line, sizeof(line), "%s %llu %.6f %.0f\n", kv.first.c_str(), kv.second.calls,
+                 kv.second.ms, kv.second.bytes);
+        out += line;
+    }
+    if (buf && capacity) {
+        size_t nbytes = out.size() < capacity - 1 ? out.size() : capacity - 1;
+        memcpy(buf, out.data(), nbytes);
+        buf[nbytes] = 0;
+    }
+    return out.size();
 }

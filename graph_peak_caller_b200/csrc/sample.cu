@@ -444,16 +444,19 @@ extern "C" int gpc_unique_reads(const int32_t* start_node, const int32_t* start_
     GPC_CUDA(cudaMemsetAsync(keys.p, 0xff, (size_t)cap * 8, stream));
     GPC_CUDA(cudaMemsetAsync(first.p, 0xff, (size_t)cap * 4, stream));
     unsigned blocks = div_up(n, 256);
+    GPC_PROF_BYTES("dedup_insert", 12.0 * n);
     dedup_insert_kernel<<<blocks, 256, 0, stream>>>(start_node, start_off, n,
                                                    keys.as<unsigned long long>(),
                                                    first.as<unsigned>(), cap - 1,
                                                    slot.as<unsigned>());
     GPC_LAUNCH_CHECK();
+    GPC_PROF("dedup_flag");
     dedup_flag_kernel<<<blocks, 256, 0, stream>>>(first.as<unsigned>(), slot.as<unsigned>(), n,
                                                  keep.as<uint8_t>());
     GPC_LAUNCH_CHECK();
     GPC_TRY(exclusive_scan<uint8_t>(keep.as<uint8_t>(), offs.as<uint32_t>(), n,
                                     total.as<unsigned long long>(), stream));
+    GPC_PROF("compact_index");
     compact_index_kernel<<<blocks, 256, 0, stream>>>(keep.as<uint8_t>(), offs.as<uint32_t>(), n,
                                                     out_index);
     GPC_LAUNCH_CHECK();
@@ -485,6 +488,7 @@ extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* re
     GPC_CUDA(cudaMemsetAsync(ctr.p, 0, 16, stream));
     unsigned long long* count = ctr.as<unsigned long long>();
     int* err = reinterpret_cast<int*>(count + 1);
+    GPC_PROF("walk_reads");
     walk_reads_kernel<<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
         *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
         touched, err);
@@ -493,6 +497,9 @@ extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* re
     GPC_CUDA(cudaMemcpyAsync(h, ctr.p, 16, cudaMemcpyDeviceToHost, stream));
     GPC_CUDA(cudaStreamSynchronize(stream));
     *n_events = h[0];
+    // reads SoA (4 x int32 + 2 x int64 path_ptr + index) in, events out; the path
+    // nodes and the graph records it gathers are counted in DESIGN.md per read
+    prof_add_bytes("walk_reads", 36.0 * (double)n_reads + 4.0 * (double)h[0]);
     int e = (int)(h[1] & 0xffffffffu);
     if (e == GPC_ERR_INVALID_INTERVAL) {
         set_error("Interval has node(s) not part of graph/pileup");
@@ -538,6 +545,7 @@ extern "C" int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64
     unsigned long long* st2 = reinterpret_cast<unsigned long long*>(prefixes + tiles);
     unsigned long long* st3 = st2 + tiles;
     unsigned* st1 = reinterpret_cast<unsigned*>(st3 + tiles);
+    GPC_PROF_BYTES("events_to_runs", 4.0 * n_events);
     events_to_runs_kernel<<<tiles, RUN_THREADS, 0, stream>>>(
         sorted, (unsigned)n_events, frag_idx, frag_val, direct_idx, direct_val, aggs, prefixes, st1,
         st2, st3, ticket, counts);
@@ -547,5 +555,6 @@ extern "C" int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64
     GPC_CUDA(cudaStreamSynchronize(stream));
     *n_frag = h[0];
     *n_direct = h[1];
+    prof_add_bytes("events_to_runs", 8.0 * (double)(h[0] + h[1]));
     return GPC_OK;
 }

@@ -67,6 +67,7 @@ int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* t
     GPC_CUDA(cudaMemsetAsync(sc.p, 0, (size_t)tiles * 8 + 16, stream));
     unsigned long long* status = sc.as<unsigned long long>() + 2;
     unsigned* ticket = sc.as<unsigned>();
+    GPC_PROF_BYTES("excl_scan", (double)n * (sizeof(InT) + 4));
     excl_scan_kernel<InT><<<tiles, SC_THREADS, 0, stream>>>(in, out, (unsigned)n, status, ticket, total_dev);
     GPC_LAUNCH_CHECK();
     return GPC_OK;

@@ -83,15 +83,21 @@ class DeviceGraph:
 class DeviceReads:
     """Reads SoA in HBM (include/gpc_b200.h: gpc_reads_t)."""
 
-    def __init__(self, batch, pinned=False):
+    def __init__(self, batch):
         self.batch = batch
         self.n = len(batch)
-        self.start_node = to_device(batch.start_node)
-        self.start_off = to_device(batch.start_off)
-        self.end_node = to_device(batch.end_node)
-        self.end_off = to_device(batch.end_off)
-        self.path_ptr = to_device(batch.path_ptr)
-        self.path = to_device(batch.path)
+        pinned = getattr(batch, "_pinned", None)
+        if pinned is not None:      # page-locked host tensors: asynchronous copies
+            dev = device()
+            (self.start_node, self.start_off, self.end_node, self.end_off, self.path_ptr,
+             self.path) = [t.to(dev, non_blocking=True) for t in pinned]
+        else:
+            self.start_node = to_device(batch.start_node)
+            self.start_off = to_device(batch.start_off)
+            self.end_node = to_device(batch.end_node)
+            self.end_off = to_device(batch.end_off)
+            self.path_ptr = to_device(batch.path_ptr)
+            self.path = to_device(batch.path)
         self.c = _lib.GpcReads(self.n, ptr(self.start_node), ptr(self.start_off),
                                ptr(self.end_node), ptr(self.end_off),
                                ptr(self.path_ptr), ptr(self.path))

@@ -198,7 +198,7 @@ def clean_holes(dgraph, pos, val, max_size, touched):
     """H2-H4.  Returns (pos int32[Uh], value uint8[Uh])."""
     torch = torch_cuda()
     lib = _lib.load()
-    cap = 2 * pos.numel() + 1024
+    cap = pos.numel() + 16
     while True:
         op, ov = empty(cap, torch.int32), empty(cap, torch.uint8)
         n_out = _u64()
@@ -216,7 +216,7 @@ def max_paths(dgraph, pos, val, score_pos, score_val, q_pos, q_val, internal_id_
     """M1-M3.  Returns a dict of CUDA tensors (see include/gpc_b200.h)."""
     torch = torch_cuda()
     lib = _lib.load()
-    pcap, ncap = max(1024, pos.numel()), max(4096, 4 * pos.numel())
+    pcap, ncap = max(1024, pos.numel()), max(1 << 16, 32 * pos.numel())
     while True:
         t = dict(start=empty(pcap, torch.int32), end=empty(pcap, torch.int32),
                  length=empty(pcap, torch.int32), score=empty(pcap, torch.float64),

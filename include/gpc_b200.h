@@ -189,8 +189,8 @@ int gpc_threshold(const uint32_t* pos, const double* q, uint64_t n_runs, double 
  * nodes, on graph sources/sinks, in line-graph components of more than 36
  * pieces or without an entry piece are never filled.  touched: n_nodes bytes
  * or NULL (every node touched).  Output: canonical boolean track; capacity
- * 2 * (number of hole pieces) + 2 is always enough, GPC_ERR_CAPACITY reports
- * the needed size in *n_out. */
+ * n_runs + 2 is always enough (cleaning only removes runs); GPC_ERR_CAPACITY
+ * reports the needed size in *n_out. */
 int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
                     uint64_t n_runs, int32_t max_size, const uint8_t* touched, uint32_t* out_pos,
                     uint8_t* out_val, uint64_t out_capacity, uint64_t* n_out, void* stream);
@@ -225,6 +225,15 @@ int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* 
                   uint32_t* peak_node_ptr, uint64_t peak_capacity, int32_t* peak_nodes,
                   uint64_t node_capacity, uint32_t* order, uint64_t* n_peaks,
                   uint64_t* n_nodes_total, void* stream);
+
+/* ---- measurement hooks (no reference counterpart) ---------------------------
+ * gpc_launch_count: kernels launched by this library since it was loaded.
+ * gpc_profile_enable(1): time every kernel launch with a CUDA event pair on
+ * its stream; gpc_profile_report writes "name calls total_ms" lines for the
+ * launches since the previous report and returns the bytes needed. */
+uint64_t gpc_launch_count(void);
+void gpc_profile_enable(int on);
+uint64_t gpc_profile_report(char* buf, uint64_t capacity);
 
 /* ---- C1  LinearMap.from_graph / find_starts / find_ends
  *          (control/linearmap.py:102-154) ------------------------------------

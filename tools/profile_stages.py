@@ -1,0 +1,42 @@
+"""Per-kernel time breakdown of one callpeaks pass (CUDA events recorded by the
+library around every launch).  python tools/profile_stages.py [backbone_bp] [reads]"""
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from graph_peak_caller_b200 import _lib, pipeline
+from graph_peak_caller_b200.control.linearmap import LinearMap
+from graph_peak_caller_b200.device import DeviceGraph, DeviceReads
+from graph_peak_caller_b200.synthetic import make_graph, make_reads
+
+bp = int(float(sys.argv[1])) if len(sys.argv) > 1 else 51_000_000
+nr = int(float(sys.argv[2])) if len(sys.argv) > 2 else 5_000_000
+t = time.time()
+g = make_graph(bp, 0.02, seed=20261001)
+s = make_reads(g, nr, 36, 200, seed=1)
+c = make_reads(g, nr, 36, 200, seed=2, peak_frac=0.0, dup_frac=0.0)
+lm = LinearMap.from_graph(g)
+print("generated %r in %.1fs" % (g, time.time() - t), flush=True)
+dg = DeviceGraph(g, lm.as_arrays())
+ds, dc = DeviceReads(s), DeviceReads(c)
+torch.cuda.synchronize()
+for it in range(3):
+    _lib.profile_enable(it == 2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    st, qt, q, thr, cleaned, peaks = pipeline.callpeaks(dg, ds, dc, 36, 200, True, None, True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print("iter %d: %.2f ms  (%d+%d unique reads, %d events, %d/%d sample/direct runs, "
+          "%d control entries, %d p runs, %d distinct p, %d thr runs, %d cleaned, %d peaks)" % (
+              it, dt * 1e3, st.n_sample, st.n_control, st.n_events, st.sample[0].numel(),
+              st.direct[0].numel(), st.control[0].numel(), st.p_values[0].numel(),
+              qt[0].numel(), thr[0].numel(), cleaned[0].numel(), len(peaks)), flush=True)
+rep = _lib.profile_report()
+tot = sum(ms for _, ms in rep.values())
+print("kernel time total %.3f ms over %d launches" % (tot, sum(c for c, _ in rep.values())))
+for name, (calls, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
+    print("  %-28s %4d calls %9.3f ms  %5.1f%%" % (name, calls, ms, 100 * ms / tot))
