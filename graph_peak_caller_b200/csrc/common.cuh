@@ -44,6 +44,8 @@ void prof_add_bytes(const char* name, double algorithmic_bytes);
         GPC_CUDA(cudaGetLastError());                                          \
     } while (0)
 
+int sm_count();
+
 // Stream-ordered scratch that frees itself (cudaMallocAsync pool).
 struct Scratch {
     void* p = nullptr;
@@ -54,6 +56,7 @@ struct Scratch {
     ~Scratch() { release(); }
     cudaError_t alloc(size_t bytes, cudaStream_t stream) {
         release();
+        sm_count();   // first call configures the memory pool of this device
         s = stream;
         if (bytes == 0) bytes = 16;
         return cudaMallocAsync(&p, bytes, stream);
@@ -64,8 +67,6 @@ struct Scratch {
     }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
-
-int sm_count();
 
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 

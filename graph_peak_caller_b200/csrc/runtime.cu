@@ -52,6 +52,17 @@ void prof_end() {
     g_pending = nullptr;
 }
 
+// The stream-ordered pool gives freed scratch back to the OS at every
+// synchronisation unless told otherwise; keep it (the path allocates and frees
+// the same few hundred MB every pass).
+static void keep_pool_memory(int dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+}
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -59,6 +70,7 @@ int sm_count() {
         if (cudaGetDevice(&dev) != cudaSuccess ||
             cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
             n = 148;
+        keep_pool_memory(dev);
     }
     return n;
 }

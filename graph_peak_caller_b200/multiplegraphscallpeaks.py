@@ -1,0 +1,149 @@
+"""``MultipleGraphsCallpeaks`` with the reference's constructor and methods
+(graph_peak_caller/multiplegraphscallpeaks.py:14-168): one graph per
+chromosome, p-values per chromosome, ONE q mapping over all chromosomes,
+peaks per chromosome.
+
+The reference runs the chromosomes one after the other (or as separate OS
+processes joined through ``*_pvalues_*.npy`` files).  Here the chromosomes are
+distributed over the ranks of ``torch.distributed`` (one process per GPU,
+longest-processing-time bin packing by graph size) and the join is one
+all-gather of the (p, base pairs) tables (multigraph.gather_p_tables).  In a
+single process it degenerates to the reference's sequential loop.
+
+Inputs per chromosome: a ``Graph`` (or a file written by ``Graph.to_file``),
+reads as ``Intervals`` / ``UniqueIntervals`` / ``ReadBatch`` / iterable of
+obg-style intervals (or a file written by ``ReadBatch.to_file``), a linear map
+(``LinearMap`` or ``.npz`` file).  vg JSON / .nobg parsing is ingest and stays
+with the reference's own tooling."""
+import logging
+
+import numpy as np
+
+from . import kernels, multigraph
+from .callpeaks import CallPeaks
+from .graph import Graph
+from .intervals import Intervals, UniqueIntervals
+from .reads import ReadBatch
+from .sparsepvalues import PToQValuesMapper
+
+
+class MultipleGraphsCallpeaks:
+    def __init__(self, graph_names, graph_file_names, samples, controls, linear_maps, config,
+                 reporter, sequence_retrievers=None, stop_after_p_values=False,
+                 linear_path_file_names=None, variant_maps_path=None):
+        if variant_maps_path is not None:
+            raise NotImplementedError("variant maps are outside this path")
+        self._config = config
+        self._reporter = reporter
+        self.names = list(graph_names)
+        self.graph_file_names = list(graph_file_names)
+        self.linear_maps = list(linear_maps)
+        self.sequence_retrievers = sequence_retrievers
+        self.samples = list(samples)
+        self.controls = list(controls)
+        self.stop_after_p_values = stop_after_p_values
+        self.linear_path_file_names = linear_path_file_names
+        self._graphs = {}
+        self._callers = {}
+        self._mine = None
+        if self.stop_after_p_values:
+            logging.info("Will only run until p-values have been computed.")
+
+    # -- helpers ---------------------------------------------------------------
+    def _graph(self, i):
+        if i not in self._graphs:
+            g = self.graph_file_names[i]
+            self._graphs[i] = Graph.from_file(g) if isinstance(g, str) else Graph.from_obg(g)
+        return self._graphs[i]
+
+    def my_chromosomes(self):
+        """Indexes of the chromosomes this rank works on."""
+        if self._mine is None:
+            rank, world = multigraph.world()
+            if world == 1:
+                self._mine = list(range(len(self.names)))
+            else:
+                sizes = [self._graph(i).size_bp for i in range(len(self.names))]
+                self._mine = sorted(multigraph.assign_chromosomes(sizes, world)[rank])
+        return self._mine
+
+    @classmethod
+    def count_number_of_unique_reads(cls, sample_reads):
+        """reference multiplegraphscallpeaks.py:41-63, on the device."""
+        from .device import device_reads
+        n_unique = 0
+        for reads in sample_reads:
+            batch = reads if isinstance(reads, ReadBatch) else ReadBatch.from_intervals(
+                getattr(reads, "intervals", reads))
+            _, n = kernels.unique_reads(device_reads(batch))
+            n_unique += n
+        logging.info("In total %d unique reads" % n_unique)
+        return n_unique
+
+    def get_intervals(self, sample, control, graph):
+        def load(x):
+            if isinstance(x, (Intervals, UniqueIntervals)):
+                return x
+            if isinstance(x, str):
+                x = ReadBatch.from_file(x)
+            if self._config.keep_duplicates:
+                logging.warning("Keeping duplicates. Should only be used for testing.")
+                return Intervals(x)
+            return UniqueIntervals(x)
+        return load(sample), load(control)
+
+    # -- reference surface -------------------------------------------------------
+    def run(self):
+        self.run_to_p_values()
+        if self.stop_after_p_values:
+            logging.info("Stopping, as planned, after p-values")
+            return
+        self.create_joined_q_value_mapping()
+        self.run_from_p_values()
+
+    def run_to_p_values(self):
+        for i in self.my_chromosomes():
+            name = self.names[i]
+            logging.info("Running to p values, %s" % name)
+            graph = self._graph(i)
+            sample, control = self.get_intervals(self.samples[i], self.controls[i], graph)
+            config = self._config.copy()
+            config.linear_map_name = self.linear_maps[i]
+            caller = CallPeaks(graph, config, self._reporter.get_sub_reporter(name))
+            caller.run_to_p_values(sample, control)
+            self._callers[i] = caller
+            logging.info("In total %d duplicates were removed from sample" % sample.n_duplicates)
+
+    def create_joined_q_value_mapping(self):
+        torch = kernels.torch_cuda()
+        tps, tcs, total = [], [], 0
+        for i in self.my_chromosomes():
+            pv = self._callers[i].p_values_pileup
+            pos, p = pv.device_arrays()
+            tp, tc = kernels.ptable_local(pos, p, int(pv.track_size))
+            tps.append(tp)
+            tcs.append(tc)
+            total += int(pv.track_size)
+        if tps:
+            tp, tc = torch.cat(tps), torch.cat(tcs)
+        else:
+            from .device import empty
+            tp, tc = empty(0, torch.float64), empty(0, torch.int64)
+        tp, tc, total = multigraph.gather_p_tables(tp, tc, total)
+        mapper = PToQValuesMapper._from_device_table(tp, tc, total)
+        self._q_value_mapping = mapper.get_p_to_q_values()
+
+    def run_from_p_values(self, only_chromosome=None):
+        for i in self.my_chromosomes():
+            name = self.names[i]
+            if only_chromosome is not None and only_chromosome != name:
+                logging.info("Skipping %s" % str(name))
+                continue
+            caller = self._callers[i]
+            caller.p_to_q_values_mapping = self._q_value_mapping
+            caller.get_q_values()
+            caller.call_peaks_from_q_values()
+
+    def peaks(self):
+        """{chromosome name: list of Peak} for this rank's chromosomes."""
+        return {self.names[i]: self._callers[i].max_path_peaks for i in self.my_chromosomes()}

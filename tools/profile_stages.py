@@ -36,7 +36,7 @@ for it in range(3):
               st.direct[0].numel(), st.control[0].numel(), st.p_values[0].numel(),
               qt[0].numel(), thr[0].numel(), cleaned[0].numel(), len(peaks)), flush=True)
 rep = _lib.profile_report()
-tot = sum(ms for _, ms in rep.values())
-print("kernel time total %.3f ms over %d launches" % (tot, sum(c for c, _ in rep.values())))
-for name, (calls, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
+tot = sum(v[1] for v in rep.values())
+print("kernel time total %.3f ms over %d launches" % (tot, sum(v[0] for v in rep.values())))
+for name, (calls, ms, nbytes) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
     print("  %-28s %4d calls %9.3f ms  %5.1f%%" % (name, calls, ms, 100 * ms / tot))
