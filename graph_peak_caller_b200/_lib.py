@@ -6,7 +6,7 @@ import os
 from .custom_exceptions import DeviceLibraryMissing, InvalidPileupInterval
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgpc_b200.so")
+LIB_PATH = os.environ.get("GPC_B200_LIB", os.path.join(HERE, "libgpc_b200.so"))
 
 GPC_OK = 0
 GPC_ERR_CUDA = 1

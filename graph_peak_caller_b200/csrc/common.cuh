@@ -157,6 +157,40 @@ __device__ __forceinline__ unsigned long long lookback_excl(unsigned long long* 
     return excl;
 }
 
+// Warp-wide variant: all 32 lanes of ONE warp call it with the same arguments.
+// 32 predecessors are inspected per step, so a wavefront of tiles finishing
+// together costs ceil(depth / 32) round trips instead of `depth`.
+__device__ __forceinline__ unsigned long long lookback_excl_warp(unsigned long long* status,
+                                                                 unsigned tile,
+                                                                 unsigned long long agg) {
+    const unsigned lane = threadIdx.x & 31;
+    if (tile == 0) {
+        if (lane == 0) lb_store(&status[0], LB_PREFIX | agg);
+        return 0;
+    }
+    if (lane == 0) lb_store(&status[tile], LB_AGG | agg);
+    unsigned long long excl = 0;
+    int newest = (int)tile - 1;
+    while (true) {
+        int t = newest - (int)lane;                 // lane 0 = nearest predecessor
+        unsigned long long s = (t >= 0) ? lb_load(&status[t]) : LB_PREFIX;
+        unsigned long long st = s & ~LB_MASK;
+        unsigned empty = __ballot_sync(0xffffffffu, st == LB_EMPTY);
+        unsigned pref = __ballot_sync(0xffffffffu, st == LB_PREFIX);
+        int first_pref = pref ? (__ffs(pref) - 1) : 32;
+        unsigned need = (first_pref >= 31) ? 0xffffffffu : ((2u << first_pref) - 1u);
+        if (empty & need) continue;                 // someone in the window is not ready
+        unsigned long long v = ((int)lane <= first_pref) ? (s & LB_MASK) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        excl += v;
+        if (first_pref < 32) break;
+        newest -= 32;
+    }
+    if (lane == 0) lb_store(&status[tile], LB_PREFIX | (excl + agg));
+    return excl;
+}
+
 __device__ __forceinline__ uint4 node_record(const gpc_graph_t& g, uint32_t v) {
     return __ldg(reinterpret_cast<const uint4*>(g.node_rec) + v);
 }

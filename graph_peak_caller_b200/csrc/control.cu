@@ -8,10 +8,18 @@
 //   LinearMap.to_sparse_pileup                                     control/linearmap.py:76-99
 //
 // Formulation.  Every control read start is projected to the linear axis with
-// the reference's exact float64 operations.  Each extension window w turns a
-// start x into a +1 at x-e_w and a -1 at x+e_w; all windows' events are sorted
-// once (64-bit order-preserving keys) and one chained scan keeps an integer
-// count per window.  The linear lambda is
+// the reference's exact float64 operations and the R projected starts are
+// radix sorted once (64-bit order-preserving keys) and run-length compressed
+// (distinct x, multiplicity).  Each extension window w turns a start x into a
+// +1 at x-e_w and a -1 at x+e_w, so the 2W event streams are all shifted views
+// of the same sorted array.  They are merged without ever materialising or
+// sorting the 2WR events: every T-th element of every view is a splitter, the
+// sorted splitters cut the value axis into tiles that hold at most ~T elements
+// of each view, and one CTA per tile merges its <= 2W(T+2) elements in shared
+// memory (rank by binary search), then scans integer counts per window.  The
+// counts at a tile's left edge follow directly from the split indexes, so tiles
+// are independent; only the output offset goes through a chained scan.
+// The linear lambda is
 //     max( min_value , max_w count_w * weight_w )
 // (before the first event of window 0 the clip and window 0 do not apply: that
 // is what clip_min on the first track followed by maximum() does).  Counts are
@@ -36,12 +44,11 @@ struct WindowParams {
 
 // x = node_start + scale * offset   (forward)   /   node_end - scale * offset (reverse)
 // with scale = (node_end - node_start) / node_size; no FMA contraction.
-__global__ void project_events_kernel(gpc_graph_t graph, const int32_t* __restrict__ start_node,
-                                      const int32_t* __restrict__ start_off,
-                                      const uint32_t* __restrict__ read_index, unsigned n_reads,
-                                      WindowParams wp, unsigned long long* __restrict__ keys,
-                                      uint32_t* __restrict__ tags, double* __restrict__ x_out,
-                                      int* __restrict__ err) {
+__global__ void project_keys_kernel(gpc_graph_t graph, const int32_t* __restrict__ start_node,
+                                    const int32_t* __restrict__ start_off,
+                                    const uint32_t* __restrict__ read_index, unsigned n_reads,
+                                    unsigned long long* __restrict__ keys,
+                                    double* __restrict__ x_out, int* __restrict__ err) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_reads) return;
     unsigned r = read_index ? read_index[i] : i;
@@ -57,46 +64,100 @@ __global__ void project_events_kernel(gpc_graph_t graph, const int32_t* __restri
     double so = __dmul_rn(scale, (double)start_off[r]);
     double x = id > 0 ? __dadd_rn(ns, so) : __dsub_rn(ne, so);
     if (x_out) x_out[i] = x;
-    for (int w = 0; w < wp.n_windows; ++w) {
-        size_t o = ((size_t)w * n_reads + i) * 2;
-        keys[o] = f64_to_key(__dsub_rn(x, wp.half[w]));
-        tags[o] = (uint32_t)(w << 1);
-        keys[o + 1] = f64_to_key(__dadd_rn(x, wp.half[w]));
-        tags[o + 1] = (uint32_t)(w << 1) | 1u;
+    keys[i] = f64_to_key(x);
+}
+
+// distinct x and the index of their first occurrence (== weight prefix)
+__global__ void unique_flag_kernel(const unsigned long long* __restrict__ keys, unsigned n,
+                                   uint8_t* __restrict__ head) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) head[i] = (i == 0) || keys[i] != keys[i - 1];
+}
+__global__ void unique_emit_kernel(const unsigned long long* __restrict__ keys, unsigned n,
+                                   const uint8_t* __restrict__ head,
+                                   const uint32_t* __restrict__ offs, unsigned n_unique,
+                                   double* __restrict__ xu, uint32_t* __restrict__ wpre) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) wpre[n_unique] = n;
+    if (i < n && head[i]) {
+        xu[offs[i]] = key_to_f64(keys[i]);
+        wpre[offs[i]] = i;
     }
 }
 
-// ---- sorted window events -> linear lambda track -----------------------------
-constexpr int LIN_THREADS = 256;
-constexpr int LIN_ITEMS = 4;
-constexpr int LIN_TILE = LIN_THREADS * LIN_ITEMS;
+// view q of the sorted starts: q = 2*w + is_end  ->  x -/+ half[w]
+__device__ __forceinline__ double view_value(double x, int q, const WindowParams& wp) {
+    double h = wp.half[q >> 1];
+    return (q & 1) ? __dadd_rn(x, h) : __dsub_rn(x, h);
+}
+
+constexpr int MERGE_T = 128;                       // splitter stride per view
+constexpr int MERGE_THREADS = 256;
+constexpr int MERGE_MAXQ = 2 * MAX_WINDOWS;
+constexpr int MERGE_CAP = 3072;                    // elements per tile (shared memory)
+constexpr int MERGE_PER_THREAD = MERGE_CAP / MERGE_THREADS;
+constexpr size_t MERGE_SMEM = (size_t)MERGE_CAP * (8 + 8 + 4 + 1);
+
+__global__ void splitters_kernel(const double* __restrict__ xu, unsigned n_unique, WindowParams wp,
+                                 unsigned per_view, unsigned long long* __restrict__ sp) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned nq = 2 * wp.n_windows;
+    if (i >= per_view * nq) return;
+    unsigned q = i / per_view, j = i % per_view;
+    sp[i] = f64_to_key(view_value(xu[(size_t)j * MERGE_T], (int)q, wp));
+}
+
+// bounds[k][q] = first index i with view_q(i) >= splitter k-1   (k = 1..ns);
+// bounds[0][q] = 0, bounds[ns+1][q] = n_unique.  Tile k = [bounds[k], bounds[k+1]).
+__global__ void tile_bounds_kernel(const double* __restrict__ xu, unsigned n_unique, WindowParams wp,
+                                   const unsigned long long* __restrict__ sp, unsigned ns,
+                                   uint32_t* __restrict__ bounds) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned nq = 2 * wp.n_windows;
+    if (i >= (ns + 2) * nq) return;
+    unsigned k = i / nq, q = i % nq;
+    uint32_t r;
+    if (k == 0) r = 0;
+    else if (k == ns + 1) r = n_unique;
+    else {
+        unsigned long long s = sp[k - 1];
+        unsigned lo = 0, hi = n_unique;
+        while (lo < hi) {
+            unsigned mid = (lo + hi) >> 1;
+            if (f64_to_key(view_value(xu[mid], (int)q, wp)) < s) lo = mid + 1; else hi = mid;
+        }
+        r = lo;
+    }
+    bounds[i] = r;
+}
+
+// merged rank of every splitter boundary, then tile edges: tile t starts at the
+// last boundary whose rank is <= t * stride.  Consecutive boundaries are at most
+// nq * (T + 2) elements apart, so a tile holds at most stride + nq * (T + 2).
+__global__ void boundary_rank_kernel(const uint32_t* __restrict__ bounds, unsigned n_bounds,
+                                     unsigned nq, unsigned long long* __restrict__ rank) {
+    unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_bounds) return;
+    unsigned long long r = 0;
+    for (unsigned q = 0; q < nq; ++q) r += bounds[(size_t)k * nq + q];
+    rank[k] = r;
+}
+__global__ void pick_tiles_kernel(const unsigned long long* __restrict__ rank, unsigned n_bounds,
+                                  unsigned n_tiles, unsigned long long stride,
+                                  uint32_t* __restrict__ pick) {
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    if (t == n_tiles) { pick[t] = n_bounds - 1; return; }
+    unsigned long long target = (unsigned long long)t * stride;
+    unsigned lo = 0, hi = n_bounds;            // first boundary with rank > target
+    while (lo < hi) {
+        unsigned mid = (lo + hi) >> 1;
+        if (rank[mid] <= target) lo = mid + 1; else hi = mid;
+    }
+    pick[t] = lo - 1;                          // rank[0] == 0 <= target, so lo >= 1
+}
+
 constexpr int NC = 4;            // count per window (3) + "window-0 starts seen"
-
-struct LinAgg {
-    int tot[NC];
-    int seg[NC];
-    int has_head;
-    int pad[3];
-};
-
-struct SegN { int head; int c[NC]; };
-__device__ __forceinline__ SegN segn_combine(const SegN& x, const SegN& y) {
-    if (y.head) return y;
-    SegN r;
-    r.head = x.head;
-#pragma unroll
-    for (int k = 0; k < NC; ++k) r.c[k] = x.c[k] + y.c[k];
-    return r;
-}
-
-__device__ __forceinline__ void tag_delta(uint32_t tag, int d[NC]) {
-#pragma unroll
-    for (int k = 0; k < NC; ++k) d[k] = 0;
-    int w = tag >> 1;
-    bool is_end = tag & 1u;
-    d[w] = is_end ? -1 : 1;
-    if (w == 0 && !is_end) d[3] = 1;
-}
 
 __device__ __forceinline__ double lambda_of(const int c[NC], const WindowParams& wp) {
     double best = 0.0;
@@ -107,174 +168,166 @@ __device__ __forceinline__ double lambda_of(const int c[NC], const WindowParams&
     return best;
 }
 
-__global__ void __launch_bounds__(LIN_THREADS)
-linear_track_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ tags,
-                    unsigned n, WindowParams wp, double* __restrict__ out_pos,
-                    double* __restrict__ out_val, LinAgg* __restrict__ aggs,
-                    LinAgg* __restrict__ prefixes, unsigned* __restrict__ st1,
-                    unsigned long long* __restrict__ st2, unsigned* __restrict__ ticket,
-                    unsigned long long* __restrict__ out_count) {
-    __shared__ unsigned s_slot;
+__global__ void __launch_bounds__(MERGE_THREADS)
+linear_tiles_kernel(const double* __restrict__ xu, const uint32_t* __restrict__ wpre,
+                    WindowParams wp, const uint32_t* __restrict__ bounds,
+                    const uint32_t* __restrict__ pick, unsigned n_tiles,
+                    double* __restrict__ out_pos, double* __restrict__ out_val,
+                    unsigned long long* __restrict__ status, unsigned* __restrict__ ticket,
+                    unsigned long long* __restrict__ out_count, int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long* s_stage = reinterpret_cast<unsigned long long*>(s_raw);   // view-major
+    unsigned long long* s_key = s_stage + MERGE_CAP;                              // merged order
+    uint32_t* s_mul = reinterpret_cast<uint32_t*>(s_key + MERGE_CAP);
+    uint8_t* s_tag = reinterpret_cast<uint8_t*>(s_mul + MERGE_CAP);
+    __shared__ uint32_t s_lo[MERGE_MAXQ], s_hi[MERGE_MAXQ], s_off[MERGE_MAXQ + 1];
+    __shared__ int s_base[NC];
+    __shared__ int s_warp[MERGE_THREADS / 32][NC];
     __shared__ int s_scan[33];
-    __shared__ SegN s_seg[LIN_THREADS / 32];
-    __shared__ LinAgg s_carry;
     __shared__ unsigned long long s_obase;
-    const unsigned tile = claim_tile(ticket, &s_slot);
-    const unsigned base = tile * LIN_TILE + threadIdx.x * LIN_ITEMS;
-
-    unsigned long long key[LIN_ITEMS + 1];
-    uint32_t tag[LIN_ITEMS];
-#pragma unroll
-    for (int j = 0; j <= LIN_ITEMS; ++j)
-        key[j] = (base + j < n) ? keys[base + j] : ~0ull;
-#pragma unroll
-    for (int j = 0; j < LIN_ITEMS; ++j) tag[j] = (base + j < n) ? tags[base + j] : 0u;
-    const unsigned long long prev_key = (base > 0 && base - 1 < n) ? keys[base - 1] : ~0ull;
-
-    int tot[NC] = {0, 0, 0, 0};
-    SegN seg;
-    seg.head = 0;
-#pragma unroll
-    for (int k = 0; k < NC; ++k) seg.c[k] = 0;
-    unsigned long long pk = prev_key;
-#pragma unroll
-    for (int j = 0; j < LIN_ITEMS; ++j) {
-        if (base + j < n) {
-            SegN e;
-            tag_delta(tag[j], e.c);
-            e.head = (base + j == 0 || key[j] != pk) ? 1 : 0;
-            seg = segn_combine(seg, e);
-#pragma unroll
-            for (int k = 0; k < NC; ++k) tot[k] += e.c[k];
-            pk = key[j];
-        }
+    // tiles are taken in launch order (blockIdx): a tile only waits on earlier ones
+    const unsigned tile = blockIdx.x;
+    const int nq = 2 * wp.n_windows;
+    if ((int)threadIdx.x < nq) {
+        s_lo[threadIdx.x] = bounds[(size_t)pick[tile] * nq + threadIdx.x];
+        s_hi[threadIdx.x] = bounds[(size_t)pick[tile + 1] * nq + threadIdx.x];
     }
-    // exclusive prefix of the totals over the threads of the tile
-    int ex[NC], tile_tot[NC];
-#pragma unroll
-    for (int k = 0; k < NC; ++k) ex[k] = block_excl_sum<int>(tot[k], s_scan, tile_tot[k]);
-    // exclusive segmented prefix over the threads
-    SegN incl = seg;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        SegN o;
-        o.head = __shfl_up_sync(FULL, incl.head, d);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) o.c[k] = __shfl_up_sync(FULL, incl.c[k], d);
-        if (lane_id() >= (unsigned)d) incl = segn_combine(o, incl);
-    }
-    if (lane_id() == 31) s_seg[warp_id()] = incl;
     __syncthreads();
-    SegN carry;
-    carry.head = 0;
-#pragma unroll
-    for (int k = 0; k < NC; ++k) carry.c[k] = 0;
-    for (unsigned w = 0; w < warp_id(); ++w) carry = segn_combine(carry, s_seg[w]);
+    if (threadIdx.x == 0) {
+        unsigned off = 0;
+        for (int q = 0; q < nq; ++q) { s_off[q] = off; off += s_hi[q] - s_lo[q]; }
+        s_off[nq] = off;
+    }
+    // counts in force at the tile's left edge, straight from the split indexes
+    if (threadIdx.x >= 32 && (int)threadIdx.x < 32 + NC) {
+        int k = threadIdx.x - 32;
+        int v = 0;
+        if (k < wp.n_windows) v = (int)wpre[s_lo[2 * k]] - (int)wpre[s_lo[2 * k + 1]];
+        else if (k == 3) v = (int)wpre[s_lo[0]];
+        s_base[k] = v;
+    }
+    __syncthreads();
+    const unsigned m = s_off[nq];
+    if (m > MERGE_CAP) {          // cannot happen (<= T+2 per view); fail loudly
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) atomicExch(err, GPC_ERR_INTERNAL);
+            lookback_excl_warp(status, tile, 0ull);
+        }
+        return;
+    }
+    // stage every view's slice as keys
+    for (unsigned e = threadIdx.x; e < m; e += MERGE_THREADS) {
+        int q = 0;
+        while (e >= s_off[q + 1]) ++q;
+        unsigned i = s_lo[q] + (e - s_off[q]);
+        s_stage[e] = f64_to_key(view_value(xu[i], q, wp));
+    }
+    __syncthreads();
+    // merged rank = own offset + elements of the other views that sort before
+    // (ties between views are broken by view id, so ranks are unique).  Every
+    // thread ranks a contiguous chunk of one view: the first element costs a
+    // binary search per other view, the following ones just advance pointers.
+    const unsigned per = (m + MERGE_THREADS - 1) / MERGE_THREADS;
+    const unsigned a0 = min(m, threadIdx.x * per), a1 = min(m, a0 + per);
     {
-        SegN up;
-        up.head = __shfl_up_sync(FULL, incl.head, 1);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) up.c[k] = __shfl_up_sync(FULL, incl.c[k], 1);
-        if (lane_id() > 0) carry = segn_combine(carry, up);
-    }
-    if (threadIdx.x == LIN_THREADS - 1) {
-        SegN all = segn_combine(carry, seg);
-        LinAgg mine, in;
-#pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            mine.tot[k] = tile_tot[k];
-            mine.seg[k] = all.c[k];
-            in.tot[k] = 0;
-            in.seg[k] = 0;
-        }
-        mine.has_head = all.head;
-        in.has_head = 0;
-        volatile unsigned* vs = st1;
-        if (tile > 0) {
-            aggs[tile] = mine;
-            __threadfence();
-            vs[tile] = 1;
-            bool seg_closed = false;
-            int t = (int)tile - 1;
-            while (true) {
-                unsigned s = vs[t];
-                if (s == 0) continue;
-                __threadfence();
-                LinAgg a = (s == 2) ? prefixes[t] : aggs[t];
-#pragma unroll
-                for (int k = 0; k < NC; ++k) in.tot[k] += a.tot[k];
-                if (!seg_closed) {
-#pragma unroll
-                    for (int k = 0; k < NC; ++k) in.seg[k] += a.seg[k];
-                    if (a.has_head) seg_closed = true;
-                }
-                if (s == 2) break;
-                --t;
+        unsigned ptr[MERGE_MAXQ];
+        int q = -1;
+        for (unsigned e = a0; e < a1; ++e) {
+            const unsigned long long key = s_stage[e];
+            const bool fresh = (q < 0) || e >= s_off[q + 1];
+            if (fresh) {
+                q = 0;
+                while (e >= s_off[q + 1]) ++q;
             }
-        }
-        LinAgg pre;
+            unsigned rank = e - s_off[q];
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            pre.tot[k] = in.tot[k] + mine.tot[k];
-            pre.seg[k] = mine.has_head ? mine.seg[k] : in.seg[k] + mine.seg[k];
+            for (int o = 0; o < MERGE_MAXQ; ++o) {
+                if (o >= nq || o == q) continue;
+                const unsigned end = s_off[o + 1];
+                unsigned p;
+                if (fresh) {
+                    unsigned lo = s_off[o], hi = end;
+                    if (o < q) { while (lo < hi) { unsigned mid = (lo + hi) >> 1; if (s_stage[mid] <= key) lo = mid + 1; else hi = mid; } }
+                    else       { while (lo < hi) { unsigned mid = (lo + hi) >> 1; if (s_stage[mid] <  key) lo = mid + 1; else hi = mid; } }
+                    p = lo;
+                } else {
+                    p = ptr[o];
+                    if (o < q) { while (p < end && s_stage[p] <= key) ++p; }
+                    else       { while (p < end && s_stage[p] <  key) ++p; }
+                }
+                ptr[o] = p;
+                rank += p - s_off[o];
+            }
+            unsigned i = s_lo[q] + (e - s_off[q]);
+            s_key[rank] = key;
+            s_tag[rank] = (uint8_t)q;
+            s_mul[rank] = wpre[i + 1] - wpre[i];
         }
-        pre.has_head = 1;
-        prefixes[tile] = pre;
-        __threadfence();
-        vs[tile] = 2;
-        s_carry = in;
     }
     __syncthreads();
-    const LinAgg tin = s_carry;
-    int run[NC];
-    SegN sg;
-    sg.head = carry.head;
-#pragma unroll
-    for (int k = 0; k < NC; ++k) {
-        run[k] = tin.tot[k] + ex[k];
-        sg.c[k] = carry.head ? carry.c[k] : carry.c[k] + tin.seg[k];
+    // same contiguous chunks, now over the merged order: block scan of the counters
+    int tot[NC] = {0, 0, 0, 0};
+    for (unsigned r = a0; r < a1; ++r) {
+        int q = s_tag[r], mul = (int)s_mul[r];
+        tot[q >> 1] += (q & 1) ? -mul : mul;
+        if (q == 0) tot[3] += mul;
     }
-    double e_pos[LIN_ITEMS], e_val[LIN_ITEMS];
+    // block exclusive scan of the four counters with one barrier pair
+    int run[NC];
+    {
+        int incl[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            incl[k] = warp_incl_sum(tot[k]);
+            if (lane_id() == 31) s_warp[warp_id()][k] = incl[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            int pre = s_base[k];
+            for (unsigned w = 0; w < warp_id(); ++w) pre += s_warp[w][k];
+            run[k] = pre + incl[k] - tot[k];
+        }
+    }
+    // emit one breakpoint per group of equal keys whose lambda differs from the
+    // lambda before the group (groups never span tiles: tiles are cut by value)
+    double e_pos[MERGE_PER_THREAD], e_val[MERGE_PER_THREAD];
     int cnt = 0;
-    pk = prev_key;
+    for (unsigned r = a0; r < a1; ++r) {
+        int q = s_tag[r], mul = (int)s_mul[r];
+        run[q >> 1] += (q & 1) ? -mul : mul;
+        if (q == 0) run[3] += mul;
+        bool last = (r + 1 >= m) || s_key[r + 1] != s_key[r];
+        if (last) {
+            int before[NC];
 #pragma unroll
-    for (int j = 0; j < LIN_ITEMS; ++j) {
-        if (base + j < n) {
-            int d[NC];
-            tag_delta(tag[j], d);
-            bool head = (base + j == 0) || key[j] != pk;
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                if (head) sg.c[k] = 0;
-                sg.c[k] += d[k];
-                run[k] += d[k];
+            for (int k = 0; k < NC; ++k) before[k] = run[k];
+            for (unsigned g = r + 1; g-- > 0;) {
+                if (s_key[g] != s_key[r]) break;
+                int qq = s_tag[g], mm = (int)s_mul[g];
+                before[qq >> 1] -= (qq & 1) ? -mm : mm;
+                if (qq == 0) before[3] -= mm;
             }
-            bool last = (base + j + 1 >= n) || key[j + 1] != key[j];
-            if (last) {
-                int before[NC];
-#pragma unroll
-                for (int k = 0; k < NC; ++k) before[k] = run[k] - sg.c[k];
-                double now = lambda_of(run, wp), was = lambda_of(before, wp);
-                if (now != was) {
-                    e_pos[cnt] = key_to_f64(key[j]);
-                    e_val[cnt] = now;
-                    ++cnt;
-                }
+            double now = lambda_of(run, wp), was = lambda_of(before, wp);
+            if (now != was && cnt < MERGE_PER_THREAD) {
+                e_pos[cnt] = key_to_f64(s_key[r]);
+                e_val[cnt] = now;
+                ++cnt;
             }
-            pk = key[j];
         }
     }
     int tile_out;
     int o = block_excl_sum<int>(cnt, s_scan, tile_out);
-    if (threadIdx.x == 0) {
-        s_obase = lookback_excl(st2, tile, (unsigned long long)tile_out);
-        if (tile == gridDim.x - 1) *out_count = s_obase + tile_out;
+    if (threadIdx.x < 32) {
+        unsigned long long b = lookback_excl_warp(status, tile, (unsigned long long)tile_out);
+        if (threadIdx.x == 0) {
+            s_obase = b;
+            if (tile == n_tiles - 1) *out_count = b + tile_out;
+        }
     }
     __syncthreads();
     unsigned long long wbase = s_obase + o;
-#pragma unroll
-    for (int j = 0; j < LIN_ITEMS; ++j)
-        if (j < cnt) { out_pos[wbase + j] = e_pos[j]; out_val[wbase + j] = e_val[j]; }
+    for (int j = 0; j < cnt; ++j) { out_pos[wbase + j] = e_pos[j]; out_val[wbase + j] = e_val[j]; }
 }
 
 // ---- back-projection ---------------------------------------------------------
@@ -393,55 +446,111 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
         double s = (double)(half * 2) / (double)fragment_length;
         wp.weight[w] = 1.0 / s;
     }
-    const size_t n_ev = (size_t)n_reads * 2 * n_extensions;
-    Scratch k0, k1, t0, t1, small;
-    GPC_CUDA(k0.alloc(n_ev * 8, stream));
-    GPC_CUDA(k1.alloc(n_ev * 8, stream));
-    GPC_CUDA(t0.alloc(n_ev * 4, stream));
-    GPC_CUDA(t1.alloc(n_ev * 4, stream));
+    const unsigned n = (unsigned)n_reads;
+    const unsigned nq = 2 * n_extensions;
+    Scratch k0, k1, small, head, offs, total, xu, wpre;
+    GPC_CUDA(k0.alloc((size_t)n * 8, stream));
+    GPC_CUDA(k1.alloc((size_t)n * 8, stream));
     GPC_CUDA(small.alloc(64, stream));
     GPC_CUDA(cudaMemsetAsync(small.p, 0, 64, stream));
     int* err = small.as<int>();
-    GPC_PROF_BYTES("project_events", 12.0 * n_reads + 12.0 * n_ev);
-    project_events_kernel<<<div_up(n_reads, 256), 256, 0, stream>>>(
-        *graph, start_node, start_off, read_index, (unsigned)n_reads, wp,
-        k0.as<unsigned long long>(), t0.as<uint32_t>(), x_out, err);
+    GPC_PROF_BYTES("project_keys", 20.0 * n);
+    project_keys_kernel<<<div_up(n, 256), 256, 0, stream>>>(*graph, start_node, start_off, read_index,
+                                                            n, k0.as<unsigned long long>(), x_out, err);
     GPC_LAUNCH_CHECK();
     bool in_tmp = false;
-    GPC_TRY((radix_sort<unsigned long long, true>(k0.as<unsigned long long>(),
-                                                  k1.as<unsigned long long>(), t0.as<uint32_t>(),
-                                                  t1.as<uint32_t>(), n_ev, 0, 64, true, &in_tmp,
-                                                  stream)));
+    GPC_TRY((radix_sort<unsigned long long, false>(k0.as<unsigned long long>(),
+                                                   k1.as<unsigned long long>(), nullptr, nullptr, n,
+                                                   0, 64, true, &in_tmp, stream)));
     const unsigned long long* keys = in_tmp ? k1.as<unsigned long long>() : k0.as<unsigned long long>();
-    const uint32_t* tags = in_tmp ? t1.as<uint32_t>() : t0.as<uint32_t>();
-    unsigned tiles = div_up(n_ev, LIN_TILE);
-    size_t bytes = (size_t)tiles * (2 * sizeof(LinAgg) + 4 + 8) + 64;
-    Scratch sc;
-    GPC_CUDA(sc.alloc(bytes, stream));
-    GPC_CUDA(cudaMemsetAsync(sc.p, 0, bytes, stream));
-    char* p = sc.as<char>();
-    unsigned long long* count = reinterpret_cast<unsigned long long*>(p);
-    unsigned* ticket = reinterpret_cast<unsigned*>(p + 16);
-    LinAgg* aggs = reinterpret_cast<LinAgg*>(p + 64);
-    LinAgg* prefixes = aggs + tiles;
-    unsigned long long* st2 = reinterpret_cast<unsigned long long*>(prefixes + tiles);
-    unsigned* st1 = reinterpret_cast<unsigned*>(st2 + tiles);
-    GPC_PROF_BYTES("linear_track", 12.0 * n_ev);
-    linear_track_kernel<<<tiles, LIN_THREADS, 0, stream>>>(keys, tags, (unsigned)n_ev, wp, out_pos,
-                                                          out_val, aggs, prefixes, st1, st2,
-                                                          ticket, count);
+    // distinct starts + multiplicity prefix
+    GPC_CUDA(head.alloc(n, stream));
+    GPC_CUDA(offs.alloc((size_t)n * 4, stream));
+    GPC_CUDA(total.alloc(8, stream));
+    GPC_PROF("unique_flag");
+    unique_flag_kernel<<<div_up(n, 256), 256, 0, stream>>>(keys, n, head.as<uint8_t>());
     GPC_LAUNCH_CHECK();
-    unsigned long long h = 0;
+    GPC_TRY(exclusive_scan<uint8_t>(head.as<uint8_t>(), offs.as<uint32_t>(), n,
+                                    total.as<unsigned long long>(), stream));
+    unsigned long long hU = 0;
     int herr = 0;
-    GPC_CUDA(cudaMemcpyAsync(&h, count, 8, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaMemcpyAsync(&hU, total.p, 8, cudaMemcpyDeviceToHost, stream));
     GPC_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, stream));
     GPC_CUDA(cudaStreamSynchronize(stream));
     if (herr) {
         set_error("Interval has node(s) not part of graph/pileup");
         return herr;
     }
+    const unsigned U = (unsigned)hU;
+    GPC_CUDA(xu.alloc((size_t)U * 8, stream));
+    GPC_CUDA(wpre.alloc((size_t)(U + 1) * 4, stream));
+    GPC_PROF("unique_emit");
+    unique_emit_kernel<<<div_up(n, 256), 256, 0, stream>>>(keys, n, head.as<uint8_t>(),
+                                                           offs.as<uint32_t>(), U, xu.as<double>(),
+                                                           wpre.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
+    // splitters: every MERGE_T-th element of every view, sorted
+    const unsigned per_view = div_up(U, MERGE_T);
+    const unsigned ns = per_view * nq;
+    Scratch sp0, sp1, bounds, sc;
+    GPC_CUDA(sp0.alloc((size_t)ns * 8, stream));
+    GPC_CUDA(sp1.alloc((size_t)ns * 8, stream));
+    GPC_PROF("splitters");
+    splitters_kernel<<<div_up(ns, 256), 256, 0, stream>>>(xu.as<double>(), U, wp, per_view,
+                                                          sp0.as<unsigned long long>());
+    GPC_LAUNCH_CHECK();
+    bool sp_tmp = false;
+    GPC_TRY((radix_sort<unsigned long long, false>(sp0.as<unsigned long long>(),
+                                                   sp1.as<unsigned long long>(), nullptr, nullptr,
+                                                   ns, 0, 64, true, &sp_tmp, stream)));
+    const unsigned long long* sp = sp_tmp ? sp1.as<unsigned long long>() : sp0.as<unsigned long long>();
+    const unsigned n_bounds = ns + 2;
+    Scratch brank, pick;
+    GPC_CUDA(bounds.alloc((size_t)n_bounds * nq * 4, stream));
+    GPC_CUDA(brank.alloc((size_t)n_bounds * 8, stream));
+    GPC_PROF("tile_bounds");
+    tile_bounds_kernel<<<div_up((size_t)n_bounds * nq, 256), 256, 0, stream>>>(
+        xu.as<double>(), U, wp, sp, ns, bounds.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
+    GPC_PROF("boundary_rank");
+    boundary_rank_kernel<<<div_up(n_bounds, 256), 256, 0, stream>>>(bounds.as<uint32_t>(), n_bounds,
+                                                                  nq, brank.as<unsigned long long>());
+    GPC_LAUNCH_CHECK();
+    const unsigned long long total_ev = (unsigned long long)nq * U;
+    const unsigned long long stride = MERGE_CAP - (unsigned long long)nq * (MERGE_T + 2);
+    const unsigned n_tiles = (unsigned)((total_ev + stride - 1) / stride);
+    GPC_CUDA(pick.alloc((size_t)(n_tiles + 1) * 4, stream));
+    GPC_PROF("pick_tiles");
+    pick_tiles_kernel<<<div_up(n_tiles + 1, 256), 256, 0, stream>>>(
+        brank.as<unsigned long long>(), n_bounds, n_tiles, stride, pick.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
+    size_t bytes = (size_t)n_tiles * 8 + 64;
+    GPC_CUDA(sc.alloc(bytes, stream));
+    GPC_CUDA(cudaMemsetAsync(sc.p, 0, bytes, stream));
+    unsigned long long* count = sc.as<unsigned long long>();
+    unsigned* ticket = reinterpret_cast<unsigned*>(count + 1);
+    unsigned long long* status = count + 8;
+    static bool smem_set = false;
+    if (!smem_set) {
+        GPC_CUDA(cudaFuncSetAttribute(linear_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)MERGE_SMEM));
+        smem_set = true;
+    }
+    GPC_PROF_BYTES("linear_tiles", (8.0 + 4.0) * nq * U);
+    linear_tiles_kernel<<<n_tiles, MERGE_THREADS, MERGE_SMEM, stream>>>(
+        xu.as<double>(), wpre.as<uint32_t>(), wp, bounds.as<uint32_t>(), pick.as<uint32_t>(), n_tiles,
+        out_pos, out_val, status, ticket, count, err);
+    GPC_LAUNCH_CHECK();
+    unsigned long long h = 0;
+    GPC_CUDA(cudaMemcpyAsync(&h, count, 8, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    if (herr) {
+        set_error("linear track: merge tile overflow");
+        return herr;
+    }
     *n_out = h;
-    prof_add_bytes("linear_track", 16.0 * (double)h);
+    prof_add_bytes("linear_tiles", 16.0 * (double)h);
     return GPC_OK;
 }
 

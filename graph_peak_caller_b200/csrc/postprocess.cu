@@ -371,6 +371,52 @@ __global__ void hole_relax_kernel(gpc_graph_t g, VertexView vw, const uint32_t* 
     fr[u] = best;
 }
 
+// All rounds in one launch for the usual small active set: one CTA, a block
+// barrier between rounds (in-place relaxation is monotone, so a round that
+// sees some fresh values only converges faster).
+constexpr int RELAX_ROUNDS = 37;
+__global__ void __launch_bounds__(1024)
+hole_relax_fused_kernel(gpc_graph_t g, VertexView vw, const uint32_t* __restrict__ list,
+                        uint32_t n_list, const uint32_t* __restrict__ p_start,
+                        const uint32_t* __restrict__ p_end, const uint8_t* __restrict__ is_exit,
+                        int32_t* __restrict__ to, int32_t* __restrict__ fr) {
+    for (int round = 0; round < RELAX_ROUNDS; ++round) {
+        for (uint32_t i = threadIdx.x; i < n_list; i += blockDim.x) {
+            uint32_t u = list[i];
+            int t = vw.type_of[u];
+            uint32_t a = vw.node_of[u];
+            uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
+            int size = (int)(p_end[u] - p_start[u]);
+            volatile int32_t* vto = to;
+            volatile int32_t* vfr = fr;
+            if (t != PIECE_TAIL) {
+                int best = vto[u];
+                for (uint32_t e = r0.z; e < r1.z; ++e) {
+                    int32_t w = vw.out_vertex[g.pred[e]];
+                    if (w >= 0) {
+                        int d = vto[w];
+                        if (d < INF_I) best = min(best, d + (int)(p_end[w] - p_start[w]));
+                    }
+                }
+                vto[u] = best;
+            }
+            int best = vfr[u];
+            if (is_exit[u]) best = min(best, size);
+            if (t != PIECE_HEAD) {
+                for (uint32_t e = r0.y; e < r1.y; ++e) {
+                    int32_t w = vw.in_vertex[g.succ[e]];
+                    if (w >= 0) {
+                        int d = vfr[w];
+                        if (d < INF_I) best = min(best, d + size);
+                    }
+                }
+            }
+            vfr[u] = best;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void hole_decide_kernel(const uint32_t* __restrict__ list, uint32_t n_list,
                                    const int32_t* __restrict__ to, const int32_t* __restrict__ fr,
                                    int max_size, uint8_t* __restrict__ p_keep) {
@@ -668,6 +714,8 @@ __global__ void peak_lengths_kernel(uint32_t n_comp, uint32_t n_internal,
     else if (i < n_comp + n_internal) n_nodes[i] = 1;
 }
 
+// One warp per peak: lanes take the path nodes round-robin, each scans the q
+// runs under its piece; warp reductions give length and score.
 __global__ void peaks_kernel(gpc_graph_t g, uint32_t n_comp, uint32_t n_internal,
                              const uint32_t* __restrict__ comp_ptr, const uint32_t* __restrict__ path,
                              const uint32_t* __restrict__ path_len, const uint8_t* __restrict__ info,
@@ -680,14 +728,15 @@ __global__ void peaks_kernel(gpc_graph_t g, uint32_t n_comp, uint32_t n_internal
                              int32_t* __restrict__ out_start, int32_t* __restrict__ out_end,
                              int32_t* __restrict__ out_length, double* __restrict__ out_score,
                              uint8_t* __restrict__ out_info) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = lane_id();
     if (i >= n_comp + n_internal) return;
-    uint32_t o = node_ptr[i];
-    uint32_t len = i < n_comp ? path_len[i] : 1;
+    const uint32_t o = node_ptr[i];
+    const uint32_t len = i < n_comp ? path_len[i] : 1;
     double best = -INFINITY;
     long long bp = 0;
     uint32_t first_start = 0, last_end = 0;
-    for (uint32_t k = 0; k < len; ++k) {
+    for (uint32_t k = lane; k < len; k += 32) {
         uint32_t pid = i < n_comp ? piece_of_vertex[path[comp_ptr[i] + k]]
                                   : internal_piece[i - n_comp];
         uint32_t v = p_node[pid];
@@ -708,11 +757,20 @@ __global__ void peaks_kernel(gpc_graph_t g, uint32_t n_comp, uint32_t n_internal
             while (j < n_q && q_pos[j] < b) { best = fmax(best, q_val[j]); ++j; }
         }
     }
-    out_start[i] = (int32_t)first_start;
-    out_end[i] = (int32_t)last_end;
-    out_length[i] = (int32_t)bp;
-    out_score[i] = bp == 0 ? 0.0 : best;
-    out_info[i] = i < n_comp ? info[i] : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        best = fmax(best, __shfl_xor_sync(FULL, best, d));
+        bp += __shfl_xor_sync(FULL, bp, d);
+        first_start += __shfl_xor_sync(FULL, first_start, d);   // only one lane is non-zero
+        last_end += __shfl_xor_sync(FULL, last_end, d);
+    }
+    if (lane == 0) {
+        out_start[i] = (int32_t)first_start;
+        out_end[i] = (int32_t)last_end;
+        out_length[i] = (int32_t)bp;
+        out_score[i] = bp == 0 ? 0.0 : best;
+        out_info[i] = i < n_comp ? info[i] : 0;
+    }
 }
 
 __global__ void score_keys_kernel(const double* __restrict__ score, uint32_t n,
@@ -888,13 +946,21 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
             compact_u32_kernel<<<GRID(P)>>>(active.as<uint8_t>(), aoffs.as<uint32_t>(), P,
                                             alist.as<uint32_t>());
             GPC_LAUNCH_CHECK();
-            for (int round = 0; round < 37; ++round) {
-                GPC_PROF("hole_relax");
-                hole_relax_kernel<<<GRID(n_active)>>>(*graph, vw, alist.as<uint32_t>(),
-                                                      (uint32_t)n_active, p_start.as<uint32_t>(),
-                                                      p_end.as<uint32_t>(), is_exit.as<uint8_t>(),
-                                                      to.as<int32_t>(), fr.as<int32_t>());
+            if (n_active <= 32768) {
+                GPC_PROF("hole_relax_fused");
+                hole_relax_fused_kernel<<<1, 1024, 0, stream>>>(
+                    *graph, vw, alist.as<uint32_t>(), (uint32_t)n_active, p_start.as<uint32_t>(),
+                    p_end.as<uint32_t>(), is_exit.as<uint8_t>(), to.as<int32_t>(), fr.as<int32_t>());
                 GPC_LAUNCH_CHECK();
+            } else {
+                for (int round = 0; round < RELAX_ROUNDS; ++round) {
+                    GPC_PROF("hole_relax");
+                    hole_relax_kernel<<<GRID(n_active)>>>(*graph, vw, alist.as<uint32_t>(),
+                                                          (uint32_t)n_active, p_start.as<uint32_t>(),
+                                                          p_end.as<uint32_t>(), is_exit.as<uint8_t>(),
+                                                          to.as<int32_t>(), fr.as<int32_t>());
+                    GPC_LAUNCH_CHECK();
+                }
             }
             GPC_PROF("hole_decide");
             hole_decide_kernel<<<GRID(n_active)>>>(alist.as<uint32_t>(), (uint32_t)n_active,
@@ -1119,7 +1185,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     uint32_t tn = (uint32_t)total_nodes;
     GPC_CUDA(cudaMemcpyAsync(peak_node_ptr + n_pk, &tn, 4, cudaMemcpyHostToDevice, stream));
     GPC_PROF("peaks");
-    peaks_kernel<<<GRID(n_pk)>>>(*graph, (uint32_t)n_comp, (uint32_t)n_i, comp_ptr.as<uint32_t>(),
+    peaks_kernel<<<GRID((size_t)n_pk * 32)>>>(*graph, (uint32_t)n_comp, (uint32_t)n_i, comp_ptr.as<uint32_t>(),
                                  path.as<uint32_t>(), path_len.as<uint32_t>(), info.as<uint8_t>(),
                                  piece_of_vertex.as<uint32_t>(), internal_piece.as<uint32_t>(),
                                  p_node.as<uint32_t>(), p_start.as<uint32_t>(), p_end.as<uint32_t>(),

@@ -14,6 +14,8 @@
 // q-values: the (p -> base pairs) table is a hash aggregation with warp-level
 // pre-combining, the distinct p are radix sorted descending, ranked, turned
 // into q with the running minimum, and looked up per run by exact key.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "poisson.cuh"
 #include "radix_sort.cuh"
@@ -21,66 +23,184 @@
 
 namespace gpc {
 
+// Opportunistic memo of p(count, lambda): tracks take few distinct (count,
+// lambda) pairs (tens of thousands) compared to runs (tens of millions).  The
+// first thread that claims the slot of a pair evaluates it and publishes the
+// result; later threads reuse it.  Nobody ever waits: a slot that is claimed
+// but not yet published is simply recomputed by the visitor.
+//
+// One 32-byte, write-once entry per pair, read with ordinary (L1-cached) loads:
+// an entry whose tag says READY was complete when the line was fetched, and a
+// stale line can only say "empty"/"claimed", in which case the atomic CAS
+// (served by L2) tells the truth.  Common pairs are therefore served from L1.
+struct __align__(32) MemoEntry {
+    unsigned long long tag;    // 0 empty | hash|1 claimed | hash|3 ready (hash has bits 0-1 clear)
+    double count, lam, p;
+};
+struct PMemo {
+    MemoEntry* e;              // [mask + 1] or nullptr
+    unsigned mask;
+};
+
+__device__ __forceinline__ unsigned long long memo_hash(double count, double lam) {
+    unsigned long long x = (unsigned long long)__double_as_longlong(lam);
+    x ^= (unsigned long long)__double_as_longlong(count) * 0x9e3779b97f4a7c15ull;
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x & ~3ull;
+}
+
+__device__ __forceinline__ double memo_pvalue(const PMemo& m, double count, double lam) {
+    if (count == 0.0) return 0.0;
+#ifdef GPC_EXP_DUMMY_P
+    return count + lam;
+#endif
+#ifdef GPC_EXP_NO_MEMO
+    return neglog10_poisson_sf(count, lam);
+#endif
+    if (!m.e) return neglog10_poisson_sf(count, lam);
+    const unsigned long long h = memo_hash(count, lam);
+    unsigned s = (unsigned)(h >> 20) & m.mask;
+    for (int probe = 0; probe < 16; ++probe) {
+        MemoEntry* e = &m.e[s];
+        unsigned long long tag = e->tag;                       // L1-cached
+        if (tag == (h | 3ull)) {
+            if (e->count == count && e->lam == lam) return e->p;
+        } else if ((tag | 3ull) != (h | 3ull)) {
+            if (tag != 0ull && (tag & 3ull) == 3ull) {         // another pair lives here
+                s = (s + 1) & m.mask;
+                continue;
+            }
+        }
+        if (tag != (h | 3ull)) {
+            // empty or claimed as far as this SM's L1 knows: ask L2
+            unsigned long long old = atomicCAS(&e->tag, 0ull, h | 1ull);
+            if (old == 0ull) {                                 // mine: evaluate and publish
+                double p = neglog10_poisson_sf(count, lam);
+                e->count = count;
+                e->lam = lam;
+                e->p = p;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned long long*>(&e->tag) = h | 3ull;
+                return p;
+            }
+            if (old == (h | 3ull)) {                           // ready in L2, stale in L1
+                if (__ldcg(&e->count) == count && __ldcg(&e->lam) == lam) return __ldcg(&e->p);
+            } else if (old == (h | 1ull)) {
+                break;                                         // owner still busy: do not wait
+            }
+        }
+        s = (s + 1) & m.mask;                                  // different pair: next slot
+    }
+    return neglog10_poisson_sf(count, lam);
+}
+
 constexpr int PV_THREADS = 256;
 constexpr int PV_ITEMS = 8;
 constexpr int PV_TILE = PV_THREADS * PV_ITEMS;
 
+// Coarse merge-path partition: number of sample entries among the first
+// t * PV_TILE merged elements (ties: sample entry first), one thread per tile edge.
+__global__ void pv_partition_kernel(const uint32_t* __restrict__ spos, unsigned ns,
+                                    const uint32_t* __restrict__ cpos, unsigned nc,
+                                    unsigned n_tiles, uint32_t* __restrict__ split) {
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    unsigned long long dd = (unsigned long long)t * PV_TILE;
+    unsigned d = (unsigned)min(dd, (unsigned long long)ns + nc);
+    unsigned lo = d > nc ? d - nc : 0, hi = min(d, ns);
+    while (lo < hi) {
+        unsigned mid = (lo + hi) >> 1;
+        if (spos[mid] <= cpos[d - 1 - mid]) lo = mid + 1; else hi = mid;
+    }
+    split[t] = lo;
+}
+
 __global__ void __launch_bounds__(PV_THREADS)
 pvalues_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sval, unsigned ns,
                double sample_scale, const uint32_t* __restrict__ cpos,
-               const double* __restrict__ cval, unsigned nc, double control_scale,
-               uint32_t* __restrict__ out_pos,
+               const double* __restrict__ cval, unsigned nc, double control_scale, PMemo memo,
+               const uint32_t* __restrict__ split, uint32_t* __restrict__ out_pos,
                double* __restrict__ out_p, unsigned long long* __restrict__ status,
                unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_count) {
+    // slices of both tracks that this tile merges, plus one element before
+    // (state in force at the tile's left edge) and one after (look-ahead)
+    __shared__ uint32_t a_pos[PV_TILE + 2];
+    __shared__ int32_t a_val[PV_TILE + 2];
+    __shared__ uint32_t b_pos[PV_TILE + 2];
+    __shared__ double b_val[PV_TILE + 2];
     __shared__ unsigned s_slot;
     __shared__ int s_scan[33];
     __shared__ unsigned long long s_obase;
     const unsigned tile = claim_tile(ticket, &s_slot);
     const unsigned total = ns + nc;
-    const unsigned d0 = min(total, tile * PV_TILE + threadIdx.x * PV_ITEMS);
-    const unsigned d1 = min(total, d0 + PV_ITEMS);
+    const unsigned t0 = min(total, tile * PV_TILE), t1 = min(total, t0 + PV_TILE);
+    const unsigned i_lo = split[tile], i_hi = split[tile + 1];
+    const unsigned j_lo = t0 - i_lo, j_hi = t1 - i_hi;
+    const unsigned na = i_hi - i_lo, nb = j_hi - j_lo;
+    // slot k of a_* holds global sample entry i_lo - 1 + k  (k = 0 .. na + 1)
+    for (unsigned k = threadIdx.x; k < na + 2; k += PV_THREADS) {
+        long long gi = (long long)i_lo - 1 + k;
+        bool ok = gi >= 0 && gi < (long long)ns;
+        a_pos[k] = ok ? spos[gi] : 0xffffffffu;
+        a_val[k] = ok ? sval[gi] : 0;
+    }
+    for (unsigned k = threadIdx.x; k < nb + 2; k += PV_THREADS) {
+        long long gj = (long long)j_lo - 1 + k;
+        bool ok = gj >= 0 && gj < (long long)nc;
+        b_pos[k] = ok ? cpos[gj] : 0xffffffffu;
+        b_val[k] = ok ? __dmul_rn(cval[gj], control_scale) : 0.0;
+    }
+    __syncthreads();
+    // local coordinates: sample entry x <-> a_*[x + 1], control entry y <-> b_*[y + 1]
+    const unsigned m = na + nb;
+    const unsigned d0 = min(m, threadIdx.x * PV_ITEMS), d1 = min(m, d0 + PV_ITEMS);
     uint32_t e_pos[PV_ITEMS];
     double e_p[PV_ITEMS];
     int cnt = 0;
     if (d0 < d1) {
-        // merge-path split of diagonal d0 (ties: sample entry first)
-        unsigned lo = d0 > nc ? d0 - nc : 0, hi = min(d0, ns);
+        // merge-path split of the local diagonal d0 (ties: sample entry first)
+        unsigned lo = d0 > nb ? d0 - nb : 0, hi = min(d0, na);
         while (lo < hi) {
             unsigned mid = (lo + hi) >> 1;
-            if (spos[mid] <= cpos[d0 - 1 - mid]) lo = mid + 1; else hi = mid;
+            if (a_pos[mid + 1] <= b_pos[d0 - 1 - mid + 1]) lo = mid + 1; else hi = mid;
         }
         unsigned i = lo, j = d0 - lo;
-        // state in force before my first element's position
+        // end of the previous position group = state before my first position
         uint32_t first_pos;
         {
-            bool take_s = i < ns && (j >= nc || spos[i] <= cpos[j]);
-            first_pos = take_s ? spos[i] : cpos[j];
+            bool take_s = i < na && (j >= nb || a_pos[i + 1] <= b_pos[j + 1]);
+            first_pos = take_s ? a_pos[i + 1] : b_pos[j + 1];
         }
-        unsigned ib = i, jb = j;
-        while (ib > 0 && spos[ib - 1] == first_pos) --ib;
-        while (jb > 0 && cpos[jb - 1] == first_pos) --jb;
-        bool have_prev = (ib > 0) || (jb > 0);
+        bool have_prev;
         double prev_p = 0.0;
-        if (have_prev) {
-            double k = ib > 0 ? (double)sval[ib - 1] : 0.0;
-            double lam = jb > 0 ? __dmul_rn(cval[jb - 1], control_scale) : 0.0;
-            prev_p = neglog10_poisson_sf(k == 0.0 ? 0.0 : k * sample_scale, lam);
-        }
-        double k_cur = i > 0 ? (double)sval[i - 1] : 0.0;
-        double lam_cur = j > 0 ? __dmul_rn(cval[j - 1], control_scale) : 0.0;
-        for (unsigned d = d0; d < d1; ++d) {
-            bool take_s = i < ns && (j >= nc || spos[i] <= cpos[j]);
-            uint32_t pos;
-            if (take_s) { pos = spos[i]; k_cur = (double)sval[i]; ++i; }
-            else { pos = cpos[j]; lam_cur = __dmul_rn(cval[j], control_scale); ++j; }
-            bool more = i < ns || j < nc;
-            uint32_t next_pos = 0;
-            if (more) {
-                bool ts = i < ns && (j >= nc || spos[i] <= cpos[j]);
-                next_pos = ts ? spos[i] : cpos[j];
+        {
+            // walk back over entries of the same position; slot 0 is the entry just
+            // before the tile, anything earlier is read from global memory (rare)
+            long long gi = (long long)i_lo + i, gj = (long long)j_lo + j;   // global cursors
+            while (gi > 0 && (gi - 1 >= (long long)i_lo - 1 ? a_pos[gi - i_lo] : spos[gi - 1]) == first_pos) --gi;
+            while (gj > 0 && (gj - 1 >= (long long)j_lo - 1 ? b_pos[gj - j_lo] : cpos[gj - 1]) == first_pos) --gj;
+            have_prev = gi > 0 || gj > 0;
+            if (have_prev) {
+                double k = 0.0, lam = 0.0;
+                if (gi > 0) k = (gi - 1 >= (long long)i_lo - 1) ? (double)a_val[gi - i_lo] : (double)sval[gi - 1];
+                if (gj > 0) lam = (gj - 1 >= (long long)j_lo - 1) ? b_val[gj - j_lo]
+                                                                   : __dmul_rn(cval[gj - 1], control_scale);
+                prev_p = memo_pvalue(memo, k == 0.0 ? 0.0 : k * sample_scale, lam);
             }
-            if (!more || next_pos != pos) {
-                double p = neglog10_poisson_sf(k_cur == 0.0 ? 0.0 : k_cur * sample_scale, lam_cur);
+        }
+        // values in force before my first element (slot 0 = entry before the tile; empty -> 0)
+        double k_cur = (double)a_val[i], lam_cur = b_val[j];
+        for (unsigned d = d0; d < d1; ++d) {
+            bool take_s = i < na && (j >= nb || a_pos[i + 1] <= b_pos[j + 1]);
+            uint32_t pos;
+            if (take_s) { pos = a_pos[i + 1]; k_cur = (double)a_val[i + 1]; ++i; }
+            else { pos = b_pos[j + 1]; lam_cur = b_val[j + 1]; ++j; }
+            // look-ahead: slots na + 1 / nb + 1 hold the first entries after the tile
+            uint32_t next_pos = min(a_pos[i + 1], b_pos[j + 1]);     // 0xffffffff when exhausted
+            if (next_pos != pos) {
+                double p = memo_pvalue(memo, k_cur == 0.0 ? 0.0 : k_cur * sample_scale, lam_cur);
                 if (!have_prev || p != prev_p) {
                     e_pos[cnt] = pos;
                     e_p[cnt] = p;
@@ -93,9 +213,12 @@ pvalues_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
     }
     int tile_out;
     int o = block_excl_sum<int>(cnt, s_scan, tile_out);
-    if (threadIdx.x == 0) {
-        s_obase = lookback_excl(status, tile, (unsigned long long)tile_out);
-        if (tile == gridDim.x - 1) *out_count = s_obase + tile_out;
+    if (threadIdx.x < 32) {
+        unsigned long long b = lookback_excl_warp(status, tile, (unsigned long long)tile_out);
+        if (threadIdx.x == 0) {
+            s_obase = b;
+            if (tile == gridDim.x - 1) *out_count = b + tile_out;
+        }
     }
     __syncthreads();
     unsigned long long w = s_obase + o;
@@ -312,11 +435,31 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
     unsigned long long* count = sc.as<unsigned long long>();
     unsigned* ticket = reinterpret_cast<unsigned*>(count + 1);
     unsigned long long* status = count + 4;
+    // memo table: 2^20 entries of 32 B (stays in L2); small inputs do without
+    Scratch memo_buf;
+    PMemo memo;
+    memo.e = nullptr;
+    memo.mask = 0;
+    if (total >= (1u << 16)) {
+        int lg = 20;
+        if (const char* v = getenv("GPC_MEMO_LOG2")) lg = atoi(v);
+        const size_t cap = (size_t)1 << lg;
+        GPC_CUDA(memo_buf.alloc(cap * sizeof(MemoEntry), stream));
+        GPC_CUDA(cudaMemsetAsync(memo_buf.p, 0, cap * sizeof(MemoEntry), stream));
+        memo.e = memo_buf.as<MemoEntry>();
+        memo.mask = (unsigned)(cap - 1);
+    }
+    Scratch split;
+    GPC_CUDA(split.alloc((size_t)(tiles + 1) * 4, stream));
+    GPC_PROF("pv_partition");
+    pv_partition_kernel<<<div_up(tiles + 1, 256), 256, 0, stream>>>(
+        sample_pos, (unsigned)n_sample, control_pos, (unsigned)n_control, tiles, split.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
     GPC_PROF_BYTES("pvalues", 8.0 * n_sample + 12.0 * n_control);
     pvalues_kernel<<<tiles, PV_THREADS, 0, stream>>>(sample_pos, sample_val, (unsigned)n_sample,
                                                     sample_scale, control_pos, control_val,
-                                                    (unsigned)n_control, control_scale, out_pos,
-                                                    out_p, status,
+                                                    (unsigned)n_control, control_scale, memo,
+                                                    split.as<uint32_t>(), out_pos, out_p, status,
                                                     ticket, count);
     GPC_LAUNCH_CHECK();
     unsigned long long h = 0;

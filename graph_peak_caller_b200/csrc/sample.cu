@@ -347,12 +347,16 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
     int tot0, tot1;
     int o0 = block_excl_sum<int>(c0, s_scan, tot0);
     int o1 = block_excl_sum<int>(c1, s_scan, tot1);
-    if (threadIdx.x == 0) {
-        s_obase[0] = lookback_excl(st2, tile, (unsigned long long)tot0);
-        s_obase[1] = lookback_excl(st3, tile, (unsigned long long)tot1);
-        if (tile == gridDim.x - 1) {
-            out_counts[0] = s_obase[0] + tot0;
-            out_counts[1] = s_obase[1] + tot1;
+    if (threadIdx.x < 32) {
+        unsigned long long b0 = lookback_excl_warp(st2, tile, (unsigned long long)tot0);
+        unsigned long long b1 = lookback_excl_warp(st3, tile, (unsigned long long)tot1);
+        if (threadIdx.x == 0) {
+            s_obase[0] = b0;
+            s_obase[1] = b1;
+            if (tile == gridDim.x - 1) {
+                out_counts[0] = b0 + tot0;
+                out_counts[1] = b1 + tot1;
+            }
         }
     }
     __syncthreads();

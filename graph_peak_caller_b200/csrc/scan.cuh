@@ -39,10 +39,12 @@ excl_scan_kernel(const InT* __restrict__ in, uint32_t* __restrict__ out, unsigne
     }
     unsigned tile_total;
     unsigned ex = block_excl_sum<unsigned>(sum, s_scan, tile_total);
-    if (threadIdx.x == 0) {
-        unsigned long long p = lookback_excl(status, tile, tile_total);
-        s_prefix = p;
-        if (tile == gridDim.x - 1 && total) *total = p + tile_total;
+    if (threadIdx.x < 32) {
+        unsigned long long p = lookback_excl_warp(status, tile, tile_total);
+        if (threadIdx.x == 0) {
+            s_prefix = p;
+            if (tile == gridDim.x - 1 && total) *total = p + tile_total;
+        }
     }
     __syncthreads();
     unsigned run = (unsigned)s_prefix + ex;
