@@ -153,8 +153,8 @@ __device__ __forceinline__ unsigned long long lookback_excl(unsigned long long* 
         if (st == LB_PREFIX) break;
         --t;
     }
-    lb_store(&status[tile], LB_PREFIX | (excl + agg));
-    return excl;
+    lb_store(&status[tile], LB_PREFIX | ((excl + agg) & LB_MASK));
+    return excl & LB_MASK;
 }
 
 // Warp-wide variant: all 32 lanes of ONE warp call it with the same arguments.
@@ -164,6 +164,7 @@ __device__ __forceinline__ unsigned long long lookback_excl_warp(unsigned long l
                                                                  unsigned tile,
                                                                  unsigned long long agg) {
     const unsigned lane = threadIdx.x & 31;
+    agg &= LB_MASK;
     if (tile == 0) {
         if (lane == 0) lb_store(&status[0], LB_PREFIX | agg);
         return 0;
@@ -187,8 +188,9 @@ __device__ __forceinline__ unsigned long long lookback_excl_warp(unsigned long l
         if (first_pref < 32) break;
         newest -= 32;
     }
-    if (lane == 0) lb_store(&status[tile], LB_PREFIX | (excl + agg));
-    return excl;
+    // sums are taken modulo 2^62, so packed signed payloads work as well
+    if (lane == 0) lb_store(&status[tile], LB_PREFIX | ((excl + agg) & LB_MASK));
+    return excl & LB_MASK;
 }
 
 __device__ __forceinline__ uint4 node_record(const gpc_graph_t& g, uint32_t v) {

@@ -290,30 +290,38 @@ linear_tiles_kernel(const double* __restrict__ xu, const uint32_t* __restrict__ 
         }
     }
     // emit one breakpoint per group of equal keys whose lambda differs from the
-    // lambda before the group (groups never span tiles: tiles are cut by value)
+    // lambda before the group (groups never span tiles: tiles are cut by value).
+    // `was` is the lambda in force before the current group; inside a chunk it is
+    // simply the previous group's lambda, only the chunk's first group has to
+    // reconstruct it (its group may have started in an earlier thread's chunk).
     double e_pos[MERGE_PER_THREAD], e_val[MERGE_PER_THREAD];
     int cnt = 0;
+    double was = 0.0;
+    if (a0 < a1) {
+        int before[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) before[k] = run[k];
+        for (unsigned g = a0; g-- > 0;) {              // earlier members of my first group
+            if (s_key[g] != s_key[a0]) break;
+            int qq = s_tag[g], mm = (int)s_mul[g];
+            before[qq >> 1] -= (qq & 1) ? -mm : mm;
+            if (qq == 0) before[3] -= mm;
+        }
+        was = lambda_of(before, wp);
+    }
     for (unsigned r = a0; r < a1; ++r) {
         int q = s_tag[r], mul = (int)s_mul[r];
         run[q >> 1] += (q & 1) ? -mul : mul;
         if (q == 0) run[3] += mul;
         bool last = (r + 1 >= m) || s_key[r + 1] != s_key[r];
         if (last) {
-            int before[NC];
-#pragma unroll
-            for (int k = 0; k < NC; ++k) before[k] = run[k];
-            for (unsigned g = r + 1; g-- > 0;) {
-                if (s_key[g] != s_key[r]) break;
-                int qq = s_tag[g], mm = (int)s_mul[g];
-                before[qq >> 1] -= (qq & 1) ? -mm : mm;
-                if (qq == 0) before[3] -= mm;
-            }
-            double now = lambda_of(run, wp), was = lambda_of(before, wp);
+            double now = lambda_of(run, wp);
             if (now != was && cnt < MERGE_PER_THREAD) {
                 e_pos[cnt] = key_to_f64(s_key[r]);
                 e_val[cnt] = now;
                 ++cnt;
             }
+            was = now;
         }
     }
     int tile_out;

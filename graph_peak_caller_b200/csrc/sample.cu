@@ -212,8 +212,8 @@ __global__ void __launch_bounds__(RUN_THREADS)
 events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
                       uint32_t* __restrict__ frag_idx, int32_t* __restrict__ frag_val,
                       uint32_t* __restrict__ dir_idx, int32_t* __restrict__ dir_val,
-                      RunAgg* __restrict__ aggs, RunAgg* __restrict__ prefixes,
-                      unsigned* __restrict__ st1 /* zeroed */,
+                      unsigned long long* __restrict__ st_tot /* zeroed */,
+                      unsigned long long* __restrict__ st_seg /* zeroed */,
                       unsigned long long* __restrict__ st2 /* zeroed */,
                       unsigned long long* __restrict__ st3 /* zeroed */,
                       unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts) {
@@ -221,6 +221,7 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
     __shared__ int s_scan[33];
     __shared__ Seg s_seg[RUN_THREADS / 32];
     __shared__ RunAgg s_carry;
+    __shared__ Seg s_all;
     __shared__ unsigned long long s_obase[2];
     const unsigned tile = claim_tile(ticket, &s_slot);
     const unsigned base = tile * RUN_TILE + threadIdx.x * RUN_ITEMS;
@@ -274,45 +275,52 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
         up.b = __shfl_up_sync(FULL, incl.b, 1);
         if (lane_id() > 0) carry = seg_combine(carry, up);
     }
-    // tile aggregate -> first chained scan (totals + open-group partial sums)
+    // tile aggregates: totals go through a packed single-word chained scan; the
+    // open-group sums only need the tiles back to the nearest one that contains
+    // a position change, so they are published once and never prefixed
     if (threadIdx.x == RUN_THREADS - 1) {
         Seg all = seg_combine(carry, seg);
-        RunAgg mine;
-        mine.tot[0] = tile_f; mine.tot[1] = tile_d;
-        mine.seg[0] = all.a; mine.seg[1] = all.b; mine.has_head = all.head;
-        RunAgg in;           // exclusive prefix over earlier tiles
-        in.tot[0] = in.tot[1] = in.seg[0] = in.seg[1] = in.has_head = 0;
-        volatile unsigned* vs = st1;
-        if (tile > 0) {
-            aggs[tile] = mine;
-            __threadfence();
-            vs[tile] = 1;
-            // walk back; `in` is built right-to-left
-            bool seg_closed = false;
-            int t = (int)tile - 1;
-            while (true) {
-                unsigned s = vs[t];
-                if (s == 0) continue;
-                __threadfence();
-                RunAgg a = (s == 2) ? prefixes[t] : aggs[t];
-                in.tot[0] += a.tot[0]; in.tot[1] += a.tot[1];
-                if (!seg_closed) {
-                    in.seg[0] += a.seg[0]; in.seg[1] += a.seg[1];
-                    if (a.has_head) seg_closed = true;
-                }
-                if (s == 2) break;
-                --t;
-            }
+        s_all = all;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        const Seg all = s_all;
+        if (lane == 0)
+            lb_store(&st_seg[tile], (1ull << 62) | ((unsigned long long)(all.head ? 1 : 0) << 61) |
+                                        ((unsigned long long)((unsigned)all.a & 0x3fffffffu) << 30) |
+                                        (unsigned long long)((unsigned)all.b & 0x3fffffffu));
+        int in_a = 0, in_b = 0;
+        int newest = (int)tile - 1;
+        while (newest >= 0) {
+            int t = newest - (int)lane;
+            unsigned long long w = (t >= 0) ? lb_load(&st_seg[t]) : ((1ull << 62) | (1ull << 61));
+            unsigned ready = __ballot_sync(FULL, (w >> 62) != 0);
+            unsigned heads = __ballot_sync(FULL, (w >> 61) & 1ull);
+            int first_head = heads ? (__ffs(heads) - 1) : 32;
+            unsigned need = (first_head >= 31) ? FULL : ((2u << first_head) - 1u);
+            if ((ready & need) != need) continue;
+            int a = ((int)((unsigned)(w >> 30) << 2)) >> 2;       // sign-extend 30 bits
+            int b = ((int)((unsigned)w << 2)) >> 2;
+            if ((int)lane > first_head) { a = 0; b = 0; }
+            in_a += warp_sum(a);
+            in_b += warp_sum(b);
+            if (first_head < 32) break;
+            newest -= 32;
         }
-        RunAgg pre;          // inclusive prefix = state after this tile
-        pre.tot[0] = in.tot[0] + mine.tot[0]; pre.tot[1] = in.tot[1] + mine.tot[1];
-        if (mine.has_head) { pre.seg[0] = mine.seg[0]; pre.seg[1] = mine.seg[1]; }
-        else { pre.seg[0] = in.seg[0] + mine.seg[0]; pre.seg[1] = in.seg[1] + mine.seg[1]; }
-        pre.has_head = 1;    // as a prefix the segment sums are complete
-        prefixes[tile] = pre;
-        __threadfence();
-        vs[tile] = 2;
-        s_carry = in;
+        long long packed = ((long long)tile_f << 32) + (long long)tile_d;
+        unsigned long long ex = lookback_excl_warp(st_tot, tile, (unsigned long long)packed & LB_MASK);
+        if (lane == 0) {
+            long long v = (long long)(ex << 2) >> 2;              // sign-extend 62 bits
+            int d = (int)(unsigned)(v & 0xffffffffll);
+            RunAgg in;
+            in.tot[1] = d;
+            in.tot[0] = (int)((v - (long long)d) >> 32);
+            in.seg[0] = in_a;
+            in.seg[1] = in_b;
+            in.has_head = 0;
+            s_carry = in;
+        }
     }
     __syncthreads();
     const RunAgg tin = s_carry;
@@ -537,21 +545,20 @@ extern "C" int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64
                                          false, &in_tmp, stream)));
     const uint32_t* sorted = in_tmp ? events_tmp : events;
     unsigned tiles = div_up(n_events, RUN_TILE);
-    size_t bytes = (size_t)tiles * (2 * sizeof(RunAgg) + 4 + 8 + 8) + 64;
+    size_t bytes = (size_t)tiles * 32 + 64;
     Scratch sc;
     GPC_CUDA(sc.alloc(bytes, stream));
     GPC_CUDA(cudaMemsetAsync(sc.p, 0, bytes, stream));
     char* p = sc.as<char>();
     unsigned long long* counts = reinterpret_cast<unsigned long long*>(p);            // 2
     unsigned* ticket = reinterpret_cast<unsigned*>(p + 16);
-    RunAgg* aggs = reinterpret_cast<RunAgg*>(p + 64);
-    RunAgg* prefixes = aggs + tiles;
-    unsigned long long* st2 = reinterpret_cast<unsigned long long*>(prefixes + tiles);
+    unsigned long long* st_tot = reinterpret_cast<unsigned long long*>(p + 64);
+    unsigned long long* st_seg = st_tot + tiles;
+    unsigned long long* st2 = st_seg + tiles;
     unsigned long long* st3 = st2 + tiles;
-    unsigned* st1 = reinterpret_cast<unsigned*>(st3 + tiles);
     GPC_PROF_BYTES("events_to_runs", 4.0 * n_events);
     events_to_runs_kernel<<<tiles, RUN_THREADS, 0, stream>>>(
-        sorted, (unsigned)n_events, frag_idx, frag_val, direct_idx, direct_val, aggs, prefixes, st1,
+        sorted, (unsigned)n_events, frag_idx, frag_val, direct_idx, direct_val, st_tot, st_seg,
         st2, st3, ticket, counts);
     GPC_LAUNCH_CHECK();
     unsigned long long h[2];
