@@ -1,4 +1,4 @@
-// LSD radix sort, 8-bit digits, "onesweep" structure:
+// LSD radix sort, 8- or 9-bit digits, "onesweep" structure:
 //   1. one histogram kernel counts every digit of every pass in a single read
 //      of the keys;
 //   2. per pass, one scatter kernel: each 4096-key tile ranks its keys with
@@ -12,8 +12,6 @@
 
 namespace gpc {
 
-constexpr int RS_BITS = 8;
-constexpr int RS_RADIX = 1 << RS_BITS;
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 
@@ -21,10 +19,11 @@ template <typename KeyT> struct RsTraits;
 template <> struct RsTraits<uint32_t> { static constexpr int ITEMS = 16; static constexpr int MAX_PASSES = 4; };
 template <> struct RsTraits<unsigned long long> { static constexpr int ITEMS = 8; static constexpr int MAX_PASSES = 8; };
 
-template <typename KeyT>
+template <typename KeyT, int RS_BITS>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_hist_kernel(const KeyT* __restrict__ keys, size_t n, int begin_bit, int n_passes,
-               unsigned* __restrict__ hist /* [n_passes][256] */) {
+               unsigned* __restrict__ hist /* [n_passes][RADIX] */) {
+    constexpr int RS_RADIX = 1 << RS_BITS;
     __shared__ unsigned sh[RsTraits<KeyT>::MAX_PASSES * RS_RADIX];
     for (int i = threadIdx.x; i < n_passes * RS_RADIX; i += RS_THREADS) sh[i] = 0;
     __syncthreads();
@@ -43,30 +42,45 @@ rs_hist_kernel(const KeyT* __restrict__ keys, size_t n, int begin_bit, int n_pas
     }
 }
 
-// One block per pass: exclusive scan of its 256 counts (in place) and a flag
-// telling whether one digit holds every key (pass can be skipped).
-static __global__ void __launch_bounds__(RS_RADIX)
+// One block per pass: exclusive scan of its RADIX counts (in place) and a flag
+// telling whether one digit holds every key (pass can be skipped).  Thread t
+// owns the DPT consecutive digits t*DPT .. t*DPT+DPT-1.
+template <int RS_BITS>
+__global__ void __launch_bounds__(RS_THREADS)
 rs_scan_hist_kernel(unsigned* __restrict__ hist, unsigned n, unsigned* __restrict__ trivial) {
+    constexpr int RS_RADIX = 1 << RS_BITS;
+    constexpr int DPT = RS_RADIX / RS_THREADS;
     __shared__ unsigned sm[33];
     unsigned* h = hist + blockIdx.x * RS_RADIX;
-    unsigned v = h[threadIdx.x];
-    if (v == n && n > 0) trivial[blockIdx.x] = 1;
+    unsigned v[DPT], sum = 0;
+#pragma unroll
+    for (int t = 0; t < DPT; ++t) {
+        v[t] = h[threadIdx.x * DPT + t];
+        if (v[t] == n && n > 0) trivial[blockIdx.x] = 1;
+        sum += v[t];
+    }
     unsigned total;
-    unsigned ex = block_excl_sum<unsigned>(v, sm, total);
-    h[threadIdx.x] = ex;
+    unsigned ex = block_excl_sum<unsigned>(sum, sm, total);
+#pragma unroll
+    for (int t = 0; t < DPT; ++t) {
+        h[threadIdx.x * DPT + t] = ex;
+        ex += v[t];
+    }
 }
 
 constexpr unsigned RS_ST_AGG = 1u << 30;
 constexpr unsigned RS_ST_PREFIX = 2u << 30;
 constexpr unsigned RS_ST_MASK = (1u << 30) - 1;
 
-template <typename KeyT, bool HAS_VALUE>
+template <typename KeyT, bool HAS_VALUE, int RS_BITS>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                    const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                    unsigned n, int shift, const unsigned* __restrict__ digit_base,
-                   unsigned* __restrict__ status /* [tiles][256], zeroed */,
+                   unsigned* __restrict__ status /* [tiles][RADIX], zeroed */,
                    unsigned* __restrict__ ticket /* zeroed */) {
+    constexpr int RS_RADIX = 1 << RS_BITS;
+    constexpr int DPT = RS_RADIX / RS_THREADS;
     constexpr int ITEMS = RsTraits<KeyT>::ITEMS;
     constexpr int TILE = RS_THREADS * ITEMS;
     __shared__ unsigned warp_hist[RS_WARPS][RS_RADIX];
@@ -111,39 +125,48 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out
         __syncwarp();
     }
     __syncthreads();
-    // per digit: exclusive scan over the warps, tile count
-    const unsigned d = threadIdx.x;   // RS_THREADS == RS_RADIX
-    unsigned tot = 0;
+    // per digit (thread t owns digits t*DPT ..): exclusive scan over the warps,
+    // tile count, then the chained scan of that digit over the tiles
+    unsigned tot[DPT], thread_sum = 0;
 #pragma unroll
-    for (int ww = 0; ww < RS_WARPS; ++ww) {
-        unsigned t = warp_hist[ww][d];
-        warp_hist[ww][d] = tot;
-        tot += t;
+    for (int t = 0; t < DPT; ++t) {
+        const unsigned d = threadIdx.x * DPT + t;
+        unsigned acc = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) {
+            unsigned c = warp_hist[ww][d];
+            warp_hist[ww][d] = acc;
+            acc += c;
+        }
+        tot[t] = acc;
+        thread_sum += acc;
     }
     unsigned tile_total;
-    unsigned dstart = block_excl_sum<unsigned>(tot, s_scan, tile_total);
-    digit_start[d] = dstart;
-    // chained scan for digit d over the tiles
-    unsigned excl = 0;
-    {
+    unsigned dstart = block_excl_sum<unsigned>(thread_sum, s_scan, tile_total);
+#pragma unroll
+    for (int t = 0; t < DPT; ++t) {
+        const unsigned d = threadIdx.x * DPT + t;
+        digit_start[d] = dstart;
+        unsigned excl = 0;
         volatile unsigned* st = status;
         if (tile == 0) {
-            st[d] = RS_ST_PREFIX | tot;
+            st[d] = RS_ST_PREFIX | tot[t];
         } else {
-            st[tile * RS_RADIX + d] = RS_ST_AGG | tot;
-            int t = (int)tile - 1;
+            st[tile * RS_RADIX + d] = RS_ST_AGG | tot[t];
+            int tt = (int)tile - 1;
             while (true) {
-                unsigned s = st[t * RS_RADIX + d];
-                unsigned flag = s & ~RS_ST_MASK;
+                unsigned sv = st[tt * RS_RADIX + d];
+                unsigned flag = sv & ~RS_ST_MASK;
                 if (flag == 0) continue;
-                excl += s & RS_ST_MASK;
+                excl += sv & RS_ST_MASK;
                 if (flag == RS_ST_PREFIX) break;
-                --t;
+                --tt;
             }
-            st[tile * RS_RADIX + d] = RS_ST_PREFIX | (excl + tot);
+            st[tile * RS_RADIX + d] = RS_ST_PREFIX | (excl + tot[t]);
         }
+        out_base[d] = digit_base[d] + excl - dstart;
+        dstart += tot[t];
     }
-    out_base[d] = digit_base[d] + excl - dstart;
     __syncthreads();
     // tile-local sorted position of every key
     unsigned pos[ITEMS];
@@ -173,10 +196,11 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out
 // Host driver.  Sorts bits [begin_bit, end_bit) of `keys` (n < 2^30).
 // `keys`/`vals` and `keys_tmp`/`vals_tmp` ping-pong; *result_in_tmp says where
 // the sorted data ended up.  `skip_trivial` costs one 32-byte D2H read.
-template <typename KeyT, bool HAS_VALUE>
-int radix_sort(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, size_t n,
-               int begin_bit, int end_bit, bool skip_trivial, bool* result_in_tmp,
-               cudaStream_t stream) {
+template <typename KeyT, bool HAS_VALUE, int RS_BITS>
+int radix_sort_bits(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, size_t n,
+                    int begin_bit, int end_bit, bool skip_trivial, bool* result_in_tmp,
+                    cudaStream_t stream) {
+    constexpr int RS_RADIX = 1 << RS_BITS;
     *result_in_tmp = false;
     if (n <= 1) return GPC_OK;
     if (n >= (1ull << 30)) {
@@ -203,10 +227,10 @@ int radix_sort(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, s
     GPC_CUDA(cudaMemsetAsync(sc.p, 0, (head + per_pass * n_passes) * sizeof(unsigned), stream));
     unsigned hist_blocks = min(div_up(n, RS_THREADS * 8), (unsigned)(sm_count() * 8));
     GPC_PROF_BYTES("rs_hist", (double)n * sizeof(KeyT));
-    rs_hist_kernel<KeyT><<<hist_blocks, RS_THREADS, 0, stream>>>(keys, n, begin_bit, n_passes, hist);
+    rs_hist_kernel<KeyT, RS_BITS><<<hist_blocks, RS_THREADS, 0, stream>>>(keys, n, begin_bit, n_passes, hist);
     GPC_LAUNCH_CHECK();
     GPC_PROF("rs_scan_hist");
-    rs_scan_hist_kernel<<<n_passes, RS_RADIX, 0, stream>>>(hist, (unsigned)n, trivial);
+    rs_scan_hist_kernel<RS_BITS><<<n_passes, RS_THREADS, 0, stream>>>(hist, (unsigned)n, trivial);
     GPC_LAUNCH_CHECK();
     unsigned h_trivial[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (skip_trivial) {
@@ -221,7 +245,7 @@ int radix_sort(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, s
         const uint32_t* vin = in_tmp ? vals_tmp : vals;
         uint32_t* vout = in_tmp ? vals : vals_tmp;
         GPC_PROF_BYTES("rs_onesweep", 2.0 * n * (sizeof(KeyT) + (HAS_VALUE ? 4 : 0)));
-        rs_onesweep_kernel<KeyT, HAS_VALUE><<<tiles, RS_THREADS, 0, stream>>>(
+        rs_onesweep_kernel<KeyT, HAS_VALUE, RS_BITS><<<tiles, RS_THREADS, 0, stream>>>(
             kin, kout, vin, vout, (unsigned)n, begin_bit + p * RS_BITS,
             hist + (size_t)p * RS_RADIX, status + per_pass * p, ticket + p);
         GPC_LAUNCH_CHECK();
@@ -229,6 +253,20 @@ int radix_sort(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, s
     }
     *result_in_tmp = in_tmp;
     return GPC_OK;
+}
+
+// Picks the digit width: 9-bit digits when that saves a pass for 32-bit keys
+// (e.g. 26 significant bits: 3 passes instead of 4), else 8-bit digits.
+template <typename KeyT, bool HAS_VALUE>
+int radix_sort(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, size_t n,
+               int begin_bit, int end_bit, bool skip_trivial, bool* result_in_tmp,
+               cudaStream_t stream) {
+    const int range = end_bit - begin_bit;
+    if (sizeof(KeyT) == 4 && !HAS_VALUE && (range + 8) / 9 < (range + 7) / 8)
+        return radix_sort_bits<KeyT, HAS_VALUE, 9>(keys, keys_tmp, vals, vals_tmp, n, begin_bit,
+                                                   end_bit, skip_trivial, result_in_tmp, stream);
+    return radix_sort_bits<KeyT, HAS_VALUE, 8>(keys, keys_tmp, vals, vals_tmp, n, begin_bit, end_bit,
+                                               skip_trivial, result_in_tmp, stream);
 }
 
 }  // namespace gpc

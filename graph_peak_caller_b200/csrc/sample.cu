@@ -14,13 +14,9 @@
 // as packed +1/-1 events.  One event stream feeds both the fragment pileup and
 // the direct (reads only) pileup; one radix sort and one chained scan turn it
 // into the two canonical run-length tracks.
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace gpc {
 
@@ -28,8 +24,8 @@ namespace gpc {
 constexpr unsigned TAG_BOTH = 0, TAG_DIRECT = 1, TAG_FRAG = 2;
 constexpr int EVENT_POS_SHIFT = 3;
 
-constexpr int WALK_THREADS = 256;
-constexpr int WALK_STAGE = 3072;     // staged events per block (12 KB)
+constexpr int WALK_THREADS = 128;
+constexpr int WALK_STAGE = 1536;     // staged events per block (6 KB)
 constexpr int FRONTIER_CAP = 32;
 
 struct Emitter {
@@ -46,11 +42,7 @@ struct Emitter {
         uint32_t pos = fwd ? p : (G - p);
         bool minus = fwd ? close : !close;
         uint32_t key = (pos << EVENT_POS_SHIFT) | (tag << 1) | (minus ? 1u : 0u);
-        cg::coalesced_group g = cg::coalesced_threads();
-        unsigned base = 0;
-        if (g.thread_rank() == 0) base = atomicAdd(s_count, g.size());
-        base = g.shfl(base, 0);
-        unsigned slot = base + g.thread_rank();
+        unsigned slot = atomicAdd(s_count, 1u);
         if (slot < WALK_STAGE) {
             s_buf[slot] = key;
         } else {   // staging full: append straight to the global stream
@@ -59,6 +51,34 @@ struct Emitter {
         }
     }
 };
+
+// Everything the walk needs to know about one node, in its direction of travel.
+struct WalkNode {
+    uint32_t off, len;
+    uint32_t n_adj;        // successors (forward) / predecessors (reverse)
+    uint32_t adj0, adj1;   // the first two of them
+};
+__device__ __forceinline__ WalkNode load_walk_node(const gpc_graph_t& g, uint32_t v, bool fwd) {
+    WalkNode w;
+    if (g.walk_rec) {
+        const uint4* p = reinterpret_cast<const uint4*>(g.walk_rec) + 2ull * v;
+        uint4 a = __ldg(p), b = __ldg(p + 1);
+        w.off = a.x;
+        w.len = a.y;
+        w.n_adj = fwd ? (a.z & 0xffffu) : (a.z >> 16);
+        w.adj0 = fwd ? a.w : b.y;
+        w.adj1 = fwd ? b.x : b.z;
+    } else {
+        uint4 a = node_record(g, v), b = node_record(g, v + 1);
+        w.off = a.x;
+        w.len = a.w;
+        w.n_adj = fwd ? (b.y - a.y) : (b.z - a.z);
+        const uint32_t* adj = fwd ? g.succ + a.y : g.pred + a.z;
+        w.adj0 = w.n_adj > 0 ? adj[0] : 0;
+        w.adj1 = w.n_adj > 1 ? adj[1] : 0;
+    }
+    return w;
+}
 
 __global__ void __launch_bounds__(WALK_THREADS)
 walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restrict__ read_index,
@@ -96,13 +116,14 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
             uint32_t ce = 0;          // oriented end of the currently open interval
             uint32_t last_len = 0, last_start = 0;
             uint32_t last_v = 0;
+            WalkNode cur{0, 0, 0, 0, 0};      // the node whose neighbours are pushed next
             const int k = (int)(p1 - p0);
             for (int j = 0; j < k; ++j) {
                 int id = reads.path[p0 + j];
                 uint32_t v = (uint32_t)((id < 0 ? -id : id) - mn);
-                uint4 rec = node_record(graph, v);
-                uint32_t len = rec.w;
-                uint32_t ns = fwd ? rec.x : (G - rec.x - len);
+                WalkNode wn = load_walk_node(graph, v, fwd);
+                uint32_t len = wn.len;
+                uint32_t ns = fwd ? wn.off : (G - wn.off - len);
                 uint32_t ps = (j == 0) ? ns + (uint32_t)so : ns;
                 touched[v] = 1;
                 if (j == 0) {
@@ -113,6 +134,7 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
                 }
                 ce = ns + len;
                 last_len = len; last_start = ns; last_v = v;
+                cur = wn;
             }
             // ---- read end: direct pileup closes here, fragment goes on ------
             em.emit(last_start + (uint32_t)eo, true, TAG_DIRECT);
@@ -127,12 +149,15 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
             uint32_t carry = total > last_len ? total - last_len : 0;
             while (true) {
                 if (carry) {
-                    uint4 a = node_record(graph, cur_v);
-                    uint4 b = node_record(graph, cur_v + 1);
-                    uint32_t lo = fwd ? a.y : a.z, hi = fwd ? b.y : b.z;
-                    const uint32_t* adj = fwd ? graph.succ : graph.pred;
+                    // neighbours of cur_v: inline in its walk record, CSR beyond two
+                    uint32_t lo = 0, hi = cur.n_adj;
+                    const uint32_t* adj = nullptr;
+                    if (cur.n_adj > 2) {
+                        uint4 a = node_record(graph, cur_v);
+                        adj = (fwd ? graph.succ + a.y : graph.pred + a.z);
+                    }
                     for (uint32_t e = lo; e < hi; ++e) {
-                        uint32_t wv = adj[e];
+                        uint32_t wv = adj ? adj[e] : (e == 0 ? cur.adj0 : cur.adj1);
                         uint32_t key = fwd ? wv : ~wv;
                         int f = 0;
                         for (; f < fc; ++f) if (fkey[f] == key) break;
@@ -152,9 +177,9 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
                 --fc;
                 fkey[best] = fkey[fc]; frem[best] = frem[fc];
                 cur_v = fwd ? key : ~key;
-                uint4 rec = node_record(graph, cur_v);
-                uint32_t len = rec.w;
-                uint32_t ns = fwd ? rec.x : (G - rec.x - len);
+                cur = load_walk_node(graph, cur_v, fwd);
+                uint32_t len = cur.len;
+                uint32_t ns = fwd ? cur.off : (G - cur.off - len);
                 touched[cur_v] = 1;
                 if (ns != ce) {
                     em.emit(ce, true, TAG_FRAG);
@@ -541,8 +566,10 @@ extern "C" int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64
     int bits = EVENT_POS_SHIFT;
     while (bits < 32 && (((unsigned long long)size_bp << EVENT_POS_SHIFT) >> bits)) ++bits;
     bool in_tmp = false;
-    GPC_TRY((radix_sort<uint32_t, false>(events, events_tmp, nullptr, nullptr, n_events, 0, bits,
-                                         false, &in_tmp, stream)));
+    // only the position bits have to be ordered: the scan groups equal positions
+    // and adds their deltas in any order
+    GPC_TRY((radix_sort<uint32_t, false>(events, events_tmp, nullptr, nullptr, n_events,
+                                         EVENT_POS_SHIFT, bits, false, &in_tmp, stream)));
     const uint32_t* sorted = in_tmp ? events_tmp : events;
     unsigned tiles = div_up(n_events, RUN_TILE);
     size_t bytes = (size_t)tiles * 32 + 64;

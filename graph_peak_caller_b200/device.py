@@ -53,7 +53,21 @@ class DeviceGraph:
         rec[:, 1] = graph.succ_ptr
         rec[:, 2] = graph.pred_ptr
         rec[:n, 3] = graph.node_len
+        # walk records: one 32-byte sector per node with the first two neighbours inline
+        wrec = np.zeros((n, 8), dtype=np.uint32)
+        deg_s = np.diff(graph.succ_ptr)
+        deg_p = np.diff(graph.pred_ptr)
+        wrec[:, 0] = graph.node_off[:n]
+        wrec[:, 1] = graph.node_len
+        wrec[:, 2] = np.minimum(deg_s, 0xffff) | (np.minimum(deg_p, 0xffff) << 16)
+        for col, ptr, adj, deg, k in ((3, graph.succ_ptr, graph.succ, deg_s, 0),
+                                      (4, graph.succ_ptr, graph.succ, deg_s, 1),
+                                      (5, graph.pred_ptr, graph.pred, deg_p, 0),
+                                      (6, graph.pred_ptr, graph.pred, deg_p, 1)):
+            has = deg > k
+            wrec[has, col] = adj[ptr[:n][has] + k]
         self.graph = graph
+        self.walk_rec = to_device(wrec.view(np.int32))
         self.node_rec = to_device(rec.view(np.int32))
         self.succ = to_device(graph.succ.astype(np.int32))
         self.pred = to_device(graph.pred.astype(np.int32))
@@ -72,11 +86,12 @@ class DeviceGraph:
         g = self.graph
         self.c = _lib.GpcGraph(g.n_nodes, g.n_edges, g.size_bp, g.min_node,
                                ptr(self.node_rec), ptr(self.succ), ptr(self.pred),
-                               ptr(self.lin_start), ptr(self.lin_end))
+                               ptr(self.lin_start), ptr(self.lin_end), ptr(self.walk_rec))
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in
-                   (self.node_rec, self.succ, self.pred, self.lin_start, self.lin_end)
+                   (self.node_rec, self.succ, self.pred, self.lin_start, self.lin_end,
+                    self.walk_rec)
                    if t is not None)
 
 

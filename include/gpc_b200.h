@@ -58,6 +58,11 @@ typedef struct gpc_graph {
     const uint32_t* pred;
     const double* lin_start; /* LinearMap._node_starts (may be NULL) */
     const double* lin_end;   /* LinearMap._node_ends   (may be NULL) */
+    /* Optional (may be NULL): n_nodes records of eight uint32, 32-byte aligned,
+     *   { node_off, node_len, n_succ | n_pred << 16, succ0, succ1, pred0, pred1, 0 }
+     * so that the read walk needs one 32-byte load per visited node; nodes with
+     * more than two successors / predecessors fall back to the CSR arrays. */
+    const uint32_t* walk_rec;
 } gpc_graph_t;
 
 /* Reads in HBM, structure of arrays (signed node ids: negative == reverse

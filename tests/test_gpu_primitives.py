@@ -12,7 +12,8 @@ def _dev(a):
 
 @pytest.mark.parametrize("n,bits", [(1, 32), (2, 32), (257, 32), (4096, 32), (4097, 32),
                                     (100_003, 32), (1_000_000, 29), (3_000_017, 24),
-                                    (50_000, 8), (70_000, 13)])
+                                    (50_000, 8), (70_000, 13),
+                                    (2_000_003, 26), (300_000, 27), (123_457, 17), (5000, 25)])
 def test_sort_u32(n, bits):
     from graph_peak_caller_b200 import kernels
     rng = np.random.default_rng(n)
