@@ -46,6 +46,8 @@ class CallPeaks(object):
         self.direct_pileup = None
 
     def run_pre_callpeaks(self, input_reads, control_reads):
+        if hasattr(control_reads, "prefetch") and control_reads is not input_reads:
+            control_reads.prefetch()          # overlaps the upload with the sample stage
         sample_pileup = get_fragment_pileup(self.graph, input_reads, self.config,
                                             self._reporter)
         self.direct_pileup = sample_pileup.direct_pileup

@@ -27,6 +27,8 @@
 // +-weight steps in float64; the two agree to ~1e-13 relative.
 // Back-projection to graph positions is two binary searches per node plus a
 // segmented copy, with numpy's float floor-division replicated bit for bit.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
@@ -76,14 +78,39 @@ __global__ void unique_flag_kernel(const unsigned long long* __restrict__ keys, 
 __global__ void unique_emit_kernel(const unsigned long long* __restrict__ keys, unsigned n,
                                    const uint8_t* __restrict__ head,
                                    const uint32_t* __restrict__ offs, unsigned n_unique,
-                                   double* __restrict__ xu, uint32_t* __restrict__ wpre) {
+                                   double* __restrict__ xu, uint32_t* __restrict__ wpre,
+                                   int* __restrict__ not_integer) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) wpre[n_unique] = n;
     if (i < n && head[i]) {
-        xu[offs[i]] = key_to_f64(keys[i]);
+        double x = key_to_f64(keys[i]);
+        xu[offs[i]] = x;
         wpre[offs[i]] = i;
+        if (!(x == floor(x)) || !(x >= 0.0) || !(x < 1073741824.0)) *not_integer = 1;
     }
 }
+
+// ---- dense path: every projected start is a non-negative integer -----------------
+// The linear axis is cut into tiles of DENSE_W positions.  The events of a tile
+// are contiguous slices of the sorted starts in every view (two binary searches
+// per view); they are scattered into per-window difference arrays in shared
+// memory, one block scan turns those into counts per position, and a breakpoint
+// is written wherever lambda differs from the position before.  Counts at the
+// tile's left edge come from the slice starts, so tiles are independent.
+constexpr int DENSE_W = 2048;
+constexpr int DENSE_THREADS = 256;
+constexpr int DENSE_PER = DENSE_W / DENSE_THREADS;
+
+__device__ __forceinline__ unsigned lower_bound_xu(const double* xu, unsigned n, double x) {
+    unsigned lo = 0, hi = n;
+    while (lo < hi) {
+        unsigned mid = (lo + hi) >> 1;
+        if (xu[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+
 
 // view q of the sorted starts: q = 2*w + is_end  ->  x -/+ half[w]
 __device__ __forceinline__ double view_value(double x, int q, const WindowParams& wp) {
@@ -166,6 +193,134 @@ __device__ __forceinline__ double lambda_of(const int c[NC], const WindowParams&
         best = fmax(best, __dmul_rn((double)c[w], wp.weight[w]));
     if (clipped) best = fmax(best, wp.min_value);
     return best;
+}
+
+// slice edges of every tile in every view: bounds[t][q] = first start whose event
+// in view q lies at or after the left edge of tile t (t = 0 .. n_tiles)
+__global__ void dense_bounds_kernel(const double* __restrict__ xu, unsigned n_unique,
+                                    WindowParams wp, long long origin, unsigned n_tiles,
+                                    uint32_t* __restrict__ bounds) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned nq = 2 * wp.n_windows;
+    if (i >= (n_tiles + 1) * nq) return;
+    unsigned t = i / nq, q = i % nq;
+    double h = wp.half[q >> 1];
+    double x = (double)(origin + (long long)t * DENSE_W) + ((q & 1) ? -h : h);
+    bounds[i] = lower_bound_xu(xu, n_unique, x);
+}
+
+__global__ void __launch_bounds__(DENSE_THREADS)
+linear_dense_kernel(const double* __restrict__ xu, const uint32_t* __restrict__ wpre,
+                    unsigned n_unique, WindowParams wp, long long origin, unsigned n_tiles,
+                    const uint32_t* __restrict__ bounds,
+                    double* __restrict__ tmp_pos, double* __restrict__ tmp_val,
+                    uint32_t* __restrict__ tile_base, uint32_t* __restrict__ tile_cnt,
+                    unsigned long long* __restrict__ out_count) {
+    __shared__ int s_diff[NC][DENSE_W];
+    __shared__ uint32_t s_lo[MERGE_MAXQ], s_hi[MERGE_MAXQ];
+    __shared__ int s_warp[DENSE_THREADS / 32][NC];
+    __shared__ int s_scan[33];
+    __shared__ unsigned long long s_obase;
+    const unsigned tile = blockIdx.x;
+    const int nq = 2 * wp.n_windows;
+    const long long a = origin + (long long)tile * DENSE_W;      // first position of the tile
+    if ((int)threadIdx.x < nq) {
+        s_lo[threadIdx.x] = bounds[(size_t)tile * nq + threadIdx.x];
+        s_hi[threadIdx.x] = bounds[(size_t)(tile + 1) * nq + threadIdx.x];
+    }
+    for (int i = threadIdx.x; i < NC * DENSE_W; i += DENSE_THREADS) (&s_diff[0][0])[i] = 0;
+    __syncthreads();
+    // scatter the events
+    for (int q = 0; q < nq; ++q) {
+        const int w = q >> 1;
+        const double h = wp.half[w];
+        for (unsigned i = s_lo[q] + threadIdx.x; i < s_hi[q]; i += DENSE_THREADS) {
+            double t = (q & 1) ? xu[i] + h : xu[i] - h;            // exact: integers
+            int p = (int)((long long)t - a);
+            int mul = (int)(wpre[i + 1] - wpre[i]);
+            atomicAdd(&s_diff[w][p], (q & 1) ? -mul : mul);
+            if (q == 0) atomicAdd(&s_diff[3][p], mul);
+        }
+    }
+    __syncthreads();
+    // counts per position: thread owns DENSE_PER consecutive positions
+    const int p0 = threadIdx.x * DENSE_PER;
+    int tot[NC] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < NC; ++k)
+#pragma unroll
+        for (int j = 0; j < DENSE_PER; ++j) tot[k] += s_diff[k][p0 + j];
+    int run[NC];
+    {
+        int incl[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            incl[k] = warp_incl_sum(tot[k]);
+            if (lane_id() == 31) s_warp[warp_id()][k] = incl[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            // counts in force before the tile, straight from the slice starts
+            int pre = (k < wp.n_windows) ? (int)wpre[s_lo[2 * k]] - (int)wpre[s_lo[2 * k + 1]]
+                                         : (k == 3 ? (int)wpre[s_lo[0]] : 0);
+            for (unsigned ww = 0; ww < warp_id(); ++ww) pre += s_warp[ww][k];
+            run[k] = pre + incl[k] - tot[k];
+        }
+    }
+    double was = lambda_of(run, wp);
+    double e_pos[DENSE_PER], e_val[DENSE_PER];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < DENSE_PER; ++j) {
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            int d = s_diff[k][p0 + j];
+            run[k] += d;
+            any |= d != 0;
+        }
+        if (any) {
+            double now = lambda_of(run, wp);
+            if (now != was) {
+                e_pos[cnt] = (double)(a + p0 + j);
+                e_val[cnt] = now;
+                ++cnt;
+            }
+            was = now;
+        }
+    }
+    // Output space is reserved with one atomicAdd per tile (chunks land in
+    // completion order); dense_gather_kernel puts them in tile order afterwards.
+    // A chained scan would serialise here: equally sized tiles finish as one
+    // wavefront and each would walk back through the whole wave.
+    int tile_out;
+    int o = block_excl_sum<int>(cnt, s_scan, tile_out);
+    if (threadIdx.x == 0) {
+        unsigned long long b = tile_out ? atomicAdd(out_count, (unsigned long long)tile_out) : 0ull;
+        s_obase = b;
+        tile_base[tile] = (uint32_t)b;
+        tile_cnt[tile] = (uint32_t)tile_out;
+    }
+    __syncthreads();
+    unsigned long long wbase = s_obase + o;
+    for (int j = 0; j < cnt; ++j) { tmp_pos[wbase + j] = e_pos[j]; tmp_val[wbase + j] = e_val[j]; }
+}
+
+// one warp per tile: move the tile's chunk to its place in tile order
+__global__ void dense_gather_kernel(const double* __restrict__ tmp_pos,
+                                    const double* __restrict__ tmp_val,
+                                    const uint32_t* __restrict__ tile_base,
+                                    const uint32_t* __restrict__ tile_cnt,
+                                    const uint32_t* __restrict__ tile_off, unsigned n_tiles,
+                                    double* __restrict__ out_pos, double* __restrict__ out_val) {
+    unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tiles) return;
+    unsigned c = tile_cnt[t], src = tile_base[t], dst = tile_off[t];
+    for (unsigned i = lane_id(); i < c; i += 32) {
+        out_pos[dst + i] = tmp_pos[src + i];
+        out_val[dst + i] = tmp_val[src + i];
+    }
 }
 
 __global__ void __launch_bounds__(MERGE_THREADS)
@@ -342,6 +497,11 @@ linear_tiles_kernel(const double* __restrict__ xu, const uint32_t* __restrict__ 
 
 // numpy's float64 floor_divide (npy_divmod): fmod based, then corrected.
 __device__ __forceinline__ double np_floor_divide(double a, double b) {
+    // b == 1 (every node whose linear span equals its length): fmod(a, 1) is the
+    // fractional part, (a - mod) / 1 the integer part towards zero, minus one when
+    // a is negative and not integral -- i.e. exactly floor(a); the result is -0.0
+    // only for a == -0.0, and callers add an integer offset anyway
+    if (b == 1.0) return floor(a);
     double mod = fmod(a, b);
     double div = __ddiv_rn(__dsub_rn(a, mod), b);
     if (mod != 0.0) {
@@ -495,8 +655,55 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
     GPC_PROF("unique_emit");
     unique_emit_kernel<<<div_up(n, 256), 256, 0, stream>>>(keys, n, head.as<uint8_t>(),
                                                            offs.as<uint32_t>(), U, xu.as<double>(),
-                                                           wpre.as<uint32_t>());
+                                                           wpre.as<uint32_t>(), err + 1);
     GPC_LAUNCH_CHECK();
+    // integer coordinates (no node with a non-integer scale was hit): dense path
+    int not_integer = 0;
+    double x_last = 0.0;
+    GPC_CUDA(cudaMemcpyAsync(&not_integer, err + 1, 4, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaMemcpyAsync(&x_last, xu.as<double>() + (U - 1), 8, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    if (!not_integer && !getenv("GPC_FORCE_MERGE_PATH")) {
+        long long e_max = 0;
+        for (int w = 0; w < n_extensions; ++w) e_max = (long long)wp.half[w] > e_max ? (long long)wp.half[w] : e_max;
+        const long long origin = -e_max;
+        const long long span = (long long)x_last + 2 * e_max + 1;
+        const unsigned n_dense = (unsigned)((span + DENSE_W - 1) / DENSE_W);
+        Scratch dsc, dbounds, tbase, tcnt, toff, tpos, tval, ttotal;
+        GPC_CUDA(dsc.alloc(64, stream));
+        GPC_CUDA(cudaMemsetAsync(dsc.p, 0, 64, stream));
+        unsigned long long* dcount = dsc.as<unsigned long long>();
+        const size_t cap = (size_t)nq * U;                      // every event could be a breakpoint
+        GPC_CUDA(tbase.alloc((size_t)n_dense * 4, stream));
+        GPC_CUDA(tcnt.alloc((size_t)n_dense * 4, stream));
+        GPC_CUDA(toff.alloc((size_t)n_dense * 4, stream));
+        GPC_CUDA(tpos.alloc(cap * 8, stream));
+        GPC_CUDA(tval.alloc(cap * 8, stream));
+        GPC_CUDA(ttotal.alloc(8, stream));
+        GPC_CUDA(dbounds.alloc((size_t)(n_dense + 1) * nq * 4, stream));
+        GPC_PROF("dense_bounds");
+        dense_bounds_kernel<<<div_up((size_t)(n_dense + 1) * nq, 256), 256, 0, stream>>>(
+            xu.as<double>(), U, wp, origin, n_dense, dbounds.as<uint32_t>());
+        GPC_LAUNCH_CHECK();
+        GPC_PROF_BYTES("linear_dense", 12.0 * nq * U);
+        linear_dense_kernel<<<n_dense, DENSE_THREADS, 0, stream>>>(
+            xu.as<double>(), wpre.as<uint32_t>(), U, wp, origin, n_dense, dbounds.as<uint32_t>(),
+            tpos.as<double>(), tval.as<double>(), tbase.as<uint32_t>(), tcnt.as<uint32_t>(), dcount);
+        GPC_LAUNCH_CHECK();
+        GPC_TRY(exclusive_scan<uint32_t>(tcnt.as<uint32_t>(), toff.as<uint32_t>(), n_dense,
+                                         ttotal.as<unsigned long long>(), stream));
+        GPC_PROF("dense_gather");
+        dense_gather_kernel<<<div_up((size_t)n_dense * 32, 256), 256, 0, stream>>>(
+            tpos.as<double>(), tval.as<double>(), tbase.as<uint32_t>(), tcnt.as<uint32_t>(),
+            toff.as<uint32_t>(), n_dense, out_pos, out_val);
+        GPC_LAUNCH_CHECK();
+        unsigned long long hd = 0;
+        GPC_CUDA(cudaMemcpyAsync(&hd, dcount, 8, cudaMemcpyDeviceToHost, stream));
+        GPC_CUDA(cudaStreamSynchronize(stream));
+        *n_out = hd;
+        prof_add_bytes("linear_dense", 16.0 * (double)hd);
+        return GPC_OK;
+    }
     // splitters: every MERGE_T-th element of every view, sorted
     const unsigned per_view = div_up(U, MERGE_T);
     const unsigned ns = per_view * nq;

@@ -134,4 +134,30 @@ def device_reads(batch):
     if dr is None:
         dr = DeviceReads(batch)
         batch._device = dr
+    ready = getattr(dr, "ready_event", None)
+    if ready is not None:                 # uploaded by prefetch_reads on a side stream
+        cur = torch_cuda().cuda.current_stream()
+        cur.wait_event(ready)
+        for t in (dr.start_node, dr.start_off, dr.end_node, dr.end_off, dr.path_ptr, dr.path):
+            t.record_stream(cur)          # allocated on the copy stream, used on this one
+        dr.ready_event = None
     return dr
+
+
+_copy_stream = None
+
+
+def prefetch_reads(batch):
+    """Upload a ReadBatch on a dedicated copy stream; device_reads() later makes
+    the compute stream wait for it."""
+    global _copy_stream
+    if getattr(batch, "_device", None) is not None:
+        return
+    torch = torch_cuda()
+    if _copy_stream is None:
+        _copy_stream = torch.cuda.Stream()
+    with torch.cuda.stream(_copy_stream):
+        dr = DeviceReads(batch)
+        dr.ready_event = torch.cuda.Event()
+        dr.ready_event.record(_copy_stream)
+    batch._device = dr

@@ -35,11 +35,21 @@ class Intervals:
             self._batch = _as_batch(self._intervals)
         return self._batch
 
+    def prefetch(self):
+        """Start the host->device copy of the reads on a side stream (useful
+        when the batch sits in page-locked memory): CallPeaks uploads the
+        control reads this way while the sample pileup is being computed."""
+        from .device import prefetch_reads
+        prefetch_reads(self.batch)
+
+    def _device_reads(self):
+        from .device import device_reads
+        return device_reads(self.batch)
+
     def consume(self):
         """Called by the pipeline: returns (DeviceReads, read index tensor or
         None, number of reads) and sets the counters."""
-        from .device import device_reads
-        dr = device_reads(self.batch)
+        dr = self._device_reads()
         self.n_reads = dr.n
         return dr, None, dr.n
 
@@ -55,8 +65,7 @@ class UniqueIntervals(Intervals):
 
     def consume(self):
         from . import kernels
-        from .device import device_reads
-        dr = device_reads(self.batch)
+        dr = self._device_reads()
         index, n = kernels.unique_reads(dr)
         self.n_reads = n
         self.n_duplicates = dr.n - n

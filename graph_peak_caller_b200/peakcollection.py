@@ -16,6 +16,28 @@ class Peak(Interval):
         self.chromosome = chromosome
         self._length = None
 
+    @classmethod
+    def from_flat(cls, start, end, nodes, graph, score, info, length):
+        """Constructor for the kernels' output (plain ints already): skips the
+        argument normalisation of ``Interval.__init__``."""
+        from .reads import Position
+        self = object.__new__(cls)
+        self.start_position = Position.__new__(Position)
+        self.start_position.region_path_id = nodes[0]
+        self.start_position.offset = start
+        self.end_position = Position.__new__(Position)
+        self.end_position.region_path_id = nodes[-1]
+        self.end_position.offset = end
+        self.region_paths = nodes
+        self.graph = graph
+        self.direction = 1
+        self.score = score
+        self.unique_id = None
+        self.info = info
+        self.chromosome = None
+        self._length = length
+        return self
+
     def __str__(self):
         return super().__repr__() + " [%s]" % self.score
 

@@ -47,11 +47,11 @@ class SparseMaxPaths:
         raw = self.run_raw()
         ps = pipeline.PeakSet(raw, 0)
         self.order = ps.order          # stable order by score, descending (device sort)
-        peaks = []
-        for i in range(ps.n_all):
-            start, end, nodes, info, score = ps.peak(i)
-            peak = Peak(start, end, nodes, graph=self._graph, score=score)
-            peak.info = info
-            peak._length = int(ps.length[i])
-            peaks.append(peak)
+        start, end = ps.start.tolist(), ps.end.tolist()
+        score, length = ps.score.tolist(), ps.length.tolist()
+        info, ptr, nodes = ps.info.tolist(), ps.node_ptr.tolist(), ps.nodes.tolist()
+        graph = self._graph
+        peaks = [Peak.from_flat(start[i], end[i], nodes[ptr[i]:ptr[i + 1]], graph, score[i],
+                                (bool(info[i] & 1), bool(info[i] & 2)), length[i])
+                 for i in range(ps.n_all)]
         return peaks, [None] * len(peaks)

@@ -93,18 +93,72 @@ class PToQValuesMapper:
 
     def get_p_to_q_values(self):
         """dict p -> q with d[0] = 0 (reference sparsepvalues.py:95-103).  The
-        dict is what the reference API hands around; lookups on the device use
-        the table it was built from (kept as attribute ``device_table``)."""
-        p, q = self._table
-        d = PToQDict(zip(p.cpu().numpy().tolist(), q.cpu().numpy().tolist()))
-        d[0] = 0
-        d.device_table = self._table
-        return d
+        dict is what the reference API hands around; it is filled from the
+        device table the first time somebody looks inside, and lookups on the
+        device use the table itself (attribute ``device_table``)."""
+        return PToQDict(self._table)
 
 
 class PToQDict(dict):
-    """A plain dict plus the device-resident copy of the same table."""
-    device_table = None
+    """A real ``dict`` (the reference asserts ``isinstance(..., dict)``) that
+    copies the (p, q) table from the device on first use."""
+
+    def __init__(self, device_table):
+        super().__init__()
+        self.device_table = device_table
+        self._pending = device_table is not None
+
+    def _fill(self):
+        if self._pending:
+            self._pending = False
+            p, q = self.device_table
+            super().update(zip(p.cpu().numpy().tolist(), q.cpu().numpy().tolist()))
+            super().__setitem__(0, 0)
+
+    def __getitem__(self, key):
+        self._fill()
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        self._fill()
+        return super().get(key, default)
+
+    def __contains__(self, key):
+        self._fill()
+        return super().__contains__(key)
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __len__(self):
+        self._fill()
+        return super().__len__()
+
+    def keys(self):
+        self._fill()
+        return super().keys()
+
+    def values(self):
+        self._fill()
+        return super().values()
+
+    def items(self):
+        self._fill()
+        return super().items()
+
+    def __setitem__(self, key, value):
+        self._fill()
+        self.device_table = None          # modified by the caller: the dict is the truth now
+        super().__setitem__(key, value)
+
+    def __eq__(self, other):
+        self._fill()
+        return super().__eq__(other)
+
+    def __repr__(self):
+        self._fill()
+        return super().__repr__()
 
 
 class QValuesFinder:

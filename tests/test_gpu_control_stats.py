@@ -145,3 +145,28 @@ def test_q_table_matches_dict():
     lens = np.diff(np.r_[pi, g.size_bp])
     assert int(tc.sum()) + int(lens[pv == 0].sum()) == g.size_bp
     assert tp.size == np.unique(pv[pv != 0]).size
+
+
+def test_dense_and_merge_paths_of_the_linear_track_agree(monkeypatch):
+    """Integer linear coordinates take the dense shared-memory path, anything
+    else the sample-partitioned merge; on integer input both must give the
+    same breakpoints and values bit for bit."""
+    import os
+    from graph_peak_caller_b200 import kernels
+    from graph_peak_caller_b200.device import DeviceGraph, DeviceReads
+    g = make_graph(300000, 0.02, seed=71)                 # SNPs / indels only: integer scales
+    lm = ocontrol.linear_map_from_graph(g)
+    c = make_reads(g, 40000, 36, 200, seed=72, peak_frac=0.3, peak_spacing=20000, dup_frac=0.1)
+    dg, dc = DeviceGraph(g, lm), DeviceReads(c)
+    out = {}
+    for mode in ("dense", "merge"):
+        if mode == "merge":
+            monkeypatch.setenv("GPC_FORCE_MERGE_PATH", "1")
+        bp, val, x = kernels.control_linear_track(dg, dc, None, len(c), [200, 1000, 10000], 200,
+                                                  0.9, want_x=True)
+        out[mode] = (cpu(bp), cpu(val))
+        assert np.all(cpu(x) == np.floor(cpu(x)))
+    monkeypatch.delenv("GPC_FORCE_MERGE_PATH")
+    assert np.array_equal(out["dense"][0], out["merge"][0])
+    assert np.array_equal(out["dense"][1], out["merge"][1])
+    assert out["dense"][0].size > 1000

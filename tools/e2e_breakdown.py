@@ -1,0 +1,35 @@
+"""Where the end-to-end API path spends its wall time."""
+import sys, time
+import numpy as np, torch
+sys.path.insert(0, ".")
+import cProfile, pstats
+from graph_peak_caller_b200 import CallPeaks, Configuration
+from graph_peak_caller_b200.control.linearmap import LinearMap
+from graph_peak_caller_b200.intervals import UniqueIntervals
+from graph_peak_caller_b200.reads import ReadBatch
+from graph_peak_caller_b200.reporter import Reporter
+from graph_peak_caller_b200.synthetic import make_graph, make_reads
+g = make_graph(51_000_000, 0.02, seed=20261001)
+s = make_reads(g, 5_000_000, 36, 200, seed=1)
+c = make_reads(g, 5_000_000, 36, 200, seed=2, peak_frac=0.0, dup_frac=0.0)
+lm = LinearMap.from_graph(g)
+config = Configuration(); config.read_length, config.fragment_length, config.has_control = 36, 200, True
+config.linear_map_name = lm
+pinned = {t: [torch.from_numpy(a).pin_memory() for a in (rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr, rb.path)] for t, rb in (("s", s), ("c", c))}
+def fresh(tag):
+    rb = ReadBatch.__new__(ReadBatch)
+    (rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr, rb.path) = [t.numpy() for t in pinned[tag]]
+    rb._device = None; rb._pinned = pinned[tag]
+    return rb
+def step():
+    caller = CallPeaks(g, config, Reporter(None))
+    caller.run(UniqueIntervals(fresh("s")), UniqueIntervals(fresh("c")))
+    return caller.max_path_peaks
+for _ in range(3): step()
+torch.cuda.synchronize(); t=time.perf_counter()
+for _ in range(5): p = step()
+torch.cuda.synchronize(); print("e2e ms/step", 1e3*(time.perf_counter()-t)/5, len(p))
+pr = cProfile.Profile(); pr.enable()
+for _ in range(3): step()
+torch.cuda.synchronize(); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
