@@ -78,16 +78,20 @@ __global__ void unique_flag_kernel(const unsigned long long* __restrict__ keys, 
 __global__ void unique_emit_kernel(const unsigned long long* __restrict__ keys, unsigned n,
                                    const uint8_t* __restrict__ head,
                                    const uint32_t* __restrict__ offs, unsigned n_unique,
-                                   double* __restrict__ xu, uint32_t* __restrict__ wpre,
-                                   int* __restrict__ not_integer) {
+                                   double* __restrict__ xu, uint32_t* __restrict__ wpre) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) wpre[n_unique] = n;
     if (i < n && head[i]) {
-        double x = key_to_f64(keys[i]);
-        xu[offs[i]] = x;
+        xu[offs[i]] = key_to_f64(keys[i]);
         wpre[offs[i]] = i;
-        if (!(x == floor(x)) || !(x >= 0.0) || !(x < 1073741824.0)) *not_integer = 1;
     }
+}
+__global__ void integer_check_kernel(const unsigned long long* __restrict__ keys, unsigned n,
+                                     int* __restrict__ not_integer) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = key_to_f64(keys[i]);
+    if (!(x == floor(x)) || !(x >= 0.0) || !(x < 1073741824.0)) *not_integer = 1;
 }
 
 // ---- dense path: every projected start is a non-negative integer -----------------
@@ -640,11 +644,18 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
     GPC_LAUNCH_CHECK();
     GPC_TRY(exclusive_scan<uint8_t>(head.as<uint8_t>(), offs.as<uint32_t>(), n,
                                     total.as<unsigned long long>(), stream));
-    unsigned long long hU = 0;
-    int herr = 0;
+    // largest start = last sorted key; integrality of the starts
+    GPC_PROF("integer_check");
+    integer_check_kernel<<<div_up(n, 256), 256, 0, stream>>>(keys, n, err + 1);
+    GPC_LAUNCH_CHECK();
+    unsigned long long hU = 0, last_key = 0;
+    int herr = 0, not_integer = 0;
     GPC_CUDA(cudaMemcpyAsync(&hU, total.p, 8, cudaMemcpyDeviceToHost, stream));
     GPC_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaMemcpyAsync(&not_integer, err + 1, 4, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaMemcpyAsync(&last_key, keys + (n - 1), 8, cudaMemcpyDeviceToHost, stream));
     GPC_CUDA(cudaStreamSynchronize(stream));
+    const double x_last = key_to_f64(last_key);
     if (herr) {
         set_error("Interval has node(s) not part of graph/pileup");
         return herr;
@@ -655,14 +666,9 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
     GPC_PROF("unique_emit");
     unique_emit_kernel<<<div_up(n, 256), 256, 0, stream>>>(keys, n, head.as<uint8_t>(),
                                                            offs.as<uint32_t>(), U, xu.as<double>(),
-                                                           wpre.as<uint32_t>(), err + 1);
+                                                           wpre.as<uint32_t>());
     GPC_LAUNCH_CHECK();
     // integer coordinates (no node with a non-integer scale was hit): dense path
-    int not_integer = 0;
-    double x_last = 0.0;
-    GPC_CUDA(cudaMemcpyAsync(&not_integer, err + 1, 4, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaMemcpyAsync(&x_last, xu.as<double>() + (U - 1), 8, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
     if (!not_integer && !getenv("GPC_FORCE_MERGE_PATH")) {
         long long e_max = 0;
         for (int w = 0; w < n_extensions; ++w) e_max = (long long)wp.half[w] > e_max ? (long long)wp.half[w] : e_max;

@@ -278,8 +278,16 @@ __global__ void uf_edges_kernel(gpc_graph_t g, VertexView vw, uint32_t* __restri
 }
 
 // entry / exit flags of hole vertices (graphs.py:47-58) and component stats
+// np.searchsorted(node_off, last position): number of node offsets < pos.  Successors
+// with a larger 1-based index are ignored (graphs.py:55) -> 0-based bound  s < last_node.
+__global__ void last_node_kernel(gpc_graph_t g, const uint32_t* __restrict__ last_pos, int trailing,
+                                 uint32_t* __restrict__ out) {
+    if (!trailing) { *out = g.n_nodes + 1; return; }
+    *out = node_ending(g, *last_pos) + 1;
+}
+
 __global__ void hole_flags_kernel(gpc_graph_t g, const uint8_t* __restrict__ touched,
-                                  uint32_t last_node, VertexView vw,
+                                  const uint32_t* __restrict__ last_node_ptr, VertexView vw,
                                   const uint8_t* __restrict__ node_into,
                                   const uint8_t* __restrict__ node_outof,
                                   uint32_t* __restrict__ parent, uint8_t* __restrict__ is_entry,
@@ -290,6 +298,7 @@ __global__ void hole_flags_kernel(gpc_graph_t g, const uint8_t* __restrict__ tou
     is_entry[u] = 0;
     is_exit[u] = 0;
     if (!vw.alive[u]) return;
+    const uint32_t last_node = *last_node_ptr;
     int t = vw.type_of[u];
     uint32_t a = vw.node_of[u];
     uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
@@ -842,8 +851,6 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
     const int trailing = v_last == 0;
     if (trailing) hi -= 1;
     const uint32_t n_holes = hi > lo ? (hi - lo) / 2 : 0;
-    // last_node (holecleaner.py:27-33) as an exclusive 0-based bound on node indexes
-    uint32_t last_node = n + 1;
     Segments sg{pos, lo, n_holes, hi, 0};
     Scratch v0, v1, cnt, offs;
     unsigned long long n_pieces = 0;
@@ -858,18 +865,11 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
         GPC_LAUNCH_CHECK();
         GPC_TRY(scan_counts(cnt.as<uint32_t>(), offs.as<uint32_t>(), n_holes, &n_pieces, stream));
     }
-    if (trailing) {
-        // np.searchsorted(node_off, p_last): number of node offsets < p_last.  Successors with a
-        // larger 1-based index are ignored (graphs.py:55)  ->  0-based bound  s < last_node.
-        uint32_t a = 0, b = n + 1;
-        while (a < b) {
-            uint32_t mid = (a + b) >> 1, off = 0;
-            GPC_CUDA(cudaMemcpyAsync(&off, graph->node_rec + 4ull * mid, 4, cudaMemcpyDeviceToHost, stream));
-            GPC_CUDA(cudaStreamSynchronize(stream));
-            if (off < p_last) a = mid + 1; else b = mid;
-        }
-        last_node = a;
-    }
+    Scratch last_node;
+    GPC_CUDA(last_node.alloc(4, stream));
+    GPC_PROF("last_node");
+    last_node_kernel<<<1, 1, 0, stream>>>(*graph, pos + n_runs - 1, trailing, last_node.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
     const uint32_t P = (uint32_t)n_pieces;
     Scratch p_node, p_start, p_end, p_type, p_vertex, p_keep, in_v, out_v, n_into, n_outof;
     GPC_CUDA(p_node.alloc((size_t)P * 4, stream));
@@ -927,7 +927,7 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
         uf_edges_kernel<<<GRID(P)>>>(*graph, vw, parent.as<uint32_t>());
         GPC_LAUNCH_CHECK();
         GPC_PROF("hole_flags");
-        hole_flags_kernel<<<GRID(P)>>>(*graph, touched, last_node, vw, n_into.as<uint8_t>(),
+        hole_flags_kernel<<<GRID(P)>>>(*graph, touched, last_node.as<uint32_t>(), vw, n_into.as<uint8_t>(),
                                        n_outof.as<uint8_t>(), parent.as<uint32_t>(),
                                        is_entry.as<uint8_t>(), is_exit.as<uint8_t>(),
                                        csize.as<uint32_t>(), centry.as<uint32_t>());
@@ -972,9 +972,8 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
     }
     // kept pieces -> sorted boundary events -> canonical boolean track
     const size_t n_ev = 1 + 2 * (size_t)n_kept + (trailing ? 1 : 0);
-    Scratch ev0, ev1, flag, eoffs;
+    Scratch ev0, flag, eoffs;
     GPC_CUDA(ev0.alloc(n_ev * 4, stream));
-    GPC_CUDA(ev1.alloc(n_ev * 4, stream));
     GPC_CUDA(flag.alloc(n_ev, stream));
     GPC_CUDA(eoffs.alloc(n_ev * 4, stream));
     GPC_PROF("hole_events");
@@ -982,12 +981,11 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
                                             p_start.as<uint32_t>(), p_end.as<uint32_t>(),
                                             (uint32_t)n_kept, trailing, p_last, ev0.as<uint32_t>());
     GPC_LAUNCH_CHECK();
-    int bits = 1;
-    while (bits < 32 && (((unsigned long long)graph->size_bp << 1) >> bits)) ++bits;
-    bool in_tmp = false;
-    GPC_TRY((radix_sort<uint32_t, false>(ev0.as<uint32_t>(), ev1.as<uint32_t>(), nullptr, nullptr,
-                                         n_ev, 0, bits, false, &in_tmp, stream)));
-    const uint32_t* ev = in_tmp ? ev1.as<uint32_t>() : ev0.as<uint32_t>();
+    // No sort: pieces are numbered hole by hole and node by node, i.e. by position,
+    // the compaction keeps that order, a piece's end precedes the next piece's start
+    // (equal positions: end first, as the canonicalisation wants), the synthetic
+    // event sits at position 0 and the trailing one after every kept piece.
+    const uint32_t* ev = ev0.as<uint32_t>();
     GPC_PROF("bool_runs_flag");
     bool_runs_flag_kernel<<<GRID(n_ev)>>>(ev, (uint32_t)n_ev, flag.as<uint8_t>());
     GPC_LAUNCH_CHECK();
@@ -1042,8 +1040,14 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
                                       between.as<uint32_t>());
     GPC_LAUNCH_CHECK();
     unsigned long long n_multi = 0, n_between = 0;
-    GPC_TRY(scan_counts(multi.as<uint32_t>(), multi_rank.as<uint32_t>(), S, &n_multi, stream));
-    GPC_TRY(scan_counts(between.as<uint32_t>(), between_offs.as<uint32_t>(), S, &n_between, stream));
+    {
+        const uint32_t* in[2] = {multi.as<uint32_t>(), between.as<uint32_t>()};
+        uint32_t* out[2] = {multi_rank.as<uint32_t>(), between_offs.as<uint32_t>()};
+        unsigned long long tot[2];
+        GPC_TRY(multi_scan(2, in, out, S, tot, stream));
+        n_multi = tot[0];
+        n_between = tot[1];
+    }
     const uint32_t P = S + (uint32_t)n_multi + (uint32_t)n_between;
     Scratch p_node, p_start, p_end, p_type, f_t, f_w, f_h, f_i, r_t, r_w, r_h, r_i;
     GPC_CUDA(p_node.alloc((size_t)P * 4, stream));
@@ -1063,10 +1067,15 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
                                     f_h.as<uint32_t>(), f_i.as<uint32_t>());
     GPC_LAUNCH_CHECK();
     unsigned long long n_t = 0, n_w = 0, n_h = 0, n_i = 0;
-    GPC_TRY(scan_counts(f_t.as<uint32_t>(), r_t.as<uint32_t>(), P, &n_t, stream));
-    GPC_TRY(scan_counts(f_w.as<uint32_t>(), r_w.as<uint32_t>(), P, &n_w, stream));
-    GPC_TRY(scan_counts(f_h.as<uint32_t>(), r_h.as<uint32_t>(), P, &n_h, stream));
-    GPC_TRY(scan_counts(f_i.as<uint32_t>(), r_i.as<uint32_t>(), P, &n_i, stream));
+    {
+        const uint32_t* in[4] = {f_t.as<uint32_t>(), f_w.as<uint32_t>(), f_h.as<uint32_t>(),
+                                 f_i.as<uint32_t>()};
+        uint32_t* out[4] = {r_t.as<uint32_t>(), r_w.as<uint32_t>(), r_h.as<uint32_t>(),
+                            r_i.as<uint32_t>()};
+        unsigned long long tot[4];
+        GPC_TRY(multi_scan(4, in, out, P, tot, stream));
+        n_t = tot[0]; n_w = tot[1]; n_h = tot[2]; n_i = tot[3];
+    }
     const uint32_t V = (uint32_t)(n_t + n_w + n_h);
     // internal pieces in piece order
     Scratch internal_piece;

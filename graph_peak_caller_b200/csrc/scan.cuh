@@ -75,4 +75,71 @@ int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* t
     return GPC_OK;
 }
 
+// Up to four independent exclusive scans of uint32 arrays of the same length in
+// one launch (one chained scan each); totals[k] receives the sum of array k.
+struct MultiScanArgs {
+    const uint32_t* in[4];
+    uint32_t* out[4];
+    unsigned long long* status[4];
+    int k;
+};
+
+static __global__ void __launch_bounds__(SC_THREADS)
+multi_scan_kernel(MultiScanArgs a, unsigned n, unsigned long long* __restrict__ totals) {
+    __shared__ unsigned s_scan[33];
+    __shared__ unsigned long long s_prefix[4];
+    const unsigned tile = blockIdx.x;          // launch order
+    const unsigned base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
+    for (int k = 0; k < a.k; ++k) {
+        unsigned v[SC_ITEMS], sum = 0;
+#pragma unroll
+        for (int j = 0; j < SC_ITEMS; ++j) {
+            v[j] = (base + j < n) ? a.in[k][base + j] : 0u;
+            sum += v[j];
+        }
+        unsigned tile_total;
+        unsigned ex = block_excl_sum<unsigned>(sum, s_scan, tile_total);
+        if (threadIdx.x < 32) {
+            unsigned long long p = lookback_excl_warp(a.status[k], tile, tile_total);
+            if (threadIdx.x == 0) {
+                s_prefix[k] = p;
+                if (tile == gridDim.x - 1) totals[k] = p + tile_total;
+            }
+        }
+        __syncthreads();
+        unsigned run = (unsigned)s_prefix[k] + ex;
+#pragma unroll
+        for (int j = 0; j < SC_ITEMS; ++j) {
+            if (base + j < n) a.out[k][base + j] = run;
+            run += v[j];
+        }
+    }
+}
+
+// Host driver; totals_host[k] are written after one synchronisation.
+inline int multi_scan(int k, const uint32_t* const* in, uint32_t* const* out, size_t n,
+                      unsigned long long* totals_host, cudaStream_t stream) {
+    for (int i = 0; i < k; ++i) totals_host[i] = 0;
+    if (n == 0) return GPC_OK;
+    unsigned tiles = div_up(n, SC_TILE);
+    Scratch sc;
+    size_t bytes = ((size_t)tiles * k + 8) * 8;
+    GPC_CUDA(sc.alloc(bytes, stream));
+    GPC_CUDA(cudaMemsetAsync(sc.p, 0, bytes, stream));
+    MultiScanArgs a;
+    a.k = k;
+    unsigned long long* totals = sc.as<unsigned long long>();
+    for (int i = 0; i < 4; ++i) {
+        a.in[i] = i < k ? in[i] : nullptr;
+        a.out[i] = i < k ? out[i] : nullptr;
+        a.status[i] = totals + 8 + (size_t)tiles * (i < k ? i : 0);
+    }
+    GPC_PROF("multi_scan");
+    multi_scan_kernel<<<tiles, SC_THREADS, 0, stream>>>(a, (unsigned)n, totals);
+    GPC_LAUNCH_CHECK();
+    GPC_CUDA(cudaMemcpyAsync(totals_host, totals, 8 * k, cudaMemcpyDeviceToHost, stream));
+    GPC_CUDA(cudaStreamSynchronize(stream));
+    return GPC_OK;
+}
+
 }  // namespace gpc
