@@ -16,7 +16,10 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 
 template <typename KeyT> struct RsTraits;
-template <> struct RsTraits<uint32_t> { static constexpr int ITEMS = 16; static constexpr int MAX_PASSES = 4; };
+#ifndef GPC_RS_ITEMS32
+#define GPC_RS_ITEMS32 16
+#endif
+template <> struct RsTraits<uint32_t> { static constexpr int ITEMS = GPC_RS_ITEMS32; static constexpr int MAX_PASSES = 4; };
 template <> struct RsTraits<unsigned long long> { static constexpr int ITEMS = 8; static constexpr int MAX_PASSES = 8; };
 
 template <typename KeyT, int RS_BITS>
@@ -72,8 +75,11 @@ constexpr unsigned RS_ST_AGG = 1u << 30;
 constexpr unsigned RS_ST_PREFIX = 2u << 30;
 constexpr unsigned RS_ST_MASK = (1u << 30) - 1;
 
+#ifndef GPC_RS_MIN_BLOCKS
+#define GPC_RS_MIN_BLOCKS 4
+#endif
 template <typename KeyT, bool HAS_VALUE, int RS_BITS>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, GPC_RS_MIN_BLOCKS)
 rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                    const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                    unsigned n, int shift, const unsigned* __restrict__ digit_base,
@@ -108,11 +114,90 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out
         unsigned idx = warp_base + j * 32 + l;
         key[j] = (idx < count) ? keys_in[tile_base + idx] : ~KeyT(0);
     }
+    // ---- early count: the tile's digit histogram, published before the ranking so
+    // that later tiles never wait for a tile that is still ranking its keys ----------
+    for (int i = threadIdx.x; i < RS_RADIX; i += RS_THREADS) digit_start[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+        atomicAdd(&digit_start[(unsigned)(key[j] >> shift) & (RS_RADIX - 1)], 1u);
+    __syncthreads();
+    {
+        unsigned tot[DPT], thread_sum = 0;
+#pragma unroll
+        for (int t = 0; t < DPT; ++t) {
+            tot[t] = digit_start[threadIdx.x * DPT + t];
+            thread_sum += tot[t];
+        }
+        unsigned tile_total;
+        unsigned dstart = block_excl_sum<unsigned>(thread_sum, s_scan, tile_total);
+        // chained scan of every digit over the tiles; the DPT digits of a thread walk
+        // back together so that their loads are in flight at the same time
+        unsigned excl[DPT];
+        volatile unsigned* st = status;
+#pragma unroll
+        for (int t = 0; t < DPT; ++t) excl[t] = 0;
+#ifdef GPC_EXP_NO_LOOKBACK
+        if (true) {
+#else
+        if (tile == 0) {
+#endif
+#pragma unroll
+            for (int t = 0; t < DPT; ++t)
+                st[tile * RS_RADIX + threadIdx.x * DPT + t] = RS_ST_PREFIX | tot[t];
+        } else {
+#pragma unroll
+            for (int t = 0; t < DPT; ++t)
+                st[tile * RS_RADIX + threadIdx.x * DPT + t] = RS_ST_AGG | tot[t];
+            int tt[DPT];
+            bool done[DPT];
+#pragma unroll
+            for (int t = 0; t < DPT; ++t) { tt[t] = (int)tile - 1; done[t] = false; }
+            bool all_done = false;
+            while (!all_done) {
+                unsigned sv[DPT];
+#pragma unroll
+                for (int t = 0; t < DPT; ++t)
+                    sv[t] = done[t] ? 0u : st[tt[t] * RS_RADIX + threadIdx.x * DPT + t];
+                all_done = true;
+#pragma unroll
+                for (int t = 0; t < DPT; ++t) {
+                    if (done[t]) continue;
+                    unsigned flag = sv[t] & ~RS_ST_MASK;
+                    if (flag != 0) {
+                        excl[t] += sv[t] & RS_ST_MASK;
+                        if (flag == RS_ST_PREFIX) done[t] = true; else --tt[t];
+                    }
+                    all_done &= done[t];
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < DPT; ++t)
+                st[tile * RS_RADIX + threadIdx.x * DPT + t] = RS_ST_PREFIX | (excl[t] + tot[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < DPT; ++t) {
+            const unsigned d = threadIdx.x * DPT + t;
+            digit_start[d] = dstart;                 // exclusive offset of digit d inside the tile
+            out_base[d] = digit_base[d] + excl[t] - dstart;
+            dstart += tot[t];
+        }
+    }
     // stable ranking: items in (j, lane) order == memory order inside the warp chunk
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         unsigned d = (unsigned)(key[j] >> shift) & (RS_RADIX - 1);
+#ifdef GPC_RS_USE_MATCH
         unsigned peers = __match_any_sync(FULL, d);
+#else
+        // lanes holding the same digit, from one ballot per digit bit
+        unsigned peers = FULL;
+#pragma unroll
+        for (int b = 0; b < RS_BITS; ++b) {
+            unsigned vote = __ballot_sync(FULL, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? vote : ~vote;
+        }
+#endif
         unsigned leader = __ffs(peers) - 1;
         unsigned before = __popc(peers & ((1u << l) - 1));
         unsigned old = 0;
@@ -125,9 +210,7 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out
         __syncwarp();
     }
     __syncthreads();
-    // per digit (thread t owns digits t*DPT ..): exclusive scan over the warps,
-    // tile count, then the chained scan of that digit over the tiles
-    unsigned tot[DPT], thread_sum = 0;
+    // per digit (thread t owns digits t*DPT ..): exclusive scan over the warps
 #pragma unroll
     for (int t = 0; t < DPT; ++t) {
         const unsigned d = threadIdx.x * DPT + t;
@@ -138,34 +221,6 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out
             warp_hist[ww][d] = acc;
             acc += c;
         }
-        tot[t] = acc;
-        thread_sum += acc;
-    }
-    unsigned tile_total;
-    unsigned dstart = block_excl_sum<unsigned>(thread_sum, s_scan, tile_total);
-#pragma unroll
-    for (int t = 0; t < DPT; ++t) {
-        const unsigned d = threadIdx.x * DPT + t;
-        digit_start[d] = dstart;
-        unsigned excl = 0;
-        volatile unsigned* st = status;
-        if (tile == 0) {
-            st[d] = RS_ST_PREFIX | tot[t];
-        } else {
-            st[tile * RS_RADIX + d] = RS_ST_AGG | tot[t];
-            int tt = (int)tile - 1;
-            while (true) {
-                unsigned sv = st[tt * RS_RADIX + d];
-                unsigned flag = sv & ~RS_ST_MASK;
-                if (flag == 0) continue;
-                excl += sv & RS_ST_MASK;
-                if (flag == RS_ST_PREFIX) break;
-                --tt;
-            }
-            st[tile * RS_RADIX + d] = RS_ST_PREFIX | (excl + tot[t]);
-        }
-        out_base[d] = digit_base[d] + excl - dstart;
-        dstart += tot[t];
     }
     __syncthreads();
     // tile-local sorted position of every key

@@ -55,3 +55,22 @@ elif what == "pvalues":
     rep = _lib.profile_report()
     print("pvalues stage %.3f ms, kernel %.3f ms, %d runs, identical to the dump: %s" % (
         ms, rep["pvalues"][1], ppos.numel(), same))
+elif what == "sort32":
+    n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 16_000_000
+    bits = int(sys.argv[3]) if len(sys.argv) > 3 else 26
+    rng = np.random.default_rng(0)
+    keys = torch.from_numpy(rng.integers(0, 2 ** bits, size=n, dtype=np.int64).astype(np.uint32)
+                            .view(np.int32)).cuda()
+    _lib.profile_enable(True)
+    best = 1e9
+    for _ in range(6):
+        k = keys.clone()
+        torch.cuda.synchronize()
+        _lib.profile_report()
+        out = kernels.sort_u32(k, 0, bits)
+        rep = _lib.profile_report()
+        ms = rep["rs_onesweep"][1] / rep["rs_onesweep"][0]
+        best = min(best, ms)
+    ok = bool((out[1:].view(torch.int32).to(torch.int64) & 0xffffffff >= out[:-1].to(torch.int64) & 0xffffffff).all())
+    print("sort32 n=%d bits=%d: %d passes, %.1f us per pass, %.0f GB/s per pass (keys read+written), sorted=%s" % (
+        n, bits, rep["rs_onesweep"][0], best * 1e3, 8.0 * n / (best / 1e3) / 1e9, ok))
