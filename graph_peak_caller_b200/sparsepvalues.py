@@ -89,6 +89,14 @@ class PToQValuesMapper:
         return cls._from_device_table(torch.cat(tps), torch.cat(tcs), total)
 
     def device_table(self):
+        if self._table is None and self.p_values is not None:
+            # built the reference's way from (distinct p descending, cumulative counts)
+            counts = np.ediff1d(np.asarray(self.cum_counts, dtype=np.int64),
+                                to_begin=self.cum_counts[0])
+            p = np.asarray(self.p_values, dtype=np.float64)
+            keep = p != 0
+            self._table = kernels.qtable_build(to_device(p[keep]), to_device(counts[keep]),
+                                               int(self.cum_counts[-1]))
         return self._table
 
     def get_p_to_q_values(self):
@@ -96,7 +104,7 @@ class PToQValuesMapper:
         dict is what the reference API hands around; it is filled from the
         device table the first time somebody looks inside, and lookups on the
         device use the table itself (attribute ``device_table``)."""
-        return PToQDict(self._table)
+        return PToQDict(self.device_table())
 
 
 class PToQDict(dict):
