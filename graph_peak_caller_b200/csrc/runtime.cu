@@ -1,7 +1,9 @@
 // Error text, version string, device properties.
 #include <stdarg.h>
 
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -23,14 +25,17 @@ struct ProfRec { const char* name; cudaEvent_t a, b; double bytes; };
 static std::map<std::string, double> g_extra_bytes;
 static std::vector<ProfRec> g_recs;
 static bool g_prof_on = false;
-static unsigned long long g_launches = 0;
-static const char* g_pending = nullptr;
-static cudaStream_t g_pending_stream = nullptr;
-static cudaEvent_t g_pending_a = nullptr;
-static double g_pending_bytes = 0.0;
+static std::atomic<unsigned long long> g_launches{0};
+static thread_local const char* g_pending = nullptr;
+static thread_local cudaStream_t g_pending_stream = nullptr;
+static thread_local cudaEvent_t g_pending_a = nullptr;
+static thread_local double g_pending_bytes = 0.0;
+static std::mutex g_prof_mutex;        // stage functions may run on several host threads
 
 void prof_add_bytes(const char* name, double bytes) {
-    if (g_prof_on) g_extra_bytes[name] += bytes;
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_extra_bytes[name] += bytes;
 }
 
 void prof_begin(const char* name, cudaStream_t stream, double bytes) {
@@ -43,12 +48,15 @@ void prof_begin(const char* name, cudaStream_t stream, double bytes) {
 }
 
 void prof_end() {
-    ++g_launches;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     if (!g_pending) return;
     ProfRec r{g_pending, g_pending_a, nullptr, g_pending_bytes};
     cudaEventCreate(&r.b);
     cudaEventRecord(r.b, g_pending_stream);
-    g_recs.push_back(r);
+    {
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
+        g_recs.push_back(r);
+    }
     g_pending = nullptr;
 }
 
@@ -108,13 +116,14 @@ extern "C" int gpc_linear_map_from_graph_host(const int64_t* node_len, const int
 }
 
 extern "C" void gpc_profile_enable(int on) { gpc::g_prof_on = on != 0; }
-extern "C" uint64_t gpc_launch_count(void) { return gpc::g_launches; }
+extern "C" uint64_t gpc_launch_count(void) { return gpc::g_launches.load(); }
 
 // Writes "name calls total_ms algorithmic_bytes\n" lines for every kernel timed since the last
 // report (synchronises the device) and clears the records.  Returns the
 // number of bytes needed (excluding the terminating 0).
 extern "C" uint64_t gpc_profile_report(char* buf, uint64_t capacity) {
     cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lock(gpc::g_prof_mutex);
     struct Acc { unsigned long long calls = 0; double ms = 0, bytes = 0; };
     std::map<std::string, Acc> acc;
     for (auto& r : gpc::g_recs) {

@@ -46,9 +46,10 @@ def sample_pileup(dgraph, dreads, read_index, n_reads, extension):
     return frag, direct, touched, int(events.numel())
 
 
-def background_track(dgraph, dreads, read_index, n_reads, extensions, fragment_length,
-                     touched, global_min=None, value_scale=1.0):
-    """get_background_track (control/__init__.py:7-14) -> SparseControl.create."""
+def linear_background(dgraph, dreads, read_index, n_reads, extensions, fragment_length,
+                      global_min=None):
+    """First half of SparseControl.create (controlgenerator.py:21-41): needs only
+    the control reads, so it can run beside the sample pileup."""
     if global_min is not None:
         min_value = global_min
     else:
@@ -56,6 +57,16 @@ def background_track(dgraph, dreads, read_index, n_reads, extensions, fragment_l
         min_value = n_reads * fragment_length / np.float64(dgraph.linear_length)
     bp, val, _ = kernels.control_linear_track(dgraph, dreads, read_index, n_reads,
                                               extensions, fragment_length, min_value)
+    return bp, val, float(min_value)
+
+
+def background_track(dgraph, dreads, read_index, n_reads, extensions, fragment_length,
+                     touched, global_min=None, value_scale=1.0, linear=None):
+    """get_background_track (control/__init__.py:7-14) -> SparseControl.create."""
+    if linear is None:
+        linear = linear_background(dgraph, dreads, read_index, n_reads, extensions,
+                                   fragment_length, global_min)
+    bp, val, min_value = linear
     cpos, clam = kernels.control_backproject(dgraph, touched, bp, val, min_value, value_scale)
     return (cpos, clam), (bp, val), float(min_value)
 
@@ -69,21 +80,31 @@ def run_to_p_values(dgraph, dsample, dcontrol, read_length, fragment_length,
     assert fragment_length > read_length, \
         "Read length %d is larger than fragment size" % read_length
     st = PValueState()
+    extensions = control_extensions(fragment_length, has_control)
+
+    def control_chain():
+        ci, nc = control_index if control_index is not None else (None, dcontrol.n)
+        if unique:
+            ci, nc = kernels.unique_reads(dcontrol)
+        return ci, nc, linear_background(dgraph, dcontrol, ci, nc, extensions,
+                                         fragment_length, global_min)
+
+    # (running the control chain on a second stream beside the sample chain was
+    # measured: no gain, the pass is not gap-bound enough -- kept sequential)
     si, ns = sample_index if sample_index is not None else (None, dsample.n)
-    ci, nc = control_index if control_index is not None else (None, dcontrol.n)
     if unique:
         si, ns = kernels.unique_reads(dsample)
-        ci, nc = kernels.unique_reads(dcontrol)
-    st.n_sample, st.n_control = ns, nc
     st.sample, st.direct, st.touched, st.n_events = sample_pileup(
         dgraph, dsample, si, ns, fragment_length - read_length)
+    ci, nc, linear = control_chain()
+    st.n_sample, st.n_control = ns, nc
     # scale_tracks (control/__init__.py:32-42)
     st.ratio = ns / nc
     st.sample_scale = 1 / st.ratio if st.ratio > 1 else 1.0
     value_scale = st.ratio if st.ratio < 1 else 1.0
     st.control, st.linear, st.min_value = background_track(
-        dgraph, dcontrol, ci, nc, control_extensions(fragment_length, has_control),
-        fragment_length, st.touched, global_min, value_scale)
+        dgraph, dcontrol, ci, nc, extensions, fragment_length, st.touched, global_min,
+        value_scale, linear=linear)
     st.p_values = kernels.pvalues(st.sample[0], st.sample[1], st.sample_scale,
                                   st.control[0], st.control[1])
     st.track_size = dgraph.graph.size_bp
