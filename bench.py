@@ -323,7 +323,7 @@ def main_ours(args):
                             read_length=R, fragment_length=F, with_control=True,
                             peaks=len(peaks), events=st.n_events,
                             l2="inputs (%.0f MB reads + %.0f MB graph per GPU) exceed the 126 MB L2"
-                               % ((ds.batch.nbytes()) / 1e6 * 2, dg.nbytes() / 1e6)),
+                               % ((ds.host_bytes) / 1e6 * 2, dg.nbytes() / 1e6)),
                 pileup_bp_per_sec=pileup_bp(st.n_sample, st.n_control) * world / (ms_per_step / 1e3),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=total_reads / (e2e_ms / 1e3), unit="reads/s",

@@ -98,14 +98,32 @@ class DeviceGraph:
 class DeviceReads:
     """Reads SoA in HBM (include/gpc_b200.h: gpc_reads_t)."""
 
-    def __init__(self, batch):
-        self.batch = batch
+    def __init__(self, batch, copy_stream=None):
+        torch = torch_cuda()
+        # (no back-reference to the batch: batch._device -> this object would make a
+        #  cycle and the device arrays would wait for the cyclic collector)
         self.n = len(batch)
+        self.host_bytes = batch.nbytes()
+        self.ready_event = None
         pinned = getattr(batch, "_pinned", None)
         if pinned is not None:      # page-locked host tensors: asynchronous copies
             dev = device()
+            # destinations come from the current stream's cached pool; with a copy
+            # stream only the transfers run there (it first waits for whatever the
+            # current stream did with that memory before)
+            dst = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in pinned]
+            if copy_stream is not None:
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(copy_stream):
+                    for a, b in zip(dst, pinned):
+                        a.copy_(b, non_blocking=True)
+                    self.ready_event = torch.cuda.Event()
+                    self.ready_event.record(copy_stream)
+            else:
+                for a, b in zip(dst, pinned):
+                    a.copy_(b, non_blocking=True)
             (self.start_node, self.start_off, self.end_node, self.end_off, self.path_ptr,
-             self.path) = [t.to(dev, non_blocking=True) for t in pinned]
+             self.path) = dst
         else:
             self.start_node = to_device(batch.start_node)
             self.start_off = to_device(batch.start_off)
@@ -135,11 +153,8 @@ def device_reads(batch):
         dr = DeviceReads(batch)
         batch._device = dr
     ready = getattr(dr, "ready_event", None)
-    if ready is not None:                 # uploaded by prefetch_reads on a side stream
-        cur = torch_cuda().cuda.current_stream()
-        cur.wait_event(ready)
-        for t in (dr.start_node, dr.start_off, dr.end_node, dr.end_off, dr.path_ptr, dr.path):
-            t.record_stream(cur)          # allocated on the copy stream, used on this one
+    if ready is not None:                 # transfers issued by prefetch_reads on the copy stream
+        torch_cuda().cuda.current_stream().wait_event(ready)
         dr.ready_event = None
     return dr
 
@@ -154,10 +169,8 @@ def prefetch_reads(batch):
     if getattr(batch, "_device", None) is not None:
         return
     torch = torch_cuda()
+    if getattr(batch, "_pinned", None) is None:
+        return                            # pageable memory: nothing to overlap
     if _copy_stream is None:
         _copy_stream = torch.cuda.Stream()
-    with torch.cuda.stream(_copy_stream):
-        dr = DeviceReads(batch)
-        dr.ready_event = torch.cuda.Event()
-        dr.ready_event.record(_copy_stream)
-    batch._device = dr
+    batch._device = DeviceReads(batch, copy_stream=_copy_stream)

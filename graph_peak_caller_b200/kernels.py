@@ -217,11 +217,20 @@ def max_paths(dgraph, pos, val, score_pos, score_val, q_pos, q_val, internal_id_
     torch = torch_cuda()
     lib = _lib.load()
     pcap, ncap = max(1024, pos.numel()), max(1 << 16, 32 * pos.numel())
+    fields = (("score", torch.float64, 8), ("start", torch.int32, 4), ("end", torch.int32, 4),
+              ("length", torch.int32, 4), ("order", torch.int32, 4), ("node_ptr", torch.int32, 4),
+              ("info", torch.uint8, 1), ("nodes", torch.int32, 4))   # ragged part last
     while True:
-        t = dict(start=empty(pcap, torch.int32), end=empty(pcap, torch.int32),
-                 length=empty(pcap, torch.int32), score=empty(pcap, torch.float64),
-                 info=empty(pcap, torch.uint8), node_ptr=empty(pcap + 1, torch.int32),
-                 nodes=empty(ncap, torch.int32), order=empty(pcap, torch.int32))
+        # one arena for all outputs, so that the host reads them back in one copy
+        counts = dict(score=pcap, start=pcap, end=pcap, length=pcap, order=pcap,
+                      node_ptr=pcap + 1, nodes=ncap, info=pcap)
+        layout, off = {}, 0
+        for name, dtype, size in fields:
+            layout[name] = (off, dtype, size)
+            off += (counts[name] * size + 15) & ~15
+        arena = empty(off, torch.uint8)
+        t = {name: arena[o:o + counts[name] * size].view(dtype)
+             for name, (o, dtype, size) in layout.items()}
         n_peaks, n_nodes = _u64(), _u64()
         status = lib.gpc_max_paths(
             ctypes.byref(dgraph.c), ptr(pos), ptr(val), pos.numel(), ptr(score_pos),
@@ -241,4 +250,6 @@ def max_paths(dgraph, pos, val, score_pos, score_val, q_pos, q_val, internal_id_
         out["node_ptr"] = t["node_ptr"][:n + 1]
         out["nodes"] = t["nodes"][:m]
         out["n"] = n
+        out["arena"] = (arena, {name: (o, dtype, size, out[name].numel())
+                                for name, (o, dtype, size) in layout.items()})
         return out

@@ -125,7 +125,15 @@ class PeakSet:
     """Final peaks of one graph, still as flat arrays (host numpy)."""
 
     def __init__(self, raw, fragment_length):
-        cpu = lambda t: t.cpu().numpy()
+        if "arena" in raw:          # all outputs live in one buffer: one readback
+            arena, layout = raw["arena"]
+            last = max(o + size * cnt for o, _, size, cnt in layout.values())
+            host = arena[:last].cpu()
+            views = {name: host[o:o + size * cnt].view(dtype).numpy()
+                     for name, (o, dtype, size, cnt) in layout.items()}
+            cpu = lambda t: views[next(k for k in layout if raw[k] is t)]
+        else:
+            cpu = lambda t: t.cpu().numpy()
         self.n_all = raw["n"]
         self.start = cpu(raw["start"])
         self.end = cpu(raw["end"])

@@ -38,7 +38,7 @@ def gpu_max_paths(graph, idx, val, sidx, sval, qidx, qval, shift):
                             to_device(np.asarray(sval, dtype=np.float64)),
                             to_device(np.asarray(qidx, dtype=np.int32)),
                             to_device(np.asarray(qval, dtype=np.float64)), shift)
-    o = {k: (cpu(v) if k != "n" else v) for k, v in out.items()}
+    o = {k: (cpu(v) if k not in ("n", "arena") else v) for k, v in out.items()}
     peaks = []
     for i in range(o["n"]):
         nodes = o["nodes"][o["node_ptr"][i]:o["node_ptr"][i + 1]].tolist()

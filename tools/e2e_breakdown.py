@@ -33,3 +33,22 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(3): step()
 torch.cuda.synchronize(); pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+
+# allocator behaviour: does a step still reach cudaMalloc in steady state?
+import graph_peak_caller_b200.device as _dev
+_orig_empty = torch.empty
+slow = []
+def _timed_empty(*a, **k):
+    t0 = time.perf_counter(); r = _orig_empty(*a, **k); dt = time.perf_counter() - t0
+    if dt > 3e-4: slow.append((round(dt * 1e3, 2), r.numel() * r.element_size()))
+    return r
+torch.empty = _timed_empty
+for i in range(4):
+    ms0 = torch.cuda.memory_stats()
+    step()
+    ms1 = torch.cuda.memory_stats()
+    print("step", i, "cudaMalloc calls", ms1["num_device_alloc"] - ms0["num_device_alloc"],
+          "cudaFree", ms1["num_device_free"] - ms0["num_device_free"],
+          "reserved MB", ms1["reserved_bytes.all.current"] >> 20,
+          "allocated MB", ms1["allocated_bytes.all.current"] >> 20, "slow empties", slow)
+    slow.clear()
