@@ -24,15 +24,14 @@
 namespace gpc {
 
 // Opportunistic memo of p(count, lambda): tracks take few distinct (count,
-// lambda) pairs (tens of thousands) compared to runs (tens of millions).  The
-// first thread that claims the slot of a pair evaluates it and publishes the
-// result; later threads reuse it.  Nobody ever waits: a slot that is claimed
-// but not yet published is simply recomputed by the visitor.
+// lambda) pairs (tens of thousands) compared to runs (tens of millions).
+// Whoever evaluates a pair publishes it; later visitors reuse it.  Nobody ever
+// waits: a pair that is not published (yet) is simply evaluated again.
 //
-// One 32-byte, write-once entry per pair, read with ordinary (L1-cached) loads:
-// an entry whose tag says READY was complete when the line was fetched, and a
-// stale line can only say "empty"/"claimed", in which case the atomic CAS
-// (served by L2) tells the truth.  Common pairs are therefore served from L1.
+// One 32-byte, write-once entry per pair.  The fast probe uses ordinary
+// (L1-cached) loads: an entry whose tag says READY was complete when the line
+// was fetched, and a stale line can only say "empty"/"claimed", which sends the
+// pair to the tile's miss queue, where the probe is repeated against L2.
 struct __align__(32) MemoEntry {
     unsigned long long tag;    // 0 empty | hash|1 claimed | hash|3 ready (hash has bits 0-1 clear)
     double count, lam, p;
@@ -51,49 +50,50 @@ __device__ __forceinline__ unsigned long long memo_hash(double count, double lam
     return x & ~3ull;
 }
 
-__device__ __forceinline__ double memo_pvalue(const PMemo& m, double count, double lam) {
-    if (count == 0.0) return 0.0;
-#ifdef GPC_EXP_DUMMY_P
-    return count + lam;
-#endif
-#ifdef GPC_EXP_NO_MEMO
-    return neglog10_poisson_sf(count, lam);
-#endif
-    if (!m.e) return neglog10_poisson_sf(count, lam);
-    const unsigned long long h = memo_hash(count, lam);
+constexpr int MEMO_PROBES = 16;
+
+// Read-only probe.  FROM_L2 bypasses L1 (used right before an evaluation).
+template <bool FROM_L2>
+__device__ __forceinline__ bool memo_find(const PMemo& m, unsigned long long h, double count,
+                                          double lam, double& p) {
     unsigned s = (unsigned)(h >> 20) & m.mask;
-    for (int probe = 0; probe < 16; ++probe) {
-        MemoEntry* e = &m.e[s];
-        unsigned long long tag = e->tag;                       // L1-cached
+    for (int probe = 0; probe < MEMO_PROBES; ++probe) {
+        const MemoEntry* e = &m.e[s];
+        unsigned long long tag = FROM_L2 ? __ldcg(&e->tag) : e->tag;
         if (tag == (h | 3ull)) {
-            if (e->count == count && e->lam == lam) return e->p;
-        } else if ((tag | 3ull) != (h | 3ull)) {
-            if (tag != 0ull && (tag & 3ull) == 3ull) {         // another pair lives here
-                s = (s + 1) & m.mask;
-                continue;
+            double c = FROM_L2 ? __ldcg(&e->count) : e->count;
+            double l = FROM_L2 ? __ldcg(&e->lam) : e->lam;
+            if (c == count && l == lam) {
+                p = FROM_L2 ? __ldcg(&e->p) : e->p;
+                return true;
             }
+        } else if (tag == 0ull || (tag | 3ull) == (h | 3ull)) {
+            return false;          // end of the chain, or the pair is being evaluated right now
         }
-        if (tag != (h | 3ull)) {
-            // empty or claimed as far as this SM's L1 knows: ask L2
-            unsigned long long old = atomicCAS(&e->tag, 0ull, h | 1ull);
-            if (old == 0ull) {                                 // mine: evaluate and publish
-                double p = neglog10_poisson_sf(count, lam);
-                e->count = count;
-                e->lam = lam;
-                e->p = p;
-                __threadfence();
-                *reinterpret_cast<volatile unsigned long long*>(&e->tag) = h | 3ull;
-                return p;
-            }
-            if (old == (h | 3ull)) {                           // ready in L2, stale in L1
-                if (__ldcg(&e->count) == count && __ldcg(&e->lam) == lam) return __ldcg(&e->p);
-            } else if (old == (h | 1ull)) {
-                break;                                         // owner still busy: do not wait
-            }
-        }
-        s = (s + 1) & m.mask;                                  // different pair: next slot
+        s = (s + 1) & m.mask;      // another pair lives (or is about to live) here
     }
-    return neglog10_poisson_sf(count, lam);
+    return false;
+}
+
+// Publishes an evaluated pair in the first free slot of its chain (best effort).
+__device__ __forceinline__ void memo_publish(const PMemo& m, unsigned long long h, double count,
+                                             double lam, double p) {
+    unsigned s = (unsigned)(h >> 20) & m.mask;
+    for (int probe = 0; probe < MEMO_PROBES; ++probe) {
+        MemoEntry* e = &m.e[s];
+        unsigned long long tag = __ldcg(&e->tag);
+        if (tag == 0ull) tag = atomicCAS(&e->tag, 0ull, h | 1ull);
+        if (tag == 0ull) {                                     // mine
+            e->count = count;
+            e->lam = lam;
+            e->p = p;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned long long*>(&e->tag) = h | 3ull;
+            return;
+        }
+        if ((tag | 3ull) == (h | 3ull)) return;                // somebody else publishes this hash
+        s = (s + 1) & m.mask;
+    }
 }
 
 constexpr int PV_THREADS = 256;
@@ -117,23 +117,37 @@ __global__ void pv_partition_kernel(const uint32_t* __restrict__ spos, unsigned 
     split[t] = lo;
 }
 
+// Step 1: merge the two tracks and evaluate p at every distinct position.
+//
+// The number of positions a tile emits is known from the merge alone, so the
+// tile publishes its share of the chained scan BEFORE any Poisson evaluation:
+// a tile that has to evaluate new (count, lambda) pairs (tens of microseconds)
+// delays nobody else.  (The first version compacted equal neighbouring p in
+// this kernel; the output count then depended on p, every tile waited in the
+// look-back for the slowest tile of its wave, and 56 % of all stall samples
+// sat on that barrier -- profiles/pvalues_r01_before_raw.csv.)
+// Pairs that the L1 probe does not find go to a per-tile queue that the whole
+// block drains, one pair per thread, so evaluations run on full warps.
 __global__ void __launch_bounds__(PV_THREADS)
-pvalues_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sval, unsigned ns,
+pv_eval_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sval, unsigned ns,
                double sample_scale, const uint32_t* __restrict__ cpos,
                const double* __restrict__ cval, unsigned nc, double control_scale, PMemo memo,
                const uint32_t* __restrict__ split, uint32_t* __restrict__ out_pos,
                double* __restrict__ out_p, unsigned long long* __restrict__ status,
                unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_count) {
     // slices of both tracks that this tile merges, plus one element before
-    // (state in force at the tile's left edge) and one after (look-ahead)
+    // (state in force at the tile's left edge) and one after (look-ahead);
+    // after the merge a_val / b_val are reused as the miss queue
     __shared__ uint32_t a_pos[PV_TILE + 2];
     __shared__ int32_t a_val[PV_TILE + 2];
     __shared__ uint32_t b_pos[PV_TILE + 2];
     __shared__ double b_val[PV_TILE + 2];
     __shared__ unsigned s_slot;
+    __shared__ unsigned s_nq;
     __shared__ int s_scan[33];
     __shared__ unsigned long long s_obase;
     const unsigned tile = claim_tile(ticket, &s_slot);
+    if (threadIdx.x == 0) s_nq = 0;
     const unsigned total = ns + nc;
     const unsigned t0 = min(total, tile * PV_TILE), t1 = min(total, t0 + PV_TILE);
     const unsigned i_lo = split[tile], i_hi = split[tile + 1];
@@ -157,7 +171,8 @@ pvalues_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
     const unsigned m = na + nb;
     const unsigned d0 = min(m, threadIdx.x * PV_ITEMS), d1 = min(m, d0 + PV_ITEMS);
     uint32_t e_pos[PV_ITEMS];
-    double e_p[PV_ITEMS];
+    int32_t e_k[PV_ITEMS];
+    double e_lam[PV_ITEMS];
     int cnt = 0;
     if (d0 < d1) {
         // merge-path split of the local diagonal d0 (ties: sample entry first)
@@ -167,48 +182,106 @@ pvalues_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
             if (a_pos[mid + 1] <= b_pos[d0 - 1 - mid + 1]) lo = mid + 1; else hi = mid;
         }
         unsigned i = lo, j = d0 - lo;
-        // end of the previous position group = state before my first position
-        uint32_t first_pos;
-        {
-            bool take_s = i < na && (j >= nb || a_pos[i + 1] <= b_pos[j + 1]);
-            first_pos = take_s ? a_pos[i + 1] : b_pos[j + 1];
-        }
-        bool have_prev;
-        double prev_p = 0.0;
-        {
-            // walk back over entries of the same position; slot 0 is the entry just
-            // before the tile, anything earlier is read from global memory (rare)
-            long long gi = (long long)i_lo + i, gj = (long long)j_lo + j;   // global cursors
-            while (gi > 0 && (gi - 1 >= (long long)i_lo - 1 ? a_pos[gi - i_lo] : spos[gi - 1]) == first_pos) --gi;
-            while (gj > 0 && (gj - 1 >= (long long)j_lo - 1 ? b_pos[gj - j_lo] : cpos[gj - 1]) == first_pos) --gj;
-            have_prev = gi > 0 || gj > 0;
-            if (have_prev) {
-                double k = 0.0, lam = 0.0;
-                if (gi > 0) k = (gi - 1 >= (long long)i_lo - 1) ? (double)a_val[gi - i_lo] : (double)sval[gi - 1];
-                if (gj > 0) lam = (gj - 1 >= (long long)j_lo - 1) ? b_val[gj - j_lo]
-                                                                   : __dmul_rn(cval[gj - 1], control_scale);
-                prev_p = memo_pvalue(memo, k == 0.0 ? 0.0 : k * sample_scale, lam);
-            }
-        }
         // values in force before my first element (slot 0 = entry before the tile; empty -> 0)
-        double k_cur = (double)a_val[i], lam_cur = b_val[j];
+        int32_t k_cur = a_val[i];
+        double lam_cur = b_val[j];
         for (unsigned d = d0; d < d1; ++d) {
             bool take_s = i < na && (j >= nb || a_pos[i + 1] <= b_pos[j + 1]);
             uint32_t pos;
-            if (take_s) { pos = a_pos[i + 1]; k_cur = (double)a_val[i + 1]; ++i; }
+            if (take_s) { pos = a_pos[i + 1]; k_cur = a_val[i + 1]; ++i; }
             else { pos = b_pos[j + 1]; lam_cur = b_val[j + 1]; ++j; }
-            // look-ahead: slots na + 1 / nb + 1 hold the first entries after the tile
+            // look-ahead: slots na + 1 / nb + 1 hold the first entries after the tile;
+            // the last entry of a position group carries the values in force there
             uint32_t next_pos = min(a_pos[i + 1], b_pos[j + 1]);     // 0xffffffff when exhausted
             if (next_pos != pos) {
-                double p = memo_pvalue(memo, k_cur == 0.0 ? 0.0 : k_cur * sample_scale, lam_cur);
-                if (!have_prev || p != prev_p) {
-                    e_pos[cnt] = pos;
-                    e_p[cnt] = p;
-                    ++cnt;
-                }
-                prev_p = p;
-                have_prev = true;
+                e_pos[cnt] = pos;
+                e_k[cnt] = k_cur;
+                e_lam[cnt] = lam_cur;
+                ++cnt;
             }
+        }
+    }
+    int tile_out;
+    int o = block_excl_sum<int>(cnt, s_scan, tile_out);     // (barriers: the merge is over)
+    if (threadIdx.x < 32) {
+        unsigned long long b = lookback_excl_warp(status, tile, (unsigned long long)tile_out);
+        if (threadIdx.x == 0) {
+            s_obase = b;
+            if (tile == gridDim.x - 1) *out_count = b + tile_out;
+        }
+    }
+    // fast path: L1 probe of the memo
+    double e_p[PV_ITEMS];
+    unsigned miss = 0;
+#pragma unroll
+    for (int t = 0; t < PV_ITEMS; ++t) {
+        e_p[t] = 0.0;
+        if (t < cnt && e_k[t] != 0) {
+            double count = (double)e_k[t] * sample_scale;
+            bool found = false;
+#if !defined(GPC_EXP_NO_MEMO)
+            if (memo.e) found = memo_find<false>(memo, memo_hash(count, e_lam[t]), count, e_lam[t], e_p[t]);
+#endif
+            if (!found) miss |= 1u << t;
+        }
+    }
+    unsigned q0 = 0;
+    if (miss) {
+        q0 = atomicAdd(&s_nq, (unsigned)__popc(miss));
+        unsigned q = q0;
+#pragma unroll
+        for (int t = 0; t < PV_ITEMS; ++t)
+            if ((miss >> t) & 1u) { a_val[q] = e_k[t]; b_val[q] = e_lam[t]; ++q; }
+    }
+    __syncthreads();
+    // slow path: the block drains the queue; L2 probe first (pairs published meanwhile)
+    const unsigned nq = s_nq;
+    for (unsigned q = threadIdx.x; q < nq; q += PV_THREADS) {
+        double count = (double)a_val[q] * sample_scale, lam = b_val[q], p;
+        unsigned long long h = memo_hash(count, lam);
+        if (!(memo.e && memo_find<true>(memo, h, count, lam, p))) {
+            p = neglog10_poisson_sf(count, lam);
+            if (memo.e) memo_publish(memo, h, count, lam, p);
+        }
+        b_val[q] = p;
+    }
+    __syncthreads();
+    if (miss) {
+        unsigned q = q0;
+#pragma unroll
+        for (int t = 0; t < PV_ITEMS; ++t)
+            if ((miss >> t) & 1u) e_p[t] = b_val[q++];
+    }
+    unsigned long long w = s_obase + o;
+#pragma unroll
+    for (int t = 0; t < PV_ITEMS; ++t)
+        if (t < cnt) { out_pos[w + t] = e_pos[t]; out_p[w + t] = e_p[t]; }
+}
+
+// Step 2: canonical runs -- entries whose p equals the previous position's p
+// are dropped (SparseDiffs keeps only positions where the value changes).
+// n is read from device memory (the count step 1 left there).
+__global__ void __launch_bounds__(SC_THREADS)
+pv_canon_kernel(const uint32_t* __restrict__ in_pos, const double* __restrict__ in_p,
+                const unsigned long long* __restrict__ n_ptr, uint32_t* __restrict__ out_pos,
+                double* __restrict__ out_p, unsigned long long* __restrict__ status,
+                unsigned long long* __restrict__ out_count) {
+    __shared__ int s_scan[33];
+    __shared__ unsigned long long s_obase;
+    const unsigned n = (unsigned)*n_ptr;
+    const unsigned tile = blockIdx.x;
+    if ((unsigned long long)tile * SC_TILE >= n) return;
+    const unsigned base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
+    double v[SC_ITEMS];
+    double prev = (base > 0 && base < n) ? in_p[base - 1] : 0.0;
+    unsigned keep = 0;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        if (base + j < n) {
+            v[j] = in_p[base + j];
+            if (base + j == 0 || v[j] != prev) { keep |= 1u << j; ++cnt; }
+            prev = v[j];
         }
     }
     int tile_out;
@@ -217,14 +290,14 @@ pvalues_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
         unsigned long long b = lookback_excl_warp(status, tile, (unsigned long long)tile_out);
         if (threadIdx.x == 0) {
             s_obase = b;
-            if (tile == gridDim.x - 1) *out_count = b + tile_out;
+            if (tile == (n - 1) / SC_TILE) *out_count = b + tile_out;
         }
     }
     __syncthreads();
     unsigned long long w = s_obase + o;
 #pragma unroll
-    for (int t = 0; t < PV_ITEMS; ++t)
-        if (t < cnt) { out_pos[w + t] = e_pos[t]; out_p[w + t] = e_p[t]; }
+    for (int j = 0; j < SC_ITEMS; ++j)
+        if ((keep >> j) & 1u) { out_pos[w] = in_pos[base + j]; out_p[w] = v[j]; ++w; }
 }
 
 // ---- (p -> base pairs) table --------------------------------------------------
@@ -428,13 +501,15 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
     if (total == 0) return GPC_OK;
     if (total >= (1ull << 31)) { set_error("tracks too long"); return GPC_ERR_ARG; }
     unsigned tiles = div_up(total, PV_TILE);
+    unsigned ctiles = div_up(total, SC_TILE);
     Scratch sc;
-    size_t bytes = (size_t)tiles * 8 + 32;
+    size_t bytes = ((size_t)tiles + ctiles) * 8 + 64;
     GPC_CUDA(sc.alloc(bytes, stream));
     GPC_CUDA(cudaMemsetAsync(sc.p, 0, bytes, stream));
-    unsigned long long* count = sc.as<unsigned long long>();
-    unsigned* ticket = reinterpret_cast<unsigned*>(count + 1);
+    unsigned long long* count = sc.as<unsigned long long>();      // [0] positions, [1] runs
+    unsigned* ticket = reinterpret_cast<unsigned*>(count + 2);
     unsigned long long* status = count + 4;
+    unsigned long long* cstatus = status + tiles;
     // memo table: 2^20 entries of 32 B (stays in L2); small inputs do without
     Scratch memo_buf;
     PMemo memo;
@@ -449,24 +524,31 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
         memo.e = memo_buf.as<MemoEntry>();
         memo.mask = (unsigned)(cap - 1);
     }
-    Scratch split;
+    Scratch split, tmp_pos, tmp_p;
     GPC_CUDA(split.alloc((size_t)(tiles + 1) * 4, stream));
+    GPC_CUDA(tmp_pos.alloc(total * 4, stream));
+    GPC_CUDA(tmp_p.alloc(total * 8, stream));
     GPC_PROF("pv_partition");
     pv_partition_kernel<<<div_up(tiles + 1, 256), 256, 0, stream>>>(
         sample_pos, (unsigned)n_sample, control_pos, (unsigned)n_control, tiles, split.as<uint32_t>());
     GPC_LAUNCH_CHECK();
     GPC_PROF_BYTES("pvalues", 8.0 * n_sample + 12.0 * n_control);
-    pvalues_kernel<<<tiles, PV_THREADS, 0, stream>>>(sample_pos, sample_val, (unsigned)n_sample,
+    pv_eval_kernel<<<tiles, PV_THREADS, 0, stream>>>(sample_pos, sample_val, (unsigned)n_sample,
                                                     sample_scale, control_pos, control_val,
                                                     (unsigned)n_control, control_scale, memo,
-                                                    split.as<uint32_t>(), out_pos, out_p, status,
-                                                    ticket, count);
+                                                    split.as<uint32_t>(), tmp_pos.as<uint32_t>(),
+                                                    tmp_p.as<double>(), status, ticket, count);
     GPC_LAUNCH_CHECK();
-    unsigned long long h = 0;
-    GPC_CUDA(cudaMemcpyAsync(&h, count, 8, cudaMemcpyDeviceToHost, stream));
+    GPC_PROF("pv_canon");
+    pv_canon_kernel<<<ctiles, SC_THREADS, 0, stream>>>(tmp_pos.as<uint32_t>(), tmp_p.as<double>(),
+                                                      count, out_pos, out_p, cstatus, count + 1);
+    GPC_LAUNCH_CHECK();
+    unsigned long long h[2] = {0, 0};
+    GPC_CUDA(cudaMemcpyAsync(h, count, 16, cudaMemcpyDeviceToHost, stream));
     GPC_CUDA(cudaStreamSynchronize(stream));
-    *n_out = h;
-    prof_add_bytes("pvalues", 12.0 * (double)h);
+    *n_out = h[1];
+    prof_add_bytes("pvalues", 12.0 * (double)h[1]);
+    prof_add_bytes("pv_canon", 12.0 * (double)h[0] + 12.0 * (double)h[1]);
     return GPC_OK;
 }
 

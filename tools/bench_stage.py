@@ -55,6 +55,16 @@ elif what == "pvalues":
     rep = _lib.profile_report()
     print("pvalues stage %.3f ms, kernel %.3f ms, %d runs, identical to the dump: %s" % (
         ms, rep["pvalues"][1], ppos.numel(), same))
+    print({k: round(v[1], 3) for k, v in rep.items()})
+    if len(sys.argv) > 2 and sys.argv[2] == "stats":
+        u = torch.unique(torch.cat([spos, cpos]))
+        k = sval[(torch.searchsorted(spos, u, right=True) - 1).clamp(min=0)]
+        # last control entry of a position wins
+        lam = cval[(torch.searchsorted(cpos, u, right=True) - 1).clamp(min=0)]
+        nz = k != 0
+        pairs = torch.unique(torch.stack([k[nz].to(torch.float64), lam[nz]]), dim=1)
+        print("positions %d, with count != 0: %d, distinct (count, lambda) pairs: %d, distinct lambda %d, max count %d"
+              % (u.numel(), int(nz.sum()), pairs.shape[1], torch.unique(lam).numel(), int(k.max())))
 elif what == "sort32":
     n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 16_000_000
     bits = int(sys.argv[3]) if len(sys.argv) > 3 else 26
