@@ -650,11 +650,7 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
     GPC_LAUNCH_CHECK();
     unsigned long long hU = 0, last_key = 0;
     int herr = 0, not_integer = 0;
-    GPC_CUDA(cudaMemcpyAsync(&hU, total.p, 8, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaMemcpyAsync(&not_integer, err + 1, 4, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaMemcpyAsync(&last_key, keys + (n - 1), 8, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({total.p, &hU, (unsigned)(8)}, {err, &herr, (unsigned)(4)}, {err + 1, &not_integer, (unsigned)(4)}, {keys + (n - 1), &last_key, (unsigned)(8)});
     const double x_last = key_to_f64(last_key);
     if (herr) {
         set_error("Interval has node(s) not part of graph/pileup");
@@ -704,8 +700,7 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
             toff.as<uint32_t>(), n_dense, out_pos, out_val);
         GPC_LAUNCH_CHECK();
         unsigned long long hd = 0;
-        GPC_CUDA(cudaMemcpyAsync(&hd, dcount, 8, cudaMemcpyDeviceToHost, stream));
-        GPC_CUDA(cudaStreamSynchronize(stream));
+        GPC_READ_BACK({dcount, &hd, (unsigned)(8)});
         *n_out = hd;
         prof_add_bytes("linear_dense", 16.0 * (double)hd);
         return GPC_OK;
@@ -763,9 +758,7 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
         out_pos, out_val, status, ticket, count, err);
     GPC_LAUNCH_CHECK();
     unsigned long long h = 0;
-    GPC_CUDA(cudaMemcpyAsync(&h, count, 8, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({count, &h, (unsigned)(8)}, {err, &herr, (unsigned)(4)});
     if (herr) {
         set_error("linear track: merge tile overflow");
         return herr;
@@ -799,8 +792,7 @@ extern "C" int gpc_control_backproject(const gpc_graph_t* graph, const uint8_t* 
     GPC_TRY(exclusive_scan<uint32_t>(count.as<uint32_t>(), offs.as<uint32_t>(), n,
                                      total.as<unsigned long long>(), stream));
     unsigned long long h = 0;
-    GPC_CUDA(cudaMemcpyAsync(&h, total.p, 8, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({total.p, &h, (unsigned)(8)});
     *n_out = h;
     if (h > out_capacity) return GPC_ERR_CAPACITY;
     GPC_PROF("backproject_emit");

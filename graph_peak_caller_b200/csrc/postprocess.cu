@@ -812,8 +812,7 @@ static int scan_flags(const uint8_t* flag, uint32_t* offs, size_t n, unsigned lo
     Scratch t;
     GPC_CUDA(t.alloc(8, stream));
     GPC_TRY(exclusive_scan<uint8_t>(flag, offs, n, t.as<unsigned long long>(), stream));
-    GPC_CUDA(cudaMemcpyAsync(total_host, t.p, 8, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({t.p, total_host, (unsigned)(8)});
     return GPC_OK;
 }
 static int scan_counts(const uint32_t* cnt, uint32_t* offs, size_t n, unsigned long long* total_host,
@@ -821,8 +820,7 @@ static int scan_counts(const uint32_t* cnt, uint32_t* offs, size_t n, unsigned l
     Scratch t;
     GPC_CUDA(t.alloc(8, stream));
     GPC_TRY(exclusive_scan<uint32_t>(cnt, offs, n, t.as<unsigned long long>(), stream));
-    GPC_CUDA(cudaMemcpyAsync(total_host, t.p, 8, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({t.p, total_host, (unsigned)(8)});
     return GPC_OK;
 }
 
@@ -842,10 +840,7 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
     const uint32_t n = graph->n_nodes;
     uint8_t v_first = 0, v_last = 0;
     uint32_t p_last = 0;
-    GPC_CUDA(cudaMemcpyAsync(&v_first, val, 1, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaMemcpyAsync(&v_last, val + n_runs - 1, 1, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaMemcpyAsync(&p_last, pos + n_runs - 1, 4, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({val, &v_first, (unsigned)(1)}, {val + n_runs - 1, &v_last, (unsigned)(1)}, {pos + n_runs - 1, &p_last, (unsigned)(4)});
     const uint32_t lo = v_first ? 1 : 0;
     uint32_t hi = (uint32_t)n_runs;
     const int trailing = v_last == 0;
@@ -997,7 +992,6 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
     bool_runs_emit_kernel<<<GRID(n_ev)>>>(ev, (uint32_t)n_ev, flag.as<uint8_t>(),
                                           eoffs.as<uint32_t>(), out_pos, out_val);
     GPC_LAUNCH_CHECK();
-    GPC_CUDA(cudaStreamSynchronize(stream));
     *n_out = total;
     return GPC_OK;
 }
@@ -1017,9 +1011,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     if (n_runs == 0) { set_error("empty track"); return GPC_ERR_ARG; }
     const uint32_t n = graph->n_nodes;
     uint8_t v_first = 0, v_last = 0;
-    GPC_CUDA(cudaMemcpyAsync(&v_first, val, 1, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaMemcpyAsync(&v_last, val + n_runs - 1, 1, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({val, &v_first, (unsigned)(1)}, {val + n_runs - 1, &v_last, (unsigned)(1)});
     // get_segments (maxpaths.py:43-50)
     const uint32_t first = v_first ? 0 : 1;
     const uint32_t n_idx = (uint32_t)n_runs - first + (v_last ? 1 : 0);
@@ -1218,7 +1210,6 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
                                                   stream)));
     GPC_CUDA(cudaMemcpyAsync(order, in_tmp ? si1.p : si0.p, (size_t)n_pk * 4,
                              cudaMemcpyDeviceToDevice, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
     return GPC_OK;
 }
 

@@ -41,8 +41,7 @@ extern "C" int gpc_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_
     GPC_CUDA(t.alloc(8, stream));
     GPC_TRY(exclusive_scan<uint32_t>(in, out, n, t.as<unsigned long long>(), stream));
     unsigned long long h = 0;
-    GPC_CUDA(cudaMemcpyAsync(&h, t.p, 8, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({t.p, &h, (unsigned)(8)});
     *total = h;
     return GPC_OK;
 }

@@ -261,43 +261,70 @@ pv_eval_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
 // Step 2: canonical runs -- entries whose p equals the previous position's p
 // are dropped (SparseDiffs keeps only positions where the value changes).
 // n is read from device memory (the count step 1 left there).
+// Persistent blocks, two tiles in flight: a tile's aggregate is published, then
+// the NEXT tile is loaded, and only then the first tile's prefix is resolved.
+struct CanonTile {
+    unsigned tile, keep;
+    int o, total;
+    double v[SC_ITEMS];
+};
+
 __global__ void __launch_bounds__(SC_THREADS)
 pv_canon_kernel(const uint32_t* __restrict__ in_pos, const double* __restrict__ in_p,
                 const unsigned long long* __restrict__ n_ptr, uint32_t* __restrict__ out_pos,
                 double* __restrict__ out_p, unsigned long long* __restrict__ status,
-                unsigned long long* __restrict__ out_count) {
+                unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_count) {
     __shared__ int s_scan[33];
+    __shared__ unsigned s_slot;
     __shared__ unsigned long long s_obase;
     const unsigned n = (unsigned)*n_ptr;
-    const unsigned tile = blockIdx.x;
-    if ((unsigned long long)tile * SC_TILE >= n) return;
-    const unsigned base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
-    double v[SC_ITEMS];
-    double prev = (base > 0 && base < n) ? in_p[base - 1] : 0.0;
-    unsigned keep = 0;
-    int cnt = 0;
+    const unsigned n_tiles = (n + SC_TILE - 1) / SC_TILE;
+
+    auto stage = [&](CanonTile& t) -> bool {       // claim, load, count, publish the aggregate
+        t.tile = claim_tile(ticket, &s_slot);
+        if (t.tile >= n_tiles) return false;
+        const unsigned base = t.tile * SC_TILE + threadIdx.x * SC_ITEMS;
+        double prev = (base > 0 && base < n) ? in_p[base - 1] : 0.0;
+        t.keep = 0;
+        int cnt = 0;
 #pragma unroll
-    for (int j = 0; j < SC_ITEMS; ++j) {
-        if (base + j < n) {
-            v[j] = in_p[base + j];
-            if (base + j == 0 || v[j] != prev) { keep |= 1u << j; ++cnt; }
-            prev = v[j];
+        for (int j = 0; j < SC_ITEMS; ++j) {
+            t.v[j] = 0.0;
+            if (base + j < n) {
+                t.v[j] = in_p[base + j];
+                if (base + j == 0 || t.v[j] != prev) { t.keep |= 1u << j; ++cnt; }
+                prev = t.v[j];
+            }
         }
-    }
-    int tile_out;
-    int o = block_excl_sum<int>(cnt, s_scan, tile_out);
-    if (threadIdx.x < 32) {
-        unsigned long long b = lookback_excl_warp(status, tile, (unsigned long long)tile_out);
-        if (threadIdx.x == 0) {
-            s_obase = b;
-            if (tile == (n - 1) / SC_TILE) *out_count = b + tile_out;
+        t.o = block_excl_sum<int>(cnt, s_scan, t.total);
+        if (threadIdx.x == 0) lb_publish_agg(status, t.tile, (unsigned long long)t.total);
+        return true;
+    };
+    auto finish = [&](const CanonTile& t) {        // resolve the prefix, write
+        if (threadIdx.x < 32) {
+            unsigned long long b = lb_resolve_warp(status, t.tile, (unsigned long long)t.total);
+            if (threadIdx.x == 0) {
+                s_obase = b;
+                if (t.tile == n_tiles - 1) *out_count = b + t.total;
+            }
         }
-    }
-    __syncthreads();
-    unsigned long long w = s_obase + o;
+        __syncthreads();
+        unsigned long long w = s_obase + t.o;
+        const unsigned base = t.tile * SC_TILE + threadIdx.x * SC_ITEMS;
 #pragma unroll
-    for (int j = 0; j < SC_ITEMS; ++j)
-        if ((keep >> j) & 1u) { out_pos[w] = in_pos[base + j]; out_p[w] = v[j]; ++w; }
+        for (int j = 0; j < SC_ITEMS; ++j)
+            if ((t.keep >> j) & 1u) { out_pos[w] = in_pos[base + j]; out_p[w] = t.v[j]; ++w; }
+        __syncthreads();                           // s_obase is reused
+    };
+
+    CanonTile a, b;
+    if (!stage(a)) return;
+    while (true) {
+        bool more = stage(b);
+        finish(a);
+        if (!more) break;
+        a = b;
+    }
 }
 
 // ---- (p -> base pairs) table --------------------------------------------------
@@ -508,6 +535,7 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
     GPC_CUDA(cudaMemsetAsync(sc.p, 0, bytes, stream));
     unsigned long long* count = sc.as<unsigned long long>();      // [0] positions, [1] runs
     unsigned* ticket = reinterpret_cast<unsigned*>(count + 2);
+    unsigned* cticket = ticket + 1;
     unsigned long long* status = count + 4;
     unsigned long long* cstatus = status + tiles;
     // memo table: 2^20 entries of 32 B (stays in L2); small inputs do without
@@ -540,12 +568,12 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
                                                     tmp_p.as<double>(), status, ticket, count);
     GPC_LAUNCH_CHECK();
     GPC_PROF("pv_canon");
-    pv_canon_kernel<<<ctiles, SC_THREADS, 0, stream>>>(tmp_pos.as<uint32_t>(), tmp_p.as<double>(),
-                                                      count, out_pos, out_p, cstatus, count + 1);
+    pv_canon_kernel<<<min(ctiles, (unsigned)sm_count() * 6u), SC_THREADS, 0, stream>>>(
+        tmp_pos.as<uint32_t>(), tmp_p.as<double>(), count, out_pos, out_p, cstatus, cticket,
+        count + 1);
     GPC_LAUNCH_CHECK();
     unsigned long long h[2] = {0, 0};
-    GPC_CUDA(cudaMemcpyAsync(h, count, 16, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({count, h, (unsigned)(16)});
     *n_out = h[1];
     prof_add_bytes("pvalues", 12.0 * (double)h[1]);
     prof_add_bytes("pv_canon", 12.0 * (double)h[0] + 12.0 * (double)h[1]);
@@ -585,9 +613,7 @@ extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n
                                         total.as<unsigned long long>(), stream));
         unsigned long long h = 0;
         int hfail = 0;
-        GPC_CUDA(cudaMemcpyAsync(&h, total.p, 8, cudaMemcpyDeviceToHost, stream));
-        GPC_CUDA(cudaMemcpyAsync(&hfail, fail.p, 4, cudaMemcpyDeviceToHost, stream));
-        GPC_CUDA(cudaStreamSynchronize(stream));
+        GPC_READ_BACK({total.p, &h, (unsigned)(8)}, {fail.p, &hfail, (unsigned)(4)});
         if (hfail || h * 2 > cap) {               // too full: grow and redo
             if (cap >= 4ull * n + (1ull << 16)) { set_error("p table overflow"); return GPC_ERR_INTERNAL; }
             cap <<= 2;
@@ -600,8 +626,7 @@ extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n
             keys.as<unsigned long long>(), counts.as<unsigned long long>(), offs.as<uint32_t>(),
             (unsigned)cap, table_p, reinterpret_cast<unsigned long long*>(table_count));
         GPC_LAUNCH_CHECK();
-        GPC_CUDA(cudaStreamSynchronize(stream));
-        return GPC_OK;
+        return GPC_OK;                            // (outputs complete in stream order)
     }
 }
 
@@ -635,8 +660,7 @@ extern "C" int gpc_qtable_build(const double* table_p, const uint64_t* table_cou
         out_p, out_q, cnt.as<unsigned long long>());
     GPC_LAUNCH_CHECK();
     unsigned long long h = 0;
-    GPC_CUDA(cudaMemcpyAsync(&h, cnt.p, 8, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({cnt.p, &h, (unsigned)(8)});
     *n_out = h;
     return GPC_OK;
 }
@@ -654,8 +678,7 @@ extern "C" int gpc_qvalues_apply(const double* p, uint64_t n_runs, const double*
         p, (unsigned)n_runs, table_p, table_q, (unsigned)n_table, out_q, miss.as<int>());
     GPC_LAUNCH_CHECK();
     int h = 0;
-    GPC_CUDA(cudaMemcpyAsync(&h, miss.p, 4, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({miss.p, &h, (unsigned)(4)});
     if (h) { set_error("p-value without an entry in the p->q table"); return GPC_ERR_ARG; }
     return GPC_OK;
 }
@@ -680,8 +703,7 @@ extern "C" int gpc_threshold(const uint32_t* pos, const double* q, uint64_t n_ru
                                                              offs.as<uint32_t>(), out_pos, out_val);
     GPC_LAUNCH_CHECK();
     unsigned long long h = 0;
-    GPC_CUDA(cudaMemcpyAsync(&h, total.p, 8, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({total.p, &h, (unsigned)(8)});
     *n_out = h;
     return GPC_OK;
 }

@@ -149,24 +149,41 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out
 #pragma unroll
             for (int t = 0; t < DPT; ++t)
                 st[tile * RS_RADIX + threadIdx.x * DPT + t] = RS_ST_AGG | tot[t];
+            // LB_WIDE predecessors per round trip.  With one predecessor per round
+            // the walk is as slow as the tiles are spaced and its depth never
+            // shrinks (16 round trips per tile were measured); several at once
+            // make the walk outrun the wavefront, so the depth collapses.
+#ifdef GPC_RS_LB_WIDE
+            constexpr int LB_WIDE = GPC_RS_LB_WIDE;
+#else
+            constexpr int LB_WIDE = 8 / DPT;
+#endif
             int tt[DPT];
             bool done[DPT];
 #pragma unroll
             for (int t = 0; t < DPT; ++t) { tt[t] = (int)tile - 1; done[t] = false; }
             bool all_done = false;
             while (!all_done) {
-                unsigned sv[DPT];
+                unsigned sv[DPT][LB_WIDE];
 #pragma unroll
                 for (int t = 0; t < DPT; ++t)
-                    sv[t] = done[t] ? 0u : st[tt[t] * RS_RADIX + threadIdx.x * DPT + t];
+#pragma unroll
+                    for (int k = 0; k < LB_WIDE; ++k)
+                        sv[t][k] = done[t] ? 0u
+                                           : st[max(tt[t] - k, 0) * RS_RADIX + threadIdx.x * DPT + t];
                 all_done = true;
 #pragma unroll
                 for (int t = 0; t < DPT; ++t) {
-                    if (done[t]) continue;
-                    unsigned flag = sv[t] & ~RS_ST_MASK;
-                    if (flag != 0) {
-                        excl[t] += sv[t] & RS_ST_MASK;
-                        if (flag == RS_ST_PREFIX) done[t] = true; else --tt[t];
+                    bool open = !done[t];                // false once an empty slot was met
+#pragma unroll
+                    for (int k = 0; k < LB_WIDE; ++k) {
+                        unsigned flag = sv[t][k] & ~RS_ST_MASK;
+                        open = open && flag != 0;
+                        if (open) {
+                            excl[t] += sv[t][k] & RS_ST_MASK;
+                            --tt[t];
+                            if (flag == RS_ST_PREFIX) { done[t] = true; open = false; }
+                        }
                     }
                     all_done &= done[t];
                 }
@@ -289,8 +306,7 @@ int radix_sort_bits(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_t
     GPC_LAUNCH_CHECK();
     unsigned h_trivial[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (skip_trivial) {
-        GPC_CUDA(cudaMemcpyAsync(h_trivial, trivial, sizeof(h_trivial), cudaMemcpyDeviceToHost, stream));
-        GPC_CUDA(cudaStreamSynchronize(stream));
+        GPC_READ_BACK({trivial, h_trivial, (unsigned)(sizeof(h_trivial))});
     }
     bool in_tmp = false;
     for (int p = 0; p < n_passes; ++p) {

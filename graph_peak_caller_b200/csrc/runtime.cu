@@ -1,5 +1,7 @@
 // Error text, version string, device properties.
 #include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <map>
@@ -83,6 +85,67 @@ int sm_count() {
     return n;
 }
 
+// ---- read_back ---------------------------------------------------------------
+struct RbArgs { const unsigned char* src[4]; unsigned bytes[4]; int n; };
+constexpr unsigned RB_PAYLOAD = 160;
+
+__global__ void readback_kernel(RbArgs a, volatile unsigned char* slot, unsigned long long seq) {
+    unsigned off = 0;
+    for (int i = 0; i < a.n; ++i) {
+        for (unsigned b = 0; b < a.bytes[i]; ++b) slot[off + b] = a.src[i][b];
+        off += (a.bytes[i] + 7u) & ~7u;
+    }
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(slot + RB_PAYLOAD) = seq;
+}
+
+struct RbSlot {
+    unsigned char* host = nullptr;
+    unsigned char* dev = nullptr;
+    unsigned long long seq = 0;
+};
+static thread_local RbSlot g_rb;
+
+int read_back(const RbItem* items, int n_items, cudaStream_t stream) {
+    if (n_items <= 0) return GPC_OK;
+    if (!g_rb.host) {
+        GPC_CUDA(cudaHostAlloc((void**)&g_rb.host, 256, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(g_rb.host, 0, 256);
+        GPC_CUDA(cudaHostGetDevicePointer((void**)&g_rb.dev, g_rb.host, 0));
+    }
+    RbArgs a;
+    unsigned total = 0;
+    a.n = n_items;
+    if (n_items > 4) { set_error("read_back: too many items"); return GPC_ERR_INTERNAL; }
+    for (int i = 0; i < 4; ++i) {
+        a.src[i] = i < n_items ? static_cast<const unsigned char*>(items[i].dev) : nullptr;
+        a.bytes[i] = i < n_items ? items[i].bytes : 0;
+        total += (a.bytes[i] + 7u) & ~7u;
+    }
+    if (total > RB_PAYLOAD) { set_error("read_back: payload too large"); return GPC_ERR_INTERNAL; }
+    const unsigned long long seq = ++g_rb.seq;
+    prof_begin("readback", stream);
+    readback_kernel<<<1, 1, 0, stream>>>(a, g_rb.dev, seq);
+    GPC_LAUNCH_CHECK();
+    volatile unsigned long long* flag =
+        reinterpret_cast<volatile unsigned long long*>(g_rb.host + RB_PAYLOAD);
+    for (unsigned spins = 1; *flag != seq; ++spins) {
+        if ((spins & 0x3fff) == 0) {              // a faulting kernel must not hang the host
+            cudaError_t q = cudaStreamQuery(stream);
+            if (q == cudaErrorNotReady) continue;
+            GPC_CUDA(q);
+            if (*flag != seq) { set_error("read_back: value never arrived"); return GPC_ERR_INTERNAL; }
+        }
+    }
+    __sync_synchronize();
+    unsigned off = 0;
+    for (int i = 0; i < n_items; ++i) {
+        memcpy(items[i].host, g_rb.host + off, items[i].bytes);
+        off += (items[i].bytes + 7u) & ~7u;
+    }
+    return GPC_OK;
+}
+
 }  // namespace gpc
 
 extern "C" const char* gpc_last_error_string(void) { return gpc::g_error; }
@@ -135,6 +198,20 @@ extern "C" uint64_t gpc_profile_report(char* buf, uint64_t capacity) {
         e.bytes += r.bytes;
     }
     for (auto& kv : gpc::g_extra_bytes) acc[kv.first].bytes += kv.second;
+    // debugging aid: GPC_PROF_TIMELINE=<file> gets "name start_ms duration_ms" per launch
+    if (const char* path = getenv("GPC_PROF_TIMELINE")) {
+        if (buf && capacity && !gpc::g_recs.empty()) {
+            if (FILE* fh = fopen(path, "w")) {
+                for (auto& r : gpc::g_recs) {
+                    float t0 = 0.f, d = 0.f;
+                    cudaEventElapsedTime(&t0, gpc::g_recs[0].a, r.a);
+                    cudaEventElapsedTime(&d, r.a, r.b);
+                    fprintf(fh, "%s %.6f %.6f\n", r.name, t0, d);
+                }
+                fclose(fh);
+            }
+        }
+    }
     if (buf && capacity) {       // a size query (buf == NULL) keeps the records
         for (auto& r : gpc::g_recs) {
             cudaEventDestroy(r.a);

@@ -498,8 +498,7 @@ extern "C" int gpc_unique_reads(const int32_t* start_node, const int32_t* start_
                                                     out_index);
     GPC_LAUNCH_CHECK();
     unsigned long long h = 0;
-    GPC_CUDA(cudaMemcpyAsync(&h, total.p, 8, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({total.p, &h, (unsigned)(8)});
     *out_count = h;
     return GPC_OK;
 }
@@ -531,8 +530,7 @@ extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* re
         touched, err);
     GPC_LAUNCH_CHECK();
     unsigned long long h[2] = {0, 0};
-    GPC_CUDA(cudaMemcpyAsync(h, ctr.p, 16, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({ctr.p, h, (unsigned)(16)});
     *n_events = h[0];
     // reads SoA (4 x int32 + 2 x int64 path_ptr + index) in, events out; the path
     // nodes and the graph records it gathers are counted in DESIGN.md per read
@@ -589,8 +587,7 @@ extern "C" int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64
         st2, st3, ticket, counts);
     GPC_LAUNCH_CHECK();
     unsigned long long h[2];
-    GPC_CUDA(cudaMemcpyAsync(h, counts, 16, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({counts, h, (unsigned)(16)});
     *n_frag = h[0];
     *n_direct = h[1];
     prof_add_bytes("events_to_runs", 8.0 * (double)(h[0] + h[1]));

@@ -137,8 +137,7 @@ inline int multi_scan(int k, const uint32_t* const* in, uint32_t* const* out, si
     GPC_PROF("multi_scan");
     multi_scan_kernel<<<tiles, SC_THREADS, 0, stream>>>(a, (unsigned)n, totals);
     GPC_LAUNCH_CHECK();
-    GPC_CUDA(cudaMemcpyAsync(totals_host, totals, 8 * k, cudaMemcpyDeviceToHost, stream));
-    GPC_CUDA(cudaStreamSynchronize(stream));
+    GPC_READ_BACK({totals, totals_host, (unsigned)(8 * k)});
     return GPC_OK;
 }
 

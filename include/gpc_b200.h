@@ -11,8 +11,9 @@
  * Conventions
  *   - all array arguments are DEVICE pointers unless the name ends in _host
  *     or the parameter is a scalar out-parameter (uint64_t* n_xxx): those are
- *     host pointers, written before the function returns (the function
- *     synchronises the stream when it has to report a count);
+ *     host pointers, written before the function returns (the function waits
+ *     for its own kernels when it has to report a count); output ARRAYS are
+ *     complete in stream order, like any other work enqueued on `stream`;
  *   - `stream` is a cudaStream_t passed as void*;
  *   - outputs are caller-allocated with the documented capacity; temporary
  *     scratch comes from the stream-ordered pool (cudaMallocAsync);

@@ -23,8 +23,8 @@ print("generated %r in %.1fs" % (g, time.time() - t), flush=True)
 dg = DeviceGraph(g, lm.as_arrays())
 ds, dc = DeviceReads(s), DeviceReads(c)
 torch.cuda.synchronize()
-for it in range(3):
-    _lib.profile_enable(it == 2)
+for it in range(7):
+    _lib.profile_enable(it == 6)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     st, qt, q, thr, cleaned, peaks = pipeline.callpeaks(dg, ds, dc, 36, 200, True, None, True)
@@ -40,3 +40,18 @@ tot = sum(v[1] for v in rep.values())
 print("kernel time total %.3f ms over %d launches" % (tot, sum(v[0] for v in rep.values())))
 for name, (calls, ms, nbytes) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
     print("  %-28s %4d calls %9.3f ms  %5.1f%%" % (name, calls, ms, 100 * ms / tot))
+
+# GPU idle time between consecutive launches (GPC_PROF_TIMELINE=<file> set before the run)
+import os
+path = os.environ.get("GPC_PROF_TIMELINE")
+if path and os.path.exists(path):
+    recs = [l.split() for l in open(path)]
+    recs = [(n, float(a), float(d)) for n, a, d in recs]
+    gaps = []
+    for (n0, a0, d0), (n1, a1, d1) in zip(recs, recs[1:]):
+        gaps.append((a1 - (a0 + d0), n0, n1))
+    span = recs[-1][1] + recs[-1][2]
+    print("timeline: span %.3f ms, kernels %.3f ms, idle %.3f ms" % (
+        span, sum(r[2] for r in recs), sum(g[0] for g in gaps)))
+    for gap, n0, n1 in sorted(gaps, reverse=True)[:40]:
+        print("  idle %7.1f us between %-22s and %s" % (gap * 1e3, n0, n1))
