@@ -574,6 +574,65 @@ __global__ void comp_ptr_kernel(const uint8_t* __restrict__ head, const uint32_t
     local_of_vertex[u] = i;                         // position in member order
 }
 
+// Successor lists of the component graph in member order (member i = i-th
+// entry of the sorted (component, vertex) keys): targets as member indices,
+// ascending (= the CSR order of the reference's sliced matrix).  Built by one
+// thread per vertex so that the sequential replay below touches two arrays per
+// vertex instead of chasing node records, edges and vertex maps.
+__device__ __forceinline__ uint32_t member_vertex(const unsigned long long* keys, uint32_t i) {
+    return (uint32_t)(keys[i] & 0xffffffffu);
+}
+
+__global__ void adj_count_kernel(gpc_graph_t g, VertexView vw, uint32_t V,
+                                 const unsigned long long* __restrict__ member_keys,
+                                 uint32_t* __restrict__ deg /* [V + 1] */) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > V) return;
+    uint32_t cnt = 0;
+    if (i < V) {
+        uint32_t u = member_vertex(member_keys, i);
+        if (vw.type_of[u] != PIECE_HEAD) {
+            uint32_t a = vw.node_of[u];
+            uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
+            for (uint32_t e = r0.y; e < r1.y; ++e) cnt += vw.in_vertex[g.succ[e]] >= 0;
+        }
+    }
+    deg[i] = cnt;
+}
+
+__global__ void adj_fill_kernel(gpc_graph_t g, VertexView vw, uint32_t V,
+                                const unsigned long long* __restrict__ member_keys,
+                                const uint32_t* __restrict__ local_of_vertex,
+                                const uint32_t* __restrict__ adj_ptr,
+                                const int32_t* __restrict__ weight,
+                                const uint8_t* __restrict__ is_entry,
+                                const uint8_t* __restrict__ is_exit, uint32_t* __restrict__ adj,
+                                int32_t* __restrict__ m_weight, uint8_t* __restrict__ m_flags,
+                                uint8_t* __restrict__ comp_backward) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    uint32_t u = member_vertex(member_keys, i);
+    m_weight[i] = weight[u];
+    m_flags[i] = (uint8_t)((is_entry[u] ? 1 : 0) | (is_exit[u] ? 2 : 0));
+    if (vw.type_of[u] == PIECE_HEAD) return;
+    uint32_t a = vw.node_of[u];
+    uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
+    uint32_t w = adj_ptr[i];
+    long long last = -1;
+    while (true) {                           // selection by increasing vertex id
+        long long best = -1;
+        for (uint32_t e = r0.y; e < r1.y; ++e) {
+            int32_t t = vw.in_vertex[g.succ[e]];
+            if (t >= 0 && (long long)t > last && (best < 0 || (long long)t < best)) best = t;
+        }
+        if (best < 0) break;
+        uint32_t m = local_of_vertex[best];
+        if (m <= i) comp_backward[(uint32_t)(member_keys[i] >> 32)] = 1;
+        adj[w++] = m;
+        last = best;
+    }
+}
+
 struct PathOut {
     uint32_t* path;        // [n_vertices] path of comp c at comp_ptr[c] (forward order, vertex ids)
     uint32_t* path_len;    // [n_comp]
@@ -581,47 +640,38 @@ struct PathOut {
 };
 
 // One thread per component: literal replay of PosDividedLineGraph.max_paths.
-__global__ void max_paths_kernel(gpc_graph_t g, VertexView vw, uint32_t n_comp,
-                                 const uint32_t* __restrict__ comp_ptr,
+// When every edge of the component points to a later member (the vertex order
+// is topological -- always the case for graphs with ascending edges) one sweep
+// of each relaxation is exact and the confirming sweep is skipped.
+__global__ void max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ comp_ptr,
                                  const unsigned long long* __restrict__ member_keys,
-                                 const uint32_t* __restrict__ local_of_vertex,
-                                 const int32_t* __restrict__ weight, const uint8_t* __restrict__ is_entry,
-                                 const uint8_t* __restrict__ is_exit, long long* __restrict__ dist,
-                                 long long* __restrict__ dsink, int32_t* __restrict__ pred,
-                                 PathOut out) {
+                                 const uint32_t* __restrict__ adj_ptr,
+                                 const uint32_t* __restrict__ adj,
+                                 const int32_t* __restrict__ m_weight,
+                                 const uint8_t* __restrict__ m_flags,
+                                 const uint8_t* __restrict__ comp_backward,
+                                 long long* __restrict__ dist, long long* __restrict__ dsink,
+                                 int32_t* __restrict__ pred, PathOut out) {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_comp) return;
     const uint32_t lo = comp_ptr[c], hi = comp_ptr[c + 1];
     const int nv = (int)(hi - lo);           // vertices without the sink
     const long long INF = (1ll << 60);
-    auto vertex_at = [&](int j) { return (uint32_t)(member_keys[lo + j] & 0xffffffffu); };
+    auto vertex_at = [&](int j) { return member_vertex(member_keys, lo + j); };
     if (nv == 1) {                           // graphs.py:342-345
         out.path[lo] = vertex_at(0);
         out.path_len[c] = 1;
         out.info[c] = 0;
         return;
     }
+    const bool one_sweep = comp_backward[(uint32_t)(member_keys[lo] >> 32)] == 0;
     // Edge iteration of local vertex j in ascending target order (CSR order of
     // the reference's sliced matrix): piece targets sorted by vertex id, sink last.
     auto for_edges = [&](int j, auto&& fn) {
-        uint32_t u = vertex_at(j);
-        int t = vw.type_of[u];
-        if (t != PIECE_HEAD) {
-            uint32_t a = vw.node_of[u];
-            uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
-            long long last = -1;
-            while (true) {                   // selection by increasing vertex id
-                long long best = -1;
-                for (uint32_t e = r0.y; e < r1.y; ++e) {
-                    int32_t w = vw.in_vertex[g.succ[e]];
-                    if (w >= 0 && (long long)w > last && (best < 0 || (long long)w < best)) best = w;
-                }
-                if (best < 0) break;
-                fn((int)(local_of_vertex[best] - lo));
-                last = best;
-            }
-        }
-        if (is_exit[u]) fn(nv);              // sink = local index nv
+        const uint32_t e0 = adj_ptr[lo + j], e1 = adj_ptr[lo + j + 1];
+        const bool to_sink = (m_flags[lo + j] & 2) != 0;
+        for (uint32_t e = e0; e < e1; ++e) fn((int)(adj[e] - lo));
+        if (to_sink) fn(nv);                 // sink = local index nv
     };
     // distance of every vertex to the sink (value only, order independent)
     for (int j = 0; j < nv; ++j) dsink[lo + j] = INF;
@@ -629,7 +679,7 @@ __global__ void max_paths_kernel(gpc_graph_t g, VertexView vw, uint32_t n_comp,
     while (changed) {
         changed = false;
         for (int j = nv - 1; j >= 0; --j) {
-            long long w = -(long long)weight[vertex_at(j)];
+            long long w = -(long long)m_weight[lo + j];
             long long best = dsink[lo + j];
             for_edges(j, [&](int tgt) {
                 long long d = tgt == nv ? 0 : dsink[lo + tgt];
@@ -637,11 +687,12 @@ __global__ void max_paths_kernel(gpc_graph_t g, VertexView vw, uint32_t n_comp,
             });
             if (best < dsink[lo + j]) { dsink[lo + j] = best; changed = true; }
         }
+        if (one_sweep) break;
     }
     // start = first entry vertex with minimal distance to the sink (np.argmin)
     int first = -1;
     for (int j = 0; j < nv; ++j)
-        if (is_entry[vertex_at(j)] && (first < 0 || dsink[lo + j] < dsink[lo + first])) first = j;
+        if ((m_flags[lo + j] & 1) && (first < 0 || dsink[lo + j] < dsink[lo + first])) first = j;
     if (first < 0) first = 0;
     // Bellman-Ford from `first`, scipy sweep order, first strict improvement wins
     long long dist_sink = INF;
@@ -653,7 +704,7 @@ __global__ void max_paths_kernel(gpc_graph_t g, VertexView vw, uint32_t n_comp,
         for (int j = 0; j < nv; ++j) {
             long long d1 = dist[lo + j];
             if (d1 >= INF) continue;
-            long long w = -(long long)weight[vertex_at(j)];
+            long long w = -(long long)m_weight[lo + j];
             for_edges(j, [&](int tgt) {
                 if (tgt == nv) {
                     if (d1 + w < dist_sink) { dist_sink = d1 + w; pred_sink = j; any = true; }
@@ -664,7 +715,7 @@ __global__ void max_paths_kernel(gpc_graph_t g, VertexView vw, uint32_t n_comp,
                 }
             });
         }
-        if (!any) break;
+        if (!any || one_sweep) break;
     }
     // _backtrace (graphs.py:273-283): stops at local vertex 0 as well
     int len = 0;
@@ -679,7 +730,7 @@ __global__ void max_paths_kernel(gpc_graph_t g, VertexView vw, uint32_t n_comp,
     long long wsum = 0;
     for (int j = 0; j < nv; ++j) {
         if (dsink[lo + j] < score) score = dsink[lo + j];
-        wsum += (long long)weight[vertex_at(j)];
+        wsum += (long long)m_weight[lo + j];
     }
     int info = 0;
     if (len > 1) {
@@ -688,7 +739,7 @@ __global__ void max_paths_kernel(gpc_graph_t g, VertexView vw, uint32_t n_comp,
         for (int q = len - 1; q >= 1 && !amb; --q) {      // path[:-1] in forward order
             int node = (int)out.path[lo + q];
             long long reach = dist[lo + node];
-            long long w = -(long long)weight[vertex_at(node)];
+            long long w = -(long long)m_weight[lo + node];
             for_edges(node, [&](int tgt) {
                 if (amb) return;
                 if (tgt != nv) {
@@ -1106,6 +1157,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     GPC_LAUNCH_CHECK();
     Scratch parent, is_entry, is_exit, keys0, keys1, head, hoffs, comp_ptr, local_of, comp_of;
     Scratch dist, dsink, pred, path, path_len, info;
+    Scratch adj_deg, adj_ptr, adj, m_weight, m_flags, comp_backward;
     unsigned long long n_comp = 0;
     if (V) {
         GPC_CUDA(v_node.alloc((size_t)V * 4, stream));
@@ -1162,11 +1214,32 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
         GPC_CUDA(path_len.alloc((size_t)n_comp * 4, stream));
         GPC_CUDA(info.alloc((size_t)n_comp, stream));
         PathOut po{path.as<uint32_t>(), path_len.as<uint32_t>(), info.as<uint8_t>()};
+        // successor lists in member order (at most one list entry per graph edge)
+        GPC_CUDA(adj_deg.alloc((size_t)(V + 1) * 4, stream));
+        GPC_CUDA(adj_ptr.alloc((size_t)(V + 1) * 4, stream));
+        GPC_CUDA(adj.alloc((size_t)graph->n_edges * 4 + 16, stream));
+        GPC_CUDA(m_weight.alloc((size_t)V * 4, stream));
+        GPC_CUDA(m_flags.alloc(V, stream));
+        GPC_CUDA(comp_backward.alloc(V, stream));         // indexed by component label (< V)
+        GPC_CUDA(cudaMemsetAsync(comp_backward.p, 0, V, stream));
+        GPC_PROF("adj_count");
+        adj_count_kernel<<<GRID(V + 1)>>>(*graph, vw, V, mk, adj_deg.as<uint32_t>());
+        GPC_LAUNCH_CHECK();
+        GPC_TRY(exclusive_scan<uint32_t>(adj_deg.as<uint32_t>(), adj_ptr.as<uint32_t>(), (size_t)V + 1,
+                                         nullptr, stream));
+        GPC_PROF("adj_fill");
+        adj_fill_kernel<<<GRID(V)>>>(*graph, vw, V, mk, local_of.as<uint32_t>(),
+                                     adj_ptr.as<uint32_t>(), weight.as<int32_t>(),
+                                     is_entry.as<uint8_t>(), is_exit.as<uint8_t>(),
+                                     adj.as<uint32_t>(), m_weight.as<int32_t>(),
+                                     m_flags.as<uint8_t>(), comp_backward.as<uint8_t>());
+        GPC_LAUNCH_CHECK();
         GPC_PROF("max_paths");
-        max_paths_kernel<<<div_up(n_comp, 64), 64, 0, stream>>>(
-            *graph, vw, (uint32_t)n_comp, comp_ptr.as<uint32_t>(), mk, local_of.as<uint32_t>(),
-            weight.as<int32_t>(), is_entry.as<uint8_t>(), is_exit.as<uint8_t>(),
-            dist.as<long long>(), dsink.as<long long>(), pred.as<int32_t>(), po);
+        max_paths_kernel<<<div_up(n_comp, 32), 32, 0, stream>>>(
+            (uint32_t)n_comp, comp_ptr.as<uint32_t>(), mk, adj_ptr.as<uint32_t>(),
+            adj.as<uint32_t>(), m_weight.as<int32_t>(), m_flags.as<uint8_t>(),
+            comp_backward.as<uint8_t>(), dist.as<long long>(), dsink.as<long long>(),
+            pred.as<int32_t>(), po);
         GPC_LAUNCH_CHECK();
     }
     const uint32_t n_pk = (uint32_t)n_comp + (uint32_t)n_i;

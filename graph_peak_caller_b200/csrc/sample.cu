@@ -421,13 +421,14 @@ constexpr unsigned long long DEDUP_EMPTY = ~0ull;
 __global__ void dedup_insert_kernel(const int32_t* __restrict__ start_node,
                                     const int32_t* __restrict__ start_off, unsigned n,
                                     unsigned long long* __restrict__ table_keys,
-                                    unsigned* __restrict__ table_first, unsigned mask,
+                                    unsigned* __restrict__ table_first, unsigned cap,
                                     unsigned* __restrict__ slot_of) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned long long key = ((unsigned long long)(uint32_t)start_node[i] << 32) |
                              (uint32_t)start_off[i];
-    unsigned h = (unsigned)mix64(key) & mask;
+    // any capacity (not only powers of two): multiply-shift range reduction
+    unsigned h = __umulhi((unsigned)(mix64(key) >> 32), cap);
     while (true) {
         unsigned long long cur = table_keys[h];
         if (cur == DEDUP_EMPTY) {
@@ -439,7 +440,7 @@ __global__ void dedup_insert_kernel(const int32_t* __restrict__ start_node,
             slot_of[i] = h;
             return;
         }
-        h = (h + 1) & mask;
+        if (++h == cap) h = 0;
     }
 }
 
@@ -469,8 +470,9 @@ extern "C" int gpc_unique_reads(const int32_t* start_node, const int32_t* start_
     if (n_reads == 0) return GPC_OK;
     if (n_reads >= (1ull << 31)) { set_error("too many reads"); return GPC_ERR_ARG; }
     unsigned n = (unsigned)n_reads;
-    unsigned cap = 1024;
-    while (cap < 2ull * n) cap <<= 1;
+    // load factor 2/3: 12 bytes per slot, so the table of a 5 M read batch (90 MB)
+    // stays inside the 126 MB L2 instead of turning every probe into a DRAM access
+    unsigned cap = (unsigned)max(1024ull, (3ull * n + 1) / 2);
     Scratch keys, first, slot, keep, offs, total;
     GPC_CUDA(keys.alloc((size_t)cap * 8, stream));
     GPC_CUDA(first.alloc((size_t)cap * 4, stream));
@@ -484,7 +486,7 @@ extern "C" int gpc_unique_reads(const int32_t* start_node, const int32_t* start_
     GPC_PROF_BYTES("dedup_insert", 12.0 * n);
     dedup_insert_kernel<<<blocks, 256, 0, stream>>>(start_node, start_off, n,
                                                    keys.as<unsigned long long>(),
-                                                   first.as<unsigned>(), cap - 1,
+                                                   first.as<unsigned>(), cap,
                                                    slot.as<unsigned>());
     GPC_LAUNCH_CHECK();
     GPC_PROF("dedup_flag");
