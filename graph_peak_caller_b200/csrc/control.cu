@@ -190,11 +190,19 @@ __global__ void pick_tiles_kernel(const unsigned long long* __restrict__ rank, u
 
 constexpr int NC = 4;            // count per window (3) + "window-0 starts seen"
 
+// exact double of a non-negative int below 2^31 with one DADD: I2F.F64 runs at a
+// fraction of the FP64 rate and was 22 % of the dense kernel's stall samples
+__device__ __forceinline__ double count_to_f64(int c) {
+    return __hiloint2double(0x43300000, c) - 4503599627370496.0;
+}
+
 __device__ __forceinline__ double lambda_of(const int c[NC], const WindowParams& wp) {
     double best = 0.0;
     bool clipped = c[3] > 0;
-    for (int w = clipped ? 0 : 1; w < wp.n_windows; ++w)
-        best = fmax(best, __dmul_rn((double)c[w], wp.weight[w]));
+#pragma unroll
+    for (int w = 0; w < MAX_WINDOWS; ++w)      // static indices: wp stays in the constant bank
+        if (w < wp.n_windows && (w > 0 || clipped))
+            best = fmax(best, __dmul_rn(count_to_f64(c[w]), wp.weight[w]));
     if (clipped) best = fmax(best, wp.min_value);
     return best;
 }
@@ -234,11 +242,23 @@ linear_dense_kernel(const double* __restrict__ xu, const uint32_t* __restrict__ 
     }
     for (int i = threadIdx.x; i < NC * DENSE_W; i += DENSE_THREADS) (&s_diff[0][0])[i] = 0;
     __syncthreads();
-    // scatter the events
-    for (int q = 0; q < nq; ++q) {
-        const int w = q >> 1;
-        const double h = wp.half[w];
-        for (unsigned i = s_lo[q] + threadIdx.x; i < s_hi[q]; i += DENSE_THREADS) {
+    // scatter the events: the slices of all views as one index space, so that the
+    // loads of different views are in flight together
+    {
+        unsigned pre[MERGE_MAXQ + 1];
+        pre[0] = 0;
+#pragma unroll
+        for (int q = 0; q < MERGE_MAXQ; ++q)
+            pre[q + 1] = pre[q] + (q < nq ? s_hi[q] - s_lo[q] : 0u);
+        for (unsigned f = threadIdx.x; f < pre[MERGE_MAXQ]; f += DENSE_THREADS) {
+            int q = 0;
+            unsigned first = 0;                // pre[q], without indexing the array
+#pragma unroll
+            for (int qq = 1; qq < MERGE_MAXQ; ++qq)
+                if (f >= pre[qq]) { q = qq; first = pre[qq]; }
+            const unsigned i = s_lo[q] + (f - first);
+            const int w = q >> 1;
+            const double h = w == 0 ? wp.half[0] : (w == 1 ? wp.half[1] : wp.half[2]);
             double t = (q & 1) ? xu[i] + h : xu[i] - h;            // exact: integers
             int p = (int)((long long)t - a);
             int mul = (int)(wpre[i + 1] - wpre[i]);
@@ -273,7 +293,8 @@ linear_dense_kernel(const double* __restrict__ xu, const uint32_t* __restrict__ 
         }
     }
     double was = lambda_of(run, wp);
-    double e_pos[DENSE_PER], e_val[DENSE_PER];
+    double e_val[DENSE_PER];
+    unsigned emit = 0;                         // bit j: position p0 + j is a breakpoint
     int cnt = 0;
 #pragma unroll
     for (int j = 0; j < DENSE_PER; ++j) {
@@ -284,11 +305,12 @@ linear_dense_kernel(const double* __restrict__ xu, const uint32_t* __restrict__ 
             run[k] += d;
             any |= d != 0;
         }
+        e_val[j] = 0.0;
         if (any) {
             double now = lambda_of(run, wp);
             if (now != was) {
-                e_pos[cnt] = (double)(a + p0 + j);
-                e_val[cnt] = now;
+                e_val[j] = now;
+                emit |= 1u << j;
                 ++cnt;
             }
             was = now;
@@ -308,7 +330,13 @@ linear_dense_kernel(const double* __restrict__ xu, const uint32_t* __restrict__ 
     }
     __syncthreads();
     unsigned long long wbase = s_obase + o;
-    for (int j = 0; j < cnt; ++j) { tmp_pos[wbase + j] = e_pos[j]; tmp_val[wbase + j] = e_val[j]; }
+#pragma unroll
+    for (int j = 0; j < DENSE_PER; ++j)
+        if ((emit >> j) & 1u) {
+            tmp_pos[wbase] = (double)(a + p0 + j);
+            tmp_val[wbase] = e_val[j];
+            ++wbase;
+        }
 }
 
 // one warp per tile: move the tile's chunk to its place in tile order
