@@ -148,6 +148,20 @@ def cpu_sample_text(n_chrom):
                 round(WORKLOAD["backbone_bp"] / CPU_SAMPLE["backbone_bp"])))
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` (dram__bytes_read.sum + dram__bytes_write.sum,
+    averaged over its launches in one pass) from the committed ncu capture of this
+    same command; None when the capture has no entry for it."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            table = json.load(fh)
+        e = table["kernels"][kernel]
+        return e["dram_bytes_per_launch"], table.get("source")
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -215,8 +229,6 @@ def main_ours(args):
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _lib.launch_count()
-    _lib.profile_enable(True)
-    _lib.profile_report()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -224,10 +236,22 @@ def main_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    _lib.profile_enable(False)
-    prof = _lib.profile_report()
     launches = (_lib.launch_count() - launches0) // max(args.steps, 1)
     clocks = sampler.stop() if sampler else None
+    # ---- the same K steps again with a CUDA-event pair around every launch (on the
+    # launching stream): per-kernel durations for the roofline.  Kept out of the
+    # region above because 2 x 140 event records per step cost ~0.5 ms of host time.
+    _lib.profile_enable(True)
+    _lib.profile_report()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        step()
+    p1.record()
+    barrier()
+    instrumented_ms = p0.elapsed_time(p1) / args.steps
+    _lib.profile_enable(False)
+    prof = _lib.profile_report()
     t = torch.tensor([ms, float(n_reads)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
@@ -299,8 +323,13 @@ def main_ours(args):
     top, (calls, tms, nbytes) = kt[0]
     achieved = nbytes / (tms / 1e3) / 1e9 if tms > 0 else 0.0
     kernel_ms = sum(v[1] for v in prof.values()) / args.steps
+    traffic, traffic_src = ncu_traffic(top)
     roofline = dict(bound="hbm", kernel=top, achieved=achieved, peak=peak_gbs, unit="GB/s",
-                    frac=achieved / peak_gbs, traffic=None, peak_source=peak_kind,
+                    frac=achieved / peak_gbs, traffic=traffic, traffic_source=traffic_src,
+                    algorithmic_bytes_per_launch=nbytes / max(calls, 1),
+                    peak_source=peak_kind,
+                    timing="CUDA-event pair around every launch, second pass over the same "
+                           "%d steps (%.3f ms/step with the events)" % (args.steps, instrumented_ms),
                     launches_per_step=calls // args.steps,
                     avg_launch_ms=tms / max(calls, 1),
                     share_of_kernel_time=tms / max(sum(v[1] for v in prof.values()), 1e-9),

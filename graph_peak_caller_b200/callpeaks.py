@@ -47,7 +47,12 @@ class CallPeaks(object):
 
     def run_pre_callpeaks(self, input_reads, control_reads):
         if hasattr(control_reads, "prefetch") and control_reads is not input_reads:
-            control_reads.prefetch()          # overlaps the upload with the sample stage
+            # sample upload first (it is needed first and gets the whole link); the
+            # control copies queue behind it on the copy stream and overlap the
+            # sample stage instead of competing with the sample upload
+            if hasattr(input_reads, "_device_reads"):
+                input_reads._device_reads()
+            control_reads.prefetch()
         sample_pileup = get_fragment_pileup(self.graph, input_reads, self.config,
                                             self._reporter)
         self.direct_pileup = sample_pileup.direct_pileup

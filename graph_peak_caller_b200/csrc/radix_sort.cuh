@@ -333,9 +333,11 @@ int radix_sort(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, s
                int begin_bit, int end_bit, bool skip_trivial, bool* result_in_tmp,
                cudaStream_t stream) {
     const int range = end_bit - begin_bit;
-    if (sizeof(KeyT) == 4 && !HAS_VALUE && (range + 8) / 9 < (range + 7) / 8)
-        return radix_sort_bits<KeyT, HAS_VALUE, 9>(keys, keys_tmp, vals, vals_tmp, n, begin_bit,
-                                                   end_bit, skip_trivial, result_in_tmp, stream);
+    if constexpr (sizeof(KeyT) == 4 && !HAS_VALUE) {
+        if ((range + 8) / 9 < (range + 7) / 8)
+            return radix_sort_bits<KeyT, HAS_VALUE, 9>(keys, keys_tmp, vals, vals_tmp, n, begin_bit,
+                                                       end_bit, skip_trivial, result_in_tmp, stream);
+    }
     return radix_sort_bits<KeyT, HAS_VALUE, 8>(keys, keys_tmp, vals, vals_tmp, n, begin_bit, end_bit,
                                                skip_trivial, result_in_tmp, stream);
 }

@@ -40,20 +40,35 @@ void prof_add_bytes(const char* name, double bytes) {
     g_extra_bytes[name] += bytes;
 }
 
+// events are recycled: cudaEventCreate costs more than the record itself
+static std::vector<cudaEvent_t> g_free_events;
+static cudaEvent_t take_event() {
+    {
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
+        if (!g_free_events.empty()) {
+            cudaEvent_t e = g_free_events.back();
+            g_free_events.pop_back();
+            return e;
+        }
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
 void prof_begin(const char* name, cudaStream_t stream, double bytes) {
     if (!g_prof_on) return;
     g_pending = name;
     g_pending_bytes = bytes;
     g_pending_stream = stream;
-    cudaEventCreate(&g_pending_a);
+    g_pending_a = take_event();
     cudaEventRecord(g_pending_a, stream);
 }
 
 void prof_end() {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (!g_pending) return;
-    ProfRec r{g_pending, g_pending_a, nullptr, g_pending_bytes};
-    cudaEventCreate(&r.b);
+    ProfRec r{g_pending, g_pending_a, take_event(), g_pending_bytes};
     cudaEventRecord(r.b, g_pending_stream);
     {
         std::lock_guard<std::mutex> lock(g_prof_mutex);
@@ -214,8 +229,8 @@ extern "C" uint64_t gpc_profile_report(char* buf, uint64_t capacity) {
     }
     if (buf && capacity) {       // a size query (buf == NULL) keeps the records
         for (auto& r : gpc::g_recs) {
-            cudaEventDestroy(r.a);
-            cudaEventDestroy(r.b);
+            gpc::g_free_events.push_back(r.a);
+            gpc::g_free_events.push_back(r.b);
         }
         gpc::g_recs.clear();
         gpc::g_extra_bytes.clear();

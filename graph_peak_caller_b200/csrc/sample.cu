@@ -458,6 +458,24 @@ __global__ void compact_index_kernel(const uint8_t* __restrict__ keep,
     if (i < n && keep[i]) out[offs[i]] = i;
 }
 
+// Reads arrive in arbitrary order; walking them in (coarse) graph order makes
+// neighbouring threads gather the same node records, so the walk is served by
+// L1/L2 instead of DRAM (814 MB of DRAM traffic per launch for 197 MB of
+// compulsory bytes were measured without it -- profiles/traffic.json, r01).
+__global__ void walk_order_keys_kernel(const int32_t* __restrict__ start_node,
+                                       const uint32_t* __restrict__ read_index, unsigned n,
+                                       int min_node, uint32_t n_nodes, int shift,
+                                       uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned r = read_index ? read_index[i] : i;
+    const int sn = start_node[r];
+    long long v = (long long)(sn < 0 ? -(long long)sn : (long long)sn) - min_node;
+    v = v < 0 ? 0 : (v >= (long long)n_nodes ? (long long)n_nodes - 1 : v);   // validated by the walk
+    keys[i] = (uint32_t)v >> shift;
+    vals[i] = r;
+}
+
 }  // namespace gpc
 
 using namespace gpc;
@@ -526,6 +544,27 @@ extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* re
     GPC_CUDA(cudaMemsetAsync(ctr.p, 0, 16, stream));
     unsigned long long* count = ctr.as<unsigned long long>();
     int* err = reinterpret_cast<int*>(count + 1);
+    // walk order: read indices sorted by start node / 2^shift (16-bit keys, two passes)
+    Scratch ok0, ok1, ov0, ov1;
+    if (n_reads >= (1u << 16) && n_reads < (1ull << 30) && !getenv("GPC_NO_WALK_ORDER")) {
+        int bits = 1;
+        while ((1ull << bits) < graph->n_nodes) ++bits;
+        const int shift = bits > 16 ? bits - 16 : 0;
+        GPC_CUDA(ok0.alloc(n_reads * 4, stream));
+        GPC_CUDA(ok1.alloc(n_reads * 4, stream));
+        GPC_CUDA(ov0.alloc(n_reads * 4, stream));
+        GPC_CUDA(ov1.alloc(n_reads * 4, stream));
+        GPC_PROF("walk_order_keys");
+        walk_order_keys_kernel<<<div_up(n_reads, 256), 256, 0, stream>>>(
+            reads->start_node, read_index, (unsigned)n_reads, graph->min_node, graph->n_nodes,
+            shift, ok0.as<uint32_t>(), ov0.as<uint32_t>());
+        GPC_LAUNCH_CHECK();
+        bool in_tmp = false;
+        GPC_TRY((radix_sort<uint32_t, true>(ok0.as<uint32_t>(), ok1.as<uint32_t>(),
+                                            ov0.as<uint32_t>(), ov1.as<uint32_t>(), n_reads, 0,
+                                            bits - shift, false, &in_tmp, stream)));
+        read_index = in_tmp ? ov1.as<uint32_t>() : ov0.as<uint32_t>();
+    }
     GPC_PROF("walk_reads");
     walk_reads_kernel<<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
         *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
