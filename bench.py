@@ -222,12 +222,15 @@ def main_ours(args):
                                                   R, F)
         return st, pipeline.PeakSet(raw, F)
 
+    # nvidia-smi needs ~0.1 s before its first sample, longer than a short timed
+    # region: it is started before the warm-up and runs through the timed and the
+    # instrumented steps (the same load throughout)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         st, peaks = step()
     n_reads = st.n_sample + st.n_control
     # ---- timed region: K steps, device time, max over ranks --------------------
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -237,7 +240,6 @@ def main_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = (_lib.launch_count() - launches0) // max(args.steps, 1)
-    clocks = sampler.stop() if sampler else None
     # ---- the same K steps again with a CUDA-event pair around every launch (on the
     # launching stream): per-kernel durations for the roofline.  Kept out of the
     # region above because 2 x 140 event records per step cost ~0.5 ms of host time.
@@ -252,6 +254,9 @@ def main_ours(args):
     instrumented_ms = p0.elapsed_time(p1) / args.steps
     _lib.profile_enable(False)
     prof = _lib.profile_report()
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed + instrumented steps"
     t = torch.tensor([ms, float(n_reads)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()

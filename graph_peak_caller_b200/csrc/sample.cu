@@ -80,7 +80,77 @@ __device__ __forceinline__ WalkNode load_walk_node(const gpc_graph_t& g, uint32_
     return w;
 }
 
-__global__ void __launch_bounds__(WALK_THREADS)
+// The extension frontier: pending (node key, bases still to cover) pairs, popped
+// in increasing key order (= the reference's sweep over ascending node ids),
+// one entry per node holding the largest remainder seen for it.  The first
+// four entries live in registers, kept sorted -- the usual frontier of a bubble
+// graph is 1-3 nodes, and the linear scans over a local-memory array were 45 %
+// of the kernel's instructions; more entries spill into a local array.
+struct FrontierSpill {                      // (a separate object: a struct holding a
+    uint32_t key[FRONTIER_CAP], rem[FRONTIER_CAP];   //  dynamically indexed array lives in local memory as a whole)
+};
+struct Frontier {
+    uint32_t k0, k1, k2, k3, r0, r1, r2, r3;
+    int n;                                  // entries in registers (sorted by key)
+    int xn;                                 // spilled entries (unsorted)
+    bool overflow;
+    uint32_t* xkey;
+    uint32_t* xrem;
+
+    __device__ __forceinline__ void init(FrontierSpill& sp) {
+        n = 0; xn = 0; overflow = false;
+        k0 = k1 = k2 = k3 = 0; r0 = r1 = r2 = r3 = 0;
+        xkey = sp.key; xrem = sp.rem;
+    }
+    __device__ __forceinline__ bool empty() const { return n == 0 && xn == 0; }
+
+    __device__ __forceinline__ void push(uint32_t key, uint32_t rem) {
+        if (n > 0 && k0 == key) { r0 = max(r0, rem); return; }
+        if (n > 1 && k1 == key) { r1 = max(r1, rem); return; }
+        if (n > 2 && k2 == key) { r2 = max(r2, rem); return; }
+        if (n > 3 && k3 == key) { r3 = max(r3, rem); return; }
+        if (xn > 0) {
+            for (int f = 0; f < xn; ++f)
+                if (xkey[f] == key) { xrem[f] = max(xrem[f], rem); return; }
+        }
+        if (n < 4) {
+            if (n == 0) { k0 = key; r0 = rem; }
+            else if (n == 1) { k1 = key; r1 = rem; }
+            else if (n == 2) { k2 = key; r2 = rem; }
+            else { k3 = key; r3 = rem; }
+            ++n;
+            uint32_t t;
+            if (n > 3 && k3 < k2) { t = k2; k2 = k3; k3 = t; t = r2; r2 = r3; r3 = t; }
+            if (n > 2 && k2 < k1) { t = k1; k1 = k2; k2 = t; t = r1; r1 = r2; r2 = t; }
+            if (n > 1 && k1 < k0) { t = k0; k0 = k1; k1 = t; t = r0; r0 = r1; r1 = t; }
+        } else if (xn < FRONTIER_CAP) {
+            xkey[xn] = key; xrem[xn] = rem; ++xn;
+        } else {
+            overflow = true;
+        }
+    }
+
+    // smallest key (must not be empty)
+    __device__ __forceinline__ void pop(uint32_t& key, uint32_t& rem) {
+        int best = -1;
+        if (xn > 0) {
+            best = 0;
+            for (int f = 1; f < xn; ++f) if (xkey[f] < xkey[best]) best = f;
+            if (n > 0 && k0 < xkey[best]) best = -1;
+        }
+        if (best < 0) {
+            key = k0; rem = r0;
+            k0 = k1; r0 = r1; k1 = k2; r1 = r2; k2 = k3; r2 = r3;
+            --n;
+        } else {
+            key = xkey[best]; rem = xrem[best];
+            --xn;
+            xkey[best] = xkey[xn]; xrem[best] = xrem[xn];
+        }
+    }
+};
+
+__global__ void __launch_bounds__(WALK_THREADS, 10)
 walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restrict__ read_index,
                   unsigned n_reads, int extension, uint32_t* __restrict__ events,
                   unsigned long long event_cap, unsigned long long* __restrict__ event_count,
@@ -141,41 +211,29 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
             uint32_t total = (uint32_t)eo + (uint32_t)extension;
             ce = last_start + min(total, last_len);
             // ---- extension frontier ----------------------------------------
-            uint32_t fkey[FRONTIER_CAP];
-            uint32_t frem[FRONTIER_CAP];
-            int fc = 0;
-            bool overflow = false;
+            FrontierSpill spill;
+            Frontier fr;
+            fr.init(spill);
             uint32_t cur_v = last_v;
             uint32_t carry = total > last_len ? total - last_len : 0;
             while (true) {
                 if (carry) {
                     // neighbours of cur_v: inline in its walk record, CSR beyond two
-                    uint32_t lo = 0, hi = cur.n_adj;
-                    const uint32_t* adj = nullptr;
                     if (cur.n_adj > 2) {
                         uint4 a = node_record(graph, cur_v);
-                        adj = (fwd ? graph.succ + a.y : graph.pred + a.z);
-                    }
-                    for (uint32_t e = lo; e < hi; ++e) {
-                        uint32_t wv = adj ? adj[e] : (e == 0 ? cur.adj0 : cur.adj1);
-                        uint32_t key = fwd ? wv : ~wv;
-                        int f = 0;
-                        for (; f < fc; ++f) if (fkey[f] == key) break;
-                        if (f < fc) {
-                            frem[f] = max(frem[f], carry);
-                        } else if (fc < FRONTIER_CAP) {
-                            fkey[fc] = key; frem[fc] = carry; ++fc;
-                        } else {
-                            overflow = true;
+                        const uint32_t* adj = (fwd ? graph.succ + a.y : graph.pred + a.z);
+                        for (uint32_t e = 0; e < cur.n_adj; ++e) {
+                            uint32_t wv = adj[e];
+                            fr.push(fwd ? wv : ~wv, carry);
                         }
+                    } else {
+                        if (cur.n_adj > 0) fr.push(fwd ? cur.adj0 : ~cur.adj0, carry);
+                        if (cur.n_adj > 1) fr.push(fwd ? cur.adj1 : ~cur.adj1, carry);
                     }
                 }
-                if (fc == 0) break;
-                int best = 0;
-                for (int f = 1; f < fc; ++f) if (fkey[f] < fkey[best]) best = f;
-                uint32_t key = fkey[best], rem = frem[best];
-                --fc;
-                fkey[best] = fkey[fc]; frem[best] = frem[fc];
+                if (fr.empty()) break;
+                uint32_t key, rem;
+                fr.pop(key, rem);
                 cur_v = fwd ? key : ~key;
                 cur = load_walk_node(graph, cur_v, fwd);
                 uint32_t len = cur.len;
@@ -188,6 +246,7 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
                 ce = ns + min(rem, len);
                 carry = rem > len ? rem - len : 0;
             }
+            const bool overflow = fr.overflow;
             em.emit(ce, true, TAG_FRAG);
             if (overflow) atomicExch(err, GPC_ERR_FRONTIER_OVERFLOW);
         }
