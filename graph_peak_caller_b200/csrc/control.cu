@@ -70,29 +70,25 @@ __global__ void project_keys_kernel(gpc_graph_t graph, const int32_t* __restrict
 }
 
 // distinct x and the index of their first occurrence (== weight prefix)
-__global__ void unique_flag_kernel(const unsigned long long* __restrict__ keys, unsigned n,
-                                   uint8_t* __restrict__ head) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) head[i] = (i == 0) || keys[i] != keys[i - 1];
-}
-__global__ void unique_emit_kernel(const unsigned long long* __restrict__ keys, unsigned n,
-                                   const uint8_t* __restrict__ head,
-                                   const uint32_t* __restrict__ offs, unsigned n_unique,
-                                   double* __restrict__ xu, uint32_t* __restrict__ wpre) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) wpre[n_unique] = n;
-    if (i < n && head[i]) {
-        xu[offs[i]] = key_to_f64(keys[i]);
-        wpre[offs[i]] = i;
+// distinct projected starts with their multiplicities (as prefix counts), plus
+// the check that every start is a non-negative integer below 2^30
+struct UniqueStartsOp {
+    const unsigned long long* keys;
+    unsigned n;
+    double* xu;             // [n]  distinct starts, ascending
+    uint32_t* wpre;         // [n + 1]  index of the first copy of each; wpre[count] = n
+    int* not_integer;
+    __device__ __forceinline__ bool keep(unsigned i) const {
+        double x = key_to_f64(keys[i]);
+        if (!(x == floor(x)) || !(x >= 0.0) || !(x < 1073741824.0)) *not_integer = 1;
+        return i == 0 || keys[i] != keys[i - 1];
     }
-}
-__global__ void integer_check_kernel(const unsigned long long* __restrict__ keys, unsigned n,
-                                     int* __restrict__ not_integer) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double x = key_to_f64(keys[i]);
-    if (!(x == floor(x)) || !(x >= 0.0) || !(x < 1073741824.0)) *not_integer = 1;
-}
+    __device__ __forceinline__ void emit(unsigned i, unsigned long long w) const {
+        xu[w] = key_to_f64(keys[i]);
+        wpre[w] = i;
+    }
+    __device__ __forceinline__ void finish(unsigned long long count) const { wpre[count] = n; }
+};
 
 // ---- dense path: every projected start is a non-negative integer -----------------
 // The linear axis is cut into tiles of DENSE_W positions.  The events of a tile
@@ -648,7 +644,7 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
     }
     const unsigned n = (unsigned)n_reads;
     const unsigned nq = 2 * n_extensions;
-    Scratch k0, k1, small, head, offs, total, xu, wpre;
+    Scratch k0, k1, small, total, xu, wpre;
     GPC_CUDA(k0.alloc((size_t)n * 8, stream));
     GPC_CUDA(k1.alloc((size_t)n * 8, stream));
     GPC_CUDA(small.alloc(64, stream));
@@ -663,19 +659,13 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
                                                    k1.as<unsigned long long>(), nullptr, nullptr, n,
                                                    0, 64, true, &in_tmp, stream)));
     const unsigned long long* keys = in_tmp ? k1.as<unsigned long long>() : k0.as<unsigned long long>();
-    // distinct starts + multiplicity prefix
-    GPC_CUDA(head.alloc(n, stream));
-    GPC_CUDA(offs.alloc((size_t)n * 4, stream));
     GPC_CUDA(total.alloc(8, stream));
-    GPC_PROF("unique_flag");
-    unique_flag_kernel<<<div_up(n, 256), 256, 0, stream>>>(keys, n, head.as<uint8_t>());
-    GPC_LAUNCH_CHECK();
-    GPC_TRY(exclusive_scan<uint8_t>(head.as<uint8_t>(), offs.as<uint32_t>(), n,
-                                    total.as<unsigned long long>(), stream));
-    // largest start = last sorted key; integrality of the starts
-    GPC_PROF("integer_check");
-    integer_check_kernel<<<div_up(n, 256), 256, 0, stream>>>(keys, n, err + 1);
-    GPC_LAUNCH_CHECK();
+    // distinct starts; largest start = last sorted key; integrality of the starts
+    GPC_CUDA(xu.alloc((size_t)n * 8, stream));
+    GPC_CUDA(wpre.alloc((size_t)(n + 1) * 4, stream));
+    GPC_TRY(select_if("unique_starts",
+                      UniqueStartsOp{keys, n, xu.as<double>(), wpre.as<uint32_t>(), err + 1}, n,
+                      total.as<unsigned long long>(), stream));
     unsigned long long hU = 0, last_key = 0;
     int herr = 0, not_integer = 0;
     GPC_READ_BACK({total.p, &hU, (unsigned)(8)}, {err, &herr, (unsigned)(4)}, {err + 1, &not_integer, (unsigned)(4)}, {keys + (n - 1), &last_key, (unsigned)(8)});
@@ -685,13 +675,6 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
         return herr;
     }
     const unsigned U = (unsigned)hU;
-    GPC_CUDA(xu.alloc((size_t)U * 8, stream));
-    GPC_CUDA(wpre.alloc((size_t)(U + 1) * 4, stream));
-    GPC_PROF("unique_emit");
-    unique_emit_kernel<<<div_up(n, 256), 256, 0, stream>>>(keys, n, head.as<uint8_t>(),
-                                                           offs.as<uint32_t>(), U, xu.as<double>(),
-                                                           wpre.as<uint32_t>());
-    GPC_LAUNCH_CHECK();
     // integer coordinates (no node with a non-integer scale was hit): dense path
     if (!not_integer && !getenv("GPC_FORCE_MERGE_PATH")) {
         long long e_max = 0;

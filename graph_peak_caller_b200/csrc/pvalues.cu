@@ -336,46 +336,82 @@ __device__ __forceinline__ unsigned long long hash64(unsigned long long x) {
     return x;
 }
 
-__global__ void ptable_insert_kernel(const uint32_t* __restrict__ pos, const double* __restrict__ p,
-                                     unsigned n, uint32_t track_size,
-                                     unsigned long long* __restrict__ tkeys,
-                                     unsigned long long* __restrict__ tcount, unsigned mask,
-                                     int* __restrict__ fail) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long key = 0, len = 0;
-    if (i < n) {
-        double v = p[i];
-        if (v != 0.0) {
-            key = (unsigned long long)__double_as_longlong(v);
-            uint32_t next = (i + 1 < n) ? pos[i + 1] : track_size;
-            len = next - pos[i];
-        }
-    }
-    // combine equal keys inside the warp before touching the table
-    unsigned peers = __match_any_sync(FULL, key);
-    unsigned long long sum = 0;
-#pragma unroll
-    for (int src = 0; src < 32; ++src) {
-        unsigned long long l = __shfl_sync(FULL, len, src);
-        if ((peers >> src) & 1u) sum += l;
-    }
-    bool leader = (__ffs(peers) - 1) == (int)lane_id();
-    if (key == 0 || !leader || sum == 0) return;
-    unsigned h = (unsigned)hash64(key) & mask;
-    for (unsigned probe = 0; probe <= mask; ++probe) {
-        unsigned long long cur = tkeys[h];
+// Adds `len` base pairs to key in the global table (linear probing).
+__device__ __forceinline__ void ptable_global_add(unsigned long long key, unsigned long long len,
+                                                  unsigned long long h,
+                                                  unsigned long long* __restrict__ tkeys,
+                                                  unsigned long long* __restrict__ tcount,
+                                                  unsigned mask, int* __restrict__ fail) {
+    unsigned s = (unsigned)(h >> 16) & mask;
+    for (unsigned probe = 0; probe < 256; ++probe) {
+        unsigned long long cur = tkeys[s];
         if (cur == 0) {
-            unsigned long long old = atomicCAS(&tkeys[h], 0ull, key);
+            unsigned long long old = atomicCAS(&tkeys[s], 0ull, key);
             cur = old == 0 ? key : old;
         }
         if (cur == key) {
-            atomicAdd(&tcount[h], sum);
+            atomicAdd(&tcount[s], len);
             return;
         }
-        h = (h + 1) & mask;
-        if (probe > 4096) break;
+        s = (s + 1) & mask;
     }
-    atomicExch(fail, 1);
+    atomicExch(fail, 1);      // table too full: the host grows it and starts over
+}
+
+// Neighbouring runs never share a p (the track is canonical) but a stretch of
+// a few thousand runs holds few distinct values: each block first aggregates
+// its PT_TILE runs in a shared-memory table and then adds one entry per
+// distinct value to the global table.  (The first version combined equal keys
+// inside a warp with match_any + 32 shuffles per run and was MIO bound.)
+constexpr int PT_THREADS = 256;
+constexpr int PT_ITEMS = 8;
+constexpr int PT_TILE = PT_THREADS * PT_ITEMS;
+constexpr int PT_SLOTS = 2048;
+
+__global__ void __launch_bounds__(PT_THREADS)
+ptable_insert_kernel(const uint32_t* __restrict__ pos, const double* __restrict__ p, unsigned n,
+                     uint32_t track_size, unsigned long long* __restrict__ tkeys,
+                     unsigned long long* __restrict__ tcount, unsigned mask,
+                     int* __restrict__ fail) {
+    __shared__ unsigned long long s_key[PT_SLOTS];
+    __shared__ unsigned s_cnt[PT_SLOTS];     // a tile's lengths sum to less than the track size (< 2^32): native 32-bit atomics
+    __shared__ int s_failed;
+    for (int i = threadIdx.x; i < PT_SLOTS; i += PT_THREADS) { s_key[i] = 0; s_cnt[i] = 0; }
+    if (threadIdx.x == 0) s_failed = *reinterpret_cast<volatile int*>(fail);
+    __syncthreads();
+    if (s_failed) return;                    // an earlier block gave up already (uniform exit)
+    const unsigned base = blockIdx.x * PT_TILE;
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        unsigned i = base + j * PT_THREADS + threadIdx.x;
+        if (i >= n) break;
+        double v = p[i];
+        if (v == 0.0) continue;
+        unsigned long long key = (unsigned long long)__double_as_longlong(v);
+        uint32_t next = (i + 1 < n) ? pos[i + 1] : track_size;
+        unsigned len = next - pos[i];
+        unsigned long long h = hash64(key);
+        unsigned s = (unsigned)h & (PT_SLOTS - 1);
+        bool done = false;
+        for (int probe = 0; probe < 8 && !done; ++probe) {
+            unsigned long long cur = s_key[s];
+            if (cur == 0) {
+                unsigned long long old = atomicCAS(&s_key[s], 0ull, key);
+                cur = old == 0 ? key : old;
+            }
+            if (cur == key) {
+                atomicAdd(&s_cnt[s], len);
+                done = true;
+            }
+            s = (s + 1) & (PT_SLOTS - 1);
+        }
+        if (!done) ptable_global_add(key, len, h, tkeys, tcount, mask, fail);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PT_SLOTS; i += PT_THREADS) {
+        unsigned long long key = s_key[i];
+        if (key) ptable_global_add(key, s_cnt[i], hash64(key), tkeys, tcount, mask, fail);
+    }
 }
 
 __global__ void ptable_flag_kernel(const unsigned long long* __restrict__ tkeys, unsigned cap,
@@ -495,24 +531,21 @@ __global__ void qvalues_apply_kernel(const double* __restrict__ p, unsigned n,
 }
 
 // threshold: value >= cutoff, canonical boolean runs
-__global__ void threshold_flag_kernel(const double* __restrict__ q, unsigned n, double cutoff,
-                                      uint8_t* __restrict__ flag) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    bool cur = q[i] >= cutoff;
-    flag[i] = (i == 0) || (cur != (q[i - 1] >= cutoff));
-}
-
-__global__ void threshold_emit_kernel(const uint32_t* __restrict__ pos, const double* __restrict__ q,
-                                      unsigned n, double cutoff, const uint8_t* __restrict__ flag,
-                                      const uint32_t* __restrict__ offs,
-                                      uint32_t* __restrict__ out_pos, uint8_t* __restrict__ out_val) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && flag[i]) {
-        out_pos[offs[i]] = pos[i];
-        out_val[offs[i]] = q[i] >= cutoff;
+struct ThresholdOp {
+    const uint32_t* pos;
+    const double* q;
+    double cutoff;
+    uint32_t* out_pos;
+    uint8_t* out_val;
+    __device__ __forceinline__ bool keep(unsigned i) const {
+        return i == 0 || ((q[i] >= cutoff) != (q[i - 1] >= cutoff));
     }
-}
+    __device__ __forceinline__ void emit(unsigned i, unsigned long long w) const {
+        out_pos[w] = pos[i];
+        out_val[w] = q[i] >= cutoff;
+    }
+    __device__ __forceinline__ void finish(unsigned long long) const {}
+};
 
 }  // namespace gpc
 
@@ -587,8 +620,9 @@ extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n
     *n_distinct = 0;
     if (n_runs == 0) return GPC_OK;
     unsigned n = (unsigned)n_runs;
-    unsigned long long cap = 1ull << 16;
-    while (cap < 2ull * n && cap < (1ull << 22)) cap <<= 1;
+    // tracks hold few distinct p (tens of thousands): start small, grow when the
+    // table turns out more than half full
+    unsigned long long cap = 1ull << 17;
     while (true) {
         Scratch keys, counts, fail, flag, offs, total;
         GPC_CUDA(keys.alloc(cap * 8, stream));
@@ -598,7 +632,7 @@ extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n
         GPC_CUDA(cudaMemsetAsync(counts.p, 0, cap * 8, stream));
         GPC_CUDA(cudaMemsetAsync(fail.p, 0, 8, stream));
         GPC_PROF("ptable_insert");
-        ptable_insert_kernel<<<div_up(n, 256), 256, 0, stream>>>(
+        ptable_insert_kernel<<<div_up(n, PT_TILE), PT_THREADS, 0, stream>>>(
             pos, p, n, track_size, keys.as<unsigned long long>(), counts.as<unsigned long long>(),
             (unsigned)(cap - 1), fail.as<int>());
         GPC_LAUNCH_CHECK();
@@ -615,8 +649,8 @@ extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n
         int hfail = 0;
         GPC_READ_BACK({total.p, &h, (unsigned)(8)}, {fail.p, &hfail, (unsigned)(4)});
         if (hfail || h * 2 > cap) {               // too full: grow and redo
-            if (cap >= 4ull * n + (1ull << 16)) { set_error("p table overflow"); return GPC_ERR_INTERNAL; }
-            cap <<= 2;
+            if (cap >= 4ull * n + (1ull << 17)) { set_error("p table overflow"); return GPC_ERR_INTERNAL; }
+            cap <<= 3;
             continue;
         }
         *n_distinct = h;
@@ -689,19 +723,10 @@ extern "C" int gpc_threshold(const uint32_t* pos, const double* q, uint64_t n_ru
     *n_out = 0;
     if (n_runs == 0) return GPC_OK;
     unsigned n = (unsigned)n_runs;
-    Scratch flag, offs, total;
-    GPC_CUDA(flag.alloc(n, stream));
-    GPC_CUDA(offs.alloc((size_t)n * 4, stream));
+    Scratch total;
     GPC_CUDA(total.alloc(8, stream));
-    GPC_PROF("threshold_flag");
-    threshold_flag_kernel<<<div_up(n, 256), 256, 0, stream>>>(q, n, cutoff, flag.as<uint8_t>());
-    GPC_LAUNCH_CHECK();
-    GPC_TRY(exclusive_scan<uint8_t>(flag.as<uint8_t>(), offs.as<uint32_t>(), n,
-                                    total.as<unsigned long long>(), stream));
-    GPC_PROF("threshold_emit");
-    threshold_emit_kernel<<<div_up(n, 256), 256, 0, stream>>>(pos, q, n, cutoff, flag.as<uint8_t>(),
-                                                             offs.as<uint32_t>(), out_pos, out_val);
-    GPC_LAUNCH_CHECK();
+    GPC_TRY(select_if("threshold", ThresholdOp{pos, q, cutoff, out_pos, out_val}, n,
+                      total.as<unsigned long long>(), stream));
     unsigned long long h = 0;
     GPC_READ_BACK({total.p, &h, (unsigned)(8)});
     *n_out = h;

@@ -503,19 +503,15 @@ __global__ void dedup_insert_kernel(const int32_t* __restrict__ start_node,
     }
 }
 
-__global__ void dedup_flag_kernel(const unsigned* __restrict__ table_first,
-                                  const unsigned* __restrict__ slot_of, unsigned n,
-                                  uint8_t* __restrict__ keep) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keep[i] = table_first[slot_of[i]] == i;
-}
-
-__global__ void compact_index_kernel(const uint8_t* __restrict__ keep,
-                                     const uint32_t* __restrict__ offs, unsigned n,
-                                     uint32_t* __restrict__ out) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && keep[i]) out[offs[i]] = i;
-}
+// Pass 2 (compaction): the reads that own their slot, in input order.
+struct DedupOp {
+    const unsigned* table_first;
+    const unsigned* slot_of;
+    uint32_t* out;
+    __device__ __forceinline__ bool keep(unsigned i) const { return table_first[slot_of[i]] == i; }
+    __device__ __forceinline__ void emit(unsigned i, unsigned long long w) const { out[w] = i; }
+    __device__ __forceinline__ void finish(unsigned long long) const {}
+};
 
 // Reads arrive in arbitrary order; walking them in (coarse) graph order makes
 // neighbouring threads gather the same node records, so the walk is served by
@@ -550,12 +546,10 @@ extern "C" int gpc_unique_reads(const int32_t* start_node, const int32_t* start_
     // load factor 2/3: 12 bytes per slot, so the table of a 5 M read batch (90 MB)
     // stays inside the 126 MB L2 instead of turning every probe into a DRAM access
     unsigned cap = (unsigned)max(1024ull, (3ull * n + 1) / 2);
-    Scratch keys, first, slot, keep, offs, total;
+    Scratch keys, first, slot, total;
     GPC_CUDA(keys.alloc((size_t)cap * 8, stream));
     GPC_CUDA(first.alloc((size_t)cap * 4, stream));
     GPC_CUDA(slot.alloc((size_t)n * 4, stream));
-    GPC_CUDA(keep.alloc(n, stream));
-    GPC_CUDA(offs.alloc((size_t)n * 4, stream));
     GPC_CUDA(total.alloc(8, stream));
     GPC_CUDA(cudaMemsetAsync(keys.p, 0xff, (size_t)cap * 8, stream));
     GPC_CUDA(cudaMemsetAsync(first.p, 0xff, (size_t)cap * 4, stream));
@@ -566,16 +560,8 @@ extern "C" int gpc_unique_reads(const int32_t* start_node, const int32_t* start_
                                                    first.as<unsigned>(), cap,
                                                    slot.as<unsigned>());
     GPC_LAUNCH_CHECK();
-    GPC_PROF("dedup_flag");
-    dedup_flag_kernel<<<blocks, 256, 0, stream>>>(first.as<unsigned>(), slot.as<unsigned>(), n,
-                                                 keep.as<uint8_t>());
-    GPC_LAUNCH_CHECK();
-    GPC_TRY(exclusive_scan<uint8_t>(keep.as<uint8_t>(), offs.as<uint32_t>(), n,
-                                    total.as<unsigned long long>(), stream));
-    GPC_PROF("compact_index");
-    compact_index_kernel<<<blocks, 256, 0, stream>>>(keep.as<uint8_t>(), offs.as<uint32_t>(), n,
-                                                    out_index);
-    GPC_LAUNCH_CHECK();
+    GPC_TRY(select_if("dedup_select", DedupOp{first.as<unsigned>(), slot.as<unsigned>(), out_index}, n,
+                      total.as<unsigned long long>(), stream));
     unsigned long long h = 0;
     GPC_READ_BACK({total.p, &h, (unsigned)(8)});
     *out_count = h;

@@ -75,6 +75,61 @@ int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* t
     return GPC_OK;
 }
 
+// Single-pass stream compaction (flag + scan + scatter in one kernel): item i is
+// kept when op.keep(i); every kept item is handed to op.emit(i, rank) with its
+// rank among the kept items; op.finish(count) runs once.  *total (device)
+// receives the number kept.
+template <typename Op>
+__global__ void __launch_bounds__(SC_THREADS)
+select_kernel(Op op, unsigned n, unsigned long long* __restrict__ status,
+              unsigned* __restrict__ ticket, unsigned long long* __restrict__ total) {
+    __shared__ int s_scan[33];
+    __shared__ unsigned s_slot;
+    __shared__ unsigned long long s_prefix;
+    const unsigned tile = claim_tile(ticket, &s_slot);
+    const unsigned base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
+    unsigned keep = 0;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j)
+        if (base + j < n && op.keep(base + j)) { keep |= 1u << j; ++cnt; }
+    int tile_total;
+    int ex = block_excl_sum<int>(cnt, s_scan, tile_total);
+    if (threadIdx.x < 32) {
+        unsigned long long p = lookback_excl_warp(status, tile, (unsigned long long)tile_total);
+        if (threadIdx.x == 0) {
+            s_prefix = p;
+            if (tile == gridDim.x - 1) {
+                if (total) *total = p + tile_total;
+                op.finish(p + tile_total);          // number kept, known to the last tile
+            }
+        }
+    }
+    __syncthreads();
+    unsigned long long w = s_prefix + ex;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j)
+        if ((keep >> j) & 1u) op.emit(base + j, w++);
+}
+
+template <typename Op>
+int select_if(const char* name, Op op, size_t n, unsigned long long* total_dev, cudaStream_t stream) {
+    if (n == 0) {
+        if (total_dev) GPC_CUDA(cudaMemsetAsync(total_dev, 0, 8, stream));
+        return GPC_OK;
+    }
+    unsigned tiles = div_up(n, SC_TILE);
+    Scratch sc;
+    GPC_CUDA(sc.alloc((size_t)tiles * 8 + 16, stream));
+    GPC_CUDA(cudaMemsetAsync(sc.p, 0, (size_t)tiles * 8 + 16, stream));
+    unsigned long long* status = sc.as<unsigned long long>() + 2;
+    unsigned* ticket = sc.as<unsigned>();
+    GPC_PROF(name);
+    select_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, status, ticket, total_dev);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+
 // Up to four independent exclusive scans of uint32 arrays of the same length in
 // one launch (one chained scan each); totals[k] receives the sum of array k.
 struct MultiScanArgs {

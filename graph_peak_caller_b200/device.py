@@ -9,12 +9,20 @@ from . import _lib
 from .custom_exceptions import DeviceLibraryMissing
 
 
+_torch = None
+
+
 def torch_cuda():
-    import torch
-    if not torch.cuda.is_available():
-        raise DeviceLibraryMissing(
-            "no CUDA device visible: the callpeaks path runs on the GPU only")
-    return torch
+    """torch, after checking once that a CUDA device is there (the check reads the
+    environment every time and this is called a few hundred times per pass)."""
+    global _torch
+    if _torch is None:
+        import torch
+        if not torch.cuda.is_available():
+            raise DeviceLibraryMissing(
+                "no CUDA device visible: the callpeaks path runs on the GPU only")
+        _torch = torch
+    return _torch
 
 
 def device():
