@@ -260,72 +260,18 @@ pv_eval_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
 
 // Step 2: canonical runs -- entries whose p equals the previous position's p
 // are dropped (SparseDiffs keeps only positions where the value changes).
-// n is read from device memory (the count step 1 left there).
-// Persistent blocks, two tiles in flight: a tile's aggregate is published, then
-// the NEXT tile is loaded, and only then the first tile's prefix is resolved.
-struct CanonTile {
-    unsigned tile, keep;
-    int o, total;
-    double v[SC_ITEMS];
-};
-
-__global__ void __launch_bounds__(SC_THREADS)
-pv_canon_kernel(const uint32_t* __restrict__ in_pos, const double* __restrict__ in_p,
-                const unsigned long long* __restrict__ n_ptr, uint32_t* __restrict__ out_pos,
-                double* __restrict__ out_p, unsigned long long* __restrict__ status,
-                unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_count) {
-    __shared__ int s_scan[33];
-    __shared__ unsigned s_slot;
-    __shared__ unsigned long long s_obase;
-    const unsigned n = (unsigned)*n_ptr;
-    const unsigned n_tiles = (n + SC_TILE - 1) / SC_TILE;
-
-    auto stage = [&](CanonTile& t) -> bool {       // claim, load, count, publish the aggregate
-        t.tile = claim_tile(ticket, &s_slot);
-        if (t.tile >= n_tiles) return false;
-        const unsigned base = t.tile * SC_TILE + threadIdx.x * SC_ITEMS;
-        double prev = (base > 0 && base < n) ? in_p[base - 1] : 0.0;
-        t.keep = 0;
-        int cnt = 0;
-#pragma unroll
-        for (int j = 0; j < SC_ITEMS; ++j) {
-            t.v[j] = 0.0;
-            if (base + j < n) {
-                t.v[j] = in_p[base + j];
-                if (base + j == 0 || t.v[j] != prev) { t.keep |= 1u << j; ++cnt; }
-                prev = t.v[j];
-            }
-        }
-        t.o = block_excl_sum<int>(cnt, s_scan, t.total);
-        if (threadIdx.x == 0) lb_publish_agg(status, t.tile, (unsigned long long)t.total);
-        return true;
-    };
-    auto finish = [&](const CanonTile& t) {        // resolve the prefix, write
-        if (threadIdx.x < 32) {
-            unsigned long long b = lb_resolve_warp(status, t.tile, (unsigned long long)t.total);
-            if (threadIdx.x == 0) {
-                s_obase = b;
-                if (t.tile == n_tiles - 1) *out_count = b + t.total;
-            }
-        }
-        __syncthreads();
-        unsigned long long w = s_obase + t.o;
-        const unsigned base = t.tile * SC_TILE + threadIdx.x * SC_ITEMS;
-#pragma unroll
-        for (int j = 0; j < SC_ITEMS; ++j)
-            if ((t.keep >> j) & 1u) { out_pos[w] = in_pos[base + j]; out_p[w] = t.v[j]; ++w; }
-        __syncthreads();                           // s_obase is reused
-    };
-
-    CanonTile a, b;
-    if (!stage(a)) return;
-    while (true) {
-        bool more = stage(b);
-        finish(a);
-        if (!more) break;
-        a = b;
+struct CanonOp {
+    const uint32_t* in_pos;
+    const double* in_p;
+    uint32_t* out_pos;
+    double* out_p;
+    __device__ __forceinline__ bool keep(unsigned i) const { return i == 0 || in_p[i] != in_p[i - 1]; }
+    __device__ __forceinline__ void emit(unsigned i, unsigned long long w) const {
+        out_pos[w] = in_pos[i];
+        out_p[w] = in_p[i];
     }
-}
+    __device__ __forceinline__ void finish(unsigned long long) const {}
+};
 
 // ---- (p -> base pairs) table --------------------------------------------------
 
@@ -561,16 +507,13 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
     if (total == 0) return GPC_OK;
     if (total >= (1ull << 31)) { set_error("tracks too long"); return GPC_ERR_ARG; }
     unsigned tiles = div_up(total, PV_TILE);
-    unsigned ctiles = div_up(total, SC_TILE);
     Scratch sc;
-    size_t bytes = ((size_t)tiles + ctiles) * 8 + 64;
+    size_t bytes = (size_t)tiles * 8 + 64;
     GPC_CUDA(sc.alloc(bytes, stream));
     GPC_CUDA(cudaMemsetAsync(sc.p, 0, bytes, stream));
     unsigned long long* count = sc.as<unsigned long long>();      // [0] positions, [1] runs
     unsigned* ticket = reinterpret_cast<unsigned*>(count + 2);
-    unsigned* cticket = ticket + 1;
     unsigned long long* status = count + 4;
-    unsigned long long* cstatus = status + tiles;
     // memo table: 2^20 entries of 32 B (stays in L2); small inputs do without
     Scratch memo_buf;
     PMemo memo;
@@ -600,11 +543,9 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
                                                     split.as<uint32_t>(), tmp_pos.as<uint32_t>(),
                                                     tmp_p.as<double>(), status, ticket, count);
     GPC_LAUNCH_CHECK();
-    GPC_PROF("pv_canon");
-    pv_canon_kernel<<<min(ctiles, (unsigned)sm_count() * 6u), SC_THREADS, 0, stream>>>(
-        tmp_pos.as<uint32_t>(), tmp_p.as<double>(), count, out_pos, out_p, cstatus, cticket,
-        count + 1);
-    GPC_LAUNCH_CHECK();
+    // (the number of positions stays on the device: no host round trip in between)
+    GPC_TRY(select_if("pv_canon", CanonOp{tmp_pos.as<uint32_t>(), tmp_p.as<double>(), out_pos, out_p},
+                      total, count + 1, stream, count));
     unsigned long long h[2] = {0, 0};
     GPC_READ_BACK({count, h, (unsigned)(16)});
     *n_out = h[1];

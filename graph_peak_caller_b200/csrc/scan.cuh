@@ -81,39 +81,61 @@ int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* t
 // receives the number kept.
 template <typename Op>
 __global__ void __launch_bounds__(SC_THREADS)
-select_kernel(Op op, unsigned n, unsigned long long* __restrict__ status,
-              unsigned* __restrict__ ticket, unsigned long long* __restrict__ total) {
-    __shared__ int s_scan[33];
+select_kernel(Op op, unsigned n_max, const unsigned long long* __restrict__ n_dev,
+              unsigned long long* __restrict__ status, unsigned* __restrict__ ticket,
+              unsigned long long* __restrict__ total) {
+    // striped items (row j of the tile = 256 consecutive items, one per thread):
+    // loads and stores of a warp are contiguous; ranks come from ballots
+    constexpr int WARPS = SC_THREADS / 32;
+    __shared__ unsigned s_cnt[SC_ITEMS * WARPS + 1];
     __shared__ unsigned s_slot;
     __shared__ unsigned long long s_prefix;
     const unsigned tile = claim_tile(ticket, &s_slot);
-    const unsigned base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
-    unsigned keep = 0;
-    int cnt = 0;
+    // the item count may still sit in device memory (produced by the previous kernel)
+    const unsigned n = n_dev ? (unsigned)min((unsigned long long)n_max, *n_dev) : n_max;
+    if ((unsigned long long)tile * SC_TILE >= n) return;       // (whole block, nobody waits on it)
+    const unsigned last_tile = (n - 1) / SC_TILE;
+    const unsigned base = tile * SC_TILE + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned keep = 0, before[SC_ITEMS];
 #pragma unroll
-    for (int j = 0; j < SC_ITEMS; ++j)
-        if (base + j < n && op.keep(base + j)) { keep |= 1u << j; ++cnt; }
-    int tile_total;
-    int ex = block_excl_sum<int>(cnt, s_scan, tile_total);
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        const unsigned i = base + j * SC_THREADS;
+        const bool k = i < n && op.keep(i);
+        const unsigned b = __ballot_sync(0xffffffffu, k);
+        before[j] = __popc(b & ((1u << lane) - 1u));
+        if (k) keep |= 1u << j;
+        if (lane == 0) s_cnt[j * WARPS + w] = __popc(b);
+    }
+    __syncthreads();
     if (threadIdx.x < 32) {
+        // exclusive scan of the SC_ITEMS x WARPS (= 64) counts, two per lane
+        unsigned a0 = s_cnt[2 * lane], a1 = s_cnt[2 * lane + 1];
+        unsigned incl = warp_incl_sum(a0 + a1);
+        unsigned tile_total = __shfl_sync(0xffffffffu, incl, 31);
+        s_cnt[2 * lane] = incl - a0 - a1;
+        s_cnt[2 * lane + 1] = incl - a1;
         unsigned long long p = lookback_excl_warp(status, tile, (unsigned long long)tile_total);
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             s_prefix = p;
-            if (tile == gridDim.x - 1) {
+            if (tile == last_tile) {
                 if (total) *total = p + tile_total;
                 op.finish(p + tile_total);          // number kept, known to the last tile
             }
         }
     }
     __syncthreads();
-    unsigned long long w = s_prefix + ex;
+    const unsigned long long p = s_prefix;
 #pragma unroll
     for (int j = 0; j < SC_ITEMS; ++j)
-        if ((keep >> j) & 1u) op.emit(base + j, w++);
+        if ((keep >> j) & 1u)
+            op.emit(base + j * SC_THREADS, p + s_cnt[j * WARPS + w] + before[j]);
 }
 
+// n_dev (optional): the real item count, <= n, read by the kernel from device memory.
 template <typename Op>
-int select_if(const char* name, Op op, size_t n, unsigned long long* total_dev, cudaStream_t stream) {
+int select_if(const char* name, Op op, size_t n, unsigned long long* total_dev, cudaStream_t stream,
+              const unsigned long long* n_dev = nullptr) {
     if (n == 0) {
         if (total_dev) GPC_CUDA(cudaMemsetAsync(total_dev, 0, 8, stream));
         return GPC_OK;
@@ -125,7 +147,8 @@ int select_if(const char* name, Op op, size_t n, unsigned long long* total_dev, 
     unsigned long long* status = sc.as<unsigned long long>() + 2;
     unsigned* ticket = sc.as<unsigned>();
     GPC_PROF(name);
-    select_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, status, ticket, total_dev);
+    select_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, n_dev, status, ticket,
+                                                        total_dev);
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }
