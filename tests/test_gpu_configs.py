@@ -164,3 +164,38 @@ def test_medium_size_determinism_and_idempotent_dedup(medium):
     idx2, n2 = kernels.unique_reads(DeviceReads(once))
     assert n2 == n
     assert np.array_equal(cpu(idx2), np.arange(n))
+
+
+def test_mhc_shaped_config_full_size_vs_oracle():
+    """BASELINE.json configs[0] at its real size (the MHC blobs of the reference are
+    missing, SURVEY.md §8d replaces them by this generator): 5 Mbp, 200 k + 200 k
+    reads, F = 135, R = 36, with control -- the largest case the CPU oracle still
+    finishes in seconds.  Whole path through the public classes."""
+    from graph_peak_caller_b200 import CallPeaks
+    from graph_peak_caller_b200.intervals import UniqueIntervals
+    from graph_peak_caller_b200.synthetic import CONFIGS, config_seed
+    cfg = CONFIGS["mhc_shaped"]
+    R, F = cfg["read_length"], cfg["fragment_length"]
+    seed = config_seed(1)
+    g = make_graph(cfg["backbone_bp"], cfg["site_rate"], seed=seed)
+    s = make_reads(g, cfg["n_sample"], R, F, seed=seed + 1)
+    c = make_reads(g, cfg["n_control"], R, F, seed=seed + 2, peak_frac=0.0, dup_frac=0.0)
+    lm = LinearMap.from_graph(g)
+    config = Configuration()
+    config.read_length, config.fragment_length, config.has_control = R, F, True
+    config.linear_map_name = lm
+    reporter = Reporter(None)
+    caller = CallPeaks(g, config, reporter)
+    caller.run(UniqueIntervals(s), UniqueIntervals(c))
+    ref = opipeline.callpeaks(g, lm.as_arrays(), opipeline.unique_reads(s),
+                              opipeline.unique_reads(c), R, F, True)
+    direct = reporter.memory["direct_pileup"]
+    assert_exact((direct.indices, direct.values.astype(float)), ref["direct"], "direct pileup")
+    q = caller.q_values_pileup
+    assert_step_close((q.indices, q.values), ref["q_values"], "q", upto=g.size_bp)
+    h = reporter.memory["hole_cleaned"]
+    assert_exact((h.indices, h.values.astype(bool)), ref["hole_cleaned"], "holes")
+    got = [(p.start_position.offset, p.end_position.offset, list(p.region_paths),
+            (bool(p.info[0]), bool(p.info[1])), float(p.score)) for p in caller.max_path_peaks]
+    assert len(got) > 50
+    assert_same_peaks(got, ref["peaks"])
