@@ -89,12 +89,21 @@ def test_dense_variation_graph_vs_oracle():
     assert_same_peaks(peaks.final_peaks(), ref["peaks"])
 
 
-@pytest.fixture(scope="module")
-def medium():
+@pytest.fixture(scope="module", params=["medium", "chr22_scale"])
+def medium(request):
+    """Sizes the Python oracle cannot finish.  "chr22_scale" is BASELINE.json
+    configs[1] at its full size (the workload bench.py times)."""
     from graph_peak_caller_b200.device import DeviceGraph, DeviceReads
-    g = make_graph(4_000_000, 0.05, seed=91, mnp_frac=0.05, indel_mean=10.0)
-    s = make_reads(g, 400_000, 36, 200, seed=92)
-    c = make_reads(g, 450_000, 36, 200, seed=93, peak_frac=0.0, dup_frac=0.0)
+    if request.param == "medium":
+        g = make_graph(4_000_000, 0.05, seed=91, mnp_frac=0.05, indel_mean=10.0)
+        s = make_reads(g, 400_000, 36, 200, seed=92)
+        c = make_reads(g, 450_000, 36, 200, seed=93, peak_frac=0.0, dup_frac=0.0)
+    else:
+        from graph_peak_caller_b200.synthetic import CONFIGS
+        cfg = CONFIGS["chr22_scale"]
+        g = make_graph(cfg["backbone_bp"], cfg["site_rate"], seed=20261001)
+        s = make_reads(g, cfg["n_sample"], 36, 200, seed=1)
+        c = make_reads(g, cfg["n_control"], 36, 200, seed=2, peak_frac=0.0, dup_frac=0.0)
     lm = LinearMap.from_graph(g).as_arrays()
     return g, s, c, DeviceGraph(g, lm), DeviceReads(s), DeviceReads(c)
 
@@ -147,6 +156,40 @@ def test_medium_size_invariants(medium):
     for start, end, nodes, info, score in final:
         assert all(g.min_node <= v < g.min_node + g.n_nodes for v in nodes)
         assert score >= -np.log10(0.05) - 1e-9
+
+
+def _add_step_functions(a, b, size):
+    """Sum of two canonical step functions (positions, values)."""
+    grid = np.union1d(a[0], b[0])
+    va = a[1][np.searchsorted(a[0], grid, side="right") - 1]
+    vb = b[1][np.searchsorted(b[0], grid, side="right") - 1]
+    v = va + vb
+    keep = np.r_[True, v[1:] != v[:-1]]
+    return grid[keep], v[keep]
+
+
+def test_pileup_is_additive_over_read_subsets(medium):
+    """Linearity at full size: the pileups of two halves of the reads add up,
+    bit for bit, to the pileup of all of them (walk, event sort and run
+    extraction on 2 x 8 M events against 16 M events)."""
+    from graph_peak_caller_b200 import pipeline
+    from graph_peak_caller_b200.device import DeviceReads
+    g, s, c, dg, ds, dc = medium
+    n = len(s)
+    u = lambda t: cpu(t).view(np.uint32).astype(np.int64)
+    whole = pipeline.sample_pileup(dg, ds, None, n, 164)
+    half = np.arange(n) % 2 == 0
+    parts = []
+    for mask in (half, ~half):
+        sub = s.select(np.flatnonzero(mask))
+        parts.append(pipeline.sample_pileup(dg, DeviceReads(sub), None, len(sub), 164))
+    for k, name in ((0, "fragment"), (1, "direct")):
+        a, b = ((u(p[k][0]), cpu(p[k][1]).astype(np.int64)) for p in parts)
+        pos, val = _add_step_functions(a, b, g.size_bp)
+        assert np.array_equal(pos, u(whole[k][0])), name
+        assert np.array_equal(val, cpu(whole[k][1]).astype(np.int64)), name
+    touched = cpu(parts[0][2]).astype(bool) | cpu(parts[1][2]).astype(bool)
+    assert np.array_equal(touched, cpu(whole[2]).astype(bool))
 
 
 def test_medium_size_determinism_and_idempotent_dedup(medium):
