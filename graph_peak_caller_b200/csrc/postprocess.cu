@@ -1193,9 +1193,14 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
         comp_keys_kernel<<<GRID(V)>>>(V, parent.as<uint32_t>(), keys0.as<unsigned long long>());
         GPC_LAUNCH_CHECK();
         bool in_tmp = false;
+        // keys are (root << 32 | vertex) written in vertex order: a stable sort on the
+        // root bits alone gives (root, vertex) order
+        int root_bits = 1;
+        while ((1ull << root_bits) < (unsigned long long)V) ++root_bits;
         GPC_TRY((radix_sort<unsigned long long, false>(keys0.as<unsigned long long>(),
                                                        keys1.as<unsigned long long>(), nullptr,
-                                                       nullptr, V, 0, 64, true, &in_tmp, stream)));
+                                                       nullptr, V, 32, 32 + root_bits, false,
+                                                       &in_tmp, stream)));
         const unsigned long long* mk = in_tmp ? keys1.as<unsigned long long>() : keys0.as<unsigned long long>();
         GPC_PROF("comp_heads");
         comp_heads_kernel<<<GRID(V)>>>(mk, V, head.as<uint8_t>());

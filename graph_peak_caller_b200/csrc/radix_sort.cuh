@@ -15,12 +15,19 @@ namespace gpc {
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 
-template <typename KeyT> struct RsTraits;
+// keys per thread: bounded by the 48 KB of static shared memory a tile's keys
+// (and values) are staged in
+template <typename KeyT, bool HAS_VALUE = false> struct RsTraits;
 #ifndef GPC_RS_ITEMS32
-#define GPC_RS_ITEMS32 16
+#define GPC_RS_ITEMS32 24
 #endif
-template <> struct RsTraits<uint32_t> { static constexpr int ITEMS = GPC_RS_ITEMS32; static constexpr int MAX_PASSES = 4; };
-template <> struct RsTraits<unsigned long long> { static constexpr int ITEMS = 8; static constexpr int MAX_PASSES = 8; };
+#ifndef GPC_RS_ITEMS64
+#define GPC_RS_ITEMS64 16
+#endif
+template <> struct RsTraits<uint32_t, false> { static constexpr int ITEMS = GPC_RS_ITEMS32; static constexpr int MAX_PASSES = 4; };
+template <> struct RsTraits<uint32_t, true> { static constexpr int ITEMS = 16; static constexpr int MAX_PASSES = 4; };
+template <> struct RsTraits<unsigned long long, false> { static constexpr int ITEMS = GPC_RS_ITEMS64; static constexpr int MAX_PASSES = 8; };
+template <> struct RsTraits<unsigned long long, true> { static constexpr int ITEMS = 8; static constexpr int MAX_PASSES = 8; };
 
 template <typename KeyT, int RS_BITS>
 __global__ void __launch_bounds__(RS_THREADS)
@@ -76,7 +83,7 @@ constexpr unsigned RS_ST_PREFIX = 2u << 30;
 constexpr unsigned RS_ST_MASK = (1u << 30) - 1;
 
 #ifndef GPC_RS_MIN_BLOCKS
-#define GPC_RS_MIN_BLOCKS 4
+#define GPC_RS_MIN_BLOCKS 3
 #endif
 template <typename KeyT, bool HAS_VALUE, int RS_BITS>
 __global__ void __launch_bounds__(RS_THREADS, GPC_RS_MIN_BLOCKS)
@@ -87,7 +94,7 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out
                    unsigned* __restrict__ ticket /* zeroed */) {
     constexpr int RS_RADIX = 1 << RS_BITS;
     constexpr int DPT = RS_RADIX / RS_THREADS;
-    constexpr int ITEMS = RsTraits<KeyT>::ITEMS;
+    constexpr int ITEMS = RsTraits<KeyT, HAS_VALUE>::ITEMS;
     constexpr int TILE = RS_THREADS * ITEMS;
     __shared__ unsigned warp_hist[RS_WARPS][RS_RADIX];
     __shared__ unsigned digit_start[RS_RADIX];   // exclusive offsets inside the tile
@@ -279,7 +286,7 @@ int radix_sort_bits(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_t
         set_error("radix_sort: %zu keys exceed the 2^30 limit", n);
         return GPC_ERR_ARG;
     }
-    constexpr int TILE = RS_THREADS * RsTraits<KeyT>::ITEMS;
+    constexpr int TILE = RS_THREADS * RsTraits<KeyT, HAS_VALUE>::ITEMS;
     const int n_passes = (end_bit - begin_bit + RS_BITS - 1) / RS_BITS;
     if (n_passes <= 0) return GPC_OK;
     if (n_passes > RsTraits<KeyT>::MAX_PASSES) {
@@ -326,6 +333,140 @@ int radix_sort_bits(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_t
     return GPC_OK;
 }
 
+// ---- small inputs: the whole sort in one block ------------------------------------
+// Up to RS_SMALL_N keys are sorted by ONE block entirely in shared memory (all
+// passes in one launch, no histogram kernels, no tile status, no read-back): a
+// 1000-key sort used to cost 8 passes x ~10 us of launch + latency.
+constexpr int RS_SMALL_THREADS = 512;
+constexpr int RS_SMALL_WARPS = RS_SMALL_THREADS / 32;
+constexpr int RS_SMALL_ITEMS = 8;
+constexpr int RS_SMALL_N = RS_SMALL_THREADS * RS_SMALL_ITEMS;      // 4096
+
+template <typename KeyT, bool HAS_VALUE>
+constexpr size_t rs_small_smem() {
+    return 2 * RS_SMALL_N * sizeof(KeyT) + (HAS_VALUE ? 2 * RS_SMALL_N * 4 : 0) +
+           RS_SMALL_WARPS * 256 * 4 + 256 * 4 + 64 * 4;
+}
+
+template <typename KeyT, bool HAS_VALUE>
+__global__ void __launch_bounds__(RS_SMALL_THREADS)
+rs_small_kernel(KeyT* __restrict__ keys, uint32_t* __restrict__ vals, unsigned n, int begin_bit,
+                int end_bit) {
+    extern __shared__ __align__(16) unsigned char rs_small_raw[];
+    KeyT* kbuf = reinterpret_cast<KeyT*>(rs_small_raw);                           // [2][N]
+    uint32_t* vbuf = reinterpret_cast<uint32_t*>(kbuf + 2 * RS_SMALL_N);          // [2][N] if HAS_VALUE
+    unsigned* warp_hist = vbuf + (HAS_VALUE ? 2 * RS_SMALL_N : 0);                // [WARPS][256]
+    unsigned* digit_start = warp_hist + RS_SMALL_WARPS * 256;                      // [256]
+    unsigned* s_scan = digit_start + 256;                                          // [33]
+    KeyT* s_or = reinterpret_cast<KeyT*>(s_scan + 34);                             // [2], 8-byte aligned
+    const unsigned w = warp_id(), l = lane_id();
+    // load (padding = all ones: largest digit in every pass, behind all real keys)
+    KeyT v_or = 0, v_and = ~KeyT(0);
+    for (unsigned i = threadIdx.x; i < RS_SMALL_N; i += RS_SMALL_THREADS) {
+        KeyT k = i < n ? keys[i] : ~KeyT(0);
+        kbuf[i] = k;
+        if (HAS_VALUE) vbuf[i] = i < n ? vals[i] : 0u;
+        if (i < n) { v_or |= k; v_and &= k; }
+    }
+    // bits that differ between keys: passes over constant digits are skipped
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        v_or |= __shfl_xor_sync(FULL, v_or, d);
+        v_and &= __shfl_xor_sync(FULL, v_and, d);
+    }
+    if (threadIdx.x == 0) { s_or[0] = 0; s_or[1] = ~KeyT(0); }
+    __syncthreads();
+    if (l == 0) {
+        if (sizeof(KeyT) == 8) {
+            atomicOr(reinterpret_cast<unsigned long long*>(&s_or[0]), (unsigned long long)v_or);
+            atomicAnd(reinterpret_cast<unsigned long long*>(&s_or[1]), (unsigned long long)v_and);
+        } else {
+            atomicOr(reinterpret_cast<unsigned*>(&s_or[0]), (unsigned)v_or);
+            atomicAnd(reinterpret_cast<unsigned*>(&s_or[1]), (unsigned)v_and);
+        }
+    }
+    __syncthreads();
+    const KeyT varying = s_or[0] ^ s_or[1];
+    int cur = 0;
+    for (int bit = begin_bit; bit < end_bit; bit += 8) {
+        const int width = min(8, end_bit - bit);
+        const unsigned mask = (1u << width) - 1u;
+        if ((((unsigned)(varying >> bit)) & mask) == 0) continue;        // uniform decision
+        KeyT* kin = kbuf + cur * RS_SMALL_N;
+        KeyT* kout = kbuf + (cur ^ 1) * RS_SMALL_N;
+        uint32_t* vin = vbuf + cur * RS_SMALL_N;
+        uint32_t* vout = vbuf + (cur ^ 1) * RS_SMALL_N;
+        for (int i = threadIdx.x; i < RS_SMALL_WARPS * 256; i += RS_SMALL_THREADS) warp_hist[i] = 0;
+        __syncthreads();
+        KeyT key[RS_SMALL_ITEMS];
+        unsigned rank[RS_SMALL_ITEMS];
+        const unsigned warp_base = w * (RS_SMALL_ITEMS * 32);
+#pragma unroll
+        for (int j = 0; j < RS_SMALL_ITEMS; ++j) {
+            key[j] = kin[warp_base + j * 32 + l];
+            unsigned d = (unsigned)(key[j] >> bit) & mask;
+            unsigned peers = FULL;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                unsigned vote = __ballot_sync(FULL, (d >> b) & 1u);
+                peers &= ((d >> b) & 1u) ? vote : ~vote;
+            }
+            unsigned leader = __ffs(peers) - 1;
+            unsigned old = 0;
+            if (l == leader) {
+                old = warp_hist[w * 256 + d];
+                warp_hist[w * 256 + d] = old + __popc(peers);
+            }
+            old = __shfl_sync(FULL, old, leader);
+            rank[j] = old + __popc(peers & ((1u << l) - 1u));
+            __syncwarp();
+        }
+        __syncthreads();
+        unsigned total = 0;
+        if (threadIdx.x < 256) {
+            for (int ww = 0; ww < RS_SMALL_WARPS; ++ww) {
+                unsigned c = warp_hist[ww * 256 + threadIdx.x];
+                warp_hist[ww * 256 + threadIdx.x] = total;
+                total += c;
+            }
+        }
+        unsigned all;
+        unsigned start = block_excl_sum<unsigned>(total, s_scan, all);
+        if (threadIdx.x < 256) digit_start[threadIdx.x] = start;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < RS_SMALL_ITEMS; ++j) {
+            unsigned d = (unsigned)(key[j] >> bit) & mask;
+            unsigned pos = digit_start[d] + warp_hist[w * 256 + d] + rank[j];
+            kout[pos] = key[j];
+            if (HAS_VALUE) vout[pos] = vin[warp_base + j * 32 + l];
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    for (unsigned i = threadIdx.x; i < n; i += RS_SMALL_THREADS) {
+        keys[i] = kbuf[cur * RS_SMALL_N + i];
+        if (HAS_VALUE) vals[i] = vbuf[cur * RS_SMALL_N + i];
+    }
+}
+
+template <typename KeyT, bool HAS_VALUE>
+int radix_sort_small(KeyT* keys, uint32_t* vals, size_t n, int begin_bit, int end_bit,
+                     cudaStream_t stream) {
+    static bool configured = false;          // opt in to > 48 KB of dynamic shared memory once
+    if (!configured) {
+        GPC_CUDA(cudaFuncSetAttribute(rs_small_kernel<KeyT, HAS_VALUE>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)rs_small_smem<KeyT, HAS_VALUE>()));
+        configured = true;
+    }
+    GPC_PROF("rs_small");
+    rs_small_kernel<KeyT, HAS_VALUE><<<1, RS_SMALL_THREADS, rs_small_smem<KeyT, HAS_VALUE>(), stream>>>(
+        keys, vals, (unsigned)n, begin_bit, end_bit);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+
 // Picks the digit width: 9-bit digits when that saves a pass for 32-bit keys
 // (e.g. 26 significant bits: 3 passes instead of 4), else 8-bit digits.
 template <typename KeyT, bool HAS_VALUE>
@@ -333,6 +474,10 @@ int radix_sort(KeyT* keys, KeyT* keys_tmp, uint32_t* vals, uint32_t* vals_tmp, s
                int begin_bit, int end_bit, bool skip_trivial, bool* result_in_tmp,
                cudaStream_t stream) {
     const int range = end_bit - begin_bit;
+    if (n <= (size_t)RS_SMALL_N && n > 1 && range > 0) {
+        *result_in_tmp = false;
+        return radix_sort_small<KeyT, HAS_VALUE>(keys, vals, n, begin_bit, end_bit, stream);
+    }
     if constexpr (sizeof(KeyT) == 4 && !HAS_VALUE) {
         if ((range + 8) / 9 < (range + 7) / 8)
             return radix_sort_bits<KeyT, HAS_VALUE, 9>(keys, keys_tmp, vals, vals_tmp, n, begin_bit,

@@ -55,3 +55,5 @@ if path and os.path.exists(path):
         span, sum(r[2] for r in recs), sum(g[0] for g in gaps)))
     for gap, n0, n1 in sorted(gaps, reverse=True)[:40]:
         print("  idle %7.1f us between %-22s and %s" % (gap * 1e3, n0, n1))
+if path and os.path.exists(path):
+    print("rs_onesweep launches (ms):", " ".join("%.3f" % d for n_, a_, d in recs if n_ == "rs_onesweep"))
