@@ -163,8 +163,9 @@ class CallPeaksFromQvalues:
         chromosome = None if self._reporter._base_name is None \
             else self._reporter._base_name.replace("_", "")
         for peak in max_paths:
-            peak.set_score(float(peak.score))
-            if peak.length() != 0:
+            if type(peak.score) is not float:
+                peak.set_score(float(peak.score))
+            if chromosome is not None and peak.length() != 0:
                 peak.chromosome = chromosome
         order = finder.order     # stable sort by score, descending (callpeaks.py:204-205)
         logging.info("N unfiltered peaks: %s", len(max_paths))

@@ -3,10 +3,16 @@
 written one JSON object per line."""
 import json
 
-from .reads import Interval
+from .reads import Interval, Position
 
 
 class Peak(Interval):
+    # peaks built from the kernels' flat output keep the two offsets and create
+    # the Position objects on first access (a thousand peaks per chromosome are
+    # built per call; most callers only look at a few fields)
+    _sp = _ep = None
+    _start_off = _end_off = 0
+
     def __init__(self, start_position, end_position, region_paths=None, graph=None,
                  direction=None, score=0, unique_id=None, chromosome=None):
         super().__init__(start_position, end_position, region_paths, graph, direction)
@@ -16,26 +22,40 @@ class Peak(Interval):
         self.chromosome = chromosome
         self._length = None
 
+    @property
+    def start_position(self):
+        if self._sp is None:
+            p = Position.__new__(Position)
+            p.region_path_id = self.region_paths[0]
+            p.offset = self._start_off
+            self._sp = p
+        return self._sp
+
+    @start_position.setter
+    def start_position(self, value):
+        self._sp = value
+
+    @property
+    def end_position(self):
+        if self._ep is None:
+            p = Position.__new__(Position)
+            p.region_path_id = self.region_paths[-1]
+            p.offset = self._end_off
+            self._ep = p
+        return self._ep
+
+    @end_position.setter
+    def end_position(self, value):
+        self._ep = value
+
     @classmethod
     def from_flat(cls, start, end, nodes, graph, score, info, length):
         """Constructor for the kernels' output (plain ints already): skips the
         argument normalisation of ``Interval.__init__``."""
-        from .reads import Position
         self = object.__new__(cls)
-        self.start_position = Position.__new__(Position)
-        self.start_position.region_path_id = nodes[0]
-        self.start_position.offset = start
-        self.end_position = Position.__new__(Position)
-        self.end_position.region_path_id = nodes[-1]
-        self.end_position.offset = end
-        self.region_paths = nodes
-        self.graph = graph
-        self.direction = 1
-        self.score = score
-        self.unique_id = None
-        self.info = info
-        self.chromosome = None
-        self._length = length
+        self.__dict__.update(_start_off=start, _end_off=end, region_paths=nodes, graph=graph,
+                             direction=1, score=score, unique_id=None, info=info,
+                             chromosome=None, _length=length)
         return self
 
     def __str__(self):
