@@ -276,7 +276,7 @@ def main_ours(args):
     pinned = {}
     for tag, rb in (("s", s), ("c", c)):
         pinned[tag] = [torch.from_numpy(a).pin_memory() for a in (
-            rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr, rb.path)]
+            rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr.astype(np.int32), rb.path)]
     h2d = sum(t_.numel() * t_.element_size() for v in pinned.values() for t_ in v)
 
     def fresh(tag):

@@ -31,7 +31,7 @@ class GpcGraph(ctypes.Structure):
 class GpcReads(ctypes.Structure):
     _fields_ = [("n_reads", u64), ("start_node", c_void_p), ("start_off", c_void_p),
                 ("end_node", c_void_p), ("end_off", c_void_p),
-                ("path_ptr", c_void_p), ("path", c_void_p)]
+                ("path_ptr", c_void_p), ("path", c_void_p), ("path_ptr32", c_void_p)]
 
 
 P = ctypes.POINTER

@@ -166,7 +166,8 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
         const unsigned r = read_index ? read_index[i] : i;
         const int sn = reads.start_node[r], en = reads.end_node[r];
         const int so = reads.start_off[r], eo = reads.end_off[r];
-        const long long p0 = reads.path_ptr[r], p1 = reads.path_ptr[r + 1];
+        const long long p0 = reads.path_ptr32 ? (long long)reads.path_ptr32[r] : reads.path_ptr[r];
+        const long long p1 = reads.path_ptr32 ? (long long)reads.path_ptr32[r + 1] : reads.path_ptr[r + 1];
         const bool fwd = sn > 0;
         const uint32_t n = graph.n_nodes, G = graph.size_bp;
         const int mn = graph.min_node;

@@ -139,9 +139,14 @@ class DeviceReads:
             self.end_off = to_device(batch.end_off)
             self.path_ptr = to_device(batch.path_ptr)
             self.path = to_device(batch.path)
+        # 32-bit path offsets (a page-locked batch may carry them: 4 bytes less per
+        # read on the link) go into path_ptr32, 64-bit ones into path_ptr
+        narrow = self.path_ptr.element_size() == 4
+        null = ctypes.c_void_p(0)
         self.c = _lib.GpcReads(self.n, ptr(self.start_node), ptr(self.start_off),
                                ptr(self.end_node), ptr(self.end_off),
-                               ptr(self.path_ptr), ptr(self.path))
+                               null if narrow else ptr(self.path_ptr), ptr(self.path),
+                               ptr(self.path_ptr) if narrow else null)
 
 
 def device_graph(graph, linear_map=None):

@@ -74,8 +74,10 @@ typedef struct gpc_reads {
     const int32_t* start_off;
     const int32_t* end_node;
     const int32_t* end_off;
-    const int64_t* path_ptr; /* n_reads + 1 */
+    const int64_t* path_ptr; /* n_reads + 1 (may be NULL when path_ptr32 is given) */
     const int32_t* path;
+    const uint32_t* path_ptr32; /* optional: the same offsets in 32 bits (fewer bytes to
+                                   upload when the paths hold < 2^32 nodes); used if non-NULL */
 } gpc_reads_t;
 
 /* ---- S1  UniqueIntervals.__iter__  (graph_peak_caller/intervals.py:23-33) ---

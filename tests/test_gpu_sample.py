@@ -116,3 +116,32 @@ def test_medium_size_properties():
     e_node = np.abs(r.end_node) - g.min_node
     length = per_read - r.start_off - (g.node_len[e_node] - r.end_off)
     assert mass == int(length.sum())
+
+
+def test_page_locked_batch_with_32_bit_path_offsets():
+    """A batch that sits in page-locked memory is copied asynchronously; when it
+    carries 32-bit path offsets they travel as they are (gpc_reads_t.path_ptr32)."""
+    import torch
+    from graph_peak_caller_b200 import pipeline as gp
+    from graph_peak_caller_b200.device import DeviceGraph, DeviceReads, device_reads, prefetch_reads
+    from graph_peak_caller_b200.reads import ReadBatch
+    g = make_graph(30000, 0.05, seed=77)
+    r = make_reads(g, 4000, 20, 90, seed=78)
+    dg = DeviceGraph(g)
+    want = gp.sample_pileup(dg, DeviceReads(r), None, len(r), 70)
+    pinned = [torch.from_numpy(a).pin_memory() for a in (
+        r.start_node, r.start_off, r.end_node, r.end_off, r.path_ptr.astype(np.int32), r.path)]
+    for use_prefetch in (False, True):
+        rb = ReadBatch.__new__(ReadBatch)
+        (rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr, rb.path) = \
+            [t.numpy() for t in pinned]
+        rb._device = None
+        rb._pinned = pinned
+        if use_prefetch:
+            prefetch_reads(rb)
+        dr = device_reads(rb)
+        assert dr.path_ptr.element_size() == 4
+        got = gp.sample_pileup(dg, dr, None, len(r), 70)
+        for a, b in zip(want[:2], got[:2]):
+            assert bool((a[0] == b[0]).all()) and bool((a[1] == b[1]).all())
+        assert bool((want[2] == got[2]).all())

@@ -15,7 +15,7 @@ c = make_reads(g, 5_000_000, 36, 200, seed=2, peak_frac=0.0, dup_frac=0.0)
 lm = LinearMap.from_graph(g)
 config = Configuration(); config.read_length, config.fragment_length, config.has_control = 36, 200, True
 config.linear_map_name = lm
-pinned = {t: [torch.from_numpy(a).pin_memory() for a in (rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr, rb.path)] for t, rb in (("s", s), ("c", c))}
+pinned = {t: [torch.from_numpy(a).pin_memory() for a in (rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr.astype(np.int32), rb.path)] for t, rb in (("s", s), ("c", c))}
 def fresh(tag):
     rb = ReadBatch.__new__(ReadBatch)
     (rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr, rb.path) = [t.numpy() for t in pinned[tag]]
