@@ -58,3 +58,33 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof / offsetof of gpc_graph_t and gpc_reads_t as the C compiler sees
+    them against the ctypes mirrors the host side passes."""
+    import ctypes
+    import shutil
+    import subprocess
+    from graph_peak_caller_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    fields = {"gpc_graph_t": [f[0] for f in _lib.GpcGraph._fields_],
+              "gpc_reads_t": [f[0] for f in _lib.GpcReads._fields_]}
+    body = ['#include <stdio.h>', '#include <stddef.h>', '#include "gpc_b200.h"', 'int main(void) {']
+    for name, fs in fields.items():
+        body.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f in fs:
+            body.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    body.append("return 0; }")
+    src.write_text("\n".join(body))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                       check=True).stdout.splitlines())
+    for name, cls in (("gpc_graph_t", _lib.GpcGraph), ("gpc_reads_t", _lib.GpcReads)):
+        assert int(out[name]) == ctypes.sizeof(cls), name
+        for f in fields[name]:
+            assert int(out["%s.%s" % (name, f)]) == getattr(cls, f).offset, (name, f)
