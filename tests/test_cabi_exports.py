@@ -3,6 +3,8 @@ include/gpc_b200.h declares; the Python binding table matches the header."""
 import os
 import re
 
+import pytest
+
 from graph_peak_caller_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
