@@ -21,30 +21,44 @@ def world():
     return (d.get_rank(), d.get_world_size()) if d else (0, 1)
 
 
+_capacity = 1 << 16      # entries per rank in the exchange buffer (grown on demand)
+
+
 def gather_p_tables(table_p, table_count, total_bp, group=None):
     """table_p float64[D], table_count int64[D] (torch tensors, CUDA for NCCL,
     CPU for gloo), total_bp: local sum of track sizes.  Returns the
-    concatenation over all ranks and the global total."""
+    concatenation over all ranks and the global total.
+
+    One collective: every rank contributes a fixed-capacity buffer whose first
+    column is a header (entries, base pairs); the capacity only grows -- on all
+    ranks alike, they read the same headers -- when a table does not fit."""
+    global _capacity
     import torch
     d = _dist()
     if d is None or d.get_world_size(group) == 1:
         return table_p, table_count, int(total_bp)
     ws = d.get_world_size(group)
-    meta = torch.tensor([table_p.numel(), int(total_bp)], dtype=torch.int64,
-                        device=table_p.device)
-    metas = [torch.empty_like(meta) for _ in range(ws)]
-    d.all_gather(metas, meta, group=group)
-    metas = torch.stack(metas).cpu().numpy()
-    sizes, totals = metas[:, 0], metas[:, 1]
-    width = int(sizes.max())
-    buf = torch.zeros((2, max(width, 1)), dtype=torch.int64, device=table_p.device)
     n = table_p.numel()
-    buf[0, :n] = table_p.view(torch.int64)        # bit pattern of the doubles
-    buf[1, :n] = table_count
-    bufs = [torch.empty_like(buf) for _ in range(ws)]
-    d.all_gather(bufs, buf, group=group)
-    ps = torch.cat([b[0, :int(s)] for b, s in zip(bufs, sizes)]).view(torch.float64)
-    cs = torch.cat([b[1, :int(s)] for b, s in zip(bufs, sizes)])
+    while True:
+        cap = _capacity
+        buf = torch.empty((2, cap + 1), dtype=torch.int64, device=table_p.device)
+        buf[:, 0] = torch.tensor([n, int(total_bp)], dtype=torch.int64)
+        m = min(n, cap)
+        buf[0, 1:m + 1] = table_p.view(torch.int64)[:m]        # bit pattern of the doubles
+        buf[1, 1:m + 1] = table_count[:m]
+        out = torch.empty((ws, 2, cap + 1), dtype=torch.int64, device=table_p.device)
+        if d.get_backend(group) == "nccl":
+            d.all_gather_into_tensor(out, buf, group=group)
+        else:                                  # gloo (CPU tests): list form
+            d.all_gather([out[r] for r in range(ws)], buf, group=group)
+        head = out[:, :, 0].cpu().numpy()
+        sizes, totals = head[:, 0], head[:, 1]
+        if int(sizes.max()) <= cap:
+            break
+        while _capacity < int(sizes.max()):
+            _capacity *= 2
+    ps = torch.cat([out[r, 0, 1:int(k) + 1] for r, k in enumerate(sizes)]).view(torch.float64)
+    cs = torch.cat([out[r, 1, 1:int(k) + 1] for r, k in enumerate(sizes)])
     return ps, cs, int(totals.sum())
 
 

@@ -28,9 +28,11 @@ def local_table(idx, val, size):
     return p, np.bincount(inv, weights=lens[nz]).astype(np.int64)
 
 
-def worker(rank, world, port, out_dir):
+def worker(rank, world, port, out_dir, capacity=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    if capacity is not None:
+        multigraph._capacity = capacity        # too small: the exchange has to grow it
     idx, val, size = chromosome_tracks(rank)
     p, cnt = local_table(idx, val, size)
     gp, gc, total = multigraph.gather_p_tables(torch.from_numpy(p), torch.from_numpy(cnt), size)
@@ -38,9 +40,10 @@ def worker(rank, world, port, out_dir):
     torch.distributed.destroy_process_group()
 
 
-def test_gather_p_tables_world_size_2(tmp_path):
-    port = 29500 + os.getpid() % 500
-    mp.spawn(worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("capacity", [None, 4])
+def test_gather_p_tables_world_size_2(tmp_path, capacity):
+    port = 29500 + os.getpid() % 500 + (0 if capacity is None else 500)
+    mp.spawn(worker, args=(2, port, str(tmp_path), capacity), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
     assert np.array_equal(r0["p"], r1["p"]) and np.array_equal(r0["c"], r1["c"])
     assert int(r0["total"]) == int(r1["total"]) == 50000 + 51000
