@@ -303,7 +303,7 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
                       unsigned long long* __restrict__ st3 /* zeroed */,
                       unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts) {
     __shared__ unsigned s_slot;
-    __shared__ int s_scan[33];
+    __shared__ long long s_scan64[33];
     __shared__ Seg s_seg[RUN_THREADS / 32];
     __shared__ RunAgg s_carry;
     __shared__ Seg s_all;
@@ -335,10 +335,18 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
             ppos = pos;
         }
     }
-    // block scan of totals
-    int tile_f, tile_d;
-    int ex_f = block_excl_sum<int>(tf, s_scan, tile_f);
-    int ex_d = block_excl_sum<int>(td, s_scan, tile_d);
+    // block scan of totals (both tracks in one 64-bit scan: high word fragment,
+    // low word direct; the borrow of a negative low word is undone when unpacking)
+    int tile_f, tile_d, ex_f, ex_d;
+    {
+        long long tile_pk;
+        long long ex_pk = block_excl_sum<long long>(((long long)tf << 32) + (long long)td, s_scan64,
+                                                    tile_pk);
+        ex_d = (int)(unsigned)(ex_pk & 0xffffffffll);
+        ex_f = (int)((ex_pk - (long long)ex_d) >> 32);
+        tile_d = (int)(unsigned)(tile_pk & 0xffffffffll);
+        tile_f = (int)((tile_pk - (long long)tile_d) >> 32);
+    }
     // block exclusive scan of the segmented operator
     Seg incl = seg;
 #pragma unroll
@@ -368,6 +376,8 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
         s_all = all;
     }
     __syncthreads();
+    // the two chains are independent: warp 0 walks back the open-group sums while
+    // warp 1 resolves the totals
     if (threadIdx.x < 32) {
         const unsigned lane = threadIdx.x;
         const Seg all = s_all;
@@ -393,18 +403,19 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
             if (first_head < 32) break;
             newest -= 32;
         }
+        if (lane == 0) {
+            s_carry.seg[0] = in_a;
+            s_carry.seg[1] = in_b;
+            s_carry.has_head = 0;
+        }
+    } else if (threadIdx.x < 64) {
         long long packed = ((long long)tile_f << 32) + (long long)tile_d;
         unsigned long long ex = lookback_excl_warp(st_tot, tile, (unsigned long long)packed & LB_MASK);
-        if (lane == 0) {
+        if (threadIdx.x == 32) {
             long long v = (long long)(ex << 2) >> 2;              // sign-extend 62 bits
             int d = (int)(unsigned)(v & 0xffffffffll);
-            RunAgg in;
-            in.tot[1] = d;
-            in.tot[0] = (int)((v - (long long)d) >> 32);
-            in.seg[0] = in_a;
-            in.seg[1] = in_b;
-            in.has_head = 0;
-            s_carry = in;
+            s_carry.tot[1] = d;
+            s_carry.tot[0] = (int)((v - (long long)d) >> 32);
         }
     }
     __syncthreads();
@@ -412,12 +423,14 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
     // second thread-local pass: decide emissions
     int run_f = tin.tot[0] + ex_f, run_d = tin.tot[1] + ex_d;
     Seg sg = carry.head ? carry : Seg{0, carry.a + tin.seg[0], carry.b + tin.seg[1]};
-    uint32_t e_idx[2][RUN_ITEMS];
+    // entries are kept at their event slot j (static indexing, no local memory);
+    // bit j of emit[t] says that slot j of track t holds an entry
     int e_val[2][RUN_ITEMS];
-    int cnt[2] = {0, 0};
+    unsigned emit[2] = {0u, 0u};
     ppos = prev_key >> EVENT_POS_SHIFT;
 #pragma unroll
     for (int j = 0; j < RUN_ITEMS; ++j) {
+        e_val[0][j] = 0; e_val[1][j] = 0;
         if (valid[j]) {
             int df, dd;
             event_delta(key[j], df, dd);
@@ -428,40 +441,41 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
             run_f += df; run_d += dd;
             bool last = (base + j + 1 >= n) || (key[j + 1] >> EVENT_POS_SHIFT) != pos;
             if (last) {
-                if (sg.a != 0 || pos == 0) { e_idx[0][cnt[0]] = pos; e_val[0][cnt[0]] = run_f; ++cnt[0]; }
-                if (sg.b != 0 || pos == 0) { e_idx[1][cnt[1]] = pos; e_val[1][cnt[1]] = run_d; ++cnt[1]; }
+                if (sg.a != 0 || pos == 0) { e_val[0][j] = run_f; emit[0] |= 1u << j; }
+                if (sg.b != 0 || pos == 0) { e_val[1][j] = run_d; emit[1] |= 1u << j; }
             }
             ppos = pos;
         }
     }
     // an entry at position 0 always exists: synthesise it when no event sits there
     const bool synth = (tile == 0 && threadIdx.x == 0 && (key[0] >> EVENT_POS_SHIFT) != 0);
-    int c0 = cnt[0] + (synth ? 1 : 0), c1 = cnt[1] + (synth ? 1 : 0);
-    int tot0, tot1;
-    int o0 = block_excl_sum<int>(c0, s_scan, tot0);
-    int o1 = block_excl_sum<int>(c1, s_scan, tot1);
+    const int c0 = __popc(emit[0]) + (synth ? 1 : 0), c1 = __popc(emit[1]) + (synth ? 1 : 0);
+    // both output offsets through one packed scan and one chained scan (2 x 31 bits)
+    long long tile_pk;
+    long long o_pk = block_excl_sum<long long>(((long long)c0 << 31) | (long long)c1, s_scan64, tile_pk);
     if (threadIdx.x < 32) {
-        unsigned long long b0 = lookback_excl_warp(st2, tile, (unsigned long long)tot0);
-        unsigned long long b1 = lookback_excl_warp(st3, tile, (unsigned long long)tot1);
+        unsigned long long b = lookback_excl_warp(st2, tile, (unsigned long long)tile_pk);
         if (threadIdx.x == 0) {
-            s_obase[0] = b0;
-            s_obase[1] = b1;
+            s_obase[0] = b;
             if (tile == gridDim.x - 1) {
-                out_counts[0] = b0 + tot0;
-                out_counts[1] = b1 + tot1;
+                unsigned long long tot = b + (unsigned long long)tile_pk;
+                out_counts[0] = tot >> 31;
+                out_counts[1] = tot & 0x7fffffffull;
             }
         }
     }
     __syncthreads();
-    unsigned long long w0 = s_obase[0] + o0, w1 = s_obase[1] + o1;
+    const unsigned long long w_pk = s_obase[0] + (unsigned long long)o_pk;
+    unsigned long long w0 = w_pk >> 31, w1 = w_pk & 0x7fffffffull;
     if (synth) {
         frag_idx[w0] = 0; frag_val[w0] = 0; ++w0;
         dir_idx[w1] = 0; dir_val[w1] = 0; ++w1;
     }
 #pragma unroll
     for (int j = 0; j < RUN_ITEMS; ++j) {
-        if (j < cnt[0]) { frag_idx[w0 + j] = e_idx[0][j]; frag_val[w0 + j] = e_val[0][j]; }
-        if (j < cnt[1]) { dir_idx[w1 + j] = e_idx[1][j]; dir_val[w1 + j] = e_val[1][j]; }
+        const uint32_t pos = key[j] >> EVENT_POS_SHIFT;
+        if ((emit[0] >> j) & 1u) { frag_idx[w0] = pos; frag_val[w0] = e_val[0][j]; ++w0; }
+        if ((emit[1] >> j) & 1u) { dir_idx[w1] = pos; dir_val[w1] = e_val[1][j]; ++w1; }
     }
 }
 
