@@ -219,9 +219,7 @@ pv_eval_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
         if (t < cnt && e_k[t] != 0) {
             double count = (double)e_k[t] * sample_scale;
             bool found = false;
-#if !defined(GPC_EXP_NO_MEMO)
             if (memo.e) found = memo_find<false>(memo, memo_hash(count, e_lam[t]), count, e_lam[t], e_p[t]);
-#endif
             if (!found) miss |= 1u << t;
         }
     }

@@ -1,12 +1,14 @@
 // LSD radix sort, 8- or 9-bit digits, "onesweep" structure:
 //   1. one histogram kernel counts every digit of every pass in a single read
 //      of the keys;
-//   2. per pass, one scatter kernel: each 4096-key tile ranks its keys with
-//      warp match_any (stable), publishes its 256 digit counts through a
-//      chained scan (decoupled look-back) and writes its keys out grouped by
-//      digit, staged through shared memory so that stores are coalesced runs.
-// Traffic per pass: keys read once, written once (+1 KB of tile status).
+//   2. per pass, one scatter kernel: each tile (4096-6144 keys) counts its
+//      digits and publishes them through a chained scan (decoupled look-back,
+//      several predecessors per round trip) BEFORE ranking its keys (stable,
+//      one ballot per digit bit), then writes the keys out grouped by digit,
+//      staged through shared memory so that stores are coalesced runs.
+// Traffic per pass: keys read once, written once (+1-2 KB of tile status).
 // Passes whose digit is the same for every key are skipped (64-bit keys).
+// Inputs of at most 4096 keys are sorted by one block in shared memory.
 #pragma once
 #include "common.cuh"
 
@@ -144,11 +146,7 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out
         volatile unsigned* st = status;
 #pragma unroll
         for (int t = 0; t < DPT; ++t) excl[t] = 0;
-#ifdef GPC_EXP_NO_LOOKBACK
-        if (true) {
-#else
         if (tile == 0) {
-#endif
 #pragma unroll
             for (int t = 0; t < DPT; ++t)
                 st[tile * RS_RADIX + threadIdx.x * DPT + t] = RS_ST_PREFIX | tot[t];
@@ -160,11 +158,7 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out
             // the walk is as slow as the tiles are spaced and its depth never
             // shrinks (16 round trips per tile were measured); several at once
             // make the walk outrun the wavefront, so the depth collapses.
-#ifdef GPC_RS_LB_WIDE
-            constexpr int LB_WIDE = GPC_RS_LB_WIDE;
-#else
             constexpr int LB_WIDE = 8 / DPT;
-#endif
             int tt[DPT];
             bool done[DPT];
 #pragma unroll
@@ -211,9 +205,6 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         unsigned d = (unsigned)(key[j] >> shift) & (RS_RADIX - 1);
-#ifdef GPC_RS_USE_MATCH
-        unsigned peers = __match_any_sync(FULL, d);
-#else
         // lanes holding the same digit, from one ballot per digit bit
         unsigned peers = FULL;
 #pragma unroll
@@ -221,7 +212,6 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out
             unsigned vote = __ballot_sync(FULL, (d >> b) & 1u);
             peers &= ((d >> b) & 1u) ? vote : ~vote;
         }
-#endif
         unsigned leader = __ffs(peers) - 1;
         unsigned before = __popc(peers & ((1u << l) - 1));
         unsigned old = 0;
