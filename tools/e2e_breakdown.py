@@ -32,7 +32,7 @@ torch.cuda.synchronize(); print("e2e ms/step", 1e3*(time.perf_counter()-t)/5, le
 pr = cProfile.Profile(); pr.enable()
 for _ in range(3): step()
 torch.cuda.synchronize(); pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(30)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
 
 # allocator behaviour: does a step still reach cudaMalloc in steady state?
 import graph_peak_caller_b200.device as _dev
