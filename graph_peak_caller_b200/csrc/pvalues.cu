@@ -393,6 +393,7 @@ __global__ void qtable_keys_kernel(const double* __restrict__ p, unsigned n,
 // 0, running minimum (sparsepvalues.py:95-103).  Writes the distinct p
 // (descending) and their q, returns how many.
 constexpr int QT_THREADS = 1024;
+constexpr int QT_ITEMS = 8;               // consecutive entries per thread (their loads overlap)
 __global__ void __launch_bounds__(QT_THREADS)
 qtable_kernel(const unsigned long long* __restrict__ sorted_keys,
               const uint32_t* __restrict__ sorted_idx,
@@ -405,32 +406,47 @@ qtable_kernel(const unsigned long long* __restrict__ sorted_keys,
     unsigned long long carry_count = 0;   // bp in all earlier chunks
     double carry_min = INFINITY;          // running minimum over earlier chunks
     unsigned carry_out = 0;
-    for (unsigned base = 0; base < n; base += QT_THREADS) {
-        unsigned i = base + threadIdx.x;
-        bool valid = i < n;
-        unsigned long long key = valid ? sorted_keys[i] : 0;
-        unsigned long long c = valid ? counts[sorted_idx[i]] : 0;
-        unsigned long long tot_c;
-        unsigned long long ex_c = block_excl_sum<unsigned long long>(c, s_cnt, tot_c);
-        bool last = valid && (i + 1 >= n || sorted_keys[i + 1] != key);
-        // bp with strictly larger p = running count before the first entry of this p
-        // (computed at the group's first element, consumed at its last)
-        double p = valid ? key_to_f64(~key) : 0.0;
-        // every element of a group needs the count before the group's first
-        // element; groups are tiny, walk back
-        double q = INFINITY;
-        if (last) {
-            unsigned long long before = carry_count + ex_c;
-            unsigned g = i;
-            while (g > 0 && sorted_keys[g - 1] == key) {
-                --g;
-                before -= counts[sorted_idx[g]];
-            }
-            q = p + log10(1.0 + (double)before) - log_n;
-            if (g == 0) q = fmax(0.0, q);
+    for (unsigned base = 0; base < n; base += QT_THREADS * QT_ITEMS) {
+        const unsigned i0 = base + threadIdx.x * QT_ITEMS;
+        unsigned long long key[QT_ITEMS + 1], c[QT_ITEMS];
+#pragma unroll
+        for (int j = 0; j <= QT_ITEMS; ++j) key[j] = (i0 + j < n) ? sorted_keys[i0 + j] : 0ull;
+        unsigned long long tc = 0;
+#pragma unroll
+        for (int j = 0; j < QT_ITEMS; ++j) {
+            c[j] = (i0 + j < n) ? counts[sorted_idx[i0 + j]] : 0ull;
+            tc += c[j];
         }
-        // inclusive running minimum over the block
-        double m = q;
+        unsigned long long tot_c;
+        unsigned long long run = carry_count + block_excl_sum<unsigned long long>(tc, s_cnt, tot_c);
+        // q at the last entry of every distinct p; bp with strictly larger p =
+        // running count before the group's first entry (groups are tiny: walk back)
+        double p[QT_ITEMS], q[QT_ITEMS];
+        unsigned last = 0;
+#pragma unroll
+        for (int j = 0; j < QT_ITEMS; ++j) {
+            const unsigned i = i0 + j;
+            const bool valid = i < n;
+            p[j] = valid ? key_to_f64(~key[j]) : 0.0;
+            q[j] = INFINITY;
+            if (valid && (i + 1 >= n || key[j + 1] != key[j])) {
+                last |= 1u << j;
+                unsigned long long before = run;            // count before entry i
+                unsigned g = i;
+                while (g > 0 && sorted_keys[g - 1] == key[j]) {
+                    --g;
+                    before -= counts[sorted_idx[g]];
+                }
+                q[j] = p[j] + log10(1.0 + (double)before) - log_n;
+                if (g == 0) q[j] = fmax(0.0, q[j]);
+            }
+            run += c[j];
+        }
+        // inclusive running minimum: inside the thread, then over the block
+        double tmin = INFINITY;
+#pragma unroll
+        for (int j = 0; j < QT_ITEMS; ++j) { tmin = fmin(tmin, q[j]); q[j] = tmin; }
+        double m = tmin;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             double o = __shfl_up_sync(FULL, m, d);
@@ -438,17 +454,24 @@ qtable_kernel(const unsigned long long* __restrict__ sorted_keys,
         }
         if (lane_id() == 31) s_min[warp_id()] = m;
         __syncthreads();
-        double pre = carry_min;
+        double pre = carry_min;                       // everything before this thread
         for (unsigned w = 0; w < warp_id(); ++w) pre = fmin(pre, s_min[w]);
-        m = fmin(m, pre);
+        {
+            double up = __shfl_up_sync(FULL, m, 1);
+            if (lane_id() > 0) pre = fmin(pre, up);
+        }
         double chunk_min = carry_min;
         for (unsigned w = 0; w < QT_THREADS / 32; ++w) chunk_min = fmin(chunk_min, s_min[w]);
         int tot_o;
-        int ex_o = block_excl_sum<int>(last ? 1 : 0, s_int, tot_o);
-        if (last) {
-            out_p[carry_out + ex_o] = p;
-            out_q[carry_out + ex_o] = m;
-        }
+        int ex_o = block_excl_sum<int>(__popc(last), s_int, tot_o);
+        unsigned w_out = carry_out + (unsigned)ex_o;
+#pragma unroll
+        for (int j = 0; j < QT_ITEMS; ++j)
+            if ((last >> j) & 1u) {
+                out_p[w_out] = p[j];
+                out_q[w_out] = fmin(pre, q[j]);
+                ++w_out;
+            }
         carry_count += tot_c;
         carry_min = chunk_min;
         carry_out += tot_o;
