@@ -105,24 +105,36 @@ struct Frontier {
     __device__ __forceinline__ bool empty() const { return n == 0 && xn == 0; }
 
     __device__ __forceinline__ void push(uint32_t key, uint32_t rem) {
-        if (n > 0 && k0 == key) { r0 = max(r0, rem); return; }
-        if (n > 1 && k1 == key) { r1 = max(r1, rem); return; }
-        if (n > 2 && k2 == key) { r2 = max(r2, rem); return; }
+        // the usual cases (a bubble graph keeps one or two nodes pending) first,
+        // each with the few moves it needs
+        if (n == 0) { k0 = key; r0 = rem; n = 1; return; }
+        if (k0 == key) { r0 = max(r0, rem); return; }
+        if (n == 1) {
+            if (key < k0) { k1 = k0; r1 = r0; k0 = key; r0 = rem; }
+            else { k1 = key; r1 = rem; }
+            n = 2;
+            return;
+        }
+        if (k1 == key) { r1 = max(r1, rem); return; }
+        if (n == 2) {
+            if (key < k0) { k2 = k1; r2 = r1; k1 = k0; r1 = r0; k0 = key; r0 = rem; }
+            else if (key < k1) { k2 = k1; r2 = r1; k1 = key; r1 = rem; }
+            else { k2 = key; r2 = rem; }
+            n = 3;
+            return;
+        }
+        if (k2 == key) { r2 = max(r2, rem); return; }
         if (n > 3 && k3 == key) { r3 = max(r3, rem); return; }
         if (xn > 0) {
             for (int f = 0; f < xn; ++f)
                 if (xkey[f] == key) { xrem[f] = max(xrem[f], rem); return; }
         }
-        if (n < 4) {
-            if (n == 0) { k0 = key; r0 = rem; }
-            else if (n == 1) { k1 = key; r1 = rem; }
-            else if (n == 2) { k2 = key; r2 = rem; }
-            else { k3 = key; r3 = rem; }
-            ++n;
+        if (n == 3) {
+            k3 = key; r3 = rem; n = 4;
             uint32_t t;
-            if (n > 3 && k3 < k2) { t = k2; k2 = k3; k3 = t; t = r2; r2 = r3; r3 = t; }
-            if (n > 2 && k2 < k1) { t = k1; k1 = k2; k2 = t; t = r1; r1 = r2; r2 = t; }
-            if (n > 1 && k1 < k0) { t = k0; k0 = k1; k1 = t; t = r0; r0 = r1; r1 = t; }
+            if (k3 < k2) { t = k2; k2 = k3; k3 = t; t = r2; r2 = r3; r3 = t; }
+            if (k2 < k1) { t = k1; k1 = k2; k2 = t; t = r1; r1 = r2; r2 = t; }
+            if (k1 < k0) { t = k0; k0 = k1; k1 = t; t = r0; r0 = r1; r1 = t; }
         } else if (xn < FRONTIER_CAP) {
             xkey[xn] = key; xrem[xn] = rem; ++xn;
         } else {
