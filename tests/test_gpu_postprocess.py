@@ -137,3 +137,23 @@ def test_offset_ids_sane_internal_peaks():
     quirk_all = opost.max_paths(g, idx, val, sidx, sval, G, replicate_internal_id_quirk=True)
     got_q, _ = gpu_max_paths(g, idx, val, sidx, sval, sidx, sval, -(g.min_node - 1))
     assert [(p[0], p[1], p[2]) for p in got_q] == [(p[0], p[1], p[2]) for p in quirk_all]
+
+
+@pytest.mark.parametrize("backbone,site_rate", [(2500, 0.05), (1500, 0.2)])
+def test_max_paths_one_giant_component(backbone, site_rate):
+    """A track that is set everywhere: the whole graph is one component of
+    several hundred vertices (the replay's global-memory path; small components
+    keep their working arrays in shared memory)."""
+    g = make_graph(backbone, site_rate=site_rate, seed=77, min_node=1, mnp_frac=0.2,
+                   indel_mean=4.0)
+    G = g.size_bp
+    assert g.n_nodes > 300
+    rng = np.random.default_rng(3)
+    idx, val = np.array([0]), np.array([1], dtype=np.uint8)
+    sidx = np.unique(np.r_[0, rng.integers(1, G, size=G // 7)])
+    sval = rng.integers(0, 5, size=sidx.size).astype(np.float64)
+    ref_all = opost.max_paths(g, idx, val.astype(bool), sidx, sval, G)
+    got_all, _ = gpu_max_paths(g, idx, val, sidx, sval, sidx, sval, 0)
+    assert len(got_all) == 1 and len(got_all[0][2]) > 128
+    assert [(p[0], p[1], p[2], p[3]) for p in got_all] == \
+        [(p[0], p[1], p[2], tuple(p[3])) for p in ref_all]
