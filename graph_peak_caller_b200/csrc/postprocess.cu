@@ -390,6 +390,7 @@ hole_relax_fused_kernel(gpc_graph_t g, VertexView vw, const uint32_t* __restrict
                         const uint32_t* __restrict__ p_end, const uint8_t* __restrict__ is_exit,
                         int32_t* __restrict__ to, int32_t* __restrict__ fr) {
     for (int round = 0; round < RELAX_ROUNDS; ++round) {
+        int changed = 0;
         for (uint32_t i = threadIdx.x; i < n_list; i += blockDim.x) {
             uint32_t u = list[i];
             int t = vw.type_of[u];
@@ -399,7 +400,8 @@ hole_relax_fused_kernel(gpc_graph_t g, VertexView vw, const uint32_t* __restrict
             volatile int32_t* vto = to;
             volatile int32_t* vfr = fr;
             if (t != PIECE_TAIL) {
-                int best = vto[u];
+                const int old = vto[u];
+                int best = old;
                 for (uint32_t e = r0.z; e < r1.z; ++e) {
                     int32_t w = vw.out_vertex[g.pred[e]];
                     if (w >= 0) {
@@ -407,9 +409,10 @@ hole_relax_fused_kernel(gpc_graph_t g, VertexView vw, const uint32_t* __restrict
                         if (d < INF_I) best = min(best, d + (int)(p_end[w] - p_start[w]));
                     }
                 }
-                vto[u] = best;
+                if (best != old) { vto[u] = best; changed = 1; }
             }
-            int best = vfr[u];
+            const int old = vfr[u];
+            int best = old;
             if (is_exit[u]) best = min(best, size);
             if (t != PIECE_HEAD) {
                 for (uint32_t e = r0.y; e < r1.y; ++e) {
@@ -420,9 +423,11 @@ hole_relax_fused_kernel(gpc_graph_t g, VertexView vw, const uint32_t* __restrict
                     }
                 }
             }
-            vfr[u] = best;
+            if (best != old) { vfr[u] = best; changed = 1; }
         }
-        __syncthreads();
+        // fixed point: a whole round without an improvement (small holes need a
+        // handful of rounds, the bound of 37 is the reference's component size limit)
+        if (!__syncthreads_or(changed)) break;
     }
 }
 
