@@ -277,6 +277,69 @@ __global__ void uf_edges_kernel(gpc_graph_t g, VertexView vw, uint32_t* __restri
     }
 }
 
+// Two-level variant for large vertex sets: edges between vertices of the same
+// 1024-vertex block (vertex ids follow graph positions, so that is almost every
+// edge) are united in shared memory without touching global memory; each block
+// then writes its vertices' parents (the block-local minimum) with plain stores,
+// and the few edges that cross a block edge go to a list that a second, tiny
+// kernel unites with the global lock-free algorithm.  Replaces one global
+// find/CAS chain per edge (0.26 ms for 2.9 M hole pieces) -- and also the iota.
+constexpr int UFB_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t ufs_find(volatile uint32_t* parent, uint32_t x) {
+    while (true) {
+        uint32_t p = parent[x];
+        if (p == x) return x;
+        uint32_t gp = parent[p];
+        if (gp != p) parent[x] = gp;
+        x = p;
+    }
+}
+
+__global__ void __launch_bounds__(UFB_THREADS)
+uf_block_edges_kernel(gpc_graph_t g, VertexView vw, uint32_t* __restrict__ parent,
+                      uint2* __restrict__ cross, unsigned long long cross_cap,
+                      unsigned long long* __restrict__ n_cross) {
+    __shared__ uint32_t s_parent[UFB_THREADS];
+    const uint32_t base = blockIdx.x * UFB_THREADS;
+    const uint32_t u = base + threadIdx.x;
+    s_parent[threadIdx.x] = threadIdx.x;
+    __syncthreads();
+    const bool live = u < vw.n && !(vw.alive && !vw.alive[u]) && vw.type_of[u] != PIECE_HEAD;
+    if (live) {
+        uint32_t a = vw.node_of[u];
+        uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
+        for (uint32_t e = r0.y; e < r1.y; ++e) {
+            int32_t w = vw.in_vertex[g.succ[e]];
+            if (w < 0) continue;
+            if ((uint32_t)w >= base && (uint32_t)w < base + UFB_THREADS) {
+                uint32_t x = threadIdx.x, y = (uint32_t)w - base;
+                while (true) {                       // lock-free union, smaller index wins
+                    x = ufs_find(s_parent, x);
+                    y = ufs_find(s_parent, y);
+                    if (x == y) break;
+                    if (x < y) { uint32_t t = x; x = y; y = t; }
+                    if (atomicCAS(&s_parent[x], x, y) == x) break;
+                }
+            } else {
+                unsigned long long at = atomicAdd(n_cross, 1ull);
+                if (at < cross_cap) cross[at] = make_uint2(u, (uint32_t)w);
+            }
+        }
+    }
+    __syncthreads();
+    if (u < vw.n) parent[u] = base + ufs_find(s_parent, threadIdx.x);
+}
+
+__global__ void uf_cross_edges_kernel(const uint2* __restrict__ cross,
+                                      const unsigned long long* __restrict__ n_cross,
+                                      uint32_t* __restrict__ parent) {
+    const unsigned long long n = *n_cross;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        uf_union(parent, cross[i].x, cross[i].y);
+}
+
 // entry / exit flags of hole vertices (graphs.py:47-58) and component stats
 // np.searchsorted(node_off, last position): number of node offsets < pos.  Successors
 // with a larger 1-based index are ignored (graphs.py:55) -> 0-based bound  s < last_node.
@@ -893,6 +956,36 @@ static int scan_counts(const uint32_t* cnt, uint32_t* offs, size_t n, unsigned l
     return GPC_OK;
 }
 
+// parent[] <- union-find forest of the vertex graph (callers resolve roots with
+// uf_find).  Large vertex sets take the two-level kernels.
+static int uf_components(const gpc_graph_t* graph, const VertexView& vw, uint32_t* parent,
+                         cudaStream_t stream) {
+    const uint32_t V = vw.n;
+    if (V < 4 * UFB_THREADS) {
+        GPC_PROF("iota");
+        iota_kernel<<<div_up(V, 256), 256, 0, stream>>>(parent, V);
+        GPC_LAUNCH_CHECK();
+        GPC_PROF("uf_edges");
+        uf_edges_kernel<<<div_up(V, 256), 256, 0, stream>>>(*graph, vw, parent);
+        GPC_LAUNCH_CHECK();
+        return GPC_OK;
+    }
+    Scratch cross, counter;
+    const unsigned long long cap = (unsigned long long)graph->n_edges + 16;
+    GPC_CUDA(cross.alloc(cap * sizeof(uint2), stream));
+    GPC_CUDA(counter.alloc(8, stream));
+    GPC_CUDA(cudaMemsetAsync(counter.p, 0, 8, stream));
+    GPC_PROF("uf_edges");
+    uf_block_edges_kernel<<<div_up(V, UFB_THREADS), UFB_THREADS, 0, stream>>>(
+        *graph, vw, parent, cross.as<uint2>(), cap, counter.as<unsigned long long>());
+    GPC_LAUNCH_CHECK();
+    GPC_PROF("uf_cross_edges");
+    uf_cross_edges_kernel<<<sm_count(), 256, 0, stream>>>(cross.as<uint2>(),
+                                                         counter.as<unsigned long long>(), parent);
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+
 }  // namespace gpc
 
 using namespace gpc;
@@ -984,12 +1077,7 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
         GPC_CUDA(aoffs.alloc((size_t)P * 4, stream));
         GPC_CUDA(cudaMemsetAsync(csize.p, 0, (size_t)P * 4, stream));
         GPC_CUDA(cudaMemsetAsync(centry.p, 0, (size_t)P * 4, stream));
-        GPC_PROF("iota");
-        iota_kernel<<<GRID(P)>>>(parent.as<uint32_t>(), P);
-        GPC_LAUNCH_CHECK();
-        GPC_PROF("uf_edges");
-        uf_edges_kernel<<<GRID(P)>>>(*graph, vw, parent.as<uint32_t>());
-        GPC_LAUNCH_CHECK();
+        GPC_TRY(uf_components(graph, vw, parent.as<uint32_t>(), stream));
         GPC_PROF("hole_flags");
         hole_flags_kernel<<<GRID(P)>>>(*graph, touched, last_node.as<uint32_t>(), vw, n_into.as<uint8_t>(),
                                        n_outof.as<uint8_t>(), parent.as<uint32_t>(),
@@ -1198,12 +1286,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
         GPC_CUDA(hoffs.alloc((size_t)V * 4, stream));
         GPC_CUDA(local_of.alloc((size_t)V * 4, stream));
         GPC_CUDA(comp_of.alloc((size_t)V * 4, stream));
-        GPC_PROF("iota");
-        iota_kernel<<<GRID(V)>>>(parent.as<uint32_t>(), V);
-        GPC_LAUNCH_CHECK();
-        GPC_PROF("uf_edges");
-        uf_edges_kernel<<<GRID(V)>>>(*graph, vw, parent.as<uint32_t>());
-        GPC_LAUNCH_CHECK();
+        GPC_TRY(uf_components(graph, vw, parent.as<uint32_t>(), stream));
         GPC_PROF("peak_flags");
         peak_flags_kernel<<<GRID(V)>>>(*graph, vw, is_entry.as<uint8_t>(), is_exit.as<uint8_t>());
         GPC_LAUNCH_CHECK();
