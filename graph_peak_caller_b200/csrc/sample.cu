@@ -500,29 +500,34 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     return x;
 }
 
-constexpr unsigned long long DEDUP_EMPTY = ~0ull;
+constexpr unsigned DEDUP_EMPTY = 0xffffffffu;
 
-// Pass 1: claim a slot for the key (start node, start offset) and keep the
-// smallest read index that carries it ("first read wins", intervals.py:26-33).
+// Pass 1: every slot of the table holds one read index -- the smallest index
+// seen so far among the reads that share its key (start node, start offset);
+// "first read wins", intervals.py:26-33.  The key of a slot is the key of the
+// read it names, compared by looking that read up, so the table is 4 bytes per
+// slot (30 MB for 5 M reads, L2-resident next to the two key arrays) and an
+// insertion is one CAS in the common case.
 __global__ void dedup_insert_kernel(const int32_t* __restrict__ start_node,
                                     const int32_t* __restrict__ start_off, unsigned n,
-                                    unsigned long long* __restrict__ table_keys,
-                                    unsigned* __restrict__ table_first, unsigned cap,
+                                    unsigned* __restrict__ table, unsigned cap,
                                     unsigned* __restrict__ slot_of) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    unsigned long long key = ((unsigned long long)(uint32_t)start_node[i] << 32) |
-                             (uint32_t)start_off[i];
+    const int32_t node = start_node[i], off = start_off[i];
+    unsigned long long key = ((unsigned long long)(uint32_t)node << 32) | (uint32_t)off;
     // any capacity (not only powers of two): multiply-shift range reduction
     unsigned h = __umulhi((unsigned)(mix64(key) >> 32), cap);
     while (true) {
-        unsigned long long cur = table_keys[h];
+        unsigned cur = table[h];
         if (cur == DEDUP_EMPTY) {
-            unsigned long long old = atomicCAS(&table_keys[h], DEDUP_EMPTY, key);
-            cur = (old == DEDUP_EMPTY) ? key : old;
+            cur = atomicCAS(&table[h], DEDUP_EMPTY, i);
+            if (cur == DEDUP_EMPTY) { slot_of[i] = h; return; }
         }
-        if (cur == key) {
-            atomicMin(&table_first[h], i);
+        // occupied: the slot's key is the key of read `cur` (all reads that ever
+        // own this slot share it)
+        if (start_node[cur] == node && start_off[cur] == off) {
+            atomicMin(&table[h], i);
             slot_of[i] = h;
             return;
         }
@@ -570,20 +575,17 @@ extern "C" int gpc_unique_reads(const int32_t* start_node, const int32_t* start_
     if (n_reads == 0) return GPC_OK;
     if (n_reads >= (1ull << 31)) { set_error("too many reads"); return GPC_ERR_ARG; }
     unsigned n = (unsigned)n_reads;
-    // load factor 2/3: 12 bytes per slot, so the table of a 5 M read batch (90 MB)
-    // stays inside the 126 MB L2 instead of turning every probe into a DRAM access
+    // load factor 2/3, 4 bytes per slot: the table of a 5 M read batch (30 MB) stays
+    // inside the 126 MB L2 instead of turning every probe into a DRAM access
     unsigned cap = (unsigned)max(1024ull, (3ull * n + 1) / 2);
-    Scratch keys, first, slot, total;
-    GPC_CUDA(keys.alloc((size_t)cap * 8, stream));
+    Scratch first, slot, total;
     GPC_CUDA(first.alloc((size_t)cap * 4, stream));
     GPC_CUDA(slot.alloc((size_t)n * 4, stream));
     GPC_CUDA(total.alloc(8, stream));
-    GPC_CUDA(cudaMemsetAsync(keys.p, 0xff, (size_t)cap * 8, stream));
     GPC_CUDA(cudaMemsetAsync(first.p, 0xff, (size_t)cap * 4, stream));
     unsigned blocks = div_up(n, 256);
     GPC_PROF_BYTES("dedup_insert", 12.0 * n);
     dedup_insert_kernel<<<blocks, 256, 0, stream>>>(start_node, start_off, n,
-                                                   keys.as<unsigned long long>(),
                                                    first.as<unsigned>(), cap,
                                                    slot.as<unsigned>());
     GPC_LAUNCH_CHECK();
