@@ -25,13 +25,25 @@ def torch_cuda():
     return _torch
 
 
+_devices = {}
+
+
 def device():
     torch = torch_cuda()
-    return torch.device("cuda", torch.cuda.current_device())
+    index = torch.cuda.current_device()
+    dev = _devices.get(index)
+    if dev is None:
+        dev = _devices[index] = torch.device("cuda", index)
+    return dev
 
 
 def stream_ptr():
+    """cudaStream_t of torch's current stream (the raw accessor when this torch
+    has it: the Stream object costs microseconds, and every stage asks)."""
     torch = torch_cuda()
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return ctypes.c_void_p(raw(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
