@@ -9,6 +9,21 @@ chr22-scale workload of BASELINE.json configs[1] (51 Mbp backbone, 2 % variant
 sites, 5 M sample + 5 M control reads of 36 bp, fragment length 200, with
 control).  N > 1: one such chromosome per rank (weak scaling), joined by the
 single all-gather of the p-value tables.  Prints ONE JSON line on rank 0.
+
+Regions, in order (GPU arm):
+  1. W warm-up steps;
+  2. the timed region: K steps bracketed by barrier + synchronize, CUDA events on
+     the launching stream, max over ranks -> `value`, `ms_per_step`;
+  3. the same K steps again with an event pair around every kernel launch (the
+     library's profiler) -> per-kernel times for `roofline`; kept out of (2)
+     because the event records cost host time;
+  4. K end-to-end steps through CallPeaks.run with page-locked HOST arrays
+     (H2D of both read sets and D2H of the peaks inside the wall-clock region)
+     -> `e2e`;
+  5. rank 0, N == 1: the CPU port of the reference algorithm (oracle/) on a
+     bounded slice -> `cpu_baseline`.
+`--impl reference` runs only the CPU port (one process per chromosome, as the
+reference's README prescribes) and prints the same line with impl=reference.
 """
 import argparse
 import json
