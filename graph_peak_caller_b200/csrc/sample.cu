@@ -105,6 +105,12 @@ struct Frontier {
     __device__ __forceinline__ bool empty() const { return n == 0 && xn == 0; }
 
     __device__ __forceinline__ void push(uint32_t key, uint32_t rem) {
+        // a node that sits in the spill list must be found there before any of the
+        // register paths may insert it (rare: only after more than four were pending)
+        if (xn > 0) {
+            for (int f = 0; f < xn; ++f)
+                if (xkey[f] == key) { xrem[f] = max(xrem[f], rem); return; }
+        }
         // the usual cases (a bubble graph keeps one or two nodes pending) first,
         // each with the few moves it needs
         if (n == 0) { k0 = key; r0 = rem; n = 1; return; }
@@ -125,10 +131,6 @@ struct Frontier {
         }
         if (k2 == key) { r2 = max(r2, rem); return; }
         if (n > 3 && k3 == key) { r3 = max(r3, rem); return; }
-        if (xn > 0) {
-            for (int f = 0; f < xn; ++f)
-                if (xkey[f] == key) { xrem[f] = max(xrem[f], rem); return; }
-        }
         if (n == 3) {
             k3 = key; r3 = rem; n = 4;
             uint32_t t;

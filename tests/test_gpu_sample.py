@@ -145,3 +145,51 @@ def test_page_locked_batch_with_32_bit_path_offsets():
         for a, b in zip(want[:2], got[:2]):
             assert bool((a[0] == b[0]).all()) and bool((a[1] == b[1]).all())
         assert bool((want[2] == got[2]).all())
+
+
+def _fan_graph(rng, n_layers, width):
+    """Layers of `width` short parallel nodes with random forward edges between
+    neighbouring layers and some skipping a layer: more than four nodes pending
+    at once, and nodes reached again while others are pending."""
+    from graph_peak_caller_b200.graph import Graph
+    node_len, layers, src, dst = [8], [[0]], [], []
+    for layer in range(n_layers):
+        w = int(rng.integers(2, width + 1)) if layer % 2 == 0 else 1
+        ids = list(range(len(node_len), len(node_len) + w))
+        node_len += [int(x) for x in rng.integers(1, 4, size=w)]
+        for v in ids:                                   # every node gets a predecessor
+            src.append(int(rng.choice(layers[-1]))); dst.append(v)
+        for u in layers[-1]:                            # ... and a successor
+            src.append(u); dst.append(int(rng.choice(ids)))
+        for u in layers[-1]:
+            for v in ids:
+                if rng.random() < 0.5:
+                    src.append(u); dst.append(v)
+        if len(layers) > 1:
+            for u in layers[-2]:
+                if rng.random() < 0.3:
+                    src.append(u); dst.append(int(rng.choice(ids)))
+        layers.append(ids)
+    pairs = sorted(set(zip(src, dst)))
+    return Graph.from_edges(node_len, [a for a, _ in pairs], [b for _, b in pairs], 1)
+
+
+@pytest.mark.parametrize("trial", range(6))
+def test_wide_fan_out_frontier(trial):
+    """Extension frontiers of up to ten nodes (the register part holds four, the
+    rest spills), both strands, against the oracle's node sweep."""
+    from graph_peak_caller_b200.reads import ReadBatch
+    rng = np.random.default_rng(900 + trial)
+    g = _fan_graph(rng, n_layers=14, width=10)
+    n = g.n_nodes
+    fan = np.flatnonzero(np.diff(g.succ_ptr) > 4)
+    assert fan.size > 0
+    # one-node reads on every node, both strands: every fan-out is crossed by extensions
+    nodes = np.arange(n)
+    length = g.node_len[nodes]
+    start_off = np.zeros(n, dtype=np.int64)
+    fwd = ReadBatch(nodes + 1, start_off, nodes + 1, length, np.arange(n + 1), nodes + 1)
+    rev = ReadBatch(-(nodes + 1), start_off, -(nodes + 1), length, np.arange(n + 1), -(nodes + 1))
+    for reads in (fwd, rev):
+        for extension in (3, 11, 40):
+            check(g, reads, extension, False)
