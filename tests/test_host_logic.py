@@ -159,3 +159,21 @@ def test_chromosome_bin_packing():
     assert sorted(i for b in bins for i in b) == list(range(24))
     loads = [sum(hg19[i] for i in b) for b in bins]
     assert max(loads) <= 1.1 * sum(hg19) / 8
+
+
+def test_peak_from_flat_builds_positions_on_demand():
+    """Peaks made from the kernels' flat output behave like constructed ones."""
+    from graph_peak_caller_b200.peakcollection import Peak
+    from graph_peak_caller_b200.reads import Position
+    g = make_graph(500, 0.05, seed=1)
+    p = Peak.from_flat(3, 2, [1, 2, 4], g, 4.5, (True, False), 17)
+    assert "_sp" not in p.__dict__                       # nothing built yet
+    assert p.start_position == Position(1, 3) and p.end_position == Position(4, 2)
+    assert p.length() == 17 and p.score == 4.5 and p.info == (True, False)
+    assert p.region_paths == [1, 2, 4] and p.direction == 1 and p.chromosome is None
+    same = Peak(Position(1, 3), Position(4, 2), [1, 2, 4], g, score=4.5)
+    assert json.loads(p.to_file_line())["region_paths"] == json.loads(same.to_file_line())["region_paths"]
+    q = Peak.from_file_line(p.to_file_line(), g)
+    assert q.start_position == p.start_position and q.end_position == p.end_position
+    p.start_position = Position(1, 0)                    # still assignable, as on an Interval
+    assert p.start_position.offset == 0
