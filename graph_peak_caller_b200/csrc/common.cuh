@@ -146,32 +146,8 @@ __device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long lo
     *reinterpret_cast<volatile unsigned long long*>(p) = v;
 }
 
-// Called by ONE thread of the tile.  Publishes `agg` (< 2^62), walks back and
-// returns the exclusive prefix (sum of the aggregates of all earlier tiles),
-// then publishes the inclusive prefix.
-__device__ __forceinline__ unsigned long long lookback_excl(unsigned long long* status,
-                                                            unsigned tile,
-                                                            unsigned long long agg) {
-    if (tile == 0) {
-        lb_store(&status[0], LB_PREFIX | agg);
-        return 0;
-    }
-    lb_store(&status[tile], LB_AGG | agg);
-    unsigned long long excl = 0;
-    int t = (int)tile - 1;
-    while (true) {
-        unsigned long long s = lb_load(&status[t]);
-        unsigned long long st = s & ~LB_MASK;
-        if (st == LB_EMPTY) continue;
-        excl += s & LB_MASK;
-        if (st == LB_PREFIX) break;
-        --t;
-    }
-    lb_store(&status[tile], LB_PREFIX | ((excl + agg) & LB_MASK));
-    return excl & LB_MASK;
-}
-
-// Warp-wide variant in two halves, so that a block can put other work (the
+// The walk back is warp-wide (32 predecessors per step) and comes in two halves,
+// so that a block can put other work (the
 // loads of its next tile) between publishing a tile's aggregate and needing
 // its prefix: by then the predecessors have published too and the walk back
 // costs one or two round trips instead of a spin.

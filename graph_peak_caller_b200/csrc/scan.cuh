@@ -163,10 +163,12 @@ struct MultiScanArgs {
 };
 
 static __global__ void __launch_bounds__(SC_THREADS)
-multi_scan_kernel(MultiScanArgs a, unsigned n, unsigned long long* __restrict__ totals) {
+multi_scan_kernel(MultiScanArgs a, unsigned n, unsigned long long* __restrict__ totals,
+                  unsigned* __restrict__ ticket) {
     __shared__ unsigned s_scan[33];
+    __shared__ unsigned s_slot;
     __shared__ unsigned long long s_prefix[4];
-    const unsigned tile = blockIdx.x;          // launch order
+    const unsigned tile = claim_tile(ticket, &s_slot);
     const unsigned base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
     for (int k = 0; k < a.k; ++k) {
         unsigned v[SC_ITEMS], sum = 0;
@@ -212,8 +214,9 @@ inline int multi_scan(int k, const uint32_t* const* in, uint32_t* const* out, si
         a.out[i] = i < k ? out[i] : nullptr;
         a.status[i] = totals + 8 + (size_t)tiles * (i < k ? i : 0);
     }
+    unsigned* ticket = reinterpret_cast<unsigned*>(totals + 7);       // zeroed with the rest
     GPC_PROF("multi_scan");
-    multi_scan_kernel<<<tiles, SC_THREADS, 0, stream>>>(a, (unsigned)n, totals);
+    multi_scan_kernel<<<tiles, SC_THREADS, 0, stream>>>(a, (unsigned)n, totals, ticket);
     GPC_LAUNCH_CHECK();
     GPC_READ_BACK({totals, totals_host, (unsigned)(8 * k)});
     return GPC_OK;
