@@ -1,14 +1,20 @@
-"""Summarises an .ncu-rep (raw page): per kernel duration, DRAM bytes, occupancy,
+"""Summarises an .ncu-rep (raw page) or a saved raw-page CSV: per kernel duration, DRAM bytes, occupancy,
 issue utilisation and the top warp-stall reasons.  python tools/ncu_summary.py rep [out.csv]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):                     # a saved `--page raw --csv` export
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h = rows[0]
 col = {k: i for i, k in enumerate(h)}
 def f(r, k):
     try: return float(r[col[k]].replace(",", ""))
     except Exception: return float("nan")
+TO_MB = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6}
+def mb(r, k):                                # ncu scales every column on its own
+    return f(r, k) * TO_MB.get(rows[1][col[k]], float("nan"))
 out = []
 for r in rows[2:]:
     name = r[col["Kernel Name"]].split("(")[0]
@@ -17,8 +23,8 @@ for r in rows[2:]:
                      and f(r, k) == f(r, k)), reverse=True)[:3]
     rec = dict(kernel=name, ms=f(r, "gpu__time_duration.sum") / (1e6 if h and rows[1][col["gpu__time_duration.sum"]] == "ns" else 1),
                unit=rows[1][col["gpu__time_duration.sum"]],
-               dram_MB=(f(r, "dram__bytes_read.sum") + f(r, "dram__bytes_write.sum")),
-               dram_unit=rows[1][col["dram__bytes_read.sum"]],
+               dram_MB=mb(r, "dram__bytes_read.sum") + mb(r, "dram__bytes_write.sum"),
+               dram_unit="Mbyte",
                regs=f(r, "launch__registers_per_thread"), grid=f(r, "launch__grid_size"),
                warps_active_pct=f(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
                issue_pct=f(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
