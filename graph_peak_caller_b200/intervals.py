@@ -8,12 +8,16 @@ is flattened once on the host).  ``UniqueIntervals`` does not filter on the
 host: it asks the device for the index list of first-per-start-position reads
 (kernel gpc_unique_reads) when the pipeline consumes it.
 """
+import os
+
 from .reads import ReadBatch
 
 
 def _as_batch(intervals):
     if isinstance(intervals, ReadBatch):
         return intervals
+    if isinstance(intervals, (str, os.PathLike)):           # an .intervalcollection text file
+        return ReadBatch.from_intervalcollection_file(os.fspath(intervals))
     inner = getattr(intervals, "intervals", intervals)     # obg IntervalCollection
     if isinstance(inner, ReadBatch):
         return inner

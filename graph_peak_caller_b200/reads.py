@@ -159,6 +159,32 @@ class ReadBatch:
             ptr.append(len(path))
         return cls(sn, so, en, eo, ptr, path)
 
+    @classmethod
+    def from_intervalcollection_file(cls, file_name, n_threads=0):
+        """Reads an ``.intervalcollection`` text file (one JSON interval per line,
+        obg ``IntervalCollection.to_file(text_file=True)``) with the library's
+        native parser (``gpc_parse_intervals_host``, host threads) -- same result
+        as ``from_intervals(IntervalCollection.from_file(file_name))`` at a few
+        hundred times the speed of the json module."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        text = np.fromfile(file_name, dtype=np.uint8)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data if a is not None else 0)
+        n_reads, n_nodes = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _lib.check(lib.gpc_parse_intervals_host(vp(text), text.size, int(n_threads), None, None,
+                                                None, None, None, None, ctypes.byref(n_reads),
+                                                ctypes.byref(n_nodes)))
+        r, m = int(n_reads.value), int(n_nodes.value)
+        sn, so, en, eo = (np.empty(r, dtype=np.int32) for _ in range(4))
+        ptr = np.zeros(r + 1, dtype=np.int64)
+        path = np.empty(m, dtype=np.int32)
+        if r:
+            _lib.check(lib.gpc_parse_intervals_host(vp(text), text.size, int(n_threads), vp(sn),
+                                                    vp(so), vp(en), vp(eo), vp(ptr), vp(path),
+                                                    ctypes.byref(n_reads), ctypes.byref(n_nodes)))
+        return cls(sn, so, en, eo, ptr, path)
+
     def __iter__(self):
         for i in range(len(self)):
             yield self.interval(i)

@@ -243,6 +243,23 @@ uint64_t gpc_launch_count(void);
 void gpc_profile_enable(int on);
 uint64_t gpc_profile_report(char* buf, uint64_t capacity);
 
+/* ---- ingest: IntervalCollection text file -> reads SoA, on
+ *      the HOST ----------------------------------------------------------------------
+ * One JSON object per line, as offsetbasedgraph's Interval.to_file_line writes it
+ * and the reference reads it back (callpeaks_interface.py:64-66 after vg JSON
+ * conversion; reporter.py:25-33 for peaks):
+ *     {"start": 3, "end": 17, "region_paths": [12, 13, 15], "direction": 1}
+ * keys in any order, unknown keys skipped, blank lines ignored.  A read's start /
+ * end node is its first / last region path.  `text` need not be 0-terminated.
+ * All pointers are host pointers; `n_threads` <= 0 uses every host core.
+ * Call once with all output arrays NULL to get the counts, allocate
+ * (path_ptr: n_reads + 1), call again with *n_reads / *n_path_nodes set to the
+ * capacities.  GPC_ERR_ARG on a malformed line (see gpc_last_error_string). */
+int gpc_parse_intervals_host(const char* text, uint64_t n_bytes, int32_t n_threads,
+                             int32_t* start_node, int32_t* start_off, int32_t* end_node,
+                             int32_t* end_off, int64_t* path_ptr, int32_t* path,
+                             uint64_t* n_reads, uint64_t* n_path_nodes);
+
 /* ---- C1  LinearMap.from_graph / find_starts / find_ends
  *          (control/linearmap.py:102-154) ------------------------------------
  * HOST function on HOST arrays (one-off preprocessing that the reference
