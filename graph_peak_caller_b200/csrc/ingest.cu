@@ -1,5 +1,6 @@
 // Ingest (the first row after the hot path): text files of
-// offsetbasedgraph intervals -> the reads structure of arrays, on the host.
+// offsetbasedgraph intervals and of vg alignments -> the reads structure of arrays,
+// on the host.
 //
 // An `.intervalcollection` text file holds one JSON object per line, as written
 // by Interval.to_file_line / IntervalCollection.to_file(text_file=True) -- the
@@ -14,6 +15,7 @@
 // second and core, and splits the buffer over host threads at line ends.
 // Host code only: no kernel, all pointers are host pointers.
 #include <stdlib.h>
+#include <string.h>
 
 #include <string>
 #include <thread>
@@ -136,8 +138,9 @@ bool blank(const char* b, const char* e) {
 struct Chunk {
     const char* b;
     const char* e;
-    unsigned long long reads = 0, nodes = 0;
+    unsigned long long reads = 0, nodes = 0, empty = 0, lines = 0;
     long long bad_line = -1;           // index of the first malformed line inside the chunk
+    int bad_kind = 0;                  // -1 malformed, -2 outside the graph
 };
 
 // Applies fn(line begin, line end) to every non-blank line of the chunk.
@@ -152,22 +155,165 @@ void for_lines(const Chunk& ch, Fn&& fn) {
     }
 }
 
-}  // namespace
-}  // namespace gpc
 
-using namespace gpc;
+// ---- vg alignments (`vg view -aj`): one JSON Alignment per line -----------------------
+// What pyvg.conversion.vg_json_file_to_intervals makes of a line (pyvg is not part of
+// the reference tree; restated from its published classes, anchored on the reference's
+// tests/examples.py:5-31 which builds Position(node_id, offset, is_reverse),
+// Edit(to_length, from_length, sequence), Mapping(position, edits) and expects
+// Interval(10, 15, [0]) from one mapping at offset 10 with edits of from_length 4 + 1):
+//   region_paths = [mapping.position.node_id, negated when position.is_reverse]
+//   start        = offset of the first mapping's position (absent = 0)
+//   end          = offset of the last mapping's position + sum of its edits' from_length
+// protobuf's JSON form writes 64-bit integers as strings ("node_id": "8235641"), so
+// quoted integers are accepted (the reference's own splitter allows for them too,
+// preprocess_interface.py:109).  Alignments without a path or with no mappings
+// (unaligned reads) produce no interval.
 
-extern "C" int gpc_parse_intervals_host(const char* text, uint64_t n_bytes, int32_t n_threads,
-                                        int32_t* start_node, int32_t* start_off,
-                                        int32_t* end_node, int32_t* end_off, int64_t* path_ptr,
-                                        int32_t* path, uint64_t* n_reads,
-                                        uint64_t* n_path_nodes) {
+bool parse_json_int(Cursor& c, long long& out) {
+    c.skip_ws();
+    const bool quoted = !c.eof() && *c.p == '"';
+    if (quoted) ++c.p;
+    if (!parse_int(c, out)) return false;
+    if (quoted) {
+        if (c.eof() || *c.p != '"') return false;
+        ++c.p;
+    }
+    return true;
+}
+
+bool parse_json_bool(Cursor& c, bool& out) {
+    c.skip_ws();
+    if (c.end - c.p >= 4 && !memcmp(c.p, "true", 4)) { out = true; c.p += 4; return true; }
+    if (c.end - c.p >= 5 && !memcmp(c.p, "false", 5)) { out = false; c.p += 5; return true; }
+    return false;
+}
+
+// Iterates the members of a JSON object (c.p at '{'): on_key(key, length) must consume the
+// value and return false on malformed input.
+template <typename Fn>
+bool for_members(Cursor& c, Fn&& on_key) {
+    c.skip_ws();
+    if (c.eof() || *c.p != '{') return false;
+    ++c.p;
+    while (true) {
+        c.skip_ws();
+        if (c.eof()) return false;
+        if (*c.p == '}') { ++c.p; return true; }
+        if (*c.p == ',') { ++c.p; continue; }
+        if (*c.p != '"') return false;
+        const char* k0 = c.p + 1;
+        if (!skip_string(c)) return false;
+        const size_t klen = (size_t)(c.p - 1 - k0);
+        c.skip_ws();
+        if (c.eof() || *c.p != ':') return false;
+        ++c.p;
+        if (!on_key(k0, klen)) return false;
+    }
+}
+
+// Iterates the elements of a JSON array (c.p at '['): on_item() consumes one element.
+template <typename Fn>
+bool for_items(Cursor& c, Fn&& on_item) {
+    c.skip_ws();
+    if (c.eof() || *c.p != '[') return false;
+    ++c.p;
+    while (true) {
+        c.skip_ws();
+        if (c.eof()) return false;
+        if (*c.p == ']') { ++c.p; return true; }
+        if (*c.p == ',') { ++c.p; continue; }
+        if (!on_item()) return false;
+    }
+}
+
+inline bool key_is(const char* k, size_t n, const char* name) {
+    return strlen(name) == n && !memcmp(k, name, n);
+}
+
+struct VgMapping {
+    long long node = 0, offset = 0, from_length = 0;
+    bool reverse = false, have_node = false;
+};
+
+bool parse_vg_mapping(Cursor& c, VgMapping& m) {
+    return for_members(c, [&](const char* k, size_t n) {
+        if (key_is(k, n, "position"))
+            return for_members(c, [&](const char* k2, size_t n2) {
+                if (key_is(k2, n2, "node_id")) { m.have_node = true; return parse_json_int(c, m.node); }
+                if (key_is(k2, n2, "offset")) return parse_json_int(c, m.offset);
+                if (key_is(k2, n2, "is_reverse")) return parse_json_bool(c, m.reverse);
+                return skip_value(c);
+            });
+        if (key_is(k, n, "edit"))
+            return for_items(c, [&]() {
+                return for_members(c, [&](const char* k2, size_t n2) {
+                    if (key_is(k2, n2, "from_length")) {
+                        long long v;
+                        if (!parse_json_int(c, v)) return false;
+                        m.from_length += v;
+                        return true;
+                    }
+                    return skip_value(c);
+                });
+            });
+        return skip_value(c);
+    });
+}
+
+// One alignment line.  Returns the number of mappings (0: no interval), -1 on malformed
+// input, -2 when a node lies outside [min_node, max_node] (checked when max_node > 0).
+long long parse_vg_line(const char* b, const char* e, long long min_node, long long max_node,
+                        long long& start, long long& stop, int32_t* path, long long& first,
+                        long long& last) {
+    Cursor c{b, e};
+    long long n_path = 0;
+    bool outside = false;
+    VgMapping m;
+    const bool ok = for_members(c, [&](const char* k, size_t n) {
+        if (!key_is(k, n, "path")) return skip_value(c);
+        return for_members(c, [&](const char* k2, size_t n2) {
+            if (!key_is(k2, n2, "mapping")) return skip_value(c);
+            return for_items(c, [&]() {
+                m = VgMapping();
+                if (!parse_vg_mapping(c, m) || !m.have_node) return false;
+                if (m.node < 0 || (m.node == 0 && m.reverse) || m.node > 2147483647ll ||
+                    m.offset < 0 || m.offset > 2147483647ll || m.from_length < 0)
+                    return false;
+                if (max_node > 0 && (m.node < min_node || m.node > max_node)) outside = true;
+                const long long id = m.reverse ? -m.node : m.node;
+                if (n_path == 0) { first = id; start = m.offset; }
+                last = id;
+                if (path) path[n_path] = (int32_t)id;
+                ++n_path;
+                return true;
+            });
+        });
+    });
+    if (!ok) return -1;
+    if (n_path == 0) return 0;
+    stop = m.offset + m.from_length;
+    if (stop > 2147483647ll) return -1;
+    return outside ? -2 : n_path;
+}
+
+// The two-pass driver both text formats share: pass 1 counts reads and path nodes per
+// chunk of lines, pass 2 lets every chunk fill its own range of the output arrays.
+// line_fn(begin, end, start, stop, path or NULL, first, last) returns the number of path
+// nodes, 0 for a line that holds no read, -1 for a malformed line, -2 for a read outside
+// the graph.
+template <typename LineFn>
+int parse_reads_text(const char* what, const char* text, uint64_t n_bytes, int32_t n_threads,
+                     int32_t* start_node, int32_t* start_off, int32_t* end_node,
+                     int32_t* end_off, int64_t* path_ptr, int32_t* path, uint64_t* n_reads,
+                     uint64_t* n_path_nodes, uint64_t* n_empty, LineFn line_fn) {
     const bool fill = start_node != nullptr;
     const uint64_t want_reads = *n_reads, want_nodes = *n_path_nodes;
     *n_reads = 0;
     *n_path_nodes = 0;
+    if (n_empty) *n_empty = 0;
     if (fill && (!start_off || !end_node || !end_off || !path_ptr || !path)) {
-        set_error("gpc_parse_intervals_host: all output arrays or none");
+        set_error("%s: all output arrays or none", what);
         return GPC_ERR_ARG;
     }
     unsigned threads = n_threads > 0 ? (unsigned)n_threads : std::thread::hardware_concurrency();
@@ -195,31 +341,48 @@ extern "C" int gpc_parse_intervals_host(const char* text, uint64_t n_bytes, int3
     {
         std::vector<std::thread> pool;
         for (auto& ch : chunks)
-            pool.emplace_back([&ch]() {
-                long long line = 0;
+            pool.emplace_back([&ch, &line_fn]() {
+                // counted in locals: neighbouring chunks share cache lines
+                unsigned long long reads = 0, nodes = 0, empty = 0;
+                long long line = 0, bad_line = -1;
+                int bad_kind = 0;
                 for_lines(ch, [&](const char* b, const char* e) {
                     long long s, t, f, l;
-                    long long k = parse_line(b, e, s, t, nullptr, f, l);
-                    if (k < 0) { if (ch.bad_line < 0) ch.bad_line = line; }
-                    else { ch.reads += 1; ch.nodes += (unsigned long long)k; }
+                    long long k = line_fn(b, e, s, t, (int32_t*)nullptr, f, l);
+                    if (k < 0) { if (bad_line < 0) { bad_line = line; bad_kind = (int)k; } }
+                    else if (k == 0) empty += 1;
+                    else { reads += 1; nodes += (unsigned long long)k; }
                     ++line;
                 });
+                ch.reads = reads;
+                ch.nodes = nodes;
+                ch.empty = empty;
+                ch.bad_line = bad_line;
+                ch.bad_kind = bad_kind;
+                ch.lines = (unsigned long long)line;
             });
         for (auto& th : pool) th.join();
     }
-    unsigned long long reads = 0, nodes = 0, lines_before = 0;
+    unsigned long long reads = 0, nodes = 0, empty = 0, lines_before = 0;
     for (auto& ch : chunks) {
         if (ch.bad_line >= 0) {
-            set_error("interval file: malformed line (non-blank line %llu of its chunk, ~line %llu)",
-                      (unsigned long long)ch.bad_line + 1, lines_before + ch.bad_line + 1);
+            if (ch.bad_kind == -2) {
+                set_error("%s: interval not in graph (non-blank line %llu)", what,
+                          lines_before + ch.bad_line + 1);
+                return GPC_ERR_INVALID_INTERVAL;
+            }
+            set_error("%s: malformed line (non-blank line %llu)", what,
+                      lines_before + ch.bad_line + 1);
             return GPC_ERR_ARG;
         }
-        lines_before += ch.reads;
+        lines_before += ch.lines;
         reads += ch.reads;
         nodes += ch.nodes;
+        empty += ch.empty;
     }
     *n_reads = reads;
     *n_path_nodes = nodes;
+    if (n_empty) *n_empty = empty;
     if (!fill) return GPC_OK;
     if (want_reads < reads || want_nodes < nodes) return GPC_ERR_CAPACITY;
     // pass 2: every chunk writes its own range
@@ -227,12 +390,13 @@ extern "C" int gpc_parse_intervals_host(const char* text, uint64_t n_bytes, int3
         std::vector<std::thread> pool;
         unsigned long long r0 = 0, p0 = 0;
         for (auto& ch : chunks) {
-            pool.emplace_back([&ch, r0, p0, start_node, start_off, end_node, end_off, path_ptr,
-                               path]() {
+            pool.emplace_back([&ch, &line_fn, r0, p0, start_node, start_off, end_node, end_off,
+                               path_ptr, path]() {
                 unsigned long long r = r0, q = p0;
                 for_lines(ch, [&](const char* b, const char* e) {
                     long long s = 0, t = 0, f = 0, l = 0;
-                    long long k = parse_line(b, e, s, t, path + q, f, l);
+                    long long k = line_fn(b, e, s, t, path + q, f, l);
+                    if (k <= 0) return;
                     start_node[r] = (int32_t)f;
                     start_off[r] = (int32_t)s;
                     end_node[r] = (int32_t)l;
@@ -248,5 +412,166 @@ extern "C" int gpc_parse_intervals_host(const char* text, uint64_t n_bytes, int3
         for (auto& th : pool) th.join();
     }
     path_ptr[reads] = (int64_t)nodes;
+    return GPC_OK;
+}
+
+
+// ---- vg graphs (`vg view -Vj`): {"node": [{"id", "sequence"}], "edge": [{"from", "to",
+// "from_start", "to_end"}], "path": [...]} -- one object per line, any number of lines.
+// What pyvg.conversion.json_file_to_obg_numpy_graph reads of it (the reference's
+// create_ob_graph, preprocess_interface.py:51-57): a node's length is the length of its
+// sequence; an edge leaves -from when from_start is set and enters -to when to_end is
+// set.  Paths, names and everything else are skipped.
+
+// Length of a JSON string's content in characters of the decoded text (c.p at the
+// opening quote).  Sequences are plain ASCII; an escape counts as one character.
+bool string_length(Cursor& c, long long& len) {
+    ++c.p;
+    const char* p = c.p;
+    const char* q = (const char*)memchr(p, '"', (size_t)(c.end - p));
+    if (!q) return false;
+    if (!memchr(p, '\\', (size_t)(q - p))) {           // the usual case: no escapes
+        len = q - p;
+        c.p = q + 1;
+        return true;
+    }
+    len = 0;
+    while (!c.eof() && *c.p != '"') {
+        if (*c.p == '\\') {
+            ++c.p;
+            if (!c.eof() && *c.p == 'u') c.p += 4;
+        }
+        ++c.p;
+        ++len;
+    }
+    if (c.eof()) return false;
+    ++c.p;
+    return true;
+}
+
+struct VgGraphSink {
+    int32_t* node_id;
+    int32_t* node_len;
+    int32_t* edge_from;
+    int32_t* edge_to;
+    unsigned long long nodes = 0, edges = 0;
+};
+
+bool parse_vg_graph_object(Cursor& c, VgGraphSink& out) {
+    return for_members(c, [&](const char* k, size_t n) {
+        if (key_is(k, n, "node"))
+            return for_items(c, [&]() {
+                long long id = 0, len = 0;
+                bool have_id = false;
+                if (!for_members(c, [&](const char* k2, size_t n2) {
+                        if (key_is(k2, n2, "id")) { have_id = true; return parse_json_int(c, id); }
+                        if (key_is(k2, n2, "sequence")) {
+                            c.skip_ws();
+                            if (c.eof() || *c.p != '"') return false;
+                            return string_length(c, len);
+                        }
+                        return skip_value(c);
+                    }))
+                    return false;
+                if (!have_id || id <= 0 || id > 2147483647ll || len > 2147483647ll) return false;
+                if (out.node_id) { out.node_id[out.nodes] = (int32_t)id; out.node_len[out.nodes] = (int32_t)len; }
+                ++out.nodes;
+                return true;
+            });
+        if (key_is(k, n, "edge"))
+            return for_items(c, [&]() {
+                long long from = 0, to = 0;
+                bool from_start = false, to_end = false, have_from = false, have_to = false;
+                if (!for_members(c, [&](const char* k2, size_t n2) {
+                        if (key_is(k2, n2, "from")) { have_from = true; return parse_json_int(c, from); }
+                        if (key_is(k2, n2, "to")) { have_to = true; return parse_json_int(c, to); }
+                        if (key_is(k2, n2, "from_start")) return parse_json_bool(c, from_start);
+                        if (key_is(k2, n2, "to_end")) return parse_json_bool(c, to_end);
+                        return skip_value(c);
+                    }))
+                    return false;
+                if (!have_from || !have_to || from <= 0 || to <= 0 || from > 2147483647ll ||
+                    to > 2147483647ll)
+                    return false;
+                if (out.edge_from) {
+                    out.edge_from[out.edges] = (int32_t)(from_start ? -from : from);
+                    out.edge_to[out.edges] = (int32_t)(to_end ? -to : to);
+                }
+                ++out.edges;
+                return true;
+            });
+        return skip_value(c);
+    });
+}
+
+}  // namespace
+}  // namespace gpc
+
+using namespace gpc;
+
+extern "C" int gpc_parse_intervals_host(const char* text, uint64_t n_bytes, int32_t n_threads,
+                                        int32_t* start_node, int32_t* start_off,
+                                        int32_t* end_node, int32_t* end_off, int64_t* path_ptr,
+                                        int32_t* path, uint64_t* n_reads,
+                                        uint64_t* n_path_nodes) {
+    return parse_reads_text("interval file", text, n_bytes, n_threads, start_node, start_off,
+                            end_node, end_off, path_ptr, path, n_reads, n_path_nodes, nullptr,
+                            [](const char* b, const char* e, long long& s, long long& t,
+                               int32_t* path_out, long long& f, long long& l) {
+                                return parse_line(b, e, s, t, path_out, f, l);
+                            });
+}
+
+extern "C" int gpc_parse_vg_alignments_host(const char* text, uint64_t n_bytes,
+                                            int32_t n_threads, int32_t min_node,
+                                            int32_t max_node, int32_t* start_node,
+                                            int32_t* start_off, int32_t* end_node,
+                                            int32_t* end_off, int64_t* path_ptr, int32_t* path,
+                                            uint64_t* n_reads, uint64_t* n_path_nodes,
+                                            uint64_t* n_without_path) {
+    const long long lo = min_node, hi = max_node;
+    return parse_reads_text("vg alignment file", text, n_bytes, n_threads, start_node, start_off,
+                            end_node, end_off, path_ptr, path, n_reads, n_path_nodes,
+                            n_without_path,
+                            [lo, hi](const char* b, const char* e, long long& s, long long& t,
+                                     int32_t* path_out, long long& f, long long& l) {
+                                return parse_vg_line(b, e, lo, hi, s, t, path_out, f, l);
+                            });
+}
+
+extern "C" int gpc_parse_vg_graph_host(const char* text, uint64_t n_bytes, int32_t* node_id,
+                                       int32_t* node_len, uint64_t* n_nodes,
+                                       int32_t* edge_from, int32_t* edge_to,
+                                       uint64_t* n_edges) {
+    const bool fill = node_id != nullptr;
+    const uint64_t want_nodes = *n_nodes, want_edges = *n_edges;
+    if (fill && (!node_len || !edge_from || !edge_to)) {
+        set_error("gpc_parse_vg_graph_host: all output arrays or none");
+        return GPC_ERR_ARG;
+    }
+    // the counting pass also validates, so the filling pass cannot overrun
+    for (int pass = 0; pass < (fill ? 2 : 1); ++pass) {
+        VgGraphSink sink{nullptr, nullptr, nullptr, nullptr};
+        if (pass == 1) sink = VgGraphSink{node_id, node_len, edge_from, edge_to};
+        Chunk whole;
+        whole.b = text;
+        whole.e = text + n_bytes;
+        long long line = 0, bad = -1;
+        for_lines(whole, [&](const char* b, const char* e) {
+            ++line;
+            Cursor c{b, e};
+            if (bad < 0 && !parse_vg_graph_object(c, sink)) bad = line;
+        });
+        if (bad >= 0) {
+            set_error("vg graph file: malformed JSON (non-blank line %lld)", bad);
+            return GPC_ERR_ARG;
+        }
+        if (pass == 0) {
+            *n_nodes = sink.nodes;
+            *n_edges = sink.edges;
+            if (fill && (want_nodes < sink.nodes || want_edges < sink.edges))
+                return GPC_ERR_CAPACITY;
+        }
+    }
     return GPC_OK;
 }

@@ -16,8 +16,13 @@ from .reads import ReadBatch
 def _as_batch(intervals):
     if isinstance(intervals, ReadBatch):
         return intervals
-    if isinstance(intervals, (str, os.PathLike)):           # an .intervalcollection text file
-        return ReadBatch.from_intervalcollection_file(os.fspath(intervals))
+    if isinstance(intervals, (str, os.PathLike)):
+        # by file name, as the reference's parse_input_file (callpeaks_interface.py:58-70):
+        # *.json holds vg alignments, anything else is an .intervalcollection text file
+        name = os.fspath(intervals)
+        if name.endswith(".json"):
+            return ReadBatch.from_vg_json_file(name)
+        return ReadBatch.from_intervalcollection_file(name)
     inner = getattr(intervals, "intervals", intervals)     # obg IntervalCollection
     if isinstance(inner, ReadBatch):
         return inner

@@ -10,11 +10,13 @@ longest-processing-time bin packing by graph size) and the join is one
 all-gather of the (p, base pairs) tables (multigraph.gather_p_tables).  In a
 single process it degenerates to the reference's sequential loop.
 
-Inputs per chromosome: a ``Graph`` (or a file written by ``Graph.to_file``),
-reads as ``Intervals`` / ``UniqueIntervals`` / ``ReadBatch`` / iterable of
-obg-style intervals (or a file written by ``ReadBatch.to_file``), a linear map
-(``LinearMap`` or ``.npz`` file).  vg JSON / .nobg parsing is ingest and stays
-with the reference's own tooling."""
+Inputs per chromosome: a ``Graph`` (or a file written by ``Graph.to_file``, or
+a vg graph in JSON form), reads as ``Intervals`` / ``UniqueIntervals`` /
+``ReadBatch`` / iterable of obg-style intervals or a file name
+(``*.intervalcollection`` text, vg alignment JSON, or ``ReadBatch.to_file``'s
+``.npz``; the text formats go through the native host parsers of SURVEY.md
+§8f-1), a linear map (``LinearMap`` or ``.npz`` file).  obg's binary ``.nobg``
+graph files need offsetbasedgraph itself and are not read here."""
 import logging
 
 import numpy as np
@@ -53,7 +55,11 @@ class MultipleGraphsCallpeaks:
     def _graph(self, i):
         if i not in self._graphs:
             g = self.graph_file_names[i]
-            self._graphs[i] = Graph.from_file(g) if isinstance(g, str) else Graph.from_obg(g)
+            if isinstance(g, str) and g.endswith(".json"):        # a vg graph (`vg view -Vj`)
+                from .conversion import json_file_to_obg_numpy_graph
+                self._graphs[i] = json_file_to_obg_numpy_graph(g)
+            else:
+                self._graphs[i] = Graph.from_file(g) if isinstance(g, str) else Graph.from_obg(g)
         return self._graphs[i]
 
     def my_chromosomes(self):
@@ -81,11 +87,20 @@ class MultipleGraphsCallpeaks:
         return n_unique
 
     def get_intervals(self, sample, control, graph):
+        """File names as in the reference (multiplegraphscallpeaks.py:78-104):
+        ``*.intervalcollection`` is an interval text file, any other name a vg
+        alignment JSON file read against ``graph``; additionally ``*.npz`` is a
+        batch written by ``ReadBatch.to_file``."""
         def load(x):
             if isinstance(x, (Intervals, UniqueIntervals)):
                 return x
             if isinstance(x, str):
-                x = ReadBatch.from_file(x)
+                if x.endswith(".npz"):
+                    x = ReadBatch.from_file(x)
+                elif x.endswith(".intervalcollection"):
+                    x = ReadBatch.from_intervalcollection_file(x)
+                else:
+                    x = ReadBatch.from_vg_json_file(x, graph)
             if self._config.keep_duplicates:
                 logging.warning("Keeping duplicates. Should only be used for testing.")
                 return Intervals(x)

@@ -160,6 +160,23 @@ class ReadBatch:
         return cls(sn, so, en, eo, ptr, path)
 
     @classmethod
+    def _from_text(cls, text, call):
+        """Two calls of a native text parser: sizes, then fill.  ``call(arrays or
+        Nones, n_reads, n_nodes)`` binds the entry point and its extra arguments."""
+        import ctypes
+        from . import _lib
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        n_reads, n_nodes = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        call(vp(text), [None] * 6, n_reads, n_nodes)
+        r, m = int(n_reads.value), int(n_nodes.value)
+        sn, so, en, eo = (np.empty(r, dtype=np.int32) for _ in range(4))
+        ptr = np.zeros(r + 1, dtype=np.int64)
+        path = np.empty(m, dtype=np.int32)
+        if r:
+            call(vp(text), [vp(a) for a in (sn, so, en, eo, ptr, path)], n_reads, n_nodes)
+        return cls(sn, so, en, eo, ptr, path)
+
+    @classmethod
     def from_intervalcollection_file(cls, file_name, n_threads=0):
         """Reads an ``.intervalcollection`` text file (one JSON interval per line,
         obg ``IntervalCollection.to_file(text_file=True)``) with the library's
@@ -170,20 +187,39 @@ class ReadBatch:
         from . import _lib
         lib = _lib.load()
         text = np.fromfile(file_name, dtype=np.uint8)
-        vp = lambda a: ctypes.c_void_p(a.ctypes.data if a is not None else 0)
-        n_reads, n_nodes = ctypes.c_uint64(0), ctypes.c_uint64(0)
-        _lib.check(lib.gpc_parse_intervals_host(vp(text), text.size, int(n_threads), None, None,
-                                                None, None, None, None, ctypes.byref(n_reads),
-                                                ctypes.byref(n_nodes)))
-        r, m = int(n_reads.value), int(n_nodes.value)
-        sn, so, en, eo = (np.empty(r, dtype=np.int32) for _ in range(4))
-        ptr = np.zeros(r + 1, dtype=np.int64)
-        path = np.empty(m, dtype=np.int32)
-        if r:
-            _lib.check(lib.gpc_parse_intervals_host(vp(text), text.size, int(n_threads), vp(sn),
-                                                    vp(so), vp(en), vp(eo), vp(ptr), vp(path),
+
+        def call(tp, out, n_reads, n_nodes):
+            _lib.check(lib.gpc_parse_intervals_host(tp, text.size, int(n_threads), *out,
                                                     ctypes.byref(n_reads), ctypes.byref(n_nodes)))
-        return cls(sn, so, en, eo, ptr, path)
+        return cls._from_text(text, call)
+
+    @classmethod
+    def from_vg_json_file(cls, file_name, graph=None, n_threads=0):
+        """Reads vg alignments in JSON form (``vg view -aj``, one Alignment per
+        line) with the native parser ``gpc_parse_vg_alignments_host``: what
+        ``pyvg.conversion.vg_json_file_to_interval_collection(file_name, graph)``
+        returns for the reference (callpeaks_interface.py:24,64), as flat arrays.
+        Alignments without a path (unaligned reads) are dropped; their number is
+        left in ``n_without_path``.  With a graph, a read naming a node outside it
+        raises ``IntervalNotInGraphException`` as pyvg does."""
+        import ctypes
+        from . import _lib
+        from .custom_exceptions import IntervalNotInGraphException, InvalidPileupInterval
+        lib = _lib.load()
+        text = np.fromfile(file_name, dtype=np.uint8)
+        lo, hi = (0, 0) if graph is None else (graph.min_node, graph.min_node + graph.n_nodes - 1)
+        skipped = ctypes.c_uint64(0)
+
+        def call(tp, out, n_reads, n_nodes):
+            try:
+                _lib.check(lib.gpc_parse_vg_alignments_host(
+                    tp, text.size, int(n_threads), int(lo), int(hi), *out,
+                    ctypes.byref(n_reads), ctypes.byref(n_nodes), ctypes.byref(skipped)))
+            except InvalidPileupInterval as e:
+                raise IntervalNotInGraphException(str(e)) from None
+        batch = cls._from_text(text, call)
+        batch.n_without_path = int(skipped.value)
+        return batch
 
     def __iter__(self):
         for i in range(len(self)):

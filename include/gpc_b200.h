@@ -260,6 +260,38 @@ int gpc_parse_intervals_host(const char* text, uint64_t n_bytes, int32_t n_threa
                              int32_t* end_off, int64_t* path_ptr, int32_t* path,
                              uint64_t* n_reads, uint64_t* n_path_nodes);
 
+/* ---- ingest: vg alignments as JSON (`vg view -aj`, one Alignment
+ *      per line) -> reads SoA, on the HOST ------------------------------------------
+ * Replaces pyvg.conversion.vg_json_file_to_interval_collection as the reference
+ * calls it (callpeaks_interface.py:24,64, multiplegraphscallpeaks.py:97-98,
+ * preprocess_interface.py:44).  Per line: region paths = the mappings' node ids
+ * (negated where position.is_reverse), start = offset of the first mapping, end =
+ * offset of the last mapping + sum of its edits' from_length (the reference's
+ * tests/examples.py:5-31 pins this: offset 10, from_length 4 + 1 -> Interval(10, 15)).
+ * Integers may be quoted (protobuf JSON writes 64-bit fields as strings).  Lines
+ * without a path or without mappings (unaligned reads) yield no read and are
+ * counted in *n_without_path (may be NULL).  When max_node > 0 a node id outside
+ * [min_node, max_node] is GPC_ERR_INVALID_INTERVAL (pyvg: IntervalNotInGraphException).
+ * Same two-call protocol and threading as gpc_parse_intervals_host. */
+int gpc_parse_vg_alignments_host(const char* text, uint64_t n_bytes, int32_t n_threads,
+                                 int32_t min_node, int32_t max_node, int32_t* start_node,
+                                 int32_t* start_off, int32_t* end_node, int32_t* end_off,
+                                 int64_t* path_ptr, int32_t* path, uint64_t* n_reads,
+                                 uint64_t* n_path_nodes, uint64_t* n_without_path);
+
+/* ---- ingest: vg graph as JSON (`vg view -Vj`) -> node and edge
+ *      lists, on the HOST ------------------------------------------------------------
+ * Replaces the parsing half of pyvg.conversion.json_file_to_obg_numpy_graph, which
+ * the reference's create_ob_graph calls (preprocess_interface.py:51-57): every line is
+ * an object {"node": [{"id", "sequence"}], "edge": [{"from", "to", "from_start",
+ * "to_end"}], ...}; node_len = length of the sequence; an edge is reported as
+ * (-from if from_start else from, -to if to_end else to), paths and other keys are
+ * skipped.  Nodes and edges come out in file order.  Call with all arrays NULL for
+ * the counts, then with *n_nodes / *n_edges set to the capacities. */
+int gpc_parse_vg_graph_host(const char* text, uint64_t n_bytes, int32_t* node_id,
+                            int32_t* node_len, uint64_t* n_nodes, int32_t* edge_from,
+                            int32_t* edge_to, uint64_t* n_edges);
+
 /* ---- C1  LinearMap.from_graph / find_starts / find_ends
  *          (control/linearmap.py:102-154) ------------------------------------
  * HOST function on HOST arrays (one-off preprocessing that the reference
