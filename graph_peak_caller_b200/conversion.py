@@ -65,6 +65,28 @@ def json_file_to_obg_numpy_graph(file_name, n_nodes=0):
                             dst.astype(np.int64) - min_node, min_node)
 
 
+def load_graph(file_name):
+    """A graph by file name: vg JSON (``*.json``) or the flat npz container that
+    ``Graph.to_file`` / ``callpeaks_interface.create_ob_graph`` write (under any
+    name, ``chr1.nobg`` included).  offsetbasedgraph's own binary ``.nobg`` needs
+    that package and is refused with a message that says so."""
+    import os
+    from .custom_exceptions import GraphNotFoundException
+    if isinstance(file_name, Graph):
+        return file_name
+    if not os.path.isfile(file_name):
+        raise GraphNotFoundException("Graph file %s not found" % file_name)
+    if file_name.endswith(".json"):
+        return json_file_to_obg_numpy_graph(file_name)
+    try:
+        return Graph.from_file(file_name)
+    except KeyError as e:
+        raise GraphNotFoundException(
+            "%s is not a flat graph file (%s): offsetbasedgraph's binary .nobg format is "
+            "not read here; create the graph with create_ob_graph from the vg JSON file"
+            % (file_name, e)) from None
+
+
 _NODE_ID = re.compile(rb"node_id\":\s?\"?([0-9]+)\"?")
 
 
@@ -110,5 +132,5 @@ def node_range_of(graph):
 
 
 __all__ = ["vg_json_file_to_intervals", "vg_json_file_to_interval_collection",
-           "json_file_to_obg_numpy_graph", "split_vg_json_reads_into_chromosomes",
+           "json_file_to_obg_numpy_graph", "load_graph", "split_vg_json_reads_into_chromosomes",
            "node_range_of"]

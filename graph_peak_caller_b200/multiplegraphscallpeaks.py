@@ -26,6 +26,7 @@ from .callpeaks import CallPeaks
 from .graph import Graph
 from .intervals import Intervals, UniqueIntervals
 from .reads import ReadBatch
+from .sparsediffs import SparseValues
 from .sparsepvalues import PToQValuesMapper
 
 
@@ -39,10 +40,12 @@ class MultipleGraphsCallpeaks:
         self._reporter = reporter
         self.names = list(graph_names)
         self.graph_file_names = list(graph_file_names)
-        self.linear_maps = list(linear_maps)
+        # samples / controls / linear maps are None when only the second half runs
+        # (run_callpeaks_whole_genome_from_p_values, callpeaks_interface.py:340-371)
+        self.linear_maps = None if linear_maps is None else list(linear_maps)
         self.sequence_retrievers = sequence_retrievers
-        self.samples = list(samples)
-        self.controls = list(controls)
+        self.samples = None if samples is None else list(samples)
+        self.controls = None if controls is None else list(controls)
         self.stop_after_p_values = stop_after_p_values
         self.linear_path_file_names = linear_path_file_names
         self._graphs = {}
@@ -55,11 +58,11 @@ class MultipleGraphsCallpeaks:
     def _graph(self, i):
         if i not in self._graphs:
             g = self.graph_file_names[i]
-            if isinstance(g, str) and g.endswith(".json"):        # a vg graph (`vg view -Vj`)
-                from .conversion import json_file_to_obg_numpy_graph
-                self._graphs[i] = json_file_to_obg_numpy_graph(g)
+            if isinstance(g, str):
+                from .conversion import load_graph
+                self._graphs[i] = load_graph(g)
             else:
-                self._graphs[i] = Graph.from_file(g) if isinstance(g, str) else Graph.from_obg(g)
+                self._graphs[i] = Graph.from_obg(g)
         return self._graphs[i]
 
     def my_chromosomes(self):
@@ -130,6 +133,12 @@ class MultipleGraphsCallpeaks:
             logging.info("In total %d duplicates were removed from sample" % sample.n_duplicates)
 
     def create_joined_q_value_mapping(self):
+        if not self._callers and self.samples is None:
+            # second half on its own: the p-values of every chromosome are in the files the
+            # first halves wrote (reference multiplegraphscallpeaks.py:122-124)
+            mapper = PToQValuesMapper.from_files(self._reporter._base_name)
+            self._q_value_mapping = mapper.get_p_to_q_values()
+            return
         torch = kernels.torch_cuda()
         tps, tcs, total = [], [], 0
         for i in self.my_chromosomes():
@@ -148,12 +157,25 @@ class MultipleGraphsCallpeaks:
         mapper = PToQValuesMapper._from_device_table(tp, tc, total)
         self._q_value_mapping = mapper.get_p_to_q_values()
 
+    def _caller_from_files(self, i):
+        """State after p-values read back from the Reporter's files (reference
+        multiplegraphscallpeaks.py:147-156); the direct pileup is read by
+        CallPeaksFromQvalues when it is needed (callpeaks.py:170-173)."""
+        name = self.names[i]
+        caller = CallPeaks(self._graph(i), self._config, self._reporter.get_sub_reporter(name))
+        prefix = self._reporter._base_name + (name + "_" if name != "" else "")
+        caller.p_values_pileup = SparseValues.from_sparse_files(prefix + "pvalues")
+        caller.touched_nodes = np.load(prefix + "touched_nodes.npy")
+        return caller
+
     def run_from_p_values(self, only_chromosome=None):
         for i in self.my_chromosomes():
             name = self.names[i]
             if only_chromosome is not None and only_chromosome != name:
                 logging.info("Skipping %s" % str(name))
                 continue
+            if i not in self._callers:
+                self._callers[i] = self._caller_from_files(i)
             caller = self._callers[i]
             caller.p_to_q_values_mapping = self._q_value_mapping
             caller.get_q_values()

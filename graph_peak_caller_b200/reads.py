@@ -243,6 +243,16 @@ class ReadBatch:
                          self.end_node[idx], self.end_off[idx], ptr,
                          self.path[gather])
 
+    def lengths(self, graph):
+        """Base pairs covered by every read (obg ``Interval.length()``): the
+        sizes of its nodes minus what lies before the start and after the end."""
+        size = np.asarray(graph.node_len, dtype=np.int64)
+        index = np.abs(self.path.astype(np.int64)) - graph.min_node
+        total = np.r_[0, np.cumsum(size[index])]
+        covered = total[self.path_ptr[1:]] - total[self.path_ptr[:-1]]
+        last = size[np.abs(self.end_node.astype(np.int64)) - graph.min_node]
+        return covered - self.start_off - (last - self.end_off)
+
     def nbytes(self):
         return sum(a.nbytes for a in (self.start_node, self.start_off,
                                       self.end_node, self.end_off,

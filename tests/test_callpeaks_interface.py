@@ -1,0 +1,222 @@
+"""CPU: the host side of callpeaks_interface.py -- file-name conventions,
+configuration, graph / linear-map files, read-length estimation -- i.e.
+everything the reference's entry points (callpeaks_interface.py:17-371) do
+before the first kernel runs.  The runs themselves are in
+tests/test_gpu_zz_interface.py."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+
+from graph_peak_caller_b200 import callpeaks_interface as ci
+from graph_peak_caller_b200.control.linearmap import LinearMap
+from graph_peak_caller_b200.conversion import load_graph
+from graph_peak_caller_b200.custom_exceptions import GraphNotFoundException
+from graph_peak_caller_b200.peakcollection import IntervalCollection
+from graph_peak_caller_b200.synthetic import make_graph, make_reads
+from oracle import ingest as oingest
+
+
+def args_of(**kw):
+    return types.SimpleNamespace(**kw)
+
+
+def write_graph_json(path, g, chunks=2):
+    src = np.repeat(np.arange(g.n_nodes), np.diff(g.succ_ptr))
+    with open(path, "w") as fh:
+        fh.write("\n".join(oingest.graph_to_vg_json(g.node_len, g.min_node, src, g.succ,
+                                                    chunks=chunks)) + "\n")
+    return str(path)
+
+
+def write_reads_json(path, g, reads):
+    with open(path, "w") as fh:
+        for i in range(len(reads)):
+            fh.write(json.dumps(oingest.read_to_alignment(
+                g.node_len, g.min_node, int(reads.start_off[i]), int(reads.end_off[i]),
+                reads.path[reads.path_ptr[i]:reads.path_ptr[i + 1]].tolist())) + "\n")
+    return str(path)
+
+
+def same_graph(a, b):
+    assert a.min_node == b.min_node
+    for f in ("node_len", "succ_ptr", "succ", "pred_ptr", "pred"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+
+
+def test_create_ob_graph_and_linear_map_files(tmp_path):
+    g = make_graph(8000, 0.05, seed=41, mnp_frac=0.1)
+    name = write_graph_json(tmp_path / "chr7.json", g)
+    # default output name: up to the first dot + .nobg (preprocess_interface.py:55-56)
+    out = ci.create_ob_graph(args_of(vg_json_file_name=name, out_file_name=None))
+    assert out == str(tmp_path / "chr7.nobg") and os.path.isfile(out)
+    same_graph(load_graph(out), g)
+    other = ci.create_ob_graph(args_of(vg_json_file_name=name,
+                                       out_file_name=str(tmp_path / "other.obg")))
+    same_graph(load_graph(other), g)
+    lm_name = str(tmp_path / "chr7_linear_map.npz")
+    ci.find_or_create_linear_map(load_graph(out), lm_name)
+    assert LinearMap.from_file(lm_name, g) == LinearMap.from_graph(g)
+    stamp = os.path.getmtime(lm_name)
+    ci.find_or_create_linear_map(load_graph(out), lm_name)        # found: left alone
+    assert os.path.getmtime(lm_name) == stamp
+
+
+def test_load_graph_errors(tmp_path):
+    with pytest.raises(GraphNotFoundException, match="not found"):
+        load_graph(str(tmp_path / "missing.nobg"))
+    foreign = str(tmp_path / "foreign.nobg")
+    with open(foreign, "wb") as fh:
+        np.savez(fh, blocks=np.arange(4))
+    with pytest.raises(GraphNotFoundException, match="create_ob_graph"):
+        load_graph(foreign)
+
+
+def test_read_lengths_and_estimate(tmp_path):
+    g = make_graph(20000, 0.05, seed=42, mnp_frac=0.1)
+    reads = make_reads(g, 500, 31, 120, seed=43)
+    want = [reads.interval(i, g).length() for i in range(len(reads))]
+    assert reads.lengths(g).tolist() == want
+    assert int(np.median(want)) == 31 and max(want) == 31      # reads at the graph end are cut
+    graph_file = ci.create_ob_graph(args_of(vg_json_file_name=write_graph_json(tmp_path / "g.json", g),
+                                            out_file_name=None))
+    assert ci.estimate_read_length(write_reads_json(tmp_path / "r.json", g, reads), graph_file) == 31
+    text = str(tmp_path / "r.intervalcollection")
+    IntervalCollection(list(reads)).to_file(text, text_file=True)
+    assert ci.estimate_read_length(text, graph_file) == 31
+
+
+def test_get_confiugration_and_intervals(tmp_path):
+    g = make_graph(3000, 0.05, seed=44)
+    reads = make_reads(g, 50, 20, 80, seed=45)
+    sample = write_reads_json(tmp_path / "s.json", g, reads)
+    a = args_of(control=None, linear_map=None, graph_file_name=str(tmp_path / "g.nobg"),
+                fragment_length="80", read_length="20", q_value_threshold="0.01",
+                sample=sample, graph=g)
+    config = ci.get_confiugration(a)
+    assert config.linear_map_name == str(tmp_path / "g_linear_map.npz")
+    assert (config.fragment_length, config.read_length, config.has_control) == (80, 20, False)
+    assert config.q_values_threshold == 0.01
+    a.linear_map, a.control = "given.npz", sample
+    config = ci.get_confiugration(a)
+    assert config.linear_map_name == "given.npz" and config.has_control
+    s, c = ci.get_intervals(a)
+    assert type(s).__name__ == type(c).__name__ == "UniqueIntervals"
+    assert len(s.batch) == len(c.batch) == len(reads)
+    with pytest.raises(SystemExit):
+        ci.parse_input_file(str(tmp_path / "nowhere.json"), g)
+
+
+def test_get_file_names(tmp_path):
+    for n in ("b2.nobg", "b1.nobg", "c.txt"):
+        (tmp_path / n).write_text("")
+    assert ci._get_file_names(None) is None
+    assert ci._get_file_names([str(tmp_path / "*.nobg")]) == [str(tmp_path / "b1.nobg"),
+                                                              str(tmp_path / "b2.nobg")]
+    assert ci._get_file_names(["z", "a"]) == ["a", "z"]
+    assert ci._get_file_names(["single"]) == ["single"]
+
+
+def _two_chromosomes(tmp_path):
+    out = {}
+    for k, chrom in enumerate(("1", "2")):
+        g = make_graph(6000 + 2000 * k, 0.04, seed=50 + k)
+        ci.create_ob_graph(args_of(vg_json_file_name=write_graph_json(tmp_path / ("%s.json" % chrom), g),
+                                   out_file_name=str(tmp_path / ("%s.nobg" % chrom))))
+        s = make_reads(g, 400, 20, 80, seed=60 + k, peak_frac=0.7, peak_spacing=2500)
+        c = make_reads(g, 600, 20, 80, seed=70 + k, peak_frac=0.0, dup_frac=0.0)
+        write_reads_json(tmp_path / ("sample_%s.json" % chrom), g, s)
+        write_reads_json(tmp_path / ("control_%s.json" % chrom), g, c)
+        out[chrom] = (g, s, c)
+    return out
+
+
+def test_prepare_callpeaks2(tmp_path):
+    data = _two_chromosomes(tmp_path)
+    d = str(tmp_path) + "/"
+    a = args_of(graph=[d + "*.nobg"], sample=[d + "sample_2.json", d + "sample_1.json"],
+                control=[d + "control_*.json"], fragment_length="80", read_length=None,
+                out_name=d + "run_", q_threshold="0.01", keep_duplicates="False",
+                genome_size="14000", unique_reads="700", stop_after_p_values="True")
+    caller = ci.prepare_callpeaks2(a)
+    assert caller.graph_file_names == [d + "1.nobg", d + "2.nobg"]
+    assert caller.samples == [d + "sample_1.json", d + "sample_2.json"]
+    assert caller.controls == [d + "control_1.json", d + "control_2.json"]
+    assert caller.names == ["1", "2"]                     # graph file names below data_dir, no extension
+    assert caller.linear_maps == [d + "1_linear_map.npz", d + "2_linear_map.npz"]
+    for chrom, lm in zip(("1", "2"), caller.linear_maps):
+        assert LinearMap.from_file(lm, data[chrom][0]) == LinearMap.from_graph(data[chrom][0])
+    config = caller._config
+    assert (config.fragment_length, config.read_length) == (80, 20)       # read length estimated
+    assert config.q_values_threshold == 0.01 and config.has_control and not config.keep_duplicates
+    assert config.global_min == 700 * 80 / 14000
+    assert caller.stop_after_p_values and caller._reporter._base_name == d + "run_"
+    # one graph: no extra experiment name; no control: the sample doubles as control
+    a1 = args_of(graph=[d + "1.nobg"], sample=[d + "sample_1.json"], control=None,
+                 fragment_length="80", read_length="20")
+    single = ci.prepare_callpeaks2(a1)
+    assert single.names == [""] and single.controls == single.samples
+    assert not single._config.has_control and single._config.global_min is None
+    assert single._reporter._base_name == "" and not single.stop_after_p_values
+    # the reference's hard stops
+    with pytest.raises(SystemExit):
+        ci.prepare_callpeaks2(args_of(graph=[d + "*.nobg"], sample=[d + "sample_1.json"],
+                                      control=None, fragment_length="80", read_length="20"))
+    with pytest.raises(SystemExit):
+        ci.prepare_callpeaks2(args_of(graph=[d + "1.nobg"], sample=[d + "sample_1.json"],
+                                      control=None, fragment_length="10", read_length="20"))
+    with pytest.raises(NotImplementedError, match="fragment_length"):
+        ci.prepare_callpeaks2(args_of(graph=[d + "1.nobg"], sample=[d + "sample_1.json"],
+                                      control=None, fragment_length=None, read_length="20"))
+
+
+def test_prepare_callpeaks_whole_genome(tmp_path):
+    _two_chromosomes(tmp_path)
+    d = str(tmp_path)
+    a = args_of(chromosomes="1,2", data_dir=d, sample=d + "/sample.json", control=None,
+                fragment_length="80", read_length="20", genome_size="14000", unique_reads="700",
+                out_name=None, keep_duplicates="True", stop_after_p_values="False")
+    caller = ci.prepare_callpeaks_whole_genome(a)
+    assert caller.names == ["1", "2"]
+    assert caller.graph_file_names == [d + "/1.nobg", d + "/2.nobg"]
+    assert caller.samples == [d + "/sample_1.json", d + "/sample_2.json"]
+    assert caller.controls == caller.samples and caller.controls is not caller.samples
+    assert caller.linear_maps == [d + "/1_linear_map.npz", d + "/2_linear_map.npz"]
+    assert all(os.path.isfile(f) for f in caller.linear_maps)
+    assert caller._config.keep_duplicates and not caller._config.has_control
+    assert caller._config.global_min == 4.0 and caller._reporter._base_name == ""
+    a.sample, a.control = d + "/reads_chrom.intervalcollection", d + "/control.json"
+    caller = ci.prepare_callpeaks_whole_genome(a)
+    assert caller.samples == [d + "/reads_1.intervalcollection", d + "/reads_2.intervalcollection"]
+    assert caller.controls == [d + "/control_1.json", d + "/control_2.json"]
+    assert caller._config.has_control
+
+
+def test_second_half_reads_the_reporters_files(tmp_path):
+    # state after p-values as the first half leaves it on disk (reporter.py:21-23,47-49 of the
+    # reference), picked up by a caller that was given no reads (multiplegraphscallpeaks.py:147-156)
+    from graph_peak_caller_b200 import Configuration
+    from graph_peak_caller_b200.multiplegraphscallpeaks import MultipleGraphsCallpeaks
+    from graph_peak_caller_b200.reporter import Reporter
+    from graph_peak_caller_b200.sparsediffs import SparseValues
+    g = make_graph(4000, 0.05, seed=81)
+    base = str(tmp_path / "wg_")
+    with open(str(tmp_path / "7.nobg"), "wb") as fh:
+        g.to_file(fh)
+    p = SparseValues(np.array([0, 10, 25]), np.array([0.0, 3.5, 0.0]))
+    p.track_size = g.size_bp
+    sub = Reporter(base).get_sub_reporter("7")
+    sub.add("pvalues", p)
+    sub.add("touched_nodes", {3, 1, 2})
+    config = Configuration()
+    config.read_length, config.fragment_length = 20, 80
+    caller = MultipleGraphsCallpeaks(["7"], [str(tmp_path / "7.nobg")], None, None, None, config,
+                                     Reporter(base))
+    assert caller.samples is None and caller.my_chromosomes() == [0]
+    state = caller._caller_from_files(0)
+    assert state.p_values_pileup == p and state.p_values_pileup.track_size == g.size_bp
+    assert sorted(state.touched_nodes.tolist()) == [1, 2, 3]
+    assert state._reporter._base_name == base + "7_" and state.direct_pileup is None
+    same_graph(state.graph, g)
