@@ -15,4 +15,7 @@ third-party ``offsetbasedgraph``) on the reference's own unit-test inputs and
 on randomised graphs by tests/test_oracle_vs_reference.py (runs wherever
 /root/reference exists), and with vectors generated from that reference and
 committed under tests/golden/ (tests/test_oracle_golden.py, runs everywhere).
+Exception: oracle/ingest.py (vg JSON -> reads / graph) restates the absent
+third-party package pyvg and is UNPINNED against it; its header lists the
+anchors the reference tree offers instead.
 """
