@@ -65,6 +65,18 @@ class MultipleGraphsCallpeaks:
                 self._graphs[i] = Graph.from_obg(g)
         return self._graphs[i]
 
+    def _costs(self):
+        """Packing weight per chromosome, identical on every rank: graph size in
+        base pairs -- or, when every graph is a file, the file sizes, so that a
+        rank only ever parses the graphs it works on."""
+        import os
+        names = self.graph_file_names
+        if all(isinstance(g, str) and os.path.isfile(g) for g in names):
+            kinds = {g.rsplit(".", 1)[-1] for g in names}
+            if len(kinds) == 1:                      # sizes of one format compare
+                return [os.path.getsize(g) for g in names]
+        return [self._graph(i).size_bp for i in range(len(names))]
+
     def my_chromosomes(self):
         """Indexes of the chromosomes this rank works on."""
         if self._mine is None:
@@ -72,8 +84,7 @@ class MultipleGraphsCallpeaks:
             if world == 1:
                 self._mine = list(range(len(self.names)))
             else:
-                sizes = [self._graph(i).size_bp for i in range(len(self.names))]
-                self._mine = sorted(multigraph.assign_chromosomes(sizes, world)[rank])
+                self._mine = sorted(multigraph.assign_chromosomes(self._costs(), world)[rank])
         return self._mine
 
     @classmethod

@@ -220,3 +220,26 @@ def test_second_half_reads_the_reporters_files(tmp_path):
     assert sorted(state.touched_nodes.tolist()) == [1, 2, 3]
     assert state._reporter._base_name == base + "7_" and state.direct_pileup is None
     same_graph(state.graph, g)
+
+
+def test_chromosome_costs_from_file_sizes(tmp_path):
+    # several ranks: graphs given as files are weighed by file size (no rank parses them all)
+    from graph_peak_caller_b200 import Configuration, multigraph
+    from graph_peak_caller_b200.multiplegraphscallpeaks import MultipleGraphsCallpeaks
+    from graph_peak_caller_b200.reporter import Reporter
+    files, graphs = [], []
+    for k, bp in enumerate((3000, 9000, 5000)):
+        g = make_graph(bp, 0.05, seed=90 + k)
+        files.append(write_graph_json(tmp_path / ("c%d.json" % k), g, chunks=1))
+        graphs.append(g)
+    config = Configuration()
+    config.read_length, config.fragment_length = 20, 80
+    by_file = MultipleGraphsCallpeaks(["a", "b", "c"], files, None, None, None, config, Reporter(None))
+    costs = by_file._costs()
+    assert costs == [os.path.getsize(f) for f in files] and by_file._graphs == {}
+    by_graph = MultipleGraphsCallpeaks(["a", "b", "c"], graphs, None, None, None, config,
+                                       Reporter(None))
+    assert by_graph._costs() == [g.size_bp for g in graphs]
+    # both weights pack these three the same way onto two ranks
+    assert multigraph.assign_chromosomes(costs, 2) == \
+        multigraph.assign_chromosomes(by_graph._costs(), 2) == [[1], [2, 0]]
