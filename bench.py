@@ -21,7 +21,8 @@ Regions, in order (GPU arm):
      (H2D of both read sets and D2H of the peaks inside the wall-clock region)
      -> `e2e`;
   5. rank 0, N == 1: the CPU port of the reference algorithm (oracle/) on a
-     bounded slice -> `cpu_baseline`.
+     bounded slice -> `cpu_baseline`; and the host-side ingest rate (vg alignment
+     JSON -> reads SoA, tools/ingest_rate.py) -> `ingest`.
 `--impl reference` runs only the CPU port (one process per chromosome, as the
 reference's README prescribes) and prints the same line with impl=reference.
 """
@@ -358,10 +359,15 @@ def main_ours(args):
                                   GBps=(v[2] / (v[1] / 1e3) / 1e9 if v[1] > 0 and v[2] > 0 else None))
                           for k, v in kt[:5]})
     cpu = None
+    ingest = None
     if world == 1 and not args.no_cpu:
         v, cms, cores, split = run_cpu(1, 1, 0)
         cpu = dict(value=v, unit="reads/s", cores=cores, kind="port",
                    sample=cpu_sample_text(1), stage_seconds=split)
+        # the row before the hot path, host only: vg alignment JSON -> reads SoA
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import ingest_rate
+        ingest = ingest_rate.measure()
     line = dict(metric="callpeaks_reads_per_sec", value=value, unit="reads/s", n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32+f64",
@@ -381,6 +387,8 @@ def main_ours(args):
                          note="CallPeaks.run(UniqueIntervals(host SoA), ...) incl. pinned H2D of "
                               "both read sets and D2H of the peaks; the graph is resident"),
                 roofline=roofline, cpu_baseline=cpu)
+    if ingest is not None:
+        line["ingest"] = ingest
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

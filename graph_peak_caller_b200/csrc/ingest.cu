@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -51,10 +52,15 @@ bool parse_int(Cursor& c, long long& out) {
 
 bool skip_string(Cursor& c) {               // c.p at the opening quote
     ++c.p;
-    while (!c.eof() && *c.p != '"') { if (*c.p == '\\') ++c.p; ++c.p; }
-    if (c.eof()) return false;
-    ++c.p;
-    return true;
+    while (true) {
+        const char* q = c.eof() ? nullptr : (const char*)memchr(c.p, '"', (size_t)(c.end - c.p));
+        if (!q) { c.p = c.end; return false; }
+        // the quote closes the string unless an odd number of backslashes precedes it
+        const char* b = q;
+        while (b > c.p && b[-1] == '\\') --b;
+        c.p = q + 1;
+        if (((q - b) & 1) == 0) return true;
+    }
 }
 
 bool skip_value(Cursor& c) {
@@ -75,10 +81,10 @@ bool skip_value(Cursor& c) {
     return true;
 }
 
-// One line.  `path` may be NULL (counting pass); returns the number of region
-// paths, or -1 on malformed input.
+// One line.  Region paths are appended to `path`; returns their number, or -1 on
+// malformed input (what was appended is then dropped by the caller).
 long long parse_line(const char* b, const char* e, long long& start, long long& stop,
-                     int32_t* path, long long& first, long long& last) {
+                     std::vector<int32_t>& path, long long& first, long long& last) {
     Cursor c{b, e};
     c.skip_ws();
     if (c.eof() || *c.p != '{') return -1;
@@ -117,7 +123,7 @@ long long parse_line(const char* b, const char* e, long long& start, long long& 
                 if (v > 2147483647ll || v < -2147483647ll) return -1;
                 if (n_path == 0) first = v;
                 last = v;
-                if (path) path[n_path] = (int32_t)v;
+                path.push_back((int32_t)v);
                 ++n_path;
             }
             have_path = true;
@@ -138,9 +144,6 @@ bool blank(const char* b, const char* e) {
 struct Chunk {
     const char* b;
     const char* e;
-    unsigned long long reads = 0, nodes = 0, empty = 0, lines = 0;
-    long long bad_line = -1;           // index of the first malformed line inside the chunk
-    int bad_kind = 0;                  // -1 malformed, -2 outside the graph
 };
 
 // Applies fn(line begin, line end) to every non-blank line of the chunk.
@@ -227,8 +230,9 @@ bool for_items(Cursor& c, Fn&& on_item) {
     }
 }
 
-inline bool key_is(const char* k, size_t n, const char* name) {
-    return strlen(name) == n && !memcmp(k, name, n);
+template <size_t N>
+inline bool key_is(const char* k, size_t n, const char (&name)[N]) {
+    return n == N - 1 && !memcmp(k, name, N - 1);
 }
 
 struct VgMapping {
@@ -264,8 +268,8 @@ bool parse_vg_mapping(Cursor& c, VgMapping& m) {
 // One alignment line.  Returns the number of mappings (0: no interval), -1 on malformed
 // input, -2 when a node lies outside [min_node, max_node] (checked when max_node > 0).
 long long parse_vg_line(const char* b, const char* e, long long min_node, long long max_node,
-                        long long& start, long long& stop, int32_t* path, long long& first,
-                        long long& last) {
+                        long long& start, long long& stop, std::vector<int32_t>& path,
+                        long long& first, long long& last) {
     Cursor c{b, e};
     long long n_path = 0;
     bool outside = false;
@@ -284,7 +288,7 @@ long long parse_vg_line(const char* b, const char* e, long long min_node, long l
                 const long long id = m.reverse ? -m.node : m.node;
                 if (n_path == 0) { first = id; start = m.offset; }
                 last = id;
-                if (path) path[n_path] = (int32_t)id;
+                path.push_back((int32_t)id);
                 ++n_path;
                 return true;
             });
@@ -297,31 +301,38 @@ long long parse_vg_line(const char* b, const char* e, long long min_node, long l
     return outside ? -2 : n_path;
 }
 
-// The two-pass driver both text formats share: pass 1 counts reads and path nodes per
-// chunk of lines, pass 2 lets every chunk fill its own range of the output arrays.
-// line_fn(begin, end, start, stop, path or NULL, first, last) returns the number of path
-// nodes, 0 for a line that holds no read, -1 for a malformed line, -2 for a read outside
-// the graph.
+// The driver both text formats share.  The buffer is cut into chunks of whole lines,
+// one host thread per chunk parses its lines ONCE into chunk-local arrays.  The
+// counting call (no output arrays) keeps that parse; the filling call for the same
+// buffer copies it out instead of parsing again (a filling call without a matching
+// counting call simply parses).  line_fn(begin, end, start, stop, path vector, first,
+// last) returns the number of path nodes it appended, 0 for a line that holds no read,
+// -1 for a malformed line, -2 for a read outside the graph.
+struct ParsedChunk {
+    std::vector<int32_t> start_node, start_off, end_node, end_off, n_path, path;
+    unsigned long long empty = 0, lines = 0;
+    long long bad_line = -1;           // index of the first bad line inside the chunk
+    int bad_kind = 0;                  // -1 malformed, -2 outside the graph
+};
+
+struct ParseCache {
+    const char* text = nullptr;
+    uint64_t n_bytes = 0;
+    int kind = 0;
+    long long lo = 0, hi = 0;
+    std::vector<ParsedChunk> chunks;
+};
+std::mutex g_parse_mutex;
+ParseCache g_parse_cache;              // at most one pending parse
+
 template <typename LineFn>
-int parse_reads_text(const char* what, const char* text, uint64_t n_bytes, int32_t n_threads,
-                     int32_t* start_node, int32_t* start_off, int32_t* end_node,
-                     int32_t* end_off, int64_t* path_ptr, int32_t* path, uint64_t* n_reads,
-                     uint64_t* n_path_nodes, uint64_t* n_empty, LineFn line_fn) {
-    const bool fill = start_node != nullptr;
-    const uint64_t want_reads = *n_reads, want_nodes = *n_path_nodes;
-    *n_reads = 0;
-    *n_path_nodes = 0;
-    if (n_empty) *n_empty = 0;
-    if (fill && (!start_off || !end_node || !end_off || !path_ptr || !path)) {
-        set_error("%s: all output arrays or none", what);
-        return GPC_ERR_ARG;
-    }
+void parse_chunks(const char* text, uint64_t n_bytes, int32_t n_threads, LineFn& line_fn,
+                  std::vector<ParsedChunk>& out) {
     unsigned threads = n_threads > 0 ? (unsigned)n_threads : std::thread::hardware_concurrency();
     if (threads == 0) threads = 1;
     if (threads > 64) threads = 64;
     if (n_bytes < (1u << 20)) threads = 1;
-    // chunks end at line ends
-    std::vector<Chunk> chunks;
+    std::vector<Chunk> chunks;         // chunks end at line ends
     const char* end = text + n_bytes;
     const char* p = text;
     for (unsigned t = 0; t < threads && p < end; ++t) {
@@ -337,32 +348,72 @@ int parse_reads_text(const char* what, const char* text, uint64_t n_bytes, int32
         chunks.push_back(ch);
         p = stop;
     }
-    // pass 1: reads and path nodes per chunk
-    {
-        std::vector<std::thread> pool;
-        for (auto& ch : chunks)
-            pool.emplace_back([&ch, &line_fn]() {
-                // counted in locals: neighbouring chunks share cache lines
-                unsigned long long reads = 0, nodes = 0, empty = 0;
-                long long line = 0, bad_line = -1;
-                int bad_kind = 0;
-                for_lines(ch, [&](const char* b, const char* e) {
-                    long long s, t, f, l;
-                    long long k = line_fn(b, e, s, t, (int32_t*)nullptr, f, l);
-                    if (k < 0) { if (bad_line < 0) { bad_line = line; bad_kind = (int)k; } }
-                    else if (k == 0) empty += 1;
-                    else { reads += 1; nodes += (unsigned long long)k; }
-                    ++line;
-                });
-                ch.reads = reads;
-                ch.nodes = nodes;
-                ch.empty = empty;
-                ch.bad_line = bad_line;
-                ch.bad_kind = bad_kind;
-                ch.lines = (unsigned long long)line;
+    out.clear();
+    out.resize(chunks.size());
+    std::vector<std::thread> pool;
+    for (size_t i = 0; i < chunks.size(); ++i)
+        pool.emplace_back([&chunks, &out, &line_fn, i]() {
+            ParsedChunk pc;            // filled locally, moved out at the end
+            const Chunk& ch = chunks[i];
+            const size_t guess = (size_t)(ch.e - ch.b) / 256 + 16;
+            pc.start_node.reserve(guess);
+            pc.start_off.reserve(guess);
+            pc.end_node.reserve(guess);
+            pc.end_off.reserve(guess);
+            pc.n_path.reserve(guess);
+            pc.path.reserve(3 * guess);
+            long long line = 0;
+            for_lines(ch, [&](const char* b, const char* e) {
+                long long s = 0, t = 0, f = 0, l = 0;
+                const size_t before = pc.path.size();
+                const long long k = line_fn(b, e, s, t, pc.path, f, l);
+                if (k <= 0) {
+                    pc.path.resize(before);
+                    if (k == 0) pc.empty += 1;
+                    else if (pc.bad_line < 0) { pc.bad_line = line; pc.bad_kind = (int)k; }
+                } else {
+                    pc.start_node.push_back((int32_t)f);
+                    pc.start_off.push_back((int32_t)s);
+                    pc.end_node.push_back((int32_t)l);
+                    pc.end_off.push_back((int32_t)t);
+                    pc.n_path.push_back((int32_t)k);
+                }
+                ++line;
             });
-        for (auto& th : pool) th.join();
+            pc.lines = (unsigned long long)line;
+            out[i] = std::move(pc);
+        });
+    for (auto& th : pool) th.join();
+}
+
+template <typename LineFn>
+int parse_reads_text(const char* what, int kind, long long lo, long long hi, const char* text,
+                     uint64_t n_bytes, int32_t n_threads, int32_t* start_node,
+                     int32_t* start_off, int32_t* end_node, int32_t* end_off, int64_t* path_ptr,
+                     int32_t* path, uint64_t* n_reads, uint64_t* n_path_nodes, uint64_t* n_empty,
+                     LineFn line_fn) {
+    const bool fill = start_node != nullptr;
+    const uint64_t want_reads = *n_reads, want_nodes = *n_path_nodes;
+    *n_reads = 0;
+    *n_path_nodes = 0;
+    if (n_empty) *n_empty = 0;
+    if (fill && (!start_off || !end_node || !end_off || !path_ptr || !path)) {
+        set_error("%s: all output arrays or none", what);
+        return GPC_ERR_ARG;
     }
+    std::vector<ParsedChunk> chunks;
+    bool have = false;
+    if (fill) {
+        std::lock_guard<std::mutex> lock(g_parse_mutex);
+        ParseCache& c = g_parse_cache;
+        if (c.text == text && c.n_bytes == n_bytes && c.kind == kind && c.lo == lo && c.hi == hi &&
+            text != nullptr) {
+            chunks.swap(c.chunks);
+            have = true;
+        }
+        c = ParseCache();
+    }
+    if (!have) parse_chunks(text, n_bytes, n_threads, line_fn, chunks);
     unsigned long long reads = 0, nodes = 0, empty = 0, lines_before = 0;
     for (auto& ch : chunks) {
         if (ch.bad_line >= 0) {
@@ -376,45 +427,55 @@ int parse_reads_text(const char* what, const char* text, uint64_t n_bytes, int32
             return GPC_ERR_ARG;
         }
         lines_before += ch.lines;
-        reads += ch.reads;
-        nodes += ch.nodes;
+        reads += ch.start_node.size();
+        nodes += ch.path.size();
         empty += ch.empty;
     }
     *n_reads = reads;
     *n_path_nodes = nodes;
     if (n_empty) *n_empty = empty;
-    if (!fill) return GPC_OK;
+    if (!fill) {
+        std::lock_guard<std::mutex> lock(g_parse_mutex);
+        ParseCache& c = g_parse_cache;
+        c.text = text;
+        c.n_bytes = n_bytes;
+        c.kind = kind;
+        c.lo = lo;
+        c.hi = hi;
+        c.chunks.swap(chunks);
+        return GPC_OK;
+    }
     if (want_reads < reads || want_nodes < nodes) return GPC_ERR_CAPACITY;
-    // pass 2: every chunk writes its own range
+    // every chunk copies into its own range
     {
         std::vector<std::thread> pool;
         unsigned long long r0 = 0, p0 = 0;
         for (auto& ch : chunks) {
-            pool.emplace_back([&ch, &line_fn, r0, p0, start_node, start_off, end_node, end_off,
-                               path_ptr, path]() {
-                unsigned long long r = r0, q = p0;
-                for_lines(ch, [&](const char* b, const char* e) {
-                    long long s = 0, t = 0, f = 0, l = 0;
-                    long long k = line_fn(b, e, s, t, path + q, f, l);
-                    if (k <= 0) return;
-                    start_node[r] = (int32_t)f;
-                    start_off[r] = (int32_t)s;
-                    end_node[r] = (int32_t)l;
-                    end_off[r] = (int32_t)t;
-                    path_ptr[r] = (int64_t)q;
-                    q += (unsigned long long)k;
-                    ++r;
-                });
+            pool.emplace_back([&ch, r0, p0, start_node, start_off, end_node, end_off, path_ptr,
+                               path]() {
+                const size_t r = ch.start_node.size();
+                if (r) {
+                    memcpy(start_node + r0, ch.start_node.data(), r * sizeof(int32_t));
+                    memcpy(start_off + r0, ch.start_off.data(), r * sizeof(int32_t));
+                    memcpy(end_node + r0, ch.end_node.data(), r * sizeof(int32_t));
+                    memcpy(end_off + r0, ch.end_off.data(), r * sizeof(int32_t));
+                }
+                if (!ch.path.empty())
+                    memcpy(path + p0, ch.path.data(), ch.path.size() * sizeof(int32_t));
+                unsigned long long q = p0;
+                for (size_t i = 0; i < r; ++i) {
+                    path_ptr[r0 + i] = (int64_t)q;
+                    q += (unsigned long long)ch.n_path[i];
+                }
             });
-            r0 += ch.reads;
-            p0 += ch.nodes;
+            r0 += ch.start_node.size();
+            p0 += ch.path.size();
         }
         for (auto& th : pool) th.join();
     }
     path_ptr[reads] = (int64_t)nodes;
     return GPC_OK;
 }
-
 
 // ---- vg graphs (`vg view -Vj`): {"node": [{"id", "sequence"}], "edge": [{"from", "to",
 // "from_start", "to_end"}], "path": [...]} -- one object per line, any number of lines.
@@ -514,10 +575,11 @@ extern "C" int gpc_parse_intervals_host(const char* text, uint64_t n_bytes, int3
                                         int32_t* end_node, int32_t* end_off, int64_t* path_ptr,
                                         int32_t* path, uint64_t* n_reads,
                                         uint64_t* n_path_nodes) {
-    return parse_reads_text("interval file", text, n_bytes, n_threads, start_node, start_off,
-                            end_node, end_off, path_ptr, path, n_reads, n_path_nodes, nullptr,
+    return parse_reads_text("interval file", 1, 0, 0, text, n_bytes, n_threads, start_node,
+                            start_off, end_node, end_off, path_ptr, path, n_reads, n_path_nodes,
+                            nullptr,
                             [](const char* b, const char* e, long long& s, long long& t,
-                               int32_t* path_out, long long& f, long long& l) {
+                               std::vector<int32_t>& path_out, long long& f, long long& l) {
                                 return parse_line(b, e, s, t, path_out, f, l);
                             });
 }
@@ -530,11 +592,11 @@ extern "C" int gpc_parse_vg_alignments_host(const char* text, uint64_t n_bytes,
                                             uint64_t* n_reads, uint64_t* n_path_nodes,
                                             uint64_t* n_without_path) {
     const long long lo = min_node, hi = max_node;
-    return parse_reads_text("vg alignment file", text, n_bytes, n_threads, start_node, start_off,
-                            end_node, end_off, path_ptr, path, n_reads, n_path_nodes,
+    return parse_reads_text("vg alignment file", 2, lo, hi, text, n_bytes, n_threads, start_node,
+                            start_off, end_node, end_off, path_ptr, path, n_reads, n_path_nodes,
                             n_without_path,
                             [lo, hi](const char* b, const char* e, long long& s, long long& t,
-                                     int32_t* path_out, long long& f, long long& l) {
+                                     std::vector<int32_t>& path_out, long long& f, long long& l) {
                                 return parse_vg_line(b, e, lo, hi, s, t, path_out, f, l);
                             });
 }

@@ -20,6 +20,15 @@ import json
 import numpy as np
 
 
+def _map_file(file_name):
+    """The bytes of a file as a read-only uint8 array without copying them
+    (memory-mapped; an empty file gives an empty array)."""
+    import os
+    if os.path.getsize(file_name) == 0:
+        return np.empty(0, dtype=np.uint8)
+    return np.memmap(file_name, dtype=np.uint8, mode="r")
+
+
 class Position:
     __slots__ = ("region_path_id", "offset")
 
@@ -186,7 +195,7 @@ class ReadBatch:
         import ctypes
         from . import _lib
         lib = _lib.load()
-        text = np.fromfile(file_name, dtype=np.uint8)
+        text = _map_file(file_name)
 
         def call(tp, out, n_reads, n_nodes):
             _lib.check(lib.gpc_parse_intervals_host(tp, text.size, int(n_threads), *out,
@@ -206,7 +215,7 @@ class ReadBatch:
         from . import _lib
         from .custom_exceptions import IntervalNotInGraphException, InvalidPileupInterval
         lib = _lib.load()
-        text = np.fromfile(file_name, dtype=np.uint8)
+        text = _map_file(file_name)
         lo, hi = (0, 0) if graph is None else (graph.min_node, graph.min_node + graph.n_nodes - 1)
         skipped = ctypes.c_uint64(0)
 

@@ -254,7 +254,10 @@ uint64_t gpc_profile_report(char* buf, uint64_t capacity);
  * All pointers are host pointers; `n_threads` <= 0 uses every host core.
  * Call once with all output arrays NULL to get the counts, allocate
  * (path_ptr: n_reads + 1), call again with *n_reads / *n_path_nodes set to the
- * capacities.  GPC_ERR_ARG on a malformed line (see gpc_last_error_string). */
+ * capacities.  The counting call keeps its parse and the filling call for the same
+ * (unchanged) buffer copies it out, so the text is scanned once; a filling call
+ * without a matching counting call parses on its own.  GPC_ERR_ARG on a malformed
+ * line (see gpc_last_error_string). */
 int gpc_parse_intervals_host(const char* text, uint64_t n_bytes, int32_t n_threads,
                              int32_t* start_node, int32_t* start_off, int32_t* end_node,
                              int32_t* end_off, int64_t* path_ptr, int32_t* path,

@@ -248,3 +248,16 @@ def test_multigraph_reads_the_references_file_kinds(tmp_path):
     same_batch(sample.batch, reads)
     same_batch(control.batch, reads)
     same_batch(caller.get_intervals(str(tmp_path / "reads_chr1.npz"), sample, g)[0].batch, reads)
+
+
+def test_ingest_rate_tool_reports_what_bench_prints():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
+    import ingest_rate
+    out = ingest_rate.measure(n_reads=3000, repeats=1, json_reads=500)
+    assert out["reads"] == 3000 and out["reads_per_sec"] > 0 and out["json_module_reads_per_sec"] > 0
+    json.dumps(out)
+    # the generated lines are what the restatement reads too
+    lines = ingest_rate.alignment_lines(200)
+    want = oingest.vg_json_lines_to_reads(lines)
+    assert len(want["start_node"]) == 200
