@@ -253,3 +253,17 @@ def max_paths(dgraph, pos, val, score_pos, score_val, q_pos, q_val, internal_id_
         out["arena"] = (arena, {name: (o, dtype, size, out[name].numel())
                                 for name, (o, dtype, size) in layout.items()})
         return out
+
+
+def peak_summits(dgraph, start, end, node_ptr, nodes, q_pos, q_val, window):
+    """Summits.  start / end int32[n], node_ptr int32[n + 1], nodes
+    int32[...] (node ids), q track (pos int32, val float64): all CUDA tensors.  Returns
+    int32[n, 6] = summit, length, first, last, start_off, end_off per peak."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    n = start.numel()
+    out = empty(6 * n, torch.int32)
+    _lib.check(lib.gpc_peak_summits(ctypes.byref(dgraph.c), ptr(start), ptr(end), ptr(node_ptr),
+                                    ptr(nodes), n, ptr(q_pos), ptr(q_val), q_pos.numel(),
+                                    int(window), ptr(out), stream_ptr()))
+    return out.view(n, 6)

@@ -137,3 +137,51 @@ class IntervalCollection:
 
 class PeakCollection(IntervalCollection):
     interval_class = Peak
+
+    def summits(self, q_values, n_base_pairs_around=60, graph=None):
+        """int32[n, 6] per peak: summit offset along the peak, peak length, and the
+        cut around the summit as (first node index, last node index, start offset,
+        end offset) -- kernel gpc_peak_summits over the run-length q-value track."""
+        import numpy as np
+        from . import kernels
+        from .device import device_graph, to_device
+        from .graph import Graph
+        peaks = list(self.intervals)
+        if not peaks:
+            return np.zeros((0, 6), dtype=np.int32)
+        graph = Graph.from_obg(graph if graph is not None else peaks[0].graph)
+        torch = kernels.torch_cuda()
+        start = np.array([p.start_position.offset for p in peaks], dtype=np.int32)
+        end = np.array([p.end_position.offset for p in peaks], dtype=np.int32)
+        ptr = np.zeros(len(peaks) + 1, dtype=np.int32)
+        np.cumsum([len(p.region_paths) for p in peaks], out=ptr[1:])
+        nodes = np.fromiter((r for p in peaks for r in p.region_paths), dtype=np.int32,
+                            count=int(ptr[-1]))
+        if nodes.size and nodes.min() < graph.min_node:
+            raise ValueError("summits are defined for forward peaks on nodes of the graph")
+        q_pos, q_val = q_values.device_arrays(torch.float64)
+        out = kernels.peak_summits(device_graph(graph), to_device(start), to_device(end),
+                                   to_device(ptr), to_device(nodes), q_pos, q_val,
+                                   int(n_base_pairs_around))
+        return out.cpu().numpy()
+
+    def cut_around_summit(self, q_values, n_base_pairs_around=60, graph=None):
+        """reference peakcollection.py:113-136: every peak is replaced by the part of
+        it within ``n_base_pairs_around`` of its summit, the median of the positions
+        with the highest q-value.  ``q_values`` is the ``SparseValues`` track of a run
+        (``CallPeaks.q_values_pileup`` or ``SparseValues.from_sparse_files(base +
+        "qvalues")``); no dense array is built."""
+        peaks = list(self.intervals)
+        cuts = self.summits(q_values, n_base_pairs_around, graph)
+        out = []
+        for peak, (summit, length, first, last, start_off, end_off) in zip(peaks, cuts.tolist()):
+            cut = Peak(start_off, end_off, peak.region_paths[first:last + 1],
+                       graph=peak.graph if peak.graph is not None else graph,
+                       score=peak.score, unique_id=peak.unique_id)
+            cut.info = peak.info
+            cut.chromosome = peak.chromosome
+            cut._length = min(summit + n_base_pairs_around, length) \
+                - max(0, summit - n_base_pairs_around)
+            assert cut._length <= n_base_pairs_around * 2
+            out.append(cut)
+        self.intervals = out

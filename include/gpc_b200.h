@@ -234,6 +234,23 @@ int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* 
                   uint64_t node_capacity, uint32_t* order, uint64_t* n_peaks,
                   uint64_t* n_nodes_total, void* stream);
 
+/* ---- summits  PeakCollection.cut_around_summit
+ *          (peakcollection.py:113-136) with the q-values read from the run-length
+ *          track instead of the dense array of analysis_interface.py:388-406 /
+ *          mindense.py:25-59 ------------------------------------------------------
+ * Peaks as gpc_max_paths returns them (start offset on the first node, end offset
+ * on the last node, node ids peak_nodes[peak_node_ptr[i] .. peak_node_ptr[i+1])).
+ * Per peak, out[6*i ..] = { summit, length, first, last, start_off, end_off }:
+ * summit = the (count // 2)-th smallest offset along the peak among the positions
+ * holding the peak's maximum q; the cut [max(0, summit - window), min(summit +
+ * window, length)) runs from start_off on node peak_nodes[ptr + first] to end_off
+ * on node peak_nodes[ptr + last].  Everything is device memory. */
+int gpc_peak_summits(const gpc_graph_t* graph, const int32_t* peak_start,
+                     const int32_t* peak_end, const uint32_t* peak_node_ptr,
+                     const int32_t* peak_nodes, uint64_t n_peaks, const uint32_t* q_pos,
+                     const double* q_val, uint64_t n_q, int32_t window, int32_t* out,
+                     void* stream);
+
 /* ---- measurement hooks (no reference counterpart) ---------------------------
  * gpc_launch_count: kernels launched by this library since it was loaded.
  * gpc_profile_enable(1): time every kernel launch with a CUDA event pair on

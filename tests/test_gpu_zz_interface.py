@@ -122,3 +122,52 @@ def test_whole_genome_in_two_halves(tmp_path):
         caller = ci.run_callpeaks_whole_genome_from_p_values(second)
         assert list(caller.peaks()) == [chrom]
         same_peaks(caller.peaks()[chrom], want[chrom])
+
+
+# ---- summits ---------------------------------------------------------
+
+def test_cut_around_summit_vs_oracle(tmp_path):
+    # the peaks and q-values of a run; every cut against the oracle's restatement of
+    # PeakCollection.cut_around_summit (pinned to the live reference in tests/test_summits.py)
+    from graph_peak_caller_b200.sparsediffs import SparseValues
+    from oracle import summits as osummits
+    g = make_graph(40000, 0.04, seed=120, mnp_frac=0.1)
+    s = make_reads(g, 4000, R, F, seed=121, peak_frac=0.7, peak_spacing=3000)
+    c = make_reads(g, 6000, R, F, seed=122, peak_frac=0.0, dup_frac=0.0)
+    config = Configuration()
+    config.read_length, config.fragment_length, config.has_control = R, F, True
+    config.linear_map_name = LinearMap.from_graph(g)
+    caller = CallPeaks(g, config, Reporter(str(tmp_path / "s_")))
+    caller.run(UniqueIntervals(s), UniqueIntervals(c))
+    peaks = caller.max_path_peaks
+    assert len(peaks) > 3
+    q = caller.q_values_pileup
+    dense = osummits.dense_track(q.indices, q.values, g.size_bp)
+    for window, track in ((60, q), (10, SparseValues.from_sparse_files(str(tmp_path / "s_qvalues")))):
+        collection = PeakCollection(list(peaks))
+        raw = collection.summits(track, window)
+        collection.cut_around_summit(track, window)
+        assert len(collection.intervals) == len(peaks)
+        for peak, row, cut in zip(peaks, raw.tolist(), collection.intervals):
+            summit, length, want = osummits.cut_around_summit(
+                g.node_off, g.node_len, g.min_node, dense, peak.start_position.offset,
+                peak.end_position.offset, list(peak.region_paths), window)
+            assert (row[0], row[1]) == (summit, length) and length == peak.length()
+            assert (cut.start_position.offset, cut.end_position.offset,
+                    list(cut.region_paths)) == want
+            assert cut.length() <= 2 * window and cut.score == peak.score
+
+
+def test_reference_known_answer_for_summits():
+    # reference tests/test_command_line_interface.py:121-137
+    from graph_peak_caller_b200.graph import Graph
+    from graph_peak_caller_b200.peakcollection import Peak
+    from graph_peak_caller_b200.sparsediffs import SparseValues
+    g = Graph({1: 7, 2: 4, 3: 7, 4: 4}, {1: [2, 3], 2: [4], 3: [4]})
+    qvalues = SparseValues(np.array([0]), np.array([3.0]))
+    qvalues.track_size = 22
+    collection = PeakCollection([Peak(0, 2, [1, 2], graph=g, score=3)])
+    collection.cut_around_summit(qvalues, 2)
+    cut = collection.intervals[0]
+    assert (cut.start_position.offset, cut.end_position.offset, cut.region_paths) == (2, 6, [1])
+    assert PeakCollection([]).summits(qvalues).shape == (0, 6)
