@@ -1,13 +1,28 @@
 """``Reporter``: the on-disk contract of the reference
-(graph_peak_caller/reporter.py:7-65).  Every intermediate track goes to
-``<base>X_indexes.npy`` / ``<base>X_values.npy``; peaks to JSON lines.  A
-reporter with ``base_name=None`` keeps everything in memory (nothing is
-written), which is what the benchmark uses."""
+(graph_peak_caller/reporter.py:7-65).  ``add(name, data)`` writes what the
+reference writes under the same file names:
+
+* tracks -> ``<base><name>_indexes.npy`` / ``<base><name>_values.npy``
+  (``to_sparse_files``): qvalues, pvalues, hole_cleaned, fragment_pileup,
+  background_track, direct_pileup;
+* peak lists -> ``<base><name>.intervalcollection`` (one JSON object per line):
+  all_max_paths, max_paths;
+* touched_nodes -> ``<base>touched_nodes.npy``.
+
+Anything else is kept but not written -- "thresholded" among them: the
+reference's writer for it is spelt ``thersholded`` and is never found by its
+``add`` (reporter.py:41-42,52-57); neither are sub_graphs produced here.  A reporter with
+``base_name=None`` keeps everything in memory only, which is what the benchmark
+uses; ``memory`` holds the last object reported under every name either way."""
 import logging
 
 import numpy as np
 
 from .peakcollection import PeakCollection
+
+TRACKS = frozenset(("qvalues", "pvalues", "hole_cleaned", "fragment_pileup",
+                    "background_track", "direct_pileup"))
+PEAK_LISTS = frozenset(("all_max_paths", "max_paths"))
 
 
 class Reporter:
@@ -15,48 +30,27 @@ class Reporter:
         self._base_name = base_name
         self.memory = {}
 
-    def qvalues(self, data):
-        data.to_sparse_files(self._base_name + "qvalues")
-
-    def pvalues(self, data):
-        data.to_sparse_files(self._base_name + "pvalues")
-
-    def all_max_paths(self, data):
-        PeakCollection(data).to_file(self._base_name + "all_max_paths.intervalcollection",
-                                     text_file=True)
-
-    def max_paths(self, data):
-        PeakCollection(data).to_file(self._base_name + "max_paths.intervalcollection",
-                                     text_file=True)
-
-    def hole_cleaned(self, data):
-        data.to_sparse_files(self._base_name + "hole_cleaned")
-
-    def fragment_pileup(self, data):
-        data.to_sparse_files(self._base_name + "fragment_pileup")
-
-    def background_track(self, data):
-        data.to_sparse_files(self._base_name + "background_track")
-
-    def thersholded(self, data):      # sic: the reference never writes "thresholded"
-        data.to_sparse_files(self._base_name + "thresholded")
-
-    def direct_pileup(self, data):
-        data.to_sparse_files(self._base_name + "direct_pileup")
-
-    def touched_nodes(self, data):
-        np.save(self._base_name + "touched_nodes.npy", np.array(list(data), dtype="int"))
+    def _write(self, name, data):
+        if name in TRACKS:
+            data.to_sparse_files(self._base_name + name)
+        elif name in PEAK_LISTS:
+            PeakCollection(data).to_file(self._base_name + name + ".intervalcollection",
+                                         text_file=True)
+        elif name == "touched_nodes":
+            np.save(self._base_name + "touched_nodes.npy", np.array(list(data), dtype="int"))
+        else:
+            return False
+        return True
 
     def add(self, name, data):
         self.memory[name] = data
-        if self._base_name is not None and hasattr(self, name) and name != "memory":
-            getattr(self, name)(data)
+        if self._base_name is not None and self._write(name, data):
             logging.info("Wrote %s to file", name)
         else:
             logging.info("Skipping reporting of %s", name)
 
     def get_sub_reporter(self, name):
-        if name != "":
-            name += "_"
-        base = None if self._base_name is None else self._base_name + name
-        return self.__class__(base)
+        """Reporter of one chromosome: ``<base><name>_`` (the empty name adds nothing)."""
+        if self._base_name is None:
+            return self.__class__(None)
+        return self.__class__(self._base_name + (name + "_" if name != "" else ""))

@@ -243,3 +243,37 @@ def test_chromosome_costs_from_file_sizes(tmp_path):
     # both weights pack these three the same way onto two ranks
     assert multigraph.assign_chromosomes(costs, 2) == \
         multigraph.assign_chromosomes(by_graph._costs(), 2) == [[1], [2, 0]]
+
+
+def test_reporter_file_contract(tmp_path):
+    # the file names of the reference's Reporter (reporter.py:17-57)
+    from graph_peak_caller_b200.peakcollection import Peak, PeakCollection
+    from graph_peak_caller_b200.reporter import Reporter
+    from graph_peak_caller_b200.sparsediffs import SparseValues
+    g = make_graph(2000, 0.05, seed=77)
+    base = str(tmp_path / "run_")
+    rep = Reporter(base).get_sub_reporter("chr3")
+    assert rep._base_name == base + "chr3_" and Reporter(base).get_sub_reporter("")._base_name == base
+    track = SparseValues(np.array([0, 5, 9]), np.array([0.0, 2.0, 0.0]))
+    track.track_size = g.size_bp
+    for name in ("qvalues", "pvalues", "hole_cleaned", "fragment_pileup", "background_track",
+                 "direct_pileup", "thresholded"):
+        rep.add(name, track)
+    peaks = [Peak.from_flat(1, 3, [1, 2], g, 2.5, (False, False), 5)]
+    rep.add("all_max_paths", peaks)
+    rep.add("max_paths", peaks)
+    rep.add("touched_nodes", {2, 1})
+    written = sorted(os.listdir(tmp_path))
+    want = ["run_chr3_%s_%s.npy" % (n, k) for n in ("qvalues", "pvalues", "hole_cleaned",
+            "fragment_pileup", "background_track", "direct_pileup") for k in ("indexes", "values")]
+    want += ["run_chr3_all_max_paths.intervalcollection", "run_chr3_max_paths.intervalcollection",
+             "run_chr3_touched_nodes.npy"]
+    assert written == sorted(want)                    # "thresholded" is kept but not written
+    assert rep.memory["thresholded"] is track
+    assert SparseValues.from_sparse_files(base + "chr3_qvalues") == track
+    back = PeakCollection.from_file(base + "chr3_max_paths.intervalcollection", graph=g)
+    assert back.intervals[0] == peaks[0] and back.intervals[0].score == 2.5
+    assert sorted(np.load(base + "chr3_touched_nodes.npy").tolist()) == [1, 2]
+    quiet = Reporter(None)
+    quiet.add("qvalues", track)
+    assert quiet.memory["qvalues"] is track and quiet.get_sub_reporter("x")._base_name is None
