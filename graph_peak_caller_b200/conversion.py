@@ -94,8 +94,11 @@ def split_vg_json_reads_into_chromosomes(chromosomes, reads_file_name, range_fil
     """Shards an alignment file by chromosome (preprocess_interface.py:83-145):
     a line goes to ``<base>_<chrom>.json`` of the first chromosome whose
     ``node_range_<chrom>.txt`` (``first:last``) holds the first node id found in
-    the line, else to ``<base>_unmapped.json``.  Returns the number of lines
-    that went to ``unmapped``."""
+    the line, else to ``<base>_unmapped.json`` (a node beyond every range makes the
+    reference fail with KeyError on the limits of "unmapped", :102,113-114; here
+    the line goes where its log message says).  Returns the number of lines that
+    went to ``unmapped``.  Byte-identical files with the live reference:
+    tests/test_ingest_vg.py."""
     if isinstance(chromosomes, str):
         chromosomes = chromosomes.split(",")
     base = ".".join(reads_file_name.split(".")[0:-1])

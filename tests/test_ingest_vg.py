@@ -261,3 +261,46 @@ def test_ingest_rate_tool_reports_what_bench_prints():
     lines = ingest_rate.alignment_lines(200)
     want = oingest.vg_json_lines_to_reads(lines)
     assert len(want["start_node"]) == 200
+
+
+def test_splitter_equals_the_live_reference(tmp_path):
+    # preprocess_interface.split_vg_json_reads_into_chromosomes of the unmodified reference
+    # (build container only) writes byte-identical files
+    import shutil
+    import types
+    from oracle import refbridge
+    if not refbridge.available():
+        pytest.skip("/root/reference not present")
+    refbridge._ref()
+    from graph_peak_caller import preprocess_interface
+    extra = [json.dumps({"path": {"mapping": [{"position": {"node_id": str(k) if k % 2 else k},
+                                               "edit": [{"from_length": 1}]}]}})
+             for k in (5, 15477266, 15477267)] + ['{"sequence": "ACGT"}']
+    # (a node beyond every range makes the reference look up the limits of "unmapped" and
+    # fail with KeyError, preprocess_interface.py:102,113-114; here such a line goes to the
+    # unmapped file as the reference's log message intends -- covered below, not compared)
+    with open(os.path.join(GOLDEN, "vg_alignments_15.json")) as fh:
+        lines = fh.read().splitlines() + extra
+    ranges = ["1:9029588", "9029589:15477266", "15477267:23090691", "23090692:29187850",
+              "29187851:37071876"]
+    outs = []
+    for side in ("mine", "reference"):
+        d = tmp_path / side
+        d.mkdir()
+        for i, text in enumerate(ranges, 1):
+            (d / ("node_range_%d.txt" % i)).write_text(text)
+        reads = write_lines(d / "vg_alignments.json", lines)
+        if side == "mine":
+            unmapped = conversion.split_vg_json_reads_into_chromosomes("1,2,3,4,5", reads,
+                                                                       str(d) + "/")
+            assert unmapped == 1
+        else:
+            preprocess_interface.split_vg_json_reads_into_chromosomes(types.SimpleNamespace(
+                chromosomes="1,2,3,4,5", vg_json_reads_file_name=reads,
+                range_files_base_name=str(d) + "/"))
+        outs.append({f: (d / f).read_bytes() for f in sorted(os.listdir(d))})
+    assert outs[0] == outs[1] and len(outs[0]) == 12
+    beyond = write_lines(tmp_path / "mine" / "far.json", [
+        json.dumps({"path": {"mapping": [{"position": {"node_id": 40000000}}]}})])
+    assert conversion.split_vg_json_reads_into_chromosomes("1,2", beyond, str(tmp_path / "mine") + "/") == 1
+    assert (tmp_path / "mine" / "far_unmapped.json").read_text().count("\n") == 1
