@@ -277,3 +277,86 @@ def test_reporter_file_contract(tmp_path):
     quiet = Reporter(None)
     quiet.add("qvalues", track)
     assert quiet.memory["qvalues"] is track and quiet.get_sub_reporter("x")._base_name is None
+
+
+def test_helpers_equal_the_live_reference(tmp_path):
+    # callpeaks_interface._get_file_names / get_confiugration of the unmodified reference
+    from oracle import refbridge
+    if not refbridge.available():
+        pytest.skip("/root/reference not present")
+    refbridge._ref()
+    from graph_peak_caller import callpeaks_interface as ref
+    for n in ("b2.nobg", "b1.nobg", "a.json"):
+        (tmp_path / n).write_text("")
+    for pattern in (None, [str(tmp_path / "*.nobg")], ["z", "a", "m"], ["only"],
+                    [str(tmp_path / "nothing*")]):
+        assert ci._get_file_names(pattern) == ref._get_file_names(pattern)
+    for control, linear_map in ((None, None), ("c.json", "lm.npz")):
+        a = args_of(control=control, linear_map=linear_map, graph_file_name="dir/chr1.nobg",
+                    fragment_length="135", read_length="36", q_value_threshold=None)
+        mine, theirs = ci.get_confiugration(a), ref.get_confiugration(a)
+        for field in ("has_control", "linear_map_name", "fragment_length", "read_length",
+                      "q_values_threshold", "global_min", "keep_duplicates"):
+            assert getattr(mine, field) == getattr(theirs, field), field
+
+
+class _Recorder:
+    """Stands in for the reference's MultipleGraphsCallpeaks: keeps what it was given."""
+    last = None
+
+    def __init__(self, names, graphs, samples, controls, linear_maps, config, reporter,
+                 sequence_retrievers=None, stop_after_p_values=False, **kw):
+        type(self).last = dict(names=list(names), graphs=list(graphs), samples=list(samples),
+                               controls=list(controls), linear_maps=list(linear_maps),
+                               config=dict(config.__dict__), base=reporter._base_name,
+                               stop=stop_after_p_values)
+
+    def run(self):
+        pass
+
+
+def _seen(caller):
+    return dict(names=caller.names, graphs=caller.graph_file_names, samples=caller.samples,
+                controls=caller.controls, linear_maps=caller.linear_maps,
+                config=dict(caller._config.__dict__), base=caller._reporter._base_name,
+                stop=caller.stop_after_p_values)
+
+
+def test_run_preparation_equals_the_live_reference(tmp_path, monkeypatch):
+    # what run_callpeaks2 / run_callpeaks_whole_genome of the unmodified reference hand to
+    # MultipleGraphsCallpeaks, against what the entry points here hand to theirs
+    from oracle import refbridge
+    if not refbridge.available():
+        pytest.skip("/root/reference not present")
+    refbridge._ref()
+    from graph_peak_caller import callpeaks_interface as ref
+    monkeypatch.setattr(ref, "MultipleGraphsCallpeaks", _Recorder)
+    _two_chromosomes(tmp_path)
+    monkeypatch.chdir(tmp_path)
+    for chrom in ("1", "2"):                    # present, so that neither side has to build them
+        ci.create_linear_map(load_graph(chrom + ".nobg"), chrom + "_linear_map.npz")
+    cases = [
+        dict(graph=["*.nobg"], sample=["sample_1.json", "sample_2.json"],
+             control=["control_2.json", "control_1.json"], fragment_length="80", read_length="20",
+             out_name="x_", q_threshold="0.2", keep_duplicates="True", genome_size="14000",
+             unique_reads="700", stop_after_p_values="True", min_fold_enrichment=None,
+             max_fold_enrichment=None),
+        dict(graph=["1.nobg"], sample=["sample_1.json"], control=None, fragment_length="80",
+             read_length="20", out_name=None, q_threshold=None, keep_duplicates="False",
+             genome_size=None, unique_reads=None, stop_after_p_values="False",
+             min_fold_enrichment=None, max_fold_enrichment=None),
+    ]
+    for case in cases:
+        ref.run_callpeaks2(args_of(**case))
+        assert _seen(ci.prepare_callpeaks2(args_of(**case))) == _Recorder.last
+    whole = [
+        dict(chromosomes="1,2", data_dir=".", sample="sample.json", control="control.json",
+             fragment_length="80", read_length="20", genome_size="14000", unique_reads="700",
+             out_name="wg_", keep_duplicates="False", stop_after_p_values="True"),
+        dict(chromosomes="2", data_dir=".", sample="reads_chrom.intervalcollection", control=None,
+             fragment_length="80", read_length="20", genome_size="14000", unique_reads="700",
+             out_name=None, keep_duplicates="True", stop_after_p_values="False"),
+    ]
+    for case in whole:
+        ref.run_callpeaks_whole_genome(args_of(**case))
+        assert _seen(ci.prepare_callpeaks_whole_genome(args_of(**case))) == _Recorder.last
