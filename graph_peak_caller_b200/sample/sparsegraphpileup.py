@@ -55,7 +55,10 @@ def touched_mask(touched_nodes, graph):
         return touched_nodes.mask
     from ..device import to_device
     mask = np.zeros(graph.n_nodes, dtype=np.uint8)
-    ids = np.fromiter((int(t) for t in touched_nodes), dtype=np.int64)
+    if isinstance(touched_nodes, np.ndarray):          # e.g. np.load of the Reporter's file
+        ids = touched_nodes.astype(np.int64).ravel()
+    else:
+        ids = np.fromiter((int(t) for t in touched_nodes), dtype=np.int64)
     mask[ids - graph.min_node] = 1
     return to_device(mask)
 
