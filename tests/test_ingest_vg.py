@@ -304,3 +304,96 @@ def test_splitter_equals_the_live_reference(tmp_path):
         json.dumps({"path": {"mapping": [{"position": {"node_id": 40000000}}]}})])
     assert conversion.split_vg_json_reads_into_chromosomes("1,2", beyond, str(tmp_path / "mine") + "/") == 1
     assert (tmp_path / "mine" / "far_unmapped.json").read_text().count("\n") == 1
+
+
+def test_scanner_on_random_json(tmp_path):
+    # random junk around the path (nested containers, escapes, unicode, numbers in every
+    # notation the json module writes), random key order and separators: the structure-aware
+    # scanner must see what the json module sees
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    scalars = st.one_of(st.none(), st.booleans(), st.integers(-10**12, 10**12),
+                        st.floats(allow_nan=False, allow_infinity=False), st.text(max_size=12))
+    junk = st.recursive(scalars, lambda kids: st.one_of(
+        st.lists(kids, max_size=3), st.dictionaries(st.text(max_size=8), kids, max_size=3)),
+        max_leaves=8)
+    position = st.fixed_dictionaries(
+        {"node_id": st.integers(1, 2**31 - 1)},
+        optional={"offset": st.integers(0, 5000), "is_reverse": st.booleans(), "name": st.text(max_size=5)})
+    edit = st.fixed_dictionaries({}, optional={"from_length": st.integers(0, 300),
+                                                "to_length": st.integers(0, 300),
+                                                "sequence": st.text("ACGT", max_size=6)})
+    mapping = st.fixed_dictionaries({"position": position},
+                                    optional={"edit": st.lists(edit, max_size=3),
+                                              "rank": st.integers(1, 50), "extra": junk})
+    alignment = st.fixed_dictionaries(
+        {}, optional={"path": st.fixed_dictionaries({}, optional={
+            "mapping": st.lists(mapping, max_size=4), "name": st.text(max_size=6)}),
+            "sequence": st.text(max_size=20), "refpos": junk, "fragment_next": junk,
+            "annotation": junk, "mapping": junk, "position": junk})
+
+    def dump(obj, rng_bits):
+        keys = list(obj)
+        if rng_bits & 1:
+            keys.reverse()
+        sep = ((",", ":"), (", ", ": "), (" ,  ", " :  "))[(rng_bits >> 1) % 3]
+        return json.dumps({k: obj[k] for k in keys}, separators=sep,
+                          ensure_ascii=bool(rng_bits & 8))
+
+    name = str(tmp_path / "fuzz.json")
+
+    @settings(max_examples=150, deadline=None,
+              suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(st.lists(st.tuples(alignment, st.integers(0, 15)), min_size=1, max_size=6))
+    def run(items):
+        lines = [dump(obj, bits) for obj, bits in items]
+        with open(name, "w", encoding="utf-8") as fh:
+            fh.write("\n".join(lines) + "\n")
+        want = oingest.vg_json_lines_to_reads(lines)
+        got = ReadBatch.from_vg_json_file(name)
+        same_batch(got, want)
+        assert got.n_without_path == want["n_without_path"]
+
+    run()
+
+
+def test_graph_scanner_on_random_json(tmp_path):
+    import ctypes
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from graph_peak_caller_b200 import _lib
+    scalars = st.one_of(st.none(), st.booleans(), st.integers(-10**9, 10**9), st.text(max_size=10))
+    junk = st.recursive(scalars, lambda kids: st.one_of(
+        st.lists(kids, max_size=3), st.dictionaries(st.text(max_size=6), kids, max_size=3)),
+        max_leaves=6)
+    ident = st.one_of(st.integers(1, 2**31 - 1), st.integers(1, 2**31 - 1).map(str))
+    node = st.fixed_dictionaries({"id": ident}, optional={
+        "sequence": st.text("ACGTN\\\"é", max_size=12), "name": st.text(max_size=4)})
+    edge = st.fixed_dictionaries({"from": ident, "to": ident}, optional={
+        "from_start": st.booleans(), "to_end": st.booleans(), "overlap": st.integers(0, 3)})
+    chunk = st.fixed_dictionaries({}, optional={"node": st.lists(node, max_size=5),
+                                                "edge": st.lists(edge, max_size=5),
+                                                "path": junk, "other": junk})
+    name = str(tmp_path / "fuzz_graph.json")
+    lib = _lib.load()
+
+    @settings(max_examples=120, deadline=None,
+              suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(st.lists(chunk, min_size=1, max_size=4), st.booleans())
+    def run(chunks, ascii_only):
+        lines = [json.dumps(c, ensure_ascii=ascii_only) for c in chunks]
+        ids, lens, src, dst = oingest.vg_graph_lines_to_lists(lines)
+        text = np.frombuffer(("\n".join(lines) + "\n").encode("utf-8"), dtype=np.uint8)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        n, m = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _lib.check(lib.gpc_parse_vg_graph_host(vp(text), text.size, None, None, ctypes.byref(n),
+                                               None, None, ctypes.byref(m)))
+        assert (n.value, m.value) == (len(ids), len(src))
+        out = [np.zeros(max(k, 1), dtype=np.int32) for k in (len(ids), len(ids), len(src), len(src))]
+        _lib.check(lib.gpc_parse_vg_graph_host(vp(text), text.size, vp(out[0]), vp(out[1]),
+                                               ctypes.byref(n), vp(out[2]), vp(out[3]),
+                                               ctypes.byref(m)))
+        assert out[0][:len(ids)].tolist() == ids and out[2][:len(src)].tolist() == src
+        assert out[3][:len(src)].tolist() == dst
+        if ascii_only:          # escapes count as one character each; raw UTF-8 counts bytes
+            assert out[1][:len(ids)].tolist() == lens
+
+    run()
