@@ -67,6 +67,7 @@ _SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, P(u64), P(u64), P(u64)],
     "gpc_parse_vg_graph_host": [c_void_p, u64, c_void_p, c_void_p, P(u64), c_void_p, c_void_p,
                                 P(u64)],
+    "gpc_parse_vg_sequences_host": [c_void_p, u64, c_void_p, c_void_p, c_void_p, P(u64), P(u64)],
     "gpc_linear_map_from_graph_host": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        u64, c_void_p, c_void_p],
     "gpc_sort_u32": [c_void_p, c_void_p, u64, i32, i32, P(i32), c_void_p],

@@ -21,8 +21,9 @@ all outside the data-parallel path:
   works: it is an npz container), or a vg graph in JSON form (``*.json``).
   offsetbasedgraph's own binary ``.nobg`` needs that package and is refused
   with a message that says so;
-* no sequence graphs: ``sequences.fasta`` is not written (peaks go to the
-  ``*max_paths.intervalcollection`` files of the Reporter as in the reference);
+* sequence graphs (``<graph file>.sequences``, written by ``create_ob_graph`` from
+  the vg JSON) are this package's flat ``SequenceGraph``; with them the runs write
+  ``sequences.fasta`` as the reference does;
 * no fragment-length estimation: ``fragment_length`` must be given.
 """
 import logging
@@ -39,11 +40,24 @@ from .intervals import UniqueIntervals
 from .multiplegraphscallpeaks import MultipleGraphsCallpeaks
 from .peakcollection import IntervalCollection
 from .reads import ReadBatch
+from .peakfasta import PeakFasta
 from .reporter import Reporter
+from .sequencegraph import SequenceGraph
 
 
 def _arg(args, name, default=None):
     return getattr(args, name, default)
+
+
+class _SequenceGraphFiles:
+    """Sequence graphs by chromosome index, read when asked for (the reference hands
+    MultipleGraphsCallpeaks a generator over the same files, :156-159,277-279)."""
+
+    def __init__(self, file_names):
+        self.file_names = list(file_names)
+
+    def get(self, i):
+        return SequenceGraph.from_file(self.file_names[i])
 
 
 def create_ob_graph(args):
@@ -56,6 +70,9 @@ def create_ob_graph(args):
     with open(out_name, "wb") as fh:           # a file object: numpy keeps the name as it is
         graph.to_file(fh)
     logging.info("Wrote graph to %s" % out_name)
+    # the node sequences next to it, as the reference does (preprocess_interface.py:64-68)
+    SequenceGraph.from_vg_json_file(args.vg_json_file_name, graph).to_file(out_name + ".sequences")
+    logging.info("Wrote sequence graph to %s" % (out_name + ".sequences"))
     return out_name
 
 
@@ -136,8 +153,15 @@ def run_callpeaks_interface(args):
     caller = get_callpeaks(args)
     inputs, controls = get_intervals(args)
     caller.run(inputs, controls)
+    outname = args.out_name if _arg(args, "out_name") is not None else ""
     if _arg(args, "sequence_graph") is not None:
-        logging.warning("Sequence graphs are outside this path: not writing sequences.fasta")
+        sequence_graph = args.sequence_graph
+        if isinstance(sequence_graph, str):         # a file name: <graph file>.sequences
+            sequence_graph = SequenceGraph.from_file(sequence_graph, graph=args.graph)
+        PeakFasta(sequence_graph).write_max_path_sequences(outname + "sequences.fasta",
+                                                           caller.max_path_peaks)
+    else:
+        logging.info("Not saving max path sequences, since a sequence graph was not found.")
     return caller
 
 
@@ -227,6 +251,7 @@ def prepare_callpeaks2(args):
     config.has_control = _arg(args, "control") is not None
     return MultipleGraphsCallpeaks(
         names, graphs, samples, controls, linear_map_file_names, config, Reporter(out_name),
+        sequence_retrievers=_SequenceGraphFiles(fn + ".sequences" for fn in graphs),
         stop_after_p_values=_arg(args, "stop_after_p_values") == "True")
 
 
@@ -277,6 +302,8 @@ def prepare_callpeaks_whole_genome(args):
     return MultipleGraphsCallpeaks(
         chromosomes, graph_file_names, sample_file_names, control_file_names,
         linear_map_file_names, config, Reporter(out_name),
+        sequence_retrievers=_SequenceGraphFiles(
+            args.data_dir + "/" + chrom + ".nobg.sequences" for chrom in chromosomes),
         stop_after_p_values=_arg(args, "stop_after_p_values") == "True")
 
 
@@ -308,8 +335,10 @@ def run_callpeaks_whole_genome_from_p_values(args):
         logging.info("Running with q value threshold %.3f" % config.q_values_threshold)
     config.fragment_length = int(args.fragment_length)
     config.read_length = int(args.read_length)
-    caller = MultipleGraphsCallpeaks([chromosome], graph_file_names, None, None, None, config,
-                                     Reporter(out_name))
+    caller = MultipleGraphsCallpeaks(
+        [chromosome], graph_file_names, None, None, None, config, Reporter(out_name),
+        sequence_retrievers=_SequenceGraphFiles(
+            [args.data_dir + "/" + chromosome + ".nobg.sequences"]))
     caller.create_joined_q_value_mapping()
     caller.run_from_p_values(only_chromosome=chromosome)
     return caller

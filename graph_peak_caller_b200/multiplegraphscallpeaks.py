@@ -191,6 +191,39 @@ class MultipleGraphsCallpeaks:
             caller.p_to_q_values_mapping = self._q_value_mapping
             caller.get_q_values()
             caller.call_peaks_from_q_values()
+            self._write_sequences(i, caller)
+
+    def _sequence_graph(self, i):
+        """The sequence graph of chromosome i, or None.  ``sequence_retrievers`` may be
+        indexable by chromosome (list, or an object with ``get(i)``: what the entry points
+        of callpeaks_interface.py pass) or, as in the reference, an iterator consumed in
+        chromosome order (single process only)."""
+        source = self.sequence_retrievers
+        if source is None:
+            return None
+        if hasattr(source, "get"):
+            return source.get(i)
+        if isinstance(source, (list, tuple)):
+            return source[i]
+        return next(source)
+
+    def _write_sequences(self, i, caller):
+        """``<base><name>_sequences.fasta`` (reference multiplegraphscallpeaks.py:157-166);
+        a missing sequence file is a warning, not an error."""
+        if self.sequence_retrievers is None or self._reporter._base_name is None:
+            return
+        try:
+            sequence_graph = self._sequence_graph(i)
+        except FileNotFoundError:
+            logging.warning("Could not find sequence graphs. Will not store max paths.")
+            return
+        if sequence_graph is None:
+            return
+        from .peakfasta import PeakFasta
+        name = self.names[i]
+        prefix = self._reporter._base_name + (name + "_" if name != "" else "")
+        PeakFasta(sequence_graph).write_max_path_sequences(prefix + "sequences.fasta",
+                                                           caller.max_path_peaks)
 
     def peaks(self):
         """{chromosome name: list of Peak} for this rank's chromosomes."""

@@ -138,6 +138,28 @@ class IntervalCollection:
 class PeakCollection(IntervalCollection):
     interval_class = Peak
 
+    def to_fasta_file(self, file_name, sequence_graph):
+        from .peakfasta import PeakFasta
+        PeakFasta(sequence_graph).save_intervals(file_name, self)
+
+    @classmethod
+    def from_fasta_file(cls, file_name, graph=None):
+        """Records as PeakFasta writes them (reference peakcollection.py:258-281): the
+        id is the header's first word, the peak its JSON remainder; the sequence is kept
+        on the peak."""
+        peaks = []
+        with open(file_name) as fh:
+            while True:
+                header, sequence = fh.readline(), fh.readline()
+                if not sequence:
+                    break
+                name, line = header.split(maxsplit=1)
+                peak = Peak.from_file_line(line, graph=graph)
+                peak.unique_id = name.replace(">", "")
+                peak.sequence = sequence.strip()
+                peaks.append(peak)
+        return cls(peaks)
+
     def summits(self, q_values, n_base_pairs_around=60, graph=None):
         """int32[n, 6] per peak: summit offset along the peak, peak length, and the
         cut around the summit as (first node index, last node index, start offset,

@@ -312,6 +312,16 @@ int gpc_parse_vg_graph_host(const char* text, uint64_t n_bytes, int32_t* node_id
                             int32_t* node_len, uint64_t* n_nodes, int32_t* edge_from,
                             int32_t* edge_to, uint64_t* n_edges);
 
+/* ---- node sequences of a vg graph in JSON form, on the HOST ------------------------
+ * For the sequence graph behind the reference's FASTA output
+ * (SequenceGraph.set_sequences_using_vg_json_graph at preprocess_interface.py:60-66,
+ * PeakFasta at peakfasta.py:8-18): node ids in file order, seq_ptr[n_nodes + 1]
+ * offsets into `seq`, the bases as they stand in the file.  Two-call protocol as
+ * above (*n_nodes, *n_bases = capacities on the second call). */
+int gpc_parse_vg_sequences_host(const char* text, uint64_t n_bytes, int32_t* node_id,
+                                int64_t* seq_ptr, char* seq, uint64_t* n_nodes,
+                                uint64_t* n_bases);
+
 /* ---- C1  LinearMap.from_graph / find_starts / find_ends
  *          (control/linearmap.py:102-154) ------------------------------------
  * HOST function on HOST arrays (one-off preprocessing that the reference

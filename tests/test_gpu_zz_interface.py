@@ -171,3 +171,28 @@ def test_reference_known_answer_for_summits():
     cut = collection.intervals[0]
     assert (cut.start_position.offset, cut.end_position.offset, cut.region_paths) == (2, 6, [1])
     assert PeakCollection([]).summits(qvalues).shape == (0, 6)
+
+
+def test_get_summits_known_answer(tmp_path):
+    # reference tests/test_command_line_interface.py:121-138: create_ob_graph, peaks as FASTA,
+    # q-value files, get_summits with window 2 -> Peak(2, 6, [1]) reading "tccc"
+    from graph_peak_caller_b200 import analysis_interface as ai
+    from graph_peak_caller_b200.peakcollection import Peak
+    from graph_peak_caller_b200.peakfasta import PeakFasta
+    from graph_peak_caller_b200.sequencegraph import SequenceGraph
+    from graph_peak_caller_b200.sparsediffs import SparseValues
+    from test_sequences import VG_TEST_GRAPH, write
+    d = str(tmp_path) + "/"
+    ci.create_ob_graph(args_of(vg_json_file_name=write(tmp_path / "vg_test_graph.json", VG_TEST_GRAPH),
+                               out_file_name=d + "testgraph.obg"))
+    qvalues = SparseValues(np.array([0]), np.array([3.0]))
+    qvalues.track_size = 22
+    qvalues.to_sparse_files(d + "test_qvalues")
+    sequence_graph = SequenceGraph.from_file(d + "testgraph.obg.sequences")
+    PeakFasta(sequence_graph).write_max_path_sequences(
+        d + "test_max_paths.fasta", PeakCollection([Peak(0, 2, [1, 2], score=3)]))
+    ai.get_summits(args_of(graph=d + "testgraph.obg", peaks_fasta_file=d + "test_max_paths.fasta",
+                           q_values_base_name=d + "test_qvalues", window_size="2"))
+    result = PeakCollection.from_fasta_file(d + "test_max_paths_summits.fasta")
+    assert result.intervals[0] == Peak(2, 6, [1])
+    assert result.intervals[0].sequence.lower() == "tccc"

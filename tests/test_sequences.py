@@ -1,0 +1,249 @@
+"""CPU: node sequences and FASTA output (second half):
+``SequenceGraph`` (what the reference takes from offsetbasedgraph, absent here),
+``gpc_parse_vg_sequences_host``, ``PeakFasta`` (reference peakfasta.py:4-31),
+``PeakCollection.to_fasta_file / from_fasta_file`` (peakcollection.py:254-281) and
+the ``sequences.fasta`` file names of the entry points.  Known answers are the
+reference's own: tests/test_command_line_interface.py:18-27,102-119,121-138 on
+tests/vg_test_graph.json."""
+import json
+import types
+
+import numpy as np
+import pytest
+
+from graph_peak_caller_b200 import callpeaks_interface as ci
+from graph_peak_caller_b200.graph import Graph
+from graph_peak_caller_b200.multiplegraphscallpeaks import MultipleGraphsCallpeaks
+from graph_peak_caller_b200.peakcollection import Peak, PeakCollection
+from graph_peak_caller_b200.peakfasta import PeakFasta
+from graph_peak_caller_b200.reporter import Reporter
+from graph_peak_caller_b200.sequencegraph import SequenceGraph
+from graph_peak_caller_b200.synthetic import make_graph
+
+VG_TEST_GRAPH = ('{"node": [     {"id": 1, "sequence": "TTTCCCC"},     {"id": 2, "sequence": "TTTT"},'
+                 '     {"id": 3, "sequence": "CCCCTTT"},     {"id": 4, "sequence": "ACTG"} ],'
+                 '"edge": [     {"from": 1, "to": 2},     {"from": 1, "to": 3},     {"from": 2, "to": 4},'
+                 '    {"from": 3, "to": 4} ] }')
+
+
+def reference_graph():
+    return Graph({1: 7, 2: 4, 3: 7, 4: 4}, {1: [2, 3], 2: [4], 3: [4]})
+
+
+def write(path, text):
+    with open(path, "w") as fh:
+        fh.write(text)
+    return str(path)
+
+
+def complement(s):
+    return s[::-1].translate(str.maketrans("acgtn", "tgcan"))
+
+
+def random_sequence_json(g, rng, chunks=3, min_node=None):
+    """vg graph JSON lines with random bases; returns (lines, {node id: sequence})."""
+    min_node = g.min_node if min_node is None else min_node
+    seqs = {int(i + min_node): "".join(rng.choice(list("ACGTN"), size=int(n)))
+            for i, n in enumerate(g.node_len)}
+    ids = list(seqs)
+    rng.shuffle(ids)
+    lines = []
+    for part in np.array_split(np.array(ids), chunks):
+        lines.append(json.dumps({"edge": [], "node": [{"sequence": seqs[int(i)], "name": "x\\\"y",
+                                                        "id": (str(int(i)) if i % 2 else int(i))}
+                                                       for i in part]}))
+    return lines, seqs
+
+
+def test_reference_known_answer(tmp_path):
+    # test_command_line_interface.py:102-119: Peak(0, 2, [1, 2]) reads "tttcccctt"
+    g = reference_graph()
+    sg = SequenceGraph.create_empty_from_ob_graph(g)
+    assert sg.get_interval_sequence(Peak(0, 2, [1, 2])) == "n" * 9
+    sg.set_sequences_using_vg_json_graph(write(tmp_path / "g.json", VG_TEST_GRAPH))
+    peak = Peak(0, 2, [1, 2], score=3)
+    assert sg.get_interval_sequence(peak) == "tttcccctt"
+    assert sg.get_interval_sequence(Peak(2, 6, [1])) == "tccc"        # :137-138, the summit cut
+    assert sg.get_interval_sequence(Peak(3, 4, [1, 3, 4])) == "cccc" + "ccccttt" + "actg"
+    assert sg.get_node_sequence(4) == "actg" and sg.get_sequence(3, 4) == "ttt"
+    # reverse strand: reverse complement of the node, offsets counted on that strand
+    assert sg.get_sequence(-4) == "cagt" and sg.get_sequence(-1, 0, 4) == "gggg"
+    assert sg.get_interval_sequence(Peak(1, 3, [-4, -2])) == "agt" + "aaa"
+    # PeakFasta + from_fasta_file
+    name = str(tmp_path / "peaks.fasta")
+    PeakFasta(sg).write_max_path_sequences(name, PeakCollection([peak]))
+    with open(name) as fh:
+        lines = fh.read().split("\n")
+    assert lines[0] == ">peak0 " + peak.to_file_line() and lines[1:] == ["tttcccctt", ""]
+    back = PeakCollection.from_fasta_file(name)
+    assert len(back.intervals) == 1 and back.intervals[0] == peak
+    assert back.intervals[0].sequence == "tttcccctt" and back.intervals[0].unique_id == "peak0"
+    assert back.intervals[0].score == 3
+
+
+def test_files_round_trip(tmp_path):
+    g = reference_graph()
+    graph_name = str(tmp_path / "testgraph.obg")
+    out = ci.create_ob_graph(types.SimpleNamespace(
+        vg_json_file_name=write(tmp_path / "vg_test_graph.json", VG_TEST_GRAPH),
+        out_file_name=graph_name))
+    assert out == graph_name
+    sg = SequenceGraph.from_file(graph_name + ".sequences")        # finds the graph by name
+    assert sg.get_interval_sequence(Peak(0, 2, [1, 2])) == "tttcccctt"
+    sg2 = SequenceGraph.from_file(graph_name + ".sequences", graph=g)
+    assert sg2.get_node_sequence(3) == "ccccttt"
+    with pytest.raises(FileNotFoundError):
+        SequenceGraph.from_file(str(tmp_path / "nothing.nobg.sequences"))
+    with pytest.raises(ValueError):
+        SequenceGraph.from_file(graph_name + ".sequences", graph=Graph({1: 5}, {}))
+    # PeakCollection.to_fasta_file == PeakFasta.save_intervals; several peaks, numbered in order
+    peaks = PeakCollection([Peak(0, 2, [1, 2], score=3), Peak(1, 4, [3, 4], score=1.5), Peak(0, 7, [1])])
+    name = str(tmp_path / "many.fasta")
+    peaks.to_fasta_file(name, sg)
+    back = PeakCollection.from_fasta_file(name, graph=g)
+    assert [p.unique_id for p in back.intervals] == ["peak0", "peak1", "peak2"]
+    assert [p.sequence for p in back.intervals] == ["tttcccctt", "cccttt" + "actg", "tttcccc"]
+    assert back.intervals == peaks.intervals and back.intervals[1].graph is g
+
+
+@pytest.mark.parametrize("min_node,chunks", [(1, 1), (1, 4), (500, 3)])
+def test_random_sequences_against_json_module(tmp_path, min_node, chunks):
+    rng = np.random.default_rng(7 + chunks)
+    g0 = make_graph(6000, 0.06, seed=5, mnp_frac=0.2)
+    src = np.repeat(np.arange(g0.n_nodes), np.diff(g0.succ_ptr))
+    g = Graph.from_edges(g0.node_len, src, g0.succ, min_node)
+    lines, seqs = random_sequence_json(g, rng, chunks, min_node)
+    name = write(tmp_path / "g.json", "\n".join(lines) + "\n")
+    sg = SequenceGraph.from_vg_json_file(name, g)
+    for node in rng.choice(list(seqs), size=200):
+        node = int(node)
+        assert sg.get_node_sequence(node) == seqs[node].lower()
+        assert sg.get_sequence(-node) == complement(seqs[node].lower())
+    # a path through the graph: first successor until the sink
+    node, path = min_node, []
+    while len(path) < 40:
+        path.append(node)
+        nxt = g.adj_list[node]
+        if len(nxt) == 0:
+            break
+        node = int(nxt[-1])
+    whole = "".join(seqs[n].lower() for n in path)
+    end = int(g.node_len[path[-1] - min_node])
+    assert sg.get_interval_sequence(Peak(0, end, path)) == whole
+    start = int(g.node_len[path[0] - min_node]) - 1
+    assert sg.get_interval_sequence(Peak(start, 1, path)) == \
+        whole[start:len(whole) - end + 1]
+    # file round trip keeps every base
+    sg.to_file(str(tmp_path / "g.nobg.sequences"))
+    again = SequenceGraph.from_file(str(tmp_path / "g.nobg.sequences"), graph=g)
+    assert np.array_equal(again._sequences, sg._sequences)
+
+
+def test_parser_errors(tmp_path):
+    g = reference_graph()
+    sg = SequenceGraph.create_empty_from_ob_graph(g)
+    bad_len = VG_TEST_GRAPH.replace('"TTTT"', '"TTT"')
+    with pytest.raises(ValueError, match="lengths differ"):
+        sg.set_sequences_using_vg_json_graph(write(tmp_path / "a.json", bad_len))
+    outside = VG_TEST_GRAPH.replace('"id": 4', '"id": 9')
+    with pytest.raises(ValueError, match="outside the graph"):
+        sg.set_sequences_using_vg_json_graph(write(tmp_path / "b.json", outside))
+    escaped = VG_TEST_GRAPH.replace('"ACTG"', '"AC\\u0054G"')
+    with pytest.raises(Exception, match="escaped sequence"):
+        sg.set_sequences_using_vg_json_graph(write(tmp_path / "c.json", escaped))
+    with pytest.raises(Exception, match="malformed"):
+        sg.set_sequences_using_vg_json_graph(write(tmp_path / "d.json", VG_TEST_GRAPH[:-30]))
+    # no nodes at all: nothing set, nothing raised
+    sg.set_sequences_using_vg_json_graph(write(tmp_path / "e.json", '{"edge": []}\n\n'))
+    assert sg.get_node_sequence(1) == "n" * 7
+    with pytest.raises(ValueError):
+        sg.set_sequence(2, "ACG")
+    sg.set_sequence(2, "ACGT")
+    assert sg.get_node_sequence(2) == "acgt" and sg.get_node_sequence(1) == "n" * 7
+
+
+class _Caller:
+    def __init__(self, peaks):
+        self.max_path_peaks = peaks
+
+
+def test_multigraph_sequence_files(tmp_path):
+    # <base><name>_sequences.fasta per chromosome (multiplegraphscallpeaks.py:157-166);
+    # a missing .sequences file is a warning
+    g = reference_graph()
+    ci.create_ob_graph(types.SimpleNamespace(
+        vg_json_file_name=write(tmp_path / "1.json", VG_TEST_GRAPH),
+        out_file_name=str(tmp_path / "1.nobg")))
+    base = str(tmp_path / "run_")
+    peaks = PeakCollection([Peak(0, 2, [1, 2], score=3)])
+    retrievers = ci._SequenceGraphFiles([str(tmp_path / "1.nobg.sequences"),
+                                         str(tmp_path / "2.nobg.sequences")])
+    m = MultipleGraphsCallpeaks(["1", "2"], [g, g], None, None, None, None, Reporter(base),
+                                sequence_retrievers=retrievers)
+    m._write_sequences(0, _Caller(peaks))
+    m._write_sequences(1, _Caller(peaks))                      # no such file: skipped
+    back = PeakCollection.from_fasta_file(base + "1_sequences.fasta")
+    assert back.intervals[0].sequence == "tttcccctt"
+    assert not (tmp_path / "run_2_sequences.fasta").exists()
+    # the reference's form: an iterator consumed in chromosome order; and a plain list
+    sg = SequenceGraph.from_file(str(tmp_path / "1.nobg.sequences"))
+    for source, name in ((iter([sg]), "it_"), ([sg], "list_")):
+        m = MultipleGraphsCallpeaks(["1"], [g], None, None, None, None,
+                                    Reporter(str(tmp_path / name)), sequence_retrievers=source)
+        m._write_sequences(0, _Caller(peaks))
+        assert PeakCollection.from_fasta_file(
+            str(tmp_path / name) + "1_sequences.fasta").intervals[0].sequence == "tttcccctt"
+    # nothing asked for, or a Reporter that keeps everything in memory: no file
+    m = MultipleGraphsCallpeaks(["1"], [g], None, None, None, None, Reporter(None),
+                                sequence_retrievers=[sg])
+    m._write_sequences(0, _Caller(peaks))
+
+
+# ---- the args-driven callers (analysis/analysis_interface.py) ---------------------------
+
+def test_peaks_to_fasta_known_answer(tmp_path):
+    # reference tests/test_command_line_interface.py:102-119
+    from graph_peak_caller_b200 import analysis_interface as ai
+    graph_name = str(tmp_path / "testgraph.obg")
+    ci.create_ob_graph(types.SimpleNamespace(
+        vg_json_file_name=write(tmp_path / "vg_test_graph.json", VG_TEST_GRAPH),
+        out_file_name=graph_name))
+    PeakCollection([Peak(0, 2, [1, 2], score=3)]).to_file(
+        str(tmp_path / "testintervals.intervalcollection"), text_file=True)
+    ai.peaks_to_fasta(types.SimpleNamespace(
+        sequence_graph=graph_name + ".sequences",
+        intervals_file_name=str(tmp_path / "testintervals.intervalcollection"),
+        out_file_name=str(tmp_path / "testsequences.fasta")))
+    collection = PeakCollection.from_fasta_file(str(tmp_path / "testsequences.fasta"))
+    assert len(collection.intervals) == 1
+    assert collection.intervals[0].sequence.lower() == "tttcccctt"
+
+
+def test_concatenate_fasta_files_known_answer(tmp_path, monkeypatch):
+    # reference tests/test_command_line_interface.py:80-106: two chromosomes' files, by score
+    from graph_peak_caller_b200 import analysis_interface as ai
+    monkeypatch.chdir(tmp_path)
+    peak1, peak2 = Peak(3, 5, [1], score=3), Peak(2, 5, [1], score=7)
+    write("1_sequences.fasta", ">peak1 " + peak1.to_file_line() + "\nAACC\n")
+    write("2_sequences.fasta", ">peak2 " + peak2.to_file_line() + "\nCCAA\n")
+    ai.concatenate_sequence_files(types.SimpleNamespace(
+        chromosomes="1,2", out_file_name="out.fasta", is_summits=None, use_input_file_pattern=None))
+    with open("out.fasta") as fh:
+        lines = fh.readlines()
+    assert Peak.from_file_line(lines[0].split(maxsplit=1)[1]) == peak2
+    assert Peak.from_file_line(lines[2].split(maxsplit=1)[1]) == peak1
+    assert lines[0].startswith(">peak0 ") and lines[2].startswith(">peak1 ")
+    assert [lines[1], lines[3]] == ["CCAA\n", "AACC\n"]
+    both = PeakCollection.from_file("out.intervalcollection", text_file=True)
+    assert both.intervals == [peak2, peak1]
+    # summit files through a pattern
+    write("s_1.fa", ">peak0 " + peak1.to_file_line() + "\nAA\n")
+    write("s_2.fa", ">peak0 " + peak2.to_file_line() + "\nCC\n>peak1 " + peak1.to_file_line() + "\nGG\n")
+    got = ai.concatenate_sequence_files(types.SimpleNamespace(
+        chromosomes="1,2", out_file_name="all.summits.fasta", is_summits="True",
+        use_input_file_pattern="s_[chrom].fa"))
+    assert [p.sequence for p in got] == ["CC", "AA", "GG"]          # stable among equal scores
+    assert len(PeakCollection.from_file("all.summits.intervalcollection").intervals) == 3
+    with pytest.raises(FileNotFoundError):
+        ai.concatenate_sequence_files(types.SimpleNamespace(
+            chromosomes="3", out_file_name="x.fasta", is_summits="True", use_input_file_pattern=None))
