@@ -17,7 +17,7 @@ GPC_ERR_FRONTIER_OVERFLOW = 5
 GPC_ERR_INTERNAL = 6
 
 c_void_p = ctypes.c_void_p
-u32, u64, i32 = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int32
+u32, u64, i32, i64 = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int64
 f64 = ctypes.c_double
 
 
@@ -68,6 +68,9 @@ _SIGNATURES = {
     "gpc_parse_vg_graph_host": [c_void_p, u64, c_void_p, c_void_p, P(u64), c_void_p, c_void_p,
                                 P(u64)],
     "gpc_parse_vg_sequences_host": [c_void_p, u64, c_void_p, c_void_p, c_void_p, P(u64), P(u64)],
+    "gpc_shift_model_host": [c_void_p, u64, c_void_p, u64, i64, i64, i64, i64, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, P(u64)],
+    "gpc_most_covered_path_host": [c_void_p, c_void_p, c_void_p, c_void_p, u64, c_void_p, P(u64)],
     "gpc_linear_map_from_graph_host": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        u64, c_void_p, c_void_p],
     "gpc_sort_u32": [c_void_p, c_void_p, u64, i32, i32, P(i32), c_void_p],

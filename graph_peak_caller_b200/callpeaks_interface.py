@@ -24,7 +24,8 @@ all outside the data-parallel path:
 * sequence graphs (``<graph file>.sequences``, written by ``create_ob_graph`` from
   the vg JSON) are this package's flat ``SequenceGraph``; with them the runs write
   ``sequences.fasta`` as the reference does;
-* no fragment-length estimation: ``fragment_length`` must be given.
+* ``fragment_length`` missing in ``run_callpeaks2``: estimated as in the reference
+  (``shiftestimation.py`` of this package, native host sweeps).
 """
 import logging
 import os
@@ -112,6 +113,29 @@ def estimate_read_length(file_name, graph_name):
     graph = load_graph(graph_name)
     reads = parse_input_file(file_name, graph).intervals
     return int(np.median(reads.lengths(graph)))
+
+
+def estimate_fragment_length(graphs, samples, args=None):
+    """The reference's estimate when ``-f`` is missing (:201-212): MACS2's peak model
+    over the read starts on the most-covered path of every graph
+    (``shiftestimation.MultiGraphShiftEstimator``), fold-enrichment bounds from
+    ``min_fold_enrichment`` / ``max_fold_enrichment`` (defaults 5 and 50)."""
+    from .shiftestimation import MultiGraphShiftEstimator
+    min_m, max_m = _arg(args, "min_fold_enrichment"), _arg(args, "max_fold_enrichment")
+    min_m = 5 if min_m is None else int(min_m)
+    max_m = 50 if max_m is None else int(max_m)
+    return int(MultiGraphShiftEstimator.from_files(graphs, samples, min_m, max_m).get_estimates())
+
+
+def shift_estimation(args):
+    """preprocess_interface.py:21-38: the estimate for the chromosomes of a data
+    directory (``<ob_graphs_location>/<chrom>.nobg``, ``<sample_reads_base_name><chrom>.json``)."""
+    chromosomes = args.chromosomes.split(",")
+    graphs = [args.ob_graphs_location + "/" + chrom + ".nobg" for chrom in chromosomes]
+    samples = [args.sample_reads_base_name + chrom + ".json" for chrom in chromosomes]
+    d = estimate_fragment_length(graphs, samples, args)
+    logging.info("Found shift: %d" % d)
+    return d
 
 
 def get_confiugration(args):
@@ -228,10 +252,14 @@ def prepare_callpeaks2(args):
         config.q_values_threshold = float(args.q_threshold)
         logging.info("Running with q value threshold %.3f" % config.q_values_threshold)
     if _arg(args, "fragment_length") is None:
-        raise NotImplementedError(
-            "fragment length estimation (shiftestimation/) is outside this path: "
-            "pass fragment_length")
-    config.fragment_length = int(args.fragment_length)
+        logging.info("Fragment length was not specified. Will now predict fragment length.")
+        config.fragment_length = estimate_fragment_length(graphs, samples, args)
+        logging.info("Estimated fragment length to be %d" % config.fragment_length)
+        assert config.fragment_length < 1000, \
+            "Suspiciously high fragment length. Probably a bad estimate." \
+            " Change -m/-M to try to get more paired peaks."
+    else:
+        config.fragment_length = int(args.fragment_length)
     if _arg(args, "read_length") is None:
         config.read_length = estimate_read_length(samples[0], graphs[0])
         logging.info("Estimated read length to %s" % config.read_length)
@@ -242,7 +270,9 @@ def prepare_callpeaks2(args):
         sys.exit(1)
     if _arg(args, "genome_size") is not None:
         genome_size = int(args.genome_size)
-        config.global_min = int(args.unique_reads) * int(args.fragment_length) / genome_size
+        # the reference multiplies by int(args.fragment_length) (:222), which fails after
+        # an estimate; the configured length is the same number whenever that one works
+        config.global_min = int(args.unique_reads) * config.fragment_length / genome_size
         logging.info("Computed min background signal to be %.3f" % config.global_min)
     else:
         logging.info("Not using min background.")

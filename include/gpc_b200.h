@@ -322,6 +322,29 @@ int gpc_parse_vg_sequences_host(const char* text, uint64_t n_bytes, int32_t* nod
                                 int64_t* seq_ptr, char* seq, uint64_t* n_nodes,
                                 uint64_t* n_bases);
 
+/* ---- fragment-length estimation, on the HOST ----------------------
+ * The sequential scans of PeakModel (shiftestimation/shiftestimation.py:65-336) for
+ * one chromosome: __naive_find_peaks (:262-290) + __naive_peak_pos (:292-336) on both
+ * strands, __find_pair_center (:231-260), __model_add_line (:180-218) for both
+ * strands.  plus_tags / minus_tags: SORTED read-start positions (Treatment, :26-43).
+ * The four int32 lines of 1 + 2 * peaksize + tag_expansion entries are ACCUMULATED
+ * into (the caller zeroes them once and calls per chromosome).  centers may be NULL;
+ * else *n_centers is its capacity on entry.  *n_centers = pair centres found. */
+int gpc_shift_model_host(const int64_t* plus_tags, uint64_t n_plus, const int64_t* minus_tags,
+                         uint64_t n_minus, int64_t peaksize, int64_t tag_expansion,
+                         int64_t min_tags, int64_t max_tags, int32_t* plus_start,
+                         int32_t* plus_end, int32_t* minus_start, int32_t* minus_end,
+                         int64_t* centers, uint64_t* n_centers);
+
+/* HaploTyper.get_maximum_interval_through_graph (haplotyping.py:28-58): the path from
+ * the graph's single source that always continues on the successor with the highest
+ * node_count (first of equals in adjacency order).  0-based node indexes; path may be
+ * NULL (count only); *n_path = capacity in, length out.  A graph with no or several
+ * sources is GPC_ERR_ARG ("Only works when graph has one start node", :33). */
+int gpc_most_covered_path_host(const int64_t* succ_ptr, const int32_t* succ,
+                               const int64_t* pred_ptr, const int64_t* node_count,
+                               uint64_t n_nodes, int32_t* path, uint64_t* n_path);
+
 /* ---- C1  LinearMap.from_graph / find_starts / find_ends
  *          (control/linearmap.py:102-154) ------------------------------------
  * HOST function on HOST arrays (one-off preprocessing that the reference

@@ -270,5 +270,22 @@ class NumpyIndexedInterval:
     pass
 
 
-class IndexedInterval:
-    pass
+class IndexedInterval(Interval):
+    """Enough of obg's IndexedInterval for haplotyping.py:58 and linear_filter.py:15-41.
+    get_offset_at_position is obg's (source absent from the reference tree): stated
+    here as the base pair's distance from the interval's start on the forward strand
+    -- UNPINNED, see oracle/shift.py."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._distance_to_node = {}
+        walked = -self.start_position.offset
+        for rp in self.region_paths:
+            self._distance_to_node[rp] = walked
+            walked += self.graph.node_size(rp)
+
+    def get_offset_at_position(self, position, direction="+"):
+        rp = abs(position.region_path_id)
+        if direction == "+":
+            return int(self._distance_to_node[rp] + position.offset)
+        return int(self._distance_to_node[rp] + self.graph.node_size(rp) - position.offset)

@@ -1,0 +1,192 @@
+"""CPU: fragment-length estimation -- the native sweeps behind
+``PeakModel`` / ``LinearFilter`` (csrc/shift.cu) against the oracle restatement
+(oracle/shift.py), both against golden vectors made by the unmodified reference
+(tests/golden/shift/shift_model.npz, oracle/make_golden_shift.py) and, in the build
+container, against the live reference itself."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+from graph_peak_caller_b200 import callpeaks_interface as ci
+from graph_peak_caller_b200 import shiftestimation as se
+from graph_peak_caller_b200.graph import Graph
+from graph_peak_caller_b200.synthetic import make_graph, make_reads
+from oracle import refbridge, shift as oshift
+from test_callpeaks_interface import write_graph_json, write_reads_json
+
+GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "shift", "shift_model.npz"))
+
+
+def golden_positions(k):
+    return {"+": {c: GOLDEN["m%d_plus_%s" % (k, c)] for c in ("0", "1")},
+            "-": {c: GOLDEN["m%d_minus_%s" % (k, c)] for c in ("0", "1")}}
+
+
+def model_of(positions, genome, lmfold=5, umfold=50):
+    opt = se.Opt(lmfold, umfold)
+    opt.gsize = genome
+    return se.PeakModel(opt, se.Treatment(positions))
+
+
+def random_positions(rng, genome=600_000, sites=150, chroms=("a", "b", "c"), repeat=0.0):
+    d = int(rng.integers(60, 300))
+    pos = {"+": {}, "-": {}}
+    for chrom in chroms:
+        centers = rng.choice(genome - 4000, sites, replace=False) + 2000
+        plus, minus = [rng.integers(0, genome, 1500)], [rng.integers(0, genome, 1500)]
+        for c in centers:
+            plus.append((c - d // 2 + rng.normal(0, 12, int(rng.integers(5, 40)))).astype(np.int64))
+            minus.append((c + d // 2 + rng.normal(0, 12, int(rng.integers(5, 40)))).astype(np.int64))
+        for s, parts in (("+", plus), ("-", minus)):
+            v = np.concatenate(parts)
+            if repeat:                                    # repeated tags count once per window summit
+                v = np.r_[v, rng.choice(v, int(repeat * v.size))]
+            pos[s][chrom] = v
+    return pos, genome * len(chroms)
+
+
+def same_model(got, want):
+    assert got.d == want["d"]
+    assert np.array_equal(got.plus_line, want["plus_line"])
+    assert np.array_equal(got.minus_line, want["minus_line"])
+    assert np.array_equal(got.ycorr, want["ycorr"])
+    assert got.alternative_d == list(want["alternative_d"])
+    assert (got.min_tags, got.max_tags) == (want["min_tags"], want["max_tags"])
+    assert {c: v.tolist() for c, v in got.paired_peakpos.items()} == \
+        {c: list(v) for c, v in want["centers"].items() if len(v)}
+
+
+@pytest.mark.parametrize("k", [0, 1])
+def test_golden_model(k):
+    genome, planted, min_tags, max_tags = GOLDEN["m%d_meta" % k].tolist()
+    got = model_of(golden_positions(k), genome)
+    assert got.d == GOLDEN["m%d_d" % k][0] and abs(got.d - planted) < 3
+    assert np.array_equal(got.plus_line, GOLDEN["m%d_plus_line" % k])
+    assert np.array_equal(got.minus_line, GOLDEN["m%d_minus_line" % k])
+    assert np.array_equal(got.ycorr, GOLDEN["m%d_ycorr" % k])
+    assert got.alternative_d == GOLDEN["m%d_alternative_d" % k].tolist()
+    assert (got.min_tags, got.max_tags) == (min_tags, max_tags)
+    assert got.scan_window == max(got.d, 10) * 2
+    want = oshift.peak_model(golden_positions(k), genome)          # the oracle on the same vectors
+    same_model(got, want)
+    estimator = se.MultiGraphShiftEstimator(golden_positions(k), genome)
+    assert estimator.get_estimates() == round(GOLDEN["m%d_d" % k][0])
+
+
+@pytest.mark.parametrize("seed,repeat,folds", [(1, 0.0, (5, 50)), (2, 0.5, (5, 50)), (3, 0.1, (3, 20)),
+                                               (4, 0.0, (8, 30))])
+def test_native_equals_oracle(seed, repeat, folds):
+    rng = np.random.default_rng(seed)
+    pos, genome = random_positions(rng, repeat=repeat)
+    want = oshift.peak_model(pos, genome, *folds)
+    if want["d"] is None:
+        with pytest.raises(se.NotEnoughPairsException):
+            model_of(pos, genome, *folds)
+        return
+    same_model(model_of(pos, genome, *folds), want)
+
+
+def test_small_and_degenerate_inputs():
+    rng = np.random.default_rng(9)
+    pos, genome = random_positions(rng, sites=20, chroms=("x",))
+    with pytest.raises(se.NotEnoughPairsException):                 # < 100 pairs
+        model_of(pos, genome)
+    assert oshift.peak_model(pos, genome)["d"] is None
+    # a chromosome with no reads on one strand, one with a single read: skipped
+    pos, genome = random_positions(rng, chroms=("a", "b", "c"))
+    pos["+"]["e"], pos["-"]["e"] = np.array([], dtype=np.int64), pos["-"]["a"][:500]
+    pos["+"]["f"], pos["-"]["f"] = np.array([5]), np.array([7])
+    same_model(model_of(pos, genome), oshift.peak_model(pos, genome))
+    # the library refuses unsorted tags (Treatment sorts; a direct caller must)
+    import ctypes
+    from graph_peak_caller_b200 import _lib
+    lines = np.zeros((4, 1211), dtype=np.int32)
+    tags = np.array([5, 3, 9], dtype=np.int64)
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+    n = ctypes.c_uint64(0)
+    status = _lib.load().gpc_shift_model_host(vp(tags), 3, vp(tags), 3, 600, 10, 1, 5, vp(lines[0]),
+                                              vp(lines[1]), vp(lines[2]), vp(lines[3]), None,
+                                              ctypes.byref(n))
+    assert status == _lib.GPC_ERR_ARG
+
+
+def test_golden_linear_filter():
+    n_bp, gseed, n_reads, rseed = GOLDEN["lf_graph_args"].tolist()
+    g = make_graph(n_bp, 0.05, seed=gseed, mnp_frac=0.2)
+    reads = make_reads(g, n_reads, 20, 80, seed=rseed, peak_frac=0.5, peak_spacing=2500)
+    lf = se.LinearFilter.from_reads_and_graph(reads, g)
+    assert (lf._path + g.min_node).tolist() == GOLDEN["lf_path"].tolist()
+    found = lf.find_start_positions()
+    assert found["+"].tolist() == GOLDEN["lf_plus"].tolist()
+    assert found["-"].tolist() == GOLDEN["lf_minus"].tolist()
+    assert lf.length() == GOLDEN["lf_length"][0]
+    # and the oracle's loops on the same reads
+    paths = [reads.path[reads.path_ptr[i]:reads.path_ptr[i + 1]].tolist() for i in range(len(reads))]
+    path = oshift.most_covered_path(g.node_len, g.min_node, g.succ_ptr, g.succ, g.pred_ptr, paths)
+    assert path == GOLDEN["lf_path"].tolist()
+    want = oshift.start_positions(g.node_len, g.min_node, path,
+                                  zip(reads.start_node.tolist(), reads.start_off.tolist()))
+    assert want["+"] == GOLDEN["lf_plus"].tolist() and want["-"] == GOLDEN["lf_minus"].tolist()
+
+
+def test_most_covered_path_rules():
+    # ties go to the first successor in adjacency order; zero-count successors are still followed
+    g = Graph({1: 3, 2: 2, 3: 2, 4: 5, 5: 1}, {1: [2, 3], 2: [4], 3: [4], 4: [5]})
+    assert se.most_covered_path(g, [0, 0, 0, 0, 0]).tolist() == [0, 1, 3, 4]
+    assert se.most_covered_path(g, [0, 1, 2, 0, 0]).tolist() == [0, 2, 3, 4]
+    assert se.most_covered_path(g, [9, 2, 2, 0, 0]).tolist() == [0, 1, 3, 4]
+    with pytest.raises(Exception, match="one start node"):         # haplotyping.py:33
+        se.most_covered_path(Graph({1: 3, 2: 2, 3: 2}, {1: [3], 2: [3]}), [0, 0, 0])
+    # a read start off the path is dropped; a reverse start counts from the node's far end
+    reads = types.SimpleNamespace(start_node=np.array([1, 3, -2, -4, 2], dtype=np.int32),
+                                  start_off=np.array([2, 1, 1, 5, 0], dtype=np.int32))
+    found = se.LinearFilter(reads, g, [0, 1, 3, 4]).find_start_positions()
+    assert found["+"].tolist() == [2, 3] and found["-"].tolist() == [3 + 2 - 1, 5 + 5 - 5]
+
+
+def test_estimate_from_files(tmp_path):
+    # reads with the plus pile F/2 left and the minus pile F/2 right of every site: the
+    # estimate from files on disk is F within the jitter, and callpeaks2 uses it when -f is missing
+    F, R = 180, 30
+    g = make_graph(800000, 0.02, seed=70, mnp_frac=0.1)
+    reads = make_reads(g, 50000, R, F, seed=71, peak_frac=0.8, peak_spacing=5000, dup_frac=0.0)
+    ci.create_ob_graph(types.SimpleNamespace(
+        vg_json_file_name=write_graph_json(tmp_path / "1.json", g),
+        out_file_name=str(tmp_path / "1.nobg")))
+    sample = write_reads_json(tmp_path / "sample_1.json", g, reads)
+    estimator = se.MultiGraphShiftEstimator.from_files([str(tmp_path / "1.nobg")], [sample])
+    lf = se.LinearFilter.from_reads_and_graph(reads, g)
+    assert estimator.genome_size == lf.length()
+    d = estimator.get_estimates()
+    assert isinstance(d, int) and abs(d - F) <= 12
+    assert estimator.peakmodel.n_paired_peaks >= 100
+    want = oshift.peak_model({s: {"0": v.tolist()} for s, v in lf.find_start_positions().items()},
+                             lf.length())
+    assert round(want["d"]) == d
+    assert ci.estimate_fragment_length([str(tmp_path / "1.nobg")], [sample],
+                                       types.SimpleNamespace(min_fold_enrichment=None,
+                                                             max_fold_enrichment="50")) == d
+
+
+@pytest.mark.skipif(not refbridge.available(), reason="/root/reference not present")
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_equals_live_reference(seed):
+    from oracle.make_golden_shift import reference_linear_filter, reference_model
+    rng = np.random.default_rng(seed)
+    pos, genome = random_positions(rng, repeat=0.2 * (seed % 2))
+    ref = reference_model(pos, genome, 4, 40)
+    got = model_of(pos, genome, 4, 40)
+    assert got.d == ref.d and got.alternative_d == ref.alternative_d
+    assert np.array_equal(got.plus_line, ref.plus_line) and np.array_equal(got.minus_line, ref.minus_line)
+    assert np.array_equal(got.ycorr, ref.ycorr) and np.array_equal(got.xcorr, ref.xcorr)
+    assert (got.min_tags, got.max_tags, got.scan_window) == (ref.min_tags, ref.max_tags, ref.scan_window)
+    same_model(got, oshift.peak_model(pos, genome, 4, 40))
+    g = make_graph(12000 + 1000 * seed, 0.06, seed=seed, mnp_frac=0.3)
+    reads = make_reads(g, 1500, 20, 80, seed=seed + 1, peak_frac=0.4, peak_spacing=2000)
+    path, found, length = reference_linear_filter(g, reads)
+    lf = se.LinearFilter.from_reads_and_graph(reads, g)
+    assert (lf._path + g.min_node).tolist() == path and lf.length() == length
+    mine = lf.find_start_positions()
+    assert mine["+"].tolist() == found["+"] and mine["-"].tolist() == found["-"]
