@@ -136,3 +136,89 @@ def test_oracle_equals_live_reference(trial):
                                                     peak[0], peak[1], peak[2], window)
             assert (cut.start_position.offset, cut.end_position.offset,
                     list(cut.region_paths)) == want
+
+
+# ---- the Python side of the device path, with the kernel's host build in the kernel's place ----
+
+class _Host:
+    """Stands in for a CUDA tensor holding the kernel's output."""
+
+    def __init__(self, a):
+        self.a = a
+
+    def cpu(self):
+        return self
+
+    def numpy(self):
+        return self.a
+
+
+@pytest.fixture
+def host_kernel(summits_host, monkeypatch):
+    """PeakCollection.summits / cut_around_summit / analysis_interface.get_summits run as they
+    do on the GPU box (tests/test_gpu_zz_interface.py), except that uploads are no-ops and
+    gpc_peak_summits is replaced by the same per-peak code compiled for the host."""
+    import types
+    from graph_peak_caller_b200 import device, kernels
+    from graph_peak_caller_b200.sparsediffs import SparseValues
+
+    def peak_summits(graph, start, end, ptr, nodes, q_pos, q_val, window):
+        peaks = [(int(start[i]), int(end[i]), nodes[ptr[i]:ptr[i + 1]].tolist())
+                 for i in range(start.size)]
+        return _Host(summits_host(graph, peaks, q_pos, q_val, window))
+
+    monkeypatch.setattr(kernels, "torch_cuda", lambda: types.SimpleNamespace(float64=np.float64))
+    monkeypatch.setattr(kernels, "peak_summits", peak_summits)
+    monkeypatch.setattr(device, "device_graph", lambda g: g)
+    monkeypatch.setattr(device, "to_device", lambda a, dtype=None: np.asarray(a))
+    monkeypatch.setattr(SparseValues, "device_arrays",
+                        lambda self, value_dtype=None: (np.asarray(self.indices, dtype=np.uint32),
+                                                        np.asarray(self.values, dtype=np.float64)))
+
+
+def test_cut_around_summit_python_side(host_kernel):
+    from graph_peak_caller_b200.peakcollection import Peak, PeakCollection
+    from graph_peak_caller_b200.sparsediffs import SparseValues
+    rng = np.random.default_rng(77)
+    g = make_graph(9000, 0.05, seed=8, mnp_frac=0.2)
+    peaks = random_peaks(g, 120, rng)
+    q_pos, q_val = random_track(g.size_bp, rng, 300, np.array([0.0, 1.0, 2.5, 4.0]))
+    track = SparseValues(q_pos, q_val)
+    track.track_size = g.size_bp
+    dense = osummits.dense_track(q_pos, q_val, g.size_bp)
+    collection = PeakCollection([Peak(s, e, list(n), graph=g, score=1.5, unique_id="peak%d" % i)
+                                 for i, (s, e, n) in enumerate(peaks)])
+    collection.cut_around_summit(track, 25)
+    for cut, peak in zip(collection.intervals, peaks):
+        _, _, want = osummits.cut_around_summit(g.node_off, g.node_len, g.min_node, dense,
+                                                peak[0], peak[1], peak[2], 25)
+        assert (cut.start_position.offset, cut.end_position.offset, list(cut.region_paths)) == want
+        assert cut.score == 1.5 and cut.unique_id.startswith("peak") and cut.length() <= 50
+    assert PeakCollection([]).summits(track).shape == (0, 6)
+
+
+def test_get_summits_known_answer_python_side(host_kernel, tmp_path):
+    # reference tests/test_command_line_interface.py:121-138 (the device run of the same
+    # steps: tests/test_gpu_zz_interface.py::test_get_summits_known_answer)
+    import types
+    from graph_peak_caller_b200 import analysis_interface as ai, callpeaks_interface as ci
+    from graph_peak_caller_b200.peakcollection import Peak, PeakCollection
+    from graph_peak_caller_b200.peakfasta import PeakFasta
+    from graph_peak_caller_b200.sequencegraph import SequenceGraph
+    from graph_peak_caller_b200.sparsediffs import SparseValues
+    from test_sequences import VG_TEST_GRAPH, write
+    d = str(tmp_path) + "/"
+    ci.create_ob_graph(types.SimpleNamespace(
+        vg_json_file_name=write(tmp_path / "vg_test_graph.json", VG_TEST_GRAPH),
+        out_file_name=d + "testgraph.obg"))
+    qvalues = SparseValues(np.array([0]), np.array([3.0]))
+    qvalues.track_size = 22
+    qvalues.to_sparse_files(d + "test_qvalues")
+    PeakFasta(SequenceGraph.from_file(d + "testgraph.obg.sequences")).write_max_path_sequences(
+        d + "test_max_paths.fasta", PeakCollection([Peak(0, 2, [1, 2], score=3)]))
+    ai.get_summits(types.SimpleNamespace(graph=d + "testgraph.obg", window_size="2",
+                                         peaks_fasta_file=d + "test_max_paths.fasta",
+                                         q_values_base_name=d + "test_qvalues"))
+    result = PeakCollection.from_fasta_file(d + "test_max_paths_summits.fasta")
+    assert result.intervals[0] == Peak(2, 6, [1])
+    assert result.intervals[0].sequence.lower() == "tccc"
