@@ -83,6 +83,26 @@ def create_linear_map(ob_graph, out_file_name="linear_map.npz"):
     logging.info("Created linear map, wrote to file %s" % out_file_name)
 
 
+def create_linear_map_interface(args):
+    """preprocess_interface.py:72-80: ``args.graph`` (a graph or its file name) ->
+    ``<graph file up to the first dot>_linear_map.npz`` unless a name is given."""
+    out_name = args.out_file_base_name if _arg(args, "out_file_base_name") is not None \
+        else args.graph_file_name.split(".")[0] + "_linear_map.npz"
+    create_linear_map(load_graph(args.graph), out_name)
+    logging.info("Wrote linear map to file %s" % out_name)
+    return out_name
+
+
+def count_unique_reads(chromosomes, graph_file_names, reads_file_names):
+    """preprocess_interface.py:41-48: unique reads (by start position) summed over the
+    alignment files of all chromosomes; de-duplication runs on the device."""
+    reads = (parse_input_file(f, load_graph(g)).intervals
+             for f, g in zip(reads_file_names, graph_file_names))
+    unique_reads = MultipleGraphsCallpeaks.count_number_of_unique_reads(reads)
+    print(unique_reads)
+    return unique_reads
+
+
 def find_or_create_linear_map(graph, linear_map_name):
     if os.path.isfile(linear_map_name):
         logging.info("Found linear map %s. Will be used in peak calling." % linear_map_name)

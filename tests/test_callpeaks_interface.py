@@ -363,3 +363,18 @@ def test_run_preparation_equals_the_live_reference(tmp_path, monkeypatch):
     for case in whole:
         ref.run_callpeaks_whole_genome(args_of(**case))
         assert _seen(ci.prepare_callpeaks_whole_genome(args_of(**case))) == _Recorder.last
+
+
+def test_create_linear_map_interface(tmp_path):
+    # preprocess_interface.py:72-80
+    g = make_graph(5000, 0.05, seed=3)
+    name = str(tmp_path / "g.nobg")
+    with open(name, "wb") as fh:
+        g.to_file(fh)
+    out = ci.create_linear_map_interface(args_of(graph=name, graph_file_name=name,
+                                                 out_file_base_name=None))
+    assert out == str(tmp_path / "g_linear_map.npz")
+    assert LinearMap.from_file(out, g) == LinearMap.from_graph(g)
+    out = ci.create_linear_map_interface(args_of(graph=g, graph_file_name=name,
+                                                 out_file_base_name=str(tmp_path / "other.npz")))
+    assert LinearMap.from_file(str(tmp_path / "other.npz"), g) == LinearMap.from_graph(g)

@@ -196,3 +196,14 @@ def test_get_summits_known_answer(tmp_path):
     result = PeakCollection.from_fasta_file(d + "test_max_paths_summits.fasta")
     assert result.intervals[0] == Peak(2, 6, [1])
     assert result.intervals[0].sequence.lower() == "tccc"
+
+
+def test_count_unique_reads_from_files(tmp_path, capsys):
+    # preprocess_interface.py:41-48
+    from oracle import pipeline as opipeline
+    data = chromosomes_on_disk(tmp_path)
+    d = str(tmp_path) + "/"
+    got = ci.count_unique_reads(["1", "2"], [d + "1.nobg", d + "2.nobg"],
+                                [d + "sample_1.json", d + "sample_2.json"])
+    want = sum(len(opipeline.unique_reads(s).start_node) for _, s, _ in data.values())
+    assert got == want and capsys.readouterr().out.strip() == str(want)
