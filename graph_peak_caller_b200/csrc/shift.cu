@@ -156,7 +156,9 @@ extern "C" int gpc_shift_model_host(const int64_t* plus_tags, uint64_t n_plus,
 }
 
 // haplotyping.py:28-58: from the graph's only source, follow the successor most reads
-// pass through (the first of equals in adjacency order) down to a sink.
+// pass through (the first of equals in adjacency order) down to a sink.  A node without
+// any edge is not a source: the reference's tests/test_haplotyping.py:10-25,50-66 holds
+// such a node (11) and still finds one start node.
 extern "C" int gpc_most_covered_path_host(const int64_t* succ_ptr, const int32_t* succ,
                                           const int64_t* pred_ptr, const int64_t* node_count,
                                           uint64_t n_nodes, int32_t* path, uint64_t* n_path) {
@@ -166,7 +168,7 @@ extern "C" int gpc_most_covered_path_host(const int64_t* succ_ptr, const int32_t
     }
     int64_t source = -1;
     for (uint64_t v = 0; v < n_nodes; ++v)
-        if (pred_ptr[v + 1] == pred_ptr[v]) {
+        if (pred_ptr[v + 1] == pred_ptr[v] && (succ_ptr[v + 1] > succ_ptr[v] || n_nodes == 1)) {
             if (source >= 0) { set_error("Only works when graph has one start node"); return GPC_ERR_ARG; }
             source = (int64_t)v;
         }

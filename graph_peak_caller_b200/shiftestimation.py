@@ -20,10 +20,11 @@ What stays in numpy is the cross-correlation of the two 1211-entry model lines, 
 the same operations as the reference so that ``d`` is the same float.
 
 offsetbasedgraph's ``IndexedInterval.get_offset_at_position`` is not in the reference
-tree: a read start ``(node, offset)`` on the path maps to ``distance to the node +
-offset``; on the reverse strand ``(-node, offset)`` to ``distance to the node + node
-size - offset``, the same base pair counted on the forward strand (unpinned,
-DESIGN.md §8)."""
+tree; the reference's tests/test_linearfilter.py:33-42 pins it for forward starts
+(``distance from the path's start to the node + offset``).  A reverse start
+``(-node, offset)`` is taken as the same base pair counted on the forward strand,
+``distance + node size - offset``: that test's one reverse start sits mid-node and so
+agrees with this without telling it from ``distance + offset`` (unpinned)."""
 import ctypes
 import logging
 
@@ -182,10 +183,11 @@ class LinearFilter:
     """Read starts projected onto one path through the graph (linear_filter.py:12-46).
     ``reads``: a ``ReadBatch``; ``path``: 0-based node indexes in path order."""
 
-    def __init__(self, reads, graph, path):
+    def __init__(self, reads, graph, path, start_offset=0):
         self._reads = reads
         self._graph = Graph.from_obg(graph)
         self._path = np.asarray(path, dtype=np.int64)
+        self._start_offset = int(start_offset)      # of the path on its first node
 
     def length(self):
         return int(self._graph.node_len[self._path].sum())
@@ -195,10 +197,12 @@ class LinearFilter:
         distance = np.full(g.n_nodes, -1, dtype=np.int64)
         sizes = g.node_len[self._path]
         distance[self._path] = np.cumsum(sizes) - sizes
+        on_the_path = distance >= 0
+        distance -= self._start_offset
         node = np.abs(r.start_node.astype(np.int64)) - g.min_node
         inside = (node >= 0) & (node < g.n_nodes)
         on_path = np.zeros(node.size, dtype=bool)
-        on_path[inside] = distance[node[inside]] >= 0
+        on_path[inside] = on_the_path[node[inside]]
         forward = r.start_node > 0
         offset = r.start_off.astype(np.int64)
         keep = on_path & forward

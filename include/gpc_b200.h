@@ -339,7 +339,8 @@ int gpc_shift_model_host(const int64_t* plus_tags, uint64_t n_plus, const int64_
 /* HaploTyper.get_maximum_interval_through_graph (haplotyping.py:28-58): the path from
  * the graph's single source that always continues on the successor with the highest
  * node_count (first of equals in adjacency order).  0-based node indexes; path may be
- * NULL (count only); *n_path = capacity in, length out.  A graph with no or several
+ * NULL (count only); *n_path = capacity in, length out.  Nodes without any edge are
+ * not sources (tests/test_haplotyping.py:10-25).  A graph with no or several
  * sources is GPC_ERR_ARG ("Only works when graph has one start node", :33). */
 int gpc_most_covered_path_host(const int64_t* succ_ptr, const int32_t* succ,
                                const int64_t* pred_ptr, const int64_t* node_count,

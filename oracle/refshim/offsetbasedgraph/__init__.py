@@ -128,8 +128,10 @@ class Graph:
         return out
 
     def get_first_blocks(self):
+        # nodes without any edge are not first blocks (reference
+        # tests/test_haplotyping.py:10-25,50-66 expects one start with node 11 isolated)
         return [i for i in self.blocks.keys()
-                if not self.reverse_adj_list[-i]]
+                if not self.reverse_adj_list[-i] and (self.adj_list[i] or len(self.blocks) == 1)]
 
     def convert_to_numpy_backend(self):
         return self

@@ -10,11 +10,15 @@ estimation, in plain Python loops over lists:
 
 Pinned against the live reference in tests/test_shiftestimation.py (PeakModel,
 HaploTyper, LinearFilter run unmodified) and by tests/golden/shift/shift_model.npz made from
-it (oracle/make_golden_shift.py).  One step is UNPINNED: the reference projects a read
-start with offsetbasedgraph's IndexedInterval.get_offset_at_position, whose source is
-not in the reference tree; here (and in oracle/refshim) a start (node, offset) maps to
-distance-to-node + offset, and a reverse start (-node, offset) to distance-to-node +
-node size - offset."""
+it (oracle/make_golden_shift.py), plus the reference's own known answers
+(tests/test_linearfilter.py:33-42, tests/test_haplotyping.py:28-66,
+tests/test_multigraph_shiftestimation.py:8-33).  One step is only HALF PINNED: the
+reference projects a read start with offsetbasedgraph's
+IndexedInterval.get_offset_at_position, whose source is not in the reference tree.
+test_linearfilter.py pins forward starts (distance-to-node + offset); its single
+reverse start sits mid-node, so the rule used here and in oracle/refshim for a reverse
+start (-node, offset) -- distance-to-node + node size - offset -- agrees with it without
+being told apart from distance-to-node + offset."""
 import numpy as np
 
 
@@ -146,7 +150,9 @@ def most_covered_path(node_len, min_node, succ_ptr, succ, pred_ptr, read_paths):
         for rp in path:
             counts[rp] = counts.get(rp, 0) + 1
     n = len(node_len)
-    sources = [v for v in range(n) if pred_ptr[v + 1] == pred_ptr[v]]
+    # nodes without any edge do not count (reference tests/test_haplotyping.py:10-25,50-66)
+    sources = [v for v in range(n) if pred_ptr[v + 1] == pred_ptr[v]
+               and (succ_ptr[v + 1] > succ_ptr[v] or n == 1)]
     assert len(sources) == 1, "Only works when graph has one start node"
     v, path = sources[0], []
     while True:

@@ -190,3 +190,55 @@ def test_equals_live_reference(seed):
     assert (lf._path + g.min_node).tolist() == path and lf.length() == length
     mine = lf.find_start_positions()
     assert mine["+"].tolist() == found["+"] and mine["-"].tolist() == found["-"]
+
+
+# ---- the reference's own known answers ---------------------------------------------------
+
+def test_reference_linearfilter_known_answer():
+    # reference tests/test_linearfilter.py:7-42: path 10 (from offset 5), 11, 13 of six
+    # 10-bp nodes; starts 10:7, 11:5, -11:5, 13:2 -> {"+": [2, 10, 17], "-": [10]}
+    g = Graph({i: 10 for i in (9, 10, 11, 12, 13, 14)},
+              {9: [10], 10: [11, 12], 11: [13], 12: [13], 13: [14]})
+    reads = types.SimpleNamespace(start_node=np.array([10, 11, -11, 13, 12, -9], dtype=np.int32),
+                                  start_off=np.array([7, 5, 5, 2, 1, 3], dtype=np.int32))
+    found = se.LinearFilter(reads, g, [1, 2, 4], start_offset=5).find_start_positions()
+    assert {k: v.tolist() for k, v in found.items()} == {"+": [2, 10, 17], "-": [10]}
+    want = oshift.start_positions(g.node_len, 9, [10, 11, 13], [(10, 7), (11, 5), (-11, 5), (13, 2)])
+    assert {k: [x - 5 for x in v] for k, v in want.items()} == {"+": [2, 10, 17], "-": [10]}
+
+
+def test_reference_haplotyper_known_answers():
+    # reference tests/test_haplotyping.py:28-66
+    from graph_peak_caller_b200.reads import ReadBatch
+    from graph_peak_caller_b200.peakcollection import Interval
+
+    def path_of(graph, intervals):
+        reads = ReadBatch.from_intervals([Interval(s, e, n) for s, e, n in intervals])
+        lf = se.LinearFilter.from_reads_and_graph(reads, graph)
+        return (lf._path + graph.min_node).tolist()
+
+    simple = Graph({i: 3 for i in range(1, 5)}, {1: [2, 3], 2: [4], 3: [4]})
+    assert path_of(simple, [(0, 3, [1, 3])]) == [1, 3, 4]
+    complex_graph = Graph({i: 3 for i in range(1, 13)},
+                          {1: [2, 3], 2: [7, 8], 3: [4, 5], 4: [6], 5: [6], 6: [10], 7: [9],
+                           8: [9], 9: [10], 10: [12]})
+    intervals = [(0, 3, [1, 3, 4, 6, 10]), (1, 2, [2]), (2, 3, [2]), (0, 3, [7, 9])]
+    # node 11 has no edges and is not a start node
+    assert path_of(complex_graph, intervals) == [1, 2, 7, 9, 10, 12]
+
+
+def test_reference_multigraph_shift_known_answer():
+    # reference tests/test_multigraph_shiftestimation.py:8-33: 400 sites of 40 read pairs,
+    # the minus read `shift` to the right of the plus read -> the estimate is the shift
+    rng = np.random.default_rng(5)
+    shift, genome_size = 150, 10000000
+    positions = {"+": {1: []}, "-": {1: []}}
+    for _ in range(400):
+        pos = int(rng.integers(0, genome_size - shift))
+        for _ in range(40):
+            pos += int(rng.integers(-3, 3))
+            positions["+"][1].append(pos)
+            positions["-"][1].append(pos + shift)
+    estimator = se.MultiGraphShiftEstimator(positions, genome_size)
+    assert round(estimator.get_estimates()) == shift
+    assert round(oshift.peak_model(positions, genome_size)["d"]) == shift
