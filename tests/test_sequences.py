@@ -247,3 +247,61 @@ def test_concatenate_fasta_files_known_answer(tmp_path, monkeypatch):
     with pytest.raises(FileNotFoundError):
         ai.concatenate_sequence_files(types.SimpleNamespace(
             chromosomes="3", out_file_name="x.fasta", is_summits="True", use_input_file_pattern=None))
+
+
+def test_sequence_scanner_on_random_json(tmp_path):
+    # random graph chunks (junk members, key order, quoted ids, nodes without a sequence):
+    # the scanner sees the (id, sequence) pairs the json module sees, or -- when a sequence
+    # holds an escape -- refuses the file
+    import ctypes
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from graph_peak_caller_b200 import _lib
+    scalars = st.one_of(st.none(), st.booleans(), st.integers(-10**9, 10**9), st.text(max_size=10))
+    junk = st.recursive(scalars, lambda kids: st.one_of(
+        st.lists(kids, max_size=3), st.dictionaries(st.text(max_size=6), kids, max_size=3)),
+        max_leaves=6)
+    ident = st.one_of(st.integers(1, 2**31 - 1), st.integers(1, 2**31 - 1).map(str))
+    node = st.fixed_dictionaries({"id": ident}, optional={
+        "sequence": st.text("ACGTNacgtn", max_size=12), "name": st.text(max_size=4), "x": junk})
+    hard_node = st.fixed_dictionaries({"id": ident, "sequence": st.text("AC\\\"\n", min_size=1, max_size=6)})
+    chunk = st.fixed_dictionaries({}, optional={
+        "node": st.lists(st.one_of(node, node, node, hard_node), max_size=5),
+        "edge": junk, "path": junk, "sequence": st.text(max_size=5)})
+    lib = _lib.load()
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+
+    @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(st.lists(chunk, min_size=1, max_size=4), st.booleans())
+    def run(chunks, reverse_keys):
+        lines = []
+        for c in chunks:
+            c = dict(c)
+            if "node" in c and reverse_keys:
+                c["node"] = [dict(reversed(list(n.items()))) for n in c["node"]]
+            lines.append(json.dumps(c, separators=(", ", ": ") if reverse_keys else (",", ":")))
+        want = [(int(n["id"]), n.get("sequence", "")) for c in chunks for n in c.get("node", [])]
+        escaped = any(json.dumps(s) != '"%s"' % s for _, s in want)
+        text = np.frombuffer(("\n".join(lines) + "\n").encode("utf-8"), dtype=np.uint8)
+        n, m = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        status = lib.gpc_parse_vg_sequences_host(vp(text), text.size, None, None, None,
+                                                 ctypes.byref(n), ctypes.byref(m))
+        if escaped:
+            assert status == _lib.GPC_ERR_ARG
+            return
+        assert status == _lib.GPC_OK
+        assert (n.value, m.value) == (len(want), sum(len(s) for _, s in want))
+        ids = np.zeros(len(want) + 1, dtype=np.int32)
+        ptr = np.zeros(len(want) + 1, dtype=np.int64)
+        seq = np.zeros(int(m.value) + 1, dtype=np.uint8)
+        assert lib.gpc_parse_vg_sequences_host(vp(text), text.size, vp(ids), vp(ptr), vp(seq),
+                                               ctypes.byref(n), ctypes.byref(m)) == _lib.GPC_OK
+        assert ids[:len(want)].tolist() == [i for i, _ in want]
+        bases = seq[:int(m.value)].tobytes().decode("ascii")
+        assert [bases[ptr[k]:ptr[k + 1]] for k in range(len(want))] == [s for _, s in want]
+        # too little room is reported, not overrun
+        if len(want) > 1:
+            n.value, m.value = len(want) - 1, m.value
+            assert lib.gpc_parse_vg_sequences_host(vp(text), text.size, vp(ids), vp(ptr), vp(seq),
+                                                   ctypes.byref(n), ctypes.byref(m)) == _lib.GPC_ERR_CAPACITY
+
+    run()
