@@ -242,3 +242,46 @@ def test_reference_multigraph_shift_known_answer():
     estimator = se.MultiGraphShiftEstimator(positions, genome_size)
     assert round(estimator.get_estimates()) == shift
     assert round(oshift.peak_model(positions, genome_size)["d"]) == shift
+
+
+def test_sweeps_on_random_small_inputs():
+    # the three sweeps of gpc_shift_model_host against the oracle's loops on adversarial small
+    # inputs: tiny windows, repeated tags, negative positions, empty strands, any tag bounds
+    import ctypes
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from graph_peak_caller_b200 import _lib
+    lib = _lib.load()
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+    tags = st.lists(st.integers(-40, 400), max_size=120).map(sorted)
+
+    @settings(max_examples=300, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(tags, tags, st.integers(1, 40), st.integers(0, 11), st.integers(0, 4), st.integers(0, 30))
+    def run(plus, minus, peaksize, expansion, min_tags, more):
+        max_tags = min_tags + more
+        window = 1 + 2 * peaksize + expansion
+        pp = oshift.strand_peaks(plus, peaksize, expansion, min_tags, max_tags)
+        mp = oshift.strand_peaks(minus, peaksize, expansion, min_tags, max_tags)
+        centers = oshift.pair_centers(pp, mp, peaksize) if pp and mp else []
+        want = [[0] * window for _ in range(4)]
+        oshift.add_to_line(centers, plus, peaksize, expansion, want[0], want[1])
+        oshift.add_to_line(centers, minus, peaksize, expansion, want[2], want[3])
+        p, m = np.array(plus, dtype=np.int64), np.array(minus, dtype=np.int64)
+        lines = np.zeros((4, window), dtype=np.int32)
+        out = np.zeros(len(centers) + 1, dtype=np.int64)
+        n = ctypes.c_uint64(out.size)
+        status = lib.gpc_shift_model_host(vp(p), p.size, vp(m), m.size, peaksize, expansion, min_tags,
+                                          max_tags, vp(lines[0]), vp(lines[1]), vp(lines[2]),
+                                          vp(lines[3]), vp(out), ctypes.byref(n))
+        assert status == _lib.GPC_OK and n.value == len(centers)
+        assert out[:len(centers)].tolist() == centers
+        assert lines.tolist() == want
+        if len(centers) > 1:              # too little room: reported, lines left alone
+            again = np.zeros((4, window), dtype=np.int32)
+            n.value = len(centers) - 1
+            assert lib.gpc_shift_model_host(vp(p), p.size, vp(m), m.size, peaksize, expansion,
+                                            min_tags, max_tags, vp(again[0]), vp(again[1]),
+                                            vp(again[2]), vp(again[3]), vp(out),
+                                            ctypes.byref(n)) == _lib.GPC_ERR_CAPACITY
+            assert n.value == len(centers) and not again.any()
+
+    run()
