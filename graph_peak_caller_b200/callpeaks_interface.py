@@ -103,6 +103,14 @@ def count_unique_reads(chromosomes, graph_file_names, reads_file_names):
     return unique_reads
 
 
+def count_unique_reads_interface(args):
+    """preprocess_interface.py:11-18"""
+    chromosomes = args.chromosomes.split(",")
+    graph_file_names = [args.graphs_location + chrom + ".nobg" for chrom in chromosomes]
+    reads_file_names = [args.reads_base_name + chrom + ".json" for chrom in chromosomes]
+    return count_unique_reads(chromosomes, graph_file_names, reads_file_names)
+
+
 def find_or_create_linear_map(graph, linear_map_name):
     if os.path.isfile(linear_map_name):
         logging.info("Found linear map %s. Will be used in peak calling." % linear_map_name)

@@ -207,3 +207,5 @@ def test_count_unique_reads_from_files(tmp_path, capsys):
                                 [d + "sample_1.json", d + "sample_2.json"])
     want = sum(len(opipeline.unique_reads(s).start_node) for _, s, _ in data.values())
     assert got == want and capsys.readouterr().out.strip() == str(want)
+    assert ci.count_unique_reads_interface(args_of(chromosomes="1,2", graphs_location=d,
+                                                   reads_base_name=d + "sample_")) == want
