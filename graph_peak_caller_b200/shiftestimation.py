@@ -183,7 +183,19 @@ class LinearFilter:
     """Read starts projected onto one path through the graph (linear_filter.py:12-46).
     ``reads``: a ``ReadBatch``; ``path``: 0-based node indexes in path order."""
 
-    def __init__(self, reads, graph, path, start_offset=0):
+    def __init__(self, reads, graph, path=None, start_offset=0):
+        if path is None and hasattr(graph, "region_paths"):
+            # the reference's form, LinearFilter(position_tuples, indexed_interval):
+            # an iterable of obg Positions and an interval through its graph
+            import types
+            interval = graph
+            graph = Graph.from_obg(interval.graph)
+            positions = [(int(p.region_path_id), int(p.offset)) for p in reads]
+            reads = types.SimpleNamespace(
+                start_node=np.array([p[0] for p in positions], dtype=np.int32),
+                start_off=np.array([p[1] for p in positions], dtype=np.int32))
+            path = np.array(interval.region_paths, dtype=np.int64) - graph.min_node
+            start_offset = interval.start_position.offset
         self._reads = reads
         self._graph = Graph.from_obg(graph)
         self._path = np.asarray(path, dtype=np.int64)

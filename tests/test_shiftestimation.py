@@ -203,6 +203,12 @@ def test_reference_linearfilter_known_answer():
                                   start_off=np.array([7, 5, 5, 2, 1, 3], dtype=np.int32))
     found = se.LinearFilter(reads, g, [1, 2, 4], start_offset=5).find_start_positions()
     assert {k: v.tolist() for k, v in found.items()} == {"+": [2, 10, 17], "-": [10]}
+    # the same through the reference's own constructor arguments (positions, indexed interval)
+    from graph_peak_caller_b200.peakcollection import Interval, Position
+    positions = [Position(10, 7), Position(11, 5), Position(-11, 5), Position(13, 2)]
+    interval = Interval(Position(10, 5), Position(13, 5), [10, 11, 13], graph=g)
+    found = se.LinearFilter(positions, interval).find_start_positions()
+    assert {k: v.tolist() for k, v in found.items()} == {"+": [2, 10, 17], "-": [10]}
     want = oshift.start_positions(g.node_len, 9, [10, 11, 13], [(10, 7), (11, 5), (-11, 5), (13, 2)])
     assert {k: [x - 5 for x in v] for k, v in want.items()} == {"+": [2, 10, 17], "-": [10]}
 
