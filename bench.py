@@ -365,9 +365,12 @@ def main_ours(args):
         cpu = dict(value=v, unit="reads/s", cores=cores, kind="port",
                    sample=cpu_sample_text(1), stage_seconds=split)
         # the row before the hot path, host only: vg alignment JSON -> reads SoA
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
-        import ingest_rate
-        ingest = ingest_rate.measure()
+        try:                     # a side figure: it must never cost the line above it
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import ingest_rate
+            ingest = ingest_rate.measure()
+        except Exception as e:   # noqa: BLE001
+            ingest = {"error": "%s: %s" % (type(e).__name__, e)}
     line = dict(metric="callpeaks_reads_per_sec", value=value, unit="reads/s", n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32+f64",
