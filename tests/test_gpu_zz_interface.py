@@ -95,6 +95,13 @@ def test_run_callpeaks2_two_graphs(tmp_path):
         same_peaks(got[chrom], want[chrom])
         written = PeakCollection.from_file(d + "two_%s_max_paths.intervalcollection" % chrom)
         assert shape(written.intervals) == shape(want[chrom])
+        # create_ob_graph left <graph>.sequences next to every graph: the peaks' sequences
+        # are written too (reference multiplegraphscallpeaks.py:157-166); the test graphs
+        # hold nothing but "a"
+        fasta = PeakCollection.from_fasta_file(d + "two_%s_sequences.fasta" % chrom)
+        assert shape(fasta.intervals) == shape(want[chrom])
+        assert all(set(p.sequence) == {"a"} and len(p.sequence) == q.length()
+                   for p, q in zip(fasta.intervals, want[chrom]))
 
 
 def test_whole_genome_in_two_halves(tmp_path):

@@ -305,3 +305,38 @@ def test_sequence_scanner_on_random_json(tmp_path):
                                                    ctypes.byref(n), ctypes.byref(m)) == _lib.GPC_ERR_CAPACITY
 
     run()
+
+
+def test_interval_sequences_on_random_paths():
+    # any path of forward or reverse nodes, any offsets: the slices of the flat array equal
+    # the string built node by node
+    rng = np.random.default_rng(31)
+    g = make_graph(4000, 0.08, seed=9, mnp_frac=0.3)
+    sg = SequenceGraph.create_empty_from_ob_graph(g)
+    seqs = {}
+    for i, n in enumerate(g.node_len):
+        seqs[i + g.min_node] = "".join(rng.choice(list("acgt"), size=int(n)))
+        if n:
+            sg.set_sequence(i + g.min_node, seqs[i + g.min_node].upper())
+    for _ in range(300):
+        v = int(rng.integers(0, g.n_nodes))
+        nodes = [v]
+        for _ in range(int(rng.integers(0, 5))):
+            nxt = g.succ[g.succ_ptr[v]:g.succ_ptr[v + 1]]
+            if nxt.size == 0:
+                break
+            v = int(rng.choice(nxt))
+            nodes.append(v)
+        ids = [n + g.min_node for n in nodes]
+        if rng.random() < 0.5:                                   # the same walk on the reverse strand
+            ids = [-n for n in reversed(ids)]
+        strings = [seqs[n] if n > 0 else complement(seqs[-n]) for n in ids]
+        if len(strings[0]) == 0 or len(strings[-1]) == 0:
+            continue
+        start = int(rng.integers(0, len(strings[0])))
+        end = int(rng.integers(1, len(strings[-1]) + 1))
+        if len(ids) == 1 and end <= start:
+            continue
+        whole = "".join(strings)
+        want = whole[start:len(whole) - (len(strings[-1]) - end)]
+        assert sg.get_interval_sequence(Peak(start, end, ids)) == want
