@@ -217,6 +217,10 @@ class MultipleGraphsCallpeaks:
         except FileNotFoundError:
             logging.warning("Could not find sequence graphs. Will not store max paths.")
             return
+        except (ValueError, KeyError, OSError) as e:
+            # e.g. offsetbasedgraph's own .sequences file: not this package's flat format
+            logging.warning("Could not read the sequence graph (%s). Will not store max paths." % e)
+            return
         if sequence_graph is None:
             return
         from .peakfasta import PeakFasta

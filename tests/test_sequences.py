@@ -340,3 +340,17 @@ def test_interval_sequences_on_random_paths():
         whole = "".join(strings)
         want = whole[start:len(whole) - (len(strings[-1]) - end)]
         assert sg.get_interval_sequence(Peak(start, end, ids)) == want
+
+
+def test_foreign_sequence_file_is_a_warning(tmp_path):
+    # a .sequences file that is not this package's (e.g. offsetbasedgraph's pickle): no FASTA, no error
+    import pickle
+    g = reference_graph()
+    with open(tmp_path / "1.nobg", "wb") as fh:
+        g.to_file(fh)
+    with open(tmp_path / "1.nobg.sequences", "wb") as fh:
+        pickle.dump({"sequences": ["ACGT"]}, fh)
+    m = MultipleGraphsCallpeaks(["1"], [g], None, None, None, None, Reporter(str(tmp_path / "x_")),
+                                sequence_retrievers=ci._SequenceGraphFiles([str(tmp_path / "1.nobg.sequences")]))
+    m._write_sequences(0, _Caller(PeakCollection([Peak(0, 2, [1, 2], score=3)])))
+    assert not (tmp_path / "x_1_sequences.fasta").exists()
