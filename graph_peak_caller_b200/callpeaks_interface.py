@@ -217,6 +217,17 @@ def run_callpeaks_interface(args):
     return caller
 
 
+def create_alignment_fasta(args):
+    """:94-103: the sequence of every unique alignment of a vg JSON file, one FASTA
+    record each (all named ``>1`` as in the reference)."""
+    intervals = UniqueIntervals(parse_input_file(args.vg_json_file_name, args.graph))
+    sequence_graph = SequenceGraph.from_file(
+        args.data_dir + "/" + args.chrom + ".nobg.sequences", graph=args.graph)
+    with open(args.out_file_name, "w") as out:
+        for interval in intervals:
+            out.write(">1\n" + sequence_graph.get_interval_sequence(interval) + "\n")
+
+
 def _get_file_names(pattern):
     from glob import glob
     if pattern is None:

@@ -354,3 +354,34 @@ def test_foreign_sequence_file_is_a_warning(tmp_path):
                                 sequence_retrievers=ci._SequenceGraphFiles([str(tmp_path / "1.nobg.sequences")]))
     m._write_sequences(0, _Caller(PeakCollection([Peak(0, 2, [1, 2], score=3)])))
     assert not (tmp_path / "x_1_sequences.fasta").exists()
+
+
+def test_create_alignment_fasta(tmp_path):
+    # callpeaks_interface.py:94-103: unique alignments (first per start position) as FASTA
+    g = reference_graph()
+    ci.create_ob_graph(types.SimpleNamespace(
+        vg_json_file_name=write(tmp_path / "g.json", VG_TEST_GRAPH),
+        out_file_name=str(tmp_path / "1.nobg")))
+
+    def alignment(nodes, offset, reverse=False):
+        first = {"node_id": nodes[0], "offset": offset}
+        if reverse:
+            first["is_reverse"] = True
+        mapping = [{"position": first, "edit": [{"from_length": 3, "to_length": 3}]}]
+        for n in nodes[1:]:
+            pos = {"node_id": n}
+            if reverse:
+                pos["is_reverse"] = True
+            mapping.append({"position": pos, "edit": [{"from_length": 2, "to_length": 2}]})
+        return json.dumps({"path": {"mapping": mapping}})
+
+    lines = [alignment([1, 2], 4), alignment([1, 3], 4), alignment([3], 1), alignment([4, 2], 0, True)]
+    reads = write(tmp_path / "reads.json", "\n".join(lines) + "\n")
+    out = str(tmp_path / "alignments.fasta")
+    ci.create_alignment_fasta(types.SimpleNamespace(
+        vg_json_file_name=reads, graph=ci.load_graph(str(tmp_path / "1.nobg")),
+        data_dir=str(tmp_path), chrom="1", out_file_name=out))
+    with open(out) as fh:
+        got = fh.read().split("\n")
+    # the second alignment starts where the first does (1:4) and is dropped
+    assert got == [">1", "ccc" + "tt", ">1", "ccc", ">1", "cagt" + "aa", ""]
