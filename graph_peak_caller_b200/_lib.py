@@ -67,6 +67,7 @@ _SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, P(u64), P(u64), P(u64)],
     "gpc_parse_vg_graph_host": [c_void_p, u64, c_void_p, c_void_p, P(u64), c_void_p, c_void_p,
                                 P(u64)],
+    "gpc_split_alignments_host": [c_void_p, u64, c_void_p, c_void_p, u64, c_void_p, c_void_p],
     "gpc_parse_vg_sequences_host": [c_void_p, u64, c_void_p, c_void_p, c_void_p, P(u64), P(u64)],
     "gpc_shift_model_host": [c_void_p, u64, c_void_p, u64, i64, i64, i64, i64, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, P(u64)],

@@ -15,7 +15,7 @@ step that shards one alignment file by chromosome before the per-chromosome
 (here: per-GPU) runs.
 """
 import ctypes
-import re
+import logging
 
 import numpy as np
 
@@ -87,9 +87,6 @@ def load_graph(file_name):
             % (file_name, e)) from None
 
 
-_NODE_ID = re.compile(rb"node_id\":\s?\"?([0-9]+)\"?")
-
-
 def split_vg_json_reads_into_chromosomes(chromosomes, reads_file_name, range_files_base_name):
     """Shards an alignment file by chromosome (preprocess_interface.py:83-145):
     a line goes to ``<base>_<chrom>.json`` of the first chromosome whose
@@ -97,8 +94,9 @@ def split_vg_json_reads_into_chromosomes(chromosomes, reads_file_name, range_fil
     the line, else to ``<base>_unmapped.json`` (a node beyond every range makes the
     reference fail with KeyError on the limits of "unmapped", :102,113-114; here
     the line goes where its log message says).  Returns the number of lines that
-    went to ``unmapped``.  Byte-identical files with the live reference:
-    tests/test_ingest_vg.py."""
+    went to ``unmapped``.  One native pass over the mapped file
+    (``gpc_split_alignments_host``) instead of a regular expression per line.
+    Byte-identical files with the live reference: tests/test_ingest_vg.py."""
     if isinstance(chromosomes, str):
         chromosomes = chromosomes.split(",")
     base = ".".join(reads_file_name.split(".")[0:-1])
@@ -108,25 +106,25 @@ def split_vg_json_reads_into_chromosomes(chromosomes, reads_file_name, range_fil
             first, last = fh.read().split(":")[:2]
         limits.append((int(first), int(last)))
     names = list(chromosomes) + ["unmapped"]
+    from . import _lib
+    from .reads import _map_file
+    lib = _lib.load()
+    text = _map_file(reads_file_name)
+    lo = np.array([a for a, _ in limits], dtype=np.int64)
+    hi = np.array([b for _, b in limits], dtype=np.int64)
+    counts = np.zeros(len(names), dtype=np.uint64)
     outs = [open(base + "_" + c + ".json", "wb") for c in names]
-    unmapped = 0
     try:
-        with open(reads_file_name, "rb") as fh:
-            for line in fh:
-                found = _NODE_ID.search(line)
-                where = len(limits)
-                if found is not None:
-                    node = int(found.group(1))
-                    for i, (lo, hi) in enumerate(limits):
-                        if lo <= node <= hi:
-                            where = i
-                            break
-                unmapped += where == len(limits)
-                outs[where].write(line)
+        fds = np.array([o.fileno() for o in outs], dtype=np.int32)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        _lib.check(lib.gpc_split_alignments_host(vp(text), text.size, vp(lo), vp(hi), len(limits),
+                                                 vp(fds), vp(counts)))
     finally:
         for o in outs:
             o.close()
-    return unmapped
+    logging.info("Done. Found %d lines without node id or not matching into the given list of "
+                 "chromosomes" % int(counts[-1]))
+    return int(counts[-1])
 
 
 def node_range_of(graph):

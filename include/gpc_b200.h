@@ -312,6 +312,16 @@ int gpc_parse_vg_graph_host(const char* text, uint64_t n_bytes, int32_t* node_id
                             int32_t* node_len, uint64_t* n_nodes, int32_t* edge_from,
                             int32_t* edge_to, uint64_t* n_edges);
 
+/* ---- alignment file -> one file per chromosome, on the HOST ---------------------------
+ * split_vg_json_reads_into_chromosomes (preprocess_interface.py:83-145): line i goes,
+ * byte for byte, to fds[k] of the first range [range_lo[k], range_hi[k]] holding the
+ * first node id of the line (the reference's regular expression, :109), else to
+ * fds[n_ranges] ("unmapped").  fds: n_ranges + 1 open descriptors; n_lines[n_ranges + 1]
+ * receives the lines written to each. */
+int gpc_split_alignments_host(const char* text, uint64_t n_bytes, const int64_t* range_lo,
+                              const int64_t* range_hi, uint64_t n_ranges, const int32_t* fds,
+                              uint64_t* n_lines);
+
 /* ---- node sequences of a vg graph in JSON form, on the HOST ------------------------
  * For the sequence graph behind the reference's FASTA output
  * (SequenceGraph.set_sequences_using_vg_json_graph at preprocess_interface.py:60-66,

@@ -29,6 +29,7 @@ the reference tree and are checked by tests/test_ingest_vg.py:
 Only tests/ may import this module.
 """
 import json
+import re
 
 import numpy as np
 
@@ -144,4 +145,34 @@ def graph_to_vg_json(node_len, min_node, src, dst, chunks=1, with_paths=True):
                 {"position": {"node_id": int(i + min_node)}, "rank": int(i + 1),
                  "edit": [{"from_length": 1, "to_length": 1}]} for i in range(lo, min(hi, lo + 3))]}]
         lines.append(json.dumps(obj))
+    return lines
+
+
+_NODE_ID = re.compile(rb"node_id\":\s?\"?([0-9]+)\"?")
+
+
+def split_by_chromosome(data, limits):
+    """split_vg_json_reads_into_chromosomes (preprocess_interface.py:83-145) on the bytes
+    of an alignment file: [bytes per range] + [bytes of "unmapped"].  ``limits``:
+    [(first node, last node)] per chromosome, in order."""
+    outs = [[] for _ in range(len(limits) + 1)]
+    for line in _split_newlines(data):
+        found = _NODE_ID.search(line)
+        where = len(limits)
+        if found is not None:
+            node = int(found.group(1))
+            for i, (lo, hi) in enumerate(limits):
+                if lo <= node <= hi:
+                    where = i
+                    break
+        outs[where].append(line)
+    return [b"".join(o) for o in outs]
+
+
+def _split_newlines(data):
+    """Lines end at \\n only (a file object in binary mode)."""
+    parts = data.split(b"\n")
+    lines = [p + b"\n" for p in parts[:-1]]
+    if parts[-1]:
+        lines.append(parts[-1])
     return lines

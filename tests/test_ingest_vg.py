@@ -397,3 +397,33 @@ def test_graph_scanner_on_random_json(tmp_path):
             assert out[1][:len(ids)].tolist() == lens
 
     run()
+
+
+def test_native_splitter_on_random_lines(tmp_path):
+    # the native splitter against the reference's regular expression (oracle restatement) on
+    # lines built from the fragments that regular expression cares about
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    pieces = st.sampled_from([b'node_id":', b'node_id": ', b'node_id":  ', b'node_id":"', b'node_id": "',
+                              b'"node_id": -', b'node_id', b'":', b'"', b' ', b'\t', b'\r', b'7', b'42',
+                              b'150', b'99999999999999999999999', b'{', b'}', b'x', b'\n', b'\n\n',
+                              b'{"path": {"mapping": [{"position": {"node_id": "12"}}]}}\n',
+                              b'{"path": {"mapping": [{"position": {"offset": 3, "node_id":120}}]}}\n'])
+    limits = [(1, 10), (5, 50), (100, 200)]                       # overlapping: the first range wins
+    for i, (lo, hi) in enumerate(limits, 1):
+        (tmp_path / ("node_range_%d.txt" % i)).write_text("%d:%d" % (lo, hi))
+
+    @settings(max_examples=200, deadline=None,
+              suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(st.lists(pieces, max_size=40))
+    def run(parts):
+        data = b"".join(parts)
+        with open(tmp_path / "r.json", "wb") as fh:
+            fh.write(data)
+        want = oingest.split_by_chromosome(data, limits)
+        unmapped = conversion.split_vg_json_reads_into_chromosomes("1,2,3", str(tmp_path / "r.json"),
+                                                                   str(tmp_path) + "/")
+        got = [(tmp_path / ("r_%s.json" % c)).read_bytes() for c in ("1", "2", "3", "unmapped")]
+        assert got == want
+        assert unmapped == len(oingest._split_newlines(want[-1])) if want[-1] else unmapped == 0
+
+    run()
