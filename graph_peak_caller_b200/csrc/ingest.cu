@@ -499,6 +499,7 @@ int parse_reads_text(const char* what, int kind, long long lo, long long hi, con
             r0 += ch.start_node.size();
             p0 += ch.path.size();
         }
+        spread_over_cpus(pool);
         for (auto& th : pool) th.join();
     }
     path_ptr[reads] = (int64_t)nodes;
