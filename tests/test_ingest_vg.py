@@ -341,7 +341,7 @@ def test_scanner_on_random_json(tmp_path):
 
     name = str(tmp_path / "fuzz.json")
 
-    @settings(max_examples=150, deadline=None,
+    @settings(derandomize=True, max_examples=150, deadline=None,
               suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
     @given(st.lists(st.tuples(alignment, st.integers(0, 15)), min_size=1, max_size=6))
     def run(items):
@@ -375,7 +375,7 @@ def test_graph_scanner_on_random_json(tmp_path):
     name = str(tmp_path / "fuzz_graph.json")
     lib = _lib.load()
 
-    @settings(max_examples=120, deadline=None,
+    @settings(derandomize=True, max_examples=120, deadline=None,
               suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
     @given(st.lists(chunk, min_size=1, max_size=4), st.booleans())
     def run(chunks, ascii_only):
@@ -412,7 +412,7 @@ def test_native_splitter_on_random_lines(tmp_path):
     for i, (lo, hi) in enumerate(limits, 1):
         (tmp_path / ("node_range_%d.txt" % i)).write_text("%d:%d" % (lo, hi))
 
-    @settings(max_examples=200, deadline=None,
+    @settings(derandomize=True, max_examples=200, deadline=None,
               suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
     @given(st.lists(pieces, max_size=40))
     def run(parts):

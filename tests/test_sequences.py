@@ -270,7 +270,7 @@ def test_sequence_scanner_on_random_json(tmp_path):
     lib = _lib.load()
     vp = lambda a: ctypes.c_void_p(a.ctypes.data)
 
-    @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @settings(derandomize=True, max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow])
     @given(st.lists(chunk, min_size=1, max_size=4), st.booleans())
     def run(chunks, reverse_keys):
         lines = []

@@ -260,7 +260,7 @@ def test_sweeps_on_random_small_inputs():
     vp = lambda a: ctypes.c_void_p(a.ctypes.data)
     tags = st.lists(st.integers(-40, 400), max_size=120).map(sorted)
 
-    @settings(max_examples=300, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @settings(derandomize=True, max_examples=300, deadline=None, suppress_health_check=[HealthCheck.too_slow])
     @given(tags, tags, st.integers(1, 40), st.integers(0, 11), st.integers(0, 4), st.integers(0, 30))
     def run(plus, minus, peaksize, expansion, min_tags, more):
         max_tags = min_tags + more
