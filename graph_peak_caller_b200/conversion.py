@@ -44,18 +44,26 @@ def json_file_to_obg_numpy_graph(file_name, n_nodes=0):
     rejected: the callpeaks path needs a topologically numbered DAG."""
     from . import _lib
     lib = _lib.load()
-    text = np.fromfile(file_name, dtype=np.uint8)
-    tp = ctypes.c_void_p(text.ctypes.data)
-    n, m = ctypes.c_uint64(0), ctypes.c_uint64(0)
-    _lib.check(lib.gpc_parse_vg_graph_host(tp, text.size, None, None, ctypes.byref(n),
-                                           None, None, ctypes.byref(m)))
-    ids, lens = (np.empty(int(n.value), dtype=np.int32) for _ in range(2))
-    src, dst = (np.empty(int(m.value), dtype=np.int32) for _ in range(2))
+    from .reads import _map_file
+    text = _map_file(file_name)
+    tp = ctypes.c_void_p(text.ctypes.data) if text.size else None
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+    # one parse: room for as many entries as the file could hold at all (a node object
+    # takes 8 bytes or more, an edge 17; the arrays' untouched pages cost nothing); the
+    # call says what it needs should that ever fall short
+    n, m = ctypes.c_uint64(text.size // 8 + 1), ctypes.c_uint64(text.size // 17 + 1)
+    while True:
+        ids, lens = (np.empty(int(n.value), dtype=np.int32) for _ in range(2))
+        src, dst = (np.empty(int(m.value), dtype=np.int32) for _ in range(2))
+        status = lib.gpc_parse_vg_graph_host(tp, text.size, vp(ids), vp(lens), ctypes.byref(n),
+                                             vp(src), vp(dst), ctypes.byref(m))
+        if status != _lib.GPC_ERR_CAPACITY:
+            break
+    _lib.check(status)
+    ids, lens = ids[:int(n.value)].copy(), lens[:int(n.value)].copy()
+    src, dst = src[:int(m.value)].copy(), dst[:int(m.value)].copy()
     if ids.size == 0:
         raise ValueError("%s holds no nodes" % file_name)
-    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
-    _lib.check(lib.gpc_parse_vg_graph_host(tp, text.size, vp(ids), vp(lens), ctypes.byref(n),
-                                           vp(src), vp(dst), ctypes.byref(m)))
     if src.size and (src.min() < 0 or dst.min() < 0):
         raise ValueError("reversing edges (from_start / to_end) are not supported on this path")
     min_node = int(ids.min())

@@ -544,6 +544,7 @@ struct VgGraphSink {
     int32_t* node_len;
     int32_t* edge_from;
     int32_t* edge_to;
+    unsigned long long node_room = 0, edge_room = 0;   // entries the arrays can take
     unsigned long long nodes = 0, edges = 0;
 };
 
@@ -564,7 +565,10 @@ bool parse_vg_graph_object(Cursor& c, VgGraphSink& out) {
                     }))
                     return false;
                 if (!have_id || id <= 0 || id > 2147483647ll || len > 2147483647ll) return false;
-                if (out.node_id) { out.node_id[out.nodes] = (int32_t)id; out.node_len[out.nodes] = (int32_t)len; }
+                if (out.node_id && out.nodes < out.node_room) {
+                    out.node_id[out.nodes] = (int32_t)id;
+                    out.node_len[out.nodes] = (int32_t)len;
+                }
                 ++out.nodes;
                 return true;
             });
@@ -583,7 +587,7 @@ bool parse_vg_graph_object(Cursor& c, VgGraphSink& out) {
                 if (!have_from || !have_to || from <= 0 || to <= 0 || from > 2147483647ll ||
                     to > 2147483647ll)
                     return false;
-                if (out.edge_from) {
+                if (out.edge_from && out.edges < out.edge_room) {
                     out.edge_from[out.edges] = (int32_t)(from_start ? -from : from);
                     out.edge_to[out.edges] = (int32_t)(to_end ? -to : to);
                 }
@@ -640,30 +644,26 @@ extern "C" int gpc_parse_vg_graph_host(const char* text, uint64_t n_bytes, int32
         set_error("gpc_parse_vg_graph_host: all output arrays or none");
         return GPC_ERR_ARG;
     }
-    // the counting pass also validates, so the filling pass cannot overrun
-    for (int pass = 0; pass < (fill ? 2 : 1); ++pass) {
-        VgGraphSink sink{nullptr, nullptr, nullptr, nullptr};
-        if (pass == 1) sink = VgGraphSink{node_id, node_len, edge_from, edge_to};
-        Chunk whole;
-        whole.b = text;
-        whole.e = text + n_bytes;
-        long long line = 0, bad = -1;
-        for_lines(whole, [&](const char* b, const char* e) {
-            ++line;
-            Cursor c{b, e};
-            if (bad < 0 && !parse_vg_graph_object(c, sink)) bad = line;
-        });
-        if (bad >= 0) {
-            set_error("vg graph file: malformed JSON (non-blank line %lld)", bad);
-            return GPC_ERR_ARG;
-        }
-        if (pass == 0) {
-            *n_nodes = sink.nodes;
-            *n_edges = sink.edges;
-            if (fill && (want_nodes < sink.nodes || want_edges < sink.edges))
-                return GPC_ERR_CAPACITY;
-        }
+    // one pass: entries beyond the room given are counted, not stored
+    VgGraphSink sink{node_id, node_len, edge_from, edge_to};
+    sink.node_room = fill ? want_nodes : 0;
+    sink.edge_room = fill ? want_edges : 0;
+    Chunk whole;
+    whole.b = text;
+    whole.e = text + n_bytes;
+    long long line = 0, bad = -1;
+    for_lines(whole, [&](const char* b, const char* e) {
+        ++line;
+        Cursor c{b, e};
+        if (bad < 0 && !parse_vg_graph_object(c, sink)) bad = line;
+    });
+    if (bad >= 0) {
+        set_error("vg graph file: malformed JSON (non-blank line %lld)", bad);
+        return GPC_ERR_ARG;
     }
+    *n_nodes = sink.nodes;
+    *n_edges = sink.edges;
+    if (fill && (want_nodes < sink.nodes || want_edges < sink.edges)) return GPC_ERR_CAPACITY;
     return GPC_OK;
 }
 

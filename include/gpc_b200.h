@@ -306,8 +306,11 @@ int gpc_parse_vg_alignments_host(const char* text, uint64_t n_bytes, int32_t n_t
  * an object {"node": [{"id", "sequence"}], "edge": [{"from", "to", "from_start",
  * "to_end"}], ...}; node_len = length of the sequence; an edge is reported as
  * (-from if from_start else from, -to if to_end else to), paths and other keys are
- * skipped.  Nodes and edges come out in file order.  Call with all arrays NULL for
- * the counts, then with *n_nodes / *n_edges set to the capacities. */
+ * skipped.  Nodes and edges come out in file order.  One pass over the text either
+ * way: with all arrays NULL it counts; with arrays, *n_nodes / *n_edges are their
+ * capacities on entry and the numbers found on return -- entries beyond the capacity
+ * are counted, not stored, and the call returns GPC_ERR_CAPACITY (a caller that knows
+ * an upper bound, e.g. from the file size, needs a single call). */
 int gpc_parse_vg_graph_host(const char* text, uint64_t n_bytes, int32_t* node_id,
                             int32_t* node_len, uint64_t* n_nodes, int32_t* edge_from,
                             int32_t* edge_to, uint64_t* n_edges);
