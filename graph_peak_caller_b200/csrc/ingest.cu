@@ -681,60 +681,57 @@ extern "C" int gpc_parse_vg_sequences_host(const char* text, uint64_t n_bytes, i
         set_error("gpc_parse_vg_sequences_host: all output arrays or none");
         return GPC_ERR_ARG;
     }
-    for (int pass = 0; pass < (fill ? 2 : 1); ++pass) {
-        const bool store = pass == 1;
-        unsigned long long nodes = 0, bases = 0;
-        long long line = 0, bad = -1;
-        Chunk whole;
-        whole.b = text;
-        whole.e = text + n_bytes;
-        for_lines(whole, [&](const char* b, const char* e) {
-            ++line;
-            if (bad >= 0) return;
-            Cursor c{b, e};
-            const bool ok = for_members(c, [&](const char* k, size_t n) {
-                if (!key_is(k, n, "node")) return skip_value(c);
-                return for_items(c, [&]() {
-                    long long id = 0;
-                    bool have_id = false;
-                    const char* s0 = nullptr;
-                    long long len = 0;
-                    if (!for_members(c, [&](const char* k2, size_t n2) {
-                            if (key_is(k2, n2, "id")) { have_id = true; return parse_json_int(c, id); }
-                            if (key_is(k2, n2, "sequence")) {
-                                c.skip_ws();
-                                if (c.eof() || *c.p != '"') return false;
-                                s0 = c.p + 1;
-                                if (!string_length(c, len)) return false;
-                                return (c.p - 1 - s0) == len;          // no escapes inside
-                            }
-                            return skip_value(c);
-                        }))
-                        return false;
-                    if (!have_id || id <= 0 || id > 2147483647ll) return false;
-                    if (store) {
-                        node_id[nodes] = (int32_t)id;
-                        seq_ptr[nodes] = (int64_t)bases;
-                        if (len) memcpy(seq + bases, s0, (size_t)len);
-                    }
-                    ++nodes;
-                    bases += (unsigned long long)len;
-                    return true;
-                });
+    // one pass: what does not fit the room given is counted, not stored
+    unsigned long long nodes = 0, bases = 0;
+    long long line = 0, bad = -1;
+    Chunk whole;
+    whole.b = text;
+    whole.e = text + n_bytes;
+    for_lines(whole, [&](const char* b, const char* e) {
+        ++line;
+        if (bad >= 0) return;
+        Cursor c{b, e};
+        const bool ok = for_members(c, [&](const char* k, size_t n) {
+            if (!key_is(k, n, "node")) return skip_value(c);
+            return for_items(c, [&]() {
+                long long id = 0;
+                bool have_id = false;
+                const char* s0 = nullptr;
+                long long len = 0;
+                if (!for_members(c, [&](const char* k2, size_t n2) {
+                        if (key_is(k2, n2, "id")) { have_id = true; return parse_json_int(c, id); }
+                        if (key_is(k2, n2, "sequence")) {
+                            c.skip_ws();
+                            if (c.eof() || *c.p != '"') return false;
+                            s0 = c.p + 1;
+                            if (!string_length(c, len)) return false;
+                            return (c.p - 1 - s0) == len;          // no escapes inside
+                        }
+                        return skip_value(c);
+                    }))
+                    return false;
+                if (!have_id || id <= 0 || id > 2147483647ll) return false;
+                if (fill && nodes < want_nodes && bases + (unsigned long long)len <= want_bases) {
+                    node_id[nodes] = (int32_t)id;
+                    seq_ptr[nodes] = (int64_t)bases;
+                    if (len) memcpy(seq + bases, s0, (size_t)len);
+                }
+                ++nodes;
+                bases += (unsigned long long)len;
+                return true;
             });
-            if (!ok) bad = line;
         });
-        if (bad >= 0) {
-            set_error("vg graph file: malformed JSON or escaped sequence (non-blank line %lld)", bad);
-            return GPC_ERR_ARG;
-        }
-        if (pass == 0) {
-            *n_nodes = nodes;
-            *n_bases = bases;
-            if (fill && (want_nodes < nodes || want_bases < bases)) return GPC_ERR_CAPACITY;
-        } else {
-            seq_ptr[nodes] = (int64_t)bases;
-        }
+        if (!ok) bad = line;
+    });
+    if (bad >= 0) {
+        set_error("vg graph file: malformed JSON or escaped sequence (non-blank line %lld)", bad);
+        return GPC_ERR_ARG;
+    }
+    *n_nodes = nodes;
+    *n_bases = bases;
+    if (fill) {
+        if (want_nodes < nodes || want_bases < bases) return GPC_ERR_CAPACITY;
+        seq_ptr[nodes] = (int64_t)bases;
     }
     return GPC_OK;
 }

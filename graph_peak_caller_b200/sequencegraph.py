@@ -50,15 +50,20 @@ class SequenceGraph:
         lib = _lib.load()
         text = _map_file(file_name)
         vp = lambda a: ctypes.c_void_p(a.ctypes.data)
-        n, m = ctypes.c_uint64(0), ctypes.c_uint64(0)
-        _lib.check(lib.gpc_parse_vg_sequences_host(vp(text), text.size, None, None, None,
-                                                   ctypes.byref(n), ctypes.byref(m)))
-        ids = np.empty(int(n.value), dtype=np.int32)
-        ptr = np.zeros(int(n.value) + 1, dtype=np.int64)
-        seq = np.empty(max(int(m.value), 1), dtype=np.uint8)
-        if ids.size:
-            _lib.check(lib.gpc_parse_vg_sequences_host(vp(text), text.size, vp(ids), vp(ptr),
-                                                       vp(seq), ctypes.byref(n), ctypes.byref(m)))
+        # one parse: room for whatever the file could hold (a node object takes 8 bytes or
+        # more, the bases are part of the text; untouched pages of the arrays cost nothing)
+        n, m = ctypes.c_uint64(text.size // 8 + 1), ctypes.c_uint64(text.size)
+        tp = vp(text) if text.size else None
+        while True:
+            ids = np.empty(int(n.value), dtype=np.int32)
+            ptr = np.zeros(int(n.value) + 1, dtype=np.int64)
+            seq = np.empty(max(int(m.value), 1), dtype=np.uint8)
+            status = lib.gpc_parse_vg_sequences_host(tp, text.size, vp(ids), vp(ptr), vp(seq),
+                                                     ctypes.byref(n), ctypes.byref(m))
+            if status != _lib.GPC_ERR_CAPACITY:
+                break
+        _lib.check(status)
+        ids, ptr = ids[:int(n.value)], ptr[:int(n.value) + 1]
         g = self._graph
         index = ids.astype(np.int64) - g.min_node
         if index.size and (index.min() < 0 or index.max() >= g.n_nodes):

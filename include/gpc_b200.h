@@ -329,8 +329,8 @@ int gpc_split_alignments_host(const char* text, uint64_t n_bytes, const int64_t*
  * For the sequence graph behind the reference's FASTA output
  * (SequenceGraph.set_sequences_using_vg_json_graph at preprocess_interface.py:60-66,
  * PeakFasta at peakfasta.py:8-18): node ids in file order, seq_ptr[n_nodes + 1]
- * offsets into `seq`, the bases as they stand in the file.  Two-call protocol as
- * above (*n_nodes, *n_bases = capacities on the second call). */
+ * offsets into `seq`, the bases as they stand in the file.  One pass and capacities
+ * as above (*n_nodes, *n_bases = room on entry, numbers found on return). */
 int gpc_parse_vg_sequences_host(const char* text, uint64_t n_bytes, int32_t* node_id,
                                 int64_t* seq_ptr, char* seq, uint64_t* n_nodes,
                                 uint64_t* n_bases);
