@@ -71,9 +71,18 @@ class SequenceGraph:
         lens = np.diff(ptr)
         if not np.array_equal(lens, g.node_len[index]):
             raise ValueError("%s: sequence lengths differ from the graph's node sizes" % file_name)
-        # scatter every node's bases to its slot: destination of base k of node j
-        dest = np.repeat(g.node_off[index] - ptr[:-1], lens) + np.arange(int(ptr[-1]))
-        self._sequences[dest] = seq[:int(ptr[-1])] | 0x20        # ASCII lower case
+        total = int(ptr[-1])
+        if index.size == 0:
+            return self
+        first, past = int(g.node_off[index[0]]), int(g.node_off[index[-1] + 1])
+        if np.all(index[1:] > index[:-1]) and past - first == total:
+            # nodes in id order with nothing between them (what vg writes): the bases
+            # already stand as the flat array wants them
+            np.bitwise_or(seq[:total], 0x20, out=self._sequences[first:past])   # ASCII lower case
+            return self
+        # any other order: every node's bases to its slot (destination of base k of node j)
+        dest = np.repeat(g.node_off[index] - ptr[:-1], lens) + np.arange(total)
+        self._sequences[dest] = seq[:total] | 0x20
         return self
 
     @classmethod

@@ -40,13 +40,14 @@ def complement(s):
     return s[::-1].translate(str.maketrans("acgtn", "tgcan"))
 
 
-def random_sequence_json(g, rng, chunks=3, min_node=None):
+def random_sequence_json(g, rng, chunks=3, min_node=None, shuffle=True):
     """vg graph JSON lines with random bases; returns (lines, {node id: sequence})."""
     min_node = g.min_node if min_node is None else min_node
     seqs = {int(i + min_node): "".join(rng.choice(list("ACGTN"), size=int(n)))
             for i, n in enumerate(g.node_len)}
     ids = list(seqs)
-    rng.shuffle(ids)
+    if shuffle:
+        rng.shuffle(ids)
     lines = []
     for part in np.array_split(np.array(ids), chunks):
         lines.append(json.dumps({"edge": [], "node": [{"sequence": seqs[int(i)], "name": "x\\\"y",
@@ -106,13 +107,15 @@ def test_files_round_trip(tmp_path):
     assert back.intervals == peaks.intervals and back.intervals[1].graph is g
 
 
-@pytest.mark.parametrize("min_node,chunks", [(1, 1), (1, 4), (500, 3)])
-def test_random_sequences_against_json_module(tmp_path, min_node, chunks):
+@pytest.mark.parametrize("min_node,chunks,shuffle", [(1, 1, True), (1, 4, True), (500, 3, True),
+                                                     (1, 1, False), (500, 4, False)])
+def test_random_sequences_against_json_module(tmp_path, min_node, chunks, shuffle):
+    # nodes in id order (what vg writes: one slice) and in any order (scattered node by node)
     rng = np.random.default_rng(7 + chunks)
     g0 = make_graph(6000, 0.06, seed=5, mnp_frac=0.2)
     src = np.repeat(np.arange(g0.n_nodes), np.diff(g0.succ_ptr))
     g = Graph.from_edges(g0.node_len, src, g0.succ, min_node)
-    lines, seqs = random_sequence_json(g, rng, chunks, min_node)
+    lines, seqs = random_sequence_json(g, rng, chunks, min_node, shuffle)
     name = write(tmp_path / "g.json", "\n".join(lines) + "\n")
     sg = SequenceGraph.from_vg_json_file(name, g)
     for node in rng.choice(list(seqs), size=200):
