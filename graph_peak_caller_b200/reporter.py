@@ -37,7 +37,8 @@ class Reporter:
             PeakCollection(data).to_file(self._base_name + name + ".intervalcollection",
                                          text_file=True)
         elif name == "touched_nodes":
-            np.save(self._base_name + "touched_nodes.npy", np.array(list(data), dtype="int"))
+            ids = data.ids() if hasattr(data, "ids") else list(data)      # TouchedNodes: no list
+            np.save(self._base_name + "touched_nodes.npy", np.array(ids, dtype="int"))
         else:
             return False
         return True

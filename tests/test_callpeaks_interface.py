@@ -378,3 +378,15 @@ def test_create_linear_map_interface(tmp_path):
     out = ci.create_linear_map_interface(args_of(graph=g, graph_file_name=name,
                                                  out_file_base_name=str(tmp_path / "other.npz")))
     assert LinearMap.from_file(str(tmp_path / "other.npz"), g) == LinearMap.from_graph(g)
+
+
+def test_reporter_writes_the_touched_mask_as_ids(tmp_path):
+    # what CallPeaks reports is the device mask's set-like view; the file holds node ids
+    import torch
+    from graph_peak_caller_b200.reporter import Reporter
+    from graph_peak_caller_b200.sample.sparsegraphpileup import TouchedNodes
+    touched = TouchedNodes(torch.tensor([1, 0, 0, 1, 1], dtype=torch.uint8), 10)
+    Reporter(str(tmp_path / "t_")).add("touched_nodes", touched)
+    got = np.load(str(tmp_path / "t_touched_nodes.npy"))
+    assert got.tolist() == [10, 13, 14] and got.dtype == np.dtype("int")
+    assert set(touched) == {10, 13, 14} and 13 in touched and 11 not in touched
