@@ -427,3 +427,32 @@ def test_native_splitter_on_random_lines(tmp_path):
         assert unmapped == len(oingest._split_newlines(want[-1])) if want[-1] else unmapped == 0
 
     run()
+
+
+def test_concurrent_parses_do_not_mix(tmp_path):
+    # the library keeps one pending parse between the counting and the filling call; calls
+    # from several Python threads (ctypes releases the GIL) must still each get their own file
+    import threading
+    g = make_graph(20000, 0.05, seed=31, mnp_frac=0.1)
+    files, wants = [], []
+    for k in range(4):
+        reads = make_reads(g, 3000 + 500 * k, 30, 100, seed=40 + k)
+        lines = [json.dumps(oingest.read_to_alignment(
+            g.node_len, g.min_node, int(reads.start_off[i]), int(reads.end_off[i]),
+            reads.path[reads.path_ptr[i]:reads.path_ptr[i + 1]].tolist())) for i in range(len(reads))]
+        files.append(write_lines(tmp_path / ("r%d.json" % k), lines))
+        wants.append(reads)
+    results = [None] * 16
+
+    def work(j):
+        results[j] = ReadBatch.from_vg_json_file(files[j % 4], g)
+
+    threads = [threading.Thread(target=work, args=(j,)) for j in range(16)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for j, got in enumerate(results):
+        want = wants[j % 4]
+        for f in ("start_node", "start_off", "end_node", "end_off", "path_ptr", "path"):
+            assert np.array_equal(getattr(got, f), getattr(want, f)), (j, f)
