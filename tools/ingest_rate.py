@@ -8,6 +8,7 @@ pyvg's).  No GPU involved.
 bench.py adds the result to its JSON line as "ingest" (rank 0, one GPU)."""
 import json
 import os
+import shutil
 import sys
 import tempfile
 import time
@@ -51,6 +52,28 @@ def alignment_lines(n_reads, read_length=36, seed=7):
     return out
 
 
+def _split_time(name, repeats):
+    """The chromosome splitter (split_vg_json_reads_into_chromosomes) on the same file,
+    three made-up node ranges: one native pass, lines written to four files."""
+    from graph_peak_caller_b200 import conversion
+    d = tempfile.mkdtemp()
+    try:
+        for chrom, (lo, hi) in {"1": (1, 1_000_000), "2": (1_000_001, 2_000_000),
+                                "3": (2_000_001, 4_000_000)}.items():
+            with open(os.path.join(d, "node_range_%s.txt" % chrom), "w") as fh:
+                fh.write("%d:%d" % (lo, hi))
+        copy = os.path.join(d, "reads.json")
+        os.link(name, copy) if os.stat(name).st_dev == os.stat(d).st_dev else shutil.copy(name, copy)
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            conversion.split_vg_json_reads_into_chromosomes("1,2,3", copy, d + "/")
+            times.append(time.perf_counter() - t0)
+        return min(times)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def measure(n_reads=200_000, repeats=3, json_reads=20_000):
     from graph_peak_caller_b200.reads import ReadBatch
     lines = alignment_lines(n_reads)
@@ -68,6 +91,7 @@ def measure(n_reads=200_000, repeats=3, json_reads=20_000):
                 times.append(time.perf_counter() - t0)
             assert len(batch) == n_reads
             best[label] = min(times)
+        best["split"] = _split_time(name, repeats)
     finally:
         os.unlink(name)
     t0 = time.perf_counter()
@@ -81,6 +105,7 @@ def measure(n_reads=200_000, repeats=3, json_reads=20_000):
         mb_per_sec=size / 1e6 / best["all_threads"],
         reads_per_sec_one_thread=n_reads / best["one_thread"],
         json_module_reads_per_sec=min(json_reads, n_reads) / t_json,
+        split_lines_per_sec=n_reads / best["split"], split_mb_per_sec=size / 1e6 / best["split"],
         note="native parser: mapped file, one parse, copy out; best of %d; json module: "
              "json.loads per line only (no interval objects), one thread" % repeats)
 
