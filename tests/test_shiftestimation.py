@@ -168,6 +168,18 @@ def test_estimate_from_files(tmp_path):
     assert ci.estimate_fragment_length([str(tmp_path / "1.nobg")], [sample],
                                        types.SimpleNamespace(min_fold_enrichment=None,
                                                              max_fold_enrichment="50")) == d
+    # run_callpeaks2 without -f and -r: both estimated before the run is set up
+    # (callpeaks_interface.py:201-217); -G / -u then use the estimated length
+    caller = ci.prepare_callpeaks2(types.SimpleNamespace(
+        graph=[str(tmp_path / "1.nobg")], sample=[sample], control=None, fragment_length=None,
+        read_length=None, genome_size="800000", unique_reads="40000",
+        out_name=str(tmp_path / "est_")))
+    assert caller._config.fragment_length == d and caller._config.read_length == R
+    assert caller._config.global_min == 40000 * d / 800000
+    assert ci.shift_estimation(types.SimpleNamespace(
+        chromosomes="1", ob_graphs_location=str(tmp_path),
+        sample_reads_base_name=str(tmp_path / "sample_"),
+        min_fold_enrichment=None, max_fold_enrichment=None)) == d
 
 
 @pytest.mark.skipif(not refbridge.available(), reason="/root/reference not present")
