@@ -15,7 +15,13 @@ third-party ``offsetbasedgraph``) on the reference's own unit-test inputs and
 on randomised graphs by tests/test_oracle_vs_reference.py (runs wherever
 /root/reference exists), and with vectors generated from that reference and
 committed under tests/golden/ (tests/test_oracle_golden.py, runs everywhere).
-Exception: oracle/ingest.py (vg JSON -> reads / graph) restates the absent
+Exceptions: oracle/ingest.py (vg JSON -> reads / graph) restates the absent
 third-party package pyvg and is UNPINNED against it; its header lists the
-anchors the reference tree offers instead.
+anchors the reference tree offers instead (its chromosome splitter, on the other
+hand, is pinned: byte-identical files with the live reference's).  oracle/shift.py
+(fragment-length estimation) is pinned against the live PeakModel / HaploTyper /
+LinearFilter and the reference's own known answers, except for ONE rule taken from the
+absent offsetbasedgraph: the linear offset of a reverse-strand read start (half
+pinned, see its header).  oracle/summits.py is pinned against the live
+PeakCollection.cut_around_summit and the reference's known answer.
 """
