@@ -355,7 +355,17 @@ void spread_over_cpus(std::vector<std::thread>& pool) {
 template <typename LineFn>
 void parse_chunks(const char* text, uint64_t n_bytes, int32_t n_threads, LineFn& line_fn,
                   std::vector<ParsedChunk>& out) {
-    unsigned threads = n_threads > 0 ? (unsigned)n_threads : std::thread::hardware_concurrency();
+    unsigned threads = n_threads > 0 ? (unsigned)n_threads : 0;
+    if (threads == 0) {                      // GPC_INGEST_THREADS, else every CPU this process may use
+        const char* env = getenv("GPC_INGEST_THREADS");
+        if (env && atoi(env) > 0) threads = (unsigned)atoi(env);
+    }
+    if (threads == 0) {
+        cpu_set_t allowed;
+        CPU_ZERO(&allowed);
+        if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) threads = (unsigned)CPU_COUNT(&allowed);
+    }
+    if (threads == 0) threads = std::thread::hardware_concurrency();
     if (threads == 0) threads = 1;
     if (threads > 64) threads = 64;
     if (n_bytes < (1u << 20)) threads = 1;

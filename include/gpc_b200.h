@@ -268,7 +268,9 @@ uint64_t gpc_profile_report(char* buf, uint64_t capacity);
  *     {"start": 3, "end": 17, "region_paths": [12, 13, 15], "direction": 1}
  * keys in any order, unknown keys skipped, blank lines ignored.  A read's start /
  * end node is its first / last region path.  `text` need not be 0-terminated.
- * All pointers are host pointers; `n_threads` <= 0 uses every host core.
+ * All pointers are host pointers; `n_threads` <= 0 uses GPC_INGEST_THREADS from the
+ * environment if set, else every CPU the process may run on; each worker is placed on
+ * its own CPU when it starts.
  * Call once with all output arrays NULL to get the counts, allocate
  * (path_ptr: n_reads + 1), call again with *n_reads / *n_path_nodes set to the
  * capacities.  The counting call keeps its parse and the filling call for the same
