@@ -103,6 +103,14 @@ def count_unique_reads(chromosomes, graph_file_names, reads_file_names):
     return unique_reads
 
 
+def split_vg_json_reads_into_chromosomes(args):
+    """preprocess_interface.py:83-145 with its ``args`` (``chromosomes``,
+    ``vg_json_reads_file_name``, ``range_files_base_name``); the work is
+    ``conversion.split_vg_json_reads_into_chromosomes``."""
+    from .conversion import split_vg_json_reads_into_chromosomes as split
+    return split(args.chromosomes, args.vg_json_reads_file_name, args.range_files_base_name)
+
+
 def count_unique_reads_interface(args):
     """preprocess_interface.py:11-18"""
     chromosomes = args.chromosomes.split(",")

@@ -74,6 +74,14 @@ def test_split_into_chromosomes_as_the_reference_test(tmp_path):
     unmapped = conversion.split_vg_json_reads_into_chromosomes("1,2,3,4,5", reads,
                                                                str(tmp_path) + "/")
     assert unmapped == 0
+    # the reference's own calling form (an args namespace) gives the same files
+    import types
+    from graph_peak_caller_b200 import callpeaks_interface
+    first = {c: (tmp_path / ("vg_alignments_%s.json" % c)).read_bytes() for c in ranges}
+    assert callpeaks_interface.split_vg_json_reads_into_chromosomes(types.SimpleNamespace(
+        chromosomes="1,2,3,4,5", vg_json_reads_file_name=reads,
+        range_files_base_name=str(tmp_path) + "/")) == 0
+    assert first == {c: (tmp_path / ("vg_alignments_%s.json" % c)).read_bytes() for c in ranges}
     for chrom, text in ranges.items():
         part = ReadBatch.from_vg_json_file(str(tmp_path / ("vg_alignments_%s.json" % chrom)))
         lo, hi = (int(v) for v in text.split(":"))
