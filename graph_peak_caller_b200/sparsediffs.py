@@ -318,16 +318,20 @@ class SparseDiffs:
         diffs[0] = pileup[0]
         return cls(changes, diffs)
 
+    # In-place scaling (reference sparsediffs.py:200-206).  A kernel-made track keeps its
+    # runs on the device with a lazy scale; once somebody has looked at ``_indices`` /
+    # ``_diffs`` a host copy exists as well, and BOTH must follow (device_runs() is what
+    # the p-value stage reads first).
     def __itruediv__(self, scalar):
-        if self._h_indices is None:
+        if self._runs is not None:
             self._scale /= scalar
-        else:
+        if self._h_indices is not None:
             self._h_diffs = self._h_diffs / scalar
         return self
 
     def __imul__(self, scalar):
-        if self._h_indices is None:
+        if self._runs is not None:
             self._scale *= scalar
-        else:
+        if self._h_indices is not None:
             self._h_diffs = self._h_diffs * scalar
         return self

@@ -33,8 +33,9 @@ class PValuesFinder:
         spos, sval, sscale = _runs_on_device(self.sample)
         cpos, cval, cscale = _runs_on_device(self.control)
         if sval.dtype != torch.int32:
-            # host-built sample track: counts are integer valued (possibly scaled)
-            sval = sval.to(torch.float64).round().to(torch.int32)
+            # host-built sample track: poisson.logsf floors k (sparsepvalues.py:21); the
+            # epsilon only absorbs the residue of a float cumsum of integer-valued steps
+            sval = torch.floor(sval.to(torch.float64) + 1e-9).to(torch.int32)
         cval = cval.to(torch.float64)
         pos, p = kernels.pvalues(spos, sval, sscale, cpos, cval, cscale)
         return SparseValues(pos, p)

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY -- make /root/reference importable on numpy 2 / scipy 1.18.
 
-Usage (build container only; /root/reference does not exist on the GPU box):
+Usage (build container: /root/reference; GPU box: oracle/_ref, see oracle/build_ref.py):
 
     import refcompat; refcompat.install()
     import graph_peak_caller            # the unmodified reference
@@ -8,7 +8,18 @@ Usage (build container only; /root/reference does not exist on the GPU box):
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("GPC_REFERENCE_ROOT", "/root/reference")
+_INSTALLED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_ref")
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box the copy that
+    oracle/build_ref.py pip-installed into oracle/_ref (git-ignored, travels)."""
+    if os.path.isdir("/root/reference/graph_peak_caller"):
+        return "/root/reference"
+    return _INSTALLED
+
+
+REFERENCE_ROOT = os.environ.get("GPC_REFERENCE_ROOT") or _default_root()
 
 
 def available():

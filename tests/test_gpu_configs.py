@@ -101,7 +101,7 @@ def medium(request):
     else:
         from graph_peak_caller_b200.synthetic import CONFIGS
         cfg = CONFIGS["chr22_scale"]
-        g = make_graph(cfg["backbone_bp"], cfg["site_rate"], seed=20261001)
+        g = make_graph(cfg["chromosomes"][0][1], cfg["site_rate"], seed=20261001)
         s = make_reads(g, cfg["n_sample"], 36, 200, seed=1)
         c = make_reads(g, cfg["n_control"], 36, 200, seed=2, peak_frac=0.0, dup_frac=0.0)
     lm = LinearMap.from_graph(g).as_arrays()
@@ -220,7 +220,7 @@ def test_mhc_shaped_config_full_size_vs_oracle():
     cfg = CONFIGS["mhc_shaped"]
     R, F = cfg["read_length"], cfg["fragment_length"]
     seed = config_seed(1)
-    g = make_graph(cfg["backbone_bp"], cfg["site_rate"], seed=seed)
+    g = make_graph(cfg["chromosomes"][0][1], cfg["site_rate"], seed=seed)
     s = make_reads(g, cfg["n_sample"], R, F, seed=seed + 1)
     c = make_reads(g, cfg["n_control"], R, F, seed=seed + 2, peak_frac=0.0, dup_frac=0.0)
     lm = LinearMap.from_graph(g)
