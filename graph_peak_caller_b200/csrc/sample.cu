@@ -18,6 +18,8 @@
 #include "radix_sort.cuh"
 #include "scan.cuh"
 
+#include <mutex>
+
 namespace gpc {
 
 // event key = position << 3 | tag << 1 | (delta is -1)
@@ -28,19 +30,37 @@ constexpr int WALK_THREADS = 128;
 constexpr int WALK_STAGE = 1536;     // staged events per block (6 KB)
 constexpr int FRONTIER_CAP = 32;
 
+// Where the +1 / -1 steps of the walk go.  DENSE == false: packed event keys,
+// staged per block in shared memory, appended to one global list that is then
+// sorted (sparse read sets: whole-genome depth).  DENSE == true: straight into
+// a difference array over the graph's positions, one 64-bit word per position
+// holding both pileups (high word fragment, low word direct; the borrow of a
+// negative low word is undone when unpacking) -- one fire-and-forget 64-bit
+// reduction per step, no sort (read sets with more than ~0.1 events per base).
+template <bool DENSE>
 struct Emitter {
     uint32_t* s_buf;
     unsigned* s_count;
     uint32_t* g_events;
     unsigned long long* g_count;
     unsigned long long g_cap;
+    unsigned long long* dense;
     uint32_t G;
     bool fwd;
+    unsigned n_emitted;
 
     // +1 (open) or -1 (close) at oriented position p
     __device__ __forceinline__ void emit(uint32_t p, bool close, unsigned tag) {
         uint32_t pos = fwd ? p : (G - p);
         bool minus = fwd ? close : !close;
+        if (DENSE) {
+            const long long d = minus ? -1ll : 1ll;
+            const long long add = tag == TAG_BOTH ? d * ((1ll << 32) + 1ll)
+                                                  : (tag == TAG_DIRECT ? d : d * (1ll << 32));
+            atomicAdd(dense + pos, (unsigned long long)add);
+            ++n_emitted;
+            return;
+        }
         uint32_t key = (pos << EVENT_POS_SHIFT) | (tag << 1) | (minus ? 1u : 0u);
         unsigned slot = atomicAdd(s_count, 1u);
         if (slot < WALK_STAGE) {
@@ -164,28 +184,48 @@ struct Frontier {
     }
 };
 
+template <bool DENSE>
 __global__ void __launch_bounds__(WALK_THREADS, 10)
 walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restrict__ read_index,
                   unsigned n_reads, int extension, uint32_t* __restrict__ events,
                   unsigned long long event_cap, unsigned long long* __restrict__ event_count,
+                  unsigned long long* __restrict__ dense,
                   uint8_t* __restrict__ touched, int* __restrict__ err) {
-    __shared__ uint32_t s_buf[WALK_STAGE];
+    __shared__ uint32_t s_buf[DENSE ? 1 : WALK_STAGE];
     __shared__ unsigned s_count;
     __shared__ unsigned long long s_gbase;
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
 
     const unsigned i = blockIdx.x * WALK_THREADS + threadIdx.x;
+    unsigned n_emitted = 0;
     if (i < n_reads) {
         const unsigned r = read_index ? read_index[i] : i;
-        const int sn = reads.start_node[r], en = reads.end_node[r];
-        const int so = reads.start_off[r], eo = reads.end_off[r];
-        const long long p0 = reads.path_ptr32 ? (long long)reads.path_ptr32[r] : reads.path_ptr[r];
-        const long long p1 = reads.path_ptr32 ? (long long)reads.path_ptr32[r + 1] : reads.path_ptr[r + 1];
-        const bool fwd = sn > 0;
+        int so, eo;
+        long long p0, p1;
+        bool fwd, ok;
+        if (reads.hdr) {
+            // one 16-byte record per read {path offset, path nodes | bad << 31, start
+            // offset, end offset}: a walk in graph order gathers one sector per read
+            // instead of six (the start / end node are the ends of the path)
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(reads.hdr) + r);
+            p0 = (long long)h.x;
+            p1 = p0 + (long long)(h.y & 0x7fffffffu);
+            so = (int)h.z;
+            eo = (int)h.w;
+            ok = !(h.y >> 31) && p1 > p0 && so >= 0 && eo >= 0;
+            fwd = ok ? reads.path[p0] > 0 : true;
+        } else {
+            const int sn = reads.start_node[r], en = reads.end_node[r];
+            so = reads.start_off[r];
+            eo = reads.end_off[r];
+            p0 = reads.path_ptr32 ? (long long)reads.path_ptr32[r] : reads.path_ptr[r];
+            p1 = reads.path_ptr32 ? (long long)reads.path_ptr32[r + 1] : reads.path_ptr[r + 1];
+            fwd = sn > 0;
+            ok = (p1 > p0) && ((en > 0) == fwd) && so >= 0 && eo >= 0;
+        }
         const uint32_t n = graph.n_nodes, G = graph.size_bp;
         const int mn = graph.min_node;
-        bool ok = (p1 > p0) && ((en > 0) == fwd) && so >= 0 && eo >= 0;
         if (ok) {
             for (long long q = p0; q < p1; ++q) {
                 int id = reads.path[q];
@@ -196,7 +236,7 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
         if (!ok) {
             atomicExch(err, GPC_ERR_INVALID_INTERVAL);
         } else {
-            Emitter em{s_buf, &s_count, events, event_count, event_cap, G, fwd};
+            Emitter<DENSE> em{s_buf, &s_count, events, event_count, event_cap, dense, G, fwd, 0u};
             // ---- read body --------------------------------------------------
             uint32_t ce = 0;          // oriented end of the currently open interval
             uint32_t last_len = 0, last_start = 0;
@@ -264,7 +304,15 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
             const bool overflow = fr.overflow;
             em.emit(ce, true, TAG_FRAG);
             if (overflow) atomicExch(err, GPC_ERR_FRONTIER_OVERFLOW);
+            n_emitted = em.n_emitted;
         }
+    }
+    if (DENSE) {        // only the number of steps is reported (one add per block)
+        n_emitted = warp_sum(n_emitted);
+        if (lane_id() == 0 && n_emitted) atomicAdd(&s_count, n_emitted);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_count) atomicAdd(event_count, (unsigned long long)s_count);
+        return;
     }
     __syncthreads();
     const unsigned staged = min(s_count, (unsigned)WALK_STAGE);
@@ -493,6 +541,129 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
     }
 }
 
+
+// ---- difference array -> two canonical run-length tracks ----------------------
+//
+// dense[pos] holds the net step of both pileups at graph position pos (packed as the
+// walk deposits it).  One streaming pass: a tile of 4096 positions (32 KB) is loaded
+// with 16-byte coalesced loads into shared memory laid out with a 16-byte pad per
+// thread row (so that the row reads below are conflict-free), the words are zeroed
+// behind the read (the array is clean again for the next call: no memset kernel),
+// every thread walks its 16 consecutive positions, tile totals and entry counts go
+// through two packed chained scans walked by two warps at once, and an entry
+// (position, running sum) is written wherever the net step of a track is non-zero,
+// plus always one at position 0 -- the canonical SparseValues of the reference
+// (sparsediffs.py:13-20,137-141).  HBM-bound: 8 bytes read + 8 bytes of zeroes per
+// position, 8 bytes per entry out.
+
+constexpr int DR_THREADS = 256;
+constexpr int DR_ITEMS = 16;
+constexpr int DR_TILE = DR_THREADS * DR_ITEMS;          // positions per tile
+constexpr int DR_ROW_BYTES = DR_ITEMS * 8 + 16;         // padded row of one thread
+
+__device__ __forceinline__ void dense_unpack(unsigned long long w, int& dfrag, int& ddir) {
+    ddir = (int)(unsigned)(w & 0xffffffffull);
+    dfrag = (int)(((long long)w - (long long)ddir) >> 32);
+}
+
+__global__ void __launch_bounds__(DR_THREADS)
+dense_runs_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
+                  uint32_t* __restrict__ frag_idx, int32_t* __restrict__ frag_val,
+                  uint32_t* __restrict__ dir_idx, int32_t* __restrict__ dir_val,
+                  unsigned long long cap,
+                  unsigned long long* __restrict__ st_tot /* zeroed */,
+                  unsigned long long* __restrict__ st_cnt /* zeroed */,
+                  unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts) {
+    __shared__ __align__(16) unsigned char s_rows[DR_THREADS * DR_ROW_BYTES];
+    __shared__ long long s_scan64[33];
+    __shared__ unsigned s_slot;
+    __shared__ unsigned long long s_base[2];
+    const unsigned tile = claim_tile(ticket, &s_slot);
+    const unsigned tile_base = tile * DR_TILE;
+    // ---- load (striped: a warp's loads are 512 contiguous bytes), zero behind -----
+#pragma unroll
+    for (int j = 0; j < DR_ITEMS / 2; ++j) {
+        const unsigned u = j * DR_THREADS + threadIdx.x;        // 16-byte unit inside the tile
+        const unsigned gpos = tile_base + 2 * u;
+        ulonglong2 v = make_ulonglong2(0ull, 0ull);
+        if (gpos + 1 < n_pos) {
+            ulonglong2* g = reinterpret_cast<ulonglong2*>(dense + gpos);
+            v = *g;
+            if (v.x | v.y) *g = make_ulonglong2(0ull, 0ull);
+        } else if (gpos < n_pos) {
+            v.x = dense[gpos];
+            if (v.x) dense[gpos] = 0ull;
+        }
+        *reinterpret_cast<ulonglong2*>(s_rows + (u >> 3) * DR_ROW_BYTES + (u & 7) * 16) = v;
+    }
+    __syncthreads();
+    // ---- thread-local pass over 16 consecutive positions ----------------------------
+    unsigned long long w[DR_ITEMS];
+#pragma unroll
+    for (int k = 0; k < DR_ITEMS / 2; ++k) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(s_rows + threadIdx.x * DR_ROW_BYTES + k * 16);
+        w[2 * k] = v.x;
+        w[2 * k + 1] = v.y;
+    }
+    const unsigned base = tile_base + threadIdx.x * DR_ITEMS;
+    int tf = 0, td = 0;
+    unsigned mf = 0, md = 0;              // bit k: position base + k gets an entry
+#pragma unroll
+    for (int k = 0; k < DR_ITEMS; ++k) {
+        int df, dd;
+        dense_unpack(w[k], df, dd);
+        tf += df;
+        td += dd;
+        const bool first = base + k == 0;                      // (0, value) always exists
+        if (df != 0 || first) mf |= 1u << k;
+        if (dd != 0 || first) md |= 1u << k;
+    }
+    // block scans: totals (high word fragment, low word direct) and entry counts (2 x 31 bits)
+    long long tile_tot, tile_cnt;
+    const long long ex_tot = block_excl_sum<long long>(((long long)tf << 32) + (long long)td, s_scan64, tile_tot);
+    const long long ex_cnt = block_excl_sum<long long>(((long long)__popc(mf) << 31) | (long long)__popc(md),
+                                                       s_scan64, tile_cnt);
+    // the two chains are independent: warp 0 resolves the totals, warp 1 the counts
+    if (threadIdx.x < 32) {
+        unsigned long long ex = lookback_excl_warp(st_tot, tile, (unsigned long long)tile_tot & LB_MASK);
+        if (threadIdx.x == 0) s_base[0] = ex;
+    } else if (threadIdx.x < 64) {
+        unsigned long long b = lookback_excl_warp(st_cnt, tile, (unsigned long long)tile_cnt);
+        if (threadIdx.x == 32) {
+            s_base[1] = b;
+            if (tile == gridDim.x - 1) {
+                const unsigned long long tot = b + (unsigned long long)tile_cnt;
+                out_counts[0] = tot >> 31;
+                out_counts[1] = tot & 0x7fffffffull;
+            }
+        }
+    }
+    __syncthreads();
+    int run_f, run_d;
+    {
+        const long long v = ((long long)(s_base[0] << 2) >> 2) + ex_tot;     // sign-extend 62 bits
+        run_d = (int)(unsigned)(v & 0xffffffffll);
+        run_f = (int)((v - (long long)run_d) >> 32);
+    }
+    const unsigned long long w_pk = s_base[1] + (unsigned long long)ex_cnt;
+    unsigned long long w0 = w_pk >> 31, w1 = w_pk & 0x7fffffffull;
+#pragma unroll
+    for (int k = 0; k < DR_ITEMS; ++k) {
+        int df, dd;
+        dense_unpack(w[k], df, dd);
+        run_f += df;
+        run_d += dd;
+        if ((mf >> k) & 1u) {
+            if (w0 < cap) { frag_idx[w0] = base + k; frag_val[w0] = run_f; }
+            ++w0;
+        }
+        if ((md >> k) & 1u) {
+            if (w1 < cap) { dir_idx[w1] = base + k; dir_val[w1] = run_d; }
+            ++w1;
+        }
+    }
+}
+
 // ---- duplicate filter (hash set keyed by start position) --------------------
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
@@ -565,6 +736,20 @@ __global__ void walk_order_keys_kernel(const int32_t* __restrict__ start_node,
     vals[i] = r;
 }
 
+// gpc_reads_t.hdr: one 16-byte record per read (see include/gpc_b200.h)
+__global__ void read_headers_kernel(gpc_reads_t reads, unsigned n, uint4* __restrict__ hdr) {
+    unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const long long p0 = reads.path_ptr32 ? (long long)reads.path_ptr32[r] : reads.path_ptr[r];
+    const long long p1 = reads.path_ptr32 ? (long long)reads.path_ptr32[r + 1] : reads.path_ptr[r + 1];
+    const long long k = p1 - p0;
+    bool bad = k <= 0 || k >= (1ll << 31) || p0 < 0 || p0 >= (1ll << 32);
+    if (!bad)
+        bad = reads.path[p0] != reads.start_node[r] || reads.path[p1 - 1] != reads.end_node[r];
+    hdr[r] = make_uint4((unsigned)p0, (unsigned)(bad ? 0 : k) | (bad ? 0x80000000u : 0u),
+                        (unsigned)reads.start_off[r], (unsigned)reads.end_off[r]);
+}
+
 }  // namespace gpc
 
 using namespace gpc;
@@ -599,12 +784,45 @@ extern "C" int gpc_unique_reads(const int32_t* start_node, const int32_t* start_
     return GPC_OK;
 }
 
-extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* reads,
-                                 const uint32_t* read_index, uint64_t n_reads, int32_t extension,
-                                 uint32_t* events, uint64_t event_capacity,
-                                 uint64_t* n_events, uint8_t* touched, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    *n_events = 0;
+// Walk order: read indices sorted by start node / 2^shift (16-bit keys, two passes), so
+// that neighbouring threads walk neighbouring nodes.  The sorted index list lives in `keep`.
+struct WalkOrder { Scratch k0, k1, v0, v1; };
+static int walk_order(const gpc_graph_t* graph, const gpc_reads_t* reads, const uint32_t** read_index,
+                      uint64_t n_reads, WalkOrder& keep, cudaStream_t stream) {
+    if (!(n_reads >= (1u << 16) && n_reads < (1ull << 30)) || getenv("GPC_NO_WALK_ORDER")) return GPC_OK;
+    int bits = 1;
+    while ((1ull << bits) < graph->n_nodes) ++bits;
+    const int shift = bits > 16 ? bits - 16 : 0;
+    GPC_CUDA(keep.k0.alloc(n_reads * 4, stream));
+    GPC_CUDA(keep.k1.alloc(n_reads * 4, stream));
+    GPC_CUDA(keep.v0.alloc(n_reads * 4, stream));
+    GPC_CUDA(keep.v1.alloc(n_reads * 4, stream));
+    GPC_PROF_BYTES("walk_order_keys", 16.0 * n_reads);
+    walk_order_keys_kernel<<<div_up(n_reads, 256), 256, 0, stream>>>(
+        reads->start_node, *read_index, (unsigned)n_reads, graph->min_node, graph->n_nodes,
+        shift, keep.k0.as<uint32_t>(), keep.v0.as<uint32_t>());
+    GPC_LAUNCH_CHECK();
+    bool in_tmp = false;
+    GPC_TRY((radix_sort<uint32_t, true>(keep.k0.as<uint32_t>(), keep.k1.as<uint32_t>(),
+                                        keep.v0.as<uint32_t>(), keep.v1.as<uint32_t>(), n_reads, 0,
+                                        bits - shift, false, &in_tmp, stream)));
+    *read_index = in_tmp ? keep.v1.as<uint32_t>() : keep.v0.as<uint32_t>();
+    return GPC_OK;
+}
+
+static int walk_error(int e) {
+    if (e == GPC_ERR_INVALID_INTERVAL) {
+        set_error("Interval has node(s) not part of graph/pileup");
+        return e;
+    }
+    if (e == GPC_ERR_FRONTIER_OVERFLOW) {
+        set_error("extension frontier exceeded %d simultaneous nodes", 4 + FRONTIER_CAP);
+        return e;
+    }
+    return GPC_OK;
+}
+
+static int check_sample_args(const gpc_graph_t* graph, int32_t extension) {
     if (extension <= 0) {
         set_error("Invalid extension size %d used. Must be positive. Is fragment length < read length?", extension);
         return GPC_ERR_ARG;
@@ -613,6 +831,31 @@ extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* re
         set_error("graph of %u bp exceeds the 2^29 limit of the packed event key", graph->size_bp);
         return GPC_ERR_ARG;
     }
+    return GPC_OK;
+}
+
+// bytes the walk must move per read: its header (or the six SoA fields), its index in
+// the walk order; the path nodes and graph records are counted per visit in DESIGN.md
+static double walk_read_bytes(const gpc_reads_t* reads) { return reads->hdr ? 20.0 : 36.0; }
+
+extern "C" int gpc_build_read_headers(const gpc_reads_t* reads, uint32_t* hdr, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (reads->n_reads == 0) return GPC_OK;
+    if (reads->n_reads >= (1ull << 31)) { set_error("too many reads"); return GPC_ERR_ARG; }
+    GPC_PROF_BYTES("read_headers", 48.0 * reads->n_reads);
+    read_headers_kernel<<<div_up(reads->n_reads, 256), 256, 0, stream>>>(
+        *reads, (unsigned)reads->n_reads, reinterpret_cast<uint4*>(hdr));
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+
+extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* reads,
+                                 const uint32_t* read_index, uint64_t n_reads, int32_t extension,
+                                 uint32_t* events, uint64_t event_capacity,
+                                 uint64_t* n_events, uint8_t* touched, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    *n_events = 0;
+    GPC_TRY(check_sample_args(graph, extension));
     GPC_CUDA(cudaMemsetAsync(touched, 0, graph->n_nodes, stream));
     if (n_reads == 0) return GPC_OK;
     Scratch ctr;
@@ -620,48 +863,163 @@ extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* re
     GPC_CUDA(cudaMemsetAsync(ctr.p, 0, 16, stream));
     unsigned long long* count = ctr.as<unsigned long long>();
     int* err = reinterpret_cast<int*>(count + 1);
-    // walk order: read indices sorted by start node / 2^shift (16-bit keys, two passes)
-    Scratch ok0, ok1, ov0, ov1;
-    if (n_reads >= (1u << 16) && n_reads < (1ull << 30) && !getenv("GPC_NO_WALK_ORDER")) {
-        int bits = 1;
-        while ((1ull << bits) < graph->n_nodes) ++bits;
-        const int shift = bits > 16 ? bits - 16 : 0;
-        GPC_CUDA(ok0.alloc(n_reads * 4, stream));
-        GPC_CUDA(ok1.alloc(n_reads * 4, stream));
-        GPC_CUDA(ov0.alloc(n_reads * 4, stream));
-        GPC_CUDA(ov1.alloc(n_reads * 4, stream));
-        GPC_PROF("walk_order_keys");
-        walk_order_keys_kernel<<<div_up(n_reads, 256), 256, 0, stream>>>(
-            reads->start_node, read_index, (unsigned)n_reads, graph->min_node, graph->n_nodes,
-            shift, ok0.as<uint32_t>(), ov0.as<uint32_t>());
-        GPC_LAUNCH_CHECK();
-        bool in_tmp = false;
-        GPC_TRY((radix_sort<uint32_t, true>(ok0.as<uint32_t>(), ok1.as<uint32_t>(),
-                                            ov0.as<uint32_t>(), ov1.as<uint32_t>(), n_reads, 0,
-                                            bits - shift, false, &in_tmp, stream)));
-        read_index = in_tmp ? ov1.as<uint32_t>() : ov0.as<uint32_t>();
-    }
+    WalkOrder order;
+    GPC_TRY(walk_order(graph, reads, &read_index, n_reads, order, stream));
     GPC_PROF("walk_reads");
-    walk_reads_kernel<<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+    walk_reads_kernel<false><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
         *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
-        touched, err);
+        nullptr, touched, err);
     GPC_LAUNCH_CHECK();
     unsigned long long h[2] = {0, 0};
     GPC_READ_BACK({ctr.p, h, (unsigned)(16)});
     *n_events = h[0];
-    // reads SoA (4 x int32 + 2 x int64 path_ptr + index) in, events out; the path
-    // nodes and the graph records it gathers are counted in DESIGN.md per read
-    prof_add_bytes("walk_reads", 36.0 * (double)n_reads + 4.0 * (double)h[0]);
-    int e = (int)(h[1] & 0xffffffffu);
-    if (e == GPC_ERR_INVALID_INTERVAL) {
-        set_error("Interval has node(s) not part of graph/pileup");
-        return e;
-    }
-    if (e == GPC_ERR_FRONTIER_OVERFLOW) {
-        set_error("extension frontier exceeded %d simultaneous nodes", FRONTIER_CAP);
-        return e;
-    }
+    prof_add_bytes("walk_reads", walk_read_bytes(reads) * (double)n_reads + 4.0 * (double)h[0]);
+    GPC_TRY(walk_error((int)(h[1] & 0xffffffffu)));
     if (h[0] > event_capacity) return GPC_ERR_CAPACITY;   // caller retries with *n_events
+    return GPC_OK;
+}
+
+// ---- the difference array of the dense path: one per device, kept between calls and
+// left zeroed by dense_runs_kernel (a failed call marks it dirty) -------------------------
+namespace gpc {
+struct DenseWorkspace {
+    unsigned long long* p = nullptr;
+    size_t words = 0;
+    bool busy = false, dirty = false;
+    cudaEvent_t done = nullptr;
+    cudaStream_t last_stream = nullptr;
+};
+static DenseWorkspace g_dense[64];
+static std::mutex g_dense_mutex;
+
+// Hands out `words` zeroed 64-bit words valid in `stream` order.  *ws == nullptr means the
+// cached array is in use by another host thread: `fallback` then owns a pool allocation.
+static int dense_acquire(size_t words, cudaStream_t stream, DenseWorkspace** ws, Scratch& fallback,
+                         unsigned long long** out) {
+    int dev = 0;
+    GPC_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_dense_mutex);
+    DenseWorkspace& w = g_dense[dev & 63];
+    if (w.busy) {
+        *ws = nullptr;
+        GPC_CUDA(fallback.alloc(words * 8, stream));
+        GPC_CUDA(cudaMemsetAsync(fallback.p, 0, words * 8, stream));
+        *out = fallback.as<unsigned long long>();
+        return GPC_OK;
+    }
+    if (w.done && w.last_stream != stream) GPC_CUDA(cudaStreamWaitEvent(stream, w.done, 0));
+    if (words > w.words) {
+        if (w.p) { GPC_CUDA(cudaDeviceSynchronize()); GPC_CUDA(cudaFree(w.p)); w.p = nullptr; w.words = 0; }
+        const size_t want = words + words / 8 + 4096;           // some slack: chromosomes differ in size
+        GPC_CUDA(cudaMalloc((void**)&w.p, want * 8));
+        w.words = want;
+        w.dirty = true;
+    }
+    if (w.dirty) {
+        GPC_CUDA(cudaMemsetAsync(w.p, 0, w.words * 8, stream));
+        w.dirty = false;
+    }
+    if (!w.done) GPC_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+    w.busy = true;
+    *ws = &w;
+    *out = w.p;
+    return GPC_OK;
+}
+static void dense_release(DenseWorkspace* ws, bool clean, cudaStream_t stream) {
+    if (!ws) return;
+    std::lock_guard<std::mutex> lock(g_dense_mutex);
+    ws->busy = false;
+    if (!clean) ws->dirty = true;
+    ws->last_stream = stream;
+    cudaEventRecord(ws->done, stream);
+}
+}  // namespace gpc
+
+static int events_to_runs_impl(uint32_t* events, uint32_t* events_tmp, uint64_t n_events,
+                               uint32_t size_bp, uint32_t* frag_idx, int32_t* frag_val,
+                               uint64_t* n_frag, uint32_t* direct_idx, int32_t* direct_val,
+                               uint64_t* n_direct, cudaStream_t stream);
+
+extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* reads,
+                                 const uint32_t* read_index, uint64_t n_reads, int32_t extension,
+                                 uint32_t* frag_idx, int32_t* frag_val, uint32_t* direct_idx,
+                                 int32_t* direct_val, uint64_t capacity, uint64_t* n_frag,
+                                 uint64_t* n_direct, uint64_t* n_events, uint8_t* touched,
+                                 int32_t mode, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    *n_frag = *n_direct = *n_events = 0;
+    GPC_TRY(check_sample_args(graph, extension));
+    if (capacity < 1) { *n_frag = *n_direct = 1; return GPC_ERR_CAPACITY; }
+    if (mode == 0) {
+        // a read deposits ~2 steps (more across bubbles); the array costs ~16 bytes per
+        // position, the list ~40 bytes per step (three sort passes + the run kernel)
+        if (const char* e = getenv("GPC_SAMPLE_PILEUP_MODE")) mode = atoi(e);
+        if (mode != 1 && mode != 2)
+            mode = (20.0 * (double)n_reads >= (double)graph->size_bp) ? 1 : 2;
+    }
+    if (mode == 2 || n_reads == 0) {
+        // event list: capacity guess of six steps per read, grown once if the walk needs more
+        GPC_CUDA(cudaMemsetAsync(touched, 0, graph->n_nodes, stream));
+        uint64_t cap = n_reads * 6 + 1024, n_ev = 0;
+        for (int attempt = 0;; ++attempt) {
+            Scratch ev, tmp;
+            GPC_CUDA(ev.alloc(cap * 4, stream));
+            int st = gpc_sample_events(graph, reads, read_index, n_reads, extension, ev.as<uint32_t>(),
+                                       cap, &n_ev, touched, stream_);
+            if (st == GPC_ERR_CAPACITY && attempt == 0) { cap = n_ev + 1024; continue; }
+            GPC_TRY(st);
+            *n_events = n_ev;
+            if (n_ev + 1 > capacity) { *n_frag = *n_direct = n_ev + 1; return GPC_ERR_CAPACITY; }
+            GPC_CUDA(tmp.alloc(cap * 4, stream));
+            return events_to_runs_impl(ev.as<uint32_t>(), tmp.as<uint32_t>(), n_ev, graph->size_bp,
+                                       frag_idx, frag_val, n_frag, direct_idx, direct_val, n_direct,
+                                       stream);
+        }
+    }
+    // ---- difference array ------------------------------------------------------------
+    GPC_CUDA(cudaMemsetAsync(touched, 0, graph->n_nodes, stream));
+    const unsigned n_pos = graph->size_bp + 1;           // a fragment may close at size_bp
+    const unsigned tiles = div_up(n_pos, DR_TILE);
+    DenseWorkspace* ws = nullptr;
+    Scratch fallback, sc;
+    unsigned long long* dense = nullptr;
+    GPC_TRY(dense_acquire(n_pos, stream, &ws, fallback, &dense));
+    struct Release {           // every way out gives the array back; only a finished scan leaves it clean
+        DenseWorkspace* ws; cudaStream_t s; bool clean;
+        ~Release() { dense_release(ws, clean, s); }
+    } rel{ws, stream, false};
+    const size_t bytes = (size_t)tiles * 16 + 64;
+    GPC_CUDA(sc.alloc(bytes, stream));
+    GPC_CUDA(cudaMemsetAsync(sc.p, 0, bytes, stream));
+    char* p = sc.as<char>();
+    unsigned long long* counts = reinterpret_cast<unsigned long long*>(p);            // 2 run counts
+    unsigned long long* n_steps = counts + 2;
+    int* err = reinterpret_cast<int*>(counts + 3);
+    unsigned* ticket = reinterpret_cast<unsigned*>(p + 32);
+    unsigned long long* st_tot = reinterpret_cast<unsigned long long*>(p + 64);
+    unsigned long long* st_cnt = st_tot + tiles;
+    WalkOrder order;
+    GPC_TRY(walk_order(graph, reads, &read_index, n_reads, order, stream));
+    GPC_PROF("walk_reads");
+    walk_reads_kernel<true><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+        *graph, *reads, read_index, (unsigned)n_reads, extension, nullptr, 0, n_steps, dense,
+        touched, err);
+    GPC_LAUNCH_CHECK();
+    GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
+    dense_runs_kernel<<<tiles, DR_THREADS, 0, stream>>>(dense, n_pos, frag_idx, frag_val, direct_idx,
+                                                        direct_val, capacity, st_tot, st_cnt, ticket,
+                                                        counts);
+    GPC_LAUNCH_CHECK();
+    rel.clean = true;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    GPC_READ_BACK({counts, h, (unsigned)(32)});
+    *n_frag = h[0];
+    *n_direct = h[1];
+    *n_events = h[2];
+    prof_add_bytes("walk_reads", walk_read_bytes(reads) * (double)n_reads + 8.0 * (double)h[2]);
+    prof_add_bytes("dense_runs", 8.0 * (double)(h[0] + h[1]));
+    GPC_TRY(walk_error((int)(h[3] & 0xffffffffu)));
+    if (h[0] > capacity || h[1] > capacity) return GPC_ERR_CAPACITY;
     return GPC_OK;
 }
 
@@ -669,7 +1027,14 @@ extern "C" int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64
                                   uint32_t size_bp, uint32_t* frag_idx, int32_t* frag_val,
                                   uint64_t* n_frag, uint32_t* direct_idx, int32_t* direct_val,
                                   uint64_t* n_direct, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+    return events_to_runs_impl(events, events_tmp, n_events, size_bp, frag_idx, frag_val, n_frag,
+                               direct_idx, direct_val, n_direct, (cudaStream_t)stream_);
+}
+
+static int events_to_runs_impl(uint32_t* events, uint32_t* events_tmp, uint64_t n_events,
+                               uint32_t size_bp, uint32_t* frag_idx, int32_t* frag_val,
+                               uint64_t* n_frag, uint32_t* direct_idx, int32_t* direct_val,
+                               uint64_t* n_direct, cudaStream_t stream) {
     if (n_events == 0) {   // empty track: one entry (0, 0)
         GPC_CUDA(cudaMemsetAsync(frag_idx, 0, 4, stream));
         GPC_CUDA(cudaMemsetAsync(frag_val, 0, 4, stream));

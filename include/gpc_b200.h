@@ -78,7 +78,20 @@ typedef struct gpc_reads {
     const int32_t* path;
     const uint32_t* path_ptr32; /* optional: the same offsets in 32 bits (fewer bytes to
                                    upload when the paths hold < 2^32 nodes); used if non-NULL */
+    /* Optional (may be NULL): n_reads records of four uint32, written by
+     * gpc_build_read_headers:
+     *   { path offset, path nodes | inconsistent << 31, start offset, end offset }
+     * When present the read walk loads this one record per read (its start / end node
+     * are the first / last node of its path) and ignores end_node, end_off and path_ptr*. */
+    const uint32_t* hdr;
 } gpc_reads_t;
+
+/* Builds gpc_reads_t.hdr (capacity 4 * n_reads uint32) from the arrays of `reads`
+ * (path_ptr or path_ptr32, start / end node and offset, path); the record of a read
+ * whose start / end node is not the first / last node of its path, or whose path is
+ * empty, is marked inconsistent and reported as GPC_ERR_INVALID_INTERVAL by the walk
+ * (reference: InvalidPileupInterval, sample/sparsegraphpileup.py:47-62). */
+int gpc_build_read_headers(const gpc_reads_t* reads, uint32_t* hdr, void* stream);
 
 /* ---- S1  UniqueIntervals.__iter__  (graph_peak_caller/intervals.py:23-33) ---
  * Keeps the first read of every start position (signed node id, offset).
@@ -112,6 +125,26 @@ int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64_t n_events
                        uint32_t size_bp, uint32_t* frag_idx, int32_t* frag_val, uint64_t* n_frag,
                        uint32_t* direct_idx, int32_t* direct_val, uint64_t* n_direct,
                        void* stream);
+
+/* ---- S2-S5 + T1/T2 in one call: get_fragment_pileup incl. the direct pileup
+ *      (sample/__init__.py:5-9, sample/sparsegraphpileup.py:37-250,
+ *       sparsediffs.py:137-141,180-190) ---------------------------------------------
+ * Same results as gpc_sample_events followed by gpc_events_to_runs, without the
+ * caller holding the event list.  mode 0 picks by density: read sets with at least
+ * ~0.1 steps per base pair of the graph go through a difference array over the
+ * graph's positions (64-bit reductions straight from the walk, then ONE streaming
+ * scan that emits both run-length tracks and leaves the array zeroed for the next
+ * call; no sort); sparser ones (whole-genome depth) through the event list and the
+ * radix sort.  mode 1 / 2 force the array / the event list.
+ * Capacity of each of the four output arrays: `capacity` entries;
+ * GPC_ERR_CAPACITY reports the needed size in *n_frag / *n_direct (call again).
+ * *n_events: +1/-1 steps deposited. */
+int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* reads,
+                      const uint32_t* read_index, uint64_t n_reads, int32_t extension,
+                      uint32_t* frag_idx, int32_t* frag_val, uint32_t* direct_idx,
+                      int32_t* direct_val, uint64_t capacity, uint64_t* n_frag,
+                      uint64_t* n_direct, uint64_t* n_events, uint8_t* touched, int32_t mode,
+                      void* stream);
 
 /* ---- C2/C3  LinearMap.map_interval_collection (control/linearmap.py:51-74) and
  *            SparseControl.create up to the LinearPileup

@@ -33,7 +33,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
-FLOAT_SAMPLES = 4096          # runs kept per float track
+FLOAT_SAMPLES = 512           # runs kept per float track
 
 
 def synth_core():
@@ -158,7 +158,7 @@ def main():
                             q=[float(table[x]) for x in keys[::max(1, keys.size // FLOAT_SAMPLES)]]),
                chromosomes=[recs[i] for i in range(n)], seconds=time.time() - t0)
     with open(out_path, "w") as fh:
-        json.dump(doc, fh, indent=1)
+        json.dump(doc, fh, separators=(",", ":"))
     print("wrote", out_path, "in %.0f s" % (time.time() - t0))
 
 
