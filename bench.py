@@ -261,7 +261,6 @@ def main_ours(args):
     from graph_peak_caller_b200.control.linearmap import LinearMap
     from graph_peak_caller_b200.device import DeviceGraph, DeviceReads
     from graph_peak_caller_b200.intervals import UniqueIntervals
-    from graph_peak_caller_b200.reads import ReadBatch
     from graph_peak_caller_b200.reporter import Reporter
     from graph_peak_caller_b200.sparsepvalues import PToQValuesMapper
 
@@ -379,28 +378,19 @@ def main_ours(args):
     value = total_reads / (ms_per_step / 1e3)
 
     # ---- end to end through the public API, host buffers ----------------------
-    def pin(rb):
-        return [torch.from_numpy(a).pin_memory() for a in (
-            rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr.astype(np.int32),
-            rb.path)]
-
+    # page-locked host copies of the reads in the form the API uploads (ReadBatch.pin_memory:
+    # the compact wire form when the reads allow it), prepared once like any ingest step
     for u in units:
-        u.pinned_s = pin(u.s)
-        u.pinned_c = pin(u.c) if u.c is not None else None
+        u.pinned_s = u.s.pin_memory()
+        u.pinned_c = u.c.pin_memory() if u.c is not None else None
         u.config = Configuration()
         u.config.read_length, u.config.fragment_length = R, F
         u.config.has_control, u.config.global_min = has_control, gmin
         u.config.linear_map_name = u.lm
-    h2d = sum(t_.numel() * t_.element_size() for u in units
-              for v in (u.pinned_s, u.pinned_c) if v is not None for t_ in v)
+    h2d = sum(v.upload_bytes() for u in units for v in (u.pinned_s, u.pinned_c) if v is not None)
 
     def fresh(pinned):
-        rb = ReadBatch.__new__(ReadBatch)
-        (rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr, rb.path) = \
-            [t_.numpy() for t_ in pinned]
-        rb._device = None
-        rb._pinned = pinned
-        return rb
+        return pinned.fresh_view()
 
     def e2e_step():
         callers = []
@@ -509,8 +499,10 @@ def main_ours(args):
                 e2e=dict(value=total_reads / (e2e_ms / 1e3), unit="reads/s",
                          ms_per_step=e2e_ms, h2d_bytes_per_step=int(h2d),
                          d2h_bytes_per_step=d2h,
-                         note="CallPeaks.run(UniqueIntervals(host SoA), ...) incl. pinned H2D of "
-                              "the read sets and D2H of the peaks; the graph is resident"),
+                         wire_form="compact" if getattr(units[0].pinned_s, "_compact", None) is not None
+                                   else "six arrays",
+                         note="CallPeaks.run(UniqueIntervals(page-locked host reads), ...) incl. H2D "
+                              "of the read sets and D2H of the peaks; the graph is resident"),
                 roofline=roofline, cpu_baseline=cpu)
     if world > 1 or scaling == "strong":
         line["sharding"] = dict(

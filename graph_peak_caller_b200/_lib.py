@@ -31,7 +31,8 @@ class GpcGraph(ctypes.Structure):
 class GpcReads(ctypes.Structure):
     _fields_ = [("n_reads", u64), ("start_node", c_void_p), ("start_off", c_void_p),
                 ("end_node", c_void_p), ("end_off", c_void_p),
-                ("path_ptr", c_void_p), ("path", c_void_p), ("path_ptr32", c_void_p)]
+                ("path_ptr", c_void_p), ("path", c_void_p), ("path_ptr32", c_void_p),
+                ("hdr", c_void_p)]
 
 
 P = ctypes.POINTER
@@ -39,6 +40,12 @@ _SIGNATURES = {
     "gpc_unique_reads": [c_void_p, c_void_p, u64, c_void_p, P(u64), c_void_p],
     "gpc_sample_events": [P(GpcGraph), P(GpcReads), c_void_p, u64, i32, c_void_p,
                           u64, P(u64), c_void_p, c_void_p],
+    "gpc_build_read_headers": [P(GpcReads), c_void_p, c_void_p],
+    "gpc_reads_from_compact": [c_void_p, c_void_p, c_void_p, u64, c_void_p, c_void_p, c_void_p,
+                               c_void_p],
+    "gpc_sample_pileup": [P(GpcGraph), P(GpcReads), c_void_p, u64, i32, c_void_p, c_void_p,
+                          c_void_p, c_void_p, u64, P(u64), P(u64), P(u64), c_void_p, i32,
+                          c_void_p],
     "gpc_events_to_runs": [c_void_p, c_void_p, u64, u32, c_void_p, c_void_p, P(u64),
                            c_void_p, c_void_p, P(u64), c_void_p],
     "gpc_control_linear_track": [P(GpcGraph), c_void_p, c_void_p, c_void_p, u64,

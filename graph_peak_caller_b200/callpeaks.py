@@ -159,18 +159,17 @@ class CallPeaksFromQvalues:
         finder = SparseMaxPaths(self.filtered_peaks, self.graph, score_track, self.variant_maps)
         finder.set_q_values(self.q_values)
         max_paths, _ = finder.run()
-        self._reporter.add("all_max_paths", max_paths)
         chromosome = None if self._reporter._base_name is None \
             else self._reporter._base_name.replace("_", "")
-        for peak in max_paths:
-            if type(peak.score) is not float:
-                peak.set_score(float(peak.score))
-            if chromosome is not None and peak.length() != 0:
-                peak.chromosome = chromosome
+        # scores are floats already; peaks of non-zero length carry the chromosome
+        # (callpeaks.py:191-200) -- applied when a Peak object is made
+        max_paths.set_chromosome(chromosome)
+        self._reporter.add("all_max_paths", max_paths)
         order = finder.order     # stable sort by score, descending (callpeaks.py:204-205)
         logging.info("N unfiltered peaks: %s", len(max_paths))
-        self.max_paths = [max_paths[i] for i in order
-                          if max_paths[i].length() >= self.info.fragment_length]
+        length = finder.peak_set.length
+        keep = order[length[order] >= self.info.fragment_length] if len(order) else order
+        self.max_paths = max_paths.subset(keep)
         logging.info("N filtered peaks: %s", len(self.max_paths))
         self._reporter.add("max_paths", self.max_paths)
 

@@ -406,41 +406,53 @@ __global__ void hole_active_kernel(VertexView vw, const uint32_t* __restrict__ p
     fr[u] = INF_I;
 }
 
+// One relaxation round over the whole active list (large active sets: whole-genome
+// chromosomes have 10^4-10^5 active pieces, far too many for the single CTA below).
+// changed[round] is raised when a value improved; a round whose predecessor raised
+// nothing returns at once, so the 37 launches cost a few microseconds each after the
+// fixed point (usually three or four rounds).
 __global__ void hole_relax_kernel(gpc_graph_t g, VertexView vw, const uint32_t* __restrict__ list,
                                   uint32_t n_list, const uint32_t* __restrict__ p_start,
                                   const uint32_t* __restrict__ p_end,
                                   const uint8_t* __restrict__ is_exit, int32_t* __restrict__ to,
-                                  int32_t* __restrict__ fr) {
+                                  int32_t* __restrict__ fr, int round, int* __restrict__ changed) {
+    if (round > 0 && !changed[round - 1]) return;           // (uniform over the grid)
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_list) return;
+    if (i >= n_list) i = n_list - 1;                        // the tail repeats the last piece
     uint32_t u = list[i];
     int t = vw.type_of[u];
     uint32_t a = vw.node_of[u];
     uint4 r0 = node_record(g, a), r1 = node_record(g, a + 1);
     int size = (int)(p_end[u] - p_start[u]);
+    volatile int32_t* vto = to;
+    volatile int32_t* vfr = fr;
+    bool any = false;
     if (t != PIECE_TAIL) {                      // pull `to` over incoming edges
-        int best = to[u];
+        const int old = vto[u];
+        int best = old;
         for (uint32_t e = r0.z; e < r1.z; ++e) {
             int32_t w = vw.out_vertex[g.pred[e]];
             if (w >= 0) {
-                int d = to[w];
+                int d = vto[w];
                 if (d < INF_I) best = min(best, d + (int)(p_end[w] - p_start[w]));
             }
         }
-        to[u] = best;
+        if (best != old) { vto[u] = best; any = true; }
     }
-    int best = fr[u];
+    const int old = vfr[u];
+    int best = old;
     if (is_exit[u]) best = min(best, size);
     if (t != PIECE_HEAD) {
         for (uint32_t e = r0.y; e < r1.y; ++e) {
             int32_t w = vw.in_vertex[g.succ[e]];
             if (w >= 0) {
-                int d = fr[w];
+                int d = vfr[w];
                 if (d < INF_I) best = min(best, d + size);
             }
         }
     }
-    fr[u] = best;
+    if (best != old) { vfr[u] = best; any = true; }
+    if (__syncthreads_or(any ? 1 : 0) && threadIdx.x == 0) changed[round] = 1;
 }
 
 // All rounds in one launch for the usual small active set: one CTA, a block
@@ -816,6 +828,11 @@ __global__ void max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ c
     int info = 0;
     if (len > 1) {
         if (-wsum != score) info |= 1;
+        // "is the target on the path" as a flag per vertex (the predecessor array has done
+        // its job): a scan of the path per edge made peaks of a few hundred pieces -- dense
+        // variation -- quadratic
+        for (int j = 0; j < nv; ++j) pred[j] = 0;
+        for (int z = 0; z < len; ++z) pred[(int)out.path[lo + z]] = 1;
         bool amb = false;
         for (int q = len - 1; q >= 1 && !amb; --q) {      // path[:-1] in forward order
             int node = (int)out.path[lo + q];
@@ -823,10 +840,7 @@ __global__ void max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ c
             long long w = -(long long)m_weight[lo + node];
             for_edges(node, [&](int tgt) {
                 if (amb) return;
-                if (tgt != nv) {
-                    for (int z = 0; z < len; ++z)
-                        if ((int)out.path[lo + z] == tgt) return;
-                }
+                if (tgt != nv && pred[tgt]) return;
                 long long tail = tgt == nv ? 0 : dsink[tgt];
                 if (tail < INF && reach + w + tail == score) amb = true;
             });
@@ -1098,19 +1112,23 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
             compact_u32_kernel<<<GRID(P)>>>(active.as<uint8_t>(), aoffs.as<uint32_t>(), P,
                                             alist.as<uint32_t>());
             GPC_LAUNCH_CHECK();
-            if (n_active <= 32768) {
+            if (n_active <= 4096) {
                 GPC_PROF("hole_relax_fused");
                 hole_relax_fused_kernel<<<1, 1024, 0, stream>>>(
                     *graph, vw, alist.as<uint32_t>(), (uint32_t)n_active, p_start.as<uint32_t>(),
                     p_end.as<uint32_t>(), is_exit.as<uint8_t>(), to.as<int32_t>(), fr.as<int32_t>());
                 GPC_LAUNCH_CHECK();
             } else {
+                Scratch chg;
+                GPC_CUDA(chg.alloc(RELAX_ROUNDS * sizeof(int), stream));
+                GPC_CUDA(cudaMemsetAsync(chg.p, 0, RELAX_ROUNDS * sizeof(int), stream));
                 for (int round = 0; round < RELAX_ROUNDS; ++round) {
                     GPC_PROF("hole_relax");
                     hole_relax_kernel<<<GRID(n_active)>>>(*graph, vw, alist.as<uint32_t>(),
                                                           (uint32_t)n_active, p_start.as<uint32_t>(),
                                                           p_end.as<uint32_t>(), is_exit.as<uint8_t>(),
-                                                          to.as<int32_t>(), fr.as<int32_t>());
+                                                          to.as<int32_t>(), fr.as<int32_t>(), round,
+                                                          chg.as<int>());
                     GPC_LAUNCH_CHECK();
                 }
             }

@@ -545,122 +545,140 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
 // ---- difference array -> two canonical run-length tracks ----------------------
 //
 // dense[pos] holds the net step of both pileups at graph position pos (packed as the
-// walk deposits it).  One streaming pass: a tile of 4096 positions (32 KB) is loaded
-// with 16-byte coalesced loads into shared memory laid out with a 16-byte pad per
-// thread row (so that the row reads below are conflict-free), the words are zeroed
-// behind the read (the array is clean again for the next call: no memset kernel),
-// every thread walks its 16 consecutive positions, tile totals and entry counts go
-// through two packed chained scans walked by two warps at once, and an entry
-// (position, running sum) is written wherever the net step of a track is non-zero,
-// plus always one at position 0 -- the canonical SparseValues of the reference
-// (sparsediffs.py:13-20,137-141).  HBM-bound: 8 bytes read + 8 bytes of zeroes per
+// walk deposits it).  One streaming pass, WARP-centric: every warp claims tiles of 512
+// positions (4 KB) in order, loads its tile with 16-byte coalesced loads into its own
+// slice of shared memory (rows padded by 16 bytes, so that the row reads below are
+// conflict-free), zeroes the words behind the read (the array is clean again for the next
+// call: no memset kernel), every lane walks its 16 consecutive positions, tile totals and
+// entry counts are scanned with shuffles and chained over the tiles by two packed
+// look-backs, and an entry (position, running sum) is written wherever the net step of a
+// track is non-zero, plus always one at position 0 -- the canonical SparseValues of the
+// reference (sparsediffs.py:13-20,137-141).  No block barrier anywhere: the warps of an SM
+// sit in different phases (loading, scanning, waiting for a predecessor, writing), which
+// is what keeps the memory system busy; the block-wide version of this kernel spent a
+// third of its stall samples on barriers.  HBM-bound: 8 bytes read + 8 bytes of zeroes per
 // position, 8 bytes per entry out.
 
 constexpr int DR_THREADS = 256;
+constexpr int DR_WARPS = DR_THREADS / 32;
 constexpr int DR_ITEMS = 16;
-constexpr int DR_TILE = DR_THREADS * DR_ITEMS;          // positions per tile
-constexpr int DR_ROW_BYTES = DR_ITEMS * 8 + 16;         // padded row of one thread
+constexpr int DR_TILE = 32 * DR_ITEMS;                  // positions per warp tile
+constexpr int DR_ROW_BYTES = DR_ITEMS * 8 + 16;         // padded row of one lane
 
 __device__ __forceinline__ void dense_unpack(unsigned long long w, int& dfrag, int& ddir) {
     ddir = (int)(unsigned)(w & 0xffffffffull);
     dfrag = (int)(((long long)w - (long long)ddir) >> 32);
 }
 
-__global__ void __launch_bounds__(DR_THREADS)
-dense_runs_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
+__device__ __forceinline__ long long warp_incl_sum64(long long v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        long long o = __shfl_up_sync(FULL, v, d);
+        if (lane_id() >= (unsigned)d) v += o;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(DR_THREADS, 5)
+dense_runs_kernel(unsigned long long* __restrict__ dense, unsigned n_pos, unsigned n_tiles,
                   uint32_t* __restrict__ frag_idx, int32_t* __restrict__ frag_val,
                   uint32_t* __restrict__ dir_idx, int32_t* __restrict__ dir_val,
                   unsigned long long cap,
                   unsigned long long* __restrict__ st_tot /* zeroed */,
                   unsigned long long* __restrict__ st_cnt /* zeroed */,
                   unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts) {
-    __shared__ __align__(16) unsigned char s_rows[DR_THREADS * DR_ROW_BYTES];
-    __shared__ long long s_scan64[33];
-    __shared__ unsigned s_slot;
-    __shared__ unsigned long long s_base[2];
-    const unsigned tile = claim_tile(ticket, &s_slot);
-    const unsigned tile_base = tile * DR_TILE;
-    // ---- load (striped: a warp's loads are 512 contiguous bytes), zero behind -----
+    __shared__ __align__(16) unsigned char s_rows[DR_WARPS][32 * DR_ROW_BYTES];
+    const unsigned lane = lane_id();
+    unsigned char* const rows = s_rows[warp_id()];
+    const unsigned char* const row = rows + lane * DR_ROW_BYTES;
+    while (true) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(ticket, 1u);        // tiles are claimed in order
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile >= n_tiles) break;
+        const unsigned tile_base = tile * DR_TILE;
+        // ---- load (a warp's loads are 512 contiguous bytes), zero behind ---------------
 #pragma unroll
-    for (int j = 0; j < DR_ITEMS / 2; ++j) {
-        const unsigned u = j * DR_THREADS + threadIdx.x;        // 16-byte unit inside the tile
-        const unsigned gpos = tile_base + 2 * u;
-        ulonglong2 v = make_ulonglong2(0ull, 0ull);
-        if (gpos + 1 < n_pos) {
-            ulonglong2* g = reinterpret_cast<ulonglong2*>(dense + gpos);
-            v = *g;
-            if (v.x | v.y) *g = make_ulonglong2(0ull, 0ull);
-        } else if (gpos < n_pos) {
-            v.x = dense[gpos];
-            if (v.x) dense[gpos] = 0ull;
+        for (int j = 0; j < DR_ITEMS / 2; ++j) {
+            const unsigned u = j * 32 + lane;                   // 16-byte unit inside the tile
+            const unsigned gpos = tile_base + 2 * u;
+            ulonglong2 v = make_ulonglong2(0ull, 0ull);
+            if (gpos + 1 < n_pos) {
+                ulonglong2* g = reinterpret_cast<ulonglong2*>(dense + gpos);
+                v = *g;
+                if (v.x | v.y) *g = make_ulonglong2(0ull, 0ull);
+            } else if (gpos < n_pos) {
+                v.x = dense[gpos];
+                if (v.x) dense[gpos] = 0ull;
+            }
+            *reinterpret_cast<ulonglong2*>(rows + (u >> 3) * DR_ROW_BYTES + (u & 7) * 16) = v;
         }
-        *reinterpret_cast<ulonglong2*>(s_rows + (u >> 3) * DR_ROW_BYTES + (u & 7) * 16) = v;
-    }
-    __syncthreads();
-    // ---- thread-local pass over 16 consecutive positions ----------------------------
-    unsigned long long w[DR_ITEMS];
+        __syncwarp();
+        // ---- lane-local pass over 16 consecutive positions (the row stays in shared
+        // memory and is read again for the emission) ---------------------------------
+        const unsigned base = tile_base + lane * DR_ITEMS;
+        int tf = 0, td = 0;
+        unsigned mf = 0, md = 0;              // bit k: position base + k gets an entry
 #pragma unroll
-    for (int k = 0; k < DR_ITEMS / 2; ++k) {
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(s_rows + threadIdx.x * DR_ROW_BYTES + k * 16);
-        w[2 * k] = v.x;
-        w[2 * k + 1] = v.y;
-    }
-    const unsigned base = tile_base + threadIdx.x * DR_ITEMS;
-    int tf = 0, td = 0;
-    unsigned mf = 0, md = 0;              // bit k: position base + k gets an entry
+        for (int k = 0; k < DR_ITEMS / 2; ++k) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(row + k * 16);
+            int df, dd;
+            dense_unpack(v.x, df, dd);
+            tf += df;
+            td += dd;
+            if (df != 0) mf |= 1u << (2 * k);
+            if (dd != 0) md |= 1u << (2 * k);
+            dense_unpack(v.y, df, dd);
+            tf += df;
+            td += dd;
+            if (df != 0) mf |= 2u << (2 * k);
+            if (dd != 0) md |= 2u << (2 * k);
+        }
+        if (base == 0) { mf |= 1u; md |= 1u; }                     // (0, value) always exists
+        // warp scans: totals (high word fragment, low word direct) and entry counts (2 x 31 bits)
+        const long long my_tot = ((long long)tf << 32) + (long long)td;
+        const long long my_cnt = ((long long)__popc(mf) << 31) | (long long)__popc(md);
+        const long long in_tot = warp_incl_sum64(my_tot), in_cnt = warp_incl_sum64(my_cnt);
+        const unsigned long long tile_tot = (unsigned long long)__shfl_sync(FULL, in_tot, 31) & LB_MASK;
+        const unsigned long long tile_cnt = (unsigned long long)__shfl_sync(FULL, in_cnt, 31);
+        // both aggregates are published before either chain is walked back
+        if (lane == 0) {
+            lb_publish_agg(st_tot, tile, tile_tot);
+            lb_publish_agg(st_cnt, tile, tile_cnt);
+        }
+        const unsigned long long pre_tot = lb_resolve_warp(st_tot, tile, tile_tot);
+        const unsigned long long pre_cnt = lb_resolve_warp(st_cnt, tile, tile_cnt);
+        if (tile == n_tiles - 1 && lane == 0) {
+            const unsigned long long tot = pre_cnt + tile_cnt;
+            out_counts[0] = tot >> 31;
+            out_counts[1] = tot & 0x7fffffffull;
+        }
+        if (mf | md) {
+            int run_f, run_d;
+            {
+                const long long v = ((long long)(pre_tot << 2) >> 2) + (in_tot - my_tot);   // sign-extend 62 bits
+                run_d = (int)(unsigned)(v & 0xffffffffll);
+                run_f = (int)((v - (long long)run_d) >> 32);
+            }
+            const unsigned long long w_pk = pre_cnt + (unsigned long long)(in_cnt - my_cnt);
+            unsigned long long w0 = w_pk >> 31, w1 = w_pk & 0x7fffffffull;
 #pragma unroll
-    for (int k = 0; k < DR_ITEMS; ++k) {
-        int df, dd;
-        dense_unpack(w[k], df, dd);
-        tf += df;
-        td += dd;
-        const bool first = base + k == 0;                      // (0, value) always exists
-        if (df != 0 || first) mf |= 1u << k;
-        if (dd != 0 || first) md |= 1u << k;
-    }
-    // block scans: totals (high word fragment, low word direct) and entry counts (2 x 31 bits)
-    long long tile_tot, tile_cnt;
-    const long long ex_tot = block_excl_sum<long long>(((long long)tf << 32) + (long long)td, s_scan64, tile_tot);
-    const long long ex_cnt = block_excl_sum<long long>(((long long)__popc(mf) << 31) | (long long)__popc(md),
-                                                       s_scan64, tile_cnt);
-    // the two chains are independent: warp 0 resolves the totals, warp 1 the counts
-    if (threadIdx.x < 32) {
-        unsigned long long ex = lookback_excl_warp(st_tot, tile, (unsigned long long)tile_tot & LB_MASK);
-        if (threadIdx.x == 0) s_base[0] = ex;
-    } else if (threadIdx.x < 64) {
-        unsigned long long b = lookback_excl_warp(st_cnt, tile, (unsigned long long)tile_cnt);
-        if (threadIdx.x == 32) {
-            s_base[1] = b;
-            if (tile == gridDim.x - 1) {
-                const unsigned long long tot = b + (unsigned long long)tile_cnt;
-                out_counts[0] = tot >> 31;
-                out_counts[1] = tot & 0x7fffffffull;
+            for (int k = 0; k < DR_ITEMS; ++k) {
+                int df, dd;
+                dense_unpack(*reinterpret_cast<const unsigned long long*>(row + k * 8), df, dd);
+                run_f += df;
+                run_d += dd;
+                if ((mf >> k) & 1u) {
+                    if (w0 < cap) { frag_idx[w0] = base + k; frag_val[w0] = run_f; }
+                    ++w0;
+                }
+                if ((md >> k) & 1u) {
+                    if (w1 < cap) { dir_idx[w1] = base + k; dir_val[w1] = run_d; }
+                    ++w1;
+                }
             }
         }
-    }
-    __syncthreads();
-    int run_f, run_d;
-    {
-        const long long v = ((long long)(s_base[0] << 2) >> 2) + ex_tot;     // sign-extend 62 bits
-        run_d = (int)(unsigned)(v & 0xffffffffll);
-        run_f = (int)((v - (long long)run_d) >> 32);
-    }
-    const unsigned long long w_pk = s_base[1] + (unsigned long long)ex_cnt;
-    unsigned long long w0 = w_pk >> 31, w1 = w_pk & 0x7fffffffull;
-#pragma unroll
-    for (int k = 0; k < DR_ITEMS; ++k) {
-        int df, dd;
-        dense_unpack(w[k], df, dd);
-        run_f += df;
-        run_d += dd;
-        if ((mf >> k) & 1u) {
-            if (w0 < cap) { frag_idx[w0] = base + k; frag_val[w0] = run_f; }
-            ++w0;
-        }
-        if ((md >> k) & 1u) {
-            if (w1 < cap) { dir_idx[w1] = base + k; dir_val[w1] = run_d; }
-            ++w1;
-        }
+        __syncwarp();                       // the rows are overwritten by the next tile
     }
 }
 
@@ -748,6 +766,22 @@ __global__ void read_headers_kernel(gpc_reads_t reads, unsigned n, uint4* __rest
         bad = reads.path[p0] != reads.start_node[r] || reads.path[p1 - 1] != reads.end_node[r];
     hdr[r] = make_uint4((unsigned)p0, (unsigned)(bad ? 0 : k) | (bad ? 0x80000000u : 0u),
                         (unsigned)reads.start_off[r], (unsigned)reads.end_off[r]);
+}
+
+// Compact reads (what crosses the host link) -> the arrays the kernels read.
+//   offs[r]     start offset | end offset << 16
+//   path_len[r] nodes on the read's path (1..255)
+//   path_off[r] exclusive prefix sum of path_len (computed on the device)
+__global__ void widen_reads_kernel(const uint32_t* __restrict__ offs, const uint8_t* __restrict__ path_len,
+                                   const uint32_t* __restrict__ path_off, const int32_t* __restrict__ path,
+                                   unsigned n, int32_t* __restrict__ start_node,
+                                   int32_t* __restrict__ start_off, uint4* __restrict__ hdr) {
+    unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t o = offs[r], k = path_len[r], p0 = path_off[r];
+    start_node[r] = k ? path[p0] : 0;
+    start_off[r] = (int32_t)(o & 0xffffu);
+    hdr[r] = make_uint4(p0, k ? k : 0x80000000u, o & 0xffffu, o >> 16);
 }
 
 }  // namespace gpc
@@ -845,6 +879,24 @@ extern "C" int gpc_build_read_headers(const gpc_reads_t* reads, uint32_t* hdr, v
     GPC_PROF_BYTES("read_headers", 48.0 * reads->n_reads);
     read_headers_kernel<<<div_up(reads->n_reads, 256), 256, 0, stream>>>(
         *reads, (unsigned)reads->n_reads, reinterpret_cast<uint4*>(hdr));
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+
+
+extern "C" int gpc_reads_from_compact(const uint32_t* offs, const uint8_t* path_len,
+                                      const int32_t* path, uint64_t n_reads, int32_t* start_node,
+                                      int32_t* start_off, uint32_t* hdr, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_reads == 0) return GPC_OK;
+    if (n_reads >= (1ull << 31)) { set_error("too many reads"); return GPC_ERR_ARG; }
+    Scratch off;
+    GPC_CUDA(off.alloc(n_reads * 4, stream));
+    GPC_TRY(exclusive_scan<unsigned char>(path_len, off.as<uint32_t>(), n_reads, nullptr, stream));
+    GPC_PROF_BYTES("widen_reads", 37.0 * n_reads);
+    widen_reads_kernel<<<div_up(n_reads, 256), 256, 0, stream>>>(
+        offs, path_len, off.as<uint32_t>(), path, (unsigned)n_reads, start_node, start_off,
+        reinterpret_cast<uint4*>(hdr));
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }
@@ -1006,9 +1058,10 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
         touched, err);
     GPC_LAUNCH_CHECK();
     GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
-    dense_runs_kernel<<<tiles, DR_THREADS, 0, stream>>>(dense, n_pos, frag_idx, frag_val, direct_idx,
-                                                        direct_val, capacity, st_tot, st_cnt, ticket,
-                                                        counts);
+    const unsigned blocks = min(div_up(tiles, DR_WARPS), (unsigned)(sm_count() * 5));
+    dense_runs_kernel<<<blocks, DR_THREADS, 0, stream>>>(dense, n_pos, tiles, frag_idx, frag_val,
+                                                         direct_idx, direct_val, capacity, st_tot,
+                                                         st_cnt, ticket, counts);
     GPC_LAUNCH_CHECK();
     rel.clean = true;
     unsigned long long h[4] = {0, 0, 0, 0};

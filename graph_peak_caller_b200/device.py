@@ -12,6 +12,14 @@ from .custom_exceptions import DeviceLibraryMissing
 _torch = None
 
 
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
 def torch_cuda():
     """torch, after checking once that a CUDA device is there (the check reads the
     environment every time and this is called a few hundred times per pass)."""
@@ -126,22 +134,56 @@ class DeviceReads:
         self.host_bytes = batch.nbytes()
         self.ready_event = None
         pinned = getattr(batch, "_pinned", None)
+        compact = getattr(batch, "_compact", None)
+        null = ctypes.c_void_p(0)
+        lib = _lib.load()
+
+        def on_copy_stream(fn):
+            """Run fn (copies + the kernels that finish the upload) on the copy stream when
+            there is one; the compute stream later waits for ready_event."""
+            if copy_stream is None:
+                fn(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                return
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):
+                fn(ctypes.c_void_p(copy_stream.cuda_stream))
+                self.ready_event = torch.cuda.Event()
+                self.ready_event.record(copy_stream)
+
+        self.end_node = self.end_off = self.path_ptr = None
+        if compact is not None:
+            # page-locked compact form: three asynchronous copies, then one kernel widens
+            # them into what the duplicate filter, the projection and the walk read
+            dev = device()
+            self.start_node = torch.empty(self.n, dtype=torch.int32, device=dev)
+            self.start_off = torch.empty(self.n, dtype=torch.int32, device=dev)
+            self.hdr = torch.empty(4 * self.n, dtype=torch.int32, device=dev)
+            dst = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in compact]
+
+            def go(stream):
+                for a, b in zip(dst, compact):
+                    a.copy_(b, non_blocking=True)
+                _lib.check(lib.gpc_reads_from_compact(ptr(dst[0]), ptr(dst[1]), ptr(dst[2]), self.n,
+                                                      ptr(self.start_node), ptr(self.start_off),
+                                                      ptr(self.hdr), stream))
+            on_copy_stream(go)
+            self.path = dst[2]
+            self._wire = dst[:2]            # (kept until the widening kernel has run)
+            self.host_bytes = batch.upload_bytes()
+            self.c = _lib.GpcReads(self.n, ptr(self.start_node), ptr(self.start_off), null, null,
+                                   null, ptr(self.path), null, ptr(self.hdr))
+            return
         if pinned is not None:      # page-locked host tensors: asynchronous copies
             dev = device()
             # destinations come from the current stream's cached pool; with a copy
             # stream only the transfers run there (it first waits for whatever the
             # current stream did with that memory before)
             dst = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in pinned]
-            if copy_stream is not None:
-                copy_stream.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(copy_stream):
-                    for a, b in zip(dst, pinned):
-                        a.copy_(b, non_blocking=True)
-                    self.ready_event = torch.cuda.Event()
-                    self.ready_event.record(copy_stream)
-            else:
+
+            def go(stream):
                 for a, b in zip(dst, pinned):
                     a.copy_(b, non_blocking=True)
+            on_copy_stream(go)
             (self.start_node, self.start_off, self.end_node, self.end_off, self.path_ptr,
              self.path) = dst
         else:
@@ -154,11 +196,18 @@ class DeviceReads:
         # 32-bit path offsets (a page-locked batch may carry them: 4 bytes less per
         # read on the link) go into path_ptr32, 64-bit ones into path_ptr
         narrow = self.path_ptr.element_size() == 4
-        null = ctypes.c_void_p(0)
         self.c = _lib.GpcReads(self.n, ptr(self.start_node), ptr(self.start_off),
                                ptr(self.end_node), ptr(self.end_off),
                                null if narrow else ptr(self.path_ptr), ptr(self.path),
-                               ptr(self.path_ptr) if narrow else null)
+                               ptr(self.path_ptr) if narrow else null, null)
+        # the walk's view of a read: one 16-byte record (include/gpc_b200.h, gpc_reads_t.hdr),
+        # built once per upload, in the order of the upload
+        self.hdr = None
+        if self.n and self.path.numel() < 2 ** 32:
+            self.hdr = torch.empty(4 * self.n, dtype=torch.int32, device=device())
+            on_copy_stream(lambda stream: _lib.check(lib.gpc_build_read_headers(
+                ctypes.byref(self.c), ptr(self.hdr), stream)))
+            self.c.hdr = self.hdr.data_ptr()
 
 
 def device_graph(graph, linear_map=None):

@@ -78,6 +78,34 @@ def sample_events(dgraph, dreads, read_index, n_reads, extension, events_per_rea
         return events[:n_events.value], touched
 
 
+def sample_pileup(dgraph, dreads, read_index, n_reads, extension, mode=0):
+    """S2-S5 + T1/T2 in one call.  Returns ((frag_idx, frag_val), (direct_idx, direct_val),
+    touched uint8[n_nodes], n_events).  All four run arrays live in one allocation, sized
+    from the runs per read the graph produced last time (a bubble-rich graph cuts a
+    fragment into more runs); too small means one more call."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    touched = empty(dgraph.graph.n_nodes, torch.uint8)
+    per_read = getattr(dgraph, "_runs_per_read", 2.6)
+    cap = max(1024, int(int(n_reads) * per_read) + 16)
+    while True:
+        arena = empty(4 * cap, torch.int32)
+        fi, fv, di, dv = (arena[k * cap:(k + 1) * cap] for k in range(4))
+        nf, nd, ne = _u64(), _u64(), _u64()
+        status = lib.gpc_sample_pileup(
+            ctypes.byref(dgraph.c), ctypes.byref(dreads.c), ptr(read_index), n_reads, extension,
+            ptr(fi), ptr(fv), ptr(di), ptr(dv), cap, ctypes.byref(nf), ctypes.byref(nd),
+            ctypes.byref(ne), ptr(touched), mode, stream_ptr())
+        if status == _lib.GPC_ERR_CAPACITY:
+            cap = max(int(nf.value), int(nd.value)) + 1024
+            continue
+        _lib.check(status)
+        if n_reads:
+            dgraph._runs_per_read = 1.15 * max(int(nf.value), int(nd.value), 1) / int(n_reads) + 0.05
+        return ((fi[:nf.value], fv[:nf.value]), (di[:nd.value], dv[:nd.value]), touched,
+                int(ne.value))
+
+
 def events_to_runs(events, size_bp):
     """T1/T2.  Returns ((frag_idx, frag_val), (direct_idx, direct_val))."""
     torch = torch_cuda()

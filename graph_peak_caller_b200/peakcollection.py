@@ -2,6 +2,7 @@
 (graph_peak_caller/peakcollection.py:10-66, 97-98): an interval with a score,
 written one JSON object per line."""
 import json
+from collections.abc import Sequence
 
 from .reads import Interval, Position
 
@@ -104,6 +105,77 @@ class Peak(Interval):
                     score=self.score, unique_id=self.unique_id)
         peak.info = self.info
         return peak
+
+
+class PeakList(Sequence):
+    """The peaks of one call as a read-only sequence over the kernels' flat output
+    (``pipeline.PeakSet``): ``Peak`` objects are made when an element is looked at and
+    kept, so whoever holds the list sees the same objects.  A whole-genome run yields
+    10^4-10^5 peaks per call; building them all eagerly cost more host time than the whole
+    device pass."""
+
+    def __init__(self, peak_set, graph, index=None, chromosome=None, cache=None):
+        self._ps = peak_set
+        self._graph = graph
+        self._index = None if index is None else [int(i) for i in index]
+        self._chromosome = chromosome
+        self._cache = {} if cache is None else cache
+
+    def __len__(self):
+        return self._ps.n_all if self._index is None else len(self._index)
+
+    def _peak(self, k):
+        peak = self._cache.get(k)
+        if peak is None:
+            ps = self._ps
+            lo, hi = int(ps.node_ptr[k]), int(ps.node_ptr[k + 1])
+            info = int(ps.info[k])
+            peak = Peak.from_flat(int(ps.start[k]), int(ps.end[k]), ps.nodes[lo:hi].tolist(),
+                                  self._graph, float(ps.score[k]), (bool(info & 1), bool(info & 2)),
+                                  int(ps.length[k]))
+            if self._chromosome is not None and peak._length != 0:       # callpeaks.py:199-200
+                peak.chromosome = self._chromosome
+            self._cache[k] = peak
+        return peak
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError("peak index out of range")
+        return self._peak(i if self._index is None else self._index[i])
+
+    def subset(self, index, chromosome=None):
+        """The peaks ``index`` (positions in the full output) in that order; shares the
+        objects already made."""
+        out = PeakList(self._ps, self._graph, index, self._chromosome, self._cache)
+        return out
+
+    def set_chromosome(self, chromosome):
+        self._chromosome = chromosome
+        for peak in self._cache.values():
+            if chromosome is not None and peak.length() != 0:
+                peak.chromosome = chromosome
+
+    def __eq__(self, other):
+        try:
+            return len(self) == len(other) and all(a == b for a, b in zip(self, other))
+        except TypeError:
+            return NotImplemented
+
+    __hash__ = None
+
+    def __add__(self, other):
+        return list(self) + list(other)
+
+    def __radd__(self, other):
+        return list(other) + list(self)
+
+    def __repr__(self):
+        return "PeakList(%d peaks)" % len(self)
 
 
 class IntervalCollection:

@@ -41,9 +41,9 @@ def sample_pileup(dgraph, dreads, read_index, n_reads, extension):
     if extension < 0:
         raise Exception("Invalid extension size %d used. Must be positive. "
                         "Is fragment length < read length?" % extension)
-    events, touched = kernels.sample_events(dgraph, dreads, read_index, n_reads, extension)
-    frag, direct = kernels.events_to_runs(events, dgraph.graph.size_bp)
-    return frag, direct, touched, int(events.numel())
+    frag, direct, touched, n_events = kernels.sample_pileup(dgraph, dreads, read_index, n_reads,
+                                                            extension)
+    return frag, direct, touched, n_events
 
 
 def linear_background(dgraph, dreads, read_index, n_reads, extensions, fragment_length,

@@ -7,7 +7,7 @@ are not produced here (the second element is a list of ``None``)."""
 from .. import kernels, pipeline
 from ..device import device_graph
 from ..graph import Graph
-from ..peakcollection import Peak
+from ..peakcollection import PeakList
 
 # maxpaths.py:34 subtracts (min_node - 1) from the 1-based node index of a
 # single-node peak instead of adding it.  For min_node == 1 both agree; for
@@ -47,11 +47,6 @@ class SparseMaxPaths:
         raw = self.run_raw()
         ps = pipeline.PeakSet(raw, 0)
         self.order = ps.order          # stable order by score, descending (device sort)
-        start, end = ps.start.tolist(), ps.end.tolist()
-        score, length = ps.score.tolist(), ps.length.tolist()
-        info, ptr, nodes = ps.info.tolist(), ps.node_ptr.tolist(), ps.nodes.tolist()
-        graph = self._graph
-        peaks = [Peak.from_flat(start[i], end[i], nodes[ptr[i]:ptr[i + 1]], graph, score[i],
-                                (bool(info[i] & 1), bool(info[i] & 2)), length[i])
-                 for i in range(ps.n_all)]
+        self.peak_set = ps
+        peaks = PeakList(ps, self._graph)      # Peak objects are made on access
         return peaks, [None] * len(peaks)

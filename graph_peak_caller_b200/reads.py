@@ -267,6 +267,62 @@ class ReadBatch:
                                       self.end_node, self.end_off,
                                       self.path_ptr, self.path))
 
+    # ---- the form that crosses the host link ------------------------------------
+    def compact(self):
+        """(offs uint32[R] = start offset | end offset << 16, path_len uint8[R], path) --
+        15 bytes per 36-bp read instead of 30: start / end node repeat the ends of the path,
+        path offsets are a prefix sum the device recomputes.  None when a read does not fit
+        (offset >= 65536, more than 255 path nodes, empty path, or a start / end node that is
+        not the end of its path): such a batch goes up as the six arrays."""
+        n = len(self)
+        if n == 0:
+            return None
+        lens = np.diff(self.path_ptr)
+        if lens.min() < 1 or lens.max() > 255:
+            return None
+        if min(self.start_off.min(), self.end_off.min()) < 0 or \
+                max(self.start_off.max(), self.end_off.max()) > 0xffff:
+            return None
+        if not (np.array_equal(self.path[self.path_ptr[:-1]], self.start_node)
+                and np.array_equal(self.path[self.path_ptr[1:] - 1], self.end_node)):
+            return None
+        offs = self.start_off.astype(np.uint32) | (self.end_off.astype(np.uint32) << np.uint32(16))
+        return offs, lens.astype(np.uint8), self.path
+
+    def pin_memory(self):
+        """A batch over the same reads whose arrays -- and, when the reads allow it, their
+        compact form -- sit in page-locked memory: uploads of such a batch are asynchronous
+        copies of the compact form (ingest-side preparation, done once per read set)."""
+        import torch
+        full = [torch.from_numpy(a).pin_memory() for a in (
+            self.start_node, self.start_off, self.end_node, self.end_off,
+            self.path_ptr.astype(np.int32) if self.path.size < 2 ** 31 else self.path_ptr, self.path)]
+        out = ReadBatch.__new__(ReadBatch)
+        (out.start_node, out.start_off, out.end_node, out.end_off, out.path_ptr, out.path) = \
+            [t.numpy() for t in full]
+        out._device = None
+        out._pinned = full
+        c = self.compact()
+        out._compact = None if c is None else [torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+                                               for a in c[:2]] + [full[5]]
+        return out
+
+    def fresh_view(self):
+        """The same host arrays without the cached device copy (every call uploads again)."""
+        out = ReadBatch.__new__(ReadBatch)
+        out.__dict__.update(self.__dict__)
+        out._device = None
+        return out
+
+    def upload_bytes(self):
+        c = getattr(self, "_compact", None)
+        if c is not None:
+            return sum(t.numel() * t.element_size() for t in c)
+        p = getattr(self, "_pinned", None)
+        if p is not None:
+            return sum(t.numel() * t.element_size() for t in p)
+        return self.nbytes()
+
     def to_file(self, file_name):
         np.savez(file_name, start_node=self.start_node, start_off=self.start_off,
                  end_node=self.end_node, end_off=self.end_off,

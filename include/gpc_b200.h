@@ -93,6 +93,18 @@ typedef struct gpc_reads {
  * (reference: InvalidPileupInterval, sample/sparsegraphpileup.py:47-62). */
 int gpc_build_read_headers(const gpc_reads_t* reads, uint32_t* hdr, void* stream);
 
+/* Reads as they cross the host link (15 bytes per read instead of 30 for 36-bp reads:
+ * the start / end node repeat the ends of the path, offsets fit 16 bits, path offsets
+ * are a prefix sum) -> the arrays the kernels read:
+ *   offs[r] = start offset | end offset << 16,  path_len[r] = nodes on the path (1..255),
+ *   path = the signed node ids of all paths, back to back.
+ * Writes start_node / start_off (n_reads each: the duplicate filter and the control
+ * projection read them) and hdr (4 * n_reads, see gpc_reads_t.hdr).  A read with
+ * path_len 0 is marked inconsistent (-> GPC_ERR_INVALID_INTERVAL from the walk). */
+int gpc_reads_from_compact(const uint32_t* offs, const uint8_t* path_len, const int32_t* path,
+                           uint64_t n_reads, int32_t* start_node, int32_t* start_off,
+                           uint32_t* hdr, void* stream);
+
 /* ---- S1  UniqueIntervals.__iter__  (graph_peak_caller/intervals.py:23-33) ---
  * Keeps the first read of every start position (signed node id, offset).
  * out_index: capacity n_reads, receives the kept read indexes in ascending

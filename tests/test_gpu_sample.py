@@ -10,35 +10,58 @@ from oracle import pipeline, sample as osample
 pytestmark = pytest.mark.gpu
 
 
-def gpu_sample(graph, reads, extension, unique):
+def gpu_sample(graph, reads, extension, unique, mode=None, headers=True, pinned=False):
+    """mode None: gpc_sample_events + gpc_events_to_runs (the caller holds the event list);
+    1 / 2: gpc_sample_pileup through the difference array / the event list.  headers False:
+    the walk reads the six SoA arrays instead of the 16-byte read records."""
     from graph_peak_caller_b200 import kernels
     from graph_peak_caller_b200.device import DeviceGraph, DeviceReads
+    if pinned:           # page-locked batch: goes up in the compact wire form when it can
+        reads = reads.pin_memory()
+        assert reads._compact is not None or len(reads) == 0
     dg, dr = DeviceGraph(graph), DeviceReads(reads)
+    if not headers:
+        dr.c.hdr = None
     index, n = None, len(reads)
     if unique:
         index, n = kernels.unique_reads(dr)
-    events, touched = kernels.sample_events(dg, dr, index, n, extension)
-    (fi, fv), (di, dv) = kernels.events_to_runs(events, graph.size_bp)
+    if mode is None:
+        events, touched = kernels.sample_events(dg, dr, index, n, extension)
+        (fi, fv), (di, dv) = kernels.events_to_runs(events, graph.size_bp)
+        n_events = events.numel()
+    else:
+        (fi, fv), (di, dv), touched, n_events = kernels.sample_pileup(dg, dr, index, n, extension,
+                                                                      mode=mode)
     cpu = lambda t: t.cpu().numpy()
     return dict(index=None if index is None else cpu(index), n=n,
                 sample=(cpu(fi).view(np.uint32).astype(np.int64), cpu(fv).astype(np.float64)),
                 direct=(cpu(di).view(np.uint32).astype(np.int64), cpu(dv).astype(np.float64)),
                 touched=np.flatnonzero(cpu(touched)) + graph.min_node,
-                n_events=events.numel())
+                n_events=n_events)
 
 
 def check(graph, reads, extension, unique):
-    got = gpu_sample(graph, reads, extension, unique)
     r = reads
     if unique:
         keep = osample.unique_read_mask(reads)
-        assert np.array_equal(got["index"], np.flatnonzero(keep))
         r = pipeline.unique_reads(reads)
     ref = osample.fragment_pileup(graph, r, extension)
-    for key in ("sample", "direct"):
-        assert np.array_equal(got[key][0], ref[key][0]), key
-        assert np.array_equal(got[key][1], ref[key][1]), key
-    assert np.array_equal(got["touched"], ref["touched"])
+    first = None
+    # every route to the two pileups: difference array, event list, the two-call form
+    # (with and without the per-read records)
+    for mode, headers, pinned in ((1, True, False), (2, True, False), (None, True, False),
+                                  (None, False, False), (1, False, False), (1, True, True),
+                                  (2, True, True)):
+        got = gpu_sample(graph, reads, extension, unique, mode, headers, pinned)
+        what = "mode %s headers %s pinned %s " % (mode, headers, pinned)
+        if unique:
+            assert np.array_equal(got["index"], np.flatnonzero(keep)), what
+        for key in ("sample", "direct"):
+            assert np.array_equal(got[key][0], ref[key][0]), what + key
+            assert np.array_equal(got[key][1], ref[key][1]), what + key
+        assert np.array_equal(got["touched"], ref["touched"]), what
+        assert first is None or got["n_events"] == first, what + "steps deposited"
+        first = got["n_events"]
     return got
 
 

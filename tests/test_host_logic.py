@@ -177,3 +177,21 @@ def test_peak_from_flat_builds_positions_on_demand():
     assert q.start_position == p.start_position and q.end_position == p.end_position
     p.start_position = Position(1, 0)                    # still assignable, as on an Interval
     assert p.start_position.offset == 0
+
+
+def test_compact_wire_form_of_a_read_batch():
+    """ReadBatch.compact(): offsets packed into 16 bits each, path lengths as bytes; batches
+    that do not fit (long nodes, long paths, a start node that is not the first path node)
+    report None and go up as the six arrays."""
+    g = make_graph(20000, 0.05, seed=5)
+    r = make_reads(g, 500, 20, 80, seed=6)
+    offs, plen, path = r.compact()
+    assert np.array_equal(offs & 0xffff, r.start_off) and np.array_equal(offs >> 16, r.end_off)
+    assert np.array_equal(plen, np.diff(r.path_ptr)) and path is r.path
+    far = ReadBatch(r.start_node, r.start_off + 70000, r.end_node, r.end_off, r.path_ptr, r.path)
+    assert far.compact() is None
+    other = r.start_node.copy()
+    other[0] += 1
+    assert ReadBatch(other, r.start_off, r.end_node, r.end_off, r.path_ptr, r.path).compact() is None
+    long_path = ReadBatch([1], [0], [1], [1], [0, 300], np.ones(300, dtype=np.int32))
+    assert long_path.compact() is None

@@ -8,19 +8,22 @@ from graph_peak_caller_b200.control.linearmap import LinearMap
 from graph_peak_caller_b200.intervals import UniqueIntervals
 from graph_peak_caller_b200.reads import ReadBatch
 from graph_peak_caller_b200.reporter import Reporter
-from graph_peak_caller_b200.synthetic import make_graph, make_reads
-g = make_graph(51_000_000, 0.02, seed=20261001)
-s = make_reads(g, 5_000_000, 36, 200, seed=1)
-c = make_reads(g, 5_000_000, 36, 200, seed=2, peak_frac=0.0, dup_frac=0.0)
+from graph_peak_caller_b200 import synthetic
+# python tools/e2e_breakdown.py [workload] [scale] [chromosome]
+cfg = synthetic.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "chr22_scale"]
+if len(sys.argv) > 2 and float(sys.argv[2]) > 1:
+    cfg = synthetic.scaled(cfg, float(sys.argv[2]))
+g, s, c = synthetic.chromosome_inputs(cfg, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+if c is None:
+    c = s
 lm = LinearMap.from_graph(g)
-config = Configuration(); config.read_length, config.fragment_length, config.has_control = 36, 200, True
+config = Configuration(); config.read_length, config.fragment_length, config.has_control = cfg["read_length"], cfg["fragment_length"], cfg["has_control"]
+config.global_min = synthetic.global_min_of(cfg)
 config.linear_map_name = lm
-pinned = {t: [torch.from_numpy(a).pin_memory() for a in (rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr.astype(np.int32), rb.path)] for t, rb in (("s", s), ("c", c))}
+pinned = {"s": s.pin_memory(), "c": c.pin_memory()}
+print("upload bytes per step", pinned["s"].upload_bytes() + pinned["c"].upload_bytes())
 def fresh(tag):
-    rb = ReadBatch.__new__(ReadBatch)
-    (rb.start_node, rb.start_off, rb.end_node, rb.end_off, rb.path_ptr, rb.path) = [t.numpy() for t in pinned[tag]]
-    rb._device = None; rb._pinned = pinned[tag]
-    return rb
+    return pinned[tag].fresh_view()
 def step():
     caller = CallPeaks(g, config, Reporter(None))
     caller.run(UniqueIntervals(fresh("s")), UniqueIntervals(fresh("c")))
