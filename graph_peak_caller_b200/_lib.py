@@ -25,7 +25,7 @@ class GpcGraph(ctypes.Structure):
     _fields_ = [("n_nodes", u32), ("n_edges", u32), ("size_bp", u32),
                 ("min_node", i32), ("node_rec", c_void_p), ("succ", c_void_p),
                 ("pred", c_void_p), ("lin_start", c_void_p), ("lin_end", c_void_p),
-                ("walk_rec", c_void_p)]
+                ("walk_rec", c_void_p), ("flags", u32)]
 
 
 class GpcReads(ctypes.Structure):

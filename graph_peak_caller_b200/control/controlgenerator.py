@@ -16,6 +16,7 @@ from .linearmap import LinearMap
 class SparseControl:
     def __init__(self, linear_map, graph, extension_sizes, fragment_length, touched_nodes):
         self._graph = Graph.from_obg(graph)
+        self._graph.require_ordered("SparseControl")
         if isinstance(linear_map, LinearMap):
             self._linear_map = linear_map
         else:

@@ -49,6 +49,7 @@ class LinearMap:
         import ctypes
         from .. import _lib
         g = Graph.from_obg(graph)
+        g.require_ordered("LinearMap.from_graph")
         lib = _lib.load()
         n = g.n_nodes
         starts, ends = np.zeros(n), np.zeros(n)

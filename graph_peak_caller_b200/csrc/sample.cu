@@ -109,20 +109,45 @@ __device__ __forceinline__ WalkNode load_walk_node(const gpc_graph_t& g, uint32_
 struct FrontierSpill {                      // (a separate object: a struct holding a
     uint32_t key[FRONTIER_CAP], rem[FRONTIER_CAP];   //  dynamically indexed array lives in local memory as a whole)
 };
+// More than 4 + FRONTIER_CAP pending nodes (deeply nested bubbles with long branches): the
+// spill list moves, once, into a chunk of a global pool that the launch provides
+// (SPILL_CHUNK entries; the pool is handed out by an atomic counter).  Only a read that
+// outgrows that too, or finds the pool empty, fails with GPC_ERR_FRONTIER_OVERFLOW.
+constexpr int SPILL_CHUNK = 4096;
+struct SpillPool {
+    uint32_t* base;                 // n_chunks * 2 * SPILL_CHUNK words (keys, then remainders)
+    unsigned* next;                 // chunks handed out so far
+    unsigned n_chunks;
+};
+
 struct Frontier {
     uint32_t k0, k1, k2, k3, r0, r1, r2, r3;
     int n;                                  // entries in registers (sorted by key)
     int xn;                                 // spilled entries (unsorted)
+    int xcap;
     bool overflow;
     uint32_t* xkey;
     uint32_t* xrem;
+    SpillPool pool;
 
-    __device__ __forceinline__ void init(FrontierSpill& sp) {
-        n = 0; xn = 0; overflow = false;
+    __device__ __forceinline__ void init(FrontierSpill& sp, const SpillPool& p) {
+        n = 0; xn = 0; overflow = false; xcap = FRONTIER_CAP;
         k0 = k1 = k2 = k3 = 0; r0 = r1 = r2 = r3 = 0;
         xkey = sp.key; xrem = sp.rem;
+        pool = p;
     }
     __device__ __forceinline__ bool empty() const { return n == 0 && xn == 0; }
+
+    __device__ __forceinline__ bool grow() {
+        if (xcap != FRONTIER_CAP || !pool.base) return false;
+        const unsigned c = atomicAdd(pool.next, 1u);
+        if (c >= pool.n_chunks) return false;
+        uint32_t* nk = pool.base + (size_t)c * 2 * SPILL_CHUNK;
+        uint32_t* nr = nk + SPILL_CHUNK;
+        for (int f = 0; f < xn; ++f) { nk[f] = xkey[f]; nr[f] = xrem[f]; }
+        xkey = nk; xrem = nr; xcap = SPILL_CHUNK;
+        return true;
+    }
 
     __device__ __forceinline__ void push(uint32_t key, uint32_t rem) {
         // a node that sits in the spill list must be found there before any of the
@@ -157,7 +182,7 @@ struct Frontier {
             if (k3 < k2) { t = k2; k2 = k3; k3 = t; t = r2; r2 = r3; r3 = t; }
             if (k2 < k1) { t = k1; k1 = k2; k2 = t; t = r1; r1 = r2; r2 = t; }
             if (k1 < k0) { t = k0; k0 = k1; k1 = t; t = r0; r0 = r1; r1 = t; }
-        } else if (xn < FRONTIER_CAP) {
+        } else if (xn < xcap || grow()) {
             xkey[xn] = key; xrem[xn] = rem; ++xn;
         } else {
             overflow = true;
@@ -190,7 +215,7 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
                   unsigned n_reads, int extension, uint32_t* __restrict__ events,
                   unsigned long long event_cap, unsigned long long* __restrict__ event_count,
                   unsigned long long* __restrict__ dense,
-                  uint8_t* __restrict__ touched, int* __restrict__ err) {
+                  uint8_t* __restrict__ touched, int* __restrict__ err, SpillPool pool) {
     __shared__ uint32_t s_buf[DENSE ? 1 : WALK_STAGE];
     __shared__ unsigned s_count;
     __shared__ unsigned long long s_gbase;
@@ -268,7 +293,7 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
             // ---- extension frontier ----------------------------------------
             FrontierSpill spill;
             Frontier fr;
-            fr.init(spill);
+            fr.init(spill, pool);
             uint32_t cur_v = last_v;
             uint32_t carry = total > last_len ? total - last_len : 0;
             while (true) {
@@ -308,6 +333,205 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
         }
     }
     if (DENSE) {        // only the number of steps is reported (one add per block)
+        n_emitted = warp_sum(n_emitted);
+        if (lane_id() == 0 && n_emitted) atomicAdd(&s_count, n_emitted);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_count) atomicAdd(event_count, (unsigned long long)s_count);
+        return;
+    }
+    __syncthreads();
+    const unsigned staged = min(s_count, (unsigned)WALK_STAGE);
+    if (threadIdx.x == 0) s_gbase = atomicAdd(event_count, (unsigned long long)staged);
+    __syncthreads();
+    const unsigned long long gb = s_gbase;
+    for (unsigned t = threadIdx.x; t < staged; t += WALK_THREADS)
+        if (gb + t < event_cap) events[gb + t] = s_buf[t];
+}
+
+
+// ---- graphs whose ids do not ascend along every edge (cycles) ---------------------
+//
+// The id-ordered frontier above needs a topological numbering.  Without one a read is
+// extended the way the reference's legacy path does it (legacy/extender.py:273-284 over
+// obg's GraphTraverser.extend_from_block): a worklist with visited[node] = the largest
+// number of bases still to cover on arrival; a node is covered [0, min(remaining, size))
+// and passes remaining - size on to its successors while that is positive.  What one
+// read covers is a SET of positions (legacy/areas.py BinaryContinousAreas: full nodes,
+// prefixes, suffixes): pieces of the read body and of the extension that overlap on a
+// node -- the extension wrapping around a cycle into the read -- count once.  Known
+// answers: the reference's tests/legacy/test_reversal.py:49-70.
+constexpr int CYC_CAP = 48;            // intervals / visited nodes / stack entries per read
+
+struct CycIntervals {
+    uint32_t node[CYC_CAP], a[CYC_CAP], b[CYC_CAP];
+    uint8_t body[CYC_CAP];
+    int n;
+    bool overflow;
+    __device__ __forceinline__ void add(uint32_t v, uint32_t lo, uint32_t hi, bool is_body) {
+        if (hi <= lo) return;
+        if (n >= CYC_CAP) { overflow = true; return; }
+        node[n] = v; a[n] = lo; b[n] = hi; body[n] = is_body ? 1 : 0;
+        ++n;
+    }
+};
+
+// emits the union of the intervals [first, last) of `iv` (sorted by node, then start) that
+// pass `only_body`, as +1 / -1 steps with `tag`
+template <bool DENSE>
+__device__ __forceinline__ void cyc_emit_union(const gpc_graph_t& graph, bool fwd, const CycIntervals& iv,
+                                               bool only_body, unsigned tag, Emitter<DENSE>& em) {
+    const uint32_t G = graph.size_bp;
+    int i = 0;
+    while (i < iv.n) {
+        if (only_body && !iv.body[i]) { ++i; continue; }
+        const uint32_t v = iv.node[i];
+        uint32_t lo = iv.a[i], hi = iv.b[i];
+        int j = i + 1;
+        for (; j < iv.n && iv.node[j] == v; ++j) {
+            if (only_body && !iv.body[j]) continue;
+            if (iv.a[j] <= hi) { hi = max(hi, iv.b[j]); continue; }
+            const WalkNode w = load_walk_node(graph, v, fwd);
+            const uint32_t ns = fwd ? w.off : (G - w.off - w.len);
+            em.emit(ns + lo, false, tag);
+            em.emit(ns + hi, true, tag);
+            lo = iv.a[j]; hi = iv.b[j];
+        }
+        const WalkNode w = load_walk_node(graph, v, fwd);
+        const uint32_t ns = fwd ? w.off : (G - w.off - w.len);
+        em.emit(ns + lo, false, tag);
+        em.emit(ns + hi, true, tag);
+        i = j;
+    }
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(WALK_THREADS)
+walk_reads_cyclic_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restrict__ read_index,
+                         unsigned n_reads, int extension, uint32_t* __restrict__ events,
+                         unsigned long long event_cap, unsigned long long* __restrict__ event_count,
+                         unsigned long long* __restrict__ dense,
+                         uint8_t* __restrict__ touched, int* __restrict__ err) {
+    __shared__ uint32_t s_buf[DENSE ? 1 : WALK_STAGE];
+    __shared__ unsigned s_count;
+    __shared__ unsigned long long s_gbase;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const unsigned i = blockIdx.x * WALK_THREADS + threadIdx.x;
+    unsigned n_emitted = 0;
+    if (i < n_reads) {
+        const unsigned r = read_index ? read_index[i] : i;
+        int so, eo;
+        long long p0, p1;
+        bool fwd, ok;
+        if (reads.hdr) {
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(reads.hdr) + r);
+            p0 = (long long)h.x;
+            p1 = p0 + (long long)(h.y & 0x7fffffffu);
+            so = (int)h.z;
+            eo = (int)h.w;
+            ok = !(h.y >> 31) && p1 > p0 && so >= 0 && eo >= 0;
+            fwd = ok ? reads.path[p0] > 0 : true;
+        } else {
+            const int sn = reads.start_node[r], en = reads.end_node[r];
+            so = reads.start_off[r];
+            eo = reads.end_off[r];
+            p0 = reads.path_ptr32 ? (long long)reads.path_ptr32[r] : reads.path_ptr[r];
+            p1 = reads.path_ptr32 ? (long long)reads.path_ptr32[r + 1] : reads.path_ptr[r + 1];
+            fwd = sn > 0;
+            ok = (p1 > p0) && ((en > 0) == fwd) && so >= 0 && eo >= 0;
+        }
+        const uint32_t n = graph.n_nodes;
+        const int mn = graph.min_node;
+        if (ok) {
+            for (long long q = p0; q < p1; ++q) {
+                int id = reads.path[q];
+                long long v = (long long)(id < 0 ? -id : id) - mn;
+                if ((id > 0) != fwd || v < 0 || v >= (long long)n) ok = false;
+            }
+        }
+        if (!ok) {
+            atomicExch(err, GPC_ERR_INVALID_INTERVAL);
+        } else {
+            CycIntervals iv;
+            iv.n = 0;
+            iv.overflow = false;
+            // ---- read body: [start offset, size) on the first node, whole nodes between,
+            // [0, end offset) on the last (one node: [start offset, end offset)) ---------
+            const int k = (int)(p1 - p0);
+            uint32_t last_v = 0, last_len = 0;
+            for (int j = 0; j < k; ++j) {
+                int id = reads.path[p0 + j];
+                uint32_t v = (uint32_t)((id < 0 ? -id : id) - mn);
+                const WalkNode w = load_walk_node(graph, v, fwd);
+                touched[v] = 1;
+                const uint32_t lo = j == 0 ? (uint32_t)so : 0u;
+                const uint32_t hi = j == k - 1 ? min((uint32_t)eo, w.len) : w.len;
+                iv.add(v, lo, hi, true);
+                last_v = v;
+                last_len = w.len;
+            }
+            // ---- extension: the rest of the last node, then the worklist -----------------
+            const uint32_t total = (uint32_t)eo + (uint32_t)extension;
+            iv.add(last_v, min((uint32_t)eo, last_len), min(total, last_len), false);
+            uint32_t vis_node[CYC_CAP], vis_rem[CYC_CAP], st_node[CYC_CAP], st_rem[CYC_CAP];
+            int n_vis = 0, n_st = 0;
+            bool overflow = false;
+            auto push_adjacent = [&](uint32_t v, uint32_t rem) {
+                const WalkNode w = load_walk_node(graph, v, fwd);
+                const uint4 a = node_record(graph, v);
+                const uint32_t* adj = fwd ? graph.succ + a.y : graph.pred + a.z;
+                for (uint32_t e = 0; e < w.n_adj; ++e) {
+                    const uint32_t t = w.n_adj > 2 ? adj[e] : (e == 0 ? w.adj0 : w.adj1);
+                    if (n_st >= CYC_CAP) { overflow = true; return; }
+                    st_node[n_st] = t; st_rem[n_st] = rem; ++n_st;
+                }
+            };
+            if (total > last_len) push_adjacent(last_v, total - last_len);
+            while (n_st > 0) {
+                --n_st;
+                const uint32_t v = st_node[n_st], rem = st_rem[n_st];
+                int at = -1;
+                for (int f = 0; f < n_vis; ++f) if (vis_node[f] == v) { at = f; break; }
+                if (at >= 0 && vis_rem[at] >= rem) continue;          // been here with more to spend
+                if (at < 0) {
+                    if (n_vis >= CYC_CAP) { overflow = true; break; }
+                    at = n_vis++;
+                    vis_node[at] = v;
+                }
+                vis_rem[at] = rem;
+                const WalkNode w = load_walk_node(graph, v, fwd);
+                if (rem > w.len) push_adjacent(v, rem - w.len);
+                if (overflow) break;
+            }
+            for (int f = 0; f < n_vis; ++f) {
+                const WalkNode w = load_walk_node(graph, vis_node[f], fwd);
+                touched[vis_node[f]] = 1;
+                iv.add(vis_node[f], 0u, min(vis_rem[f], w.len), false);
+            }
+            if (overflow || iv.overflow) {
+                atomicExch(err, GPC_ERR_FRONTIER_OVERFLOW);
+            } else {
+                // sort by (node, start): a few entries, insertion sort
+                for (int x = 1; x < iv.n; ++x) {
+                    const uint32_t nv = iv.node[x], na = iv.a[x], nb = iv.b[x];
+                    const uint8_t nbody = iv.body[x];
+                    int y = x - 1;
+                    while (y >= 0 && (iv.node[y] > nv || (iv.node[y] == nv && iv.a[y] > na))) {
+                        iv.node[y + 1] = iv.node[y]; iv.a[y + 1] = iv.a[y]; iv.b[y + 1] = iv.b[y];
+                        iv.body[y + 1] = iv.body[y];
+                        --y;
+                    }
+                    iv.node[y + 1] = nv; iv.a[y + 1] = na; iv.b[y + 1] = nb; iv.body[y + 1] = nbody;
+                }
+                Emitter<DENSE> em{s_buf, &s_count, events, event_count, event_cap, dense, graph.size_bp,
+                                  fwd, 0u};
+                cyc_emit_union<DENSE>(graph, fwd, iv, false, TAG_FRAG, em);
+                cyc_emit_union<DENSE>(graph, fwd, iv, true, TAG_DIRECT, em);
+                n_emitted = em.n_emitted;
+            }
+        }
+    }
+    if (DENSE) {
         n_emitted = warp_sum(n_emitted);
         if (lane_id() == 0 && n_emitted) atomicAdd(&s_count, n_emitted);
         __syncthreads();
@@ -363,7 +587,8 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
                       unsigned long long* __restrict__ st_seg /* zeroed */,
                       unsigned long long* __restrict__ st2 /* zeroed */,
                       unsigned long long* __restrict__ st3 /* zeroed */,
-                      unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts) {
+                      unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts,
+                      unsigned long long cap) {
     __shared__ unsigned s_slot;
     __shared__ long long s_scan64[33];
     __shared__ Seg s_seg[RUN_THREADS / 32];
@@ -530,14 +755,22 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
     const unsigned long long w_pk = s_obase[0] + (unsigned long long)o_pk;
     unsigned long long w0 = w_pk >> 31, w1 = w_pk & 0x7fffffffull;
     if (synth) {
-        frag_idx[w0] = 0; frag_val[w0] = 0; ++w0;
-        dir_idx[w1] = 0; dir_val[w1] = 0; ++w1;
+        if (w0 < cap) { frag_idx[w0] = 0; frag_val[w0] = 0; }
+        ++w0;
+        if (w1 < cap) { dir_idx[w1] = 0; dir_val[w1] = 0; }
+        ++w1;
     }
 #pragma unroll
     for (int j = 0; j < RUN_ITEMS; ++j) {
         const uint32_t pos = key[j] >> EVENT_POS_SHIFT;
-        if ((emit[0] >> j) & 1u) { frag_idx[w0] = pos; frag_val[w0] = e_val[0][j]; ++w0; }
-        if ((emit[1] >> j) & 1u) { dir_idx[w1] = pos; dir_val[w1] = e_val[1][j]; ++w1; }
+        if ((emit[0] >> j) & 1u) {
+            if (w0 < cap) { frag_idx[w0] = pos; frag_val[w0] = e_val[0][j]; }
+            ++w0;
+        }
+        if ((emit[1] >> j) & 1u) {
+            if (w1 < cap) { dir_idx[w1] = pos; dir_val[w1] = e_val[1][j]; }
+            ++w1;
+        }
     }
 }
 
@@ -679,6 +912,105 @@ dense_runs_kernel(unsigned long long* __restrict__ dense, unsigned n_pos, unsign
             }
         }
         __syncwarp();                       // the rows are overwritten by the next tile
+    }
+}
+
+
+// The same scan with one tile per BLOCK (ITEMS positions per thread, block-wide scans,
+// tickets per block); measured next to the warp-centric version above.
+template <int ITEMS>
+__global__ void __launch_bounds__(DR_THREADS, ITEMS == 16 ? 6 : 3)
+dense_runs_block_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
+                        uint32_t* __restrict__ frag_idx, int32_t* __restrict__ frag_val,
+                        uint32_t* __restrict__ dir_idx, int32_t* __restrict__ dir_val,
+                        unsigned long long cap,
+                        unsigned long long* __restrict__ st_tot /* zeroed */,
+                        unsigned long long* __restrict__ st_cnt /* zeroed */,
+                        unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts) {
+    constexpr int TILE = DR_THREADS * ITEMS;
+    constexpr int ROW = ITEMS * 8 + 16;
+    extern __shared__ __align__(16) unsigned char s_rows[];      // DR_THREADS * ROW
+    __shared__ long long s_scan64[33];
+    __shared__ unsigned s_slot;
+    __shared__ unsigned long long s_base[2];
+    const unsigned tile = claim_tile(ticket, &s_slot);
+    const unsigned tile_base = tile * TILE;
+#pragma unroll
+    for (int j = 0; j < ITEMS / 2; ++j) {
+        const unsigned u = j * DR_THREADS + threadIdx.x;        // 16-byte unit inside the tile
+        const unsigned gpos = tile_base + 2 * u;
+        ulonglong2 v = make_ulonglong2(0ull, 0ull);
+        if (gpos + 1 < n_pos) {
+            ulonglong2* g = reinterpret_cast<ulonglong2*>(dense + gpos);
+            v = *g;
+            if (v.x | v.y) *g = make_ulonglong2(0ull, 0ull);
+        } else if (gpos < n_pos) {
+            v.x = dense[gpos];
+            if (v.x) dense[gpos] = 0ull;
+        }
+        *reinterpret_cast<ulonglong2*>(s_rows + (u / (ITEMS / 2)) * ROW + (u % (ITEMS / 2)) * 16) = v;
+    }
+    __syncthreads();
+    const unsigned char* row = s_rows + threadIdx.x * ROW;
+    const unsigned base = tile_base + threadIdx.x * ITEMS;
+    int tf = 0, td = 0;
+    unsigned mf = 0, md = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS / 2; ++k) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(row + k * 16);
+        int df, dd;
+        dense_unpack(v.x, df, dd);
+        tf += df; td += dd;
+        if (df != 0) mf |= 1u << (2 * k);
+        if (dd != 0) md |= 1u << (2 * k);
+        dense_unpack(v.y, df, dd);
+        tf += df; td += dd;
+        if (df != 0) mf |= 2u << (2 * k);
+        if (dd != 0) md |= 2u << (2 * k);
+    }
+    if (base == 0) { mf |= 1u; md |= 1u; }
+    long long tile_tot, tile_cnt;
+    const long long ex_tot = block_excl_sum<long long>(((long long)tf << 32) + (long long)td, s_scan64, tile_tot);
+    const long long ex_cnt = block_excl_sum<long long>(((long long)__popc(mf) << 31) | (long long)__popc(md),
+                                                       s_scan64, tile_cnt);
+    if (threadIdx.x < 32) {
+        unsigned long long ex = lookback_excl_warp(st_tot, tile, (unsigned long long)tile_tot & LB_MASK);
+        if (threadIdx.x == 0) s_base[0] = ex;
+    } else if (threadIdx.x < 64) {
+        unsigned long long b = lookback_excl_warp(st_cnt, tile, (unsigned long long)tile_cnt);
+        if (threadIdx.x == 32) {
+            s_base[1] = b;
+            if (tile == gridDim.x - 1) {
+                const unsigned long long tot = b + (unsigned long long)tile_cnt;
+                out_counts[0] = tot >> 31;
+                out_counts[1] = tot & 0x7fffffffull;
+            }
+        }
+    }
+    __syncthreads();
+    if ((mf | md) == 0) return;
+    int run_f, run_d;
+    {
+        const long long v = ((long long)(s_base[0] << 2) >> 2) + ex_tot;
+        run_d = (int)(unsigned)(v & 0xffffffffll);
+        run_f = (int)((v - (long long)run_d) >> 32);
+    }
+    const unsigned long long w_pk = s_base[1] + (unsigned long long)ex_cnt;
+    unsigned long long w0 = w_pk >> 31, w1 = w_pk & 0x7fffffffull;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        int df, dd;
+        dense_unpack(*reinterpret_cast<const unsigned long long*>(row + k * 8), df, dd);
+        run_f += df;
+        run_d += dd;
+        if ((mf >> k) & 1u) {
+            if (w0 < cap) { frag_idx[w0] = base + k; frag_val[w0] = run_f; }
+            ++w0;
+        }
+        if ((md >> k) & 1u) {
+            if (w1 < cap) { dir_idx[w1] = base + k; dir_val[w1] = run_d; }
+            ++w1;
+        }
     }
 }
 
@@ -844,13 +1176,33 @@ static int walk_order(const gpc_graph_t* graph, const gpc_reads_t* reads, const 
     return GPC_OK;
 }
 
+// The pool behind Frontier::grow: 256 chunks (8 MB), enough for 256 reads of one launch to
+// hold up to 4096 pending nodes each (GPC_SPILL_CHUNKS overrides; 0 = no pool).
+struct SpillStore {
+    Scratch mem;
+    SpillPool pool{nullptr, nullptr, 0};
+    int init(cudaStream_t stream) {
+        const char* env = getenv("GPC_SPILL_CHUNKS");
+        const int chunks = env ? atoi(env) : 256;
+        if (chunks <= 0) return GPC_OK;
+        const size_t words = (size_t)chunks * 2 * SPILL_CHUNK;
+        GPC_CUDA(mem.alloc(words * 4 + 16, stream));
+        GPC_CUDA(cudaMemsetAsync(mem.p, 0, 16, stream));
+        pool.next = mem.as<unsigned>();
+        pool.base = mem.as<uint32_t>() + 4;
+        pool.n_chunks = (unsigned)chunks;
+        return GPC_OK;
+    }
+};
+
 static int walk_error(int e) {
     if (e == GPC_ERR_INVALID_INTERVAL) {
         set_error("Interval has node(s) not part of graph/pileup");
         return e;
     }
     if (e == GPC_ERR_FRONTIER_OVERFLOW) {
-        set_error("extension frontier exceeded %d simultaneous nodes", 4 + FRONTIER_CAP);
+        set_error("extension frontier: a read holds more than %d pending nodes, or more than the "
+                  "spill pool's reads hold more than %d (GPC_SPILL_CHUNKS)", SPILL_CHUNK, 4 + FRONTIER_CAP);
         return e;
     }
     return GPC_OK;
@@ -917,10 +1269,17 @@ extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* re
     int* err = reinterpret_cast<int*>(count + 1);
     WalkOrder order;
     GPC_TRY(walk_order(graph, reads, &read_index, n_reads, order, stream));
+    SpillStore spill;
+    GPC_TRY(spill.init(stream));
     GPC_PROF("walk_reads");
-    walk_reads_kernel<false><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
-        *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
-        nullptr, touched, err);
+    if (graph->flags & GPC_GRAPH_UNORDERED)
+        walk_reads_cyclic_kernel<false><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+            *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
+            nullptr, touched, err);
+    else
+        walk_reads_kernel<false><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+            *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
+            nullptr, touched, err, spill.pool);
     GPC_LAUNCH_CHECK();
     unsigned long long h[2] = {0, 0};
     GPC_READ_BACK({ctr.p, h, (unsigned)(16)});
@@ -990,7 +1349,7 @@ static void dense_release(DenseWorkspace* ws, bool clean, cudaStream_t stream) {
 static int events_to_runs_impl(uint32_t* events, uint32_t* events_tmp, uint64_t n_events,
                                uint32_t size_bp, uint32_t* frag_idx, int32_t* frag_val,
                                uint64_t* n_frag, uint32_t* direct_idx, int32_t* direct_val,
-                               uint64_t* n_direct, cudaStream_t stream);
+                               uint64_t* n_direct, uint64_t capacity, cudaStream_t stream);
 
 extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* reads,
                                  const uint32_t* read_index, uint64_t n_reads, int32_t extension,
@@ -1021,17 +1380,21 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
             if (st == GPC_ERR_CAPACITY && attempt == 0) { cap = n_ev + 1024; continue; }
             GPC_TRY(st);
             *n_events = n_ev;
-            if (n_ev + 1 > capacity) { *n_frag = *n_direct = n_ev + 1; return GPC_ERR_CAPACITY; }
             GPC_CUDA(tmp.alloc(cap * 4, stream));
+            // (runs beyond `capacity` are counted, not written: too small -> GPC_ERR_CAPACITY)
             return events_to_runs_impl(ev.as<uint32_t>(), tmp.as<uint32_t>(), n_ev, graph->size_bp,
                                        frag_idx, frag_val, n_frag, direct_idx, direct_val, n_direct,
-                                       stream);
+                                       capacity, stream);
         }
     }
     // ---- difference array ------------------------------------------------------------
     GPC_CUDA(cudaMemsetAsync(touched, 0, graph->n_nodes, stream));
     const unsigned n_pos = graph->size_bp + 1;           // a fragment may close at size_bp
-    const unsigned tiles = div_up(n_pos, DR_TILE);
+    // scan variant: 0 = one 4096-position tile per block (default), 1 = 8192 per block,
+    // 2 = one 512-position tile per warp, persistent
+    static const int variant = getenv("GPC_DENSE_SCAN") ? atoi(getenv("GPC_DENSE_SCAN")) : 0;
+    const unsigned tile_size = variant == 2 ? DR_TILE : (variant == 1 ? DR_THREADS * 32 : DR_THREADS * 16);
+    const unsigned tiles = div_up(n_pos, tile_size);
     DenseWorkspace* ws = nullptr;
     Scratch fallback, sc;
     unsigned long long* dense = nullptr;
@@ -1052,16 +1415,40 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
     unsigned long long* st_cnt = st_tot + tiles;
     WalkOrder order;
     GPC_TRY(walk_order(graph, reads, &read_index, n_reads, order, stream));
+    SpillStore spill;
+    GPC_TRY(spill.init(stream));
     GPC_PROF("walk_reads");
-    walk_reads_kernel<true><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
-        *graph, *reads, read_index, (unsigned)n_reads, extension, nullptr, 0, n_steps, dense,
-        touched, err);
+    if (graph->flags & GPC_GRAPH_UNORDERED)
+        walk_reads_cyclic_kernel<true><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+            *graph, *reads, read_index, (unsigned)n_reads, extension, nullptr, 0, n_steps, dense,
+            touched, err);
+    else
+        walk_reads_kernel<true><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+            *graph, *reads, read_index, (unsigned)n_reads, extension, nullptr, 0, n_steps, dense,
+            touched, err, spill.pool);
     GPC_LAUNCH_CHECK();
     GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
-    const unsigned blocks = min(div_up(tiles, DR_WARPS), (unsigned)(sm_count() * 5));
-    dense_runs_kernel<<<blocks, DR_THREADS, 0, stream>>>(dense, n_pos, tiles, frag_idx, frag_val,
-                                                         direct_idx, direct_val, capacity, st_tot,
-                                                         st_cnt, ticket, counts);
+    if (variant == 2) {
+        const unsigned blocks = min(div_up(tiles, DR_WARPS), (unsigned)(sm_count() * 5));
+        dense_runs_kernel<<<blocks, DR_THREADS, 0, stream>>>(dense, n_pos, tiles, frag_idx, frag_val,
+                                                             direct_idx, direct_val, capacity, st_tot,
+                                                             st_cnt, ticket, counts);
+    } else if (variant == 1) {
+        constexpr int SMEM = DR_THREADS * (32 * 8 + 16);
+        static bool configured = false;
+        if (!configured) {
+            GPC_CUDA(cudaFuncSetAttribute(dense_runs_block_kernel<32>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+            configured = true;
+        }
+        dense_runs_block_kernel<32><<<tiles, DR_THREADS, SMEM, stream>>>(
+            dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt, ticket,
+            counts);
+    } else {
+        dense_runs_block_kernel<16><<<tiles, DR_THREADS, DR_THREADS * (16 * 8 + 16), stream>>>(
+            dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt, ticket,
+            counts);
+    }
     GPC_LAUNCH_CHECK();
     rel.clean = true;
     unsigned long long h[4] = {0, 0, 0, 0};
@@ -1081,13 +1468,13 @@ extern "C" int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64
                                   uint64_t* n_frag, uint32_t* direct_idx, int32_t* direct_val,
                                   uint64_t* n_direct, void* stream_) {
     return events_to_runs_impl(events, events_tmp, n_events, size_bp, frag_idx, frag_val, n_frag,
-                               direct_idx, direct_val, n_direct, (cudaStream_t)stream_);
+                               direct_idx, direct_val, n_direct, n_events + 1, (cudaStream_t)stream_);
 }
 
 static int events_to_runs_impl(uint32_t* events, uint32_t* events_tmp, uint64_t n_events,
                                uint32_t size_bp, uint32_t* frag_idx, int32_t* frag_val,
                                uint64_t* n_frag, uint32_t* direct_idx, int32_t* direct_val,
-                               uint64_t* n_direct, cudaStream_t stream) {
+                               uint64_t* n_direct, uint64_t capacity, cudaStream_t stream) {
     if (n_events == 0) {   // empty track: one entry (0, 0)
         GPC_CUDA(cudaMemsetAsync(frag_idx, 0, 4, stream));
         GPC_CUDA(cudaMemsetAsync(frag_val, 0, 4, stream));
@@ -1119,12 +1506,12 @@ static int events_to_runs_impl(uint32_t* events, uint32_t* events_tmp, uint64_t 
     GPC_PROF_BYTES("events_to_runs", 4.0 * n_events);
     events_to_runs_kernel<<<tiles, RUN_THREADS, 0, stream>>>(
         sorted, (unsigned)n_events, frag_idx, frag_val, direct_idx, direct_val, st_tot, st_seg,
-        st2, st3, ticket, counts);
+        st2, st3, ticket, counts, capacity);
     GPC_LAUNCH_CHECK();
     unsigned long long h[2];
     GPC_READ_BACK({counts, h, (unsigned)(16)});
     *n_frag = h[0];
     *n_direct = h[1];
     prof_add_bytes("events_to_runs", 8.0 * (double)(h[0] + h[1]));
-    return GPC_OK;
+    return (h[0] > capacity || h[1] > capacity) ? GPC_ERR_CAPACITY : GPC_OK;
 }

@@ -114,7 +114,8 @@ class DeviceGraph:
         g = self.graph
         self.c = _lib.GpcGraph(g.n_nodes, g.n_edges, g.size_bp, g.min_node,
                                ptr(self.node_rec), ptr(self.succ), ptr(self.pred),
-                               ptr(self.lin_start), ptr(self.lin_end), ptr(self.walk_rec))
+                               ptr(self.lin_start), ptr(self.lin_end), ptr(self.walk_rec),
+                               0 if g.is_ordered else 1)
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in

@@ -13,10 +13,15 @@ views over six flat arrays, which is also exactly what is uploaded to HBM:
     succ_ptr[n+1]  int64   CSR row pointers, succ[m] int32 0-based targets
     pred_ptr[n+1], pred[m] the transposed CSR
 
-Node ids must ascend along every edge (vg / obg numbering); the kernels pop
-their per-read frontier in id order, which is then a topological order
-(reference sample/sparsegraphpileup.py:136-137 only needs *a* topological
-order, and its coordinates are laid out in id order anyway).
+Node ids ascend along every edge in vg / obg graphs; the kernels pop their
+per-read frontier in id order, which is then a topological order (reference
+sample/sparsegraphpileup.py:136-137 only needs *a* topological order, and its
+coordinates are laid out in id order anyway).  A graph built with the obg-style
+constructor may break that rule -- cycles as in the reference's
+tests/cyclic_graph.py:6-22 -- and is then marked ``is_ordered = False``: the sample
+pileup walks such a graph with a label-correcting worklist (the reference's
+legacy/extender.py:273-284); every stage that needs the order (linear map, hole
+cleaning, max paths) refuses it, as the live reference has no path for it either.
 """
 import numpy as np
 
@@ -116,15 +121,15 @@ class Graph:
                 src.append(a - min_node)
                 dst.append(b - min_node)
         self._init_flat(node_len, np.asarray(src, dtype=np.int64),
-                        np.asarray(dst, dtype=np.int64), min_node)
+                        np.asarray(dst, dtype=np.int64), min_node, allow_unordered=True)
 
     @classmethod
-    def from_edges(cls, node_len, src, dst, min_node=1):
+    def from_edges(cls, node_len, src, dst, min_node=1, allow_unordered=False):
         """``src``/``dst`` are 0-based node indexes."""
         self = cls.__new__(cls)
         self._init_flat(np.asarray(node_len, dtype=np.int64),
                         np.asarray(src, dtype=np.int64),
-                        np.asarray(dst, dtype=np.int64), int(min_node))
+                        np.asarray(dst, dtype=np.int64), int(min_node), allow_unordered)
         return self
 
     @classmethod
@@ -140,14 +145,21 @@ class Graph:
                 src.append(a - g.min_node)
                 dst.append(b - g.min_node)
         assert node_len.size == n
-        return cls.from_edges(node_len, src, dst, g.min_node)
+        return cls.from_edges(node_len, src, dst, g.min_node, allow_unordered=True)
 
-    def _init_flat(self, node_len, src, dst, min_node):
+    def require_ordered(self, what):
+        if not self.is_ordered:
+            raise ValueError(
+                "%s needs node ids that ascend along every edge (topological numbering); "
+                "cyclic or unsorted graphs are only supported by the sample pileup" % what)
+
+    def _init_flat(self, node_len, src, dst, min_node, allow_unordered=False):
         n = node_len.size
         if src.size and (src.min() < 0 or dst.min() < 0
                          or src.max() >= n or dst.max() >= n):
             raise ValueError("edge endpoint outside the graph")
-        if src.size and not np.all(dst > src):
+        self.is_ordered = bool(src.size == 0 or np.all(dst > src))
+        if not self.is_ordered and not allow_unordered:
             raise ValueError(
                 "node ids must ascend along every edge (topological numbering); "
                 "cyclic or unsorted graphs are not supported on this path")

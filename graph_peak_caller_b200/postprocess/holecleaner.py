@@ -12,6 +12,7 @@ from ..sparsediffs import SparseValues
 class HolesCleaner:
     def __init__(self, graph, sparse_values, max_size, touched_nodes=None):
         self._graph = Graph.from_obg(graph)
+        self._graph.require_ordered("HolesCleaner")
         self._sparse_values = sparse_values
         self._max_size = max_size
         self._touched_nodes = touched_nodes

@@ -21,6 +21,7 @@ class SparseMaxPaths:
         if variant_maps is not None:
             raise NotImplementedError("variant maps are outside this path")
         self._graph = Graph.from_obg(graph)
+        self._graph.require_ordered("SparseMaxPaths")
         self._sparse_values = sparse_values
         self._score_pileup = score_pileup
         self._q_values = None

@@ -64,7 +64,13 @@ typedef struct gpc_graph {
      * so that the read walk needs one 32-byte load per visited node; nodes with
      * more than two successors / predecessors fall back to the CSR arrays. */
     const uint32_t* walk_rec;
+    /* bit 0 (GPC_GRAPH_UNORDERED): some edge does not ascend in node id (a cyclic graph,
+     * or an unsorted one).  Only the sample pileup accepts such graphs: it then walks
+     * every read with a label-correcting worklist (visited[node] = max remaining, the
+     * reference's legacy/extender.py:273-284) instead of the id-ordered frontier. */
+    uint32_t flags;
 } gpc_graph_t;
+#define GPC_GRAPH_UNORDERED 1u
 
 /* Reads in HBM, structure of arrays (signed node ids: negative == reverse
  * strand, as obg Interval.region_paths). */

@@ -94,7 +94,11 @@ def _phase1(job):
                touched=sha(st["touched"]), touched_nodes=int(len(st["touched"])),
                control=thin(*st["control"]), p_values=thin(*st["p_values"]),
                p_runs=int(len(st["p_values"][0])), seconds_phase1=time.time() - t0)
-    return ci, rec, (st["p_values"][0], st["p_values"][1], st["track_size"])
+    # the join needs (distinct p, base pairs) only: reduced here, so that the parent never
+    # holds the p tracks of 24 chromosomes (integer counts: the reduced tables join exactly)
+    from oracle import stats as ostats
+    sp, cum = ostats.p_table(st["p_values"][1], ostats.run_lengths(st["p_values"][0], st["track_size"]))
+    return ci, rec, (sp, np.ediff1d(cum, to_begin=cum[0]))
 
 
 def _phase3(job):
@@ -142,7 +146,10 @@ def main():
         with mp.get_context("fork").Pool(procs) as pool:
             res1 = pool.map(_phase1, [(cfg, i, scratch) for i in order], chunksize=1)
         recs = {ci: rec for ci, rec, _ in res1}
-        sp, cum = opipeline.joined_p_table([t for _, _, t in sorted(res1, key=lambda r: r[0])])
+        # PToQValuesMapper.from_files (sparsepvalues.py:76-93) over the per-chromosome tables
+        parts = [t for _, _, t in sorted(res1, key=lambda r: r[0])]
+        sp, cum = ostats.p_table(np.concatenate([t[0] for t in parts]),
+                                 np.concatenate([t[1] for t in parts]))
         table = ostats.q_table(sp, cum)
         with mp.get_context("fork").Pool(procs) as pool:
             res3 = pool.map(_phase3, [(cfg, i, scratch, table) for i in order], chunksize=1)

@@ -83,6 +83,9 @@ def synthetic_cases():
         ("syn_dense_var", 5000, 0.12, 0.2, 20, 9, 45, 1000, 1200, True, 1),
         ("syn_more_sample", 5000, 0.03, 0.1, 5, 10, 36, 1200, 500, True, 1),
         ("syn_offset_ids", 3000, 0.03, 0.0, 5, 8, 30, 60, 400, True, 101),
+        # more sample than control reads at a size where peaks and holes are plentiful
+        # (the reference's float residue at zero coverage)
+        ("syn_more_sample_big", 30000, 0.03, 0.1, 5, 12, 60, 6000, 2500, True, 1),
     ]
     for i, (name, bp, rate, mnp, im, R, F, ns, nc, hc, mn) in enumerate(specs):
         g = make_graph(bp, site_rate=rate, seed=7000 + i, min_node=mn,
@@ -104,7 +107,10 @@ def main():
     if not refbridge.available():
         raise SystemExit("needs /root/reference")
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])          # python oracle/make_golden.py [case ...]
     for name, g, s, c, cfg in hand_built_cases() + synthetic_cases():
+        if only and name not in only:
+            continue
         unique = name.startswith("syn_")
         try:
             ref = refbridge.ref_callpeaks(g, s, c, cfg["read_length"],

@@ -20,7 +20,7 @@ from graph_peak_caller_b200.reporter import Reporter
 from graph_peak_caller_b200.sparsediffs import SparseValues
 from graph_peak_caller_b200.synthetic import make_graph, make_reads
 from oracle import control as ocontrol, pipeline as opipeline
-from parity_util import assert_exact, assert_step_close
+from parity_util import step_at, assert_exact, assert_step_close
 from test_gpu_postprocess import assert_same_peaks
 
 pytestmark = pytest.mark.gpu
@@ -77,6 +77,33 @@ def test_golden_end_to_end(name, tmp_path):
                     for p in written.intervals] == \
                 [(p.start_position.offset, p.end_position.offset, p.region_paths)
                  for p in caller.max_path_peaks]
+    else:
+        # More sample than control reads: the reference scales the sample by float steps of
+        # 1 / ratio, a pileup that returns to zero is left at +-1e-17, and p = 0 becomes
+        # -log10(1 - exp(-lambda)) there; the kernels count in
+        # integers and give 0.  Such p stay below the cutoff whenever lambda > 0.0513 (the
+        # background floor of any real run), they rank BELOW every larger p and so leave the
+        # q of all larger p untouched: q must agree wherever the sample is covered or the
+        # reference's q reaches the cutoff, and the thresholded and hole-cleaned tracks and
+        # the peaks must be IDENTICAL to the live reference's.
+        cutoff = -np.log10(0.05)
+        q = SparseValues.from_sparse_files(base + "qvalues")
+        rq_i, rq_v = case.track("q_values")
+        s_i, s_v = case.track("sample")
+        grid = np.union1d(np.union1d(q.indices, rq_i), s_i)
+        grid = grid[grid < G]
+        ours, theirs = step_at(q.indices, q.values, grid), step_at(rq_i, rq_v, grid)
+        covered = step_at(s_i, s_v, grid) > 1e-9
+        must = covered | (theirs >= cutoff) | (ours >= cutoff)
+        assert must.any()
+        err = np.abs(ours - theirs)[must]
+        assert np.all(err <= 1e-6 * np.abs(theirs[must]) + 1e-12), "q where it matters"
+        assert np.array_equal(ours >= cutoff, theirs >= cutoff), "thresholded track"
+        assert float(np.max(theirs[~must], initial=0.0)) < cutoff
+        h = SparseValues.from_sparse_files(base + "hole_cleaned")
+        assert_exact((h.indices, h.values.astype(bool)), case.track("hole_cleaned"), "holes")
+        if case.graph.min_node == 1:
+            assert_same_peaks(peak_tuples(caller.max_path_peaks), case.peaks)
     # the p -> q mapping is a dict with d[0] == 0, as in the reference
     assert caller.p_to_q_values_mapping[0] == 0
     assert isinstance(caller.p_to_q_values_mapping, dict)

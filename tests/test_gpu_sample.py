@@ -216,3 +216,26 @@ def test_wide_fan_out_frontier(trial):
     for reads in (fwd, rev):
         for extension in (3, 11, 40):
             check(g, reads, extension, False)
+
+
+def test_frontier_outgrows_its_local_spill_list(monkeypatch):
+    """Layers of 120 parallel nodes: more than 4 + 32 nodes pending at once.  The spill list
+    then moves into a chunk of the launch's pool (no GPC_ERR_FRONTIER_OVERFLOW any more);
+    without a pool the call still fails loudly."""
+    from graph_peak_caller_b200 import _lib, kernels
+    from graph_peak_caller_b200.device import DeviceGraph, DeviceReads
+    from graph_peak_caller_b200.reads import ReadBatch
+    rng = np.random.default_rng(4242)
+    g = _fan_graph(rng, n_layers=6, width=120)
+    assert int(np.diff(g.succ_ptr).max()) > 40
+    n = g.n_nodes
+    nodes = np.arange(n)
+    length = g.node_len[nodes]
+    zero = np.zeros(n, dtype=np.int64)
+    fwd = ReadBatch(nodes + 1, zero, nodes + 1, length, np.arange(n + 1), nodes + 1)
+    rev = ReadBatch(-(nodes + 1), zero, -(nodes + 1), length, np.arange(n + 1), -(nodes + 1))
+    for reads in (fwd, rev):
+        check(g, reads, 9, False)
+    monkeypatch.setenv("GPC_SPILL_CHUNKS", "0")
+    with pytest.raises(_lib.GpcError, match="frontier"):
+        kernels.sample_pileup(DeviceGraph(g), DeviceReads(fwd), None, n, 9, mode=1)

@@ -29,9 +29,16 @@ def test_graph_obg_surface():
     assert 3 in g.blocks and 7 not in g.blocks and g.uses_numpy_backend
 
 
-def test_graph_rejects_descending_edges():
+def test_graph_with_descending_edges_is_marked_and_refused_by_the_ordered_stages():
+    """Flat edge lists (parsers, generator) must ascend; the obg-style constructor takes any
+    graph and marks it (only the sample pileup walks such a graph, tests/test_cyclic.py)."""
     with pytest.raises(ValueError):
-        Graph({1: 5, 2: 5}, {2: [1]})
+        Graph.from_edges([5, 5], [1], [0])
+    g = Graph({1: 5, 2: 5}, {2: [1]})
+    assert not g.is_ordered
+    with pytest.raises(ValueError, match="LinearMap"):
+        LinearMap.from_graph(g)
+    assert Graph({1: 5, 2: 5}, {1: [2]}).is_ordered
 
 
 def test_graph_file_round_trip(tmp_path):
