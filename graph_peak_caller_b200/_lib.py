@@ -93,7 +93,8 @@ _lib = None
 def exported_symbols():
     """Every entry point include/gpc_b200.h declares."""
     return ["gpc_last_error_string", "gpc_version_string", "gpc_launch_count",
-            "gpc_profile_enable", "gpc_profile_report"] + sorted(_SIGNATURES)
+            "gpc_profile_enable", "gpc_profile_report", "gpc_guard_mode",
+            "gpc_guard_violations"] + sorted(_SIGNATURES)
 
 
 def load():
@@ -108,6 +109,8 @@ def load():
     lib.gpc_last_error_string.restype = ctypes.c_char_p
     lib.gpc_version_string.restype = ctypes.c_char_p
     lib.gpc_launch_count.restype = ctypes.c_uint64
+    lib.gpc_guard_violations.restype = ctypes.c_uint64
+    lib.gpc_guard_mode.restype = ctypes.c_int
     lib.gpc_profile_enable.argtypes = [ctypes.c_int]
     lib.gpc_profile_enable.restype = None
     lib.gpc_profile_report.argtypes = [ctypes.c_char_p, ctypes.c_uint64]

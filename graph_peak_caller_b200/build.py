@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgpc_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
-              "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+              "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
 def sources():

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/gpc_b200.h"
 
 namespace gpc {
@@ -46,6 +48,18 @@ void prof_add_bytes(const char* name, double algorithmic_bytes);
 
 int sm_count();
 
+// One NVTX range per C-ABI stage (tracing): a timeline tool (nsys, ncu
+// --nvtx) shows the kernels of a pass grouped under gpc_unique_reads, gpc_sample_pileup,
+// gpc_control_linear_track, ...  Header-only NVTX v3: without a tool attached a push is a
+// load and a branch.
+struct StageRange {
+    explicit StageRange(const char* name) { nvtxRangePushA(name); }
+    ~StageRange() { nvtxRangePop(); }
+    StageRange(const StageRange&) = delete;
+    StageRange& operator=(const StageRange&) = delete;
+};
+#define GPC_STAGE() gpc::StageRange stage_range__(__func__)
+
 // Small device -> host read-backs (counts, flags) without cudaMemcpy +
 // cudaStreamSynchronize: a one-thread kernel copies the words into a
 // host-mapped slot and then bumps a sequence number the host polls.  Measured
@@ -61,9 +75,20 @@ int read_back(const RbItem* items, int n_items, cudaStream_t stream);
     } while (0)
 
 // Stream-ordered scratch that frees itself (cudaMallocAsync pool).
+//
+// Guard mode (environment GPC_GUARD=1; compute-sanitizer is closed on the GPU pool this was
+// developed on): every scratch buffer is poisoned with 0xA5 when it is handed out -- a kernel
+// that reads what nobody wrote then computes garbage and the parity tests see it -- and sits
+// between two 256-byte canaries that are checked when it is given back; a kernel that wrote
+// outside its buffer is counted in gpc_guard_violations() and named on stderr.
+bool guard_mode();
+void guard_check(const void* base, size_t bytes, cudaStream_t stream);
+constexpr size_t GUARD_PAD = 256;
+
 struct Scratch {
     void* p = nullptr;
     cudaStream_t s = nullptr;
+    size_t guarded_bytes = 0;          // > 0: guard mode, p = base + GUARD_PAD
     Scratch() {}
     Scratch(const Scratch&) = delete;
     Scratch& operator=(const Scratch&) = delete;
@@ -73,11 +98,29 @@ struct Scratch {
         sm_count();   // first call configures the memory pool of this device
         s = stream;
         if (bytes == 0) bytes = 16;
+        if (guard_mode()) {
+            const size_t padded = ((bytes + 15) & ~(size_t)15) + 2 * GUARD_PAD;
+            void* base = nullptr;
+            cudaError_t e = cudaMallocAsync(&base, padded, stream);
+            if (e != cudaSuccess) return e;
+            e = cudaMemsetAsync(base, 0xA5, padded, stream);
+            if (e != cudaSuccess) return e;
+            p = static_cast<char*>(base) + GUARD_PAD;
+            guarded_bytes = bytes;
+            return cudaSuccess;
+        }
         return cudaMallocAsync(&p, bytes, stream);
     }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p && guarded_bytes) {
+            void* base = static_cast<char*>(p) - GUARD_PAD;
+            guard_check(base, guarded_bytes, s);
+            cudaFreeAsync(base, s);
+        } else if (p) {
+            cudaFreeAsync(p, s);
+        }
         p = nullptr;
+        guarded_bytes = 0;
     }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };

@@ -50,6 +50,7 @@ __global__ void project_keys_kernel(gpc_graph_t graph, const int32_t* __restrict
                                     const int32_t* __restrict__ start_off,
                                     const uint32_t* __restrict__ read_index, unsigned n_reads,
                                     unsigned long long* __restrict__ keys,
+                                    uint32_t* __restrict__ keys32,
                                     double* __restrict__ x_out, int* __restrict__ err) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_reads) return;
@@ -66,7 +67,15 @@ __global__ void project_keys_kernel(gpc_graph_t graph, const int32_t* __restrict
     double so = __dmul_rn(scale, (double)start_off[r]);
     double x = id > 0 ? __dadd_rn(ns, so) : __dsub_rn(ne, so);
     if (x_out) x_out[i] = x;
-    keys[i] = f64_to_key(x);
+    if (keys32) {
+        // the linear map is flagged all-integer (GPC_GRAPH_INTEGER_LINEAR): the start IS a
+        // small non-negative integer and is sorted as one (three 9-bit passes instead of five
+        // 8-bit passes over an order-preserving image of the double)
+        if (!(x == floor(x)) || !(x >= 0.0) || !(x < 1073741824.0)) { err[1] = 1; x = 0.0; }
+        keys32[i] = (uint32_t)x;
+    } else {
+        keys[i] = f64_to_key(x);
+    }
 }
 
 // distinct x and the index of their first occurrence (== weight prefix)
@@ -85,6 +94,19 @@ struct UniqueStartsOp {
     }
     __device__ __forceinline__ void emit(unsigned i, unsigned long long w) const {
         xu[w] = key_to_f64(keys[i]);
+        wpre[w] = i;
+    }
+    __device__ __forceinline__ void finish(unsigned long long count) const { wpre[count] = n; }
+};
+
+struct UniqueStartsOp32 {                       // the same over integer keys
+    const uint32_t* keys;
+    unsigned n;
+    double* xu;
+    uint32_t* wpre;
+    __device__ __forceinline__ bool keep(unsigned i) const { return i == 0 || keys[i] != keys[i - 1]; }
+    __device__ __forceinline__ void emit(unsigned i, unsigned long long w) const {
+        xu[w] = (double)keys[i];
         wpre[w] = i;
     }
     __device__ __forceinline__ void finish(unsigned long long count) const { wpre[count] = n; }
@@ -619,6 +641,7 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
                                         int32_t n_extensions, int32_t fragment_length,
                                         double min_value, double* out_pos, double* out_val,
                                         uint64_t* n_out, double* x_out, void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     *n_out = 0;
     if (n_extensions < 1 || n_extensions > MAX_WINDOWS) {
@@ -645,31 +668,61 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
     const unsigned n = (unsigned)n_reads;
     const unsigned nq = 2 * n_extensions;
     Scratch k0, k1, small, total, xu, wpre;
-    GPC_CUDA(k0.alloc((size_t)n * 8, stream));
-    GPC_CUDA(k1.alloc((size_t)n * 8, stream));
     GPC_CUDA(small.alloc(64, stream));
     GPC_CUDA(cudaMemsetAsync(small.p, 0, 64, stream));
     int* err = small.as<int>();
-    GPC_PROF_BYTES("project_keys", 20.0 * n);
-    project_keys_kernel<<<div_up(n, 256), 256, 0, stream>>>(*graph, start_node, start_off, read_index,
-                                                            n, k0.as<unsigned long long>(), x_out, err);
-    GPC_LAUNCH_CHECK();
-    bool in_tmp = false;
-    GPC_TRY((radix_sort<unsigned long long, false>(k0.as<unsigned long long>(),
-                                                   k1.as<unsigned long long>(), nullptr, nullptr, n,
-                                                   0, 64, true, &in_tmp, stream)));
-    const unsigned long long* keys = in_tmp ? k1.as<unsigned long long>() : k0.as<unsigned long long>();
     GPC_CUDA(total.alloc(8, stream));
-    // distinct starts; largest start = last sorted key; integrality of the starts
     GPC_CUDA(xu.alloc((size_t)n * 8, stream));
     GPC_CUDA(wpre.alloc((size_t)(n + 1) * 4, stream));
-    GPC_TRY(select_if("unique_starts",
-                      UniqueStartsOp{keys, n, xu.as<double>(), wpre.as<uint32_t>(), err + 1}, n,
-                      total.as<unsigned long long>(), stream));
     unsigned long long hU = 0, last_key = 0;
     int herr = 0, not_integer = 0;
-    GPC_READ_BACK({total.p, &hU, (unsigned)(8)}, {err, &herr, (unsigned)(4)}, {err + 1, &not_integer, (unsigned)(4)}, {keys + (n - 1), &last_key, (unsigned)(8)});
-    const double x_last = key_to_f64(last_key);
+    double x_last = 0.0;
+    // every node's linear span is a whole multiple of its length: all starts are integers
+    // below the linear length, known before anything is projected
+    const bool int_keys = (graph->flags & GPC_GRAPH_INTEGER_LINEAR) && graph->n_nodes > 0 &&
+                          !getenv("GPC_FORCE_MERGE_PATH") && !getenv("GPC_CONTROL_KEYS64");
+    if (int_keys) {
+        GPC_CUDA(k0.alloc((size_t)n * 4, stream));
+        GPC_CUDA(k1.alloc((size_t)n * 4, stream));
+        GPC_PROF_BYTES("project_keys", 16.0 * n);
+        project_keys_kernel<<<div_up(n, 256), 256, 0, stream>>>(*graph, start_node, start_off, read_index,
+                                                                n, nullptr, k0.as<uint32_t>(), x_out, err);
+        GPC_LAUNCH_CHECK();
+        bool in_tmp = false;
+        int bits = 1;                 // a start lies below the linear length <= size of the graph
+        while (bits < 30 && ((unsigned long long)graph->size_bp >> bits)) ++bits;
+        GPC_TRY((radix_sort<uint32_t, false>(k0.as<uint32_t>(), k1.as<uint32_t>(), nullptr, nullptr, n,
+                                             0, bits, false, &in_tmp, stream)));
+        const uint32_t* keys = in_tmp ? k1.as<uint32_t>() : k0.as<uint32_t>();
+        GPC_TRY(select_if("unique_starts", UniqueStartsOp32{keys, n, xu.as<double>(), wpre.as<uint32_t>()},
+                          n, total.as<unsigned long long>(), stream));
+        uint32_t last32 = 0;
+        GPC_READ_BACK({total.p, &hU, (unsigned)(8)}, {err, &herr, (unsigned)(4)}, {err + 1, &not_integer, (unsigned)(4)}, {keys + (n - 1), &last32, (unsigned)(4)});
+        x_last = (double)last32;
+        if (!herr && not_integer) {
+            set_error("linear map flagged all-integer, but a read start projects to a non-integer");
+            return GPC_ERR_INTERNAL;
+        }
+    } else {
+        GPC_CUDA(k0.alloc((size_t)n * 8, stream));
+        GPC_CUDA(k1.alloc((size_t)n * 8, stream));
+        GPC_PROF_BYTES("project_keys", 20.0 * n);
+        project_keys_kernel<<<div_up(n, 256), 256, 0, stream>>>(*graph, start_node, start_off, read_index,
+                                                                n, k0.as<unsigned long long>(), nullptr,
+                                                                x_out, err);
+        GPC_LAUNCH_CHECK();
+        bool in_tmp = false;
+        GPC_TRY((radix_sort<unsigned long long, false>(k0.as<unsigned long long>(),
+                                                       k1.as<unsigned long long>(), nullptr, nullptr, n,
+                                                       0, 64, true, &in_tmp, stream)));
+        const unsigned long long* keys = in_tmp ? k1.as<unsigned long long>() : k0.as<unsigned long long>();
+        // distinct starts; largest start = last sorted key; integrality of the starts
+        GPC_TRY(select_if("unique_starts",
+                          UniqueStartsOp{keys, n, xu.as<double>(), wpre.as<uint32_t>(), err + 1}, n,
+                          total.as<unsigned long long>(), stream));
+        GPC_READ_BACK({total.p, &hU, (unsigned)(8)}, {err, &herr, (unsigned)(4)}, {err + 1, &not_integer, (unsigned)(4)}, {keys + (n - 1), &last_key, (unsigned)(8)});
+        x_last = key_to_f64(last_key);
+    }
     if (herr) {
         set_error("Interval has node(s) not part of graph/pileup");
         return herr;
@@ -784,6 +837,7 @@ extern "C" int gpc_control_backproject(const gpc_graph_t* graph, const uint8_t* 
                                        double min_value, double value_scale, uint32_t* out_pos,
                                        double* out_val, uint64_t out_capacity, uint64_t* n_out,
                                        void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     *n_out = 0;
     if (!graph->lin_start || !graph->lin_end) {

@@ -8,6 +8,7 @@ using namespace gpc;
 
 extern "C" int gpc_sort_u32(uint32_t* keys, uint32_t* keys_tmp, uint64_t n, int32_t begin_bit,
                             int32_t end_bit, int32_t* result_in_tmp, void* stream) {
+    GPC_STAGE();
     bool in_tmp = false;
     int s = radix_sort<uint32_t, false>(keys, keys_tmp, nullptr, nullptr, n, begin_bit, end_bit,
                                         false, &in_tmp, (cudaStream_t)stream);
@@ -18,6 +19,7 @@ extern "C" int gpc_sort_u32(uint32_t* keys, uint32_t* keys_tmp, uint64_t n, int3
 extern "C" int gpc_sort_u64_pairs(uint64_t* keys, uint64_t* keys_tmp, uint32_t* vals,
                                   uint32_t* vals_tmp, uint64_t n, int32_t begin_bit,
                                   int32_t end_bit, int32_t* result_in_tmp, void* stream) {
+    GPC_STAGE();
     bool in_tmp = false;
     int s;
     if (vals)
@@ -36,6 +38,7 @@ extern "C" int gpc_sort_u64_pairs(uint64_t* keys, uint64_t* keys_tmp, uint32_t* 
 
 extern "C" int gpc_exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n,
                                       uint64_t* total, void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     Scratch t;
     GPC_CUDA(t.alloc(8, stream));

@@ -522,6 +522,7 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
                            double sample_scale, const uint32_t* control_pos,
                            const double* control_val, uint64_t n_control, double control_scale,
                            uint32_t* out_pos, double* out_p, uint64_t* n_out, void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     *n_out = 0;
     uint64_t total = n_sample + n_control;
@@ -578,6 +579,7 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
 extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n_runs,
                                 uint32_t track_size, double* table_p, uint64_t* table_count,
                                 uint64_t table_capacity, uint64_t* n_distinct, void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     *n_distinct = 0;
     if (n_runs == 0) return GPC_OK;
@@ -629,6 +631,7 @@ extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n
 extern "C" int gpc_qtable_build(const double* table_p, const uint64_t* table_count,
                                 uint64_t n_entries, uint64_t total_bp, double* out_p, double* out_q,
                                 uint64_t* n_out, void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     *n_out = 0;
     if (n_entries == 0) return GPC_OK;
@@ -664,6 +667,7 @@ extern "C" int gpc_qtable_build(const double* table_p, const uint64_t* table_cou
 extern "C" int gpc_qvalues_apply(const double* p, uint64_t n_runs, const double* table_p,
                                  const double* table_q, uint64_t n_table, double* out_q,
                                  void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_runs == 0) return GPC_OK;
     Scratch miss;
@@ -681,6 +685,7 @@ extern "C" int gpc_qvalues_apply(const double* p, uint64_t n_runs, const double*
 
 extern "C" int gpc_threshold(const uint32_t* pos, const double* q, uint64_t n_runs, double cutoff,
                              uint32_t* out_pos, uint8_t* out_val, uint64_t* n_out, void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     *n_out = 0;
     if (n_runs == 0) return GPC_OK;

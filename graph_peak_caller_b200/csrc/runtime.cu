@@ -100,6 +100,37 @@ int sm_count() {
     return n;
 }
 
+// ---- guard mode ----------------------------------------------------------------
+static std::atomic<unsigned long long> g_guard_violations{0};
+
+bool guard_mode() {
+    static const bool on = [] { const char* e = getenv("GPC_GUARD"); return e && atoi(e) != 0; }();
+    return on;
+}
+
+// base: start of the padded allocation; bytes: the size the caller asked for
+void guard_check(const void* base, size_t bytes, cudaStream_t stream) {
+    const size_t body = (bytes + 15) & ~(size_t)15;
+    unsigned char head[GUARD_PAD], tail[GUARD_PAD + 16];
+    const char* b = static_cast<const char*>(base);
+    // the unused tail of the last 16 bytes belongs to the canary as well
+    const size_t slack = body - bytes;
+    if (cudaMemcpyAsync(head, b, GUARD_PAD, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaMemcpyAsync(tail, b + GUARD_PAD + bytes, GUARD_PAD + slack, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess) {
+        cudaGetLastError();
+        return;                        // a faulted stream is reported by whoever launched on it
+    }
+    size_t bad_head = 0, bad_tail = 0;
+    for (size_t i = 0; i < GUARD_PAD; ++i) bad_head += head[i] != 0xA5;
+    for (size_t i = 0; i < GUARD_PAD + slack; ++i) bad_tail += tail[i] != 0xA5;
+    if (bad_head || bad_tail) {
+        g_guard_violations.fetch_add(1);
+        fprintf(stderr, "gpc_b200 GUARD: scratch of %zu bytes written outside its bounds "
+                        "(%zu bytes before, %zu bytes behind)\n", bytes, bad_head, bad_tail);
+    }
+}
+
 // ---- read_back ---------------------------------------------------------------
 struct RbArgs { const unsigned char* src[4]; unsigned bytes[4]; int n; };
 constexpr unsigned RB_PAYLOAD = 160;
@@ -192,6 +223,9 @@ extern "C" int gpc_linear_map_from_graph_host(const int64_t* node_len, const int
     for (uint64_t v = 0; v < n_nodes; ++v) ends[v] = length - ends[v];
     return GPC_OK;
 }
+
+extern "C" uint64_t gpc_guard_violations(void) { return gpc::g_guard_violations.load(); }
+extern "C" int gpc_guard_mode(void) { return gpc::guard_mode() ? 1 : 0; }
 
 extern "C" void gpc_profile_enable(int on) { gpc::g_prof_on = on != 0; }
 extern "C" uint64_t gpc_launch_count(void) { return gpc::g_launches.load(); }

@@ -124,32 +124,31 @@ struct Frontier {
     uint32_t k0, k1, k2, k3, r0, r1, r2, r3;
     int n;                                  // entries in registers (sorted by key)
     int xn;                                 // spilled entries (unsorted)
-    int xcap;
-    bool overflow;
+    int state;                              // bit 0: overflow, bit 1: spill list sits in the pool
     uint32_t* xkey;
     uint32_t* xrem;
-    SpillPool pool;
 
-    __device__ __forceinline__ void init(FrontierSpill& sp, const SpillPool& p) {
-        n = 0; xn = 0; overflow = false; xcap = FRONTIER_CAP;
+    __device__ __forceinline__ void init(FrontierSpill& sp) {
+        n = 0; xn = 0; state = 0;
         k0 = k1 = k2 = k3 = 0; r0 = r1 = r2 = r3 = 0;
         xkey = sp.key; xrem = sp.rem;
-        pool = p;
     }
     __device__ __forceinline__ bool empty() const { return n == 0 && xn == 0; }
 
-    __device__ __forceinline__ bool grow() {
-        if (xcap != FRONTIER_CAP || !pool.base) return false;
+    // (the pool is the kernel's parameter: it stays in the constant bank, the frontier's
+    //  own state in registers -- as a member it cost the walk 17 % of its speed)
+    __device__ __forceinline__ bool grow(const SpillPool& pool) {
+        if ((state & 2) || !pool.base) return false;
         const unsigned c = atomicAdd(pool.next, 1u);
         if (c >= pool.n_chunks) return false;
         uint32_t* nk = pool.base + (size_t)c * 2 * SPILL_CHUNK;
         uint32_t* nr = nk + SPILL_CHUNK;
         for (int f = 0; f < xn; ++f) { nk[f] = xkey[f]; nr[f] = xrem[f]; }
-        xkey = nk; xrem = nr; xcap = SPILL_CHUNK;
+        xkey = nk; xrem = nr; state |= 2;
         return true;
     }
 
-    __device__ __forceinline__ void push(uint32_t key, uint32_t rem) {
+    __device__ __forceinline__ void push(uint32_t key, uint32_t rem, const SpillPool& pool) {
         // a node that sits in the spill list must be found there before any of the
         // register paths may insert it (rare: only after more than four were pending)
         if (xn > 0) {
@@ -182,10 +181,10 @@ struct Frontier {
             if (k3 < k2) { t = k2; k2 = k3; k3 = t; t = r2; r2 = r3; r3 = t; }
             if (k2 < k1) { t = k1; k1 = k2; k2 = t; t = r1; r1 = r2; r2 = t; }
             if (k1 < k0) { t = k0; k0 = k1; k1 = t; t = r0; r0 = r1; r1 = t; }
-        } else if (xn < xcap || grow()) {
+        } else if (xn < ((state & 2) ? SPILL_CHUNK : FRONTIER_CAP) || grow(pool)) {
             xkey[xn] = key; xrem[xn] = rem; ++xn;
         } else {
-            overflow = true;
+            state |= 1;
         }
     }
 
@@ -293,7 +292,7 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
             // ---- extension frontier ----------------------------------------
             FrontierSpill spill;
             Frontier fr;
-            fr.init(spill, pool);
+            fr.init(spill);
             uint32_t cur_v = last_v;
             uint32_t carry = total > last_len ? total - last_len : 0;
             while (true) {
@@ -304,11 +303,11 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
                         const uint32_t* adj = (fwd ? graph.succ + a.y : graph.pred + a.z);
                         for (uint32_t e = 0; e < cur.n_adj; ++e) {
                             uint32_t wv = adj[e];
-                            fr.push(fwd ? wv : ~wv, carry);
+                            fr.push(fwd ? wv : ~wv, carry, pool);
                         }
                     } else {
-                        if (cur.n_adj > 0) fr.push(fwd ? cur.adj0 : ~cur.adj0, carry);
-                        if (cur.n_adj > 1) fr.push(fwd ? cur.adj1 : ~cur.adj1, carry);
+                        if (cur.n_adj > 0) fr.push(fwd ? cur.adj0 : ~cur.adj0, carry, pool);
+                        if (cur.n_adj > 1) fr.push(fwd ? cur.adj1 : ~cur.adj1, carry, pool);
                     }
                 }
                 if (fr.empty()) break;
@@ -326,7 +325,7 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
                 ce = ns + min(rem, len);
                 carry = rem > len ? rem - len : 0;
             }
-            const bool overflow = fr.overflow;
+            const bool overflow = (fr.state & 1) != 0;
             em.emit(ce, true, TAG_FRAG);
             if (overflow) atomicExch(err, GPC_ERR_FRONTIER_OVERFLOW);
             n_emitted = em.n_emitted;
@@ -1123,6 +1122,7 @@ using namespace gpc;
 extern "C" int gpc_unique_reads(const int32_t* start_node, const int32_t* start_off,
                                 uint64_t n_reads, uint32_t* out_index, uint64_t* out_count,
                                 void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     *out_count = 0;
     if (n_reads == 0) return GPC_OK;
@@ -1225,6 +1225,7 @@ static int check_sample_args(const gpc_graph_t* graph, int32_t extension) {
 static double walk_read_bytes(const gpc_reads_t* reads) { return reads->hdr ? 20.0 : 36.0; }
 
 extern "C" int gpc_build_read_headers(const gpc_reads_t* reads, uint32_t* hdr, void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     if (reads->n_reads == 0) return GPC_OK;
     if (reads->n_reads >= (1ull << 31)) { set_error("too many reads"); return GPC_ERR_ARG; }
@@ -1239,6 +1240,7 @@ extern "C" int gpc_build_read_headers(const gpc_reads_t* reads, uint32_t* hdr, v
 extern "C" int gpc_reads_from_compact(const uint32_t* offs, const uint8_t* path_len,
                                       const int32_t* path, uint64_t n_reads, int32_t* start_node,
                                       int32_t* start_off, uint32_t* hdr, void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_reads == 0) return GPC_OK;
     if (n_reads >= (1ull << 31)) { set_error("too many reads"); return GPC_ERR_ARG; }
@@ -1257,6 +1259,7 @@ extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* re
                                  const uint32_t* read_index, uint64_t n_reads, int32_t extension,
                                  uint32_t* events, uint64_t event_capacity,
                                  uint64_t* n_events, uint8_t* touched, void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     *n_events = 0;
     GPC_TRY(check_sample_args(graph, extension));
@@ -1357,6 +1360,7 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
                                  int32_t* direct_val, uint64_t capacity, uint64_t* n_frag,
                                  uint64_t* n_direct, uint64_t* n_events, uint8_t* touched,
                                  int32_t mode, void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     *n_frag = *n_direct = *n_events = 0;
     GPC_TRY(check_sample_args(graph, extension));
@@ -1467,6 +1471,7 @@ extern "C" int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64
                                   uint32_t size_bp, uint32_t* frag_idx, int32_t* frag_val,
                                   uint64_t* n_frag, uint32_t* direct_idx, int32_t* direct_val,
                                   uint64_t* n_direct, void* stream_) {
+    GPC_STAGE();
     return events_to_runs_impl(events, events_tmp, n_events, size_bp, frag_idx, frag_val, n_frag,
                                direct_idx, direct_val, n_direct, n_events + 1, (cudaStream_t)stream_);
 }

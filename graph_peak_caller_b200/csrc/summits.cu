@@ -37,6 +37,7 @@ extern "C" int gpc_peak_summits(const gpc_graph_t* graph, const int32_t* peak_st
                                 const int32_t* peak_nodes, uint64_t n_peaks,
                                 const uint32_t* q_pos, const double* q_val, uint64_t n_q,
                                 int32_t window, int32_t* out, void* stream_) {
+    GPC_STAGE();
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_peaks == 0) return GPC_OK;
     if (window < 0) { set_error("gpc_peak_summits: negative window"); return GPC_ERR_ARG; }

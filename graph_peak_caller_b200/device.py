@@ -2,6 +2,7 @@
 pointer structs of include/gpc_b200.h.  PyTorch is only the allocator and the
 stream here; every computation is a kernel of libgpc_b200.so."""
 import ctypes
+import os
 
 import numpy as np
 
@@ -65,9 +66,46 @@ def to_device(a, dtype=None):
     return torch.from_numpy(a).to(device(), non_blocking=False)
 
 
+# Guard mode (GPC_GUARD=1, see csrc/common.cuh): the output arrays the kernels fill are
+# poisoned and fenced by canaries too; check_guards() verifies the fences of every array
+# handed out since the last check.
+GUARD = os.environ.get("GPC_GUARD", "0") not in ("", "0")
+_GUARD_PAD = 256
+_guarded = []
+
+
 def empty(n, dtype):
     torch = torch_cuda()
-    return torch.empty(int(n), dtype=dtype, device=device())
+    if not GUARD:
+        return torch.empty(int(n), dtype=dtype, device=device())
+    size = torch.empty(0, dtype=dtype).element_size()
+    nbytes = int(n) * size
+    body = (nbytes + 15) & ~15
+    raw = torch.full((body + 2 * _GUARD_PAD,), 0xA5, dtype=torch.uint8, device=device())
+    _guarded.append((raw, nbytes))
+    return raw[_GUARD_PAD:_GUARD_PAD + nbytes].view(dtype)
+
+
+def check_guards():
+    """Number of guarded arrays (Python-side outputs + the library's scratch) found written
+    outside their bounds since the last call; 0 outside guard mode."""
+    torch = torch_cuda()
+    bad = 0
+    torch.cuda.synchronize()
+    for raw, nbytes in _guarded:
+        head = raw[:_GUARD_PAD]
+        tail = raw[_GUARD_PAD + nbytes:]
+        if bool((head != 0xA5).any()) or bool((tail != 0xA5).any()):
+            bad += 1
+    _guarded.clear()
+    lib = _lib.load()
+    total = int(lib.gpc_guard_violations())
+    bad += total - check_guards.seen
+    check_guards.seen = total
+    return bad
+
+
+check_guards.seen = 0
 
 
 class DeviceGraph:
@@ -105,9 +143,17 @@ class DeviceGraph:
         self._struct()
 
     def set_linear_map(self, starts, ends):
-        self.lin_start = to_device(np.asarray(starts, dtype=np.float64))
-        self.lin_end = to_device(np.asarray(ends, dtype=np.float64))
-        self.linear_length = float(np.asarray(ends)[-1])
+        starts = np.asarray(starts, dtype=np.float64)
+        ends = np.asarray(ends, dtype=np.float64)
+        self.lin_start = to_device(starts)
+        self.lin_end = to_device(ends)
+        self.linear_length = float(ends[-1])
+        # every node's linear span a whole multiple of its length (scale of
+        # control/linearmap.py:43-49 an integer everywhere): read starts project to integers
+        span, size = ends - starts, self.graph.node_len.astype(np.float64)
+        self.integer_linear = bool(size.size and np.all(size > 0) and np.all(starts == np.floor(starts))
+                                   and np.all(span == np.floor(span)) and np.all(np.fmod(span, size) == 0)
+                                   and float(ends.max()) <= self.graph.size_bp)
         self._struct()
 
     def _struct(self):
@@ -115,7 +161,7 @@ class DeviceGraph:
         self.c = _lib.GpcGraph(g.n_nodes, g.n_edges, g.size_bp, g.min_node,
                                ptr(self.node_rec), ptr(self.succ), ptr(self.pred),
                                ptr(self.lin_start), ptr(self.lin_end), ptr(self.walk_rec),
-                               0 if g.is_ordered else 1)
+                               (0 if g.is_ordered else 1) | (2 if getattr(self, "integer_linear", False) else 0))
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in

@@ -15,7 +15,7 @@ def sort_u32(keys, begin_bit=0, end_bit=32):
     """keys: int32 CUDA tensor holding uint32 bit patterns.  Returns sorted tensor."""
     torch = torch_cuda()
     lib = _lib.load()
-    tmp = torch.empty_like(keys)
+    tmp = empty(keys.numel(), keys.dtype)
     flag = ctypes.c_int32(0)
     _lib.check(lib.gpc_sort_u32(ptr(keys), ptr(tmp), keys.numel(), begin_bit, end_bit,
                                 ctypes.byref(flag), stream_ptr()))
@@ -25,8 +25,8 @@ def sort_u32(keys, begin_bit=0, end_bit=32):
 def sort_u64_pairs(keys, vals=None, begin_bit=0, end_bit=64):
     torch = torch_cuda()
     lib = _lib.load()
-    ktmp = torch.empty_like(keys)
-    vtmp = torch.empty_like(vals) if vals is not None else None
+    ktmp = empty(keys.numel(), keys.dtype)
+    vtmp = empty(vals.numel(), vals.dtype) if vals is not None else None
     flag = ctypes.c_int32(0)
     _lib.check(lib.gpc_sort_u64_pairs(ptr(keys), ptr(ktmp), ptr(vals), ptr(vtmp),
                                       keys.numel(), begin_bit, end_bit,
@@ -39,7 +39,7 @@ def sort_u64_pairs(keys, vals=None, begin_bit=0, end_bit=64):
 def exclusive_scan_u32(x):
     torch = torch_cuda()
     lib = _lib.load()
-    out = torch.empty_like(x)
+    out = empty(x.numel(), x.dtype)
     total = _u64()
     _lib.check(lib.gpc_exclusive_scan_u32(ptr(x), ptr(out), x.numel(),
                                           ctypes.byref(total), stream_ptr()))
@@ -111,7 +111,7 @@ def events_to_runs(events, size_bp):
     torch = torch_cuda()
     lib = _lib.load()
     n = events.numel()
-    tmp = torch.empty_like(events)
+    tmp = empty(events.numel(), events.dtype)
     fi, fv = empty(n + 1, torch.int32), empty(n + 1, torch.int32)
     di, dv = empty(n + 1, torch.int32), empty(n + 1, torch.int32)
     nf, nd = _u64(), _u64()
@@ -204,7 +204,7 @@ def qtable_build(table_p, table_count, total_bp):
 def qvalues_apply(p, table_p, table_q):
     torch = torch_cuda()
     lib = _lib.load()
-    q = torch.empty_like(p)
+    q = empty(p.numel(), p.dtype)
     _lib.check(lib.gpc_qvalues_apply(ptr(p), p.numel(), ptr(table_p), ptr(table_q),
                                      table_p.numel(), ptr(q), stream_ptr()))
     return q

@@ -71,6 +71,10 @@ typedef struct gpc_graph {
     uint32_t flags;
 } gpc_graph_t;
 #define GPC_GRAPH_UNORDERED 1u
+/* bit 1: the linear span (lin_end - lin_start) of every node is a whole multiple of its
+ * length, so every read start projects to an integer (control/linearmap.py:43-74): the
+ * control stage then sorts 32-bit integer keys.  Set by whoever uploads the linear map. */
+#define GPC_GRAPH_INTEGER_LINEAR 2u
 
 /* Reads in HBM, structure of arrays (signed node ids: negative == reverse
  * strand, as obg Interval.region_paths). */
@@ -308,6 +312,11 @@ int gpc_peak_summits(const gpc_graph_t* graph, const int32_t* peak_start,
  * its stream; gpc_profile_report writes "name calls total_ms" lines for the
  * launches since the previous report and returns the bytes needed. */
 uint64_t gpc_launch_count(void);
+/* Guard mode (GPC_GUARD=1 in the environment when the library is loaded): scratch buffers
+ * are poisoned and fenced by canaries; gpc_guard_violations counts buffers found written
+ * outside their bounds since the library was loaded. */
+int gpc_guard_mode(void);
+uint64_t gpc_guard_violations(void);
 void gpc_profile_enable(int on);
 uint64_t gpc_profile_report(char* buf, uint64_t capacity);
 
