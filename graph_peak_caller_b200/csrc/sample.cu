@@ -120,6 +120,21 @@ struct SpillPool {
     unsigned n_chunks;
 };
 
+// Out of line on purpose (and pointers in, pointer out: nothing of the frontier has its
+// address taken, so its state stays in registers): inlined at the three push sites the grow
+// path cost the walk 10-17 % of its speed although it never ran.
+__device__ __noinline__ uint32_t* spill_grow(const uint32_t* keys, const uint32_t* rems, int n,
+                                             SpillPool pool) {
+    if (!pool.base) return nullptr;
+    const unsigned c = atomicAdd(pool.next, 1u);
+    if (c >= pool.n_chunks) return nullptr;
+    uint32_t* nk = pool.base + (size_t)c * 2 * SPILL_CHUNK;
+    uint32_t* nr = nk + SPILL_CHUNK;
+    for (int f = 0; f < n; ++f) { nk[f] = keys[f]; nr[f] = rems[f]; }
+    return nk;
+}
+
+template <bool BIG>
 struct Frontier {
     uint32_t k0, k1, k2, k3, r0, r1, r2, r3;
     int n;                                  // entries in registers (sorted by key)
@@ -134,19 +149,6 @@ struct Frontier {
         xkey = sp.key; xrem = sp.rem;
     }
     __device__ __forceinline__ bool empty() const { return n == 0 && xn == 0; }
-
-    // (the pool is the kernel's parameter: it stays in the constant bank, the frontier's
-    //  own state in registers -- as a member it cost the walk 17 % of its speed)
-    __device__ __forceinline__ bool grow(const SpillPool& pool) {
-        if ((state & 2) || !pool.base) return false;
-        const unsigned c = atomicAdd(pool.next, 1u);
-        if (c >= pool.n_chunks) return false;
-        uint32_t* nk = pool.base + (size_t)c * 2 * SPILL_CHUNK;
-        uint32_t* nr = nk + SPILL_CHUNK;
-        for (int f = 0; f < xn; ++f) { nk[f] = xkey[f]; nr[f] = xrem[f]; }
-        xkey = nk; xrem = nr; state |= 2;
-        return true;
-    }
 
     __device__ __forceinline__ void push(uint32_t key, uint32_t rem, const SpillPool& pool) {
         // a node that sits in the spill list must be found there before any of the
@@ -181,10 +183,17 @@ struct Frontier {
             if (k3 < k2) { t = k2; k2 = k3; k3 = t; t = r2; r2 = r3; r3 = t; }
             if (k2 < k1) { t = k1; k1 = k2; k2 = t; t = r1; r1 = r2; r2 = t; }
             if (k1 < k0) { t = k0; k0 = k1; k1 = t; t = r0; r0 = r1; r1 = t; }
-        } else if (xn < ((state & 2) ? SPILL_CHUNK : FRONTIER_CAP) || grow(pool)) {
-            xkey[xn] = key; xrem[xn] = rem; ++xn;
+        } else if (!BIG) {
+            // the fast kernel gives up here; the host then runs the launch again with BIG
+            if (xn < FRONTIER_CAP) { xkey[xn] = key; xrem[xn] = rem; ++xn; }
+            else state |= 1;
         } else {
-            state |= 1;
+            if (xn >= ((state & 2) ? SPILL_CHUNK : FRONTIER_CAP)) {
+                uint32_t* nk = (state & 2) ? nullptr : spill_grow(xkey, xrem, xn, pool);
+                if (!nk) { state |= 1; return; }
+                xkey = nk; xrem = nk + SPILL_CHUNK; state |= 2;
+            }
+            xkey[xn] = key; xrem[xn] = rem; ++xn;
         }
     }
 
@@ -208,7 +217,7 @@ struct Frontier {
     }
 };
 
-template <bool DENSE>
+template <bool DENSE, bool BIG>
 __global__ void __launch_bounds__(WALK_THREADS, 10)
 walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restrict__ read_index,
                   unsigned n_reads, int extension, uint32_t* __restrict__ events,
@@ -291,7 +300,7 @@ walk_reads_kernel(gpc_graph_t graph, gpc_reads_t reads, const uint32_t* __restri
             ce = last_start + min(total, last_len);
             // ---- extension frontier ----------------------------------------
             FrontierSpill spill;
-            Frontier fr;
+            Frontier<BIG> fr;
             fr.init(spill);
             uint32_t cur_v = last_v;
             uint32_t carry = total > last_len ? total - last_len : 0;
@@ -1272,20 +1281,34 @@ extern "C" int gpc_sample_events(const gpc_graph_t* graph, const gpc_reads_t* re
     int* err = reinterpret_cast<int*>(count + 1);
     WalkOrder order;
     GPC_TRY(walk_order(graph, reads, &read_index, n_reads, order, stream));
+    // The fast kernel holds up to 4 + 32 pending nodes per read; a launch in which some read
+    // needs more (deeply nested bubbles with long branches) is run again with the kernel whose
+    // spill list can move into a pool chunk of 4096 entries.
     SpillStore spill;
-    GPC_TRY(spill.init(stream));
-    GPC_PROF("walk_reads");
-    if (graph->flags & GPC_GRAPH_UNORDERED)
-        walk_reads_cyclic_kernel<false><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
-            *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
-            nullptr, touched, err);
-    else
-        walk_reads_kernel<false><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
-            *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
-            nullptr, touched, err, spill.pool);
-    GPC_LAUNCH_CHECK();
     unsigned long long h[2] = {0, 0};
-    GPC_READ_BACK({ctr.p, h, (unsigned)(16)});
+    for (int big = 0; big < 2; ++big) {
+        if (big) {
+            GPC_TRY(spill.init(stream));
+            GPC_CUDA(cudaMemsetAsync(ctr.p, 0, 16, stream));
+        }
+        GPC_PROF("walk_reads");
+        if (graph->flags & GPC_GRAPH_UNORDERED)
+            walk_reads_cyclic_kernel<false><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+                *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
+                nullptr, touched, err);
+        else if (big)
+            walk_reads_kernel<false, true><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+                *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
+                nullptr, touched, err, spill.pool);
+        else
+            walk_reads_kernel<false, false><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+                *graph, *reads, read_index, (unsigned)n_reads, extension, events, event_capacity, count,
+                nullptr, touched, err, spill.pool);
+        GPC_LAUNCH_CHECK();
+        GPC_READ_BACK({ctr.p, h, (unsigned)(16)});
+        if ((int)(h[1] & 0xffffffffu) != GPC_ERR_FRONTIER_OVERFLOW || (graph->flags & GPC_GRAPH_UNORDERED))
+            break;
+    }
     *n_events = h[0];
     prof_add_bytes("walk_reads", walk_read_bytes(reads) * (double)n_reads + 4.0 * (double)h[0]);
     GPC_TRY(walk_error((int)(h[1] & 0xffffffffu)));
@@ -1409,7 +1432,6 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
     } rel{ws, stream, false};
     const size_t bytes = (size_t)tiles * 16 + 64;
     GPC_CUDA(sc.alloc(bytes, stream));
-    GPC_CUDA(cudaMemsetAsync(sc.p, 0, bytes, stream));
     char* p = sc.as<char>();
     unsigned long long* counts = reinterpret_cast<unsigned long long*>(p);            // 2 run counts
     unsigned long long* n_steps = counts + 2;
@@ -1420,43 +1442,55 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
     WalkOrder order;
     GPC_TRY(walk_order(graph, reads, &read_index, n_reads, order, stream));
     SpillStore spill;
-    GPC_TRY(spill.init(stream));
-    GPC_PROF("walk_reads");
-    if (graph->flags & GPC_GRAPH_UNORDERED)
-        walk_reads_cyclic_kernel<true><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
-            *graph, *reads, read_index, (unsigned)n_reads, extension, nullptr, 0, n_steps, dense,
-            touched, err);
-    else
-        walk_reads_kernel<true><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
-            *graph, *reads, read_index, (unsigned)n_reads, extension, nullptr, 0, n_steps, dense,
-            touched, err, spill.pool);
-    GPC_LAUNCH_CHECK();
-    GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
-    if (variant == 2) {
-        const unsigned blocks = min(div_up(tiles, DR_WARPS), (unsigned)(sm_count() * 5));
-        dense_runs_kernel<<<blocks, DR_THREADS, 0, stream>>>(dense, n_pos, tiles, frag_idx, frag_val,
-                                                             direct_idx, direct_val, capacity, st_tot,
-                                                             st_cnt, ticket, counts);
-    } else if (variant == 1) {
-        constexpr int SMEM = DR_THREADS * (32 * 8 + 16);
-        static bool configured = false;
-        if (!configured) {
-            GPC_CUDA(cudaFuncSetAttribute(dense_runs_block_kernel<32>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-            configured = true;
-        }
-        dense_runs_block_kernel<32><<<tiles, DR_THREADS, SMEM, stream>>>(
-            dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt, ticket,
-            counts);
-    } else {
-        dense_runs_block_kernel<16><<<tiles, DR_THREADS, DR_THREADS * (16 * 8 + 16), stream>>>(
-            dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt, ticket,
-            counts);
-    }
-    GPC_LAUNCH_CHECK();
-    rel.clean = true;
     unsigned long long h[4] = {0, 0, 0, 0};
-    GPC_READ_BACK({counts, h, (unsigned)(32)});
+    // (second round: only when the fast kernel's frontier overflowed, see gpc_sample_events;
+    //  the scan of the first round has left the array zeroed again)
+    for (int big = 0; big < 2; ++big) {
+        if (big) GPC_TRY(spill.init(stream));
+        GPC_CUDA(cudaMemsetAsync(sc.p, 0, bytes, stream));
+        rel.clean = false;
+        GPC_PROF("walk_reads");
+        if (graph->flags & GPC_GRAPH_UNORDERED)
+            walk_reads_cyclic_kernel<true><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+                *graph, *reads, read_index, (unsigned)n_reads, extension, nullptr, 0, n_steps, dense,
+                touched, err);
+        else if (big)
+            walk_reads_kernel<true, true><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+                *graph, *reads, read_index, (unsigned)n_reads, extension, nullptr, 0, n_steps, dense,
+                touched, err, spill.pool);
+        else
+            walk_reads_kernel<true, false><<<div_up(n_reads, WALK_THREADS), WALK_THREADS, 0, stream>>>(
+                *graph, *reads, read_index, (unsigned)n_reads, extension, nullptr, 0, n_steps, dense,
+                touched, err, spill.pool);
+        GPC_LAUNCH_CHECK();
+        GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
+        if (variant == 2) {
+            const unsigned blocks = min(div_up(tiles, DR_WARPS), (unsigned)(sm_count() * 5));
+            dense_runs_kernel<<<blocks, DR_THREADS, 0, stream>>>(dense, n_pos, tiles, frag_idx, frag_val,
+                                                                 direct_idx, direct_val, capacity, st_tot,
+                                                                 st_cnt, ticket, counts);
+        } else if (variant == 1) {
+            constexpr int SMEM = DR_THREADS * (32 * 8 + 16);
+            static bool configured = false;
+            if (!configured) {
+                GPC_CUDA(cudaFuncSetAttribute(dense_runs_block_kernel<32>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+                configured = true;
+            }
+            dense_runs_block_kernel<32><<<tiles, DR_THREADS, SMEM, stream>>>(
+                dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt,
+                ticket, counts);
+        } else {
+            dense_runs_block_kernel<16><<<tiles, DR_THREADS, DR_THREADS * (16 * 8 + 16), stream>>>(
+                dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt,
+                ticket, counts);
+        }
+        GPC_LAUNCH_CHECK();
+        rel.clean = true;
+        GPC_READ_BACK({counts, h, (unsigned)(32)});
+        if ((int)(h[3] & 0xffffffffu) != GPC_ERR_FRONTIER_OVERFLOW || (graph->flags & GPC_GRAPH_UNORDERED))
+            break;
+    }
     *n_frag = h[0];
     *n_direct = h[1];
     *n_events = h[2];
