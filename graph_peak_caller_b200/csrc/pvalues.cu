@@ -32,10 +32,20 @@ namespace gpc {
 // (L1-cached) loads: an entry whose tag says READY was complete when the line
 // was fetched, and a stale line can only say "empty"/"claimed", which sends the
 // pair to the tile's miss queue, where the probe is repeated against L2.
+// The payload validates itself: check = bits(count) ^ bits(lam) ^ bits(p).  A reader whose
+// tag and payload loads were served by different fills of the line (the fast probe has no
+// acquire ordering; the compiler may also split the entry into two 16-byte loads) cannot pair
+// a READY tag with a stale p: the check fails and the pair goes to the miss queue.  The only
+// stale payload that passes is all zeroes for (count 0, lambda 0), whose p is 0 anyway.
 struct __align__(32) MemoEntry {
     unsigned long long tag;    // 0 empty | hash|1 claimed | hash|3 ready (hash has bits 0-1 clear)
-    double count, lam, p;
+    double lam, p;
+    unsigned long long check;
 };
+__device__ __forceinline__ unsigned long long memo_check(double count, double lam, double p) {
+    return (unsigned long long)__double_as_longlong(count) ^ (unsigned long long)__double_as_longlong(lam) ^
+           (unsigned long long)__double_as_longlong(p);
+}
 struct PMemo {
     MemoEntry* e;              // [mask + 1] or nullptr
     unsigned mask;
@@ -61,10 +71,11 @@ __device__ __forceinline__ bool memo_find(const PMemo& m, unsigned long long h, 
         const MemoEntry* e = &m.e[s];
         unsigned long long tag = FROM_L2 ? __ldcg(&e->tag) : e->tag;
         if (tag == (h | 3ull)) {
-            double c = FROM_L2 ? __ldcg(&e->count) : e->count;
-            double l = FROM_L2 ? __ldcg(&e->lam) : e->lam;
-            if (c == count && l == lam) {
-                p = FROM_L2 ? __ldcg(&e->p) : e->p;
+            const double l = FROM_L2 ? __ldcg(&e->lam) : e->lam;
+            const double v = FROM_L2 ? __ldcg(&e->p) : e->p;
+            const unsigned long long chk = FROM_L2 ? __ldcg(&e->check) : e->check;
+            if (l == lam && chk == memo_check(count, lam, v)) {
+                p = v;
                 return true;
             }
         } else if (tag == 0ull || (tag | 3ull) == (h | 3ull)) {
@@ -84,9 +95,9 @@ __device__ __forceinline__ void memo_publish(const PMemo& m, unsigned long long 
         unsigned long long tag = __ldcg(&e->tag);
         if (tag == 0ull) tag = atomicCAS(&e->tag, 0ull, h | 1ull);
         if (tag == 0ull) {                                     // mine
-            e->count = count;
             e->lam = lam;
             e->p = p;
+            e->check = memo_check(count, lam, p);
             __threadfence();
             *reinterpret_cast<volatile unsigned long long*>(&e->tag) = h | 3ull;
             return;
@@ -544,6 +555,7 @@ extern "C" int gpc_pvalues(const uint32_t* sample_pos, const int32_t* sample_val
     if (total >= (1u << 16)) {
         int lg = 20;
         if (const char* v = getenv("GPC_MEMO_LOG2")) lg = atoi(v);
+        lg = lg < 10 ? 10 : (lg > 26 ? 26 : lg);               // 32 KB .. 2 GB of entries
         const size_t cap = (size_t)1 << lg;
         GPC_CUDA(memo_buf.alloc(cap * sizeof(MemoEntry), stream));
         GPC_CUDA(cudaMemsetAsync(memo_buf.p, 0, cap * sizeof(MemoEntry), stream));

@@ -258,13 +258,22 @@ class DeviceReads:
 
 
 def device_graph(graph, linear_map=None):
-    """Cached upload of a host Graph."""
+    """Cached upload of a host Graph.  A linear map that differs from the one installed
+    (another LinearMap object with other numbers) replaces it; the same arrays, or equal
+    ones, are not uploaded again."""
     dg = getattr(graph, "_device", None)
     if dg is None:
         dg = DeviceGraph(graph, linear_map)
         graph._device = dg
-    elif linear_map is not None and dg.lin_start is None:
-        dg.set_linear_map(*linear_map)
+        dg._lm_host = linear_map
+    elif linear_map is not None:
+        have = getattr(dg, "_lm_host", None)
+        same = have is not None and all(
+            a is b or (np.shape(a) == np.shape(b) and np.array_equal(a, b))
+            for a, b in zip(have, linear_map))
+        if dg.lin_start is None or not same:
+            dg.set_linear_map(*linear_map)
+            dg._lm_host = linear_map
     return dg
 
 

@@ -71,7 +71,10 @@ class PToQValuesMapper:
         logging.info("Creating mapping from p value dense pileup")
         pos, p = p_values.device_arrays()
         tp, tc = kernels.ptable_local(pos, p, int(p_values.track_size))
-        return cls._from_device_table(tp, tc, int(p_values.track_size))
+        # N = sum of the run lengths = track_size - indices[0] (sparsepvalues.py:70-74); tracks
+        # made by the kernels start at 0, a host-built one may not
+        first = 0 if p_values._h_idx is None else int(np.asarray(p_values._h_idx)[0])
+        return cls._from_device_table(tp, tc, int(p_values.track_size) - first)
 
     @classmethod
     def from_files(cls, base_file_name):
