@@ -1022,6 +1022,183 @@ dense_runs_block_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     }
 }
 
+
+// ---- the same scan with the tile loads on the bulk-copy engine -------------------------
+//
+// Persistent blocks, DP_STAGES tile buffers each.  ONE cp.async.bulk (1-D TMA, SASS UBLKCP)
+// per tile moves its 32 KB from the difference array into shared memory and completes on an
+// mbarrier; a block keeps DP_STAGES - 1 tiles in flight while it scans the oldest one, so the
+// load latency that the one-tile-per-block kernel waits out (long_scoreboard 13, barrier 11
+// warps per issue) is hidden behind the scan, the look-back and the writes of the tile before.
+// (First attempt: one 128-byte bulk copy per thread into padded rows -- 256 TMA operations per
+// tile, ~170 ns each per SM: 3.75 ms for the pass.  The copy engine wants few, large copies.)
+// Rows are NOT padded here (a bulk copy is contiguous): the order-free first pass reads the
+// eight 16-byte units of a thread's row rotated by the lane, which is conflict-free; the
+// emission pass needs them in order and pays the 8-way conflict.  Zeroes go back with plain
+// coalesced stores, only where a word was non-zero.
+constexpr int DP_STAGES = 3;
+constexpr int DP_ITEMS = 16;
+constexpr int DP_TILE = DR_THREADS * DP_ITEMS;            // 4096 positions
+constexpr int DP_STAGE_BYTES = DP_TILE * 8;               // 32 KB
+constexpr int DP_SMEM = DP_STAGES * DP_STAGE_BYTES;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes,
+                                          unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Tiles are dealt round-robin: block b scans tiles b, b + grid, b + 2 grid, ...  All blocks
+// of a wave then work on neighbouring tiles at the same time, so the look-back of a tile
+// finds its predecessors' aggregates published (the first version claimed tiles by ticket,
+// three per block up front: the second and third tile of a block sat in its queue while
+// the next block's first tile waited for their aggregates -- a serial chain through all
+// blocks, 2.6 ms).  A tile only ever waits on tiles of earlier waves or of the same wave in
+// blocks that are running: the launch is cooperative, i.e. refused unless the whole grid is
+// resident.
+__global__ void __launch_bounds__(DR_THREADS, 2)
+dense_runs_pipelined_kernel(unsigned long long* __restrict__ dense, unsigned n_tiles,
+                            uint32_t* __restrict__ frag_idx, int32_t* __restrict__ frag_val,
+                            uint32_t* __restrict__ dir_idx, int32_t* __restrict__ dir_val,
+                            unsigned long long cap,
+                            unsigned long long* __restrict__ st_tot /* zeroed */,
+                            unsigned long long* __restrict__ st_cnt /* zeroed */,
+                            unsigned long long* __restrict__ out_counts) {
+    extern __shared__ __align__(128) unsigned char dp_smem[];
+    __shared__ __align__(8) unsigned long long s_bar[DP_STAGES];
+    __shared__ long long s_scan64[33];
+    __shared__ unsigned long long s_base[2];
+    const unsigned t = threadIdx.x;
+    if (t == 0) {
+        for (int s = 0; s < DP_STAGES; ++s) mbar_init(&s_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // prologue: every stage gets its first tile
+        for (int s = 0; s < DP_STAGES; ++s) {
+            const unsigned tile = blockIdx.x + s * gridDim.x;
+            if (tile < n_tiles) {
+                mbar_arrive_expect_tx(&s_bar[s], DP_STAGE_BYTES);
+                bulk_load(dp_smem + s * DP_STAGE_BYTES, dense + (size_t)tile * DP_TILE, DP_STAGE_BYTES,
+                          &s_bar[s]);
+            }
+        }
+    }
+    __syncthreads();
+    for (unsigned it = 0;; ++it) {
+        const int s = it % DP_STAGES;
+        const unsigned parity = (it / DP_STAGES) & 1u;
+        const unsigned tile = blockIdx.x + it * gridDim.x;
+        if (tile >= n_tiles) break;
+        mbar_wait(&s_bar[s], parity);
+        const unsigned char* stage = dp_smem + s * DP_STAGE_BYTES;
+        // zero behind the read (striped: a warp's stores are contiguous), only non-zero words
+        {
+            unsigned long long* g = dense + (size_t)tile * DP_TILE;
+#pragma unroll
+            for (int j = 0; j < DP_ITEMS / 2; ++j) {
+                const unsigned u = j * DR_THREADS + t;
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(stage + u * 16);
+                if (v.x | v.y) *reinterpret_cast<ulonglong2*>(g + 2 * u) = make_ulonglong2(0ull, 0ull);
+            }
+        }
+        const unsigned char* row = stage + t * (DP_ITEMS * 8);
+        const unsigned base = tile * DP_TILE + t * DP_ITEMS;
+        int tf = 0, td = 0;
+        unsigned mf = 0, md = 0;
+#pragma unroll
+        for (int kk = 0; kk < DP_ITEMS / 2; ++kk) {
+            const int k = (kk + (int)t) & 7;              // rotated by the lane: conflict-free
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(row + k * 16);
+            int df, dd;
+            dense_unpack(v.x, df, dd);
+            tf += df; td += dd;
+            if (df != 0) mf |= 1u << (2 * k);
+            if (dd != 0) md |= 1u << (2 * k);
+            dense_unpack(v.y, df, dd);
+            tf += df; td += dd;
+            if (df != 0) mf |= 2u << (2 * k);
+            if (dd != 0) md |= 2u << (2 * k);
+        }
+        if (base == 0) { mf |= 1u; md |= 1u; }
+        long long tile_tot, tile_cnt;
+        const long long ex_tot = block_excl_sum<long long>(((long long)tf << 32) + (long long)td, s_scan64, tile_tot);
+        const long long ex_cnt = block_excl_sum<long long>(((long long)__popc(mf) << 31) | (long long)__popc(md),
+                                                           s_scan64, tile_cnt);
+        if (t < 32) {
+            unsigned long long ex = lookback_excl_warp(st_tot, tile, (unsigned long long)tile_tot & LB_MASK);
+            if (t == 0) s_base[0] = ex;
+        } else if (t < 64) {
+            unsigned long long b = lookback_excl_warp(st_cnt, tile, (unsigned long long)tile_cnt);
+            if (t == 32) {
+                s_base[1] = b;
+                if (tile == n_tiles - 1) {
+                    const unsigned long long tot = b + (unsigned long long)tile_cnt;
+                    out_counts[0] = tot >> 31;
+                    out_counts[1] = tot & 0x7fffffffull;
+                }
+            }
+        }
+        __syncthreads();
+        if (mf | md) {
+            int run_f, run_d;
+            {
+                const long long v = ((long long)(s_base[0] << 2) >> 2) + ex_tot;
+                run_d = (int)(unsigned)(v & 0xffffffffll);
+                run_f = (int)((v - (long long)run_d) >> 32);
+            }
+            const unsigned long long w_pk = s_base[1] + (unsigned long long)ex_cnt;
+            unsigned long long w0 = w_pk >> 31, w1 = w_pk & 0x7fffffffull;
+#pragma unroll
+            for (int k = 0; k < DP_ITEMS; ++k) {
+                int df, dd;
+                dense_unpack(*reinterpret_cast<const unsigned long long*>(row + k * 8), df, dd);
+                run_f += df;
+                run_d += dd;
+                if ((mf >> k) & 1u) {
+                    if (w0 < cap) { frag_idx[w0] = base + k; frag_val[w0] = run_f; }
+                    ++w0;
+                }
+                if ((md >> k) & 1u) {
+                    if (w1 < cap) { dir_idx[w1] = base + k; dir_val[w1] = run_d; }
+                    ++w1;
+                }
+            }
+        }
+        // the stage is free once every thread has read its row for the last time
+        __syncthreads();
+        if (t == 0) {
+            const unsigned next = tile + DP_STAGES * gridDim.x;
+            if (next < n_tiles) {
+                mbar_arrive_expect_tx(&s_bar[s], DP_STAGE_BYTES);
+                bulk_load(dp_smem + s * DP_STAGE_BYTES, dense + (size_t)next * DP_TILE, DP_STAGE_BYTES, &s_bar[s]);
+            }
+        }
+    }
+}
+
 // ---- duplicate filter (hash set keyed by start position) --------------------
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
@@ -1425,7 +1602,8 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
     DenseWorkspace* ws = nullptr;
     Scratch fallback, sc;
     unsigned long long* dense = nullptr;
-    GPC_TRY(dense_acquire(n_pos, stream, &ws, fallback, &dense));
+    // (whole 4096-position tiles: the bulk-copy variant of the scan loads full rows)
+    GPC_TRY(dense_acquire(((size_t)n_pos + 4095) & ~(size_t)4095, stream, &ws, fallback, &dense));
     struct Release {           // every way out gives the array back; only a finished scan leaves it clean
         DenseWorkspace* ws; cudaStream_t s; bool clean;
         ~Release() { dense_release(ws, clean, s); }
@@ -1464,7 +1642,28 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
                 touched, err, spill.pool);
         GPC_LAUNCH_CHECK();
         GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
-        if (variant == 2) {
+        if (variant == 3) {
+            static bool configured3 = false;
+            if (!configured3) {
+                GPC_CUDA(cudaFuncSetAttribute(dense_runs_pipelined_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM));
+                configured3 = true;
+            }
+            static int per_sm = 0;
+            if (!per_sm)
+                GPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dense_runs_pipelined_kernel,
+                                                                       DR_THREADS, DP_SMEM));
+            if (per_sm < 1) { set_error("dense_runs_pipelined does not fit an SM"); return GPC_ERR_INTERNAL; }
+            unsigned blocks = min(tiles, (unsigned)(sm_count() * per_sm));
+            unsigned n_tiles_arg = tiles;
+            unsigned long long cap_arg = capacity;
+            void* args[] = {&dense, &n_tiles_arg, &frag_idx, &frag_val, &direct_idx, &direct_val, &cap_arg,
+                            &st_tot, &st_cnt, &counts};
+            // cooperative: refused unless every block of the grid is resident (the look-back
+            // of a tile may wait on any block of its wave)
+            GPC_CUDA(cudaLaunchCooperativeKernel((void*)dense_runs_pipelined_kernel, dim3(blocks),
+                                                 dim3(DR_THREADS), args, DP_SMEM, stream));
+        } else if (variant == 2) {
             const unsigned blocks = min(div_up(tiles, DR_WARPS), (unsigned)(sm_count() * 5));
             dense_runs_kernel<<<blocks, DR_THREADS, 0, stream>>>(dense, n_pos, tiles, frag_idx, frag_val,
                                                                  direct_idx, direct_val, capacity, st_tot,

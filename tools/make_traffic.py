@@ -11,7 +11,7 @@ launches).  ncu serialises launches and its times are cold-cache, so only the
 SHARE is comparable with the live CUDA-event numbers."""
 import collections, csv, json, re, sys
 
-ALIAS = {"pv_eval": "pvalues"}
+ALIAS = {"pv_eval": "pvalues", "dense_runs_block": "dense_runs", "dense_runs_pipelined": "dense_runs"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0,
         "usecond": 1e-3, "nsecond": 1e-6, "msecond": 1.0, "second": 1e3}
 
