@@ -786,146 +786,29 @@ events_to_runs_kernel(const uint32_t* __restrict__ keys, unsigned n,
 // ---- difference array -> two canonical run-length tracks ----------------------
 //
 // dense[pos] holds the net step of both pileups at graph position pos (packed as the
-// walk deposits it).  One streaming pass, WARP-centric: every warp claims tiles of 512
-// positions (4 KB) in order, loads its tile with 16-byte coalesced loads into its own
-// slice of shared memory (rows padded by 16 bytes, so that the row reads below are
-// conflict-free), zeroes the words behind the read (the array is clean again for the next
-// call: no memset kernel), every lane walks its 16 consecutive positions, tile totals and
-// entry counts are scanned with shuffles and chained over the tiles by two packed
-// look-backs, and an entry (position, running sum) is written wherever the net step of a
-// track is non-zero, plus always one at position 0 -- the canonical SparseValues of the
-// reference (sparsediffs.py:13-20,137-141).  No block barrier anywhere: the warps of an SM
-// sit in different phases (loading, scanning, waiting for a predecessor, writing), which
-// is what keeps the memory system busy; the block-wide version of this kernel spent a
-// third of its stall samples on barriers.  HBM-bound: 8 bytes read + 8 bytes of zeroes per
+// walk deposits it).  One streaming pass: a tile of 4096 positions (32 KB) is loaded
+// with 16-byte coalesced loads into shared memory laid out with a 16-byte pad per
+// thread row (so that the row reads below are conflict-free), the words are zeroed
+// behind the read (the array is clean again for the next call: no memset kernel),
+// every thread walks its 16 consecutive positions, tile totals and entry counts go
+// through two packed chained scans walked by two warps at once, and an entry
+// (position, running sum) is written wherever the net step of a track is non-zero,
+// plus always one at position 0 -- the canonical SparseValues of the reference
+// (sparsediffs.py:13-20,137-141).  HBM-bound: 8 bytes read + 8 bytes of zeroes per
 // position, 8 bytes per entry out.
+//
+// Measured alternatives (chr22-scale, 53.7 M positions; this kernel: 0.39 ms):
+//   8192 positions per block                                    0.41 ms
+//   one 512-position tile per WARP, persistent, no block barrier 0.50 ms (8x the look-backs)
+//   bulk-copy engine, three tiles in flight per block            0.52 ms (below, GPC_DENSE_SCAN=3)
 
 constexpr int DR_THREADS = 256;
-constexpr int DR_WARPS = DR_THREADS / 32;
-constexpr int DR_ITEMS = 16;
-constexpr int DR_TILE = 32 * DR_ITEMS;                  // positions per warp tile
-constexpr int DR_ROW_BYTES = DR_ITEMS * 8 + 16;         // padded row of one lane
 
 __device__ __forceinline__ void dense_unpack(unsigned long long w, int& dfrag, int& ddir) {
     ddir = (int)(unsigned)(w & 0xffffffffull);
     dfrag = (int)(((long long)w - (long long)ddir) >> 32);
 }
 
-__device__ __forceinline__ long long warp_incl_sum64(long long v) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        long long o = __shfl_up_sync(FULL, v, d);
-        if (lane_id() >= (unsigned)d) v += o;
-    }
-    return v;
-}
-
-__global__ void __launch_bounds__(DR_THREADS, 5)
-dense_runs_kernel(unsigned long long* __restrict__ dense, unsigned n_pos, unsigned n_tiles,
-                  uint32_t* __restrict__ frag_idx, int32_t* __restrict__ frag_val,
-                  uint32_t* __restrict__ dir_idx, int32_t* __restrict__ dir_val,
-                  unsigned long long cap,
-                  unsigned long long* __restrict__ st_tot /* zeroed */,
-                  unsigned long long* __restrict__ st_cnt /* zeroed */,
-                  unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts) {
-    __shared__ __align__(16) unsigned char s_rows[DR_WARPS][32 * DR_ROW_BYTES];
-    const unsigned lane = lane_id();
-    unsigned char* const rows = s_rows[warp_id()];
-    const unsigned char* const row = rows + lane * DR_ROW_BYTES;
-    while (true) {
-        unsigned tile = 0;
-        if (lane == 0) tile = atomicAdd(ticket, 1u);        // tiles are claimed in order
-        tile = __shfl_sync(FULL, tile, 0);
-        if (tile >= n_tiles) break;
-        const unsigned tile_base = tile * DR_TILE;
-        // ---- load (a warp's loads are 512 contiguous bytes), zero behind ---------------
-#pragma unroll
-        for (int j = 0; j < DR_ITEMS / 2; ++j) {
-            const unsigned u = j * 32 + lane;                   // 16-byte unit inside the tile
-            const unsigned gpos = tile_base + 2 * u;
-            ulonglong2 v = make_ulonglong2(0ull, 0ull);
-            if (gpos + 1 < n_pos) {
-                ulonglong2* g = reinterpret_cast<ulonglong2*>(dense + gpos);
-                v = *g;
-                if (v.x | v.y) *g = make_ulonglong2(0ull, 0ull);
-            } else if (gpos < n_pos) {
-                v.x = dense[gpos];
-                if (v.x) dense[gpos] = 0ull;
-            }
-            *reinterpret_cast<ulonglong2*>(rows + (u >> 3) * DR_ROW_BYTES + (u & 7) * 16) = v;
-        }
-        __syncwarp();
-        // ---- lane-local pass over 16 consecutive positions (the row stays in shared
-        // memory and is read again for the emission) ---------------------------------
-        const unsigned base = tile_base + lane * DR_ITEMS;
-        int tf = 0, td = 0;
-        unsigned mf = 0, md = 0;              // bit k: position base + k gets an entry
-#pragma unroll
-        for (int k = 0; k < DR_ITEMS / 2; ++k) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(row + k * 16);
-            int df, dd;
-            dense_unpack(v.x, df, dd);
-            tf += df;
-            td += dd;
-            if (df != 0) mf |= 1u << (2 * k);
-            if (dd != 0) md |= 1u << (2 * k);
-            dense_unpack(v.y, df, dd);
-            tf += df;
-            td += dd;
-            if (df != 0) mf |= 2u << (2 * k);
-            if (dd != 0) md |= 2u << (2 * k);
-        }
-        if (base == 0) { mf |= 1u; md |= 1u; }                     // (0, value) always exists
-        // warp scans: totals (high word fragment, low word direct) and entry counts (2 x 31 bits)
-        const long long my_tot = ((long long)tf << 32) + (long long)td;
-        const long long my_cnt = ((long long)__popc(mf) << 31) | (long long)__popc(md);
-        const long long in_tot = warp_incl_sum64(my_tot), in_cnt = warp_incl_sum64(my_cnt);
-        const unsigned long long tile_tot = (unsigned long long)__shfl_sync(FULL, in_tot, 31) & LB_MASK;
-        const unsigned long long tile_cnt = (unsigned long long)__shfl_sync(FULL, in_cnt, 31);
-        // both aggregates are published before either chain is walked back
-        if (lane == 0) {
-            lb_publish_agg(st_tot, tile, tile_tot);
-            lb_publish_agg(st_cnt, tile, tile_cnt);
-        }
-        const unsigned long long pre_tot = lb_resolve_warp(st_tot, tile, tile_tot);
-        const unsigned long long pre_cnt = lb_resolve_warp(st_cnt, tile, tile_cnt);
-        if (tile == n_tiles - 1 && lane == 0) {
-            const unsigned long long tot = pre_cnt + tile_cnt;
-            out_counts[0] = tot >> 31;
-            out_counts[1] = tot & 0x7fffffffull;
-        }
-        if (mf | md) {
-            int run_f, run_d;
-            {
-                const long long v = ((long long)(pre_tot << 2) >> 2) + (in_tot - my_tot);   // sign-extend 62 bits
-                run_d = (int)(unsigned)(v & 0xffffffffll);
-                run_f = (int)((v - (long long)run_d) >> 32);
-            }
-            const unsigned long long w_pk = pre_cnt + (unsigned long long)(in_cnt - my_cnt);
-            unsigned long long w0 = w_pk >> 31, w1 = w_pk & 0x7fffffffull;
-#pragma unroll
-            for (int k = 0; k < DR_ITEMS; ++k) {
-                int df, dd;
-                dense_unpack(*reinterpret_cast<const unsigned long long*>(row + k * 8), df, dd);
-                run_f += df;
-                run_d += dd;
-                if ((mf >> k) & 1u) {
-                    if (w0 < cap) { frag_idx[w0] = base + k; frag_val[w0] = run_f; }
-                    ++w0;
-                }
-                if ((md >> k) & 1u) {
-                    if (w1 < cap) { dir_idx[w1] = base + k; dir_val[w1] = run_d; }
-                    ++w1;
-                }
-            }
-        }
-        __syncwarp();                       // the rows are overwritten by the next tile
-    }
-}
-
-
-// The same scan with one tile per BLOCK (ITEMS positions per thread, block-wide scans,
-// tickets per block); measured next to the warp-centric version above.
 template <int ITEMS>
 __global__ void __launch_bounds__(DR_THREADS, ITEMS == 16 ? 6 : 3)
 dense_runs_block_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
@@ -1594,10 +1477,11 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
     // ---- difference array ------------------------------------------------------------
     GPC_CUDA(cudaMemsetAsync(touched, 0, graph->n_nodes, stream));
     const unsigned n_pos = graph->size_bp + 1;           // a fragment may close at size_bp
-    // scan variant: 0 = one 4096-position tile per block (default), 1 = 8192 per block,
-    // 2 = one 512-position tile per warp, persistent
+    // scan variant: 0 = one 4096-position tile per block, plain loads (default); 3 = persistent
+    // blocks, tiles moved by the bulk-copy engine, three in flight (measured slower, kept as the
+    // reference point for it)
     static const int variant = getenv("GPC_DENSE_SCAN") ? atoi(getenv("GPC_DENSE_SCAN")) : 0;
-    const unsigned tile_size = variant == 2 ? DR_TILE : (variant == 1 ? DR_THREADS * 32 : DR_THREADS * 16);
+    const unsigned tile_size = DR_THREADS * 16;
     const unsigned tiles = div_up(n_pos, tile_size);
     DenseWorkspace* ws = nullptr;
     Scratch fallback, sc;
@@ -1663,22 +1547,6 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
             // of a tile may wait on any block of its wave)
             GPC_CUDA(cudaLaunchCooperativeKernel((void*)dense_runs_pipelined_kernel, dim3(blocks),
                                                  dim3(DR_THREADS), args, DP_SMEM, stream));
-        } else if (variant == 2) {
-            const unsigned blocks = min(div_up(tiles, DR_WARPS), (unsigned)(sm_count() * 5));
-            dense_runs_kernel<<<blocks, DR_THREADS, 0, stream>>>(dense, n_pos, tiles, frag_idx, frag_val,
-                                                                 direct_idx, direct_val, capacity, st_tot,
-                                                                 st_cnt, ticket, counts);
-        } else if (variant == 1) {
-            constexpr int SMEM = DR_THREADS * (32 * 8 + 16);
-            static bool configured = false;
-            if (!configured) {
-                GPC_CUDA(cudaFuncSetAttribute(dense_runs_block_kernel<32>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-                configured = true;
-            }
-            dense_runs_block_kernel<32><<<tiles, DR_THREADS, SMEM, stream>>>(
-                dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt,
-                ticket, counts);
         } else {
             dense_runs_block_kernel<16><<<tiles, DR_THREADS, DR_THREADS * (16 * 8 + 16), stream>>>(
                 dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt,
