@@ -81,6 +81,7 @@ _SIGNATURES = {
     "gpc_most_covered_path_host": [c_void_p, c_void_p, c_void_p, c_void_p, u64, c_void_p, P(u64)],
     "gpc_linear_map_from_graph_host": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        u64, c_void_p, c_void_p],
+    "gpc_linear_map_from_graph": [P(GpcGraph), c_void_p, c_void_p, P(u64), c_void_p],
     "gpc_sort_u32": [c_void_p, c_void_p, u64, i32, i32, P(i32), c_void_p],
     "gpc_sort_u64_pairs": [c_void_p, c_void_p, c_void_p, c_void_p, u64, i32, i32,
                            P(i32), c_void_p],

@@ -4,8 +4,9 @@ from the graph source to the node start, and the linear length minus the
 longest distance from the node end to the sink.
 
 ``from_graph`` is the one-off preprocessing step that writes
-``*_linear_map.npz``; it is a sequential
-longest-path sweep and runs natively on the host.  The projection and back-projection that use the map are kernels
+``*_linear_map.npz``: a longest-path recurrence, run as kernels
+(gpc_linear_map_from_graph) when a device is present and as a native sequential sweep on
+hosts without one.  The projection and back-projection that use the map are kernels
 (gpc_control_linear_track / gpc_control_backproject)."""
 import numpy as np
 
@@ -43,9 +44,35 @@ class LinearMap:
 
     @classmethod
     def from_graph(cls, graph):
-        """Longest-path sweeps over the CSR in id (= topological) order; a
-        plain sequential loop, done natively on the host
-        (gpc_linear_map_from_graph_host) -- preprocessing, not the measured path."""
+        """Longest distance from the source to every node start / from every node end to
+        the sink (linearmap.py:102-154).  With a CUDA device: ``gpc_linear_map_from_graph``
+        -- the recurrence cut at the nodes no edge jumps over, one thread per segment, a
+        scan of max-plus functions across segments (csrc/linearmap.cu).  On a host without
+        a device (the reference runs this step once and caches ``*_linear_map.npz``) the
+        library's sequential sweep ``from_graph_host`` does it; both are bit-identical."""
+        from ..device import cuda_available
+        if not cuda_available():
+            return cls.from_graph_host(graph)
+        import ctypes
+        from .. import _lib
+        from ..device import device_graph, empty, ptr, stream_ptr, torch_cuda
+        torch = torch_cuda()
+        g = Graph.from_obg(graph)
+        g.require_ordered("LinearMap.from_graph")
+        dg = device_graph(g)
+        starts, ends = empty(g.n_nodes, torch.float64), empty(g.n_nodes, torch.float64)
+        barriers = ctypes.c_uint64(0)
+        _lib.check(_lib.load().gpc_linear_map_from_graph(
+            ctypes.byref(dg.c), ptr(starts), ptr(ends), ctypes.byref(barriers), stream_ptr()))
+        both = torch.stack((starts, ends)).cpu().numpy()
+        lm = cls(both[0], both[1], graph)
+        lm.n_barriers = int(barriers.value)
+        return lm
+
+    @classmethod
+    def from_graph_host(cls, graph):
+        """The same as a plain sequential sweep over the CSR in id (= topological) order,
+        natively on the host (gpc_linear_map_from_graph_host)."""
         import ctypes
         from .. import _lib
         g = Graph.from_obg(graph)

@@ -728,12 +728,18 @@ extern "C" int gpc_control_linear_track(const gpc_graph_t* graph, const int32_t*
         return herr;
     }
     const unsigned U = (unsigned)hU;
-    // integer coordinates (no node with a non-integer scale was hit): dense path
-    if (!not_integer && !getenv("GPC_FORCE_MERGE_PATH")) {
-        long long e_max = 0;
-        for (int w = 0; w < n_extensions; ++w) e_max = (long long)wp.half[w] > e_max ? (long long)wp.half[w] : e_max;
-        const long long origin = -e_max;
-        const long long span = (long long)x_last + 2 * e_max + 1;
+    // integer coordinates (no node with a non-integer scale was hit): dense path -- when the
+    // reads are dense enough.  It works per linear POSITION (7 ps each, measured), the tile
+    // path below per EVENT (55 ps each): below ~0.12 events per position -- whole-genome
+    // depth, 0.075 on the human workload -- the event-driven tiles are the faster ones.
+    long long e_max = 0;
+    for (int w = 0; w < n_extensions; ++w) e_max = (long long)wp.half[w] > e_max ? (long long)wp.half[w] : e_max;
+    const long long origin = -e_max;
+    const long long span = (long long)x_last + 2 * e_max + 1;
+    double dense_min = 0.12;
+    if (const char* e = getenv("GPC_LINEAR_DENSE_MIN")) dense_min = atof(e);
+    const bool dense_enough = (double)nq * (double)U >= dense_min * (double)span;
+    if (!not_integer && dense_enough && !getenv("GPC_FORCE_MERGE_PATH")) {
         const unsigned n_dense = (unsigned)((span + DENSE_W - 1) / DENSE_W);
         Scratch dsc, dbounds, tbase, tcnt, toff, tpos, tval, ttotal;
         GPC_CUDA(dsc.alloc(64, stream));

@@ -719,51 +719,35 @@ struct PathOut {
     uint8_t* info;         // [n_comp] bit0 is_diff (two bindings), bit1 ambiguous
 };
 
-// One thread per component: literal replay of PosDividedLineGraph.max_paths.
-// When every edge of the component points to a later member (the vertex order
-// is topological -- always the case for graphs with ascending edges) one sweep
-// of each relaxation is exact and the confirming sweep is skipped.
-constexpr int MP_THREADS = 8;
-constexpr int MP_SMEM_V = 128;
+// Literal replay of PosDividedLineGraph.max_paths for ONE component, run by one thread
+// on whatever memory the view points at.  When every edge of the component points to a
+// later member (the vertex order is topological -- always the case for graphs with
+// ascending edges) one sweep of each relaxation is exact and the confirming sweep is
+// skipped.  Writes the path as local vertex indexes, BACKWARDS, into v.path; returns its
+// length, info = bit 0 is_diff (two bindings), bit 1 ambiguous.
+struct MpView {
+    const uint32_t* adj_ptr;   // [nv + 1] indexes into adj
+    const uint32_t* adj;       // targets; local index = adj[e] - v_base
+    uint32_t v_base;
+    const int32_t* weight;     // [nv]
+    const uint8_t* flags;      // [nv] bit 0 entry, bit 1 exit
+    long long* dist;           // [nv] working arrays
+    long long* dsink;
+    int32_t* pred;
+    uint32_t* path;            // [nv]
+};
 
-__global__ void max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ comp_ptr,
-                                 const unsigned long long* __restrict__ member_keys,
-                                 const uint32_t* __restrict__ adj_ptr,
-                                 const uint32_t* __restrict__ adj,
-                                 const int32_t* __restrict__ m_weight,
-                                 const uint8_t* __restrict__ m_flags,
-                                 const uint8_t* __restrict__ comp_backward,
-                                 long long* __restrict__ g_dist, long long* __restrict__ g_dsink,
-                                 int32_t* __restrict__ g_pred, PathOut out) {
-    // the replay is one dependent access after the other: components of up to
-    // MP_SMEM_V vertices keep their working arrays in shared memory (~30 cycles
-    // instead of an L2 round trip per access), larger ones use global memory
-    __shared__ long long s_dist[MP_THREADS][MP_SMEM_V];
-    __shared__ long long s_dsink[MP_THREADS][MP_SMEM_V];
-    __shared__ int32_t s_pred[MP_THREADS][MP_SMEM_V];
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_comp) return;
-    const uint32_t lo = comp_ptr[c], hi = comp_ptr[c + 1];
-    const int nv = (int)(hi - lo);           // vertices without the sink
-    const bool small = nv <= MP_SMEM_V;
-    long long* const dist = small ? &s_dist[threadIdx.x][0] : g_dist + lo;
-    long long* const dsink = small ? &s_dsink[threadIdx.x][0] : g_dsink + lo;
-    int32_t* const pred = small ? &s_pred[threadIdx.x][0] : g_pred + lo;
+__device__ __forceinline__ int mp_solve(const MpView& v, const int nv, const bool one_sweep, int& info_out) {
     const long long INF = (1ll << 60);
-    auto vertex_at = [&](int j) { return member_vertex(member_keys, lo + j); };
-    if (nv == 1) {                           // graphs.py:342-345
-        out.path[lo] = vertex_at(0);
-        out.path_len[c] = 1;
-        out.info[c] = 0;
-        return;
-    }
-    const bool one_sweep = comp_backward[(uint32_t)(member_keys[lo] >> 32)] == 0;
+    long long* const dist = v.dist;
+    long long* const dsink = v.dsink;
+    int32_t* const pred = v.pred;
     // Edge iteration of local vertex j in ascending target order (CSR order of
     // the reference's sliced matrix): piece targets sorted by vertex id, sink last.
     auto for_edges = [&](int j, auto&& fn) {
-        const uint32_t e0 = adj_ptr[lo + j], e1 = adj_ptr[lo + j + 1];
-        const bool to_sink = (m_flags[lo + j] & 2) != 0;
-        for (uint32_t e = e0; e < e1; ++e) fn((int)(adj[e] - lo));
+        const uint32_t e0 = v.adj_ptr[j], e1 = v.adj_ptr[j + 1];
+        const bool to_sink = (v.flags[j] & 2) != 0;
+        for (uint32_t e = e0; e < e1; ++e) fn((int)(v.adj[e] - v.v_base));
         if (to_sink) fn(nv);                 // sink = local index nv
     };
     // distance of every vertex to the sink (value only, order independent)
@@ -772,7 +756,7 @@ __global__ void max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ c
     while (changed) {
         changed = false;
         for (int j = nv - 1; j >= 0; --j) {
-            long long w = -(long long)m_weight[lo + j];
+            long long w = -(long long)v.weight[j];
             long long best = dsink[j];
             for_edges(j, [&](int tgt) {
                 long long d = tgt == nv ? 0 : dsink[tgt];
@@ -785,7 +769,7 @@ __global__ void max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ c
     // start = first entry vertex with minimal distance to the sink (np.argmin)
     int first = -1;
     for (int j = 0; j < nv; ++j)
-        if ((m_flags[lo + j] & 1) && (first < 0 || dsink[j] < dsink[first])) first = j;
+        if ((v.flags[j] & 1) && (first < 0 || dsink[j] < dsink[first])) first = j;
     if (first < 0) first = 0;
     // Bellman-Ford from `first`, scipy sweep order, first strict improvement wins
     long long dist_sink = INF;
@@ -797,7 +781,7 @@ __global__ void max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ c
         for (int j = 0; j < nv; ++j) {
             long long d1 = dist[j];
             if (d1 >= INF) continue;
-            long long w = -(long long)m_weight[lo + j];
+            long long w = -(long long)v.weight[j];
             for_edges(j, [&](int tgt) {
                 if (tgt == nv) {
                     if (d1 + w < dist_sink) { dist_sink = d1 + w; pred_sink = j; any = true; }
@@ -814,16 +798,16 @@ __global__ void max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ c
     int len = 0;
     int cur = pred_sink;
     while (cur > 0) {
-        out.path[lo + len++] = (uint32_t)cur;     // local ids for now, backwards
+        v.path[len++] = (uint32_t)cur;       // local ids, backwards
         cur = pred[cur];
     }
-    if (len == 0 || (int)out.path[lo + len - 1] != first) out.path[lo + len++] = (uint32_t)first;
+    if (len == 0 || (int)v.path[len - 1] != first) v.path[len++] = (uint32_t)first;
     // SubGraphAnalyzer (subgraphanalyzer.py:11-39) on the forward path
     long long score = 0;                          // dists[sink, sink] == 0 takes part in the min
     long long wsum = 0;
     for (int j = 0; j < nv; ++j) {
         if (dsink[j] < score) score = dsink[j];
-        wsum += (long long)m_weight[lo + j];
+        wsum += (long long)v.weight[j];
     }
     int info = 0;
     if (len > 1) {
@@ -832,12 +816,12 @@ __global__ void max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ c
         // its job): a scan of the path per edge made peaks of a few hundred pieces -- dense
         // variation -- quadratic
         for (int j = 0; j < nv; ++j) pred[j] = 0;
-        for (int z = 0; z < len; ++z) pred[(int)out.path[lo + z]] = 1;
+        for (int z = 0; z < len; ++z) pred[(int)v.path[z]] = 1;
         bool amb = false;
         for (int q = len - 1; q >= 1 && !amb; --q) {      // path[:-1] in forward order
-            int node = (int)out.path[lo + q];
+            int node = (int)v.path[q];
             long long reach = dist[node];
-            long long w = -(long long)m_weight[lo + node];
+            long long w = -(long long)v.weight[node];
             for_edges(node, [&](int tgt) {
                 if (amb) return;
                 if (tgt != nv && pred[tgt]) return;
@@ -847,15 +831,105 @@ __global__ void max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ c
         }
         if (amb) info |= 2;
     }
-    // reverse into forward order and translate to vertex ids
-    for (int a = 0, b = len - 1; a < b; ++a, --b) {
-        uint32_t t = out.path[lo + a];
-        out.path[lo + a] = out.path[lo + b];
-        out.path[lo + b] = t;
+    info_out = info;
+    return len;
+}
+
+// One WARP per component.  The replay itself is one dependent access after the other and
+// runs on lane 0; what the other lanes are for is the memory around it: they stage the
+// component's adjacency, weights and flags in shared memory (coalesced), the working
+// arrays live there too (~30 cycles per dependent access instead of an L2 round trip),
+// and they write the path out in forward order.  Components come in size classes (one
+// launch each over all components, a warp whose component belongs to another class
+// leaves at once) so that the shared memory of a block fits the components it holds:
+//   class 1: <= 64 vertices, 2: <= 256, 3: <= 1024 (edges <= 3 per vertex each),
+//   class 0: everything larger, working arrays in global memory.
+// (One THREAD per component, eight to a block, was the first version: the threads of a
+// warp diverge on everything, so a warp took the time of its eight components one after
+// the other -- 9.3 of 26.5 ms on the dense-variation workload, where a peak has a few
+// hundred pieces.)
+constexpr int MPW_WARPS = 4;
+__host__ __device__ constexpr int mp_class_cap(int cls) { return cls == 1 ? 64 : (cls == 2 ? 256 : 1024); }
+__host__ __device__ constexpr size_t mp_warp_smem(int capv) {
+    // dist, dsink (8 each), pred, path, weight, adj_ptr (4 each), adj (3 x 4), flags (1) per vertex
+    return (size_t)capv * (8 + 8 + 4 + 4 + 4 + 4 + 12 + 1) + 32;
+}
+__device__ __forceinline__ int mp_class(uint32_t nv, uint32_t ne) {
+    for (int cls = 1; cls <= 3; ++cls)
+        if (nv <= (uint32_t)mp_class_cap(cls) && ne <= 3u * mp_class_cap(cls)) return cls;
+    return 0;
+}
+
+template <int CLS>
+__global__ void __launch_bounds__(MPW_WARPS * 32)
+max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ comp_ptr,
+                 const unsigned long long* __restrict__ member_keys,
+                 const uint32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
+                 const int32_t* __restrict__ m_weight, const uint8_t* __restrict__ m_flags,
+                 const uint8_t* __restrict__ comp_backward,
+                 long long* g_dist, long long* g_dsink, int32_t* g_pred, PathOut out) {
+    extern __shared__ __align__(16) unsigned char s_mp[];
+    const unsigned lane = lane_id();
+    const uint32_t c = blockIdx.x * MPW_WARPS + warp_id();
+    if (c >= n_comp) return;
+    const uint32_t lo = comp_ptr[c], hi = comp_ptr[c + 1];
+    const int nv = (int)(hi - lo);           // vertices without the sink
+    const uint32_t e_lo = adj_ptr[lo], ne = adj_ptr[hi] - e_lo;
+    if (mp_class((uint32_t)nv, ne) != CLS) return;
+    if (nv == 1) {                           // graphs.py:342-345
+        if (lane == 0) {
+            out.path[lo] = member_vertex(member_keys, lo);
+            out.path_len[c] = 1;
+            out.info[c] = 0;
+        }
+        return;
     }
-    for (int a = 0; a < len; ++a) out.path[lo + a] = vertex_at((int)out.path[lo + a]);
-    out.path_len[c] = (uint32_t)len;
-    out.info[c] = (uint8_t)info;
+    const bool one_sweep = comp_backward[(uint32_t)(member_keys[lo] >> 32)] == 0;
+    MpView v;
+    if (CLS != 0) {
+        constexpr int CAP = mp_class_cap(CLS == 0 ? 1 : CLS);
+        unsigned char* base = s_mp + (size_t)warp_id() * mp_warp_smem(CAP);
+        long long* s_dist = reinterpret_cast<long long*>(base);
+        long long* s_dsink = s_dist + CAP;
+        int32_t* s_pred = reinterpret_cast<int32_t*>(s_dsink + CAP);
+        uint32_t* s_path = reinterpret_cast<uint32_t*>(s_pred + CAP);
+        int32_t* s_w = reinterpret_cast<int32_t*>(s_path + CAP);
+        uint32_t* s_adjptr = reinterpret_cast<uint32_t*>(s_w + CAP);      // CAP + 1 used
+        uint32_t* s_adj = s_adjptr + CAP + 4;
+        uint8_t* s_flags = reinterpret_cast<uint8_t*>(s_adj + 3 * CAP);
+        for (int j = lane; j < nv; j += 32) {
+            s_w[j] = m_weight[lo + j];
+            s_flags[j] = m_flags[lo + j];
+        }
+        for (int j = lane; j <= nv; j += 32) s_adjptr[j] = adj_ptr[lo + j] - e_lo;
+        for (uint32_t e = lane; e < ne; e += 32) s_adj[e] = adj[e_lo + e] - lo;
+        v = MpView{s_adjptr, s_adj, 0u, s_w, s_flags, s_dist, s_dsink, s_pred, s_path};
+    } else {
+        v = MpView{adj_ptr + lo, adj, lo, m_weight + lo, m_flags + lo, g_dist + lo, g_dsink + lo,
+                   g_pred + lo, out.path + lo};
+    }
+    __syncwarp();
+    int len = 0, info = 0;
+    if (lane == 0) len = mp_solve(v, nv, one_sweep, info);
+    __syncwarp();
+    len = __shfl_sync(FULL, len, 0);
+    // forward order, vertex ids
+    if (CLS != 0) {
+        for (int a = lane; a < len; a += 32)
+            out.path[lo + a] = member_vertex(member_keys, lo + v.path[len - 1 - a]);
+    } else {
+        for (int a = lane; a < len / 2; a += 32) {
+            const uint32_t t = v.path[a];
+            v.path[a] = v.path[len - 1 - a];
+            v.path[len - 1 - a] = t;
+        }
+        __syncwarp();
+        for (int a = lane; a < len; a += 32) v.path[a] = member_vertex(member_keys, lo + v.path[a]);
+    }
+    if (lane == 0) {
+        out.path_len[c] = (uint32_t)len;
+        out.info[c] = (uint8_t)info;
+    }
 }
 
 // peaks: component paths first (component order), then internal pieces
@@ -1369,13 +1443,28 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
                                      adj.as<uint32_t>(), m_weight.as<int32_t>(),
                                      m_flags.as<uint8_t>(), comp_backward.as<uint8_t>());
         GPC_LAUNCH_CHECK();
-        GPC_PROF("max_paths");
-        max_paths_kernel<<<div_up(n_comp, MP_THREADS), MP_THREADS, 0, stream>>>(
-            (uint32_t)n_comp, comp_ptr.as<uint32_t>(), mk, adj_ptr.as<uint32_t>(),
-            adj.as<uint32_t>(), m_weight.as<int32_t>(), m_flags.as<uint8_t>(),
-            comp_backward.as<uint8_t>(), dist.as<long long>(), dsink.as<long long>(),
-            pred.as<int32_t>(), po);
-        GPC_LAUNCH_CHECK();
+        // one launch per size class (see max_paths_kernel); the largest class needs the
+        // opt-in to more than 48 KB of dynamic shared memory per block
+        const unsigned mp_blocks = div_up(n_comp, MPW_WARPS);
+#define GPC_MP_LAUNCH(CLS, NAME)                                                                       \
+        do {                                                                                           \
+            const size_t smem__ = (CLS) == 0 ? 0 : MPW_WARPS * mp_warp_smem(mp_class_cap(CLS));        \
+            if (smem__ > 48 * 1024)                                                                    \
+                GPC_CUDA(cudaFuncSetAttribute(max_paths_kernel<CLS>,                                   \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem__)); \
+            GPC_PROF(NAME);                                                                            \
+            max_paths_kernel<CLS><<<mp_blocks, MPW_WARPS * 32, smem__, stream>>>(                      \
+                (uint32_t)n_comp, comp_ptr.as<uint32_t>(), mk, adj_ptr.as<uint32_t>(),                 \
+                adj.as<uint32_t>(), m_weight.as<int32_t>(), m_flags.as<uint8_t>(),                     \
+                comp_backward.as<uint8_t>(), dist.as<long long>(), dsink.as<long long>(),              \
+                pred.as<int32_t>(), po);                                                               \
+            GPC_LAUNCH_CHECK();                                                                        \
+        } while (0)
+        GPC_MP_LAUNCH(1, "max_paths");
+        GPC_MP_LAUNCH(2, "max_paths_256");
+        GPC_MP_LAUNCH(3, "max_paths_1024");
+        GPC_MP_LAUNCH(0, "max_paths_large");
+#undef GPC_MP_LAUNCH
     }
     const uint32_t n_pk = (uint32_t)n_comp + (uint32_t)n_i;
     *n_peaks = n_pk;

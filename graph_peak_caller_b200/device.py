@@ -34,6 +34,16 @@ def torch_cuda():
     return _torch
 
 
+def cuda_available():
+    """True when a CUDA device is visible.  Only ``LinearMap.from_graph`` asks -- the
+    preprocessing step that also exists as a host sweep for machines without a device;
+    nothing on the callpeaks path itself has a host form."""
+    if _torch is not None:
+        return True
+    import torch
+    return bool(torch.cuda.is_available())
+
+
 _devices = {}
 
 

@@ -432,6 +432,16 @@ int gpc_linear_map_from_graph_host(const int64_t* node_len, const int64_t* succ_
                                    const int32_t* pred, uint64_t n_nodes, double* starts,
                                    double* ends);
 
+/* The same on the DEVICE (graph in HBM as for every other stage; starts / ends: n_nodes
+ * float64 each, device pointers; *n_barriers (host, may be NULL): number of nodes no edge
+ * jumps over).  The recurrence is cut at those barrier nodes: one thread per segment
+ * between two barriers solves it locally, a scan of x -> max(x + a, b) functions over the
+ * segments carries it across (csrc/linearmap.cu).  Integer arithmetic, bit-identical to
+ * the host sweep and to the reference's float64 sums.  Graphs whose ids do not ascend
+ * along every edge are GPC_ERR_ARG. */
+int gpc_linear_map_from_graph(const gpc_graph_t* graph, double* starts, double* ends,
+                              uint64_t* n_barriers, void* stream);
+
 /* ---- building blocks (np.argsort / np.cumsum of the reference's
  *      sparsediffs.py, exported for the host side and the parity tests) ------
  * LSD radix sorts over bits [begin_bit, end_bit); keys/vals ping-pong with

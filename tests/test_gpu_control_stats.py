@@ -159,6 +159,7 @@ def test_dense_and_merge_paths_of_the_linear_track_agree(monkeypatch):
     c = make_reads(g, 40000, 36, 200, seed=72, peak_frac=0.3, peak_spacing=20000, dup_frac=0.1)
     dg, dc = DeviceGraph(g, lm), DeviceReads(c)
     out = {}
+    monkeypatch.setenv("GPC_LINEAR_DENSE_MIN", "0")       # the dense path whatever the read density
     for mode in ("dense", "merge"):
         if mode == "merge":
             monkeypatch.setenv("GPC_FORCE_MERGE_PATH", "1")
