@@ -19,6 +19,8 @@
 // number of relaxation rounds over the few vertices of small components.
 // Max paths replay scipy's Bellman-Ford sweep order per component (one thread
 // per component) so that ties break exactly as in the reference.
+#include <vector>
+
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
@@ -1443,6 +1445,28 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
                                      adj.as<uint32_t>(), m_weight.as<int32_t>(),
                                      m_flags.as<uint8_t>(), comp_backward.as<uint8_t>());
         GPC_LAUNCH_CHECK();
+        if (getenv("GPC_MP_STATS")) {          // debugging aid: component sizes to stderr
+            std::vector<uint32_t> cp((size_t)n_comp + 1);
+            std::vector<uint8_t> cb(V);
+            std::vector<unsigned long long> hk(V);
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(cp.data(), comp_ptr.p, ((size_t)n_comp + 1) * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(cb.data(), comp_backward.p, V, cudaMemcpyDeviceToHost);
+            cudaMemcpy(hk.data(), mk, (size_t)V * 8, cudaMemcpyDeviceToHost);
+            unsigned long long hist[6] = {0, 0, 0, 0, 0, 0}, verts[6] = {0, 0, 0, 0, 0, 0}, back = 0, biggest = 0;
+            for (unsigned long long c = 0; c < n_comp; ++c) {
+                const unsigned nv = cp[c + 1] - cp[c];
+                const int b = nv <= 1 ? 0 : nv <= 64 ? 1 : nv <= 256 ? 2 : nv <= 1024 ? 3 : nv <= 4096 ? 4 : 5;
+                hist[b]++; verts[b] += nv;
+                if (nv > biggest) biggest = nv;
+                if (cb[(uint32_t)(hk[cp[c]] >> 32)]) back++;
+            }
+            fprintf(stderr, "max_paths: %llu components, %llu vertices, %llu with backward edges, largest %llu\n",
+                    (unsigned long long)n_comp, (unsigned long long)V, back, biggest);
+            const char* names[6] = {"1", "<=64", "<=256", "<=1024", "<=4096", ">4096"};
+            for (int b = 0; b < 6; ++b)
+                fprintf(stderr, "  %-7s %8llu components %10llu vertices\n", names[b], hist[b], verts[b]);
+        }
         // one launch per size class (see max_paths_kernel); the largest class needs the
         // opt-in to more than 48 KB of dynamic shared memory per block
         const unsigned mp_blocks = div_up(n_comp, MPW_WARPS);

@@ -906,6 +906,148 @@ dense_runs_block_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
 }
 
 
+// ---- the same scan with the entries staged through shared memory -------------------------
+//
+// In the kernel above every thread writes its own entries straight to global memory: at
+// every one of its 16 steps a warp issues four stores (position and value of two tracks)
+// with ~15 % of the lanes active, each lane at its own offset -- ~2500 partial-sector
+// writes per tile for 300 sectors' worth of entries, more L2 transactions than the tile's
+// own 32 KB in and 32 KB of zeroes out.  Here the entries of a tile go to a staging area in
+// shared memory first (at the block-wide rank the count scan already provides: 16-bit
+// position in the tile + 32-bit value), and the block then copies them out with fully
+// coalesced stores.  A tile with more than DS_CAP entries in a track (> 31 % of its
+// positions) writes the overflow directly, as above.
+constexpr int DS_CAP = 1280;
+
+__global__ void __launch_bounds__(DR_THREADS, 4)
+dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
+                         uint32_t* __restrict__ frag_idx, int32_t* __restrict__ frag_val,
+                         uint32_t* __restrict__ dir_idx, int32_t* __restrict__ dir_val,
+                         unsigned long long cap,
+                         unsigned long long* __restrict__ st_tot /* zeroed */,
+                         unsigned long long* __restrict__ st_cnt /* zeroed */,
+                         unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts) {
+    constexpr int ITEMS = 16;
+    constexpr int TILE = DR_THREADS * ITEMS;
+    constexpr int ROW = ITEMS * 8 + 16;
+    extern __shared__ __align__(16) unsigned char s_rows[];      // DR_THREADS * ROW, then the staging area
+    int32_t* const s_val = reinterpret_cast<int32_t*>(s_rows + DR_THREADS * ROW);     // [2][DS_CAP]
+    uint16_t* const s_pos = reinterpret_cast<uint16_t*>(s_val + 2 * DS_CAP);          // [2][DS_CAP]
+    __shared__ long long s_scan64[33];
+    __shared__ unsigned s_slot;
+    __shared__ unsigned long long s_base[2];
+    __shared__ unsigned s_tile_cnt[2];
+    const unsigned tile = claim_tile(ticket, &s_slot);
+    const unsigned tile_base = tile * TILE;
+#pragma unroll
+    for (int j = 0; j < ITEMS / 2; ++j) {
+        const unsigned u = j * DR_THREADS + threadIdx.x;        // 16-byte unit inside the tile
+        const unsigned gpos = tile_base + 2 * u;
+        ulonglong2 v = make_ulonglong2(0ull, 0ull);
+        if (gpos + 1 < n_pos) {
+            ulonglong2* g = reinterpret_cast<ulonglong2*>(dense + gpos);
+            v = *g;
+            if (v.x | v.y) *g = make_ulonglong2(0ull, 0ull);
+        } else if (gpos < n_pos) {
+            v.x = dense[gpos];
+            if (v.x) dense[gpos] = 0ull;
+        }
+        *reinterpret_cast<ulonglong2*>(s_rows + (u / (ITEMS / 2)) * ROW + (u % (ITEMS / 2)) * 16) = v;
+    }
+    __syncthreads();
+    const unsigned char* row = s_rows + threadIdx.x * ROW;
+    const unsigned local = threadIdx.x * ITEMS;                  // first position of this thread in the tile
+    int tf = 0, td = 0;
+    unsigned mf = 0, md = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS / 2; ++k) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(row + k * 16);
+        int df, dd;
+        dense_unpack(v.x, df, dd);
+        tf += df; td += dd;
+        if (df != 0) mf |= 1u << (2 * k);
+        if (dd != 0) md |= 1u << (2 * k);
+        dense_unpack(v.y, df, dd);
+        tf += df; td += dd;
+        if (df != 0) mf |= 2u << (2 * k);
+        if (dd != 0) md |= 2u << (2 * k);
+    }
+    if (tile_base + local == 0) { mf |= 1u; md |= 1u; }
+    long long tile_tot, tile_cnt;
+    const long long ex_tot = block_excl_sum<long long>(((long long)tf << 32) + (long long)td, s_scan64, tile_tot);
+    const long long ex_cnt = block_excl_sum<long long>(((long long)__popc(mf) << 31) | (long long)__popc(md),
+                                                       s_scan64, tile_cnt);
+    if (threadIdx.x < 32) {
+        unsigned long long ex = lookback_excl_warp(st_tot, tile, (unsigned long long)tile_tot & LB_MASK);
+        if (threadIdx.x == 0) s_base[0] = ex;
+    } else if (threadIdx.x < 64) {
+        unsigned long long b = lookback_excl_warp(st_cnt, tile, (unsigned long long)tile_cnt);
+        if (threadIdx.x == 32) {
+            s_base[1] = b;
+            s_tile_cnt[0] = (unsigned)((unsigned long long)tile_cnt >> 31);
+            s_tile_cnt[1] = (unsigned)((unsigned long long)tile_cnt & 0x7fffffffull);
+            if (tile == gridDim.x - 1) {
+                const unsigned long long tot = b + (unsigned long long)tile_cnt;
+                out_counts[0] = tot >> 31;
+                out_counts[1] = tot & 0x7fffffffull;
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned long long g0 = s_base[1] >> 31, g1 = s_base[1] & 0x7fffffffull;   // tile's first entries
+    if (mf | md) {
+        int run_f, run_d;
+        {
+            const long long v = ((long long)(s_base[0] << 2) >> 2) + ex_tot;
+            run_d = (int)(unsigned)(v & 0xffffffffll);
+            run_f = (int)((v - (long long)run_d) >> 32);
+        }
+        unsigned r0 = (unsigned)((unsigned long long)ex_cnt >> 31);            // rank inside the tile
+        unsigned r1 = (unsigned)((unsigned long long)ex_cnt & 0x7fffffffull);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            int df, dd;
+            dense_unpack(*reinterpret_cast<const unsigned long long*>(row + k * 8), df, dd);
+            run_f += df;
+            run_d += dd;
+            if ((mf >> k) & 1u) {
+                if (r0 < (unsigned)DS_CAP) {
+                    s_pos[r0] = (uint16_t)(local + k);
+                    s_val[r0] = run_f;
+                } else if (g0 + r0 < cap) {
+                    frag_idx[g0 + r0] = tile_base + local + k;
+                    frag_val[g0 + r0] = run_f;
+                }
+                ++r0;
+            }
+            if ((md >> k) & 1u) {
+                if (r1 < (unsigned)DS_CAP) {
+                    s_pos[DS_CAP + r1] = (uint16_t)(local + k);
+                    s_val[DS_CAP + r1] = run_d;
+                } else if (g1 + r1 < cap) {
+                    dir_idx[g1 + r1] = tile_base + local + k;
+                    dir_val[g1 + r1] = run_d;
+                }
+                ++r1;
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned n0 = min(s_tile_cnt[0], (unsigned)DS_CAP), n1 = min(s_tile_cnt[1], (unsigned)DS_CAP);
+    for (unsigned i = threadIdx.x; i < n0; i += DR_THREADS)
+        if (g0 + i < cap) {
+            frag_idx[g0 + i] = tile_base + s_pos[i];
+            frag_val[g0 + i] = s_val[i];
+        }
+    for (unsigned i = threadIdx.x; i < n1; i += DR_THREADS)
+        if (g1 + i < cap) {
+            dir_idx[g1 + i] = tile_base + s_pos[DS_CAP + i];
+            dir_val[g1 + i] = s_val[DS_CAP + i];
+        }
+}
+constexpr int DS_SMEM = DR_THREADS * (16 * 8 + 16) + 2 * DS_CAP * 6;
+
+
 // ---- the same scan with the tile loads on the bulk-copy engine -------------------------
 //
 // Persistent blocks, DP_STAGES tile buffers each.  ONE cp.async.bulk (1-D TMA, SASS UBLKCP)
@@ -1477,9 +1619,10 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
     // ---- difference array ------------------------------------------------------------
     GPC_CUDA(cudaMemsetAsync(touched, 0, graph->n_nodes, stream));
     const unsigned n_pos = graph->size_bp + 1;           // a fragment may close at size_bp
-    // scan variant: 0 = one 4096-position tile per block, plain loads (default); 3 = persistent
-    // blocks, tiles moved by the bulk-copy engine, three in flight (measured slower, kept as the
-    // reference point for it)
+    // scan variant: 0 = one 4096-position tile per block, entries staged through shared memory
+    // and written coalesced (default); 1 = the same with every thread writing its own entries
+    // (the first version); 3 = persistent blocks, tiles moved by the bulk-copy engine, three in
+    // flight (measured slower, kept as the reference point for it)
     static const int variant = getenv("GPC_DENSE_SCAN") ? atoi(getenv("GPC_DENSE_SCAN")) : 0;
     const unsigned tile_size = DR_THREADS * 16;
     const unsigned tiles = div_up(n_pos, tile_size);
@@ -1547,6 +1690,16 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
             // of a tile may wait on any block of its wave)
             GPC_CUDA(cudaLaunchCooperativeKernel((void*)dense_runs_pipelined_kernel, dim3(blocks),
                                                  dim3(DR_THREADS), args, DP_SMEM, stream));
+        } else if (variant != 1) {
+            static bool configured4 = false;
+            if (!configured4) {
+                GPC_CUDA(cudaFuncSetAttribute(dense_runs_staged_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM));
+                configured4 = true;
+            }
+            dense_runs_staged_kernel<<<tiles, DR_THREADS, DS_SMEM, stream>>>(
+                dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt,
+                ticket, counts);
         } else {
             dense_runs_block_kernel<16><<<tiles, DR_THREADS, DR_THREADS * (16 * 8 + 16), stream>>>(
                 dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt,

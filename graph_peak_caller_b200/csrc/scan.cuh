@@ -18,34 +18,62 @@ __device__ __forceinline__ unsigned claim_tile(unsigned* ticket, unsigned* s_slo
     return t;
 }
 
-// Eight consecutive uint32 items of one thread as two 16-byte accesses where the array
-// allows it (16-byte aligned base, whole group inside the array), else item by item.
-__device__ __forceinline__ void load8_u32(const uint32_t* __restrict__ in, unsigned base, unsigned n,
-                                          unsigned (&v)[8]) {
-    if (base + 8 <= n && (reinterpret_cast<size_t>(in) & 15) == 0) {
+// N (a multiple of 4) consecutive uint32 items of one thread as 16-byte accesses where the
+// array allows it (16-byte aligned base, whole group inside the array), else item by item.
+template <int N>
+__device__ __forceinline__ void load_items_u32(const uint32_t* __restrict__ in, unsigned base, unsigned n,
+                                               unsigned (&v)[N]) {
+    if (base + N <= n && (reinterpret_cast<size_t>(in) & 15) == 0) {
         const uint4* p = reinterpret_cast<const uint4*>(in + base);
-        const uint4 a = p[0], b = p[1];
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            const uint4 a = p[q];
+            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+        }
     } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (base + j < n) ? in[base + j] : 0u;
+        for (int j = 0; j < N; ++j) v[j] = (base + j < n) ? in[base + j] : 0u;
+    }
+}
+// the same for uint8 items (N a multiple of 8)
+template <int N>
+__device__ __forceinline__ void load_items_u8(const uint8_t* __restrict__ in, unsigned base, unsigned n,
+                                              unsigned (&v)[N]) {
+    if (base + N <= n && (reinterpret_cast<size_t>(in) & 15) == 0) {
+        const uint2* p = reinterpret_cast<const uint2*>(in + base);
+#pragma unroll
+        for (int q = 0; q < N / 8; ++q) {
+            const uint2 a = p[q];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[8 * q + j] = (a.x >> (8 * j)) & 0xffu;
+                v[8 * q + 4 + j] = (a.y >> (8 * j)) & 0xffu;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = (base + j < n) ? (unsigned)in[base + j] : 0u;
     }
 }
 // out[base + j] = run + v[0] + ... + v[j - 1]
-__device__ __forceinline__ void store8_running(uint32_t* __restrict__ out, unsigned base, unsigned n,
-                                               unsigned run, const unsigned (&v)[8]) {
-    if (base + 8 <= n && (reinterpret_cast<size_t>(out) & 15) == 0) {
-        unsigned o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { o[j] = run; run += v[j]; }
+template <int N>
+__device__ __forceinline__ void store_running(uint32_t* __restrict__ out, unsigned base, unsigned n,
+                                              unsigned run, const unsigned (&v)[N]) {
+    if (base + N <= n && (reinterpret_cast<size_t>(out) & 15) == 0) {
         uint4* p = reinterpret_cast<uint4*>(out + base);
-        p[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        p[1] = make_uint4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            uint4 o;
+            o.x = run; run += v[4 * q];
+            o.y = run; run += v[4 * q + 1];
+            o.z = run; run += v[4 * q + 2];
+            o.w = run; run += v[4 * q + 3];
+            p[q] = o;
+        }
         return;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < N; ++j) {
         if (base + j < n) out[base + j] = run;
         run += v[j];
     }
@@ -53,6 +81,13 @@ __device__ __forceinline__ void store8_running(uint32_t* __restrict__ out, unsig
 
 // out[i] = sum_{j<i} in[j]  (uint32 in, uint64 running sum stored as uint32:
 // callers guarantee the total fits).  total[0] receives the grand total.
+// Sixteen items per thread in 16-byte accesses: eight scalar loads at a stride of eight
+// items replayed every sector eight times, and 2048-item tiles left the per-tile costs
+// (ticket, two block scans, look-back) uncovered -- node-sized scans ran at a tenth of
+// the copy rate.
+constexpr int ES_ITEMS = 16;
+constexpr int ES_TILE = SC_THREADS * ES_ITEMS;
+
 template <typename InT>
 __global__ void __launch_bounds__(SC_THREADS)
 excl_scan_kernel(const InT* __restrict__ in, uint32_t* __restrict__ out, unsigned n,
@@ -62,28 +97,15 @@ excl_scan_kernel(const InT* __restrict__ in, uint32_t* __restrict__ out, unsigne
     __shared__ unsigned s_slot;
     __shared__ unsigned long long s_prefix;
     const unsigned tile = claim_tile(ticket, &s_slot);
-    const unsigned base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
-    unsigned v[SC_ITEMS];
+    const unsigned base = tile * ES_TILE + threadIdx.x * ES_ITEMS;
+    unsigned v[ES_ITEMS];
     unsigned sum = 0;
-    // a thread's eight items in one (uint8) or two (uint32) vector loads when the array
-    // allows it: eight scalar loads at a stride of eight items replay every sector eight
-    // times (node-sized scans ran at a tenth of the copy rate)
-    const bool vec_in = base + SC_ITEMS <= n && (reinterpret_cast<size_t>(in) & 15) == 0;
-    if (sizeof(InT) == 4) {
-        load8_u32(reinterpret_cast<const uint32_t*>(in), base, n, v);
-    } else if (vec_in && sizeof(InT) == 1) {
-        const uint2 a = *reinterpret_cast<const uint2*>(in + base);
+    if (sizeof(InT) == 4)
+        load_items_u32<ES_ITEMS>(reinterpret_cast<const uint32_t*>(in), base, n, v);
+    else
+        load_items_u8<ES_ITEMS>(reinterpret_cast<const uint8_t*>(in), base, n, v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            v[j] = (a.x >> (8 * j)) & 0xffu;
-            v[4 + j] = (a.y >> (8 * j)) & 0xffu;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < SC_ITEMS; ++j) v[j] = (base + j < n) ? (unsigned)in[base + j] : 0u;
-    }
-#pragma unroll
-    for (int j = 0; j < SC_ITEMS; ++j) sum += v[j];
+    for (int j = 0; j < ES_ITEMS; ++j) sum += v[j];
     unsigned tile_total;
     unsigned ex = block_excl_sum<unsigned>(sum, s_scan, tile_total);
     if (threadIdx.x < 32) {
@@ -94,7 +116,7 @@ excl_scan_kernel(const InT* __restrict__ in, uint32_t* __restrict__ out, unsigne
         }
     }
     __syncthreads();
-    store8_running(out, base, n, (unsigned)s_prefix + ex, v);
+    store_running<ES_ITEMS>(out, base, n, (unsigned)s_prefix + ex, v);
 }
 
 // Host driver: scratch for status/ticket is taken from the stream pool.
@@ -105,7 +127,8 @@ int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* t
         if (total_dev) GPC_CUDA(cudaMemsetAsync(total_dev, 0, 8, stream));
         return GPC_OK;
     }
-    unsigned tiles = div_up(n, SC_TILE);
+    static_assert(sizeof(InT) == 4 || sizeof(InT) == 1, "exclusive_scan: uint32 or uint8 input");
+    unsigned tiles = div_up(n, ES_TILE);
     Scratch sc;
     GPC_CUDA(sc.alloc((size_t)tiles * 8 + 16, stream));
     GPC_CUDA(cudaMemsetAsync(sc.p, 0, (size_t)tiles * 8 + 16, stream));
@@ -214,7 +237,7 @@ multi_scan_kernel(MultiScanArgs a, unsigned n, unsigned long long* __restrict__ 
     const unsigned base = tile * SC_TILE + threadIdx.x * SC_ITEMS;
     for (int k = 0; k < a.k; ++k) {
         unsigned v[SC_ITEMS], sum = 0;
-        load8_u32(a.in[k], base, n, v);
+        load_items_u32<SC_ITEMS>(a.in[k], base, n, v);
 #pragma unroll
         for (int j = 0; j < SC_ITEMS; ++j) sum += v[j];
         unsigned tile_total;
@@ -227,7 +250,7 @@ multi_scan_kernel(MultiScanArgs a, unsigned n, unsigned long long* __restrict__ 
             }
         }
         __syncthreads();
-        store8_running(a.out[k], base, n, (unsigned)s_prefix[k] + ex, v);
+        store_running<SC_ITEMS>(a.out[k], base, n, (unsigned)s_prefix[k] + ex, v);
     }
 }
 
