@@ -392,16 +392,27 @@ def main_ours(args):
     def fresh(pinned):
         return pinned.fresh_view()
 
+    def e2e_reads(u):
+        s = fresh(u.pinned_s)
+        c = fresh(u.pinned_c) if u.pinned_c is not None else s    # one upload serves both
+        return UniqueIntervals(s), UniqueIntervals(c)
+
     def e2e_step():
         callers = []
-        for u in units:
+        ahead = e2e_reads(units[0])
+        for k, u in enumerate(units):
             caller = CallPeaks(u.g, u.config, Reporter(None))
-            s = fresh(u.pinned_s)
-            c = fresh(u.pinned_c) if u.pinned_c is not None else s    # one upload serves both
+            s, c = ahead
             if world == 1 and len(units) == 1:
-                caller.run(UniqueIntervals(s), UniqueIntervals(c))
+                caller.run(s, c)
                 return [caller]
-            caller.run_to_p_values(UniqueIntervals(s), UniqueIntervals(c))
+            if k + 1 < len(units):
+                # as MultipleGraphsCallpeaks.run_to_p_values does: the next chromosome's
+                # reads are uploaded (copy stream) while this one is computed
+                ahead = e2e_reads(units[k + 1])
+                for reads in set(ahead):
+                    reads.prefetch()
+            caller.run_to_p_values(s, c)
             callers.append(caller)
         tabs = []
         for u, caller in zip(units, callers):

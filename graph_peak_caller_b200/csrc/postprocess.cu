@@ -739,7 +739,8 @@ struct MpView {
     uint32_t* path;            // [nv]
 };
 
-__device__ __forceinline__ int mp_solve(const MpView& v, const int nv, const bool one_sweep, int& info_out) {
+__device__ __forceinline__ int mp_solve(const MpView& v, const int nv, const bool one_sweep, int& info_out,
+                                        unsigned long long* dbg = nullptr) {
     const long long INF = (1ll << 60);
     long long* const dist = v.dist;
     long long* const dsink = v.dsink;
@@ -757,6 +758,7 @@ __device__ __forceinline__ int mp_solve(const MpView& v, const int nv, const boo
     bool changed = true;
     while (changed) {
         changed = false;
+        if (dbg) atomicAdd(dbg + 0, 1ull);
         for (int j = nv - 1; j >= 0; --j) {
             long long w = -(long long)v.weight[j];
             long long best = dsink[j];
@@ -780,6 +782,7 @@ __device__ __forceinline__ int mp_solve(const MpView& v, const int nv, const boo
     dist[first] = 0;
     for (int sweep = 0; sweep < nv; ++sweep) {
         bool any = false;
+        if (dbg) atomicAdd(dbg + 1, 1ull);
         for (int j = 0; j < nv; ++j) {
             long long d1 = dist[j];
             if (d1 >= INF) continue;
@@ -869,7 +872,8 @@ max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ comp_ptr,
                  const uint32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
                  const int32_t* __restrict__ m_weight, const uint8_t* __restrict__ m_flags,
                  const uint8_t* __restrict__ comp_backward,
-                 long long* g_dist, long long* g_dsink, int32_t* g_pred, PathOut out) {
+                 long long* g_dist, long long* g_dsink, int32_t* g_pred, PathOut out,
+                 unsigned long long* dbg /* debugging aid, normally NULL */) {
     extern __shared__ __align__(16) unsigned char s_mp[];
     const unsigned lane = lane_id();
     const uint32_t c = blockIdx.x * MPW_WARPS + warp_id();
@@ -912,7 +916,14 @@ max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ comp_ptr,
     }
     __syncwarp();
     int len = 0, info = 0;
-    if (lane == 0) len = mp_solve(v, nv, one_sweep, info);
+    if (lane == 0) {
+        const long long t0 = dbg ? clock64() : 0;
+        len = mp_solve(v, nv, one_sweep, info, dbg);
+        if (dbg) {
+            atomicAdd(dbg + 2, (unsigned long long)(clock64() - t0));
+            atomicAdd(dbg + 3, (unsigned long long)nv);
+        }
+    }
     __syncwarp();
     len = __shfl_sync(FULL, len, 0);
     // forward order, vertex ids
@@ -1470,6 +1481,13 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
         // one launch per size class (see max_paths_kernel); the largest class needs the
         // opt-in to more than 48 KB of dynamic shared memory per block
         const unsigned mp_blocks = div_up(n_comp, MPW_WARPS);
+        Scratch dbg_sc;
+        unsigned long long* mp_dbg = nullptr;
+        if (getenv("GPC_MP_STATS")) {
+            GPC_CUDA(dbg_sc.alloc(32, stream));
+            GPC_CUDA(cudaMemsetAsync(dbg_sc.p, 0, 32, stream));
+            mp_dbg = dbg_sc.as<unsigned long long>();
+        }
 #define GPC_MP_LAUNCH(CLS, NAME)                                                                       \
         do {                                                                                           \
             const size_t smem__ = (CLS) == 0 ? 0 : MPW_WARPS * mp_warp_smem(mp_class_cap(CLS));        \
@@ -1481,8 +1499,16 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
                 (uint32_t)n_comp, comp_ptr.as<uint32_t>(), mk, adj_ptr.as<uint32_t>(),                 \
                 adj.as<uint32_t>(), m_weight.as<int32_t>(), m_flags.as<uint8_t>(),                     \
                 comp_backward.as<uint8_t>(), dist.as<long long>(), dsink.as<long long>(),              \
-                pred.as<int32_t>(), po);                                                               \
+                pred.as<int32_t>(), po, mp_dbg);                                                       \
             GPC_LAUNCH_CHECK();                                                                        \
+            if (mp_dbg) {                                                                              \
+                unsigned long long h__[4];                                                             \
+                cudaStreamSynchronize(stream);                                                         \
+                cudaMemcpy(h__, mp_dbg, 32, cudaMemcpyDeviceToHost);                                   \
+                cudaMemset(mp_dbg, 0, 32);                                                             \
+                fprintf(stderr, "  %s: %llu vertices, %llu + %llu sweeps, %.0f cycles per vertex\n",   \
+                        NAME, h__[3], h__[0], h__[1], h__[3] ? (double)h__[2] / (double)h__[3] : 0.0); \
+            }                                                                                          \
         } while (0)
         GPC_MP_LAUNCH(1, "max_paths");
         GPC_MP_LAUNCH(2, "max_paths_256");

@@ -906,18 +906,59 @@ dense_runs_block_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
 }
 
 
-// ---- the same scan with the entries staged through shared memory -------------------------
+// ---- the same scan, leaner: entries staged through shared memory, zero words skipped ------
 //
-// In the kernel above every thread writes its own entries straight to global memory: at
-// every one of its 16 steps a warp issues four stores (position and value of two tracks)
-// with ~15 % of the lanes active, each lane at its own offset -- ~2500 partial-sector
-// writes per tile for 300 sectors' worth of entries, more L2 transactions than the tile's
-// own 32 KB in and 32 KB of zeroes out.  Here the entries of a tile go to a staging area in
-// shared memory first (at the block-wide rank the count scan already provides: 16-bit
-// position in the tile + 32-bit value), and the block then copies them out with fully
-// coalesced stores.  A tile with more than DS_CAP entries in a track (> 31 % of its
-// positions) writes the overflow directly, as above.
+// The kernel above executes ~1450 instructions per warp and tile (ncu: 35 % of the issue
+// slots, nothing else above 41 %: it is bound by how much it executes between its waits).
+// Most of them sit in the emission pass: 16 unrolled steps x 2 tracks, each a divergent
+// region (a warp runs the body whenever ANY lane has an entry there, i.e. always) with a
+// capacity check, 64-bit addressing and two stores at ~15 % active lanes.  Here
+//   * a thread only visits its NON-ZERO words in the emission pass (a zero word changes
+//     neither running sum and emits nothing): ~3 of 16 on the chr22-scale workload, the
+//     warp-wide maximum ~8 -- a find-first-set loop instead of 16 unrolled steps;
+//   * entries go to a staging area in shared memory at the block-wide rank the count scan
+//     already provides (16-bit position in the tile + 32-bit value), branch-free (a lane
+//     without an entry writes a dump slot), and the block copies them out with coalesced
+//     stores: ~300 full sectors per tile instead of ~2500 partial ones;
+//   * both block scans (running sums, entry counts) share their barriers;
+//   * the tile total is the sum of the packed words, unpacked once.
+// A tile with more than DS_CAP entries in a track (> 31 % of its positions) takes the
+// direct path: same loop, stores straight to global memory with the capacity check.
 constexpr int DS_CAP = 1280;
+constexpr int DS_SLOTS = DS_CAP + 8;                   // + dump slot, keeps the arrays 16-byte aligned
+
+// two exclusive block sums at once (same barriers); s needs 2 x 33 entries
+__device__ __forceinline__ void block_excl_sum2(long long a, long long b, long long* s,
+                                                long long& ex_a, long long& ex_b,
+                                                long long& tot_a, long long& tot_b) {
+    long long ia = a, ib = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long oa = __shfl_up_sync(FULL, ia, d), ob = __shfl_up_sync(FULL, ib, d);
+        if (lane_id() >= (unsigned)d) { ia += oa; ib += ob; }
+    }
+    const unsigned w = warp_id(), l = lane_id();
+    if (l == 31) { s[w] = ia; s[33 + w] = ib; }
+    __syncthreads();
+    if (w == 0) {
+        const unsigned nw = (blockDim.x + 31) >> 5;
+        const long long xa = l < nw ? s[l] : 0ll, xb = l < nw ? s[33 + l] : 0ll;
+        long long ja = xa, jb = xb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long oa = __shfl_up_sync(FULL, ja, d), ob = __shfl_up_sync(FULL, jb, d);
+            if (l >= (unsigned)d) { ja += oa; jb += ob; }
+        }
+        s[l] = ja - xa;
+        s[33 + l] = jb - xb;
+        if (l == 31) { s[32] = ja; s[65] = jb; }
+    }
+    __syncthreads();
+    ex_a = s[w] + ia - a;
+    ex_b = s[33 + w] + ib - b;
+    tot_a = s[32];
+    tot_b = s[65];
+}
 
 __global__ void __launch_bounds__(DR_THREADS, 4)
 dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
@@ -931,12 +972,11 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     constexpr int TILE = DR_THREADS * ITEMS;
     constexpr int ROW = ITEMS * 8 + 16;
     extern __shared__ __align__(16) unsigned char s_rows[];      // DR_THREADS * ROW, then the staging area
-    int32_t* const s_val = reinterpret_cast<int32_t*>(s_rows + DR_THREADS * ROW);     // [2][DS_CAP]
-    uint16_t* const s_pos = reinterpret_cast<uint16_t*>(s_val + 2 * DS_CAP);          // [2][DS_CAP]
-    __shared__ long long s_scan64[33];
+    int32_t* const s_val = reinterpret_cast<int32_t*>(s_rows + DR_THREADS * ROW);     // [2][DS_SLOTS]
+    uint16_t* const s_pos = reinterpret_cast<uint16_t*>(s_val + 2 * DS_SLOTS);        // [2][DS_SLOTS]
+    __shared__ long long s_scan64[66];
     __shared__ unsigned s_slot;
     __shared__ unsigned long long s_base[2];
-    __shared__ unsigned s_tile_cnt[2];
     const unsigned tile = claim_tile(ticket, &s_slot);
     const unsigned tile_base = tile * TILE;
 #pragma unroll
@@ -957,26 +997,24 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     __syncthreads();
     const unsigned char* row = s_rows + threadIdx.x * ROW;
     const unsigned local = threadIdx.x * ITEMS;                  // first position of this thread in the tile
-    int tf = 0, td = 0;
+    // first pass: packed sum of the 16 words, one bit per word and track with a non-zero step
+    // (word = (dfrag << 32) + ddir, signed: dfrag = high word + sign bit of the low word)
+    unsigned long long wsum = 0ull;
     unsigned mf = 0, md = 0;
 #pragma unroll
     for (int k = 0; k < ITEMS / 2; ++k) {
         const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(row + k * 16);
-        int df, dd;
-        dense_unpack(v.x, df, dd);
-        tf += df; td += dd;
-        if (df != 0) mf |= 1u << (2 * k);
-        if (dd != 0) md |= 1u << (2 * k);
-        dense_unpack(v.y, df, dd);
-        tf += df; td += dd;
-        if (df != 0) mf |= 2u << (2 * k);
-        if (dd != 0) md |= 2u << (2 * k);
+        wsum += v.x + v.y;
+        const unsigned lx = (unsigned)v.x, ly = (unsigned)v.y;
+        if (lx != 0u) md |= 1u << (2 * k);
+        if ((unsigned)(v.x >> 32) + (lx >> 31) != 0u) mf |= 1u << (2 * k);
+        if (ly != 0u) md |= 2u << (2 * k);
+        if ((unsigned)(v.y >> 32) + (ly >> 31) != 0u) mf |= 2u << (2 * k);
     }
     if (tile_base + local == 0) { mf |= 1u; md |= 1u; }
-    long long tile_tot, tile_cnt;
-    const long long ex_tot = block_excl_sum<long long>(((long long)tf << 32) + (long long)td, s_scan64, tile_tot);
-    const long long ex_cnt = block_excl_sum<long long>(((long long)__popc(mf) << 31) | (long long)__popc(md),
-                                                       s_scan64, tile_cnt);
+    long long ex_tot, ex_cnt, tile_tot, tile_cnt;
+    block_excl_sum2((long long)wsum, ((long long)__popc(mf) << 31) | (long long)__popc(md), s_scan64,
+                    ex_tot, ex_cnt, tile_tot, tile_cnt);
     if (threadIdx.x < 32) {
         unsigned long long ex = lookback_excl_warp(st_tot, tile, (unsigned long long)tile_tot & LB_MASK);
         if (threadIdx.x == 0) s_base[0] = ex;
@@ -984,8 +1022,6 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
         unsigned long long b = lookback_excl_warp(st_cnt, tile, (unsigned long long)tile_cnt);
         if (threadIdx.x == 32) {
             s_base[1] = b;
-            s_tile_cnt[0] = (unsigned)((unsigned long long)tile_cnt >> 31);
-            s_tile_cnt[1] = (unsigned)((unsigned long long)tile_cnt & 0x7fffffffull);
             if (tile == gridDim.x - 1) {
                 const unsigned long long tot = b + (unsigned long long)tile_cnt;
                 out_counts[0] = tot >> 31;
@@ -995,57 +1031,67 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     }
     __syncthreads();
     const unsigned long long g0 = s_base[1] >> 31, g1 = s_base[1] & 0x7fffffffull;   // tile's first entries
-    if (mf | md) {
-        int run_f, run_d;
-        {
-            const long long v = ((long long)(s_base[0] << 2) >> 2) + ex_tot;
-            run_d = (int)(unsigned)(v & 0xffffffffll);
-            run_f = (int)((v - (long long)run_d) >> 32);
+    const unsigned n0 = (unsigned)((unsigned long long)tile_cnt >> 31);
+    const unsigned n1 = (unsigned)((unsigned long long)tile_cnt & 0x7fffffffull);
+    const bool staged = n0 <= (unsigned)DS_CAP && n1 <= (unsigned)DS_CAP;            // (uniform over the block)
+    int run_f, run_d;
+    {
+        const long long v = ((long long)(s_base[0] << 2) >> 2) + ex_tot;
+        run_d = (int)(unsigned)(v & 0xffffffffll);
+        run_f = (int)((v - (long long)run_d) >> 32);
+    }
+    unsigned r0 = (unsigned)((unsigned long long)ex_cnt >> 31);                      // rank inside the tile
+    unsigned r1 = (unsigned)((unsigned long long)ex_cnt & 0x7fffffffull);
+    unsigned m = mf | md;
+    if (staged) {
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            int df, dd;
+            dense_unpack(*reinterpret_cast<const unsigned long long*>(row + k * 8), df, dd);
+            run_f += df;
+            run_d += dd;
+            const unsigned ef = (mf >> k) & 1u, ed = (md >> k) & 1u;
+            const unsigned i0 = ef ? r0 : (unsigned)DS_CAP;                // dump slot
+            const unsigned i1 = DS_SLOTS + (ed ? r1 : (unsigned)DS_CAP);
+            s_pos[i0] = (uint16_t)(local + k);
+            s_val[i0] = run_f;
+            s_pos[i1] = (uint16_t)(local + k);
+            s_val[i1] = run_d;
+            r0 += ef;
+            r1 += ed;
         }
-        unsigned r0 = (unsigned)((unsigned long long)ex_cnt >> 31);            // rank inside the tile
-        unsigned r1 = (unsigned)((unsigned long long)ex_cnt & 0x7fffffffull);
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < n0; i += DR_THREADS)
+            if (g0 + i < cap) {
+                frag_idx[g0 + i] = tile_base + s_pos[i];
+                frag_val[g0 + i] = s_val[i];
+            }
+        for (unsigned i = threadIdx.x; i < n1; i += DR_THREADS)
+            if (g1 + i < cap) {
+                dir_idx[g1 + i] = tile_base + s_pos[DS_SLOTS + i];
+                dir_val[g1 + i] = s_val[DS_SLOTS + i];
+            }
+    } else {
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
             int df, dd;
             dense_unpack(*reinterpret_cast<const unsigned long long*>(row + k * 8), df, dd);
             run_f += df;
             run_d += dd;
             if ((mf >> k) & 1u) {
-                if (r0 < (unsigned)DS_CAP) {
-                    s_pos[r0] = (uint16_t)(local + k);
-                    s_val[r0] = run_f;
-                } else if (g0 + r0 < cap) {
-                    frag_idx[g0 + r0] = tile_base + local + k;
-                    frag_val[g0 + r0] = run_f;
-                }
+                if (g0 + r0 < cap) { frag_idx[g0 + r0] = tile_base + local + k; frag_val[g0 + r0] = run_f; }
                 ++r0;
             }
             if ((md >> k) & 1u) {
-                if (r1 < (unsigned)DS_CAP) {
-                    s_pos[DS_CAP + r1] = (uint16_t)(local + k);
-                    s_val[DS_CAP + r1] = run_d;
-                } else if (g1 + r1 < cap) {
-                    dir_idx[g1 + r1] = tile_base + local + k;
-                    dir_val[g1 + r1] = run_d;
-                }
+                if (g1 + r1 < cap) { dir_idx[g1 + r1] = tile_base + local + k; dir_val[g1 + r1] = run_d; }
                 ++r1;
             }
         }
     }
-    __syncthreads();
-    const unsigned n0 = min(s_tile_cnt[0], (unsigned)DS_CAP), n1 = min(s_tile_cnt[1], (unsigned)DS_CAP);
-    for (unsigned i = threadIdx.x; i < n0; i += DR_THREADS)
-        if (g0 + i < cap) {
-            frag_idx[g0 + i] = tile_base + s_pos[i];
-            frag_val[g0 + i] = s_val[i];
-        }
-    for (unsigned i = threadIdx.x; i < n1; i += DR_THREADS)
-        if (g1 + i < cap) {
-            dir_idx[g1 + i] = tile_base + s_pos[DS_CAP + i];
-            dir_val[g1 + i] = s_val[DS_CAP + i];
-        }
 }
-constexpr int DS_SMEM = DR_THREADS * (16 * 8 + 16) + 2 * DS_CAP * 6;
+constexpr int DS_SMEM = DR_THREADS * (16 * 8 + 16) + 2 * DS_SLOTS * 6;
 
 
 // ---- the same scan with the tile loads on the bulk-copy engine -------------------------

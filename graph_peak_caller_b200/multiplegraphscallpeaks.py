@@ -131,11 +131,24 @@ class MultipleGraphsCallpeaks:
         self.run_from_p_values()
 
     def run_to_p_values(self):
-        for i in self.my_chromosomes():
+        mine = self.my_chromosomes()
+
+        def load(i):
+            graph = self._graph(i)
+            return (graph,) + tuple(self.get_intervals(self.samples[i], self.controls[i], graph))
+
+        ahead = load(mine[0]) if mine else None
+        for k, i in enumerate(mine):
             name = self.names[i]
             logging.info("Running to p values, %s" % name)
-            graph = self._graph(i)
-            sample, control = self.get_intervals(self.samples[i], self.controls[i], graph)
+            graph, sample, control = ahead
+            ahead = None
+            if k + 1 < len(mine):
+                # the reads of the next chromosome cross the host link (copy stream) while
+                # this one is being computed
+                ahead = load(mine[k + 1])
+                for reads in ahead[1:]:
+                    reads.prefetch()
             config = self._config.copy()
             config.linear_map_name = self.linear_maps[i]
             caller = CallPeaks(graph, config, self._reporter.get_sub_reporter(name))

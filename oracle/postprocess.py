@@ -220,8 +220,13 @@ class _PieceGraph:
             self.matrix[:self.sink, :self.sink])
         keep = np.zeros(self.sink, dtype=bool)
         lookup = np.empty(self.sink + 1, dtype="int")
+        # members of every component in ascending order (= np.flatnonzero(label == comp),
+        # without one pass over all vertices per component: whole-genome chromosomes have
+        # 10^5 components)
+        order = np.argsort(label, kind="stable")
+        bounds = np.searchsorted(label[order], np.arange(n_comp + 1))
         for comp in range(n_comp):
-            members = np.r_[np.flatnonzero(label == comp), self.sink]
+            members = np.r_[order[bounds[comp]:bounds[comp + 1]], self.sink]
             if members.size - 1 > 36:
                 keep[members[:-1]] = True
                 continue
@@ -265,8 +270,10 @@ class _PieceGraph:
         n_comp, label = csgraph.connected_components(
             self.matrix[:self.sink, :self.sink])
         paths, infos = [], []
+        order = np.argsort(label, kind="stable")        # members per component, ascending
+        bounds = np.searchsorted(label[order], np.arange(n_comp + 1))
         for comp in range(n_comp):
-            members = np.r_[np.flatnonzero(label == comp), self.sink]
+            members = np.r_[order[bounds[comp]:bounds[comp + 1]], self.sink]
             sub = -self.matrix[members][:, members]
             sub.data = sub.data + 1
             if members.size == 2:
