@@ -721,83 +721,95 @@ struct PathOut {
     uint8_t* info;         // [n_comp] bit0 is_diff (two bindings), bit1 ambiguous
 };
 
-// Literal replay of PosDividedLineGraph.max_paths for ONE component, run by one thread
-// on whatever memory the view points at.  When every edge of the component points to a
-// later member (the vertex order is topological -- always the case for graphs with
-// ascending edges) one sweep of each relaxation is exact and the confirming sweep is
-// skipped.  Writes the path as local vertex indexes, BACKWARDS, into v.path; returns its
-// length, info = bit 0 is_diff (two bindings), bit 1 ambiguous.
+// PosDividedLineGraph.max_paths for ONE component, run by one thread on whatever memory
+// the view points at: scipy's Bellman-Ford (csgraph.shortest_path(method="BF"), a sweep
+// over the vertices in index order until nothing changes, first strict improvement wins)
+// restated so that ONE pass in topological order gives the same distances AND the same
+// predecessors.
+//
+// The reference numbers the vertices [pieces at node starts, whole nodes, pieces at node
+// ends], so its sweep order is not topological: a path runs end piece -> whole nodes ->
+// start piece and needs a new sweep after every step back in index.  The first version
+// here replayed the sweeps literally: 6.8 sweeps per component and relaxation on the
+// dense-variation workload (ncu-free measurement: 5 700 cycles per vertex).  What the
+// sweeps compute is order-free except for the predecessor of a vertex with several
+// tight in-edges, and that one has a closed form.  Say vertex j reaches its final
+// distance in sweep s_j by a relaxation from p_j.  j passes a final value on in the sweep
+// it is next visited in: s_j if p_j < j (later in the same sweep), else s_j + 1.  Among the
+// in-neighbours of t whose edge is tight, the one that sets dist[t] for the last time is
+// the first to arrive, i.e. the smallest (that sweep, j) -- all later ones find equality,
+// not improvement.  So, with the in-neighbours of a vertex finished before the vertex (node
+// ids ascend along every edge: the order `topo` -- members sorted by node -- is
+// topological), one push pass keeping the lexicographic minimum of (distance, sweep, j)
+// per vertex reproduces scipy's result exactly; distances to the sink are values only and
+// take one reverse pass.  Writes the path as local vertex indexes, BACKWARDS, into v.path;
+// returns its length, info = bit 0 is_diff (two bindings), bit 1 ambiguous.
 struct MpView {
     const uint32_t* adj_ptr;   // [nv + 1] indexes into adj
     const uint32_t* adj;       // targets; local index = adj[e] - v_base
     uint32_t v_base;
     const int32_t* weight;     // [nv]
     const uint8_t* flags;      // [nv] bit 0 entry, bit 1 exit
+    const uint32_t* topo;      // [nv] local index = topo[i] - v_base, in topological order
     long long* dist;           // [nv] working arrays
     long long* dsink;
     int32_t* pred;
+    int32_t* sweep;
     uint32_t* path;            // [nv]
 };
 
-__device__ __forceinline__ int mp_solve(const MpView& v, const int nv, const bool one_sweep, int& info_out,
-                                        unsigned long long* dbg = nullptr) {
+__device__ __forceinline__ int mp_solve(const MpView& v, const int nv, int& info_out) {
     const long long INF = (1ll << 60);
     long long* const dist = v.dist;
     long long* const dsink = v.dsink;
     int32_t* const pred = v.pred;
-    // Edge iteration of local vertex j in ascending target order (CSR order of
-    // the reference's sliced matrix): piece targets sorted by vertex id, sink last.
+    int32_t* const sweep = v.sweep;
+    // Edge iteration of local vertex j: piece targets, sink (local index nv) last.
     auto for_edges = [&](int j, auto&& fn) {
         const uint32_t e0 = v.adj_ptr[j], e1 = v.adj_ptr[j + 1];
         const bool to_sink = (v.flags[j] & 2) != 0;
         for (uint32_t e = e0; e < e1; ++e) fn((int)(v.adj[e] - v.v_base));
-        if (to_sink) fn(nv);                 // sink = local index nv
+        if (to_sink) fn(nv);
     };
-    // distance of every vertex to the sink (value only, order independent)
-    for (int j = 0; j < nv; ++j) dsink[j] = INF;
-    bool changed = true;
-    while (changed) {
-        changed = false;
-        if (dbg) atomicAdd(dbg + 0, 1ull);
-        for (int j = nv - 1; j >= 0; --j) {
-            long long w = -(long long)v.weight[j];
-            long long best = dsink[j];
-            for_edges(j, [&](int tgt) {
-                long long d = tgt == nv ? 0 : dsink[tgt];
-                if (d < INF && w + d < best) best = w + d;
-            });
-            if (best < dsink[j]) { dsink[j] = best; changed = true; }
-        }
-        if (one_sweep) break;
+    // distance of every vertex to the sink (value only): reverse topological order
+    for (int i = nv - 1; i >= 0; --i) {
+        const int j = (int)(v.topo[i] - v.v_base);
+        const long long w = -(long long)v.weight[j];
+        long long best = INF;
+        for_edges(j, [&](int tgt) {
+            const long long d = tgt == nv ? 0 : dsink[tgt];
+            if (d < INF && w + d < best) best = w + d;
+        });
+        dsink[j] = best;
     }
     // start = first entry vertex with minimal distance to the sink (np.argmin)
     int first = -1;
     for (int j = 0; j < nv; ++j)
         if ((v.flags[j] & 1) && (first < 0 || dsink[j] < dsink[first])) first = j;
     if (first < 0) first = 0;
-    // Bellman-Ford from `first`, scipy sweep order, first strict improvement wins
+    // shortest paths from `first` with scipy's predecessors (see above)
     long long dist_sink = INF;
-    int pred_sink = -9999;
-    for (int j = 0; j < nv; ++j) { dist[j] = INF; pred[j] = -9999; }
+    int pred_sink = -9999, sweep_sink = 0;
+    for (int j = 0; j < nv; ++j) { dist[j] = INF; pred[j] = -9999; sweep[j] = 0; }
     dist[first] = 0;
-    for (int sweep = 0; sweep < nv; ++sweep) {
-        bool any = false;
-        if (dbg) atomicAdd(dbg + 1, 1ull);
-        for (int j = 0; j < nv; ++j) {
-            long long d1 = dist[j];
-            if (d1 >= INF) continue;
-            long long w = -(long long)v.weight[j];
-            for_edges(j, [&](int tgt) {
-                if (tgt == nv) {
-                    if (d1 + w < dist_sink) { dist_sink = d1 + w; pred_sink = j; any = true; }
-                } else if (d1 + w < dist[tgt]) {
-                    dist[tgt] = d1 + w;
-                    pred[tgt] = j;
-                    any = true;
+    for (int i = 0; i < nv; ++i) {
+        const int j = (int)(v.topo[i] - v.v_base);
+        const long long d1 = dist[j];
+        if (d1 >= INF) continue;
+        const long long c = d1 - (long long)v.weight[j];
+        const int sj = sweep[j] + (pred[j] > j ? 1 : 0);      // the sweep j passes its final value on in
+        for_edges(j, [&](int tgt) {
+            if (tgt == nv) {
+                if (c < dist_sink || (c == dist_sink && (sj < sweep_sink || (sj == sweep_sink && j < pred_sink)))) {
+                    dist_sink = c; sweep_sink = sj; pred_sink = j;
                 }
-            });
-        }
-        if (!any || one_sweep) break;
+            } else {
+                const long long d2 = dist[tgt];
+                if (c < d2 || (c == d2 && (sj < sweep[tgt] || (sj == sweep[tgt] && j < pred[tgt])))) {
+                    dist[tgt] = c; sweep[tgt] = sj; pred[tgt] = j;
+                }
+            }
+        });
     }
     // _backtrace (graphs.py:273-283): stops at local vertex 0 as well
     int len = 0;
@@ -840,48 +852,70 @@ __device__ __forceinline__ int mp_solve(const MpView& v, const int nv, const boo
     return len;
 }
 
-// One WARP per component.  The replay itself is one dependent access after the other and
+// One WARP per component.  The pass itself is one dependent access after the other and
 // runs on lane 0; what the other lanes are for is the memory around it: they stage the
-// component's adjacency, weights and flags in shared memory (coalesced), the working
-// arrays live there too (~30 cycles per dependent access instead of an L2 round trip),
-// and they write the path out in forward order.  Components come in size classes (one
-// launch each over all components, a warp whose component belongs to another class
-// leaves at once) so that the shared memory of a block fits the components it holds:
+// component's adjacency, weights, flags and topological order in shared memory (coalesced),
+// the working arrays live there too (~30 cycles per dependent access instead of an L2
+// round trip), and they write the path out in forward order.  Components come in size
+// classes -- a list per class, filled by mp_classify_kernel, one launch per class -- so
+// that the shared memory of a block fits the components it holds and every warp of a
+// block has work:
 //   class 1: <= 64 vertices, 2: <= 256, 3: <= 1024 (edges <= 3 per vertex each),
 //   class 0: everything larger, working arrays in global memory.
 // (One THREAD per component, eight to a block, was the first version: the threads of a
 // warp diverge on everything, so a warp took the time of its eight components one after
-// the other -- 9.3 of 26.5 ms on the dense-variation workload, where a peak has a few
-// hundred pieces.)
+// the other.)
 constexpr int MPW_WARPS = 4;
+constexpr int MP_BYTES_PER_VERTEX = 8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 12 + 1;   // dist, dsink, pred, sweep, path,
+                                                                            // weight, adj_ptr, topo, adj (3x), flags
 __host__ __device__ constexpr int mp_class_cap(int cls) { return cls == 1 ? 64 : (cls == 2 ? 256 : 1024); }
-__host__ __device__ constexpr size_t mp_warp_smem(int capv) {
-    // dist, dsink (8 each), pred, path, weight, adj_ptr (4 each), adj (3 x 4), flags (1) per vertex
-    return (size_t)capv * (8 + 8 + 4 + 4 + 4 + 4 + 12 + 1) + 32;
-}
+__host__ __device__ constexpr size_t mp_warp_smem(int capv) { return (size_t)capv * MP_BYTES_PER_VERTEX + 32; }
 __device__ __forceinline__ int mp_class(uint32_t nv, uint32_t ne) {
     for (int cls = 1; cls <= 3; ++cls)
         if (nv <= (uint32_t)mp_class_cap(cls) && ne <= 3u * mp_class_cap(cls)) return cls;
     return 0;
 }
 
+// class_count[cls] components in class_list[cls * n_comp ...] (order inside a class is
+// irrelevant: every component writes its own outputs)
+__global__ void mp_classify_kernel(uint32_t n_comp, const uint32_t* __restrict__ comp_ptr,
+                                   const uint32_t* __restrict__ adj_ptr, uint32_t* __restrict__ class_count,
+                                   uint32_t* __restrict__ class_list) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_comp) return;
+    const uint32_t lo = comp_ptr[c], hi = comp_ptr[c + 1];
+    const int cls = mp_class(hi - lo, adj_ptr[hi] - adj_ptr[lo]);
+    class_list[(size_t)cls * n_comp + atomicAdd(class_count + cls, 1u)] = c;
+}
+
+// topological keys of the members: (component << node_bits) | node of the vertex
+__global__ void mp_topo_keys_kernel(uint32_t V, const unsigned long long* __restrict__ member_keys,
+                                    const uint32_t* __restrict__ comp_of_vertex,
+                                    const uint32_t* __restrict__ node_of, int node_bits,
+                                    unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const uint32_t u = member_vertex(member_keys, i);
+    keys[i] = ((unsigned long long)comp_of_vertex[u] << node_bits) | node_of[u];
+    vals[i] = i;
+}
+
 template <int CLS>
 __global__ void __launch_bounds__(MPW_WARPS * 32)
-max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ comp_ptr,
+max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ class_count,
+                 const uint32_t* __restrict__ class_list, const uint32_t* __restrict__ comp_ptr,
                  const unsigned long long* __restrict__ member_keys,
                  const uint32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj,
                  const int32_t* __restrict__ m_weight, const uint8_t* __restrict__ m_flags,
-                 const uint8_t* __restrict__ comp_backward,
-                 long long* g_dist, long long* g_dsink, int32_t* g_pred, PathOut out,
-                 unsigned long long* dbg /* debugging aid, normally NULL */) {
+                 const uint32_t* __restrict__ topo_member,
+                 long long* g_dist, long long* g_dsink, int32_t* g_pred, int32_t* g_sweep, PathOut out) {
     extern __shared__ __align__(16) unsigned char s_mp[];
     const unsigned lane = lane_id();
-    const uint32_t c = blockIdx.x * MPW_WARPS + warp_id();
-    if (c >= n_comp) return;
+    const uint32_t slot = blockIdx.x * MPW_WARPS + warp_id();
+    if (slot >= class_count[CLS]) return;
+    const uint32_t c = class_list[(size_t)CLS * n_comp + slot];
     const uint32_t lo = comp_ptr[c], hi = comp_ptr[c + 1];
     const int nv = (int)(hi - lo);           // vertices without the sink
-    const uint32_t e_lo = adj_ptr[lo], ne = adj_ptr[hi] - e_lo;
-    if (mp_class((uint32_t)nv, ne) != CLS) return;
     if (nv == 1) {                           // graphs.py:342-345
         if (lane == 0) {
             out.path[lo] = member_vertex(member_keys, lo);
@@ -890,40 +924,36 @@ max_paths_kernel(uint32_t n_comp, const uint32_t* __restrict__ comp_ptr,
         }
         return;
     }
-    const bool one_sweep = comp_backward[(uint32_t)(member_keys[lo] >> 32)] == 0;
     MpView v;
     if (CLS != 0) {
         constexpr int CAP = mp_class_cap(CLS == 0 ? 1 : CLS);
+        const uint32_t e_lo = adj_ptr[lo], ne = adj_ptr[hi] - e_lo;
         unsigned char* base = s_mp + (size_t)warp_id() * mp_warp_smem(CAP);
         long long* s_dist = reinterpret_cast<long long*>(base);
         long long* s_dsink = s_dist + CAP;
         int32_t* s_pred = reinterpret_cast<int32_t*>(s_dsink + CAP);
-        uint32_t* s_path = reinterpret_cast<uint32_t*>(s_pred + CAP);
+        int32_t* s_sweep = s_pred + CAP;
+        uint32_t* s_path = reinterpret_cast<uint32_t*>(s_sweep + CAP);
         int32_t* s_w = reinterpret_cast<int32_t*>(s_path + CAP);
-        uint32_t* s_adjptr = reinterpret_cast<uint32_t*>(s_w + CAP);      // CAP + 1 used
+        uint32_t* s_topo = reinterpret_cast<uint32_t*>(s_w + CAP);
+        uint32_t* s_adjptr = s_topo + CAP;                                 // CAP + 1 used
         uint32_t* s_adj = s_adjptr + CAP + 4;
         uint8_t* s_flags = reinterpret_cast<uint8_t*>(s_adj + 3 * CAP);
         for (int j = lane; j < nv; j += 32) {
             s_w[j] = m_weight[lo + j];
             s_flags[j] = m_flags[lo + j];
+            s_topo[j] = topo_member[lo + j] - lo;
         }
         for (int j = lane; j <= nv; j += 32) s_adjptr[j] = adj_ptr[lo + j] - e_lo;
         for (uint32_t e = lane; e < ne; e += 32) s_adj[e] = adj[e_lo + e] - lo;
-        v = MpView{s_adjptr, s_adj, 0u, s_w, s_flags, s_dist, s_dsink, s_pred, s_path};
+        v = MpView{s_adjptr, s_adj, 0u, s_w, s_flags, s_topo, s_dist, s_dsink, s_pred, s_sweep, s_path};
     } else {
-        v = MpView{adj_ptr + lo, adj, lo, m_weight + lo, m_flags + lo, g_dist + lo, g_dsink + lo,
-                   g_pred + lo, out.path + lo};
+        v = MpView{adj_ptr + lo, adj, lo, m_weight + lo, m_flags + lo, topo_member + lo, g_dist + lo,
+                   g_dsink + lo, g_pred + lo, g_sweep + lo, out.path + lo};
     }
     __syncwarp();
     int len = 0, info = 0;
-    if (lane == 0) {
-        const long long t0 = dbg ? clock64() : 0;
-        len = mp_solve(v, nv, one_sweep, info, dbg);
-        if (dbg) {
-            atomicAdd(dbg + 2, (unsigned long long)(clock64() - t0));
-            atomicAdd(dbg + 3, (unsigned long long)nv);
-        }
-    }
+    if (lane == 0) len = mp_solve(v, nv, info);
     __syncwarp();
     len = __shfl_sync(FULL, len, 0);
     // forward order, vertex ids
@@ -1456,38 +1486,37 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
                                      adj.as<uint32_t>(), m_weight.as<int32_t>(),
                                      m_flags.as<uint8_t>(), comp_backward.as<uint8_t>());
         GPC_LAUNCH_CHECK();
-        if (getenv("GPC_MP_STATS")) {          // debugging aid: component sizes to stderr
-            std::vector<uint32_t> cp((size_t)n_comp + 1);
-            std::vector<uint8_t> cb(V);
-            std::vector<unsigned long long> hk(V);
-            cudaStreamSynchronize(stream);
-            cudaMemcpy(cp.data(), comp_ptr.p, ((size_t)n_comp + 1) * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(cb.data(), comp_backward.p, V, cudaMemcpyDeviceToHost);
-            cudaMemcpy(hk.data(), mk, (size_t)V * 8, cudaMemcpyDeviceToHost);
-            unsigned long long hist[6] = {0, 0, 0, 0, 0, 0}, verts[6] = {0, 0, 0, 0, 0, 0}, back = 0, biggest = 0;
-            for (unsigned long long c = 0; c < n_comp; ++c) {
-                const unsigned nv = cp[c + 1] - cp[c];
-                const int b = nv <= 1 ? 0 : nv <= 64 ? 1 : nv <= 256 ? 2 : nv <= 1024 ? 3 : nv <= 4096 ? 4 : 5;
-                hist[b]++; verts[b] += nv;
-                if (nv > biggest) biggest = nv;
-                if (cb[(uint32_t)(hk[cp[c]] >> 32)]) back++;
-            }
-            fprintf(stderr, "max_paths: %llu components, %llu vertices, %llu with backward edges, largest %llu\n",
-                    (unsigned long long)n_comp, (unsigned long long)V, back, biggest);
-            const char* names[6] = {"1", "<=64", "<=256", "<=1024", "<=4096", ">4096"};
-            for (int b = 0; b < 6; ++b)
-                fprintf(stderr, "  %-7s %8llu components %10llu vertices\n", names[b], hist[b], verts[b]);
-        }
-        // one launch per size class (see max_paths_kernel); the largest class needs the
-        // opt-in to more than 48 KB of dynamic shared memory per block
+        // members of every component in topological order (sorted by node: ids ascend along
+        // every edge), as positions in the member arrays
+        Scratch tk0, tk1, tv0, tv1, sweep, ccount, clist;
+        GPC_CUDA(tk0.alloc((size_t)V * 8, stream));
+        GPC_CUDA(tk1.alloc((size_t)V * 8, stream));
+        GPC_CUDA(tv0.alloc((size_t)V * 4, stream));
+        GPC_CUDA(tv1.alloc((size_t)V * 4, stream));
+        GPC_CUDA(sweep.alloc((size_t)V * 4, stream));
+        int node_bits = 1, comp_bits = 1;
+        while ((1ull << node_bits) < (unsigned long long)graph->n_nodes) ++node_bits;
+        while ((1ull << comp_bits) < n_comp) ++comp_bits;
+        GPC_PROF("mp_topo_keys");
+        mp_topo_keys_kernel<<<GRID(V)>>>((uint32_t)V, mk, comp_of.as<uint32_t>(), v_node.as<uint32_t>(),
+                                         node_bits, tk0.as<unsigned long long>(), tv0.as<uint32_t>());
+        GPC_LAUNCH_CHECK();
+        bool topo_tmp = false;
+        GPC_TRY((radix_sort<unsigned long long, true>(tk0.as<unsigned long long>(), tk1.as<unsigned long long>(),
+                                                      tv0.as<uint32_t>(), tv1.as<uint32_t>(), V, 0,
+                                                      node_bits + comp_bits, false, &topo_tmp, stream)));
+        const uint32_t* topo_member = topo_tmp ? tv1.as<uint32_t>() : tv0.as<uint32_t>();
+        GPC_CUDA(ccount.alloc(16, stream));
+        GPC_CUDA(cudaMemsetAsync(ccount.p, 0, 16, stream));
+        GPC_CUDA(clist.alloc((size_t)n_comp * 4 * 4, stream));
+        GPC_PROF("mp_classify");
+        mp_classify_kernel<<<GRID(n_comp)>>>((uint32_t)n_comp, comp_ptr.as<uint32_t>(), adj_ptr.as<uint32_t>(),
+                                             ccount.as<uint32_t>(), clist.as<uint32_t>());
+        GPC_LAUNCH_CHECK();
+        // one launch per size class (see max_paths_kernel), each with room for every component
+        // (the class sizes stay on the device); the larger classes need the opt-in to more than
+        // 48 KB of dynamic shared memory per block
         const unsigned mp_blocks = div_up(n_comp, MPW_WARPS);
-        Scratch dbg_sc;
-        unsigned long long* mp_dbg = nullptr;
-        if (getenv("GPC_MP_STATS")) {
-            GPC_CUDA(dbg_sc.alloc(32, stream));
-            GPC_CUDA(cudaMemsetAsync(dbg_sc.p, 0, 32, stream));
-            mp_dbg = dbg_sc.as<unsigned long long>();
-        }
 #define GPC_MP_LAUNCH(CLS, NAME)                                                                       \
         do {                                                                                           \
             const size_t smem__ = (CLS) == 0 ? 0 : MPW_WARPS * mp_warp_smem(mp_class_cap(CLS));        \
@@ -1496,19 +1525,11 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem__)); \
             GPC_PROF(NAME);                                                                            \
             max_paths_kernel<CLS><<<mp_blocks, MPW_WARPS * 32, smem__, stream>>>(                      \
-                (uint32_t)n_comp, comp_ptr.as<uint32_t>(), mk, adj_ptr.as<uint32_t>(),                 \
-                adj.as<uint32_t>(), m_weight.as<int32_t>(), m_flags.as<uint8_t>(),                     \
-                comp_backward.as<uint8_t>(), dist.as<long long>(), dsink.as<long long>(),              \
-                pred.as<int32_t>(), po, mp_dbg);                                                       \
+                (uint32_t)n_comp, ccount.as<uint32_t>(), clist.as<uint32_t>(), comp_ptr.as<uint32_t>(), \
+                mk, adj_ptr.as<uint32_t>(), adj.as<uint32_t>(), m_weight.as<int32_t>(),                \
+                m_flags.as<uint8_t>(), topo_member, dist.as<long long>(), dsink.as<long long>(),       \
+                pred.as<int32_t>(), sweep.as<int32_t>(), po);                                          \
             GPC_LAUNCH_CHECK();                                                                        \
-            if (mp_dbg) {                                                                              \
-                unsigned long long h__[4];                                                             \
-                cudaStreamSynchronize(stream);                                                         \
-                cudaMemcpy(h__, mp_dbg, 32, cudaMemcpyDeviceToHost);                                   \
-                cudaMemset(mp_dbg, 0, 32);                                                             \
-                fprintf(stderr, "  %s: %llu vertices, %llu + %llu sweeps, %.0f cycles per vertex\n",   \
-                        NAME, h__[3], h__[0], h__[1], h__[3] ? (double)h__[2] / (double)h__[3] : 0.0); \
-            }                                                                                          \
         } while (0)
         GPC_MP_LAUNCH(1, "max_paths");
         GPC_MP_LAUNCH(2, "max_paths_256");
