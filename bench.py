@@ -468,6 +468,8 @@ def main_ours(args):
                                   frac=(v[2] / (v[1] / 1e3) / 1e9 / peak_gbs
                                         if v[1] > 0 and v[2] > 0 else None))
                           for k, v in kt[:8]})
+    if os.environ.get("GPC_BENCH_ALL_KERNELS"):       # every kernel label: ms per step, launches per step
+        roofline["all_kernels"] = {k: [round(v[1] / args.steps, 4), v[0] // args.steps] for k, v in kt}
     cpu = None
     ingest = None
     if world == 1 and not args.no_cpu:

@@ -195,34 +195,56 @@ __device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long lo
 // its prefix: by then the predecessors have published too and the walk back
 // costs one or two round trips instead of a spin.
 // lb_publish_agg: ONE thread.  lb_resolve_warp: all 32 lanes of ONE warp, same
-// arguments; 32 predecessors are inspected per step.
+// arguments; 32 x GPC_LB_WIDE predecessors are inspected per step.
 __device__ __forceinline__ void lb_publish_agg(unsigned long long* status, unsigned tile,
                                                unsigned long long agg) {
     lb_store(&status[tile], (tile == 0 ? LB_PREFIX : LB_AGG) | (agg & LB_MASK));
 }
+// LB_WIDE windows of 32 predecessors are loaded per round trip (the loads of a round are
+// independent: one L2 latency for all of them).  With ~600 tiles in flight that arrive at
+// their look-back as a wave, the tile at position i of the wave has to walk back over i
+// aggregates before it meets a prefix; at 32 per round trip that was up to 18 dependent L2
+// round trips (ncu of the difference-array scan: barrier 13 + long scoreboard 12 warps per
+// issue, nothing busy above 41 %), at 128 it is five.
+#ifndef GPC_LB_WIDE
+#define GPC_LB_WIDE 4
+#endif
 __device__ __forceinline__ unsigned long long lb_resolve_warp(unsigned long long* status,
                                                               unsigned tile,
                                                               unsigned long long agg) {
+    constexpr int LB_WIDE = GPC_LB_WIDE;
     const unsigned lane = threadIdx.x & 31;
     agg &= LB_MASK;
     if (tile == 0) return 0;
     unsigned long long excl = 0;
     int newest = (int)tile - 1;
     while (true) {
-        int t = newest - (int)lane;                 // lane 0 = nearest predecessor
-        unsigned long long s = (t >= 0) ? lb_load(&status[t]) : LB_PREFIX;
-        unsigned long long st = s & ~LB_MASK;
-        unsigned empty = __ballot_sync(0xffffffffu, st == LB_EMPTY);
-        unsigned pref = __ballot_sync(0xffffffffu, st == LB_PREFIX);
-        int first_pref = pref ? (__ffs(pref) - 1) : 32;
-        unsigned need = (first_pref >= 31) ? 0xffffffffu : ((2u << first_pref) - 1u);
-        if (empty & need) continue;                 // someone in the window is not ready
-        unsigned long long v = ((int)lane <= first_pref) ? (s & LB_MASK) : 0ull;
+        unsigned long long s[LB_WIDE];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        excl += v;
-        if (first_pref < 32) break;
-        newest -= 32;
+        for (int k = 0; k < LB_WIDE; ++k) {
+            const int t = newest - (int)lane - 32 * k;     // lane 0 of window 0 = nearest predecessor
+            s[k] = (t >= 0) ? lb_load(&status[t]) : LB_PREFIX;
+        }
+        bool done = false;
+        int complete = 0;                           // windows of this round that were all ready
+#pragma unroll
+        for (int k = 0; k < LB_WIDE; ++k) {
+            if (done || complete != k) continue;    // (uniform: every lane sees the same ballots)
+            const unsigned long long st = s[k] & ~LB_MASK;
+            const unsigned empty = __ballot_sync(0xffffffffu, st == LB_EMPTY);
+            const unsigned pref = __ballot_sync(0xffffffffu, st == LB_PREFIX);
+            const int first_pref = pref ? (__ffs(pref) - 1) : 32;
+            const unsigned need = (first_pref >= 31) ? 0xffffffffu : ((2u << first_pref) - 1u);
+            if (empty & need) continue;             // someone in this window is not ready: reload from here
+            unsigned long long v = ((int)lane <= first_pref) ? (s[k] & LB_MASK) : 0ull;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            excl += v;
+            complete = k + 1;
+            if (first_pref < 32) done = true;
+        }
+        if (done) break;
+        newest -= 32 * complete;                    // aggregates already summed stay summed
     }
     // sums are taken modulo 2^62, so packed signed payloads work as well
     if (lane == 0) lb_store(&status[tile], LB_PREFIX | ((excl + agg) & LB_MASK));

@@ -16,6 +16,8 @@
 // into q with the running minimum, and looked up per run by exact key.
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "poisson.cuh"
 #include "radix_sort.cuh"
@@ -596,9 +598,13 @@ extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n
     *n_distinct = 0;
     if (n_runs == 0) return GPC_OK;
     unsigned n = (unsigned)n_runs;
-    // tracks hold few distinct p (tens of thousands): start small, grow when the
-    // table turns out more than half full
-    unsigned long long cap = 1ull << 17;
+    // tracks hold few distinct p (tens of thousands) when the linear map is all-integer,
+    // millions when it is not (dense variation: every node scale its own lambda values):
+    // start from the size the last call ended with (a failed size costs a whole insert pass;
+    // the dense-variation workload went through four of them per call), grow when the table
+    // turns out more than half full
+    static std::atomic<unsigned long long> cap_hint{1ull << 17};
+    unsigned long long cap = cap_hint.load();
     while (true) {
         Scratch keys, counts, fail, flag, offs, total;
         GPC_CUDA(keys.alloc(cap * 8, stream));
@@ -630,6 +636,11 @@ extern "C" int gpc_ptable_local(const uint32_t* pos, const double* p, uint64_t n
             continue;
         }
         *n_distinct = h;
+        {   // next call: the smallest power of two that keeps this many keys below a quarter
+            unsigned long long next = 1ull << 17;
+            while (next < 4 * h) next <<= 1;
+            cap_hint.store(next);
+        }
         if (h > table_capacity) return GPC_ERR_CAPACITY;
         GPC_PROF("ptable_compact");
         ptable_compact_kernel<<<div_up(cap, 256), 256, 0, stream>>>(

@@ -173,9 +173,10 @@ def pvalues(spos, sval, sample_scale, cpos, cval, control_scale=1.0):
 
 def ptable_local(pos, p, track_size):
     """Q1 (local half).  Returns (p float64[D], bp int64[D]) unordered."""
+    global _ptable_cap
     torch = torch_cuda()
     lib = _lib.load()
-    cap = 1 << 16
+    cap = _ptable_cap          # sized from the last table: a table that does not fit costs a whole second pass
     while True:
         tp, tc = empty(cap, torch.float64), empty(cap, torch.int64)
         n_out = _u64()
@@ -186,7 +187,11 @@ def ptable_local(pos, p, track_size):
             cap = int(n_out.value) + 16
             continue
         _lib.check(status)
+        _ptable_cap = max(1 << 16, int(n_out.value) * 5 // 4 + 16)
         return tp[:n_out.value], tc[:n_out.value]
+
+
+_ptable_cap = 1 << 16
 
 
 def qtable_build(table_p, table_count, total_bp):
