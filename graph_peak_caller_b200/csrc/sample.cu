@@ -826,20 +826,22 @@ dense_runs_block_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     __shared__ unsigned long long s_base[2];
     const unsigned tile = claim_tile(ticket, &s_slot);
     const unsigned tile_base = tile * TILE;
+    // all loads of the tile first, then the zeroes: written as load / test / store per unit
+    // the compiler kept that order (the stores go to the array the next load reads), i.e.
+    // eight dependent DRAM round trips per tile -- 40 % of the kernel's stall samples.  The
+    // array is padded to whole tiles (dense_acquire), so every unit may be loaded in full.
+    ulonglong2 v[ITEMS / 2];
 #pragma unroll
     for (int j = 0; j < ITEMS / 2; ++j) {
         const unsigned u = j * DR_THREADS + threadIdx.x;        // 16-byte unit inside the tile
-        const unsigned gpos = tile_base + 2 * u;
-        ulonglong2 v = make_ulonglong2(0ull, 0ull);
-        if (gpos + 1 < n_pos) {
-            ulonglong2* g = reinterpret_cast<ulonglong2*>(dense + gpos);
-            v = *g;
-            if (v.x | v.y) *g = make_ulonglong2(0ull, 0ull);
-        } else if (gpos < n_pos) {
-            v.x = dense[gpos];
-            if (v.x) dense[gpos] = 0ull;
-        }
-        *reinterpret_cast<ulonglong2*>(s_rows + (u / (ITEMS / 2)) * ROW + (u % (ITEMS / 2)) * 16) = v;
+        v[j] = __ldcs(reinterpret_cast<const ulonglong2*>(dense + tile_base + 2 * u));
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS / 2; ++j) {
+        const unsigned u = j * DR_THREADS + threadIdx.x;
+        if (v[j].x | v[j].y)
+            *reinterpret_cast<ulonglong2*>(dense + tile_base + 2 * u) = make_ulonglong2(0ull, 0ull);
+        *reinterpret_cast<ulonglong2*>(s_rows + (u / (ITEMS / 2)) * ROW + (u % (ITEMS / 2)) * 16) = v[j];
     }
     __syncthreads();
     const unsigned char* row = s_rows + threadIdx.x * ROW;
@@ -979,20 +981,22 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     __shared__ unsigned long long s_base[2];
     const unsigned tile = claim_tile(ticket, &s_slot);
     const unsigned tile_base = tile * TILE;
+    // all loads of the tile first, then the zeroes: written as load / test / store per unit
+    // the compiler kept that order (the stores go to the array the next load reads), i.e.
+    // eight dependent DRAM round trips per tile -- 40 % of the kernel's stall samples.  The
+    // array is padded to whole tiles (dense_acquire), so every unit may be loaded in full.
+    ulonglong2 v[ITEMS / 2];
 #pragma unroll
     for (int j = 0; j < ITEMS / 2; ++j) {
         const unsigned u = j * DR_THREADS + threadIdx.x;        // 16-byte unit inside the tile
-        const unsigned gpos = tile_base + 2 * u;
-        ulonglong2 v = make_ulonglong2(0ull, 0ull);
-        if (gpos + 1 < n_pos) {
-            ulonglong2* g = reinterpret_cast<ulonglong2*>(dense + gpos);
-            v = *g;
-            if (v.x | v.y) *g = make_ulonglong2(0ull, 0ull);
-        } else if (gpos < n_pos) {
-            v.x = dense[gpos];
-            if (v.x) dense[gpos] = 0ull;
-        }
-        *reinterpret_cast<ulonglong2*>(s_rows + (u / (ITEMS / 2)) * ROW + (u % (ITEMS / 2)) * 16) = v;
+        v[j] = __ldcs(reinterpret_cast<const ulonglong2*>(dense + tile_base + 2 * u));
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS / 2; ++j) {
+        const unsigned u = j * DR_THREADS + threadIdx.x;
+        if (v[j].x | v[j].y)
+            *reinterpret_cast<ulonglong2*>(dense + tile_base + 2 * u) = make_ulonglong2(0ull, 0ull);
+        *reinterpret_cast<ulonglong2*>(s_rows + (u / (ITEMS / 2)) * ROW + (u % (ITEMS / 2)) * 16) = v[j];
     }
     __syncthreads();
     const unsigned char* row = s_rows + threadIdx.x * ROW;
