@@ -969,7 +969,8 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
                          unsigned long long cap,
                          unsigned long long* __restrict__ st_tot /* zeroed */,
                          unsigned long long* __restrict__ st_cnt /* zeroed */,
-                         unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts) {
+                         unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts,
+                         int dbg /* experiments only (GPC_DENSE_DBG): results are wrong when set */) {
     constexpr int ITEMS = 16;
     constexpr int TILE = DR_THREADS * ITEMS;
     constexpr int ROW = ITEMS * 8 + 16;
@@ -979,7 +980,7 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     __shared__ long long s_scan64[66];
     __shared__ unsigned s_slot;
     __shared__ unsigned long long s_base[2];
-    const unsigned tile = claim_tile(ticket, &s_slot);
+    const unsigned tile = (dbg & 4) ? blockIdx.x : claim_tile(ticket, &s_slot);
     const unsigned tile_base = tile * TILE;
     // all loads of the tile first, then the zeroes: written as load / test / store per unit
     // the compiler kept that order (the stores go to the array the next load reads), i.e.
@@ -994,11 +995,12 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
 #pragma unroll
     for (int j = 0; j < ITEMS / 2; ++j) {
         const unsigned u = j * DR_THREADS + threadIdx.x;
-        if (v[j].x | v[j].y)
+        if ((v[j].x | v[j].y) && !(dbg & 8))
             *reinterpret_cast<ulonglong2*>(dense + tile_base + 2 * u) = make_ulonglong2(0ull, 0ull);
         *reinterpret_cast<ulonglong2*>(s_rows + (u / (ITEMS / 2)) * ROW + (u % (ITEMS / 2)) * 16) = v[j];
     }
     __syncthreads();
+    if (dbg & 16) return;                                        // load + zero only
     const unsigned char* row = s_rows + threadIdx.x * ROW;
     const unsigned local = threadIdx.x * ITEMS;                  // first position of this thread in the tile
     // first pass: packed sum of the 16 words, one bit per word and track with a non-zero step
@@ -1019,7 +1021,9 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     long long ex_tot, ex_cnt, tile_tot, tile_cnt;
     block_excl_sum2((long long)wsum, ((long long)__popc(mf) << 31) | (long long)__popc(md), s_scan64,
                     ex_tot, ex_cnt, tile_tot, tile_cnt);
-    if (threadIdx.x < 32) {
+    if (dbg & 1) {                                               // no look-back: every tile starts at zero
+        if (threadIdx.x == 0) { s_base[0] = 0; s_base[1] = (unsigned long long)tile * (2ull << 31 | 2ull) * 600; }
+    } else if (threadIdx.x < 32) {
         unsigned long long ex = lookback_excl_warp(st_tot, tile, (unsigned long long)tile_tot & LB_MASK);
         if (threadIdx.x == 0) s_base[0] = ex;
     } else if (threadIdx.x < 64) {
@@ -1047,6 +1051,7 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     unsigned r0 = (unsigned)((unsigned long long)ex_cnt >> 31);                      // rank inside the tile
     unsigned r1 = (unsigned)((unsigned long long)ex_cnt & 0x7fffffffull);
     unsigned m = mf | md;
+    if (dbg & 2) return;                                         // no emission pass
     if (staged) {
         while (m) {
             const int k = __ffs(m) - 1;
@@ -1747,9 +1752,10 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM));
                 configured4 = true;
             }
+            static const int dbg = getenv("GPC_DENSE_DBG") ? atoi(getenv("GPC_DENSE_DBG")) : 0;
             dense_runs_staged_kernel<<<tiles, DR_THREADS, DS_SMEM, stream>>>(
                 dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt,
-                ticket, counts);
+                ticket, counts, dbg);
         } else {
             dense_runs_block_kernel<16><<<tiles, DR_THREADS, DR_THREADS * (16 * 8 + 16), stream>>>(
                 dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt,
