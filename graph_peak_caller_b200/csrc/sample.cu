@@ -962,6 +962,85 @@ __device__ __forceinline__ void block_excl_sum2(long long a, long long b, long l
     tot_b = s[65];
 }
 
+// ---- reduce, then scan: no chained scan at all ------------------------------------------
+//
+// With its parts switched off one at a time (GPC_DENSE_DBG, chr22-scale array, 13 100 tiles)
+// the single-pass kernel below takes 0.36 ms complete, 0.20 ms without the look-back, 0.19 ms
+// for loads and zeroes alone and 0.08 ms for the loads alone (5.5 TB/s): the chained scan --
+// every tile waiting for the aggregates of the tiles before it, ~600 of them in flight -- is
+// 45 % of it (ncu: 38 % of all stall samples on the barrier behind the look-back), however
+// many predecessors a round trip inspects.  Reading the array twice is cheaper than that:
+//   dense_tile_sums   one streaming read (no stores, no barrier before the loads are all in
+//                     flight): packed sum and entry counts of every tile
+//   dense_tile_scan   one block: exclusive prefixes over the ~10^4 tiles (+ the run counts)
+//   dense_runs        the kernel below with the prefixes handed in: tiles are independent
+// 0.08 + 0.01 + 0.20 ms.
+__global__ void __launch_bounds__(DR_THREADS)
+dense_tile_sums_kernel(const unsigned long long* __restrict__ dense, unsigned long long* __restrict__ sums /* [2][tiles] */) {
+    constexpr int ITEMS = 16;
+    constexpr int TILE = DR_THREADS * ITEMS;
+    __shared__ unsigned long long s_red[2][DR_THREADS / 32];
+    const unsigned tile = blockIdx.x, tile_base = tile * TILE;
+    ulonglong2 v[ITEMS / 2];
+#pragma unroll
+    for (int j = 0; j < ITEMS / 2; ++j)
+        v[j] = *reinterpret_cast<const ulonglong2*>(dense + tile_base + 2 * (j * DR_THREADS + threadIdx.x));
+    unsigned long long wsum = 0ull;
+    unsigned cf = 0, cd = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS / 2; ++j) {
+        wsum += v[j].x + v[j].y;
+        const unsigned lx = (unsigned)v[j].x, ly = (unsigned)v[j].y;
+        cd += (lx != 0u) + (ly != 0u);
+        cf += ((unsigned)(v[j].x >> 32) + (lx >> 31) != 0u) + ((unsigned)(v[j].y >> 32) + (ly >> 31) != 0u);
+    }
+    if (tile == 0 && threadIdx.x == 0) {            // position 0 always carries an entry
+        const unsigned lx = (unsigned)v[0].x;
+        cd += (lx == 0u);
+        cf += ((unsigned)(v[0].x >> 32) + (lx >> 31) == 0u);
+    }
+    unsigned long long cnt = ((unsigned long long)cf << 31) | cd;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        wsum += __shfl_xor_sync(FULL, wsum, d);
+        cnt += __shfl_xor_sync(FULL, cnt, d);
+    }
+    if (lane_id() == 0) { s_red[0][warp_id()] = wsum; s_red[1][warp_id()] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long a = 0, b = 0;
+#pragma unroll
+        for (int w = 0; w < DR_THREADS / 32; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
+        sums[tile] = a;
+        sums[gridDim.x + tile] = b;
+    }
+}
+
+// in place: sums -> exclusive prefixes (both rows); out_counts[0 / 1] = entries per track
+__global__ void __launch_bounds__(1024)
+dense_tile_scan_kernel(unsigned long long* __restrict__ sums, unsigned tiles,
+                       unsigned long long* __restrict__ out_counts) {
+    __shared__ long long s_scan64[66];
+    const unsigned per = (tiles + 1023) / 1024;
+    const unsigned lo = min(tiles, threadIdx.x * per), hi = min(tiles, lo + per);
+    unsigned long long a = 0, b = 0;
+    for (unsigned i = lo; i < hi; ++i) { a += sums[i]; b += sums[tiles + i]; }
+    long long ex_a, ex_b, tot_a, tot_b;
+    block_excl_sum2((long long)a, (long long)b, s_scan64, ex_a, ex_b, tot_a, tot_b);
+    unsigned long long ra = (unsigned long long)ex_a, rb = (unsigned long long)ex_b;
+    for (unsigned i = lo; i < hi; ++i) {
+        const unsigned long long ta = sums[i], tb = sums[tiles + i];
+        sums[i] = ra & LB_MASK;                       // (the emission kernel sign-extends 62 bits)
+        sums[tiles + i] = rb;
+        ra += ta;
+        rb += tb;
+    }
+    if (threadIdx.x == 0) {
+        out_counts[0] = (unsigned long long)tot_b >> 31;
+        out_counts[1] = (unsigned long long)tot_b & 0x7fffffffull;
+    }
+}
+
 __global__ void __launch_bounds__(DR_THREADS, 4)
 dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
                          uint32_t* __restrict__ frag_idx, int32_t* __restrict__ frag_val,
@@ -970,6 +1049,8 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
                          unsigned long long* __restrict__ st_tot /* zeroed */,
                          unsigned long long* __restrict__ st_cnt /* zeroed */,
                          unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts,
+                         const unsigned long long* __restrict__ tile_base_in /* [2][tiles] exclusive tile
+                             prefixes from dense_tile_scan_kernel, or NULL: chained scan in here */,
                          int dbg /* experiments only (GPC_DENSE_DBG): results are wrong when set */) {
     constexpr int ITEMS = 16;
     constexpr int TILE = DR_THREADS * ITEMS;
@@ -980,7 +1061,7 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     __shared__ long long s_scan64[66];
     __shared__ unsigned s_slot;
     __shared__ unsigned long long s_base[2];
-    const unsigned tile = (dbg & 4) ? blockIdx.x : claim_tile(ticket, &s_slot);
+    const unsigned tile = (tile_base_in || (dbg & 4)) ? blockIdx.x : claim_tile(ticket, &s_slot);
     const unsigned tile_base = tile * TILE;
     // all loads of the tile first, then the zeroes: written as load / test / store per unit
     // the compiler kept that order (the stores go to the array the next load reads), i.e.
@@ -1021,7 +1102,12 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     long long ex_tot, ex_cnt, tile_tot, tile_cnt;
     block_excl_sum2((long long)wsum, ((long long)__popc(mf) << 31) | (long long)__popc(md), s_scan64,
                     ex_tot, ex_cnt, tile_tot, tile_cnt);
-    if (dbg & 1) {                                               // no look-back: every tile starts at zero
+    if (tile_base_in) {                                          // prefixes over the tiles are known
+        if (threadIdx.x == 0) {
+            s_base[0] = tile_base_in[tile];
+            s_base[1] = tile_base_in[gridDim.x + tile];
+        }
+    } else if (dbg & 1) {                                        // no look-back: every tile starts at zero
         if (threadIdx.x == 0) { s_base[0] = 0; s_base[1] = (unsigned long long)tile * (2ull << 31 | 2ull) * 600; }
     } else if (threadIdx.x < 32) {
         unsigned long long ex = lookback_excl_warp(st_tot, tile, (unsigned long long)tile_tot & LB_MASK);
@@ -1674,10 +1760,11 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
     // ---- difference array ------------------------------------------------------------
     GPC_CUDA(cudaMemsetAsync(touched, 0, graph->n_nodes, stream));
     const unsigned n_pos = graph->size_bp + 1;           // a fragment may close at size_bp
-    // scan variant: 0 = one 4096-position tile per block, entries staged through shared memory
-    // and written coalesced (default); 1 = the same with every thread writing its own entries
-    // (the first version); 3 = persistent blocks, tiles moved by the bulk-copy engine, three in
-    // flight (measured slower, kept as the reference point for it)
+    // scan variant: 0 = tile sums, their scan, then independent 4096-position tiles with the
+    // entries staged through shared memory (default); 2 = the same tiles in ONE pass with a
+    // chained scan; 1 = single pass, every thread writing its own entries (the first version);
+    // 3 = persistent blocks, tiles moved by the bulk-copy engine, three in flight (measured
+    // slower, kept as the reference point for it)
     static const int variant = getenv("GPC_DENSE_SCAN") ? atoi(getenv("GPC_DENSE_SCAN")) : 0;
     const unsigned tile_size = DR_THREADS * 16;
     const unsigned tiles = div_up(n_pos, tile_size);
@@ -1723,8 +1810,8 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
                 *graph, *reads, read_index, (unsigned)n_reads, extension, nullptr, 0, n_steps, dense,
                 touched, err, spill.pool);
         GPC_LAUNCH_CHECK();
-        GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
         if (variant == 3) {
+            GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
             static bool configured3 = false;
             if (!configured3) {
                 GPC_CUDA(cudaFuncSetAttribute(dense_runs_pipelined_kernel,
@@ -1753,10 +1840,22 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
                 configured4 = true;
             }
             static const int dbg = getenv("GPC_DENSE_DBG") ? atoi(getenv("GPC_DENSE_DBG")) : 0;
+            const unsigned long long* bases = nullptr;
+            if (variant != 2) {          // reduce, then scan (st_tot / st_cnt are one [2][tiles] array)
+                GPC_PROF_BYTES("dense_tile_sums", 8.0 * n_pos);
+                dense_tile_sums_kernel<<<tiles, DR_THREADS, 0, stream>>>(dense, st_tot);
+                GPC_LAUNCH_CHECK();
+                GPC_PROF("dense_tile_scan");
+                dense_tile_scan_kernel<<<1, 1024, 0, stream>>>(st_tot, tiles, counts);
+                GPC_LAUNCH_CHECK();
+                bases = st_tot;
+            }
+            GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
             dense_runs_staged_kernel<<<tiles, DR_THREADS, DS_SMEM, stream>>>(
                 dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt,
-                ticket, counts, dbg);
+                ticket, counts, bases, dbg);
         } else {
+            GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
             dense_runs_block_kernel<16><<<tiles, DR_THREADS, DR_THREADS * (16 * 8 + 16), stream>>>(
                 dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt,
                 ticket, counts);
