@@ -79,6 +79,48 @@ __device__ __forceinline__ void store_running(uint32_t* __restrict__ out, unsign
     }
 }
 
+// ---- reduce, then scan ------------------------------------------------------------------
+// The chained scans above make every tile wait for the tiles before it; with several hundred
+// tiles in flight that wait was 45 % of the difference-array scan (measured with the look-back
+// switched off, csrc/sample.cu) and the top stall of every compaction (barrier 35-42 warps per
+// issue).  Above RTS_MIN_ITEMS items the drivers below therefore run three launches instead:
+// per-tile totals (one more read of the input), one block turning them into exclusive
+// prefixes, and the scan / compaction kernel with its prefix handed in -- tiles independent.
+constexpr size_t RTS_MIN_ITEMS = 1u << 19;
+
+// in place: tile totals -> exclusive prefixes; *total = their sum.  One block.
+static __global__ void __launch_bounds__(1024)
+tile_prefix_kernel(unsigned long long* __restrict__ sums, unsigned tiles, unsigned long long* __restrict__ total) {
+    __shared__ unsigned long long s_warp[33];
+    unsigned long long carry = 0;
+    for (unsigned base = 0; base < tiles; base += 1024 * 4) {
+        // four consecutive items per thread (coalesced enough: 32 bytes per thread)
+        const unsigned i0 = base + threadIdx.x * 4;
+        unsigned long long v[4], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[j] = i0 + j < tiles ? sums[i0 + j] : 0ull; sum += v[j]; }
+        unsigned long long incl = warp_incl_sum(sum);
+        if (lane_id() == 31) s_warp[warp_id()] = incl;
+        __syncthreads();
+        if (warp_id() == 0) {
+            const unsigned long long x = s_warp[lane_id()];
+            const unsigned long long xi = warp_incl_sum(x);
+            s_warp[lane_id()] = xi - x;
+            if (lane_id() == 31) s_warp[32] = xi;
+        }
+        __syncthreads();
+        unsigned long long run = carry + s_warp[warp_id()] + incl - sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j < tiles) sums[i0 + j] = run;
+            run += v[j];
+        }
+        carry += s_warp[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
 // out[i] = sum_{j<i} in[j]  (uint32 in, uint64 running sum stored as uint32:
 // callers guarantee the total fits).  total[0] receives the grand total.
 // Sixteen items per thread in 16-byte accesses: eight scalar loads at a stride of eight
@@ -90,13 +132,39 @@ constexpr int ES_TILE = SC_THREADS * ES_ITEMS;
 
 template <typename InT>
 __global__ void __launch_bounds__(SC_THREADS)
+excl_scan_sums_kernel(const InT* __restrict__ in, unsigned n, unsigned long long* __restrict__ sums) {
+    __shared__ unsigned s_red[SC_THREADS / 32];
+    const unsigned base = blockIdx.x * ES_TILE + threadIdx.x * ES_ITEMS;
+    unsigned v[ES_ITEMS], sum = 0;
+    if (sizeof(InT) == 4)
+        load_items_u32<ES_ITEMS>(reinterpret_cast<const uint32_t*>(in), base, n, v);
+    else
+        load_items_u8<ES_ITEMS>(reinterpret_cast<const uint8_t*>(in), base, n, v);
+#pragma unroll
+    for (int j = 0; j < ES_ITEMS; ++j) sum += v[j];
+    sum = warp_sum(sum);
+    if (lane_id() == 0) s_red[warp_id()] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < SC_THREADS / 32; ++w) t += s_red[w];
+        sums[blockIdx.x] = t;
+    }
+}
+
+// tile_prefix == NULL: chained scan over the tiles (status, ticket); else the exclusive
+// prefix of every tile is handed in and the tiles are independent
+template <typename InT>
+__global__ void __launch_bounds__(SC_THREADS)
 excl_scan_kernel(const InT* __restrict__ in, uint32_t* __restrict__ out, unsigned n,
                  unsigned long long* __restrict__ status, unsigned* __restrict__ ticket,
-                 unsigned long long* __restrict__ total) {
+                 unsigned long long* __restrict__ total,
+                 const unsigned long long* __restrict__ tile_prefix = nullptr) {
     __shared__ unsigned s_scan[33];
     __shared__ unsigned s_slot;
     __shared__ unsigned long long s_prefix;
-    const unsigned tile = claim_tile(ticket, &s_slot);
+    const unsigned tile = tile_prefix ? blockIdx.x : claim_tile(ticket, &s_slot);
     const unsigned base = tile * ES_TILE + threadIdx.x * ES_ITEMS;
     unsigned v[ES_ITEMS];
     unsigned sum = 0;
@@ -108,6 +176,10 @@ excl_scan_kernel(const InT* __restrict__ in, uint32_t* __restrict__ out, unsigne
     for (int j = 0; j < ES_ITEMS; ++j) sum += v[j];
     unsigned tile_total;
     unsigned ex = block_excl_sum<unsigned>(sum, s_scan, tile_total);
+    if (tile_prefix) {
+        store_running<ES_ITEMS>(out, base, n, (unsigned)tile_prefix[tile] + ex, v);
+        return;
+    }
     if (threadIdx.x < 32) {
         unsigned long long p = lookback_excl_warp(status, tile, tile_total);
         if (threadIdx.x == 0) {
@@ -134,6 +206,19 @@ int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* t
     GPC_CUDA(cudaMemsetAsync(sc.p, 0, (size_t)tiles * 8 + 16, stream));
     unsigned long long* status = sc.as<unsigned long long>() + 2;
     unsigned* ticket = sc.as<unsigned>();
+    if (n >= RTS_MIN_ITEMS) {
+        GPC_PROF_BYTES("excl_scan_sums", (double)n * sizeof(InT));
+        excl_scan_sums_kernel<InT><<<tiles, SC_THREADS, 0, stream>>>(in, (unsigned)n, status);
+        GPC_LAUNCH_CHECK();
+        GPC_PROF("tile_prefix");
+        tile_prefix_kernel<<<1, 1024, 0, stream>>>(status, tiles, total_dev);
+        GPC_LAUNCH_CHECK();
+        GPC_PROF_BYTES("excl_scan", (double)n * (sizeof(InT) + 4));
+        excl_scan_kernel<InT><<<tiles, SC_THREADS, 0, stream>>>(in, out, (unsigned)n, nullptr, nullptr,
+                                                                nullptr, status);
+        GPC_LAUNCH_CHECK();
+        return GPC_OK;
+    }
     GPC_PROF_BYTES("excl_scan", (double)n * (sizeof(InT) + 4));
     excl_scan_kernel<InT><<<tiles, SC_THREADS, 0, stream>>>(in, out, (unsigned)n, status, ticket, total_dev);
     GPC_LAUNCH_CHECK();
@@ -146,16 +231,43 @@ int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* t
 // receives the number kept.
 template <typename Op>
 __global__ void __launch_bounds__(SC_THREADS)
+select_count_kernel(Op op, unsigned n_max, const unsigned long long* __restrict__ n_dev,
+                    unsigned long long* __restrict__ counts) {
+    __shared__ unsigned s_red[SC_THREADS / 32];
+    const unsigned n = n_dev ? (unsigned)min((unsigned long long)n_max, *n_dev) : n_max;
+    const unsigned base = blockIdx.x * SC_TILE + threadIdx.x;
+    unsigned c = 0;
+#pragma unroll
+    for (int j = 0; j < SC_ITEMS; ++j) {
+        const unsigned i = base + j * SC_THREADS;
+        c += (i < n && op.keep(i)) ? 1u : 0u;
+    }
+    c = warp_sum(c);
+    if (lane_id() == 0) s_red[warp_id()] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+#pragma unroll
+        for (int w = 0; w < SC_THREADS / 32; ++w) t += s_red[w];
+        counts[blockIdx.x] = t;
+    }
+}
+
+// tile_prefix == NULL: chained scan over the tiles (status, ticket); else the number of
+// items kept before every tile is handed in and the tiles are independent
+template <typename Op>
+__global__ void __launch_bounds__(SC_THREADS)
 select_kernel(Op op, unsigned n_max, const unsigned long long* __restrict__ n_dev,
               unsigned long long* __restrict__ status, unsigned* __restrict__ ticket,
-              unsigned long long* __restrict__ total) {
+              unsigned long long* __restrict__ total,
+              const unsigned long long* __restrict__ tile_prefix = nullptr) {
     // striped items (row j of the tile = 256 consecutive items, one per thread):
     // loads and stores of a warp are contiguous; ranks come from ballots
     constexpr int WARPS = SC_THREADS / 32;
     __shared__ unsigned s_cnt[SC_ITEMS * WARPS + 1];
     __shared__ unsigned s_slot;
     __shared__ unsigned long long s_prefix;
-    const unsigned tile = claim_tile(ticket, &s_slot);
+    const unsigned tile = tile_prefix ? blockIdx.x : claim_tile(ticket, &s_slot);
     // the item count may still sit in device memory (produced by the previous kernel)
     const unsigned n = n_dev ? (unsigned)min((unsigned long long)n_max, *n_dev) : n_max;
     if ((unsigned long long)tile * SC_TILE >= n) return;       // (whole block, nobody waits on it)
@@ -180,7 +292,8 @@ select_kernel(Op op, unsigned n_max, const unsigned long long* __restrict__ n_de
         unsigned tile_total = __shfl_sync(0xffffffffu, incl, 31);
         s_cnt[2 * lane] = incl - a0 - a1;
         s_cnt[2 * lane + 1] = incl - a1;
-        unsigned long long p = lookback_excl_warp(status, tile, (unsigned long long)tile_total);
+        unsigned long long p = tile_prefix ? tile_prefix[tile]
+                                           : lookback_excl_warp(status, tile, (unsigned long long)tile_total);
         if (lane == 0) {
             s_prefix = p;
             if (tile == last_tile) {
@@ -211,6 +324,20 @@ int select_if(const char* name, Op op, size_t n, unsigned long long* total_dev, 
     GPC_CUDA(cudaMemsetAsync(sc.p, 0, (size_t)tiles * 8 + 16, stream));
     unsigned long long* status = sc.as<unsigned long long>() + 2;
     unsigned* ticket = sc.as<unsigned>();
+    if (n >= RTS_MIN_ITEMS) {
+        // (tiles beyond a device-side item count contribute zero and leave at once)
+        GPC_PROF("select_count");
+        select_count_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, n_dev, status);
+        GPC_LAUNCH_CHECK();
+        GPC_PROF("tile_prefix");
+        tile_prefix_kernel<<<1, 1024, 0, stream>>>(status, tiles, nullptr);
+        GPC_LAUNCH_CHECK();
+        GPC_PROF(name);
+        select_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, n_dev, nullptr, nullptr,
+                                                            total_dev, status);
+        GPC_LAUNCH_CHECK();
+        return GPC_OK;
+    }
     GPC_PROF(name);
     select_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, n_dev, status, ticket,
                                                         total_dev);
