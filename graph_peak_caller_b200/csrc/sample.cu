@@ -971,15 +971,19 @@ __device__ __forceinline__ void block_excl_sum2(long long a, long long b, long l
 // 45 % of it (ncu: 38 % of all stall samples on the barrier behind the look-back), however
 // many predecessors a round trip inspects.  Reading the array twice is cheaper than that:
 //   dense_tile_sums   one streaming read (no stores, no barrier before the loads are all in
-//                     flight): packed sum and entry counts of every tile
-//   dense_tile_scan   one block: exclusive prefixes over the ~10^4 tiles (+ the run counts)
+//                     flight): packed sum and entry counts of every tile; its last block
+//                     turns them into exclusive prefixes over the ~10^4 tiles (+ the run counts)
 //   dense_runs        the kernel below with the prefixes handed in: tiles are independent
-// 0.08 + 0.01 + 0.20 ms.
+// 0.08 + 0.22 ms.
 __global__ void __launch_bounds__(DR_THREADS)
-dense_tile_sums_kernel(const unsigned long long* __restrict__ dense, unsigned long long* __restrict__ sums /* [2][tiles] */) {
+dense_tile_sums_kernel(const unsigned long long* __restrict__ dense, unsigned long long* sums /* [2][tiles] */,
+                       unsigned* __restrict__ done /* zeroed */, unsigned long long* __restrict__ out_counts) {
     constexpr int ITEMS = 16;
     constexpr int TILE = DR_THREADS * ITEMS;
     __shared__ unsigned long long s_red[2][DR_THREADS / 32];
+    __shared__ unsigned long long s_warp[33];
+    __shared__ unsigned long long s_total;
+    __shared__ unsigned s_flag;
     const unsigned tile = blockIdx.x, tile_base = tile * TILE;
     ulonglong2 v[ITEMS / 2];
 #pragma unroll
@@ -1014,30 +1018,16 @@ dense_tile_sums_kernel(const unsigned long long* __restrict__ dense, unsigned lo
         sums[tile] = a;
         sums[gridDim.x + tile] = b;
     }
-}
-
-// in place: sums -> exclusive prefixes (both rows); out_counts[0 / 1] = entries per track
-__global__ void __launch_bounds__(1024)
-dense_tile_scan_kernel(unsigned long long* __restrict__ sums, unsigned tiles,
-                       unsigned long long* __restrict__ out_counts) {
-    __shared__ long long s_scan64[66];
-    const unsigned per = (tiles + 1023) / 1024;
-    const unsigned lo = min(tiles, threadIdx.x * per), hi = min(tiles, lo + per);
-    unsigned long long a = 0, b = 0;
-    for (unsigned i = lo; i < hi; ++i) { a += sums[i]; b += sums[tiles + i]; }
-    long long ex_a, ex_b, tot_a, tot_b;
-    block_excl_sum2((long long)a, (long long)b, s_scan64, ex_a, ex_b, tot_a, tot_b);
-    unsigned long long ra = (unsigned long long)ex_a, rb = (unsigned long long)ex_b;
-    for (unsigned i = lo; i < hi; ++i) {
-        const unsigned long long ta = sums[i], tb = sums[tiles + i];
-        sums[i] = ra & LB_MASK;                       // (the emission kernel sign-extends 62 bits)
-        sums[tiles + i] = rb;
-        ra += ta;
-        rb += tb;
-    }
-    if (threadIdx.x == 0) {
-        out_counts[0] = (unsigned long long)tot_b >> 31;
-        out_counts[1] = (unsigned long long)tot_b & 0x7fffffffull;
+    // the block that finishes last turns the totals into exclusive prefixes (both rows; the
+    // running-sum row is a packed sum modulo 2^64, the emission kernel sign-extends 62 bits)
+    if (last_block_done(done, &s_flag)) {
+        tile_prefix_block(sums, gridDim.x, nullptr, s_warp);
+        tile_prefix_block(sums + gridDim.x, gridDim.x, &s_total, s_warp);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            out_counts[0] = s_total >> 31;
+            out_counts[1] = s_total & 0x7fffffffull;
+        }
     }
 }
 
@@ -1843,10 +1833,7 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
             const unsigned long long* bases = nullptr;
             if (variant != 2) {          // reduce, then scan (st_tot / st_cnt are one [2][tiles] array)
                 GPC_PROF_BYTES("dense_tile_sums", 8.0 * n_pos);
-                dense_tile_sums_kernel<<<tiles, DR_THREADS, 0, stream>>>(dense, st_tot);
-                GPC_LAUNCH_CHECK();
-                GPC_PROF("dense_tile_scan");
-                dense_tile_scan_kernel<<<1, 1024, 0, stream>>>(st_tot, tiles, counts);
+                dense_tile_sums_kernel<<<tiles, DR_THREADS, 0, stream>>>(dense, st_tot, ticket, counts);
                 GPC_LAUNCH_CHECK();
                 bases = st_tot;
             }

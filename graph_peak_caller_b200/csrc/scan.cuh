@@ -83,27 +83,31 @@ __device__ __forceinline__ void store_running(uint32_t* __restrict__ out, unsign
 // The chained scans above make every tile wait for the tiles before it; with several hundred
 // tiles in flight that wait was 45 % of the difference-array scan (measured with the look-back
 // switched off, csrc/sample.cu) and the top stall of every compaction (barrier 35-42 warps per
-// issue).  Above RTS_MIN_ITEMS items the drivers below therefore run three launches instead:
-// per-tile totals (one more read of the input), one block turning them into exclusive
+// issue).  Above RTS_MIN_ITEMS items the drivers below therefore run two launches instead:
+// per-tile totals (one more read of the input) whose last block turns them into exclusive
 // prefixes, and the scan / compaction kernel with its prefix handed in -- tiles independent.
-constexpr size_t RTS_MIN_ITEMS = 1u << 19;
+constexpr size_t RTS_MIN_ITEMS = 1u << 20;
 
-// in place: tile totals -> exclusive prefixes; *total = their sum.  One block.
-static __global__ void __launch_bounds__(1024)
-tile_prefix_kernel(unsigned long long* __restrict__ sums, unsigned tiles, unsigned long long* __restrict__ total) {
-    __shared__ unsigned long long s_warp[33];
+// in place: tile totals -> exclusive prefixes; *total = their sum.  Run by ONE block (any
+// size that is a multiple of 32, at most 1024 threads): the block of the totals kernel that
+// finishes last (tile_prefix_by_last_block), so the prefixes cost no launch of their own.
+__device__ __forceinline__ void tile_prefix_block(unsigned long long* sums, unsigned tiles,
+                                                  unsigned long long* total, unsigned long long* s_warp /* [33] */) {
+    const unsigned nw = blockDim.x >> 5;
     unsigned long long carry = 0;
-    for (unsigned base = 0; base < tiles; base += 1024 * 4) {
-        // four consecutive items per thread (coalesced enough: 32 bytes per thread)
-        const unsigned i0 = base + threadIdx.x * 4;
+    for (unsigned base = 0; base < tiles; base += blockDim.x * 4) {
+        const unsigned i0 = base + threadIdx.x * 4;        // four consecutive items per thread
         unsigned long long v[4], sum = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { v[j] = i0 + j < tiles ? sums[i0 + j] : 0ull; sum += v[j]; }
+        for (int j = 0; j < 4; ++j) {
+            v[j] = i0 + j < tiles ? *reinterpret_cast<volatile unsigned long long*>(sums + i0 + j) : 0ull;
+            sum += v[j];
+        }
         unsigned long long incl = warp_incl_sum(sum);
         if (lane_id() == 31) s_warp[warp_id()] = incl;
         __syncthreads();
         if (warp_id() == 0) {
-            const unsigned long long x = s_warp[lane_id()];
+            const unsigned long long x = lane_id() < nw ? s_warp[lane_id()] : 0ull;
             const unsigned long long xi = warp_incl_sum(x);
             s_warp[lane_id()] = xi - x;
             if (lane_id() == 31) s_warp[32] = xi;
@@ -120,6 +124,18 @@ tile_prefix_kernel(unsigned long long* __restrict__ sums, unsigned tiles, unsign
     }
     if (threadIdx.x == 0 && total) *total = carry;
 }
+// Every block calls this after thread 0 has written its tile total: true for the block that
+// arrives last (the totals of all blocks are visible to it).  *done must start at zero.
+__device__ __forceinline__ bool last_block_done(unsigned* done, unsigned* s_flag) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        *s_flag = atomicAdd(done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    const bool last = *s_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
 
 // out[i] = sum_{j<i} in[j]  (uint32 in, uint64 running sum stored as uint32:
 // callers guarantee the total fits).  total[0] receives the grand total.
@@ -132,8 +148,11 @@ constexpr int ES_TILE = SC_THREADS * ES_ITEMS;
 
 template <typename InT>
 __global__ void __launch_bounds__(SC_THREADS)
-excl_scan_sums_kernel(const InT* __restrict__ in, unsigned n, unsigned long long* __restrict__ sums) {
+excl_scan_sums_kernel(const InT* __restrict__ in, unsigned n, unsigned long long* sums,
+                      unsigned* __restrict__ done /* zeroed */, unsigned long long* __restrict__ total) {
     __shared__ unsigned s_red[SC_THREADS / 32];
+    __shared__ unsigned long long s_warp[33];
+    __shared__ unsigned s_flag;
     const unsigned base = blockIdx.x * ES_TILE + threadIdx.x * ES_ITEMS;
     unsigned v[ES_ITEMS], sum = 0;
     if (sizeof(InT) == 4)
@@ -151,6 +170,7 @@ excl_scan_sums_kernel(const InT* __restrict__ in, unsigned n, unsigned long long
         for (int w = 0; w < SC_THREADS / 32; ++w) t += s_red[w];
         sums[blockIdx.x] = t;
     }
+    if (last_block_done(done, &s_flag)) tile_prefix_block(sums, gridDim.x, total, s_warp);
 }
 
 // tile_prefix == NULL: chained scan over the tiles (status, ticket); else the exclusive
@@ -208,10 +228,7 @@ int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* t
     unsigned* ticket = sc.as<unsigned>();
     if (n >= RTS_MIN_ITEMS) {
         GPC_PROF_BYTES("excl_scan_sums", (double)n * sizeof(InT));
-        excl_scan_sums_kernel<InT><<<tiles, SC_THREADS, 0, stream>>>(in, (unsigned)n, status);
-        GPC_LAUNCH_CHECK();
-        GPC_PROF("tile_prefix");
-        tile_prefix_kernel<<<1, 1024, 0, stream>>>(status, tiles, total_dev);
+        excl_scan_sums_kernel<InT><<<tiles, SC_THREADS, 0, stream>>>(in, (unsigned)n, status, ticket, total_dev);
         GPC_LAUNCH_CHECK();
         GPC_PROF_BYTES("excl_scan", (double)n * (sizeof(InT) + 4));
         excl_scan_kernel<InT><<<tiles, SC_THREADS, 0, stream>>>(in, out, (unsigned)n, nullptr, nullptr,
@@ -232,8 +249,10 @@ int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* t
 template <typename Op>
 __global__ void __launch_bounds__(SC_THREADS)
 select_count_kernel(Op op, unsigned n_max, const unsigned long long* __restrict__ n_dev,
-                    unsigned long long* __restrict__ counts) {
+                    unsigned long long* counts, unsigned* __restrict__ done /* zeroed */) {
     __shared__ unsigned s_red[SC_THREADS / 32];
+    __shared__ unsigned long long s_warp[33];
+    __shared__ unsigned s_flag;
     const unsigned n = n_dev ? (unsigned)min((unsigned long long)n_max, *n_dev) : n_max;
     const unsigned base = blockIdx.x * SC_TILE + threadIdx.x;
     unsigned c = 0;
@@ -251,6 +270,7 @@ select_count_kernel(Op op, unsigned n_max, const unsigned long long* __restrict_
         for (int w = 0; w < SC_THREADS / 32; ++w) t += s_red[w];
         counts[blockIdx.x] = t;
     }
+    if (last_block_done(done, &s_flag)) tile_prefix_block(counts, gridDim.x, nullptr, s_warp);
 }
 
 // tile_prefix == NULL: chained scan over the tiles (status, ticket); else the number of
@@ -327,10 +347,7 @@ int select_if(const char* name, Op op, size_t n, unsigned long long* total_dev, 
     if (n >= RTS_MIN_ITEMS) {
         // (tiles beyond a device-side item count contribute zero and leave at once)
         GPC_PROF("select_count");
-        select_count_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, n_dev, status);
-        GPC_LAUNCH_CHECK();
-        GPC_PROF("tile_prefix");
-        tile_prefix_kernel<<<1, 1024, 0, stream>>>(status, tiles, nullptr);
+        select_count_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, n_dev, status, ticket);
         GPC_LAUNCH_CHECK();
         GPC_PROF(name);
         select_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, n_dev, nullptr, nullptr,
