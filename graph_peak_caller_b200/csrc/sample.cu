@@ -1485,7 +1485,7 @@ extern "C" int gpc_unique_reads(const int32_t* start_node, const int32_t* start_
                                                    slot.as<unsigned>());
     GPC_LAUNCH_CHECK();
     GPC_TRY(select_if("dedup_select", DedupOp{first.as<unsigned>(), slot.as<unsigned>(), out_index}, n,
-                      total.as<unsigned long long>(), stream));
+                      total.as<unsigned long long>(), stream, nullptr, /*keep_is_cheap=*/false));
     unsigned long long h = 0;
     GPC_READ_BACK({total.p, &h, (unsigned)(8)});
     *out_count = h;

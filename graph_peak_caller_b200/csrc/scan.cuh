@@ -93,36 +93,42 @@ constexpr size_t RTS_MIN_ITEMS = 1u << 20;
 // finishes last (tile_prefix_by_last_block), so the prefixes cost no launch of their own.
 __device__ __forceinline__ void tile_prefix_block(unsigned long long* sums, unsigned tiles,
                                                   unsigned long long* total, unsigned long long* s_warp /* [33] */) {
+    // every thread owns a contiguous chunk: its loads are independent (all in flight at once:
+    // the block pays two L2 latencies, not one per 1024 items), one block scan in between
     const unsigned nw = blockDim.x >> 5;
-    unsigned long long carry = 0;
-    for (unsigned base = 0; base < tiles; base += blockDim.x * 4) {
-        const unsigned i0 = base + threadIdx.x * 4;        // four consecutive items per thread
-        unsigned long long v[4], sum = 0;
+    const unsigned per = (tiles + blockDim.x - 1) / blockDim.x;
+    const unsigned lo = min(tiles, threadIdx.x * per), hi = min(tiles, lo + per);
+    unsigned long long sum = 0;
+    for (unsigned i = lo; i < hi; i += 8) {
+        unsigned long long v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            v[j] = i0 + j < tiles ? *reinterpret_cast<volatile unsigned long long*>(sums + i0 + j) : 0ull;
-            sum += v[j];
-        }
-        unsigned long long incl = warp_incl_sum(sum);
-        if (lane_id() == 31) s_warp[warp_id()] = incl;
-        __syncthreads();
-        if (warp_id() == 0) {
-            const unsigned long long x = lane_id() < nw ? s_warp[lane_id()] : 0ull;
-            const unsigned long long xi = warp_incl_sum(x);
-            s_warp[lane_id()] = xi - x;
-            if (lane_id() == 31) s_warp[32] = xi;
-        }
-        __syncthreads();
-        unsigned long long run = carry + s_warp[warp_id()] + incl - sum;
+        for (int j = 0; j < 8; ++j) v[j] = i + j < hi ? __ldcg(sums + i + j) : 0ull;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (i0 + j < tiles) sums[i0 + j] = run;
+        for (int j = 0; j < 8; ++j) sum += v[j];
+    }
+    const unsigned long long incl = warp_incl_sum(sum);
+    if (lane_id() == 31) s_warp[warp_id()] = incl;
+    __syncthreads();
+    if (warp_id() == 0) {
+        const unsigned long long x = lane_id() < nw ? s_warp[lane_id()] : 0ull;
+        const unsigned long long xi = warp_incl_sum(x);
+        s_warp[lane_id()] = xi - x;
+        if (lane_id() == 31) s_warp[32] = xi;
+    }
+    __syncthreads();
+    unsigned long long run = s_warp[warp_id()] + incl - sum;
+    for (unsigned i = lo; i < hi; i += 8) {             // loads of a batch first, then its stores
+        unsigned long long v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = i + j < hi ? __ldcg(sums + i + j) : 0ull;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (i + j < hi) sums[i + j] = run;
             run += v[j];
         }
-        carry += s_warp[32];
-        __syncthreads();
     }
-    if (threadIdx.x == 0 && total) *total = carry;
+    if (threadIdx.x == 0 && total) *total = s_warp[32];
+    __syncthreads();
 }
 // Every block calls this after thread 0 has written its tile total: true for the block that
 // arrives last (the totals of all blocks are visible to it).  *done must start at zero.
@@ -333,7 +339,9 @@ select_kernel(Op op, unsigned n_max, const unsigned long long* __restrict__ n_de
 // n_dev (optional): the real item count, <= n, read by the kernel from device memory.
 template <typename Op>
 int select_if(const char* name, Op op, size_t n, unsigned long long* total_dev, cudaStream_t stream,
-              const unsigned long long* n_dev = nullptr) {
+              const unsigned long long* n_dev = nullptr, bool keep_is_cheap = true) {
+    // keep_is_cheap == false: op.keep() is a dependent gather (the duplicate filter's table
+    // probe); evaluating it twice costs more than the chained scan it would save
     if (n == 0) {
         if (total_dev) GPC_CUDA(cudaMemsetAsync(total_dev, 0, 8, stream));
         return GPC_OK;
@@ -344,7 +352,7 @@ int select_if(const char* name, Op op, size_t n, unsigned long long* total_dev, 
     GPC_CUDA(cudaMemsetAsync(sc.p, 0, (size_t)tiles * 8 + 16, stream));
     unsigned long long* status = sc.as<unsigned long long>() + 2;
     unsigned* ticket = sc.as<unsigned>();
-    if (n >= RTS_MIN_ITEMS) {
+    if (n >= RTS_MIN_ITEMS && keep_is_cheap) {
         // (tiles beyond a device-side item count contribute zero and leave at once)
         GPC_PROF("select_count");
         select_count_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, n_dev, status, ticket);
