@@ -971,19 +971,18 @@ __device__ __forceinline__ void block_excl_sum2(long long a, long long b, long l
 // 45 % of it (ncu: 38 % of all stall samples on the barrier behind the look-back), however
 // many predecessors a round trip inspects.  Reading the array twice is cheaper than that:
 //   dense_tile_sums   one streaming read (no stores, no barrier before the loads are all in
-//                     flight): packed sum and entry counts of every tile; its last block
-//                     turns them into exclusive prefixes over the ~10^4 tiles (+ the run counts)
-//   dense_runs        the kernel below with the prefixes handed in: tiles are independent
+//                     flight): packed sum and entry counts of every tile, and of every
+//                     group of 64 tiles (one atomic per tile)
+//   dense_runs        the kernel below; a tile adds up the groups and the tiles before it
+//                     (<= 270 independent loads spread over the block): tiles are independent
 // 0.08 + 0.22 ms.
 __global__ void __launch_bounds__(DR_THREADS)
-dense_tile_sums_kernel(const unsigned long long* __restrict__ dense, unsigned long long* sums /* [2][tiles] */,
-                       unsigned* __restrict__ done /* zeroed */, unsigned long long* __restrict__ out_counts) {
+dense_tile_sums_kernel(const unsigned long long* __restrict__ dense,
+                       unsigned long long* __restrict__ sums /* [2][tiles] */,
+                       unsigned long long* __restrict__ supers /* [2][groups], zeroed */, unsigned groups) {
     constexpr int ITEMS = 16;
     constexpr int TILE = DR_THREADS * ITEMS;
     __shared__ unsigned long long s_red[2][DR_THREADS / 32];
-    __shared__ unsigned long long s_warp[33];
-    __shared__ unsigned long long s_total;
-    __shared__ unsigned s_flag;
     const unsigned tile = blockIdx.x, tile_base = tile * TILE;
     ulonglong2 v[ITEMS / 2];
 #pragma unroll
@@ -1015,19 +1014,9 @@ dense_tile_sums_kernel(const unsigned long long* __restrict__ dense, unsigned lo
         unsigned long long a = 0, b = 0;
 #pragma unroll
         for (int w = 0; w < DR_THREADS / 32; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
-        sums[tile] = a;
-        sums[gridDim.x + tile] = b;
-    }
-    // the block that finishes last turns the totals into exclusive prefixes (both rows; the
-    // running-sum row is a packed sum modulo 2^64, the emission kernel sign-extends 62 bits)
-    if (last_block_done(done, &s_flag)) {
-        tile_prefix_block(sums, gridDim.x, nullptr, s_warp);
-        tile_prefix_block(sums + gridDim.x, gridDim.x, &s_total, s_warp);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            out_counts[0] = s_total >> 31;
-            out_counts[1] = s_total & 0x7fffffffull;
-        }
+        // two-level totals (scan.cuh): the emission kernel's tiles look their prefix up
+        tile_total_publish(sums, supers, tile, a);
+        tile_total_publish(sums + gridDim.x, supers + groups, tile, b);
     }
 }
 
@@ -1039,8 +1028,9 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
                          unsigned long long* __restrict__ st_tot /* zeroed */,
                          unsigned long long* __restrict__ st_cnt /* zeroed */,
                          unsigned* __restrict__ ticket, unsigned long long* __restrict__ out_counts,
-                         const unsigned long long* __restrict__ tile_base_in /* [2][tiles] exclusive tile
-                             prefixes from dense_tile_scan_kernel, or NULL: chained scan in here */,
+                         const unsigned long long* __restrict__ tile_base_in /* [2][tiles] tile totals of
+                             dense_tile_sums_kernel, or NULL: chained scan in here */,
+                         const unsigned long long* __restrict__ tile_supers /* [2][groups] */, unsigned groups,
                          int dbg /* experiments only (GPC_DENSE_DBG): results are wrong when set */) {
     constexpr int ITEMS = 16;
     constexpr int TILE = DR_THREADS * ITEMS;
@@ -1092,10 +1082,18 @@ dense_runs_staged_kernel(unsigned long long* __restrict__ dense, unsigned n_pos,
     long long ex_tot, ex_cnt, tile_tot, tile_cnt;
     block_excl_sum2((long long)wsum, ((long long)__popc(mf) << 31) | (long long)__popc(md), s_scan64,
                     ex_tot, ex_cnt, tile_tot, tile_cnt);
-    if (tile_base_in) {                                          // prefixes over the tiles are known
+    if (tile_base_in) {                                          // totals of all tiles are known
+        __shared__ unsigned long long s_red[33];
+        const unsigned long long b0 = tile_prefix_lookup(tile_base_in, tile_supers, tile, s_red);
+        const unsigned long long b1 = tile_prefix_lookup(tile_base_in + gridDim.x, tile_supers + groups, tile, s_red);
         if (threadIdx.x == 0) {
-            s_base[0] = tile_base_in[tile];
-            s_base[1] = tile_base_in[gridDim.x + tile];
+            s_base[0] = b0;
+            s_base[1] = b1;
+            if (tile == gridDim.x - 1) {
+                const unsigned long long tot = b1 + (unsigned long long)tile_cnt;
+                out_counts[0] = tot >> 31;
+                out_counts[1] = tot & 0x7fffffffull;
+            }
         }
     } else if (dbg & 1) {                                        // no look-back: every tile starts at zero
         if (threadIdx.x == 0) { s_base[0] = 0; s_base[1] = (unsigned long long)tile * (2ull << 31 | 2ull) * 600; }
@@ -1767,7 +1765,8 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
         DenseWorkspace* ws; cudaStream_t s; bool clean;
         ~Release() { dense_release(ws, clean, s); }
     } rel{ws, stream, false};
-    const size_t bytes = (size_t)tiles * 16 + 64;
+    const unsigned groups = (tiles >> RTS_GROUP_LOG2) + 1;
+    const size_t bytes = ((size_t)tiles + groups) * 16 + 64;
     GPC_CUDA(sc.alloc(bytes, stream));
     char* p = sc.as<char>();
     unsigned long long* counts = reinterpret_cast<unsigned long long*>(p);            // 2 run counts
@@ -1776,6 +1775,7 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
     unsigned* ticket = reinterpret_cast<unsigned*>(p + 32);
     unsigned long long* st_tot = reinterpret_cast<unsigned long long*>(p + 64);
     unsigned long long* st_cnt = st_tot + tiles;
+    unsigned long long* st_super = st_cnt + tiles;                                    // [2][groups]
     WalkOrder order;
     GPC_TRY(walk_order(graph, reads, &read_index, n_reads, order, stream));
     SpillStore spill;
@@ -1833,14 +1833,14 @@ extern "C" int gpc_sample_pileup(const gpc_graph_t* graph, const gpc_reads_t* re
             const unsigned long long* bases = nullptr;
             if (variant != 2) {          // reduce, then scan (st_tot / st_cnt are one [2][tiles] array)
                 GPC_PROF_BYTES("dense_tile_sums", 8.0 * n_pos);
-                dense_tile_sums_kernel<<<tiles, DR_THREADS, 0, stream>>>(dense, st_tot, ticket, counts);
+                dense_tile_sums_kernel<<<tiles, DR_THREADS, 0, stream>>>(dense, st_tot, st_super, groups);
                 GPC_LAUNCH_CHECK();
                 bases = st_tot;
             }
             GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
             dense_runs_staged_kernel<<<tiles, DR_THREADS, DS_SMEM, stream>>>(
                 dense, n_pos, frag_idx, frag_val, direct_idx, direct_val, capacity, st_tot, st_cnt,
-                ticket, counts, bases, dbg);
+                ticket, counts, bases, st_super, groups, dbg);
         } else {
             GPC_PROF_BYTES("dense_runs", 16.0 * n_pos);
             dense_runs_block_kernel<16><<<tiles, DR_THREADS, DR_THREADS * (16 * 8 + 16), stream>>>(

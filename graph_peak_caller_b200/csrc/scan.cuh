@@ -84,63 +84,41 @@ __device__ __forceinline__ void store_running(uint32_t* __restrict__ out, unsign
 // tiles in flight that wait was 45 % of the difference-array scan (measured with the look-back
 // switched off, csrc/sample.cu) and the top stall of every compaction (barrier 35-42 warps per
 // issue).  Above RTS_MIN_ITEMS items the drivers below therefore run two launches instead:
-// per-tile totals (one more read of the input) whose last block turns them into exclusive
-// prefixes, and the scan / compaction kernel with its prefix handed in -- tiles independent.
+// per-tile totals (one more read of the input), and the scan / compaction kernel, whose
+// tiles look their prefix up in the totals -- tiles independent.
 constexpr size_t RTS_MIN_ITEMS = 1u << 20;
 
-// in place: tile totals -> exclusive prefixes; *total = their sum.  Run by ONE block (any
-// size that is a multiple of 32, at most 1024 threads): the block of the totals kernel that
-// finishes last (tile_prefix_by_last_block), so the prefixes cost no launch of their own.
-__device__ __forceinline__ void tile_prefix_block(unsigned long long* sums, unsigned tiles,
-                                                  unsigned long long* total, unsigned long long* s_warp /* [33] */) {
-    // every thread owns a contiguous chunk: its loads are independent (all in flight at once:
-    // the block pays two L2 latencies, not one per 1024 items), one block scan in between
-    const unsigned nw = blockDim.x >> 5;
-    const unsigned per = (tiles + blockDim.x - 1) / blockDim.x;
-    const unsigned lo = min(tiles, threadIdx.x * per), hi = min(tiles, lo + per);
-    unsigned long long sum = 0;
-    for (unsigned i = lo; i < hi; i += 8) {
-        unsigned long long v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = i + j < hi ? __ldcg(sums + i + j) : 0ull;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sum += v[j];
-    }
-    const unsigned long long incl = warp_incl_sum(sum);
-    if (lane_id() == 31) s_warp[warp_id()] = incl;
-    __syncthreads();
-    if (warp_id() == 0) {
-        const unsigned long long x = lane_id() < nw ? s_warp[lane_id()] : 0ull;
-        const unsigned long long xi = warp_incl_sum(x);
-        s_warp[lane_id()] = xi - x;
-        if (lane_id() == 31) s_warp[32] = xi;
-    }
-    __syncthreads();
-    unsigned long long run = s_warp[warp_id()] + incl - sum;
-    for (unsigned i = lo; i < hi; i += 8) {             // loads of a batch first, then its stores
-        unsigned long long v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = i + j < hi ? __ldcg(sums + i + j) : 0ull;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (i + j < hi) sums[i + j] = run;
-            run += v[j];
-        }
-    }
-    if (threadIdx.x == 0 && total) *total = s_warp[32];
-    __syncthreads();
+// Tile totals come in two levels: sums[tile], and supers[tile / 64] accumulated by one atomic
+// per tile.  A tile's exclusive prefix is then the supers before its group plus the tiles
+// before it inside the group: at most a few hundred independent loads spread over the block
+// and one block reduction -- no serial pass over the totals, no launch of its own (a single
+// block scanning 13 100 totals took 25-45 us, as a kernel or as the tail of the last block).
+constexpr int RTS_GROUP_LOG2 = 6;
+__device__ __forceinline__ void tile_total_publish(unsigned long long* sums, unsigned long long* supers,
+                                                   unsigned tile, unsigned long long t) {   // ONE thread
+    sums[tile] = t;
+    atomicAdd(supers + (tile >> RTS_GROUP_LOG2), t);
 }
-// Every block calls this after thread 0 has written its tile total: true for the block that
-// arrives last (the totals of all blocks are visible to it).  *done must start at zero.
-__device__ __forceinline__ bool last_block_done(unsigned* done, unsigned* s_flag) {
+// every thread of the block calls it (contains barriers); s_red: 33 entries
+__device__ __forceinline__ unsigned long long tile_prefix_lookup(const unsigned long long* __restrict__ sums,
+                                                                 const unsigned long long* __restrict__ supers,
+                                                                 unsigned tile, unsigned long long* s_red) {
+    const unsigned group = tile >> RTS_GROUP_LOG2, first = group << RTS_GROUP_LOG2;
+    unsigned long long v = 0;
+    for (unsigned i = threadIdx.x; i < group; i += blockDim.x) v += supers[i];
+    for (unsigned i = first + threadIdx.x; i < tile; i += blockDim.x) v += sums[i];
+    v = warp_sum(v);
+    if (lane_id() == 0) s_red[warp_id()] = v;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        *s_flag = atomicAdd(done, 1u) == gridDim.x - 1 ? 1u : 0u;
+        unsigned long long t = 0;
+        for (unsigned w = 0; w < (blockDim.x >> 5); ++w) t += s_red[w];
+        s_red[32] = t;
     }
     __syncthreads();
-    const bool last = *s_flag != 0;
-    if (last) __threadfence();
-    return last;
+    const unsigned long long r = s_red[32];
+    __syncthreads();
+    return r;
 }
 
 // out[i] = sum_{j<i} in[j]  (uint32 in, uint64 running sum stored as uint32:
@@ -154,11 +132,9 @@ constexpr int ES_TILE = SC_THREADS * ES_ITEMS;
 
 template <typename InT>
 __global__ void __launch_bounds__(SC_THREADS)
-excl_scan_sums_kernel(const InT* __restrict__ in, unsigned n, unsigned long long* sums,
-                      unsigned* __restrict__ done /* zeroed */, unsigned long long* __restrict__ total) {
+excl_scan_sums_kernel(const InT* __restrict__ in, unsigned n, unsigned long long* __restrict__ sums,
+                      unsigned long long* __restrict__ supers /* zeroed */) {
     __shared__ unsigned s_red[SC_THREADS / 32];
-    __shared__ unsigned long long s_warp[33];
-    __shared__ unsigned s_flag;
     const unsigned base = blockIdx.x * ES_TILE + threadIdx.x * ES_ITEMS;
     unsigned v[ES_ITEMS], sum = 0;
     if (sizeof(InT) == 4)
@@ -174,9 +150,8 @@ excl_scan_sums_kernel(const InT* __restrict__ in, unsigned n, unsigned long long
         unsigned long long t = 0;
 #pragma unroll
         for (int w = 0; w < SC_THREADS / 32; ++w) t += s_red[w];
-        sums[blockIdx.x] = t;
+        tile_total_publish(sums, supers, blockIdx.x, t);
     }
-    if (last_block_done(done, &s_flag)) tile_prefix_block(sums, gridDim.x, total, s_warp);
 }
 
 // tile_prefix == NULL: chained scan over the tiles (status, ticket); else the exclusive
@@ -186,11 +161,13 @@ __global__ void __launch_bounds__(SC_THREADS)
 excl_scan_kernel(const InT* __restrict__ in, uint32_t* __restrict__ out, unsigned n,
                  unsigned long long* __restrict__ status, unsigned* __restrict__ ticket,
                  unsigned long long* __restrict__ total,
-                 const unsigned long long* __restrict__ tile_prefix = nullptr) {
+                 const unsigned long long* __restrict__ tile_sums = nullptr,
+                 const unsigned long long* __restrict__ tile_supers = nullptr) {
     __shared__ unsigned s_scan[33];
     __shared__ unsigned s_slot;
     __shared__ unsigned long long s_prefix;
-    const unsigned tile = tile_prefix ? blockIdx.x : claim_tile(ticket, &s_slot);
+    __shared__ unsigned long long s_red[33];
+    const unsigned tile = tile_sums ? blockIdx.x : claim_tile(ticket, &s_slot);
     const unsigned base = tile * ES_TILE + threadIdx.x * ES_ITEMS;
     unsigned v[ES_ITEMS];
     unsigned sum = 0;
@@ -202,8 +179,10 @@ excl_scan_kernel(const InT* __restrict__ in, uint32_t* __restrict__ out, unsigne
     for (int j = 0; j < ES_ITEMS; ++j) sum += v[j];
     unsigned tile_total;
     unsigned ex = block_excl_sum<unsigned>(sum, s_scan, tile_total);
-    if (tile_prefix) {
-        store_running<ES_ITEMS>(out, base, n, (unsigned)tile_prefix[tile] + ex, v);
+    if (tile_sums) {
+        const unsigned long long p = tile_prefix_lookup(tile_sums, tile_supers, tile, s_red);
+        if (threadIdx.x == 0 && tile == gridDim.x - 1 && total) *total = p + tile_total;
+        store_running<ES_ITEMS>(out, base, n, (unsigned)p + ex, v);
         return;
     }
     if (threadIdx.x < 32) {
@@ -227,18 +206,20 @@ int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* t
     }
     static_assert(sizeof(InT) == 4 || sizeof(InT) == 1, "exclusive_scan: uint32 or uint8 input");
     unsigned tiles = div_up(n, ES_TILE);
+    const unsigned groups = (tiles >> RTS_GROUP_LOG2) + 1;
     Scratch sc;
-    GPC_CUDA(sc.alloc((size_t)tiles * 8 + 16, stream));
-    GPC_CUDA(cudaMemsetAsync(sc.p, 0, (size_t)tiles * 8 + 16, stream));
+    GPC_CUDA(sc.alloc(((size_t)tiles + groups) * 8 + 16, stream));
+    GPC_CUDA(cudaMemsetAsync(sc.p, 0, ((size_t)tiles + groups) * 8 + 16, stream));
     unsigned long long* status = sc.as<unsigned long long>() + 2;
+    unsigned long long* supers = status + tiles;
     unsigned* ticket = sc.as<unsigned>();
     if (n >= RTS_MIN_ITEMS) {
         GPC_PROF_BYTES("excl_scan_sums", (double)n * sizeof(InT));
-        excl_scan_sums_kernel<InT><<<tiles, SC_THREADS, 0, stream>>>(in, (unsigned)n, status, ticket, total_dev);
+        excl_scan_sums_kernel<InT><<<tiles, SC_THREADS, 0, stream>>>(in, (unsigned)n, status, supers);
         GPC_LAUNCH_CHECK();
         GPC_PROF_BYTES("excl_scan", (double)n * (sizeof(InT) + 4));
         excl_scan_kernel<InT><<<tiles, SC_THREADS, 0, stream>>>(in, out, (unsigned)n, nullptr, nullptr,
-                                                                nullptr, status);
+                                                                total_dev, status, supers);
         GPC_LAUNCH_CHECK();
         return GPC_OK;
     }
@@ -255,10 +236,8 @@ int exclusive_scan(const InT* in, uint32_t* out, size_t n, unsigned long long* t
 template <typename Op>
 __global__ void __launch_bounds__(SC_THREADS)
 select_count_kernel(Op op, unsigned n_max, const unsigned long long* __restrict__ n_dev,
-                    unsigned long long* counts, unsigned* __restrict__ done /* zeroed */) {
+                    unsigned long long* __restrict__ counts, unsigned long long* __restrict__ supers /* zeroed */) {
     __shared__ unsigned s_red[SC_THREADS / 32];
-    __shared__ unsigned long long s_warp[33];
-    __shared__ unsigned s_flag;
     const unsigned n = n_dev ? (unsigned)min((unsigned long long)n_max, *n_dev) : n_max;
     const unsigned base = blockIdx.x * SC_TILE + threadIdx.x;
     unsigned c = 0;
@@ -274,9 +253,8 @@ select_count_kernel(Op op, unsigned n_max, const unsigned long long* __restrict_
         unsigned t = 0;
 #pragma unroll
         for (int w = 0; w < SC_THREADS / 32; ++w) t += s_red[w];
-        counts[blockIdx.x] = t;
+        tile_total_publish(counts, supers, blockIdx.x, (unsigned long long)t);
     }
-    if (last_block_done(done, &s_flag)) tile_prefix_block(counts, gridDim.x, nullptr, s_warp);
 }
 
 // tile_prefix == NULL: chained scan over the tiles (status, ticket); else the number of
@@ -286,14 +264,16 @@ __global__ void __launch_bounds__(SC_THREADS)
 select_kernel(Op op, unsigned n_max, const unsigned long long* __restrict__ n_dev,
               unsigned long long* __restrict__ status, unsigned* __restrict__ ticket,
               unsigned long long* __restrict__ total,
-              const unsigned long long* __restrict__ tile_prefix = nullptr) {
+              const unsigned long long* __restrict__ tile_sums = nullptr,
+              const unsigned long long* __restrict__ tile_supers = nullptr) {
     // striped items (row j of the tile = 256 consecutive items, one per thread):
     // loads and stores of a warp are contiguous; ranks come from ballots
     constexpr int WARPS = SC_THREADS / 32;
     __shared__ unsigned s_cnt[SC_ITEMS * WARPS + 1];
     __shared__ unsigned s_slot;
     __shared__ unsigned long long s_prefix;
-    const unsigned tile = tile_prefix ? blockIdx.x : claim_tile(ticket, &s_slot);
+    __shared__ unsigned long long s_red[33];
+    const unsigned tile = tile_sums ? blockIdx.x : claim_tile(ticket, &s_slot);
     // the item count may still sit in device memory (produced by the previous kernel)
     const unsigned n = n_dev ? (unsigned)min((unsigned long long)n_max, *n_dev) : n_max;
     if ((unsigned long long)tile * SC_TILE >= n) return;       // (whole block, nobody waits on it)
@@ -311,6 +291,8 @@ select_kernel(Op op, unsigned n_max, const unsigned long long* __restrict__ n_de
         if (lane == 0) s_cnt[j * WARPS + w] = __popc(b);
     }
     __syncthreads();
+    unsigned long long known = 0;                    // (uniform over the block)
+    if (tile_sums) known = tile_prefix_lookup(tile_sums, tile_supers, tile, s_red);
     if (threadIdx.x < 32) {
         // exclusive scan of the SC_ITEMS x WARPS (= 64) counts, two per lane
         unsigned a0 = s_cnt[2 * lane], a1 = s_cnt[2 * lane + 1];
@@ -318,8 +300,8 @@ select_kernel(Op op, unsigned n_max, const unsigned long long* __restrict__ n_de
         unsigned tile_total = __shfl_sync(0xffffffffu, incl, 31);
         s_cnt[2 * lane] = incl - a0 - a1;
         s_cnt[2 * lane + 1] = incl - a1;
-        unsigned long long p = tile_prefix ? tile_prefix[tile]
-                                           : lookback_excl_warp(status, tile, (unsigned long long)tile_total);
+        unsigned long long p = tile_sums ? known
+                                         : lookback_excl_warp(status, tile, (unsigned long long)tile_total);
         if (lane == 0) {
             s_prefix = p;
             if (tile == last_tile) {
@@ -347,19 +329,21 @@ int select_if(const char* name, Op op, size_t n, unsigned long long* total_dev, 
         return GPC_OK;
     }
     unsigned tiles = div_up(n, SC_TILE);
+    const unsigned groups = (tiles >> RTS_GROUP_LOG2) + 1;
     Scratch sc;
-    GPC_CUDA(sc.alloc((size_t)tiles * 8 + 16, stream));
-    GPC_CUDA(cudaMemsetAsync(sc.p, 0, (size_t)tiles * 8 + 16, stream));
+    GPC_CUDA(sc.alloc(((size_t)tiles + groups) * 8 + 16, stream));
+    GPC_CUDA(cudaMemsetAsync(sc.p, 0, ((size_t)tiles + groups) * 8 + 16, stream));
     unsigned long long* status = sc.as<unsigned long long>() + 2;
+    unsigned long long* supers = status + tiles;
     unsigned* ticket = sc.as<unsigned>();
     if (n >= RTS_MIN_ITEMS && keep_is_cheap) {
         // (tiles beyond a device-side item count contribute zero and leave at once)
         GPC_PROF("select_count");
-        select_count_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, n_dev, status, ticket);
+        select_count_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, n_dev, status, supers);
         GPC_LAUNCH_CHECK();
         GPC_PROF(name);
         select_kernel<Op><<<tiles, SC_THREADS, 0, stream>>>(op, (unsigned)n, n_dev, nullptr, nullptr,
-                                                            total_dev, status);
+                                                            total_dev, status, supers);
         GPC_LAUNCH_CHECK();
         return GPC_OK;
     }
