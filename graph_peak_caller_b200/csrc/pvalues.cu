@@ -401,96 +401,182 @@ __global__ void qtable_keys_kernel(const double* __restrict__ p, unsigned n,
     }
 }
 
-// Single block: running base-pair count in descending-p order, then per
-// distinct p:  q = p + log10(1 + bp with larger p) - log10(N), first clamped at
-// 0, running minimum (sparsepvalues.py:95-103).  Writes the distinct p
-// (descending) and their q, returns how many.
-constexpr int QT_THREADS = 1024;
+// Running base-pair count in descending-p order, then per distinct p:
+//   q = p + log10(1 + bp with larger p) - log10(N), first clamped at 0, running minimum
+// (sparsepvalues.py:95-103).  Writes the distinct p (descending) and their q.
+//
+// Three launches over tiles of 2048 sorted entries, tiles independent of each other (two-level
+// tile totals, scan.cuh): counts and group ends per tile; q of every group end + tile minima;
+// running minimum + compaction.  The first version was ONE block walking the table in chunks
+// (0.10 ms for the 35 k entries of one chr22-scale chromosome -- and 0.80 ms on every rank for
+// the joined table of eight of them, the largest kernel of the 8-GPU pass).
+constexpr int QT_THREADS = 256;
 constexpr int QT_ITEMS = 8;               // consecutive entries per thread (their loads overlap)
+constexpr int QT_TILE = QT_THREADS * QT_ITEMS;
+
+struct QtScratch {
+    unsigned long long* cnt_sums;   unsigned long long* cnt_supers;    // base pairs per tile / group of tiles
+    unsigned long long* end_sums;   unsigned long long* end_supers;    // distinct p per tile / group
+    unsigned long long* min_tile;   unsigned long long* min_super;     // ordered key of the smallest q
+    double* q;                                                          // q at group ends, +inf elsewhere
+};
+
+__device__ __forceinline__ unsigned long long qt_min_lookup(const unsigned long long* __restrict__ tiles,
+                                                            const unsigned long long* __restrict__ supers,
+                                                            unsigned tile, unsigned long long* s_red) {
+    const unsigned group = tile >> RTS_GROUP_LOG2, first = group << RTS_GROUP_LOG2;
+    unsigned long long v = ~0ull;
+    for (unsigned i = threadIdx.x; i < group; i += blockDim.x) v = min(v, supers[i]);
+    for (unsigned i = first + threadIdx.x; i < tile; i += blockDim.x) v = min(v, tiles[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(FULL, v, d));
+    if (lane_id() == 0) s_red[warp_id()] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = ~0ull;
+        for (unsigned w = 0; w < (blockDim.x >> 5); ++w) t = min(t, s_red[w]);
+        s_red[32] = t;
+    }
+    __syncthreads();
+    const unsigned long long r = s_red[32];
+    __syncthreads();
+    return r;
+}
+
 __global__ void __launch_bounds__(QT_THREADS)
-qtable_kernel(const unsigned long long* __restrict__ sorted_keys,
-              const uint32_t* __restrict__ sorted_idx,
-              const unsigned long long* __restrict__ counts, unsigned n, double log_n,
-              double* __restrict__ out_p, double* __restrict__ out_q,
-              unsigned long long* __restrict__ n_out) {
-    __shared__ unsigned long long s_cnt[33];
-    __shared__ int s_int[33];
-    __shared__ double s_min[33];
-    unsigned long long carry_count = 0;   // bp in all earlier chunks
-    double carry_min = INFINITY;          // running minimum over earlier chunks
-    unsigned carry_out = 0;
-    for (unsigned base = 0; base < n; base += QT_THREADS * QT_ITEMS) {
-        const unsigned i0 = base + threadIdx.x * QT_ITEMS;
-        unsigned long long key[QT_ITEMS + 1], c[QT_ITEMS];
+qtable_count_kernel(const unsigned long long* __restrict__ sorted_keys,
+                    const uint32_t* __restrict__ sorted_idx,
+                    const unsigned long long* __restrict__ counts, unsigned n, QtScratch sc) {
+    __shared__ unsigned long long s_red[2][QT_THREADS / 32];
+    const unsigned i0 = blockIdx.x * QT_TILE + threadIdx.x * QT_ITEMS;
+    unsigned long long key[QT_ITEMS + 1];
 #pragma unroll
-        for (int j = 0; j <= QT_ITEMS; ++j) key[j] = (i0 + j < n) ? sorted_keys[i0 + j] : 0ull;
-        unsigned long long tc = 0;
+    for (int j = 0; j <= QT_ITEMS; ++j) key[j] = (i0 + j < n) ? sorted_keys[i0 + j] : 0ull;
+    unsigned long long tc = 0, ends = 0;
 #pragma unroll
-        for (int j = 0; j < QT_ITEMS; ++j) {
-            c[j] = (i0 + j < n) ? counts[sorted_idx[i0 + j]] : 0ull;
-            tc += c[j];
+    for (int j = 0; j < QT_ITEMS; ++j) {
+        const unsigned i = i0 + j;
+        if (i < n) {
+            tc += counts[sorted_idx[i]];
+            ends += (i + 1 >= n || key[j + 1] != key[j]) ? 1u : 0u;
         }
-        unsigned long long tot_c;
-        unsigned long long run = carry_count + block_excl_sum<unsigned long long>(tc, s_cnt, tot_c);
-        // q at the last entry of every distinct p; bp with strictly larger p =
-        // running count before the group's first entry (groups are tiny: walk back)
-        double p[QT_ITEMS], q[QT_ITEMS];
-        unsigned last = 0;
+    }
+    tc = warp_sum(tc);
+    ends = warp_sum(ends);
+    if (lane_id() == 0) { s_red[0][warp_id()] = tc; s_red[1][warp_id()] = ends; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long a = 0, b = 0;
 #pragma unroll
-        for (int j = 0; j < QT_ITEMS; ++j) {
-            const unsigned i = i0 + j;
-            const bool valid = i < n;
-            p[j] = valid ? key_to_f64(~key[j]) : 0.0;
-            q[j] = INFINITY;
-            if (valid && (i + 1 >= n || key[j + 1] != key[j])) {
-                last |= 1u << j;
+        for (int w = 0; w < QT_THREADS / 32; ++w) { a += s_red[0][w]; b += s_red[1][w]; }
+        tile_total_publish(sc.cnt_sums, sc.cnt_supers, blockIdx.x, a);
+        tile_total_publish(sc.end_sums, sc.end_supers, blockIdx.x, b);
+    }
+}
+
+__global__ void __launch_bounds__(QT_THREADS)
+qtable_q_kernel(const unsigned long long* __restrict__ sorted_keys,
+                const uint32_t* __restrict__ sorted_idx,
+                const unsigned long long* __restrict__ counts, unsigned n, double log_n, QtScratch sc) {
+    __shared__ unsigned long long s_cnt[33];
+    __shared__ unsigned long long s_red[33];
+    const unsigned i0 = blockIdx.x * QT_TILE + threadIdx.x * QT_ITEMS;
+    unsigned long long key[QT_ITEMS + 1], c[QT_ITEMS];
+#pragma unroll
+    for (int j = 0; j <= QT_ITEMS; ++j) key[j] = (i0 + j < n) ? sorted_keys[i0 + j] : 0ull;
+    unsigned long long tc = 0;
+#pragma unroll
+    for (int j = 0; j < QT_ITEMS; ++j) {
+        c[j] = (i0 + j < n) ? counts[sorted_idx[i0 + j]] : 0ull;
+        tc += c[j];
+    }
+    const unsigned long long before_tile = tile_prefix_lookup(sc.cnt_sums, sc.cnt_supers, blockIdx.x, s_red);
+    unsigned long long tot_c;
+    unsigned long long run = before_tile + block_excl_sum<unsigned long long>(tc, s_cnt, tot_c);
+    // q at the last entry of every distinct p; bp with strictly larger p =
+    // running count before the group's first entry (groups are tiny: walk back)
+    double tmin = INFINITY;
+#pragma unroll
+    for (int j = 0; j < QT_ITEMS; ++j) {
+        const unsigned i = i0 + j;
+        if (i < n) {
+            double q = INFINITY;
+            if (i + 1 >= n || key[j + 1] != key[j]) {
                 unsigned long long before = run;            // count before entry i
                 unsigned g = i;
                 while (g > 0 && sorted_keys[g - 1] == key[j]) {
                     --g;
                     before -= counts[sorted_idx[g]];
                 }
-                q[j] = p[j] + log10(1.0 + (double)before) - log_n;
-                if (g == 0) q[j] = fmax(0.0, q[j]);
+                q = key_to_f64(~key[j]) + log10(1.0 + (double)before) - log_n;
+                if (g == 0) q = fmax(0.0, q);
             }
-            run += c[j];
+            sc.q[i] = q;
+            tmin = fmin(tmin, q);
         }
-        // inclusive running minimum: inside the thread, then over the block
-        double tmin = INFINITY;
-#pragma unroll
-        for (int j = 0; j < QT_ITEMS; ++j) { tmin = fmin(tmin, q[j]); q[j] = tmin; }
-        double m = tmin;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            double o = __shfl_up_sync(FULL, m, d);
-            if (lane_id() >= (unsigned)d) m = fmin(m, o);
-        }
-        if (lane_id() == 31) s_min[warp_id()] = m;
-        __syncthreads();
-        double pre = carry_min;                       // everything before this thread
-        for (unsigned w = 0; w < warp_id(); ++w) pre = fmin(pre, s_min[w]);
-        {
-            double up = __shfl_up_sync(FULL, m, 1);
-            if (lane_id() > 0) pre = fmin(pre, up);
-        }
-        double chunk_min = carry_min;
-        for (unsigned w = 0; w < QT_THREADS / 32; ++w) chunk_min = fmin(chunk_min, s_min[w]);
-        int tot_o;
-        int ex_o = block_excl_sum<int>(__popc(last), s_int, tot_o);
-        unsigned w_out = carry_out + (unsigned)ex_o;
-#pragma unroll
-        for (int j = 0; j < QT_ITEMS; ++j)
-            if ((last >> j) & 1u) {
-                out_p[w_out] = p[j];
-                out_q[w_out] = fmin(pre, q[j]);
-                ++w_out;
-            }
-        carry_count += tot_c;
-        carry_min = chunk_min;
-        carry_out += tot_o;
-        __syncthreads();
+        run += c[j];
     }
-    if (threadIdx.x == 0) *n_out = carry_out;
+    unsigned long long kmin = f64_to_key(tmin);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) kmin = min(kmin, __shfl_xor_sync(FULL, kmin, d));
+    if (lane_id() == 0) s_red[warp_id()] = kmin;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = ~0ull;
+#pragma unroll
+        for (int w = 0; w < QT_THREADS / 32; ++w) t = min(t, s_red[w]);
+        sc.min_tile[blockIdx.x] = t;
+        atomicMin(sc.min_super + (blockIdx.x >> RTS_GROUP_LOG2), t);
+    }
+}
+
+__global__ void __launch_bounds__(QT_THREADS)
+qtable_emit_kernel(const unsigned long long* __restrict__ sorted_keys, unsigned n, QtScratch sc,
+                   double* __restrict__ out_p, double* __restrict__ out_q,
+                   unsigned long long* __restrict__ n_out) {
+    __shared__ unsigned long long s_red[33];
+    __shared__ int s_int[33];
+    __shared__ double s_min[QT_THREADS / 32];
+    const unsigned i0 = blockIdx.x * QT_TILE + threadIdx.x * QT_ITEMS;
+    const unsigned long long kmin = qt_min_lookup(sc.min_tile, sc.min_super, blockIdx.x, s_red);
+    const double carry_min = kmin == ~0ull ? INFINITY : key_to_f64(kmin);     // (all ones: nothing before)
+    const unsigned long long carry_out = tile_prefix_lookup(sc.end_sums, sc.end_supers, blockIdx.x, s_red);
+    double q[QT_ITEMS];
+    unsigned last = 0;
+    double tmin = INFINITY;
+#pragma unroll
+    for (int j = 0; j < QT_ITEMS; ++j) {
+        const unsigned i = i0 + j;
+        const double v = i < n ? sc.q[i] : INFINITY;
+        if (i < n && (i + 1 >= n || sorted_keys[i + 1] != sorted_keys[i])) last |= 1u << j;
+        tmin = fmin(tmin, v);
+        q[j] = tmin;                                  // inclusive running minimum inside the thread
+    }
+    double m = tmin;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_up_sync(FULL, m, d);
+        if (lane_id() >= (unsigned)d) m = fmin(m, o);
+    }
+    if (lane_id() == 31) s_min[warp_id()] = m;
+    __syncthreads();
+    double pre = carry_min;                           // everything before this thread
+    for (unsigned w = 0; w < warp_id(); ++w) pre = fmin(pre, s_min[w]);
+    {
+        const double up = __shfl_up_sync(FULL, m, 1);
+        if (lane_id() > 0) pre = fmin(pre, up);
+    }
+    int tot_o;
+    const int ex_o = block_excl_sum<int>(__popc(last), s_int, tot_o);
+    unsigned long long w_out = carry_out + (unsigned long long)ex_o;
+#pragma unroll
+    for (int j = 0; j < QT_ITEMS; ++j)
+        if ((last >> j) & 1u) {
+            out_p[w_out] = key_to_f64(~sorted_keys[i0 + j]);
+            out_q[w_out] = fmin(pre, q[j]);
+            ++w_out;
+        }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *n_out = carry_out + (unsigned long long)tot_o;
 }
 
 __global__ void qvalues_apply_kernel(const double* __restrict__ p, unsigned n,
@@ -674,12 +760,26 @@ extern "C" int gpc_qtable_build(const double* table_p, const uint64_t* table_cou
                                                   k1.as<unsigned long long>(), i0.as<uint32_t>(),
                                                   i1.as<uint32_t>(), n, 0, 64, true, &in_tmp,
                                                   stream)));
+    const unsigned long long* sk = in_tmp ? k1.as<unsigned long long>() : k0.as<unsigned long long>();
+    const uint32_t* si = in_tmp ? i1.as<uint32_t>() : i0.as<uint32_t>();
+    const unsigned long long* tcount = reinterpret_cast<const unsigned long long*>(table_count);
+    const unsigned tiles = div_up(n, QT_TILE), groups = (tiles >> RTS_GROUP_LOG2) + 1;
+    Scratch qs, qq;
+    GPC_CUDA(qs.alloc(((size_t)tiles + groups) * 3 * 8, stream));
+    GPC_CUDA(qq.alloc((size_t)n * 8, stream));
+    unsigned long long* w = qs.as<unsigned long long>();
+    QtScratch sc{w, w + tiles, w + tiles + groups, w + 2 * tiles + groups,
+                 w + 2 * (tiles + groups), w + 2 * (tiles + groups) + tiles, qq.as<double>()};
+    GPC_CUDA(cudaMemsetAsync(w, 0, ((size_t)tiles + groups) * 2 * 8, stream));
+    GPC_CUDA(cudaMemsetAsync(sc.min_tile, 0xff, ((size_t)tiles + groups) * 8, stream));
+    GPC_PROF("qtable_count");
+    qtable_count_kernel<<<tiles, QT_THREADS, 0, stream>>>(sk, si, tcount, n, sc);
+    GPC_LAUNCH_CHECK();
+    GPC_PROF("qtable_q");
+    qtable_q_kernel<<<tiles, QT_THREADS, 0, stream>>>(sk, si, tcount, n, log10((double)total_bp), sc);
+    GPC_LAUNCH_CHECK();
     GPC_PROF("qtable");
-    qtable_kernel<<<1, QT_THREADS, 0, stream>>>(
-        in_tmp ? k1.as<unsigned long long>() : k0.as<unsigned long long>(),
-        in_tmp ? i1.as<uint32_t>() : i0.as<uint32_t>(),
-        reinterpret_cast<const unsigned long long*>(table_count), n, log10((double)total_bp),
-        out_p, out_q, cnt.as<unsigned long long>());
+    qtable_emit_kernel<<<tiles, QT_THREADS, 0, stream>>>(sk, n, sc, out_p, out_q, cnt.as<unsigned long long>());
     GPC_LAUNCH_CHECK();
     unsigned long long h = 0;
     GPC_READ_BACK({cnt.p, &h, (unsigned)(8)});
