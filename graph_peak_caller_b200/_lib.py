@@ -46,6 +46,11 @@ _SIGNATURES = {
     "gpc_sample_pileup": [P(GpcGraph), P(GpcReads), c_void_p, u64, i32, c_void_p, c_void_p,
                           c_void_p, c_void_p, u64, P(u64), P(u64), P(u64), c_void_p, i32,
                           c_void_p],
+    "gpc_diffs_to_runs": [c_void_p, c_void_p, u64, c_void_p, c_void_p, P(u64), c_void_p],
+    "gpc_diffs_merge": [c_void_p, c_void_p, u64, c_void_p, c_void_p, u64, c_void_p, c_void_p,
+                        c_void_p, P(u64), c_void_p],
+    "gpc_diffs_combine": [c_void_p, c_void_p, u64, c_void_p, c_void_p, u64, i32, i32, c_void_p,
+                          c_void_p, P(u64), c_void_p],
     "gpc_events_to_runs": [c_void_p, c_void_p, u64, u32, c_void_p, c_void_p, P(u64),
                            c_void_p, c_void_p, P(u64), c_void_p],
     "gpc_control_linear_track": [P(GpcGraph), c_void_p, c_void_p, c_void_p, u64,

@@ -4,7 +4,7 @@ of include/gpc_b200.h."""
 import ctypes
 
 from . import _lib
-from .device import empty, ptr, stream_ptr, torch_cuda
+from .device import empty, ptr, stream_ptr, to_device, torch_cuda
 
 
 def _u64():
@@ -119,6 +119,67 @@ def events_to_runs(events, size_bp):
                                       ctypes.byref(nf), ptr(di), ptr(dv),
                                       ctypes.byref(nd), stream_ptr()))
     return (fi[:nf.value], fv[:nf.value]), (di[:nd.value], dv[:nd.value])
+
+
+TRACK_OPS = {"maximum": 0, "minimum": 1, "add": 2, "subtract": 3, "multiply": 4}
+
+
+def _event_list(indices, diffs):
+    """(int64 indices, float64 diffs) of an event list as CUDA tensors (host arrays are
+    uploaded)."""
+    import numpy as np
+    torch = torch_cuda()
+    if not type(indices).__module__.startswith("torch"):
+        indices = to_device(np.asarray(indices).astype(np.int64, copy=False))
+        diffs = to_device(np.asarray(diffs).astype(np.float64, copy=False))
+    return indices.to(torch.int64), diffs.to(torch.float64)
+
+
+def diffs_to_runs(indices, diffs):
+    """T1/T2, generic: any (index, diff) list -> canonical runs (pos int32, value
+    float64) on the device."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    idx, d = _event_list(indices, diffs)
+    n = idx.numel()
+    pos, val = empty(max(n, 1), torch.int32), empty(max(n, 1), torch.float64)
+    n_out = _u64()
+    _lib.check(lib.gpc_diffs_to_runs(ptr(idx), ptr(d), n, ptr(pos), ptr(val),
+                                     ctypes.byref(n_out), stream_ptr()))
+    return pos[:n_out.value], val[:n_out.value]
+
+
+def diffs_merge(idx_a, diffs_a, idx_b, diffs_b):
+    """Distinct indices of two event lists and both tracks' running sums there:
+    (pos int32, a float64, b float64)."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    ia, da = _event_list(idx_a, diffs_a)
+    ib, db = _event_list(idx_b, diffs_b)
+    n = ia.numel() + ib.numel()
+    pos = empty(max(n, 1), torch.int32)
+    a, b = empty(max(n, 1), torch.float64), empty(max(n, 1), torch.float64)
+    n_out = _u64()
+    _lib.check(lib.gpc_diffs_merge(ptr(ia), ptr(da), ia.numel(), ptr(ib), ptr(db), ib.numel(),
+                                   ptr(pos), ptr(a), ptr(b), ctypes.byref(n_out), stream_ptr()))
+    m = n_out.value
+    return pos[:m], a[:m], b[:m]
+
+
+def diffs_combine(idx_a, diffs_a, idx_b, diffs_b, op, drop_leading_zero=False):
+    """op(a, b) of two event-list tracks as runs without repeated values: (pos int32,
+    value float64).  op: a key of TRACK_OPS."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    ia, da = _event_list(idx_a, diffs_a)
+    ib, db = _event_list(idx_b, diffs_b)
+    n = ia.numel() + ib.numel()
+    pos, val = empty(max(n, 1), torch.int32), empty(max(n, 1), torch.float64)
+    n_out = _u64()
+    _lib.check(lib.gpc_diffs_combine(ptr(ia), ptr(da), ia.numel(), ptr(ib), ptr(db), ib.numel(),
+                                     TRACK_OPS[op], 1 if drop_leading_zero else 0, ptr(pos),
+                                     ptr(val), ctypes.byref(n_out), stream_ptr()))
+    return pos[:n_out.value], val[:n_out.value]
 
 
 def control_linear_track(dgraph, dreads, read_index, n_reads, extensions,

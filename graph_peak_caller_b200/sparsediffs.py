@@ -24,6 +24,21 @@ def _to_host_index(t):
     return t.cpu().numpy().view(np.uint32).astype(np.int64)
 
 
+def _device():
+    """True when a CUDA device is visible: hand-made tracks then go through the generic
+    track kernels (gpc_diffs_to_runs / gpc_diffs_merge / gpc_diffs_combine, csrc/tracks.cu).
+    On a machine without a device (the CPU test suite, file conversion tools) the same
+    methods are the reference's numpy statements; the callpeaks path itself has no such
+    form and raises without a device."""
+    from .device import cuda_available
+    return cuda_available()
+
+
+# numpy callables of apply_binary_func that exist as a kernel operation
+_DEVICE_FUNCS = {np.maximum: "maximum", np.minimum: "minimum", np.add: "add",
+                 np.subtract: "subtract", np.multiply: "multiply"}
+
+
 class SparseValues:
     def __init__(self, indices, values, sanitize=False):
         self._h_idx = self._h_val = self._d_idx = self._d_val = None
@@ -247,6 +262,16 @@ class SparseDiffs:
         self._diffs = np.ediff1d(sv.values, to_begin=sv.values[0])
 
     def clip_min(self, min_value):
+        idx = self._indices
+        if _device() and idx.size and (idx.size == 1 or bool(np.all(idx[1:] > idx[:-1]))):
+            # maximum with the constant track that starts where this one does
+            from . import kernels
+            pos, val = kernels.diffs_combine(idx, self._diffs, idx[:1], [float(min_value)],
+                                             "maximum", drop_leading_zero=True)
+            self._runs = SparseValues(pos, val)
+            self._scale = 1.0
+            self._h_indices = self._h_diffs = None
+            return
         values = np.maximum(np.cumsum(self._diffs), min_value)
         diffs = np.empty_like(values)
         diffs[0] = values[0]
@@ -257,6 +282,9 @@ class SparseDiffs:
     def get_sparse_values(self):
         if self._runs is not None and self._h_indices is None and self._scale == 1.0:
             return self._runs
+        if _device():
+            from . import kernels
+            return SparseValues(*kernels.diffs_to_runs(self._indices, self._diffs))
         order = np.argsort(self._indices, kind="mergesort")
         return SparseValues(self._indices[order], np.cumsum(self._diffs[order]),
                             sanitize=True)
@@ -273,13 +301,31 @@ class SparseDiffs:
         return merged[last], np.cumsum(d, axis=1), last
 
     def maximum(self, other):
+        if _device():
+            from . import kernels
+            return SparseDiffs.from_device_runs(*kernels.diffs_combine(
+                self._indices, self._diffs, other._indices, other._diffs, "maximum",
+                drop_leading_zero=True))
         idx, vals, last = self._merged(other)
         top = np.max(vals, axis=0)[last]
         return SparseDiffs(idx, np.ediff1d(top, to_begin=top[0]), True)
 
     def apply_binary_func(self, func, other, return_values=False):
-        idx, vals, last = self._merged(other)
-        ret = func(vals[0], vals[1])[last]
+        if _device():
+            from . import kernels
+            if return_values and func in _DEVICE_FUNCS:
+                return SparseValues(*kernels.diffs_combine(
+                    self._indices, self._diffs, other._indices, other._diffs,
+                    _DEVICE_FUNCS[func]))
+            # an arbitrary Python callable: the merge and both running sums are kernels,
+            # the callable gets the two value arrays as the reference hands them over
+            pos, a, b = kernels.diffs_merge(self._indices, self._diffs, other._indices,
+                                            other._diffs)
+            idx = _to_host_index(pos)
+            ret = func(a.cpu().numpy(), b.cpu().numpy())
+        else:
+            idx, vals, last = self._merged(other)
+            ret = func(vals[0], vals[1])[last]
         if return_values:
             return SparseValues(idx, ret, sanitize=True)
         return SparseDiffs(idx, np.ediff1d(ret, to_begin=ret[0]))

@@ -148,6 +148,37 @@ int gpc_events_to_runs(uint32_t* events, uint32_t* events_tmp, uint64_t n_events
                        uint32_t* direct_idx, int32_t* direct_val, uint64_t* n_direct,
                        void* stream);
 
+/* ---- T1/T2, generic form: tracks from ARBITRARY event lists ---------------------------
+ * What the reference's container does with any (index, diff) list a caller hands it --
+ * float diffs, unsorted, indices repeated -- as opposed to the packed +-1 events of the
+ * callpeaks path above.  indices: int64 (0 <= index < 2^32 - 1, else GPC_ERR_ARG), diffs:
+ * float64, fewer than 2^30 entries per call; outputs need room for every input entry
+ * (n, or n_a + n_b).  Running sums are float64 and parallel: bit-identical to np.cumsum
+ * for integer-valued / exactly representable steps, equal to rounding otherwise
+ * (csrc/tracks.cu).
+ *
+ * gpc_diffs_to_runs: SparseDiffs.get_sparse_values (sparsediffs.py:137-141: stable sort
+ *   by index, running sum, SparseValues._sanitize :13-20) -> canonical runs; with the
+ *   event list of SparseDiffs.from_pileup (:180-190) as input, the pileup itself. */
+int gpc_diffs_to_runs(const int64_t* indices, const double* diffs, uint64_t n, uint32_t* out_pos,
+                      double* out_val, uint64_t* n_out, void* stream);
+/* gpc_diffs_merge: the front half of SparseDiffs.maximum / apply_binary_func
+ *   (sparsediffs.py:143-154, 208-219): the distinct indices of both lists in ascending
+ *   order and BOTH tracks' running sums there (a track is 0 before its first entry) --
+ *   the two arrays the reference hands to the caller's function. */
+int gpc_diffs_merge(const int64_t* idx_a, const double* diff_a, uint64_t n_a, const int64_t* idx_b,
+                    const double* diff_b, uint64_t n_b, uint32_t* out_pos, double* out_a,
+                    double* out_b, uint64_t* n_out, void* stream);
+/* gpc_diffs_combine: merge + op(a, b) + drop of entries repeating their predecessor's
+ *   value.  op GPC_TRACK_MAX with drop_leading_zero = 1 is SparseDiffs.maximum
+ *   (sparsediffs.py:143-159: np.max, ediff1d, _sanitize :161-165), returned as runs
+ *   (position, value); against the single event (first index, min_value) it is
+ *   SparseDiffs.clip_min (:130-135).  NaN propagates as in numpy. */
+enum { GPC_TRACK_MAX = 0, GPC_TRACK_MIN = 1, GPC_TRACK_ADD = 2, GPC_TRACK_SUB = 3, GPC_TRACK_MUL = 4 };
+int gpc_diffs_combine(const int64_t* idx_a, const double* diff_a, uint64_t n_a, const int64_t* idx_b,
+                      const double* diff_b, uint64_t n_b, int32_t op, int32_t drop_leading_zero,
+                      uint32_t* out_pos, double* out_val, uint64_t* n_out, void* stream);
+
 /* ---- S2-S5 + T1/T2 in one call: get_fragment_pileup incl. the direct pileup
  *      (sample/__init__.py:5-9, sample/sparsegraphpileup.py:37-250,
  *       sparsediffs.py:137-141,180-190) ---------------------------------------------
