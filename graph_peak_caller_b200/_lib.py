@@ -71,6 +71,9 @@ _SIGNATURES = {
                       c_void_p, c_void_p, u64, i32, c_void_p, c_void_p, c_void_p,
                       c_void_p, c_void_p, c_void_p, u64, c_void_p, u64, c_void_p, P(u64),
                       P(u64), c_void_p],
+    "gpc_peak_subgraphs": [P(GpcGraph), c_void_p, c_void_p, u64, c_void_p, c_void_p, c_void_p, u64,
+                           c_void_p, u64, c_void_p, c_void_p, c_void_p, c_void_p, u64, c_void_p,
+                           u64, P(u64), P(u64), P(u64), c_void_p],
     "gpc_peak_summits": [P(GpcGraph), c_void_p, c_void_p, c_void_p, c_void_p, u64, c_void_p,
                          c_void_p, u64, i32, c_void_p, c_void_p],
     "gpc_parse_intervals_host": [c_void_p, u64, i32, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -158,7 +158,7 @@ class CallPeaksFromQvalues:
             score_track = self.raw_pileup
         finder = SparseMaxPaths(self.filtered_peaks, self.graph, score_track, self.variant_maps)
         finder.set_q_values(self.q_values)
-        max_paths, _ = finder.run()
+        max_paths, sub_graphs = finder.run()
         chromosome = None if self._reporter._base_name is None \
             else self._reporter._base_name.replace("_", "")
         # scores are floats already; peaks of non-zero length carry the chromosome
@@ -171,6 +171,7 @@ class CallPeaksFromQvalues:
         keep = order[length[order] >= self.info.fragment_length] if len(order) else order
         self.max_paths = max_paths.subset(keep)
         logging.info("N filtered peaks: %s", len(self.max_paths))
+        self._reporter.add("sub_graphs", sub_graphs.subset(keep))      # lazy (callpeaks.py:210)
         self._reporter.add("max_paths", self.max_paths)
 
     def callpeaks(self):

@@ -1298,17 +1298,59 @@ extern "C" int gpc_clean_holes(const gpc_graph_t* graph, const uint32_t* pos, co
     return GPC_OK;
 }
 
-extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
-                             uint64_t n_runs, const uint32_t* score_pos, const double* score_val,
-                             const int32_t* score_val_i32, uint64_t n_score,
-                             const uint32_t* q_pos, const double* q_val,
-                             uint64_t n_q, int32_t internal_id_shift, int32_t* peak_start,
-                             int32_t* peak_end, int32_t* peak_length, double* peak_score,
-                             uint8_t* peak_info, uint32_t* peak_node_ptr, uint64_t peak_capacity,
-                             int32_t* peak_nodes, uint64_t node_capacity, uint32_t* order,
-                             uint64_t* n_peaks, uint64_t* n_nodes_total, void* stream_) {
-    GPC_STAGE();
-    cudaStream_t stream = (cudaStream_t)stream_;
+// Sub-graphs (gpc_peak_subgraphs): the line-graph components as they stand after the
+// adjacency lists are made -- members in (component, vertex) order, successor lists as
+// columns local to the component.
+struct SubgraphOut {
+    uint32_t* comp_ptr;
+    uint64_t comp_capacity;
+    int32_t* member_node;
+    int32_t* member_weight;
+    uint8_t* member_exit;
+    uint32_t* row_ptr;
+    uint64_t member_capacity;
+    uint32_t* col;
+    uint64_t col_capacity;
+    uint64_t* n_comp;
+    uint64_t* n_members;
+    uint64_t* n_cols;
+};
+
+__global__ void subgraph_emit_kernel(uint32_t V, int32_t min_node,
+                                     const unsigned long long* __restrict__ member_keys,
+                                     const uint32_t* __restrict__ v_node,
+                                     const uint32_t* __restrict__ comp_of_vertex,
+                                     const uint32_t* __restrict__ comp_ptr,
+                                     const uint32_t* __restrict__ adj_ptr,
+                                     const uint32_t* __restrict__ adj,
+                                     const int32_t* __restrict__ m_weight,
+                                     const uint8_t* __restrict__ m_flags,
+                                     int32_t* __restrict__ out_node, int32_t* __restrict__ out_weight,
+                                     uint8_t* __restrict__ out_exit, uint32_t* __restrict__ out_row_ptr,
+                                     uint32_t* __restrict__ out_col) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > V) return;
+    const uint32_t lo = adj_ptr[i];
+    out_row_ptr[i] = lo;
+    if (i == V) return;
+    const uint32_t u = member_vertex(member_keys, i);
+    out_node[i] = (int32_t)v_node[u] + min_node;
+    out_weight[i] = m_weight[i];
+    out_exit[i] = (m_flags[i] >> 1) & 1;
+    const uint32_t first = comp_ptr[comp_of_vertex[u]], hi = adj_ptr[i + 1];
+    for (uint32_t e = lo; e < hi; ++e) out_col[e] = adj[e] - first;
+}
+
+static int max_paths_impl(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
+                          uint64_t n_runs, const uint32_t* score_pos, const double* score_val,
+                          const int32_t* score_val_i32, uint64_t n_score,
+                          const uint32_t* q_pos, const double* q_val,
+                          uint64_t n_q, int32_t internal_id_shift, int32_t* peak_start,
+                          int32_t* peak_end, int32_t* peak_length, double* peak_score,
+                          uint8_t* peak_info, uint32_t* peak_node_ptr, uint64_t peak_capacity,
+                          int32_t* peak_nodes, uint64_t node_capacity, uint32_t* order,
+                          uint64_t* n_peaks, uint64_t* n_nodes_total, const SubgraphOut* sub,
+                          cudaStream_t stream) {
     *n_peaks = 0;
     *n_nodes_total = 0;
     if (n_runs == 0) { set_error("empty track"); return GPC_ERR_ARG; }
@@ -1486,6 +1528,26 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
                                      adj.as<uint32_t>(), m_weight.as<int32_t>(),
                                      m_flags.as<uint8_t>(), comp_backward.as<uint8_t>());
         GPC_LAUNCH_CHECK();
+        if (sub) {
+            uint32_t n_adj = 0;
+            GPC_READ_BACK({adj_ptr.as<uint32_t>() + V, &n_adj, 4u});
+            *sub->n_comp = n_comp;
+            *sub->n_members = V;
+            *sub->n_cols = n_adj;
+            if (n_comp + 1 > sub->comp_capacity || (uint64_t)V + 1 > sub->member_capacity ||
+                n_adj > sub->col_capacity)
+                return GPC_ERR_CAPACITY;
+            GPC_CUDA(cudaMemcpyAsync(sub->comp_ptr, comp_ptr.p, (size_t)(n_comp + 1) * 4,
+                                     cudaMemcpyDeviceToDevice, stream));
+            GPC_PROF("subgraph_emit");
+            subgraph_emit_kernel<<<GRID((size_t)V + 1)>>>(
+                V, graph->min_node, mk, v_node.as<uint32_t>(), comp_of.as<uint32_t>(),
+                comp_ptr.as<uint32_t>(), adj_ptr.as<uint32_t>(), adj.as<uint32_t>(),
+                m_weight.as<int32_t>(), m_flags.as<uint8_t>(), sub->member_node, sub->member_weight,
+                sub->member_exit, sub->row_ptr, sub->col);
+            GPC_LAUNCH_CHECK();
+            return GPC_OK;
+        }
         // members of every component in topological order (sorted by node: ids ascend along
         // every edge), as positions in the member arrays
         Scratch tk0, tk1, tv0, tv1, sweep, ccount, clist;
@@ -1539,6 +1601,7 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     }
     const uint32_t n_pk = (uint32_t)n_comp + (uint32_t)n_i;
     *n_peaks = n_pk;
+    if (sub) return GPC_OK;             // (no line-graph component at all)
     if (n_pk == 0) return GPC_OK;
     if (n_pk > peak_capacity) return GPC_ERR_CAPACITY;
     Scratch nn;
@@ -1581,3 +1644,35 @@ extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, cons
     return GPC_OK;
 }
 
+extern "C" int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
+                             uint64_t n_runs, const uint32_t* score_pos, const double* score_val,
+                             const int32_t* score_val_i32, uint64_t n_score,
+                             const uint32_t* q_pos, const double* q_val,
+                             uint64_t n_q, int32_t internal_id_shift, int32_t* peak_start,
+                             int32_t* peak_end, int32_t* peak_length, double* peak_score,
+                             uint8_t* peak_info, uint32_t* peak_node_ptr, uint64_t peak_capacity,
+                             int32_t* peak_nodes, uint64_t node_capacity, uint32_t* order,
+                             uint64_t* n_peaks, uint64_t* n_nodes_total, void* stream_) {
+    GPC_STAGE();
+    return max_paths_impl(graph, pos, val, n_runs, score_pos, score_val, score_val_i32, n_score, q_pos,
+                          q_val, n_q, internal_id_shift, peak_start, peak_end, peak_length, peak_score,
+                          peak_info, peak_node_ptr, peak_capacity, peak_nodes, node_capacity, order,
+                          n_peaks, n_nodes_total, nullptr, (cudaStream_t)stream_);
+}
+
+extern "C" int gpc_peak_subgraphs(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
+                                  uint64_t n_runs, const uint32_t* score_pos, const double* score_val,
+                                  const int32_t* score_val_i32, uint64_t n_score, uint32_t* comp_ptr,
+                                  uint64_t comp_capacity, int32_t* member_node, int32_t* member_weight,
+                                  uint8_t* member_exit, uint32_t* row_ptr, uint64_t member_capacity,
+                                  uint32_t* col, uint64_t col_capacity, uint64_t* n_comp,
+                                  uint64_t* n_members, uint64_t* n_cols, void* stream_) {
+    GPC_STAGE();
+    *n_comp = *n_members = *n_cols = 0;
+    SubgraphOut sub{comp_ptr, comp_capacity, member_node, member_weight, member_exit, row_ptr,
+                   member_capacity, col, col_capacity, n_comp, n_members, n_cols};
+    uint64_t n_peaks = 0, n_nodes_total = 0;
+    return max_paths_impl(graph, pos, val, n_runs, score_pos, score_val, score_val_i32, n_score, nullptr,
+                          nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0,
+                          nullptr, &n_peaks, &n_nodes_total, &sub, (cudaStream_t)stream_);
+}

@@ -349,6 +349,40 @@ def max_paths(dgraph, pos, val, score_pos, score_val, q_pos, q_val, internal_id_
         return out
 
 
+def peak_subgraphs(dgraph, pos, val, score_pos, score_val):
+    """Line-graph components of the peaks (the reference's sub-graphs).  Returns host
+    numpy arrays: comp_ptr[n_comp + 1], member node ids, member weights, member exit flags,
+    row_ptr[n_members + 1], col (local to the component)."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    ccap, mcap, ecap = 1024, max(1024, pos.numel() + 1), max(4096, 2 * pos.numel())
+    while True:
+        comp_ptr = empty(ccap, torch.int32)
+        node, weight = empty(mcap, torch.int32), empty(mcap, torch.int32)
+        ex, row_ptr = empty(mcap, torch.uint8), empty(mcap, torch.int32)
+        col = empty(ecap, torch.int32)
+        nc, nm, ne = _u64(), _u64(), _u64()
+        status = lib.gpc_peak_subgraphs(
+            ctypes.byref(dgraph.c), ptr(pos), ptr(val), pos.numel(), ptr(score_pos),
+            ptr(score_val) if score_val.dtype == torch.float64 else None,
+            ptr(score_val) if score_val.dtype == torch.int32 else None, score_pos.numel(),
+            ptr(comp_ptr), ccap, ptr(node), ptr(weight), ptr(ex), ptr(row_ptr), mcap, ptr(col),
+            ecap, ctypes.byref(nc), ctypes.byref(nm), ctypes.byref(ne), stream_ptr())
+        if status == _lib.GPC_ERR_CAPACITY:
+            ccap = max(ccap, int(nc.value) + 16)
+            mcap = max(mcap, int(nm.value) + 16)
+            ecap = max(ecap, int(ne.value) + 16)
+            continue
+        _lib.check(status)
+        c, m, e = int(nc.value), int(nm.value), int(ne.value)
+        if c == 0:
+            import numpy as np
+            z = np.zeros(0, dtype=np.int32)
+            return np.zeros(1, dtype=np.int32), z, z, z.astype(np.uint8), np.zeros(1, dtype=np.int32), z
+        return (comp_ptr[:c + 1].cpu().numpy(), node[:m].cpu().numpy(), weight[:m].cpu().numpy(),
+                ex[:m].cpu().numpy(), row_ptr[:m + 1].cpu().numpy(), col[:e].cpu().numpy())
+
+
 def peak_summits(dgraph, start, end, node_ptr, nodes, q_pos, q_val, window):
     """Summits.  start / end int32[n], node_ptr int32[n + 1], nodes
     int32[...] (node ids), q track (pos int32, val float64): all CUDA tensors.  Returns

@@ -1,13 +1,14 @@
 """``SparseMaxPaths`` with the reference's contract
 (graph_peak_caller/postprocess/maxpaths.py:11-65) over gpc_max_paths.
 
-``run()`` returns ``(peaks, subgraphs)`` like the reference; the sub-graph
-matrices the reference hands to its Reporter are an analysis by-product and
-are not produced here (the second element is a list of ``None``)."""
+``run()`` returns ``(peaks, subgraphs)`` like the reference; the sub-graphs are a lazy
+``SubGraphList`` over ``gpc_peak_subgraphs`` (postprocess/graphs.py): nothing is computed
+for them unless somebody looks (the Reporter does when it writes files)."""
 from .. import kernels, pipeline
 from ..device import device_graph
 from ..graph import Graph
 from ..peakcollection import PeakList
+from .graphs import SubGraphList
 
 # maxpaths.py:34 subtracts (min_node - 1) from the 1-based node index of a
 # single-node peak instead of adding it.  For min_node == 1 both agree; for
@@ -30,7 +31,7 @@ class SparseMaxPaths:
         """Track used for the final score (max q over the path)."""
         self._q_values = q_values
 
-    def run_raw(self):
+    def _inputs(self):
         torch = kernels.torch_cuda()
         pos, val = self._sparse_values.device_arrays()
         if val.dtype != torch.uint8:
@@ -38,6 +39,15 @@ class SparseMaxPaths:
         spos, sval = self._score_pileup.device_arrays()
         if sval.dtype not in (torch.float64, torch.int32):
             sval = sval.to(torch.float64)
+        return pos, val, spos, sval
+
+    def _sub_graph_arrays(self):
+        pos, val, spos, sval = self._inputs()
+        return kernels.peak_subgraphs(device_graph(self._graph), pos, val, spos, sval)
+
+    def run_raw(self):
+        torch = kernels.torch_cuda()
+        pos, val, spos, sval = self._inputs()
         q = self._q_values if self._q_values is not None else self._score_pileup
         qpos, qval = q.device_arrays(torch.float64)
         shift = self._graph.min_node - 1
@@ -50,4 +60,4 @@ class SparseMaxPaths:
         self.order = ps.order          # stable order by score, descending (device sort)
         self.peak_set = ps
         peaks = PeakList(ps, self._graph)      # Peak objects are made on access
-        return peaks, [None] * len(peaks)
+        return peaks, SubGraphList(self._sub_graph_arrays, ps)

@@ -7,11 +7,15 @@ reference writes under the same file names:
   background_track, direct_pileup;
 * peak lists -> ``<base><name>.intervalcollection`` (one JSON object per line):
   all_max_paths, max_paths;
-* touched_nodes -> ``<base>touched_nodes.npy``.
+* touched_nodes -> ``<base>touched_nodes.npy``;
+* sub_graphs -> ``<base>sub_graphs.graphs.npz`` / ``<base>sub_graphs.nodeids.npz``, one
+  entry ``peak<i>`` per final peak (reporter.py:11-15): the matrices and node ids of
+  ``postprocess/graphs.py``; the list is lazy, so a reporter that keeps things in memory
+  costs the pass nothing.
 
 Anything else is kept but not written -- "thresholded" among them: the
 reference's writer for it is spelt ``thersholded`` and is never found by its
-``add`` (reporter.py:41-42,52-57); neither are sub_graphs produced here.  A reporter with
+``add`` (reporter.py:41-42,52-57).  A reporter with
 ``base_name=None`` keeps everything in memory only, which is what the benchmark
 uses; ``memory`` holds the last object reported under every name either way."""
 import logging
@@ -36,6 +40,11 @@ class Reporter:
         elif name in PEAK_LISTS:
             PeakCollection(data).to_file(self._base_name + name + ".intervalcollection",
                                          text_file=True)
+        elif name == "sub_graphs":
+            np.savez(self._base_name + "sub_graphs.graphs",
+                     **{"peak%s" % i: p._graph for i, p in enumerate(data)})
+            np.savez(self._base_name + "sub_graphs.nodeids",
+                     **{"peak%s" % i: p._node_ids for i, p in enumerate(data)})
         elif name == "touched_nodes":
             ids = data.ids() if hasattr(data, "ids") else list(data)      # TouchedNodes: no list
             np.save(self._base_name + "touched_nodes.npy", np.array(ids, dtype="int"))

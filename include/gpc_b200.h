@@ -320,6 +320,32 @@ int gpc_max_paths(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* 
                   uint64_t node_capacity, uint32_t* order, uint64_t* n_peaks,
                   uint64_t* n_nodes_total, void* stream);
 
+/* ---- sub-graphs of the peaks: the second result of SparseMaxPaths.run()
+ *          (postprocess/maxpaths.py:96-124, graphs.py:106-116, 157-186, 317-338), which
+ *          CallPeaksFromQvalues hands to Reporter.sub_graphs (callpeaks.py:204-210,
+ *          reporter.py:11-15) ---------------------------------------------------------
+ * Same inputs as gpc_max_paths (cleaned boolean track, score track).  The line graph
+ * over the peak pieces -- vertices in the reference's order [tails, whole nodes, heads],
+ * an edge i -> j for every graph edge between their nodes -- split into its connected
+ * components, numbered as gpc_max_paths numbers its peaks (component c = peak c):
+ *   comp_ptr[n_comp + 1]      members of component c: comp_ptr[c] .. comp_ptr[c + 1]
+ *   member_node / member_weight / member_exit   node id, int32 piece score and "has an
+ *                             edge to the sink" per member, in ascending vertex order
+ *   row_ptr[n_members + 1], col   successor lists (CSR) with columns local to the
+ *                             component
+ * The reference's matrix of component c (k members) is (k + 1) x (k + 1) with
+ * M[i, j] = -weight_i for every successor j of i, and M[i, k] = -weight_i for exits.
+ * Capacities: comp_capacity >= n_comp + 1, member_capacity >= n_members + 1 (row_ptr;
+ * the member arrays take n_members), col_capacity >= n_cols; GPC_ERR_CAPACITY reports the
+ * three numbers (call again). */
+int gpc_peak_subgraphs(const gpc_graph_t* graph, const uint32_t* pos, const uint8_t* val,
+                       uint64_t n_runs, const uint32_t* score_pos, const double* score_val,
+                       const int32_t* score_val_i32, uint64_t n_score, uint32_t* comp_ptr,
+                       uint64_t comp_capacity, int32_t* member_node, int32_t* member_weight,
+                       uint8_t* member_exit, uint32_t* row_ptr, uint64_t member_capacity,
+                       uint32_t* col, uint64_t col_capacity, uint64_t* n_comp,
+                       uint64_t* n_members, uint64_t* n_cols, void* stream);
+
 /* ---- summits  PeakCollection.cut_around_summit
  *          (peakcollection.py:113-136) with the q-values read from the run-length
  *          track instead of the dense array of analysis_interface.py:388-406 /

@@ -262,6 +262,7 @@ class _PieceGraph:
     def best_paths(self):
         """PosDividedLineGraph.max_paths / _backtrace (graphs.py:270-355) and
         SubGraphAnalyzer.get_info (subgraphanalyzer.py:4-39)."""
+        self.subgraphs = []      # (node ids, csr matrix) per component, graphs.py:336-338
         if not self.entries.size:
             return [], []
         is_entry = np.zeros(self.sink, dtype=bool)
@@ -276,6 +277,7 @@ class _PieceGraph:
             members = np.r_[order[bounds[comp]:bounds[comp + 1]], self.sink]
             sub = -self.matrix[members][:, members]
             sub.data = sub.data + 1
+            self.subgraphs.append((self.nodes[members[:-1]], sub))
             if members.size == 2:
                 paths.append([members[0]])
                 infos.append((0, 0))
@@ -404,7 +406,7 @@ def piece_scores(pieces, score_idx, score_val, track_size):
 
 
 def max_paths(graph, indices, values, score_idx, score_val, score_track_size,
-              replicate_internal_id_quirk=True):
+              replicate_internal_id_quirk=True, with_subgraphs=False):
     """SparseMaxPaths(sparse_values, graph, score_pileup).run() without variant
     maps (maxpaths.py:11-65, 96-163).  Returns a list of peaks, each a tuple
     (start_offset, end_offset, [node ids], (is_diff, is_ambiguous)), in the
@@ -412,7 +414,13 @@ def max_paths(graph, indices, values, score_idx, score_val, score_track_size,
 
     ``replicate_internal_id_quirk``: maxpaths.py:34 subtracts (min_node-1)
     from the 1-based node index of single-node peaks instead of adding it;
-    harmless for min_node == 1.  True follows the reference literally."""
+    harmless for min_node == 1.  True follows the reference literally.
+
+    ``with_subgraphs``: also return the second element of the reference's result, one
+    SubGraph per peak (graphs.py:106-116, 336-338; maxpaths.py:120-124) as a
+    (node ids, scipy csr matrix) pair: the line-graph component of the peak with its sink
+    as last row / column and minus the piece score on every edge; a single-node peak has
+    its region path and an empty 1 x 1 matrix."""
     indices = np.asarray(indices)
     values = np.asarray(values)
     node_off = graph.node_off
@@ -452,6 +460,9 @@ def max_paths(graph, indices, values, score_idx, score_val, score_track_size,
         peaks.append((int(pieces[pi[0], 0] - node_off[nn[0] - 1]),
                       int(pieces[pi[-1], 1] - node_off[nn[-1] - 1]),
                       [int(v) for v in nn + shift], info))
+    if with_subgraphs:
+        small = [(list(p[2]), csr_matrix(([], ([], [])), shape=(1, 1))) for p in internal_peaks]
+        return peaks + internal_peaks, pg.subgraphs + small
     return peaks + internal_peaks
 
 

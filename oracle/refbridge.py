@@ -154,7 +154,8 @@ def ref_clean_holes(graph, indices, values, max_size, touched_ids):
     return out.indices, out.values
 
 
-def ref_max_paths(graph, indices, values, score_idx, score_val, track_size):
+def ref_max_paths(graph, indices, values, score_idx, score_val, track_size,
+                  with_subgraphs=False):
     _ref()
     from graph_peak_caller.postprocess.maxpaths import SparseMaxPaths
     from graph_peak_caller.sparsediffs import SparseValues
@@ -162,7 +163,10 @@ def ref_max_paths(graph, indices, values, score_idx, score_val, track_size):
     sv.track_size = track_size
     sc = SparseValues(np.array(score_idx), np.array(score_val))
     sc.track_size = track_size
-    peaks, _ = SparseMaxPaths(sv, to_ref_graph(graph), sc).run()
-    return [(int(p.start_position.offset), int(p.end_position.offset),
-             [int(r) for r in p.region_paths],
-             (bool(p.info[0]), bool(p.info[1]))) for p in peaks]
+    peaks, subs = SparseMaxPaths(sv, to_ref_graph(graph), sc).run()
+    out = [(int(p.start_position.offset), int(p.end_position.offset),
+            [int(r) for r in p.region_paths],
+            (bool(p.info[0]), bool(p.info[1]))) for p in peaks]
+    if with_subgraphs:
+        return out, [(np.asarray(s._node_ids), s._graph) for s in subs]
+    return out

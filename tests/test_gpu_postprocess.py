@@ -157,3 +157,70 @@ def test_max_paths_one_giant_component(backbone, site_rate):
     assert len(got_all) == 1 and len(got_all[0][2]) > 128
     assert [(p[0], p[1], p[2], p[3]) for p in got_all] == \
         [(p[0], p[1], p[2], tuple(p[3])) for p in ref_all]
+
+
+def _sub_graphs_of(graph, idx, val, sidx, sval, min_node_shift=None):
+    """SparseMaxPaths.run() of the product on host-made tracks -> (peaks, sub-graphs)."""
+    from graph_peak_caller_b200.postprocess.maxpaths import SparseMaxPaths
+    from graph_peak_caller_b200.sparsediffs import SparseValues
+    track = SparseValues(np.asarray(idx), np.asarray(val, dtype=bool))
+    track.track_size = graph.size_bp
+    score = SparseValues(np.asarray(sidx), np.asarray(sval, dtype=np.float64))
+    score.track_size = graph.size_bp
+    return SparseMaxPaths(track, graph, score).run()
+
+
+@pytest.mark.parametrize("trial", range(30))
+def test_sub_graphs_random_tracks(trial):
+    """The second result of SparseMaxPaths.run(): node ids and matrix of every peak's
+    line-graph component against the oracle (pinned on the live reference's SubGraph
+    objects, tests/test_oracle_vs_reference.py)."""
+    rng = np.random.default_rng(900 + trial)
+    g = make_graph(int(rng.integers(200, 4000)),
+                   site_rate=float(rng.choice([0.03, 0.1, 0.2])), seed=trial + 2000,
+                   min_node=int(rng.choice([1, 1, 57])), mnp_frac=0.2,
+                   indel_mean=float(rng.choice([2, 6])))
+    G = g.size_bp
+    idx, val = random_track(rng, G)
+    sk = int(rng.integers(1, max(2, G // 5)))
+    sidx = np.unique(np.r_[0, rng.integers(1, G, size=sk)])
+    sval = rng.integers(0, 6, size=sidx.size).astype(np.float64)
+    ref_peaks, ref_subs = opost.max_paths(g, idx, val, sidx, sval, G,
+                                          replicate_internal_id_quirk=False, with_subgraphs=True)
+    peaks, subs = _sub_graphs_of(g, idx, val, sidx, sval)
+    assert len(subs) == len(peaks) == len(ref_subs)
+    for k, (rn, rm) in enumerate(ref_subs):
+        s = subs[k]
+        assert np.array_equal(np.asarray(s._node_ids), np.asarray(rn)), k
+        assert s._graph.shape == rm.shape, k
+        assert np.array_equal(s._graph.toarray(), rm.toarray()), k
+    # a subset follows the peaks it is taken with
+    if len(subs) > 2:
+        pick = [len(subs) - 1, 0, 1]
+        sub = subs.subset(pick)
+        assert [list(np.asarray(x._node_ids)) for x in sub] == \
+            [list(np.asarray(ref_subs[i][0])) for i in pick]
+
+
+def test_sub_graphs_one_giant_component_and_no_component():
+    g = make_graph(1500, site_rate=0.2, seed=77, min_node=1, mnp_frac=0.2, indel_mean=4.0)
+    G = g.size_bp
+    rng = np.random.default_rng(3)
+    sidx = np.unique(np.r_[0, rng.integers(1, G, size=G // 7)])
+    sval = rng.integers(0, 5, size=sidx.size).astype(np.float64)
+    idx, val = np.array([0]), np.array([True])
+    _, ref_subs = opost.max_paths(g, idx, val, sidx, sval, G, with_subgraphs=True)
+    _, subs = _sub_graphs_of(g, idx, val, sidx, sval)
+    assert len(subs) == 1 and subs[0]._graph.shape[0] > 128
+    assert np.array_equal(subs[0]._graph.toarray(), ref_subs[0][1].toarray())
+    assert np.array_equal(np.asarray(subs[0]._node_ids), ref_subs[0][0])
+    # one peak strictly inside one node: no line graph at all
+    off = int(g.node_off[3])
+    idx, val = np.array([0, off + 1, off + 2]), np.array([False, True, False])
+    if g.node_len[3] < 4:
+        pytest.skip("node too short for an internal peak")
+    ref_peaks, ref_subs = opost.max_paths(g, idx, val, sidx, sval, G,
+                                          replicate_internal_id_quirk=False, with_subgraphs=True)
+    peaks, subs = _sub_graphs_of(g, idx, val, sidx, sval)
+    assert len(subs) == len(ref_subs) == 1
+    assert list(subs[0]._node_ids) == list(ref_subs[0][0]) and subs[0]._graph.shape == (1, 1)

@@ -82,7 +82,12 @@ def test_hole_cleaner_and_max_paths_random_tracks(trial):
     sk = int(rng.integers(1, max(2, G // 5)))
     sidx = np.unique(np.r_[0, rng.integers(1, G, size=sk)])
     sval = rng.integers(0, 9, size=sidx.size).astype(np.float64)
-    rp = refbridge.ref_max_paths(g, oi, ov, sidx, sval, G)
-    op = opost.max_paths(g, oi, ov, sidx, sval, G)
+    rp, rs = refbridge.ref_max_paths(g, oi, ov, sidx, sval, G, with_subgraphs=True)
+    op, osub = opost.max_paths(g, oi, ov, sidx, sval, G, with_subgraphs=True)
     assert [(p[0], p[1], p[2], tuple(p[3])) for p in op] == \
         [(p[0], p[1], p[2], tuple(p[3])) for p in rp]
+    # the sub-graph of every peak (what the reference's Reporter.sub_graphs saves)
+    assert len(osub) == len(rs) == len(op)
+    for (on, om), (rn, rm) in zip(osub, rs):
+        assert np.array_equal(np.asarray(on), np.asarray(rn))
+        assert om.shape == rm.shape and np.array_equal(om.toarray(), rm.toarray())
