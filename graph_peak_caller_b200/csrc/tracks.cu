@@ -50,16 +50,31 @@ __global__ void td_keys_kernel(const long long* __restrict__ idx_a, unsigned na,
     src[i] = i;
 }
 
-// diffs in sorted order; column b (the second track) only when two tracks are merged
+// diffs in sorted order.  One track (get_sparse_values, sparsediffs.py:138-139): every diff
+// follows its index, diffs[args].  Two tracks (maximum / apply_binary_func, :149-153): the
+// reference lays diffs_a out over the slots of track a IN THEIR GIVEN ORDER -- the k-th slot
+// of track a in merged order takes diffs_a[k] -- which is the same thing for index-sorted
+// lists (the stable sort keeps a track's entries in order) and is reproduced literally for
+// the others: rank_a[i] = slots of track a before slot i.
+__global__ void td_slot_flags_kernel(const uint32_t* __restrict__ src, unsigned n, unsigned na,
+                                     uint32_t* __restrict__ is_a) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) is_a[i] = src[i] < na ? 1u : 0u;
+}
 __global__ void td_gather_kernel(const uint32_t* __restrict__ src, unsigned n,
                                  const double* __restrict__ diff_a, unsigned na,
-                                 const double* __restrict__ diff_b, double* __restrict__ col_a,
-                                 double* __restrict__ col_b) {
+                                 const double* __restrict__ diff_b, const uint32_t* __restrict__ rank_a,
+                                 double* __restrict__ col_a, double* __restrict__ col_b) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned s = src[i];
-    col_a[i] = s < na ? diff_a[s] : 0.0;
-    if (col_b) col_b[i] = s >= na ? diff_b[s - na] : 0.0;
+    if (!col_b) {
+        col_a[i] = diff_a[s];
+        return;
+    }
+    const unsigned k = rank_a[i];
+    col_a[i] = s < na ? diff_a[k] : 0.0;
+    col_b[i] = s >= na ? diff_b[i - k] : 0.0;
 }
 
 // ---- float64 running sums: reduce, then scan --------------------------------------------
@@ -235,8 +250,18 @@ static int union_values(const int64_t* idx_a, const double* diff_a, uint64_t na,
     }
     double* ca = col_a.as<double>();
     double* cb = two ? col_b.as<double>() : nullptr;
+    Scratch is_a, rank_a;
+    if (two) {
+        GPC_CUDA(is_a.alloc((size_t)n * 4, stream));
+        GPC_CUDA(rank_a.alloc((size_t)n * 4, stream));
+        GPC_PROF("td_slot_flags");
+        td_slot_flags_kernel<<<div_up(n, 256), 256, 0, stream>>>(s, n, (unsigned)na, is_a.as<uint32_t>());
+        GPC_LAUNCH_CHECK();
+        GPC_TRY(exclusive_scan<uint32_t>(is_a.as<uint32_t>(), rank_a.as<uint32_t>(), n, nullptr, stream));
+    }
     GPC_PROF("td_gather");
-    td_gather_kernel<<<div_up(n, 256), 256, 0, stream>>>(s, n, diff_a, (unsigned)na, diff_b, ca, cb);
+    td_gather_kernel<<<div_up(n, 256), 256, 0, stream>>>(s, n, diff_a, (unsigned)na, diff_b,
+                                                          two ? rank_a.as<uint32_t>() : nullptr, ca, cb);
     GPC_LAUNCH_CHECK();
     GPC_PROF("td_tile_sums");
     td_tile_sums_kernel<<<tiles, TD_THREADS, 0, stream>>>(ca, cb, n, tsum.as<double>());

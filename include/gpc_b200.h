@@ -165,7 +165,10 @@ int gpc_diffs_to_runs(const int64_t* indices, const double* diffs, uint64_t n, u
 /* gpc_diffs_merge: the front half of SparseDiffs.maximum / apply_binary_func
  *   (sparsediffs.py:143-154, 208-219): the distinct indices of both lists in ascending
  *   order and BOTH tracks' running sums there (a track is 0 before its first entry) --
- *   the two arrays the reference hands to the caller's function. */
+ *   the two arrays the reference hands to the caller's function.  As there (:149-153)
+ *   the k-th slot of a track in merged order takes that track's k-th diff: for
+ *   index-sorted lists, the only ones the reference itself makes, every diff thereby stays
+ *   with its index. */
 int gpc_diffs_merge(const int64_t* idx_a, const double* diff_a, uint64_t n_a, const int64_t* idx_b,
                     const double* diff_b, uint64_t n_b, uint32_t* out_pos, double* out_a,
                     double* out_b, uint64_t* n_out, void* stream);
