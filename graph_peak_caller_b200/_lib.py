@@ -86,6 +86,9 @@ _SIGNATURES = {
     "gpc_parse_vg_sequences_host": [c_void_p, u64, c_void_p, c_void_p, c_void_p, P(u64), P(u64)],
     "gpc_shift_model_host": [c_void_p, u64, c_void_p, u64, i64, i64, i64, i64, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, P(u64)],
+    "gpc_node_read_counts": [c_void_p, u64, i32, u32, c_void_p, c_void_p],
+    "gpc_path_start_positions": [P(GpcGraph), c_void_p, u64, i64, c_void_p, c_void_p, u64, c_void_p,
+                                 P(u64), c_void_p, P(u64), c_void_p],
     "gpc_most_covered_path_host": [c_void_p, c_void_p, c_void_p, c_void_p, u64, c_void_p, P(u64)],
     "gpc_linear_map_from_graph_host": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        u64, c_void_p, c_void_p],

@@ -395,3 +395,29 @@ def peak_summits(dgraph, start, end, node_ptr, nodes, q_pos, q_val, window):
                                     ptr(nodes), n, ptr(q_pos), ptr(q_val), q_pos.numel(),
                                     int(window), ptr(out), stream_ptr()))
     return out.view(n, 6)
+
+
+def node_read_counts(path, min_node, n_nodes):
+    """Forward visits per node over all read paths (fragment-length estimation,
+    SURVEY.md §8f-4).  path: int32 CUDA tensor of signed node ids.  Returns int32[n_nodes]."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    counts = empty(max(int(n_nodes), 1), torch.int32)
+    _lib.check(lib.gpc_node_read_counts(ptr(path), path.numel(), int(min_node), int(n_nodes),
+                                        ptr(counts), stream_ptr()))
+    return counts[:int(n_nodes)]
+
+
+def path_start_positions(dgraph, path, start_offset, start_node, start_off):
+    """Read starts on a path, per strand, in read order: (plus int64[...], minus int64[...])
+    CUDA tensors."""
+    torch = torch_cuda()
+    lib = _lib.load()
+    n = start_node.numel()
+    plus, minus = empty(max(n, 1), torch.int64), empty(max(n, 1), torch.int64)
+    n_plus, n_minus = _u64(), _u64()
+    _lib.check(lib.gpc_path_start_positions(
+        ctypes.byref(dgraph.c), ptr(path), path.numel(), int(start_offset), ptr(start_node),
+        ptr(start_off), n, ptr(plus), ctypes.byref(n_plus), ptr(minus), ctypes.byref(n_minus),
+        stream_ptr()))
+    return plus[:n_plus.value], minus[:n_minus.value]

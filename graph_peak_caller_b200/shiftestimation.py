@@ -11,13 +11,19 @@ names --
   (linear_filter.py:12-60), over ``HaploTyper``'s most-covered path
   (haplotyping.py:18-58).
 
-The sweeps over the sorted read starts and over the graph are native host code
-(``csrc/shift.cu``: ``gpc_shift_model_host``, ``gpc_most_covered_path_host``); they
-are sequential by construction (every window starts where the one before ended) and
-take milliseconds, so there is no kernel here.  Reads are the flat ``ReadBatch``
-arrays: node counts, the filter and the projection are whole-array operations.
-What stays in numpy is the cross-correlation of the two 1211-entry model lines, in
-the same operations as the reference so that ``d`` is the same float.
+The whole-array steps -- visits per node over all read paths, the projection of every
+read start onto the most-covered path with the split by strand, the sort of the projected
+starts -- are kernels (``csrc/shiftdev.cu``: ``gpc_node_read_counts``,
+``gpc_path_start_positions``; ``gpc_sort_u64_pairs``) over the reads as they sit in HBM
+for the callpeaks pass that follows (one upload serves both).  The sweeps over the sorted
+starts and along the graph are native host code (``csrc/shift.cu``:
+``gpc_shift_model_host``, ``gpc_most_covered_path_host``): sequential by construction
+(every window starts where the one before ended), milliseconds each.  Without a CUDA device
+(``DEVICE = False``, or none visible) the whole-array steps are the numpy statements
+below -- this is a one-off preprocessing estimate, like ``LinearMap.from_graph``, not the
+callpeaks path.  What stays in numpy either way is the cross-correlation of the two
+1211-entry model lines, in the same operations as the reference so that ``d`` is the same
+float.
 
 offsetbasedgraph's ``IndexedInterval.get_offset_at_position`` is not in the reference
 tree; the reference's tests/test_linearfilter.py:33-42 pins it for forward starts
@@ -32,6 +38,30 @@ import numpy as np
 
 from . import _lib
 from .graph import Graph
+
+
+# None: use the device when one is visible; False: host arrays only (tests compare both)
+DEVICE = None
+
+
+def _use_device():
+    if DEVICE is False:
+        return False
+    from .device import cuda_available
+    return cuda_available()
+
+
+def _device_starts(reads):
+    """(start_node, start_off, path or None) of a ReadBatch / a bare namespace as CUDA
+    tensors; a ReadBatch is uploaded once for this and for the callpeaks pass."""
+    from .device import device_reads, to_device
+    if hasattr(reads, "path_ptr") and hasattr(reads, "nbytes"):
+        dr = device_reads(reads)
+        return dr.start_node, dr.start_off, dr.path
+    path = getattr(reads, "path", None)
+    return (to_device(np.asarray(reads.start_node, dtype=np.int32)),
+            to_device(np.asarray(reads.start_off, dtype=np.int32)),
+            None if path is None else to_device(np.asarray(path, dtype=np.int32)))
 
 
 class NotEnoughPairsException(Exception):
@@ -204,7 +234,34 @@ class LinearFilter:
     def length(self):
         return int(self._graph.node_len[self._path].sum())
 
-    def find_start_positions(self):
+    def find_start_positions(self, sort=False):
+        """{"+": positions, "-": positions} in read order (linear_filter.py:22-46);
+        ``sort=True``: ascending, which is what ``Treatment`` makes of them anyway."""
+        if _use_device():
+            return self._find_start_positions_device(sort)
+        found = self._find_start_positions_host()
+        return {k: np.sort(v) for k, v in found.items()} if sort else found
+
+    def _find_start_positions_device(self, sort):
+        from . import kernels
+        from .device import device_graph, to_device
+        start_node, start_off, _ = _device_starts(self._reads)
+        path = to_device(self._path.astype(np.int32))
+        plus, minus = kernels.path_start_positions(device_graph(self._graph), path,
+                                                   self._start_offset, start_node, start_off)
+        out = {}
+        for strand, pos in (("+", plus), ("-", minus)):
+            if sort and pos.numel() > 1 and self._start_offset <= 0:
+                # (positions >= 0: int64 order is uint64 order; digits equal in all keys
+                #  are skipped by the sort)
+                pos, _ = kernels.sort_u64_pairs(pos)
+                out[strand] = pos.cpu().numpy()
+            else:
+                out[strand] = np.sort(pos.cpu().numpy()) if sort else pos.cpu().numpy()
+        logging.info("Found in total %d positions" % out["+"].size)
+        return out
+
+    def _find_start_positions_host(self):
         g, r = self._graph, self._reads
         distance = np.full(g.n_nodes, -1, dtype=np.int64)
         sizes = g.node_len[self._path]
@@ -242,9 +299,14 @@ class LinearFilter:
         """Node counts as HaploTyper.build keeps them (haplotyping.py:18-26: keyed by
         signed id, so only forward visits count on the forward path)."""
         g = Graph.from_obg(graph)
-        visited = reads.path[reads.path > 0].astype(np.int64) - g.min_node
-        visited = visited[(visited >= 0) & (visited < g.n_nodes)]
-        counts = np.bincount(visited, minlength=g.n_nodes)
+        if _use_device():
+            from . import kernels
+            counts = kernels.node_read_counts(_device_starts(reads)[2], g.min_node,
+                                              g.n_nodes).cpu().numpy()
+        else:
+            visited = reads.path[reads.path > 0].astype(np.int64) - g.min_node
+            visited = visited[(visited >= 0) & (visited < g.n_nodes)]
+            counts = np.bincount(visited, minlength=g.n_nodes)
         return cls(reads, g, most_covered_path(g, counts))
 
 
@@ -271,7 +333,7 @@ class MultiGraphShiftEstimator(object):
         genome_size = 0
         for i, (graph, reads) in enumerate(zip(graph_file_names, interval_json_file_names)):
             linear_filter = LinearFilter.from_vg_json_reads_and_graph(reads, graph)
-            found = linear_filter.find_start_positions()
+            found = linear_filter.find_start_positions(sort=True)
             positions["+"][str(i)] = found["+"]
             positions["-"][str(i)] = found["-"]
             genome_size += linear_filter.length()

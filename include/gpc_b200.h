@@ -471,6 +471,24 @@ int gpc_shift_model_host(const int64_t* plus_tags, uint64_t n_plus, const int64_
                          int32_t* plus_end, int32_t* minus_start, int32_t* minus_end,
                          int64_t* centers, uint64_t* n_centers);
 
+/* ---- fragment-length estimation, the whole-array steps on the DEVICE --
+ * gpc_node_read_counts: HaploTyper.build (haplotyping.py:18-26).  path: the signed node
+ * ids of all read paths back to back (gpc_reads_t.path); counts[v] (n_nodes uint32, zeroed
+ * by the call) = forward visits of node index v -- the counter the most-covered path is
+ * chosen by. */
+int gpc_node_read_counts(const int32_t* path, uint64_t n_path_nodes, int32_t min_node,
+                         uint32_t n_nodes, uint32_t* counts, void* stream);
+/* gpc_path_start_positions: LinearFilter.find_start_positions (linear_filter.py:22-46).
+ * path: n_path 0-based node indexes in path order (device memory), start_offset: where the
+ * path starts on its first node.  A read whose start node lies on the path contributes
+ * (distance of the node from the path's start - start_offset + start offset) to out_plus
+ * when its start node id is positive, and (... + node size - start offset) to out_minus
+ * when it is negative; both lists come out in read order (capacity n_reads each). */
+int gpc_path_start_positions(const gpc_graph_t* graph, const int32_t* path, uint64_t n_path,
+                             int64_t start_offset, const int32_t* start_node,
+                             const int32_t* start_off, uint64_t n_reads, int64_t* out_plus,
+                             uint64_t* n_plus, int64_t* out_minus, uint64_t* n_minus, void* stream);
+
 /* HaploTyper.get_maximum_interval_through_graph (haplotyping.py:28-58): the path from
  * the graph's single source that always continues on the successor with the highest
  * node_count (first of equals in adjacency order).  0-based node indexes; path may be
