@@ -512,8 +512,7 @@ def main_ours(args):
                 e2e=dict(value=total_reads / (e2e_ms / 1e3), unit="reads/s",
                          ms_per_step=e2e_ms, h2d_bytes_per_step=int(h2d),
                          d2h_bytes_per_step=d2h,
-                         wire_form="compact" if getattr(units[0].pinned_s, "_compact", None) is not None
-                                   else "six arrays",
+                         wire_form=units[0].pinned_s.wire_form(),
                          note="CallPeaks.run(UniqueIntervals(page-locked host reads), ...) incl. H2D "
                               "of the read sets and D2H of the peaks; the graph is resident"),
                 roofline=roofline, cpu_baseline=cpu)

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "gpc_build_read_headers": [P(GpcReads), c_void_p, c_void_p],
     "gpc_reads_from_compact": [c_void_p, c_void_p, c_void_p, u64, c_void_p, c_void_p, c_void_p,
                                c_void_p],
+    "gpc_reads_from_compact_delta": [c_void_p, c_void_p, c_void_p, c_void_p, u64, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p],
     "gpc_sample_pileup": [P(GpcGraph), P(GpcReads), c_void_p, u64, i32, c_void_p, c_void_p,
                           c_void_p, c_void_p, u64, P(u64), P(u64), P(u64), c_void_p, i32,
                           c_void_p],

@@ -1455,6 +1455,33 @@ __global__ void widen_reads_kernel(const uint32_t* __restrict__ offs, const uint
     hdr[r] = make_uint4(p0, k ? k : 0x80000000u, o & 0xffffu, o >> 16);
 }
 
+// The same with the paths delta-coded (10.3 bytes per 36-bp read on the link instead of
+// 14.3): the first node id of every path as int32, every further node as the int8 step from
+// the node before it (graphs with sorted ids: neighbours on a path are a few ids apart).
+// Read r owns path_len[r] - 1 steps; the steps of all reads stand back to back, so those of
+// read r begin at path_off[r] - r.  Also writes the int32 path array the walk reads.
+__global__ void widen_reads_delta_kernel(const uint32_t* __restrict__ offs, const uint8_t* __restrict__ path_len,
+                                         const uint32_t* __restrict__ path_off,
+                                         const int32_t* __restrict__ first_node,
+                                         const int8_t* __restrict__ step, unsigned n,
+                                         int32_t* __restrict__ path, int32_t* __restrict__ start_node,
+                                         int32_t* __restrict__ start_off, uint4* __restrict__ hdr) {
+    unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t o = offs[r], k = path_len[r], p0 = path_off[r];
+    int32_t v = first_node[r];
+    start_node[r] = k ? v : 0;
+    start_off[r] = (int32_t)(o & 0xffffu);
+    hdr[r] = make_uint4(p0, k ? k : 0x80000000u, o & 0xffffu, o >> 16);
+    if (k == 0) return;
+    path[p0] = v;
+    const int8_t* s = step + (p0 - r);
+    for (uint32_t j = 1; j < k; ++j) {
+        v += (int32_t)s[j - 1];
+        path[p0 + j] = v;
+    }
+}
+
 }  // namespace gpc
 
 using namespace gpc;
@@ -1591,6 +1618,25 @@ extern "C" int gpc_reads_from_compact(const uint32_t* offs, const uint8_t* path_
     widen_reads_kernel<<<div_up(n_reads, 256), 256, 0, stream>>>(
         offs, path_len, off.as<uint32_t>(), path, (unsigned)n_reads, start_node, start_off,
         reinterpret_cast<uint4*>(hdr));
+    GPC_LAUNCH_CHECK();
+    return GPC_OK;
+}
+
+extern "C" int gpc_reads_from_compact_delta(const uint32_t* offs, const uint8_t* path_len,
+                                            const int32_t* first_node, const int8_t* step,
+                                            uint64_t n_reads, int32_t* path, int32_t* start_node,
+                                            int32_t* start_off, uint32_t* hdr, void* stream_) {
+    GPC_STAGE();
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_reads == 0) return GPC_OK;
+    if (n_reads >= (1ull << 31)) { set_error("too many reads"); return GPC_ERR_ARG; }
+    Scratch off;
+    GPC_CUDA(off.alloc(n_reads * 4, stream));
+    GPC_TRY(exclusive_scan<unsigned char>(path_len, off.as<uint32_t>(), n_reads, nullptr, stream));
+    GPC_PROF_BYTES("widen_reads", 42.0 * n_reads);
+    widen_reads_delta_kernel<<<div_up(n_reads, 256), 256, 0, stream>>>(
+        offs, path_len, off.as<uint32_t>(), first_node, step, (unsigned)n_reads, path, start_node,
+        start_off, reinterpret_cast<uint4*>(hdr));
     GPC_LAUNCH_CHECK();
     return GPC_OK;
 }

@@ -208,6 +208,29 @@ class DeviceReads:
                 self.ready_event.record(copy_stream)
 
         self.end_node = self.end_off = self.path_ptr = None
+        delta = getattr(batch, "_compact_delta", None)
+        if delta is not None:
+            # page-locked compact form with delta-coded paths: four asynchronous copies, one
+            # kernel rebuilds the path array and the per-read records
+            dev = device()
+            self.start_node = torch.empty(self.n, dtype=torch.int32, device=dev)
+            self.start_off = torch.empty(self.n, dtype=torch.int32, device=dev)
+            self.hdr = torch.empty(4 * self.n, dtype=torch.int32, device=dev)
+            self.path = torch.empty(int(batch.path.size), dtype=torch.int32, device=dev)
+            dst = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in delta]
+
+            def go(stream):
+                for a, b in zip(dst, delta):
+                    a.copy_(b, non_blocking=True)
+                _lib.check(lib.gpc_reads_from_compact_delta(
+                    ptr(dst[0]), ptr(dst[1]), ptr(dst[2]), ptr(dst[3]), self.n, ptr(self.path),
+                    ptr(self.start_node), ptr(self.start_off), ptr(self.hdr), stream))
+            on_copy_stream(go)
+            self._wire = dst                # (kept until the widening kernel has run)
+            self.host_bytes = batch.upload_bytes()
+            self.c = _lib.GpcReads(self.n, ptr(self.start_node), ptr(self.start_off), null, null,
+                                   null, ptr(self.path), null, ptr(self.hdr))
+            return
         if compact is not None:
             # page-locked compact form: three asynchronous copies, then one kernel widens
             # them into what the duplicate filter, the projection and the walk read

@@ -289,10 +289,28 @@ class ReadBatch:
         offs = self.start_off.astype(np.uint32) | (self.end_off.astype(np.uint32) << np.uint32(16))
         return offs, lens.astype(np.uint8), self.path
 
-    def pin_memory(self):
+    def compact_delta(self):
+        """The compact form with delta-coded paths: (offs uint32[R], path_len uint8[R],
+        first_node int32[R], step int8[sum(path_len) - R]) -- 10.3 bytes per 36-bp read.
+        None when the compact form does not apply or a step between neighbouring path nodes
+        does not fit int8 (ids not sorted along the graph)."""
+        c = self.compact()
+        if c is None:
+            return None
+        offs, lens, path = c
+        first = np.ascontiguousarray(path[self.path_ptr[:-1]], dtype=np.int32)
+        inner = np.ones(path.size, dtype=bool)
+        inner[self.path_ptr[:-1]] = False
+        step = (path[1:].astype(np.int64) - path[:-1].astype(np.int64))[inner[1:]]
+        if step.size and (step.min() < -128 or step.max() > 127):
+            return None
+        return offs, lens, first, step.astype(np.int8)
+
+    def pin_memory(self, delta=True):
         """A batch over the same reads whose arrays -- and, when the reads allow it, their
         compact form -- sit in page-locked memory: uploads of such a batch are asynchronous
-        copies of the compact form (ingest-side preparation, done once per read set)."""
+        copies of the compact form (ingest-side preparation, done once per read set);
+        ``delta``: with delta-coded paths when the node ids allow it."""
         import torch
         full = [torch.from_numpy(a).pin_memory() for a in (
             self.start_node, self.start_off, self.end_node, self.end_off,
@@ -305,6 +323,9 @@ class ReadBatch:
         c = self.compact()
         out._compact = None if c is None else [torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
                                                for a in c[:2]] + [full[5]]
+        d = self.compact_delta() if c is not None and delta else None
+        out._compact_delta = None if d is None else out._compact[:2] + [
+            torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in d[2:]]
         return out
 
     def fresh_view(self):
@@ -314,8 +335,18 @@ class ReadBatch:
         out._device = None
         return out
 
+    def wire_form(self):
+        """What an upload of this batch sends: "compact+delta", "compact", "pinned" or "pageable"."""
+        if getattr(self, "_compact_delta", None) is not None:
+            return "compact+delta"
+        if getattr(self, "_compact", None) is not None:
+            return "compact"
+        return "pinned" if getattr(self, "_pinned", None) is not None else "pageable"
+
     def upload_bytes(self):
-        c = getattr(self, "_compact", None)
+        c = getattr(self, "_compact_delta", None)
+        if c is None:
+            c = getattr(self, "_compact", None)
         if c is not None:
             return sum(t.numel() * t.element_size() for t in c)
         p = getattr(self, "_pinned", None)

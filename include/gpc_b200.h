@@ -115,6 +115,16 @@ int gpc_reads_from_compact(const uint32_t* offs, const uint8_t* path_len, const 
                            uint64_t n_reads, int32_t* start_node, int32_t* start_off,
                            uint32_t* hdr, void* stream);
 
+/* The same with delta-coded paths (10.3 bytes per 36-bp read): first_node[r] = the first
+ * node id of read r's path (int32), step = for every further path node the int8 difference
+ * to the node before it, the steps of all reads back to back (read r owns path_len[r] - 1 of
+ * them).  Also writes `path` (capacity: sum of path_len), the array gpc_reads_t.path points
+ * at.  A host that meets a step outside int8 ships the batch in the plain compact form. */
+int gpc_reads_from_compact_delta(const uint32_t* offs, const uint8_t* path_len,
+                                 const int32_t* first_node, const int8_t* step, uint64_t n_reads,
+                                 int32_t* path, int32_t* start_node, int32_t* start_off,
+                                 uint32_t* hdr, void* stream);
+
 /* ---- S1  UniqueIntervals.__iter__  (graph_peak_caller/intervals.py:23-33) ---
  * Keeps the first read of every start position (signed node id, offset).
  * out_index: capacity n_reads, receives the kept read indexes in ascending

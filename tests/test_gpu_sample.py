@@ -16,9 +16,10 @@ def gpu_sample(graph, reads, extension, unique, mode=None, headers=True, pinned=
     the walk reads the six SoA arrays instead of the 16-byte read records."""
     from graph_peak_caller_b200 import kernels
     from graph_peak_caller_b200.device import DeviceGraph, DeviceReads
-    if pinned:           # page-locked batch: goes up in the compact wire form when it can
-        reads = reads.pin_memory()
+    if pinned:           # page-locked batch: goes up in a compact wire form when it can
+        reads = reads.pin_memory(delta=(pinned != "plain"))
         assert reads._compact is not None or len(reads) == 0
+        assert pinned != "plain" or reads._compact_delta is None
     dg, dr = DeviceGraph(graph), DeviceReads(reads)
     if not headers:
         dr.c.hdr = None
@@ -51,7 +52,7 @@ def check(graph, reads, extension, unique):
     # (with and without the per-read records)
     for mode, headers, pinned in ((1, True, False), (2, True, False), (None, True, False),
                                   (None, False, False), (1, False, False), (1, True, True),
-                                  (2, True, True)):
+                                  (2, True, True), (1, True, "plain")):
         got = gpu_sample(graph, reads, extension, unique, mode, headers, pinned)
         what = "mode %s headers %s pinned %s " % (mode, headers, pinned)
         if unique:
@@ -168,6 +169,26 @@ def test_page_locked_batch_with_32_bit_path_offsets():
         for a, b in zip(want[:2], got[:2]):
             assert bool((a[0] == b[0]).all()) and bool((a[1] == b[1]).all())
         assert bool((want[2] == got[2]).all())
+
+
+@pytest.mark.parametrize("n_reads", [1, 300, 70_000, 1_300_000])
+def test_delta_coded_wire_form_decodes_to_the_same_reads(n_reads):
+    """The three uploads of one page-locked batch -- six arrays, compact, compact with
+    delta-coded paths -- leave the same arrays in HBM (start node / offset, per-read
+    records, path)."""
+    import torch
+    from graph_peak_caller_b200.device import DeviceReads
+    g = make_graph(200_000, 0.05, seed=91)
+    r = make_reads(g, n_reads, 30, 120, seed=92)
+    delta, plain = r.pin_memory(), r.pin_memory(delta=False)
+    assert delta.wire_form() == "compact+delta" and plain.wire_form() == "compact"
+    assert delta.upload_bytes() < plain.upload_bytes() < r.nbytes()
+    a, b, c = DeviceReads(delta), DeviceReads(plain), DeviceReads(r)
+    torch.cuda.synchronize()
+    for x, y in ((a, b), (a, c)):
+        assert bool((x.start_node == y.start_node).all()) and bool((x.start_off == y.start_off).all())
+        assert bool((x.path == y.path).all()) and bool((x.hdr == y.hdr).all())
+    assert np.array_equal(a.path.cpu().numpy(), r.path)
 
 
 def _fan_graph(rng, n_layers, width):

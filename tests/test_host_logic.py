@@ -202,3 +202,20 @@ def test_compact_wire_form_of_a_read_batch():
     assert ReadBatch(other, r.start_off, r.end_node, r.end_off, r.path_ptr, r.path).compact() is None
     long_path = ReadBatch([1], [0], [1], [1], [0, 300], np.ones(300, dtype=np.int32))
     assert long_path.compact() is None
+    # delta-coded paths: first node + int8 steps decode back to the path array
+    offs2, plen2, first, step = r.compact_delta()
+    assert np.array_equal(offs2, offs) and np.array_equal(plen2, plen)
+    assert first.dtype == np.int32 and step.dtype == np.int8
+    assert step.size == r.path.size - len(r)
+    rebuilt, k = [], 0
+    for i in range(len(r)):
+        v = int(first[i])
+        rebuilt.append(v)
+        for _ in range(int(plen[i]) - 1):
+            v += int(step[k])
+            k += 1
+            rebuilt.append(v)
+    assert rebuilt == r.path.tolist()
+    # a step that does not fit int8: no delta form, the plain compact form still applies
+    jump = ReadBatch([1, 5], [0, 0], [400, 6], [1, 1], [0, 2, 4], np.array([1, 400, 5, 6], dtype=np.int32))
+    assert jump.compact() is not None and jump.compact_delta() is None
