@@ -141,6 +141,26 @@ __global__ void pv_partition_kernel(const uint32_t* __restrict__ spos, unsigned 
 // sat on that barrier -- profiles/pvalues_r01_before_raw.csv.)
 // Pairs that the L1 probe does not find go to a per-tile queue that the whole
 // block drains, one pair per thread, so evaluations run on full warps.
+//
+// (Measured and dropped: collecting a tile's DISTINCT pairs in a shared-memory table first --
+// one CAS per new pair, one memo probe per occupied slot, every position reading its p from
+// shared memory -- cut the L2 probes twentyfold and made the kernel SLOWER, 0.485 -> 0.638 ms
+// on the chr22-scale tracks: three more block barriers and same-address shared-memory traffic
+// cost more than the probes they replaced.)
+//
+// Three changes of round 2 (A/B on one box, chr22-scale tracks: 0.487 ms as it stood, 0.463
+// with the first, 0.419 with the first two, 0.397 with all three; without any memo probe the
+// kernel takes 0.29 ms):
+//  * a thread's share of both slices (8-9 elements) is fetched by loads issued back to back
+//    and stored to shared memory afterwards; written as two load / store loops with a dynamic
+//    trip count, every iteration waited for its own DRAM round trip;
+//  * a tile's entries go to shared memory at their rank in the tile and leave as whole
+//    sectors (a thread's eight entries written straight to global memory are eight
+//    instructions of 32 scattered partial sectors each);
+//  * the first memo slot of four pairs at a time is fetched whole (two 16-byte loads per
+//    entry, all eight in flight together) and checked afterwards; called one after the other
+//    the probes were eight dependent pairs of round trips per thread.  A pair whose first slot
+//    holds something else goes to the miss queue, where the chain is walked.
 __global__ void __launch_bounds__(PV_THREADS)
 pv_eval_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sval, unsigned ns,
                double sample_scale, const uint32_t* __restrict__ cpos,
@@ -151,10 +171,10 @@ pv_eval_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
     // slices of both tracks that this tile merges, plus one element before
     // (state in force at the tile's left edge) and one after (look-ahead);
     // after the merge a_val / b_val are reused as the miss queue
-    __shared__ uint32_t a_pos[PV_TILE + 2];
-    __shared__ int32_t a_val[PV_TILE + 2];
-    __shared__ uint32_t b_pos[PV_TILE + 2];
-    __shared__ double b_val[PV_TILE + 2];
+    __shared__ __align__(16) uint32_t a_pos[PV_TILE + 2];
+    __shared__ __align__(16) int32_t a_val[PV_TILE + 2];
+    __shared__ __align__(16) uint32_t b_pos[PV_TILE + 2];
+    __shared__ __align__(16) double b_val[PV_TILE + 2];
     __shared__ unsigned s_slot;
     __shared__ unsigned s_nq;
     __shared__ int s_scan[33];
@@ -166,18 +186,45 @@ pv_eval_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
     const unsigned i_lo = split[tile], i_hi = split[tile + 1];
     const unsigned j_lo = t0 - i_lo, j_hi = t1 - i_hi;
     const unsigned na = i_hi - i_lo, nb = j_hi - j_lo;
-    // slot k of a_* holds global sample entry i_lo - 1 + k  (k = 0 .. na + 1)
-    for (unsigned k = threadIdx.x; k < na + 2; k += PV_THREADS) {
-        long long gi = (long long)i_lo - 1 + k;
-        bool ok = gi >= 0 && gi < (long long)ns;
-        a_pos[k] = ok ? spos[gi] : 0xffffffffu;
-        a_val[k] = ok ? sval[gi] : 0;
-    }
-    for (unsigned k = threadIdx.x; k < nb + 2; k += PV_THREADS) {
-        long long gj = (long long)j_lo - 1 + k;
-        bool ok = gj >= 0 && gj < (long long)nc;
-        b_pos[k] = ok ? cpos[gj] : 0xffffffffu;
-        b_val[k] = ok ? __dmul_rn(cval[gj], control_scale) : 0.0;
+    // slot k of a_* holds global sample entry i_lo - 1 + k  (k = 0 .. na + 1), slot k of b_* control
+    // entry j_lo - 1 + k
+    {
+        // one index space over both slices: [0, na + 2) sample, [na + 2, na + nb + 4) control
+        constexpr int ROUNDS = (PV_TILE + 4 + PV_THREADS - 1) / PV_THREADS;      // 9
+        uint32_t r_pos[ROUNDS];
+        unsigned long long r_val[ROUNDS];
+#pragma unroll
+        for (int it = 0; it < ROUNDS; ++it) {
+            const unsigned k = threadIdx.x + it * PV_THREADS;
+            r_pos[it] = 0xffffffffu;
+            r_val[it] = 0ull;
+            if (k < na + 2) {
+                const long long gi = (long long)i_lo - 1 + k;
+                if (gi >= 0 && gi < (long long)ns) {
+                    r_pos[it] = spos[gi];
+                    r_val[it] = (unsigned long long)(unsigned)sval[gi];
+                }
+            } else if (k < na + nb + 4) {
+                const long long gj = (long long)j_lo - 1 + (k - (na + 2));
+                if (gj >= 0 && gj < (long long)nc) {
+                    r_pos[it] = cpos[gj];
+                    r_val[it] = (unsigned long long)__double_as_longlong(cval[gj]);
+                }
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < ROUNDS; ++it) {
+            const unsigned k = threadIdx.x + it * PV_THREADS;
+            if (k < na + 2) {
+                a_pos[k] = r_pos[it];
+                a_val[k] = (int32_t)(unsigned)r_val[it];
+            } else if (k < na + nb + 4) {
+                const unsigned kb = k - (na + 2);
+                b_pos[kb] = r_pos[it];
+                b_val[kb] = r_pos[it] == 0xffffffffu && r_val[it] == 0ull
+                                ? 0.0 : __dmul_rn(__longlong_as_double((long long)r_val[it]), control_scale);
+            }
+        }
     }
     __syncthreads();
     // local coordinates: sample entry x <-> a_*[x + 1], control entry y <-> b_*[y + 1]
@@ -223,17 +270,48 @@ pv_eval_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
             if (tile == gridDim.x - 1) *out_count = b + tile_out;
         }
     }
-    // fast path: L1 probe of the memo
     double e_p[PV_ITEMS];
+    // fast path: the first memo slot of every pair, four pairs per round trip
     unsigned miss = 0;
+    if (memo.e) {
 #pragma unroll
-    for (int t = 0; t < PV_ITEMS; ++t) {
-        e_p[t] = 0.0;
-        if (t < cnt && e_k[t] != 0) {
-            double count = (double)e_k[t] * sample_scale;
-            bool found = false;
-            if (memo.e) found = memo_find<false>(memo, memo_hash(count, e_lam[t]), count, e_lam[t], e_p[t]);
-            if (!found) miss |= 1u << t;
+        for (int b = 0; b < PV_ITEMS; b += 4) {
+            ulonglong2 v0[4], v1[4];
+            unsigned long long hs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = b + u;
+                e_p[t] = 0.0;
+                hs[u] = 0ull;
+                v0[u] = make_ulonglong2(0ull, 0ull);
+                v1[u] = v0[u];
+                if (t < cnt && e_k[t] != 0) {
+                    hs[u] = memo_hash((double)e_k[t] * sample_scale, e_lam[t]);
+                    const ulonglong2* e = reinterpret_cast<const ulonglong2*>(
+                        &memo.e[(unsigned)(hs[u] >> 20) & memo.mask]);
+                    v0[u] = e[0];                     // tag, lambda
+                    v1[u] = e[1];                     // p, check
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = b + u;
+                if (t < cnt && e_k[t] != 0) {
+                    const double count = (double)e_k[t] * sample_scale;
+                    const double l = __longlong_as_double((long long)v0[u].y);
+                    const double v = __longlong_as_double((long long)v1[u].x);
+                    if (v0[u].x == (hs[u] | 3ull) && l == e_lam[t] && v1[u].y == memo_check(count, e_lam[t], v))
+                        e_p[t] = v;
+                    else
+                        miss |= 1u << t;
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < PV_ITEMS; ++t) {
+            e_p[t] = 0.0;
+            if (t < cnt && e_k[t] != 0) miss |= 1u << t;       // (small inputs: no memo)
         }
     }
     unsigned q0 = 0;
@@ -263,10 +341,21 @@ pv_eval_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
         for (int t = 0; t < PV_ITEMS; ++t)
             if ((miss >> t) & 1u) e_p[t] = b_val[q++];
     }
-    unsigned long long w = s_obase + o;
+    {
+        // (the miss queue is drained: a_pos / b_val are free; readers of b_val passed the
+        //  barrier above only if there were misses, so one more barrier before reuse)
+        __syncthreads();
 #pragma unroll
-    for (int t = 0; t < PV_ITEMS; ++t)
-        if (t < cnt) { out_pos[w + t] = e_pos[t]; out_p[w + t] = e_p[t]; }
+        for (int t = 0; t < PV_ITEMS; ++t)
+            if (t < cnt) { a_pos[o + t] = e_pos[t]; b_val[o + t] = e_p[t]; }
+        __syncthreads();
+        const unsigned long long w0 = s_obase;
+        for (unsigned q = threadIdx.x; q < (unsigned)tile_out; q += PV_THREADS) {
+            out_pos[w0 + q] = a_pos[q];
+            out_p[w0 + q] = b_val[q];
+        }
+    }
+}
 }
 
 // Step 2: canonical runs -- entries whose p equals the previous position's p

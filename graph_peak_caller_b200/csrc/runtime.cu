@@ -135,6 +135,10 @@ void guard_check(const void* base, size_t bytes, cudaStream_t stream) {
 struct RbArgs { const unsigned char* src[4]; unsigned bytes[4]; int n; };
 constexpr unsigned RB_PAYLOAD = 160;
 
+// One thread, byte by byte.  (Measured and dropped: one thread per payload byte with a block
+// barrier before the sequence number -- all loads in flight together, a warp's stores leaving
+// as one write -- took LONGER, 10.6 instead of 8.7 us per read-back: the time is the
+// system-scope fence and the posted write reaching the host, not the copy loop.)
 __global__ void readback_kernel(RbArgs a, volatile unsigned char* slot, unsigned long long seq) {
     unsigned off = 0;
     for (int i = 0; i < a.n; ++i) {

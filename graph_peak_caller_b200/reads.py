@@ -17,6 +17,8 @@ path never does that: it uploads the arrays as they are.
 """
 import json
 
+import os
+
 import numpy as np
 
 
@@ -306,12 +308,14 @@ class ReadBatch:
             return None
         return offs, lens, first, step.astype(np.int8)
 
-    def pin_memory(self, delta=True):
+    def pin_memory(self, delta=None):
         """A batch over the same reads whose arrays -- and, when the reads allow it, their
         compact form -- sit in page-locked memory: uploads of such a batch are asynchronous
         copies of the compact form (ingest-side preparation, done once per read set);
         ``delta``: with delta-coded paths when the node ids allow it."""
         import torch
+        if delta is None:                # GPC_WIRE_DELTA=0: plain compact form (measurements)
+            delta = os.environ.get("GPC_WIRE_DELTA", "1") != "0"
         full = [torch.from_numpy(a).pin_memory() for a in (
             self.start_node, self.start_off, self.end_node, self.end_off,
             self.path_ptr.astype(np.int32) if self.path.size < 2 ** 31 else self.path_ptr, self.path)]
