@@ -356,7 +356,6 @@ pv_eval_kernel(const uint32_t* __restrict__ spos, const int32_t* __restrict__ sv
         }
     }
 }
-}
 
 // Step 2: canonical runs -- entries whose p equals the previous position's p
 // are dropped (SparseDiffs keeps only positions where the value changes).
