@@ -140,7 +140,11 @@ __global__ void pv_partition_kernel(const uint32_t* __restrict__ spos, unsigned 
 // look-back for the slowest tile of its wave, and 56 % of all stall samples
 // sat on that barrier -- profiles/pvalues_r01_before_raw.csv.)
 // Pairs that the L1 probe does not find go to a per-tile queue that the whole
-// block drains, one pair per thread, so evaluations run on full warps.
+// block drains, one pair per thread, so evaluations run on full warps.  (The two block
+// barriers around the queue hold 20 % of the kernel's stall samples,
+// profiles/pv_eval_r02_final_raw.csv; resolving the misses in their own threads instead --
+// no queue, no barriers -- was measured at 0.485 ms against 0.397: eight inlined copies of the
+// chain walk and the Poisson tail per thread cost far more than the barriers.)
 //
 // (Measured and dropped: collecting a tile's DISTINCT pairs in a shared-memory table first --
 // one CAS per new pair, one memo probe per occupied slot, every position reading its p from
