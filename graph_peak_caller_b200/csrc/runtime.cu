@@ -88,14 +88,19 @@ static void keep_pool_memory(int dev) {
     }
 }
 
+// Per device (a process normally drives one GPU, but one that switches devices gets each
+// device's own SM count, and each device's memory pool is configured on first use).
 int sm_count() {
-    static int n = 0;
+    constexpr int MAX_DEVICES = 64;
+    static std::atomic<int> known[MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 148;
+    int n = known[dev].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
             n = 148;
         keep_pool_memory(dev);
+        known[dev].store(n, std::memory_order_relaxed);
     }
     return n;
 }

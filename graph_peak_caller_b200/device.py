@@ -322,18 +322,19 @@ def device_reads(batch):
     return dr
 
 
-_copy_stream = None
+_copy_streams = {}          # one per device index
 
 
 def prefetch_reads(batch):
     """Upload a ReadBatch on a dedicated copy stream; device_reads() later makes
     the compute stream wait for it."""
-    global _copy_stream
     if getattr(batch, "_device", None) is not None:
         return
     torch = torch_cuda()
     if getattr(batch, "_pinned", None) is None:
         return                            # pageable memory: nothing to overlap
-    if _copy_stream is None:
-        _copy_stream = torch.cuda.Stream()
-    batch._device = DeviceReads(batch, copy_stream=_copy_stream)
+    index = torch.cuda.current_device()
+    stream = _copy_streams.get(index)
+    if stream is None:
+        stream = _copy_streams[index] = torch.cuda.Stream()
+    batch._device = DeviceReads(batch, copy_stream=stream)
