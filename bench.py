@@ -21,9 +21,9 @@ Prints ONE JSON line on rank 0.  Regions, in order (GPU arm):
   3. the same K steps again with an event pair around every kernel launch (the
      library's profiler) -> per-kernel times for `roofline`; kept out of (2)
      because the event records cost host time;
-  4. K end-to-end steps through CallPeaks (the reference's API) with page-locked HOST
-     arrays (H2D of both read sets and D2H of the peaks inside the wall-clock
-     region) -> `e2e`;
+  4. W warm-up + K timed end-to-end steps through CallPeaks (the reference's API) with
+     page-locked HOST arrays (H2D of both read sets and D2H of the peaks inside the
+     wall-clock region) -> `e2e`;
   5. rank 0, N == 1: `bench.py --impl reference --steps 1` in a child process ->
      `cpu_baseline`; and the host-side ingest rate -> `ingest`.
 `--impl reference` times the UNMODIFIED reference (oracle/_ref through oracle/refshim;
