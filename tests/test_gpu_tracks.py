@@ -153,3 +153,26 @@ def test_from_pileup_inputs():
     diffs = np.r_[np.ones(p.starts.size), -np.ones(p.ends.size), p.node_starts]
     ri, rv = otracks.diffs_to_runs(idx, diffs)
     assert np.array_equal(sv.indices, ri) and np.array_equal(sv.values, rv)
+
+
+def test_in_place_scaling_after_the_track_was_looked_at():
+    """a kernel-made track whose host copy exists (somebody read ``_indices``)
+    must carry ``*=`` / ``/=`` on BOTH forms -- the p-value stage reads the device runs with
+    their scale first (reference sparsediffs.py:200-206 scales the one array it has)."""
+    from scipy.stats import poisson
+    from graph_peak_caller_b200.device import to_device
+    from graph_peak_caller_b200.sparsediffs import SparseDiffs
+    from graph_peak_caller_b200.sparsepvalues import PValuesFinder
+    t = SparseDiffs.from_device_runs(to_device(np.array([0, 5, 9], dtype=np.int32)),
+                                     to_device(np.array([2, 6, 0], dtype=np.int32)))
+    assert t._indices.tolist() == [0, 5, 9]            # materialises the host copy
+    t *= 0.5
+    assert t.device_runs()[2] == 0.5 and t._diffs.tolist() == [1.0, 2.0, -3.0]
+    t /= 0.25
+    assert t.device_runs()[2] == 2.0 and t._diffs.tolist() == [4.0, 8.0, -12.0]
+    control = SparseDiffs(np.array([0, 7]), np.array([1.5, 1.0]))      # lambda 1.5, then 2.5
+    p = PValuesFinder(t, control).get_p_values_pileup()
+    want = [-poisson.logsf(4, 1.5) / np.log(10), -poisson.logsf(12, 1.5) / np.log(10),
+            -poisson.logsf(12, 2.5) / np.log(10), 0.0]
+    assert p.indices.tolist() == [0, 5, 7, 9]
+    assert np.allclose(p.values, want, rtol=1e-9, atol=0)
