@@ -883,7 +883,8 @@ extern "C" int gpc_qtable_build(const double* table_p, const uint64_t* table_cou
 // <= 1/4, key 0 = empty: the table holds no p = 0).  The binary search it replaces made ~16
 // dependent loads per run, the last six or so to a different line in every lane: 0.174 ms for
 // the 15.7 M runs of the chr22-scale track, bound by L1 wavefronts.  One probe is one
-// scattered 16-byte load.
+// scattered 16-byte load: 0.083 ms + 0.010 ms for building the table (A/B on one box,
+// profiles/ab_r02_pvalues.txt, call 30).
 struct QSlot { unsigned long long key; double q; };
 
 __global__ void qhash_build_kernel(const double* __restrict__ table_p, const double* __restrict__ table_q,
@@ -930,9 +931,8 @@ extern "C" int gpc_qvalues_apply(const double* p, uint64_t n_runs, const double*
     Scratch miss;
     GPC_CUDA(miss.alloc(8, stream));
     GPC_CUDA(cudaMemsetAsync(miss.p, 0, 8, stream));
-    // small jobs keep the binary search (no table to build); the hash table is opt-in
-    // (GPC_Q_HASH=1) until it has run against the digests on a B200
-    static const bool force_search = getenv("GPC_Q_HASH") == nullptr;
+    // small jobs keep the binary search (no table to build); GPC_Q_SEARCH=1 forces it
+    static const bool force_search = getenv("GPC_Q_SEARCH") != nullptr;
     // (and tables of more than 2^20 distinct p -- dense variation graphs -- whose hash table
     //  would leave the L2)
     if (n_runs < (1u << 16) || n_table == 0 || n_table > (1ull << 20) || force_search) {
