@@ -57,3 +57,29 @@ def test_exclusive_scan(n):
     ref = np.cumsum(x) - x
     assert np.array_equal(out.cpu().numpy(), ref)
     assert total == int(x.sum())
+
+
+@pytest.mark.parametrize("n_table,n_runs", [(1, 70_000), (37, 70_000), (35_000, 300_000),
+                                            (800_000, 2_000_000), (1_200_000, 100_000),
+                                            (500, 3_000)])
+def test_qvalues_apply_exact_key_lookup(n_table, n_runs):
+    """gpc_qvalues_apply: every run's p is looked up by exact key (sparsepvalues.py:116-125:
+    a dict from p to q; p == 0 -> 0).  Tracks of >= 2^16 runs with tables of <= 2^20 entries go
+    through the per-call hash table, everything else through the binary search: both routes
+    against numpy, on tables of distinct doubles that differ in their last bits."""
+    from graph_peak_caller_b200 import kernels
+    rng = np.random.default_rng(n_table + n_runs)
+    base = np.sort(rng.random(n_table) * 50.0 + 1e-9)[::-1]
+    table_p = np.unique(np.r_[base, np.nextafter(base[: n_table // 3], np.inf)])[::-1].copy()
+    table_q = np.minimum.accumulate(rng.random(table_p.size) * 10.0)[::-1][::-1].copy()
+    pick = rng.integers(0, table_p.size, size=n_runs)
+    p = table_p[pick]
+    zero = rng.random(n_runs) < 0.1
+    p[zero] = 0.0
+    got = kernels.qvalues_apply(_dev(p), _dev(table_p), _dev(table_q)).cpu().numpy()
+    want = np.where(zero, 0.0, table_q[pick])
+    assert np.array_equal(got, want)
+    # a p that is not in the table is an error, not a silent zero
+    p[0] = 123.456
+    with pytest.raises(Exception):
+        kernels.qvalues_apply(_dev(p), _dev(table_p), _dev(table_q))
